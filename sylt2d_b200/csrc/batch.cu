@@ -1,0 +1,947 @@
+// batch.cu — batches of independent small worlds (BASELINE.json configs 4 and 5): ONE CTA PER WORLD.
+//
+// The reference has no batched API: this is N separate `World`s each running World::step
+// (/root/reference/src/world.rs:107-152).  Here a CTA loads its world into shared memory once, runs `n_steps`
+// complete steps there, and writes the state back:
+//
+//   per step, all in shared memory
+//     bodies     (cos,sin), AABB, force integration                         world.rs:113-120
+//     pairs      warp-per-row all-pairs AABB filter -> key-ordered candidate slots (static-static skipped, :79-81)
+//     narrow     one thread per candidate: box_box (narrow.cuh)             collide.rs:140-297
+//     match      binary search of last step's key-sorted slots: Arbiter::update with quirks Q-2 / Q-17
+//     colour     persisting arbiters keep their colour, new ones get the lowest free colour (sequential, warp 0)
+//     solve      Arbiter::pre_step, Joint::pre_step, iterations x apply_impulse, colour by colour with
+//                __syncthreads() between colours                            arbiter.rs:182-298, joint.rs:57-130
+//     integrate  positions, all bodies                                      world.rs:143-150
+//
+// Worlds never exchange data, so a batch shards across GPUs with no collective; the only cross-GPU quantity is the
+// SyltBatchStats record (sylt_batch_stats), reduced by the caller.
+#include <algorithm>
+#include <numeric>
+#include "common.h"
+#include "narrow.cuh"
+#include "solver.cuh"
+
+using namespace sylt;
+
+namespace {
+
+constexpr int BNC = 32;        // colours per world
+constexpr int MAX_JC = 16;     // joint colours per world
+constexpr unsigned char NO_COLOR = 0xff;
+
+struct SlotExport {  // full record of one arbiter slot, written for worlds in the export range only
+    unsigned key;    // body1 << 16 | body2 (indices local to the world)
+    float friction;
+    int count, color;
+    float nx, ny;
+    float geo[2][3];  // px, py, separation   (written by the narrow phase of the launch's last step)
+    float sol[2][9];  // r1x,r1y,r2x,r2y,mass_n,mass_t,bias,pn,pt   (written after the solve)
+    unsigned feat[2];
+};
+
+struct BatchArgs {
+    int n_worlds, n_steps, iterations, accumulate, warm, poscorr;
+    float dt, inv_dt, gx, gy;
+    int Bmax, Jmax, cap;
+    int export_first, export_count;
+    const int *body_off, *joint_off;
+    float4 *pose, *vel;              // (x,y,rot,_), (vx,vy,w,_)
+    const float4* mp;                // (inv_mass, inv_moi, friction, _)
+    const float2* wh;                // Body.width
+    const int2* jbodies;             // world-local body indices
+    const float4* jla;
+    const float2* jparam;
+    float2* jp;
+    float4 *jr, *jm;
+    float2* jbias;
+    const int* jorder;               // per joint slot (CSR like joints): colour-major joint index, world-local
+    const int* jcolor_start;         // per world: MAX_JC + 1 entries
+    const int* n_jcolors;            // per world
+    // persistent per-world slot cache (cap entries per world)
+    int* c_count;
+    unsigned* c_key;
+    float *c_fric, *c_pn, *c_pt;
+    unsigned char* c_color;          // NO_COLOR = inactive slot (candidate without contacts)
+    // per-world summary
+    int *w_err, *w_ncon, *w_narb, *w_ncolors, *w_errjoint;
+    float* w_maxpen;
+    float4* w_badk;
+    SlotExport* exp_slots;           // export_count * cap
+    int* exp_count;                  // export_count
+};
+
+struct Smem {
+    float2* pos; float* rot; float2* cs; float4* vel; float2* inv; float2* wh; float* fric; float4* aabb; unsigned char* stat;
+    unsigned* used;
+    int* rowcnt;                       // Bmax + 1
+    // slots
+    unsigned* key; float* sfric; float2* nrm; unsigned char* cnt; unsigned char* color; unsigned* feat; float* con;  // con: cap*2*9
+    unsigned short* order;
+    // old cache
+    unsigned* okey; float* ofric; float* opn; float* opt; unsigned char* ocolor;
+    // joints
+    int2* jb; float4* jla; float2* jparam; float2* jp; float4* jr; float4* jm; float2* jbias; unsigned short* jorder;
+    int* misc;                         // scan scratch (40) + colour bins
+};
+
+__host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
+
+// identical carve-up on host (size only) and device
+__host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int B, int J, int cap) {
+    size_t o = 0;
+#define TAKE(field, type, n)                          \
+    do {                                              \
+        if (s) s->field = (type*)(base + o);          \
+        o = align16(o + sizeof(type) * (size_t)(n)); \
+    } while (0)
+    TAKE(pos, float2, B); TAKE(rot, float, B); TAKE(cs, float2, B); TAKE(vel, float4, B); TAKE(inv, float2, B); TAKE(wh, float2, B);
+    TAKE(fric, float, B); TAKE(aabb, float4, B); TAKE(stat, unsigned char, B); TAKE(used, unsigned, B); TAKE(rowcnt, int, B + 1);
+    TAKE(key, unsigned, cap); TAKE(sfric, float, cap); TAKE(nrm, float2, cap); TAKE(cnt, unsigned char, cap); TAKE(color, unsigned char, cap);
+    TAKE(feat, unsigned, 2 * cap); TAKE(con, float, 18 * cap); TAKE(order, unsigned short, cap);
+    TAKE(okey, unsigned, cap); TAKE(ofric, float, cap); TAKE(opn, float, cap); TAKE(opt, float, cap); TAKE(ocolor, unsigned char, cap);
+    TAKE(jb, int2, J + 1); TAKE(jla, float4, J + 1); TAKE(jparam, float2, J + 1); TAKE(jp, float2, J + 1); TAKE(jr, float4, J + 1);
+    TAKE(jm, float4, J + 1); TAKE(jbias, float2, J + 1); TAKE(jorder, unsigned short, J + 1);
+    TAKE(misc, int, 40 + 3 * BNC + 8);
+#undef TAKE
+    return o;
+}
+
+__device__ __forceinline__ int warp_incl_scan_i(int v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += u;
+    }
+    return v;
+}
+// in-place exclusive scan of a[0..n) in shared memory by the whole block; returns the total
+__device__ int block_scan_inplace(int* a, int n, int* sh /* 34 ints */) {
+    const int T = blockDim.x, tid = threadIdx.x;
+    const int chunk = (n + T - 1) / T;
+    const int s0 = min(tid * chunk, n), s1 = min(s0 + chunk, n);
+    int s = 0;
+    for (int k = s0; k < s1; k++) s += a[k];
+    int inc = warp_incl_scan_i(s);
+    const int w = tid >> 5, l = tid & 31;
+    if (l == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        int v = l < (T >> 5) ? sh[l] : 0;
+        int vi = warp_incl_scan_i(v);
+        sh[l] = vi - v;
+        if (l == 31) sh[32] = vi;
+    }
+    __syncthreads();
+    int run = sh[w] + inc - s;
+    for (int k = s0; k < s1; k++) { int t = a[k]; a[k] = run; run += t; }
+    int total = sh[32];
+    __syncthreads();
+    return total;
+}
+
+__device__ __forceinline__ bool overlap4(float4 a, float4 b) { return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w); }
+
+__device__ __forceinline__ Vel ld_vel(const float4* v, int b) { float4 t = v[b]; Vel o; o.v = mk(t.x, t.y); o.w = t.z; return o; }
+__device__ __forceinline__ void st_vel(float4* v, int b, const Vel& x) { v[b] = make_float4(x.v.x, x.v.y, x.w, 0.0f); }
+
+__global__ void __launch_bounds__(256) k_batch_step(BatchArgs a) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int wld = blockIdx.x;
+    if (wld >= a.n_worlds) return;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int b0 = a.body_off[wld], B = a.body_off[wld + 1] - b0;
+    const int j0 = a.joint_off[wld], J = a.joint_off[wld + 1] - j0;
+    const int cap = a.cap;
+    Smem s;
+    carve(&s, smem_raw, a.Bmax, a.Jmax, cap);
+    int* scan_sh = s.misc;           // 34
+    int* s_P = s.misc + 36;          // current candidate count
+    int* s_Pold = s.misc + 37;
+    int* s_err = s.misc + 38;
+    int* ccount = s.misc + 40;       // BNC
+    int* cstart = ccount + BNC;      // BNC + 1
+    int* cfill = cstart + BNC + 1;   // BNC
+
+    // ---- load the world
+    for (int i = tid; i < B; i += T) {
+        float4 p = a.pose[b0 + i], v = a.vel[b0 + i], m = a.mp[b0 + i];
+        s.pos[i] = make_float2(p.x, p.y); s.rot[i] = p.z; s.vel[i] = v; s.inv[i] = make_float2(m.x, m.y); s.fric[i] = m.z;
+        s.wh[i] = a.wh[b0 + i];
+        s.stat[i] = (m.x == 0.0f) ? 1 : 0;
+    }
+    for (int j = tid; j < J; j += T) {
+        s.jb[j] = a.jbodies[j0 + j]; s.jla[j] = a.jla[j0 + j]; s.jparam[j] = a.jparam[j0 + j]; s.jp[j] = a.jp[j0 + j];
+        s.jorder[j] = (unsigned short)a.jorder[j0 + j];
+        s.jr[j] = make_float4(0, 0, 0, 0); s.jm[j] = make_float4(0, 0, 0, 0); s.jbias[j] = make_float2(0, 0);
+    }
+    const int Pold0 = min(a.c_count[wld], cap);
+    for (int k = tid; k < Pold0; k += T) {
+        size_t g = (size_t)wld * cap + k;
+        s.okey[k] = a.c_key[g]; s.ofric[k] = a.c_fric[g]; s.opn[k] = a.c_pn[g]; s.opt[k] = a.c_pt[g]; s.ocolor[k] = a.c_color[g];
+    }
+    if (tid == 0) { *s_Pold = Pold0; *s_err = a.w_err[wld]; *s_P = 0; }
+    const int njc = a.n_jcolors[wld];
+    const int* jcs = a.jcolor_start + (size_t)wld * (MAX_JC + 1);
+    __syncthreads();
+    const bool acc = a.accumulate != 0, warm = a.warm != 0, poscorr = a.poscorr != 0;
+    const float kbias = poscorr ? 0.2f : 0.0f;
+    int ncolors = 0, P = 0;
+    float maxpen = 0.0f;
+    const bool exporting = wld >= a.export_first && wld < a.export_first + a.export_count;
+
+    for (int step = 0; step < a.n_steps; step++) {
+        if (*s_err) break;  // a world that raised an error stays frozen (block-uniform: read after a barrier)
+        maxpen = 0.0f;
+        // ---- 1. bodies: rotation cache, AABB, force integration (world.rs:113-120; no external forces in a batch)
+        for (int i = tid; i < B; i += T) {
+            float r = s.rot[i];
+            float c = sylt_cosf(r), sn = sylt_sinf(r);
+            s.cs[i] = make_float2(c, sn);
+            float2 p = s.pos[i], w = s.wh[i];
+            float hx = w.x * 0.5f, hy = w.y * 0.5f;
+            float ex = fabsf(c) * hx + fabsf(sn) * hy, ey = fabsf(sn) * hx + fabsf(c) * hy;
+            float mg = 1.0e-6f * (fabsf(p.x) + fabsf(p.y)) + 2.0e-5f * (ex + ey) + 1.0e-6f;
+            s.aabb[i] = make_float4(p.x - ex - mg, p.y - ey - mg, p.x + ex + mg, p.y + ey + mg);
+            float2 iv = s.inv[i];
+            if (iv.x != 0.0f) {
+                float4 v = s.vel[i];
+                V2 nv = mk(v.x, v.y) + (mk(a.gx, a.gy) + mk(0.0f, 0.0f) * iv.x) * a.dt;
+                v.x = nv.x; v.y = nv.y;
+                v.z += iv.y * 0.0f * a.dt;
+                s.vel[i] = v;
+            }
+            s.used[i] = 0u;
+        }
+        for (int c = tid; c < 3 * BNC + 1; c += T) ccount[c] = 0;
+        __syncthreads();
+        // ---- 2. candidate rows (warp per row, lanes over j): count, scan, emit in (i, j) order
+        for (int i = warp; i < B; i += nwarps) {
+            float4 my = s.aabb[i];
+            const bool st = s.stat[i] != 0;
+            int n = 0;
+            for (int jb = i + 1; jb < B; jb += 32) {
+                int j = jb + lane;
+                bool hit = j < B && !(st && s.stat[j]) && overlap4(my, s.aabb[j]);
+                n += __popc(__ballot_sync(0xffffffffu, hit));
+            }
+            if (lane == 0) s.rowcnt[i] = n;
+        }
+        __syncthreads();
+        P = block_scan_inplace(s.rowcnt, B, scan_sh);
+        if (P > cap) {  // block-uniform
+            if (tid == 0) *s_err = SYLT_ERR_CAPACITY;
+            __syncthreads();
+            break;
+        }
+        for (int i = warp; i < B; i += nwarps) {
+            float4 my = s.aabb[i];
+            const bool st = s.stat[i] != 0;
+            int base = s.rowcnt[i];
+            for (int jb = i + 1; jb < B; jb += 32) {
+                int j = jb + lane;
+                bool hit = j < B && !(st && s.stat[j]) && overlap4(my, s.aabb[j]);
+                unsigned m = __ballot_sync(0xffffffffu, hit);
+                if (hit) s.key[base + __popc(m & ((1u << lane) - 1))] = ((unsigned)i << 16) | (unsigned)j;
+                base += __popc(m);
+            }
+        }
+        __syncthreads();
+        // ---- 3. narrow phase + match with last step's slots, one thread per candidate slot
+        const int Pold = *s_Pold;
+        for (int p = tid; p < P; p += T) {
+            unsigned key = s.key[p];
+            int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
+            ContactOut out[2];
+            float2 p1 = s.pos[b1], p2 = s.pos[b2], c1 = s.cs[b1], c2 = s.cs[b2], w1 = s.wh[b1], w2 = s.wh[b2];
+            int n = box_box(mk(p1.x, p1.y), c1.x, c1.y, mk(w1.x, w1.y), mk(p2.x, p2.y), c2.x, c2.y, mk(w2.x, w2.y), out);
+            s.cnt[p] = (unsigned char)n;
+            unsigned char color = NO_COLOR;
+            if (n > 0) {
+                int lo = 0, hi = Pold;  // first old slot with key >= this key
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (s.okey[mid] < key) lo = mid + 1; else hi = mid; }
+                float fr, pn = 0.0f, pt = 0.0f;
+                if (lo < Pold && s.okey[lo] == key && s.ocolor[lo] != NO_COLOR) {  // Arbiter::update (arbiter.rs:137-181)
+                    fr = s.ofric[lo];             // quirk Q-17
+                    color = s.ocolor[lo];
+                    if (warm) { pn = s.opn[lo]; pt = s.opt[lo]; }  // quirk Q-2: all contacts inherit old contact 0
+                } else {
+                    fr = sqrtf(s.fric[b1] * s.fric[b2]);  // arbiter.rs:128
+                }
+                s.sfric[p] = fr;
+                s.nrm[p] = make_float2(out[0].nx, out[0].ny);
+                for (int q = 0; q < n; q++) {
+                    float* cc = s.con + (size_t)(2 * p + q) * 9;
+                    cc[0] = out[q].px; cc[1] = out[q].py; cc[6] = out[q].sep; cc[7] = pn; cc[8] = pt;
+                    s.feat[2 * p + q] = out[q].feat;
+                }
+                if (color != NO_COLOR) {
+                    if (!s.stat[b1]) atomicOr(&s.used[b1], 1u << color);
+                    if (!s.stat[b2]) atomicOr(&s.used[b2], 1u << color);
+                    atomicAdd(&ccount[color], 1);
+                }
+            }
+            s.color[p] = color;
+            if (exporting && step == a.n_steps - 1) {
+                SlotExport* e = &a.exp_slots[(size_t)(wld - a.export_first) * cap + p];
+                e->key = key; e->count = n; e->nx = n > 0 ? out[0].nx : 0.0f; e->ny = n > 0 ? out[0].ny : 0.0f;
+                for (int q = 0; q < 2; q++) {
+                    e->geo[q][0] = q < n ? out[q].px : 0.0f; e->geo[q][1] = q < n ? out[q].py : 0.0f; e->geo[q][2] = q < n ? out[q].sep : 0.0f;
+                    e->feat[q] = q < n ? out[q].feat : 0u;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- 4. colour the new arbiters: lowest free colour, in key order (warp 0 finds them, lane 0 assigns)
+        if (warp == 0) {
+            for (int pb = 0; pb < P; pb += 32) {
+                int p = pb + lane;
+                bool need = p < P && s.cnt[p] > 0 && s.color[p] == NO_COLOR;
+                unsigned m = __ballot_sync(0xffffffffu, need);
+                if (lane == 0) {
+                    while (m) {
+                        int q = pb + __ffs(m) - 1;
+                        m &= m - 1;
+                        unsigned key = s.key[q];
+                        int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
+                        unsigned um = (s.stat[b1] ? 0u : s.used[b1]) | (s.stat[b2] ? 0u : s.used[b2]);
+                        unsigned fr = ~um;
+                        if (!fr) { *s_err = SYLT_ERR_CAPACITY; continue; }
+                        int c = __ffs(fr) - 1;
+                        s.color[q] = (unsigned char)c;
+                        if (!s.stat[b1]) s.used[b1] |= 1u << c;
+                        if (!s.stat[b2]) s.used[b2] |= 1u << c;
+                        ccount[c]++;
+                    }
+                }
+                __syncwarp();
+            }
+            if (lane == 0) {
+                int run = 0, nc = 0;
+                for (int c = 0; c < BNC; c++) { cstart[c] = run; if (ccount[c] > 0) nc = c + 1; run += ccount[c]; }
+                cstart[BNC] = run;
+                s.misc[35] = nc;
+            }
+        }
+        __syncthreads();
+        if (*s_err) break;
+        ncolors = s.misc[35];
+        for (int p = tid; p < P; p += T)
+            if (s.cnt[p] > 0) s.order[cstart[s.color[p]] + atomicAdd(&cfill[s.color[p]], 1)] = (unsigned short)p;
+        __syncthreads();
+        // ---- 5. Arbiter::pre_step colour by colour
+        for (int c = 0; c < ncolors; c++) {
+            for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
+                int p = s.order[k];
+                unsigned key = s.key[p];
+                int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
+                float2 i1 = s.inv[b1], i2 = s.inv[b2], p1 = s.pos[b1], p2 = s.pos[b2], nn = s.nrm[p];
+                Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
+                int n = s.cnt[p];
+                for (int q = 0; q < n; q++) {
+                    float* cc = s.con + (size_t)(2 * p + q) * 9;
+                    ContactConst k0;
+                    contact_prestep(mk(cc[0], cc[1]), mk(nn.x, nn.y), cc[6], mk(p1.x, p1.y), mk(p2.x, p2.y), i1.x, i1.y, i2.x, i2.y,
+                                    a.inv_dt, kbias, acc, cc[7], cc[8], v1, v2, k0);
+                    maxpen = fmaxf(maxpen, -cc[6]);
+                    cc[0] = k0.r1.x; cc[1] = k0.r1.y; cc[2] = k0.r2.x; cc[3] = k0.r2.y; cc[4] = k0.mass_n; cc[5] = k0.mass_t; cc[6] = k0.bias;
+                }
+                if (acc) {
+                    if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b1, v1);
+                    if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b2, v2);
+                }
+            }
+            if (acc) __syncthreads();
+        }
+        __syncthreads();
+        // ---- 6. Joint::pre_step by joint colour
+        for (int c = 0; c < njc; c++) {
+            for (int k = jcs[c] + tid; k < jcs[c + 1]; k += T) {
+                int j = s.jorder[k];
+                int2 b = s.jb[j];
+                float2 i1 = s.inv[b.x], i2 = s.inv[b.y], p1 = s.pos[b.x], p2 = s.pos[b.y], c1 = s.cs[b.x], c2 = s.cs[b.y];
+                Vel v1 = ld_vel(s.vel, b.x), v2 = ld_vel(s.vel, b.y);
+                float4 la = s.jla[j];
+                float2 pr = s.jparam[j], pa = s.jp[j];
+                V2 pacc = mk(pa.x, pa.y);
+                JointConst jc;
+                M2 bad;
+                bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), c1.x, c1.y, mk(p2.x, p2.y), c2.x, c2.y,
+                                        i1.x, i1.y, i2.x, i2.y, a.inv_dt, poscorr, warm, pacc, v1, v2, jc, &bad);
+                s.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
+                if (!ok) {  // quirk Q-15
+                    if (atomicCAS(s_err, 0, SYLT_ERR_NO_INVERSE) == 0) {
+                        a.w_errjoint[wld] = j;
+                        a.w_badk[wld] = make_float4(bad.c1.x, bad.c2.x, bad.c1.y, bad.c2.y);
+                    }
+                    continue;
+                }
+                s.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
+                s.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
+                s.jp[j] = make_float2(pacc.x, pacc.y);
+                if (warm) {
+                    if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b.x, v1);
+                    if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b.y, v2);
+                }
+            }
+            __syncthreads();
+        }
+        if (*s_err) break;
+        // ---- 7. iterations (world.rs:132-140)
+        for (int it = 0; it < a.iterations; it++) {
+            for (int c = 0; c < ncolors; c++) {
+                for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
+                    int p = s.order[k];
+                    unsigned key = s.key[p];
+                    int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
+                    float2 i1 = s.inv[b1], i2 = s.inv[b2], nn = s.nrm[p];
+                    float fr = s.sfric[p];
+                    Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
+                    int n = s.cnt[p];
+                    for (int q = 0; q < n; q++) {
+                        float* cc = s.con + (size_t)(2 * p + q) * 9;
+                        ContactConst k0;
+                        k0.n = mk(nn.x, nn.y); k0.r1 = mk(cc[0], cc[1]); k0.r2 = mk(cc[2], cc[3]);
+                        k0.mass_n = cc[4]; k0.mass_t = cc[5]; k0.bias = cc[6];
+                        float pn = cc[7], pt = cc[8];
+                        contact_apply(k0, fr, i1.x, i1.y, i2.x, i2.y, acc, pn, pt, v1, v2);
+                        if (acc) { cc[7] = pn; cc[8] = pt; }
+                    }
+                    if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b1, v1);
+                    if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b2, v2);
+                }
+                __syncthreads();
+            }
+            for (int c = 0; c < njc; c++) {
+                for (int k = jcs[c] + tid; k < jcs[c + 1]; k += T) {
+                    int j = s.jorder[k];
+                    int2 b = s.jb[j];
+                    float2 i1 = s.inv[b.x], i2 = s.inv[b.y];
+                    Vel v1 = ld_vel(s.vel, b.x), v2 = ld_vel(s.vel, b.y);
+                    float4 r = s.jr[j], mm = s.jm[j];
+                    float2 bs = s.jbias[j], pa = s.jp[j];
+                    JointConst jc;
+                    jc.r1 = mk(r.x, r.y); jc.r2 = mk(r.z, r.w); jc.bias = mk(bs.x, bs.y);
+                    jc.m = mk(mk(mm.x, mm.z), mk(mm.y, mm.w));
+                    jc.softness = s.jparam[j].x;
+                    V2 pacc = mk(pa.x, pa.y);
+                    joint_apply(jc, i1.x, i1.y, i2.x, i2.y, pacc, v1, v2);
+                    s.jp[j] = make_float2(pacc.x, pacc.y);
+                    if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b.x, v1);
+                    if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b.y, v2);
+                }
+                __syncthreads();
+            }
+        }
+        // ---- 8. integrate positions (world.rs:143-150, all bodies)
+        for (int i = tid; i < B; i += T) {
+            float4 v = s.vel[i];
+            float2 p = s.pos[i];
+            V2 np = mk(p.x, p.y) + mk(v.x, v.y) * a.dt;
+            s.pos[i] = make_float2(np.x, np.y);
+            s.rot[i] += v.z * a.dt;
+        }
+        // ---- 9. this step's slots become the cache of the next one
+        for (int p = tid; p < P; p += T) {
+            s.okey[p] = s.key[p];
+            unsigned char col = s.cnt[p] > 0 ? s.color[p] : NO_COLOR;
+            s.ocolor[p] = col;
+            if (col != NO_COLOR) { s.ofric[p] = s.sfric[p]; s.opn[p] = s.con[(size_t)(2 * p) * 9 + 7]; s.opt[p] = s.con[(size_t)(2 * p) * 9 + 8]; }
+        }
+        if (tid == 0) *s_Pold = P;
+        __syncthreads();
+    }
+
+    // ---- store the world
+    __syncthreads();
+    const int err = *s_err;
+    for (int i = tid; i < B; i += T) {
+        float2 p = s.pos[i];
+        a.pose[b0 + i] = make_float4(p.x, p.y, s.rot[i], 0.0f);
+        a.vel[b0 + i] = s.vel[i];
+    }
+    for (int j = tid; j < J; j += T) {
+        a.jp[j0 + j] = s.jp[j]; a.jr[j0 + j] = s.jr[j]; a.jm[j0 + j] = s.jm[j]; a.jbias[j0 + j] = s.jbias[j];
+    }
+    const int Pn = *s_Pold;
+    int ncon = 0, narb = 0;
+    for (int k = tid; k < Pn; k += T) {
+        size_t g = (size_t)wld * cap + k;
+        a.c_key[g] = s.okey[k]; a.c_fric[g] = s.ofric[k]; a.c_pn[g] = s.opn[k]; a.c_pt[g] = s.opt[k]; a.c_color[g] = s.ocolor[k];
+        if (!err && k < P && s.cnt[k] > 0) { ncon += s.cnt[k]; narb++; }
+    }
+    // block reductions of (ncon, narb, maxpen) through shared memory atomics
+    if (tid == 0) { s.misc[0] = 0; s.misc[1] = 0; s.misc[2] = 0; }
+    __syncthreads();
+    atomicAdd(&s.misc[0], ncon);
+    atomicAdd(&s.misc[1], narb);
+    atomicMax(&s.misc[2], __float_as_int(fmaxf(maxpen, 0.0f)));
+    __syncthreads();
+    if (tid == 0) {
+        a.c_count[wld] = Pn;
+        a.w_err[wld] = err;
+        a.w_ncon[wld] = s.misc[0];
+        a.w_narb[wld] = s.misc[1];
+        a.w_maxpen[wld] = __int_as_float(s.misc[2]);
+        a.w_ncolors[wld] = ncolors;
+    }
+    // ---- optional full export of the last step's arbiters (parity tests / renderer read-back)
+    if (exporting) {
+        const int xw = wld - a.export_first;
+        const bool valid = !err && a.n_steps > 0;
+        for (int p = tid; p < (valid ? P : 0); p += T) {
+            SlotExport* e = &a.exp_slots[(size_t)xw * cap + p];
+            e->friction = s.sfric[p]; e->color = s.color[p];
+            for (int q = 0; q < 2; q++)
+                for (int k = 0; k < 9; k++) e->sol[q][k] = s.con[(size_t)(2 * p + q) * 9 + k];
+        }
+        if (tid == 0) a.exp_count[xw] = valid ? P : 0;
+    }
+}
+
+struct StatsOut {
+    unsigned long long contacts, errors;
+    double ke;
+    float maxpen;
+};
+
+__global__ void k_batch_stats(int n_worlds, const int* body_off, const float4* vel, const float4* mp, const float* mass_moi /*2 per body*/,
+                              const int* w_err, const int* w_ncon, const float* w_maxpen, StatsOut* out) {
+    __shared__ double sh_ke[256];
+    __shared__ unsigned long long sh_c[256], sh_e[256];
+    __shared__ float sh_p[256];
+    double ke = 0.0;
+    unsigned long long c = 0, e = 0;
+    float mp_ = 0.0f;
+    for (int w = blockIdx.x * blockDim.x + threadIdx.x; w < n_worlds; w += gridDim.x * blockDim.x) {
+        for (int i = body_off[w]; i < body_off[w + 1]; i++) {
+            float4 m = mp[i];
+            if (m.x != 0.0f) {
+                float4 v = vel[i];
+                ke += 0.5 * (double)mass_moi[2 * i] * ((double)v.x * v.x + (double)v.y * v.y) + 0.5 * (double)mass_moi[2 * i + 1] * (double)v.z * v.z;
+            }
+        }
+        c += (unsigned long long)w_ncon[w];
+        e += w_err[w] ? 1ull : 0ull;
+        mp_ = fmaxf(mp_, w_maxpen[w]);
+    }
+    sh_ke[threadIdx.x] = ke; sh_c[threadIdx.x] = c; sh_e[threadIdx.x] = e; sh_p[threadIdx.x] = mp_;
+    __syncthreads();
+    for (int o = blockDim.x / 2; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sh_ke[threadIdx.x] += sh_ke[threadIdx.x + o]; sh_c[threadIdx.x] += sh_c[threadIdx.x + o]; sh_e[threadIdx.x] += sh_e[threadIdx.x + o];
+            sh_p[threadIdx.x] = fmaxf(sh_p[threadIdx.x], sh_p[threadIdx.x + o]);
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        atomicAdd(&out->contacts, sh_c[0]);
+        atomicAdd(&out->errors, sh_e[0]);
+        atomicAdd(&out->ke, sh_ke[0]);
+        atomicMax((int*)&out->maxpen, __float_as_int(sh_p[0]));
+    }
+}
+
+}  // namespace
+
+// ====================================================================== host side
+struct SyltBatch {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int n_worlds = 0, Bmax = 0, Jmax = 0, cap = 0, threads = 256;
+    int64_t n_bodies = 0, n_joints = 0;
+    float gx = 0, gy = 0;
+    uint32_t iterations = 10;
+    int accumulate = 1, warm = 0, poscorr = 1;  // World::new defaults (world.rs:38-42)
+    size_t smem = 0;
+    int64_t launches = 0;
+    uint64_t body_steps = 0;
+    int export_first = 0, export_count = 0;
+    int last_steps = 0;
+    bool inflight = false;
+    std::vector<int> h_body_off, h_joint_off, h_jorder;
+    std::vector<uint64_t> h_ids;
+    struct HJ { int b1, b2; float la1x, la1y, la2x, la2y, softness, bias_factor; };
+    std::vector<HJ> h_joints;
+    DBuf<int> body_off, joint_off, jorder, jcolor_start, n_jcolors, c_count, w_err, w_ncon, w_narb, w_ncolors, w_errjoint, exp_count;
+    DBuf<float4> pose, vel, mp, jla, jr, jm, w_badk;
+    DBuf<float2> wh, jparam, jp, jbias;
+    DBuf<float> mass_moi, c_fric, c_pn, c_pt, w_maxpen;
+    DBuf<int2> jbodies;
+    DBuf<unsigned> c_key;
+    DBuf<unsigned char> c_color;
+    DBuf<SlotExport> exp_slots;
+    DBuf<StatsOut> stats;
+};
+
+namespace {
+
+void batch_free(SyltBatch* b) {
+    b->body_off.release(); b->joint_off.release(); b->jorder.release(); b->jcolor_start.release(); b->n_jcolors.release();
+    b->c_count.release(); b->w_err.release(); b->w_ncon.release(); b->w_narb.release(); b->w_ncolors.release(); b->w_errjoint.release();
+    b->exp_count.release(); b->pose.release(); b->vel.release(); b->mp.release(); b->jla.release(); b->jr.release(); b->jm.release();
+    b->w_badk.release(); b->wh.release(); b->jparam.release(); b->jp.release(); b->jbias.release(); b->mass_moi.release();
+    b->c_fric.release(); b->c_pn.release(); b->c_pt.release(); b->w_maxpen.release(); b->jbodies.release(); b->c_key.release();
+    b->c_color.release(); b->exp_slots.release(); b->stats.release();
+}
+
+template <typename T>
+int upload(DBuf<T>& d, const std::vector<T>& h, size_t min_n = 1) {
+    SYLT_CUDA(d.ensure(std::max(h.size(), min_n)));
+    if (!h.empty()) SYLT_CUDA(cudaMemcpy(d.p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return SYLT_OK;
+}
+template <typename T>
+int zeroed(DBuf<T>& d, size_t n) {
+    SYLT_CUDA(d.ensure(std::max<size_t>(n, 1)));
+    SYLT_CUDA(cudaMemset(d.p, 0, std::max<size_t>(n, 1) * sizeof(T)));
+    return SYLT_OK;
+}
+
+int batch_enqueue(SyltBatch* b, float dt, int n) {
+    BatchArgs a;
+    memset(&a, 0, sizeof a);
+    a.n_worlds = b->n_worlds; a.n_steps = n; a.iterations = (int)b->iterations;
+    a.accumulate = b->accumulate; a.warm = b->warm; a.poscorr = b->poscorr;
+    a.dt = dt; a.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;  // world.rs:108
+    a.gx = b->gx; a.gy = b->gy; a.Bmax = b->Bmax; a.Jmax = b->Jmax; a.cap = b->cap;
+    a.export_first = b->export_first; a.export_count = b->export_count;
+    a.body_off = b->body_off.p; a.joint_off = b->joint_off.p; a.pose = b->pose.p; a.vel = b->vel.p; a.mp = b->mp.p; a.wh = b->wh.p;
+    a.jbodies = b->jbodies.p; a.jla = b->jla.p; a.jparam = b->jparam.p; a.jp = b->jp.p; a.jr = b->jr.p; a.jm = b->jm.p; a.jbias = b->jbias.p;
+    a.jorder = b->jorder.p; a.jcolor_start = b->jcolor_start.p; a.n_jcolors = b->n_jcolors.p;
+    a.c_count = b->c_count.p; a.c_key = b->c_key.p; a.c_fric = b->c_fric.p; a.c_pn = b->c_pn.p; a.c_pt = b->c_pt.p; a.c_color = b->c_color.p;
+    a.w_err = b->w_err.p; a.w_ncon = b->w_ncon.p; a.w_narb = b->w_narb.p; a.w_ncolors = b->w_ncolors.p; a.w_errjoint = b->w_errjoint.p;
+    a.w_maxpen = b->w_maxpen.p; a.w_badk = b->w_badk.p; a.exp_slots = b->exp_slots.p; a.exp_count = b->exp_count.p;
+    k_batch_step<<<b->n_worlds, b->threads, b->smem, b->stream>>>(a);
+    SYLT_CUDA(cudaGetLastError());
+    b->launches++;
+    b->body_steps += (uint64_t)b->n_bodies * (uint64_t)n;
+    b->last_steps = n;
+    b->inflight = true;
+    return SYLT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltBodyDesc* bodies, const int32_t* joint_offsets,
+                      const SyltJointDesc* joints, float gx, float gy, uint32_t iterations, int device, SyltBatch** out) {
+    if (!out || n_worlds < 1 || !body_offsets || !bodies) return SYLT_ERR_INVALID;
+    *out = nullptr;
+    int ndev = 0;
+    SYLT_CUDA(cudaGetDeviceCount(&ndev));
+    if (device < 0 || device >= ndev) { set_last_error("no such CUDA device"); return SYLT_ERR_CUDA; }
+    SYLT_CUDA(cudaSetDevice(device));
+    const int64_t NB = body_offsets[n_worlds];
+    const int64_t NJ = joint_offsets ? joint_offsets[n_worlds] : 0;
+    if (NJ > 0 && !joints) return SYLT_ERR_INVALID;
+    SyltBatch* b = new SyltBatch();
+    b->device = device; b->n_worlds = n_worlds; b->gx = gx; b->gy = gy; b->iterations = iterations;
+    b->n_bodies = NB; b->n_joints = NJ;
+    b->h_body_off.assign(body_offsets, body_offsets + n_worlds + 1);
+    if (joint_offsets) b->h_joint_off.assign(joint_offsets, joint_offsets + n_worlds + 1);
+    else b->h_joint_off.assign((size_t)n_worlds + 1, 0);
+    std::vector<float4> pose((size_t)NB), vel((size_t)NB), mp((size_t)NB);
+    std::vector<float2> wh((size_t)NB);
+    std::vector<float> mm((size_t)NB * 2);
+    b->h_ids.resize((size_t)NB);
+    int Bmax = 0, Jmax = 0;
+    std::vector<V2> scratch;
+    for (int w = 0; w < n_worlds; w++) {
+        int o0 = body_offsets[w], o1 = body_offsets[w + 1];
+        if (o1 < o0) { delete b; return SYLT_ERR_INVALID; }
+        Bmax = std::max(Bmax, o1 - o0);
+        Jmax = std::max(Jmax, b->h_joint_off[(size_t)w + 1] - b->h_joint_off[(size_t)w]);
+        std::vector<HostBody> hbs;
+        for (int i = o0; i < o1; i++) {
+            const SyltBodyDesc& d = bodies[i];
+            if (d.shape != SYLT_SHAPE_BOX) { delete b; return SYLT_ERR_UNSUPPORTED; }
+            HostBody hb;
+            scratch.clear();
+            int e = make_host_body(d, nullptr, 0, &hb, &scratch);
+            if (e) { delete b; return e; }
+            hbs.push_back(hb);
+            pose[(size_t)i] = make_float4(d.x, d.y, d.rotation, 0.0f);
+            vel[(size_t)i] = make_float4(d.vx, d.vy, d.angular_velocity, 0.0f);
+            mp[(size_t)i] = make_float4(hb.inv_mass, hb.inv_moi, hb.friction, 0.0f);
+            wh[(size_t)i] = make_float2(hb.width_x, hb.width_y);
+            mm[(size_t)i * 2] = hb.mass; mm[(size_t)i * 2 + 1] = hb.moi;
+            b->h_ids[(size_t)i] = d.id;
+        }
+        if (body_order_violated(hbs)) { delete b; return SYLT_ERR_BODY_ORDER; }  // quirk Q-6
+    }
+    if (Bmax > 4096) { delete b; return SYLT_ERR_UNSUPPORTED; }
+    // joints: Joint::new (joint.rs:26-55) per world, then a greedy colouring of each world's joint graph
+    std::vector<int2> jb((size_t)NJ);
+    std::vector<float4> jla((size_t)NJ);
+    std::vector<float2> jparam((size_t)NJ);
+    std::vector<int> jorder((size_t)NJ), jcs((size_t)n_worlds * (MAX_JC + 1), 0), njc((size_t)n_worlds, 0);
+    b->h_joints.resize((size_t)NJ);
+    for (int w = 0; w < n_worlds; w++) {
+        int o0 = body_offsets[w], nb = body_offsets[w + 1] - o0;
+        int q0 = b->h_joint_off[(size_t)w], nj = b->h_joint_off[(size_t)w + 1] - q0;
+        std::vector<unsigned> used((size_t)nb, 0u);
+        std::vector<int> color((size_t)nj, 0);
+        int nc = 0;
+        for (int j = 0; j < nj; j++) {
+            const SyltJointDesc& d = joints[q0 + j];
+            int b1 = -1, b2 = -1;
+            for (int i = 0; i < nb && (b1 < 0 || b2 < 0); i++) {
+                if (b1 < 0 && bodies[o0 + i].id == d.id1) b1 = i;
+                if (b2 < 0 && bodies[o0 + i].id == d.id2) b2 = i;
+            }
+            if (b1 < 0 || b2 < 0) { delete b; return SYLT_ERR_BODY_NOT_FOUND; }
+            const SyltBodyDesc &s1 = bodies[o0 + b1], &s2 = bodies[o0 + b2];
+            M2 rt1 = transpose(rot_angle(s1.rotation)), rt2 = transpose(rot_angle(s2.rotation));
+            V2 anchor = mk(d.anchor_x, d.anchor_y);
+            V2 la1 = rt1 * (anchor - mk(s1.x, s1.y)), la2 = rt2 * (anchor - mk(s2.x, s2.y));
+            jb[(size_t)(q0 + j)] = make_int2(b1, b2);
+            jla[(size_t)(q0 + j)] = make_float4(la1.x, la1.y, la2.x, la2.y);
+            jparam[(size_t)(q0 + j)] = make_float2(d.softness, d.bias_factor);
+            SyltBatch::HJ hj = {b1, b2, la1.x, la1.y, la2.x, la2.y, d.softness, d.bias_factor};
+            b->h_joints[(size_t)(q0 + j)] = hj;
+            bool d1 = mp[(size_t)(o0 + b1)].x != 0.0f || mp[(size_t)(o0 + b1)].y != 0.0f;
+            bool d2 = mp[(size_t)(o0 + b2)].x != 0.0f || mp[(size_t)(o0 + b2)].y != 0.0f;
+            unsigned m = (d1 ? used[(size_t)b1] : 0u) | (d2 ? used[(size_t)b2] : 0u);
+            int c = 0;
+            while (c < MAX_JC && ((m >> c) & 1u)) c++;
+            if (c >= MAX_JC) { delete b; return SYLT_ERR_UNSUPPORTED; }
+            color[(size_t)j] = c;
+            if (d1) used[(size_t)b1] |= 1u << c;
+            if (d2) used[(size_t)b2] |= 1u << c;
+            nc = std::max(nc, c + 1);
+        }
+        njc[(size_t)w] = nc;
+        int* st = &jcs[(size_t)w * (MAX_JC + 1)];
+        for (int j = 0; j < nj; j++) st[color[(size_t)j] + 1]++;
+        for (int c = 0; c < MAX_JC; c++) st[c + 1] += st[c];
+        std::vector<int> fill(st, st + MAX_JC);
+        for (int j = 0; j < nj; j++) jorder[(size_t)(q0 + fill[(size_t)color[(size_t)j]]++)] = j;
+    }
+    b->h_jorder = jorder;
+    b->Bmax = Bmax; b->Jmax = Jmax;
+    b->cap = std::max(32, 2 * Bmax + 32);
+    if (b->cap > 65535) b->cap = 65535;
+    b->smem = carve(nullptr, nullptr, Bmax, Jmax, b->cap);
+    int max_smem = 0;
+    SYLT_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    if (b->smem > (size_t)max_smem) {
+        delete b;
+        set_last_error("world too large for the one-CTA-per-world path (shared memory)");
+        return SYLT_ERR_UNSUPPORTED;
+    }
+    SYLT_CUDA(cudaFuncSetAttribute(k_batch_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
+    int t = std::max(Bmax, (b->cap + 1) / 2);
+    t = ((t + 31) / 32) * 32;
+    b->threads = std::min(256, std::max(32, t));
+    SYLT_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
+    SYLT_CUDA(cudaEventCreate(&b->ev0));
+    SYLT_CUDA(cudaEventCreate(&b->ev1));
+    int e = 0;
+    if ((e = upload(b->body_off, b->h_body_off)) || (e = upload(b->joint_off, b->h_joint_off)) || (e = upload(b->pose, pose)) ||
+        (e = upload(b->vel, vel)) || (e = upload(b->mp, mp)) || (e = upload(b->wh, wh)) || (e = upload(b->mass_moi, mm)) ||
+        (e = upload(b->jbodies, jb)) || (e = upload(b->jla, jla)) || (e = upload(b->jparam, jparam)) || (e = upload(b->jorder, jorder)) ||
+        (e = upload(b->jcolor_start, jcs)) || (e = upload(b->n_jcolors, njc))) { sylt_batch_destroy(b); return e; }
+    const size_t W = (size_t)n_worlds, WC = W * (size_t)b->cap;
+    if ((e = zeroed(b->jp, (size_t)NJ)) || (e = zeroed(b->jr, (size_t)NJ)) || (e = zeroed(b->jm, (size_t)NJ)) || (e = zeroed(b->jbias, (size_t)NJ)) ||
+        (e = zeroed(b->c_count, W)) || (e = zeroed(b->c_key, WC)) || (e = zeroed(b->c_fric, WC)) || (e = zeroed(b->c_pn, WC)) ||
+        (e = zeroed(b->c_pt, WC)) || (e = zeroed(b->c_color, WC)) || (e = zeroed(b->w_err, W)) || (e = zeroed(b->w_ncon, W)) ||
+        (e = zeroed(b->w_narb, W)) || (e = zeroed(b->w_ncolors, W)) || (e = zeroed(b->w_errjoint, W)) || (e = zeroed(b->w_maxpen, W)) ||
+        (e = zeroed(b->w_badk, W)) || (e = zeroed(b->stats, 1))) { sylt_batch_destroy(b); return e; }
+    b->export_first = 0;
+    b->export_count = std::min(n_worlds, 64);
+    if ((e = zeroed(b->exp_slots, (size_t)b->export_count * (size_t)b->cap)) || (e = zeroed(b->exp_count, (size_t)b->export_count))) {
+        sylt_batch_destroy(b);
+        return e;
+    }
+    *out = b;
+    return SYLT_OK;
+}
+
+int sylt_batch_destroy(SyltBatch* b) {
+    if (!b) return SYLT_OK;
+    cudaSetDevice(b->device);
+    if (b->stream) cudaStreamSynchronize(b->stream);
+    batch_free(b);
+    if (b->ev0) cudaEventDestroy(b->ev0);
+    if (b->ev1) cudaEventDestroy(b->ev1);
+    if (b->stream) cudaStreamDestroy(b->stream);
+    delete b;
+    return SYLT_OK;
+}
+
+int sylt_batch_set_context(SyltBatch* b, int acc, int warm, int pc) {
+    if (!b) return SYLT_ERR_INVALID;
+    b->accumulate = acc != 0; b->warm = warm != 0; b->poscorr = pc != 0;
+    return SYLT_OK;
+}
+
+int sylt_batch_sync(SyltBatch* b) {
+    if (!b) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    SYLT_CUDA(cudaStreamSynchronize(b->stream));
+    b->inflight = false;
+    return SYLT_OK;
+}
+int sylt_batch_step_n_async(SyltBatch* b, float dt, int32_t n) {
+    if (!b || n < 0) return SYLT_ERR_INVALID;
+    if (n == 0) return SYLT_OK;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    return batch_enqueue(b, dt, n);
+}
+int sylt_batch_step_n(SyltBatch* b, float dt, int32_t n) {
+    int e = sylt_batch_step_n_async(b, dt, n);
+    if (e) return e;
+    return sylt_batch_sync(b);
+}
+int sylt_batch_timer_start(SyltBatch* b) {
+    if (!b) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    SYLT_CUDA(cudaEventRecord(b->ev0, b->stream));
+    return SYLT_OK;
+}
+int sylt_batch_timer_stop(SyltBatch* b, float* ms) {
+    if (!b || !ms) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    SYLT_CUDA(cudaEventRecord(b->ev1, b->stream));
+    SYLT_CUDA(cudaEventSynchronize(b->ev1));
+    SYLT_CUDA(cudaEventElapsedTime(ms, b->ev0, b->ev1));
+    b->inflight = false;
+    return SYLT_OK;
+}
+int64_t sylt_batch_launch_count(SyltBatch* b) { return b ? b->launches : 0; }
+int sylt_batch_num_worlds(SyltBatch* b) { return b ? b->n_worlds : 0; }
+int64_t sylt_batch_num_bodies(SyltBatch* b) { return b ? b->n_bodies : 0; }
+
+int sylt_batch_get_bodies(SyltBatch* b, int32_t first, int32_t nw, SyltBodyState* out, int64_t cap) {
+    if (!b || first < 0 || nw < 0 || first + nw > b->n_worlds) return -SYLT_ERR_INVALID;
+    const int o0 = b->h_body_off[(size_t)first], o1 = b->h_body_off[(size_t)(first + nw)];
+    const int n = o1 - o0;
+    if (n > cap) return -SYLT_ERR_CAPACITY;
+    if (n == 0) return 0;
+    if (cudaSetDevice(b->device) != cudaSuccess) return -SYLT_ERR_CUDA;
+    std::vector<float4> p((size_t)n), v((size_t)n);
+    cudaMemcpyAsync(p.data(), b->pose.p + o0, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, b->stream);
+    cudaMemcpyAsync(v.data(), b->vel.p + o0, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, b->stream);
+    cudaError_t ce = cudaStreamSynchronize(b->stream);
+    if (ce != cudaSuccess) { set_last_error(cudaGetErrorString(ce)); return -SYLT_ERR_CUDA; }
+    for (int i = 0; i < n; i++) {
+        SyltBodyState s = {p[(size_t)i].x, p[(size_t)i].y, p[(size_t)i].z, v[(size_t)i].x, v[(size_t)i].y, v[(size_t)i].z, 0.0f, 0.0f, 0.0f};
+        out[i] = s;
+    }
+    return n;
+}
+
+int sylt_batch_set_bodies(SyltBatch* b, int32_t first, int32_t nw, const SyltBodyState* in, int64_t count) {
+    if (!b || first < 0 || nw < 0 || first + nw > b->n_worlds) return SYLT_ERR_INVALID;
+    const int o0 = b->h_body_off[(size_t)first], o1 = b->h_body_off[(size_t)(first + nw)];
+    const int n = o1 - o0;
+    if (count != n) return SYLT_ERR_INVALID;
+    if (n == 0) return SYLT_OK;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    std::vector<float4> p((size_t)n), v((size_t)n);
+    for (int i = 0; i < n; i++) {
+        p[(size_t)i] = make_float4(in[i].x, in[i].y, in[i].rotation, 0.0f);
+        v[(size_t)i] = make_float4(in[i].vx, in[i].vy, in[i].angular_velocity, 0.0f);
+    }
+    SYLT_CUDA(cudaMemcpyAsync(b->pose.p + o0, p.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, b->stream));
+    SYLT_CUDA(cudaMemcpyAsync(b->vel.p + o0, v.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, b->stream));
+    SYLT_CUDA(cudaStreamSynchronize(b->stream));
+    return SYLT_OK;
+}
+
+int sylt_batch_get_arbiters(SyltBatch* b, int32_t world, SyltArbiterInfo* arbiters, int32_t arbiter_cap, SyltContact* contacts, int32_t contact_cap) {
+    if (!b || world < 0 || world >= b->n_worlds) return -SYLT_ERR_INVALID;
+    if (world < b->export_first || world >= b->export_first + b->export_count) return -SYLT_ERR_UNSUPPORTED;
+    if (cudaSetDevice(b->device) != cudaSuccess) return -SYLT_ERR_CUDA;
+    const int xw = world - b->export_first;
+    int P = 0;
+    cudaStreamSynchronize(b->stream);
+    if (cudaMemcpy(&P, b->exp_count.p + xw, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -SYLT_ERR_CUDA;
+    std::vector<SlotExport> sl((size_t)std::max(P, 1));
+    if (P > 0 && cudaMemcpy(sl.data(), b->exp_slots.p + (size_t)xw * b->cap, (size_t)P * sizeof(SlotExport), cudaMemcpyDeviceToHost) != cudaSuccess)
+        return -SYLT_ERR_CUDA;
+    const int o0 = b->h_body_off[(size_t)world];
+    int na = 0, nc = 0;
+    for (int p = 0; p < P; p++) {
+        const SlotExport& e = sl[(size_t)p];
+        if (e.count <= 0) continue;
+        if (na >= arbiter_cap || nc + e.count > contact_cap) return -SYLT_ERR_CAPACITY;
+        SyltArbiterInfo& o = arbiters[na++];
+        o.body1 = (int)(e.key >> 16); o.body2 = (int)(e.key & 0xffffu);
+        o.id1 = b->h_ids[(size_t)(o0 + o.body1)]; o.id2 = b->h_ids[(size_t)(o0 + o.body2)];
+        o.friction = e.friction; o.num_contacts = e.count; o.contact_offset = nc; o.color = e.color;
+        const bool zero_r = b->iterations == 0;
+        for (int q = 0; q < e.count; q++) {
+            SyltContact& c = contacts[nc++];
+            memset(&c, 0, sizeof c);
+            c.px = e.geo[q][0]; c.py = e.geo[q][1]; c.separation = e.geo[q][2]; c.nx = e.nx; c.ny = e.ny;
+            if (!zero_r) { c.r1x = e.sol[q][0]; c.r1y = e.sol[q][1]; c.r2x = e.sol[q][2]; c.r2y = e.sol[q][3]; }
+            c.mass_normal = e.sol[q][4]; c.mass_tangent = e.sol[q][5]; c.bias = e.sol[q][6]; c.pn = e.sol[q][7]; c.pt = e.sol[q][8];
+            c.in_edge_1 = e.feat[q] & 0xff; c.out_edge_1 = (e.feat[q] >> 8) & 0xff; c.in_edge_2 = (e.feat[q] >> 16) & 0xff;
+            c.out_edge_2 = (e.feat[q] >> 24) & 0xff;
+        }
+    }
+    return na;
+}
+
+int sylt_batch_get_joints(SyltBatch* b, int32_t world, SyltJointState* out, int32_t cap) {
+    if (!b || world < 0 || world >= b->n_worlds) return -SYLT_ERR_INVALID;
+    if (cudaSetDevice(b->device) != cudaSuccess) return -SYLT_ERR_CUDA;
+    const int q0 = b->h_joint_off[(size_t)world], J = std::min<int>(cap, b->h_joint_off[(size_t)world + 1] - q0);
+    if (J <= 0) return 0;
+    std::vector<float2> p((size_t)J), bs((size_t)J);
+    std::vector<float4> r((size_t)J), m((size_t)J);
+    cudaStreamSynchronize(b->stream);
+    cudaMemcpy(p.data(), b->jp.p + q0, (size_t)J * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(bs.data(), b->jbias.p + q0, (size_t)J * sizeof(float2), cudaMemcpyDeviceToHost);
+    cudaMemcpy(r.data(), b->jr.p + q0, (size_t)J * sizeof(float4), cudaMemcpyDeviceToHost);
+    if (cudaMemcpy(m.data(), b->jm.p + q0, (size_t)J * sizeof(float4), cudaMemcpyDeviceToHost) != cudaSuccess) return -SYLT_ERR_CUDA;
+    for (int j = 0; j < J; j++) {
+        const SyltBatch::HJ& h = b->h_joints[(size_t)(q0 + j)];
+        SyltJointState s;
+        s.px = p[(size_t)j].x; s.py = p[(size_t)j].y; s.bias_x = bs[(size_t)j].x; s.bias_y = bs[(size_t)j].y;
+        s.r1x = r[(size_t)j].x; s.r1y = r[(size_t)j].y; s.r2x = r[(size_t)j].z; s.r2y = r[(size_t)j].w;
+        s.m11 = m[(size_t)j].x; s.m12 = m[(size_t)j].y; s.m21 = m[(size_t)j].z; s.m22 = m[(size_t)j].w;
+        s.bias_factor = h.bias_factor; s.softness = h.softness; s.la1x = h.la1x; s.la1y = h.la1y; s.la2x = h.la2x; s.la2y = h.la2y;
+        s.body1 = h.b1; s.body2 = h.b2;
+        out[j] = s;
+    }
+    return J;
+}
+
+int sylt_batch_get_joint_order(SyltBatch* b, int32_t world, int32_t* out, int32_t cap) {
+    if (!b || world < 0 || world >= b->n_worlds) return -SYLT_ERR_INVALID;
+    const int q0 = b->h_joint_off[(size_t)world], J = std::min<int>(cap, b->h_joint_off[(size_t)world + 1] - q0);
+    for (int j = 0; j < J; j++) out[j] = b->h_jorder[(size_t)(q0 + j)];
+    return std::max(J, 0);
+}
+
+int sylt_batch_get_errors(SyltBatch* b, int32_t* out, int32_t cap) {
+    if (!b || !out) return -SYLT_ERR_INVALID;
+    if (cudaSetDevice(b->device) != cudaSuccess) return -SYLT_ERR_CUDA;
+    int n = std::min<int>(cap, b->n_worlds);
+    cudaStreamSynchronize(b->stream);
+    if (cudaMemcpy(out, b->w_err.p, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -SYLT_ERR_CUDA;
+    return n;
+}
+
+int sylt_batch_stats(SyltBatch* b, SyltBatchStats* out) {
+    if (!b || !out) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    SYLT_CUDA(cudaMemsetAsync(b->stats.p, 0, sizeof(StatsOut), b->stream));
+    k_batch_stats<<<std::min(1024, (b->n_worlds + 255) / 256), 256, 0, b->stream>>>(b->n_worlds, b->body_off.p, b->vel.p, b->mp.p, b->mass_moi.p,
+                                                                                    b->w_err.p, b->w_ncon.p, b->w_maxpen.p, b->stats.p);
+    b->launches++;
+    StatsOut so;
+    SYLT_CUDA(cudaMemcpyAsync(&so, b->stats.p, sizeof so, cudaMemcpyDeviceToHost, b->stream));
+    SYLT_CUDA(cudaStreamSynchronize(b->stream));
+    memset(out, 0, sizeof *out);
+    out->body_steps = b->body_steps; out->contacts = so.contacts; out->errors = so.errors; out->kinetic_energy = so.ke;
+    out->max_penetration = so.maxpen;
+    return SYLT_OK;
+}
+
+}  // extern "C"

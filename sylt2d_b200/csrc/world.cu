@@ -1,0 +1,1582 @@
+// world.cu — the single (large) world: World::step on one B200.
+//
+// Restates the behaviour of /root/reference/src/world.rs:73-152 (broad_phase + step) with a different
+// algorithmic structure (nothing here is a translation of the Rust loops):
+//
+//   k_prepare      body        (cos,sin) cache, conservative AABB, hashed uniform-grid cell, force integration
+//                              (world.rs:113-120)
+//   scan           bucket      counting-sort offsets of the grid (hand-written 3-kernel exclusive scan)
+//   k_fill_cells   body        bodies grouped by cell
+//   k_rows<count|emit>  body   candidate rows: for body i every AABB-overlapping partner it "owns", partner-sorted;
+//                              static-static pairs skipped (world.rs:79-81).  Large bodies (ground, walls) bypass
+//                              the grid through a short list.
+//   k_narrow       pair        one thread per candidate pair: box_box / poly_poly (narrow.cuh)
+//   scan           pair        (arbiter, contact) offsets in one packed 64-bit scan
+//   k_build        pair        compaction into the arbiter / contact SoA; match against last step's arbiters
+//                              (Arbiter::update, arbiter.rs:137-181 incl. quirk Q-2; friction persistence Q-17);
+//                              persisting arbiters keep their colour
+//   k_solve        cooperative persistent kernel: incremental graph colouring of new arbiters, then
+//                              Arbiter::pre_step / Joint::pre_step / iterations x apply_impulse per colour with grid
+//                              barriers (arbiter.rs:182-298, joint.rs:57-130), then position integration
+//                              (world.rs:143-150)
+//
+// Gauss-Seidel order: arbiter colours ascending, then joint colours ascending (within a colour constraints touch
+// disjoint dynamic bodies, so the result equals the sequential sweep in that order bit for bit; static bodies
+// are never written).  The order is reported through sylt_world_get_arbiters(...).color / get_joint_order so the
+// oracle can replay it.
+#include <cooperative_groups.h>
+#include <algorithm>
+#include <mutex>
+#include "common.h"
+#include "narrow.cuh"
+#include "solver.cuh"
+
+namespace cg = cooperative_groups;
+using namespace sylt;
+
+namespace sylt {
+static thread_local std::string g_last_error;
+static std::mutex g_err_mu;
+static std::string g_last_error_global;
+void set_last_error(const std::string& s) {
+    g_last_error = s;
+    std::lock_guard<std::mutex> l(g_err_mu);
+    g_last_error_global = s;
+}
+}  // namespace sylt
+
+namespace {
+
+constexpr int NC = 32;          // max arbiter colours
+constexpr int MAX_ROUNDS = 256; // colouring rounds per step (only new arbiters take part)
+constexpr int SPREAD = 4;       // new arbiters propose one of their first SPREAD free colours
+constexpr int FLAG_POLY = 1, FLAG_LARGE = 2, FLAG_STATIC = 4;
+
+struct Counters {
+    // sticky across the steps of one step_n call (reset by do_steps):
+    int err, err_joint;
+    float badk[4];
+    // per step (reset by enqueue_step):
+    int n_pairs, n_arb, n_con;
+    int n_colors, rounds, n_uncolored, warn_ext;
+    int color_count[NC];
+    int color_start[NC + 1];
+    int color_fill[NC];
+    int remaining[MAX_ROUNDS];
+};
+
+// ------------------------------------------------------------------ device-wide exclusive scan (3 kernels)
+constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+template <typename T>
+__device__ __forceinline__ T warp_incl_scan(T v) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        T u = __shfl_up_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) >= o) v += u;
+    }
+    return v;
+}
+// exclusive scan of one value per thread across the block; returns the exclusive prefix, *total = block sum
+template <typename T>
+__device__ __forceinline__ T block_excl_scan(T v, T* total, T* sh /* >= 33 */) {
+    T inc = warp_incl_scan(v);
+    int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 31) sh[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+        T s = (l < (int)(blockDim.x >> 5)) ? sh[l] : T(0);
+        T si = warp_incl_scan(s);
+        sh[l] = si - s;
+        if (l == 31) sh[32] = si;
+    }
+    __syncthreads();
+    T r = sh[w] + inc - v;
+    *total = sh[32];
+    __syncthreads();
+    return r;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const T* in, int n_host, const int* n_dev, T* partial) {
+    __shared__ T sh[33];
+    int n = n_dev ? min(*n_dev, n_host) : n_host;
+    int base = blockIdx.x * SCAN_TILE;
+    if (base >= n) return;
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int i = base + threadIdx.x * SCAN_ITEMS + k;
+        if (i < n) s += in[i];
+    }
+    T tot;
+    block_excl_scan(s, &tot, sh);
+    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
+}
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(T* partial, int n_host, const int* n_dev, T* out_total) {
+    __shared__ T sh[33];
+    int n = n_dev ? min(*n_dev, n_host) : n_host;
+    int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
+    T run = 0;
+    for (int base = 0; base < nb; base += SCAN_THREADS) {
+        int i = base + threadIdx.x;
+        T v = i < nb ? partial[i] : T(0);
+        T tot;
+        T ex = block_excl_scan(v, &tot, sh);
+        if (i < nb) partial[i] = run + ex;
+        run += tot;
+    }
+    if (threadIdx.x == 0 && out_total) *out_total = run;
+}
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const T* in, T* out, int n_host, const int* n_dev, const T* partial, const T* total) {
+    __shared__ T sh[33];
+    int n = n_dev ? min(*n_dev, n_host) : n_host;
+    int base = blockIdx.x * SCAN_TILE;
+    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
+    if (base >= n) return;
+    T v[SCAN_ITEMS];
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int i = base + threadIdx.x * SCAN_ITEMS + k;
+        v[k] = i < n ? in[i] : T(0);
+        s += v[k];
+    }
+    T tot;
+    T ex = block_excl_scan(s, &tot, sh) + partial[blockIdx.x];
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        int i = base + threadIdx.x * SCAN_ITEMS + k;
+        if (i < n) out[i] = ex;
+        ex += v[k];
+    }
+}
+
+// ------------------------------------------------------------------ broad phase
+struct GridParams {
+    float cell;
+    int mask;  // buckets - 1
+};
+__device__ __forceinline__ int cell_coord(float x, float cell) {
+    float q = floorf(x / cell);
+    q = fminf(fmaxf(q, -1.0e9f), 1.0e9f);
+    return (int)q;
+}
+__device__ __forceinline__ int cell_hash(int cx, int cy, int mask) {
+    return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u)) & mask;
+}
+__device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
+    return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w);
+}
+
+__global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* vel, const float4* force, const float4* mp, const float4* geom,
+                                                 const int* bflags, const float2* lverts, float2* rotc, float4* aabb, int4* cinfo,
+                                                 int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
+                                                 Counters* cn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float4 p = pose[i];
+    float4 m = mp[i];
+    float4 g = geom[i];
+    int fl = bflags[i];
+    float c = sylt_cosf(p.z), s = sylt_sinf(p.z);
+    rotc[i] = make_float2(c, s);
+    if (integrate && m.x != 0.0f) {  // world.rs:113-120
+        float4 v = vel[i];
+        float4 f = force[i];
+        V2 nv = mk(v.x, v.y) + (mk(gx, gy) + mk(f.x, f.y) * m.x) * dt;
+        v.x = nv.x; v.y = nv.y;
+        v.z += m.y * f.z * dt;
+        vel[i] = v;
+    }
+    float minx, miny, maxx, maxy;
+    if (fl & FLAG_POLY) {
+        int off = __float_as_int(g.z), nv = (fl >> 8) & 0xff;
+        M2 r = rot_cs(c, s);
+        minx = miny = 3.402823466e+38f; maxx = maxy = -3.402823466e+38f;
+        for (int k = 0; k < nv; k++) {
+            float2 lv = lverts[off + k];
+            V2 w = r * mk(lv.x, lv.y) + mk(p.x, p.y);
+            minx = fminf(minx, w.x); maxx = fmaxf(maxx, w.x);
+            miny = fminf(miny, w.y); maxy = fmaxf(maxy, w.y);
+        }
+    } else {
+        float hx = g.x * 0.5f, hy = g.y * 0.5f;
+        float ex = fabsf(c) * hx + fabsf(s) * hy, ey = fabsf(s) * hx + fabsf(c) * hy;
+        minx = p.x - ex; maxx = p.x + ex; miny = p.y - ey; maxy = p.y + ey;
+    }
+    // conservative margin: a few ulps of the absolute coordinates plus a relative slack on the extent
+    float mg = 1.0e-6f * (fabsf(p.x) + fabsf(p.y)) + 1.0e-5f * ((maxx - minx) + (maxy - miny)) + 1.0e-6f;
+    minx -= mg; miny -= mg; maxx += mg; maxy += mg;
+    aabb[i] = make_float4(minx, miny, maxx, maxy);
+    int cx = 0, cy = 0;
+    if (!(fl & FLAG_LARGE)) {
+        cx = cell_coord(0.5f * (minx + maxx), gp.cell);
+        cy = cell_coord(0.5f * (miny + maxy), gp.cell);
+        int h = cell_hash(cx, cy, gp.mask);
+        rank[i] = atomicAdd(&cell_count[h], 1);
+        if (maxx - minx > gp.cell || maxy - miny > gp.cell) atomicAdd(&cn->warn_ext, 1);
+    }
+    cinfo[i] = make_int4(cx, cy, fl, 0);
+}
+
+__global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, const int* rank, const int* cell_start, int* cell_bodies, GridParams gp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int4 ci = cinfo[i];
+    if (ci.z & FLAG_LARGE) return;
+    cell_bodies[cell_start[cell_hash(ci.x, ci.y, gp.mask)] + rank[i]] = i;
+}
+
+// Row i = partners body i owns: small-small pairs belong to the lower index, small-large pairs to the small
+// body, large-large pairs to the lower index.  Partners are emitted sorted ascending.
+template <bool EMIT>
+__global__ void __launch_bounds__(128) k_rows(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int* cell_bodies,
+                                              const int* large, int n_large, GridParams gp, int* row_count, const int* row_start,
+                                              int2* pairs, int cap_pairs, Counters* cn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    float4 my = aabb[i];
+    int4 ci = cinfo[i];
+    const bool st_i = (ci.z & FLAG_STATIC) != 0;
+    int n = 0;
+    int base = 0;
+    if (EMIT) {
+        base = row_start[i];
+        int end = row_start[i + 1];
+        if (end > cap_pairs) {  // whole row does not fit: flag and drop (k_scan already clamped the total)
+            atomicExch(&cn->err, SYLT_ERR_CAPACITY);
+            return;
+        }
+    }
+    if (!(ci.z & FLAG_LARGE)) {
+        int x0 = cell_coord(my.x - 0.5f * gp.cell, gp.cell), x1 = cell_coord(my.z + 0.5f * gp.cell, gp.cell);
+        int y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell), y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
+        for (int cy = y0; cy <= y1; cy++)
+            for (int cx = x0; cx <= x1; cx++) {
+                int h = cell_hash(cx, cy, gp.mask);
+                int k1 = cell_start[h + 1];
+                for (int k = cell_start[h]; k < k1; k++) {
+                    int j = cell_bodies[k];
+                    if (j <= i) continue;
+                    int4 cj = cinfo[j];
+                    if (cj.x != cx || cj.y != cy) continue;  // another cell sharing the bucket
+                    if (st_i && (cj.z & FLAG_STATIC)) continue;
+                    if (!aabb_overlap(my, aabb[j])) continue;
+                    if (EMIT) pairs[base + n] = make_int2(i, j);
+                    n++;
+                }
+            }
+        for (int k = 0; k < n_large; k++) {
+            int j = large[k];
+            if (st_i && (cinfo[j].z & FLAG_STATIC)) continue;
+            if (!aabb_overlap(my, aabb[j])) continue;
+            if (EMIT) pairs[base + n] = make_int2(i, j);
+            n++;
+        }
+    } else {
+        for (int k = 0; k < n_large; k++) {
+            int j = large[k];
+            if (j <= i) continue;
+            if (st_i && (cinfo[j].z & FLAG_STATIC)) continue;
+            if (!aabb_overlap(my, aabb[j])) continue;
+            if (EMIT) pairs[base + n] = make_int2(i, j);
+            n++;
+        }
+    }
+    if (EMIT) {
+        for (int a = 1; a < n; a++) {  // insertion sort by partner (rows are short)
+            int2 v = pairs[base + a];
+            int b = a - 1;
+            while (b >= 0 && pairs[base + b].y > v.y) { pairs[base + b + 1] = pairs[base + b]; b--; }
+            pairs[base + b + 1] = v;
+        }
+    } else {
+        row_count[i] = n;
+    }
+}
+
+// ------------------------------------------------------------------ narrow phase: one thread per candidate pair
+template <int MAXC>
+__global__ void __launch_bounds__(128) k_narrow(const Counters* cn, int cap_pairs, const int2* pairs, const float4* pose, const float2* rotc,
+                                                const float4* geom, const int* bflags, const float2* lverts,
+                                                unsigned long long* info, float4* tmp_a, float2* tmp_b, Counters* cnw) {
+    int P = min(cn->n_pairs, cap_pairs);
+    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+        int2 pr = pairs[p];
+        int a = min(pr.x, pr.y), b = max(pr.x, pr.y);  // Arbiter::new: body1 = lower id (arbiter.rs:120-122)
+        float4 pa = pose[a], pb = pose[b];
+        float2 ra = rotc[a], rb = rotc[b];
+        float4 ga = geom[a], gb = geom[b];
+        int fa = bflags[a], fb = bflags[b];
+        ContactOut out[MAXC];
+        int n;
+        if (MAXC == 2 || !((fa | fb) & FLAG_POLY)) {
+            n = box_box(mk(pa.x, pa.y), ra.x, ra.y, mk(ga.x, ga.y), mk(pb.x, pb.y), rb.x, rb.y, mk(gb.x, gb.y), out);
+        } else {
+            V2 w0[MAX_POLY_VERTS], w1[MAX_POLY_VERTS];
+            int n0 = (fa >> 8) & 0xff, n1 = (fb >> 8) & 0xff;
+            int o0 = __float_as_int(ga.z), o1 = __float_as_int(gb.z);
+            M2 r0 = rot_cs(ra.x, ra.y), r1 = rot_cs(rb.x, rb.y);
+            for (int k = 0; k < n0; k++) { float2 l = lverts[o0 + k]; w0[k] = r0 * mk(l.x, l.y) + mk(pa.x, pa.y); }  // rotate + translate (body.rs:148-168)
+            for (int k = 0; k < n1; k++) { float2 l = lverts[o1 + k]; w1[k] = r1 * mk(l.x, l.y) + mk(pb.x, pb.y); }
+            bool ovf = false;
+            n = poly_poly(w0, n0, w1, n1, out, &ovf);
+            if (ovf) atomicExch(&cnw->err, SYLT_ERR_CAPACITY);
+        }
+        info[p] = n > 0 ? ((1ull << 32) | (unsigned)n) : 0ull;
+        for (int k = 0; k < n; k++) {
+            tmp_a[(size_t)p * MAXC + k] = make_float4(out[k].px, out[k].py, out[k].nx, out[k].ny);
+            tmp_b[(size_t)p * MAXC + k] = make_float2(out[k].sep, __uint_as_float(out[k].feat));
+        }
+    }
+}
+
+// Arbiter arrays of one step (double buffered: "cur" is being built, "old" is last step's result)
+struct ArbSet {
+    int2* bodies;      // (body1, body2), body1 < body2
+    int2* meta;        // (num_contacts, contact_offset)
+    int* partner;      // partner index in the owner's row (lookup key for the next step)
+    float* friction;
+    int* color;
+    int* row_start;    // per body: first arbiter of its row (B+1 entries)
+    float4 *ca, *cb, *cc, *cd;  // contacts: (nx,ny,r1x,r1y) (r2x,r2y,mass_n,mass_t) (bias,pn,pt,sep) (px,py,pnb,feat)
+};
+
+__device__ __forceinline__ void pair_owner(int a, int b, int fa, int fb, int* owner, int* partner) {
+    bool la = (fa & FLAG_LARGE) != 0, lb = (fb & FLAG_LARGE) != 0;
+    if (la == lb) { *owner = a; *partner = b; }  // a < b
+    else if (la) { *owner = b; *partner = a; }
+    else { *owner = a; *partner = b; }
+}
+
+template <int MAXC>
+__global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int cap_arb, int cap_con, int B, int B_old, int have_old,
+                                               const int2* pairs, const unsigned long long* info, const unsigned long long* scan,
+                                               const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
+                                               const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
+                                               unsigned* used, int* uncolored) {
+    int P = min(cn->n_pairs, cap_pairs);
+    int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int i = tid; i <= B; i += nth) {
+        int rs = i < B ? min(row_start[i], P) : P;
+        cur.row_start[i] = (int)(scan[rs] >> 32);
+    }
+    for (int p = tid; p < P; p += nth) {
+        unsigned long long in = info[p];
+        if (!in) continue;
+        int n = (int)(unsigned)in;
+        unsigned long long s = scan[p];
+        int a = (int)(s >> 32), coff = (int)(unsigned)s;
+        if (a >= cap_arb || coff + n > cap_con) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); continue; }
+        int2 pr = pairs[p];
+        int b1 = min(pr.x, pr.y), b2 = max(pr.x, pr.y);
+        float4 m1 = mp[b1], m2 = mp[b2];
+        // ---- Arbiter::update / insert (world.rs:85-98): look the pair up in last step's arbiters
+        int found = -1;
+        if (have_old && b2 < B_old) {
+            int oo, op;
+            pair_owner(b1, b2, bflags_old[b1], bflags_old[b2], &oo, &op);
+            int lo = old.row_start[oo], hi = old.row_start[oo + 1];
+            for (int k = lo; k < hi; k++)
+                if (old.partner[k] == op) { found = k; break; }
+        }
+        float fr, pn = 0.0f, pt = 0.0f, pnb = 0.0f;
+        int color = -1;
+        if (found >= 0) {
+            fr = old.friction[found];  // quirk Q-17: friction fixed at first insertion
+            color = old.color[found];
+            if (warm) {                // quirk Q-2: every new contact inherits old contact 0
+                int oc = old.meta[found].y;
+                float4 c = old.cc[oc];
+                pn = c.y; pt = c.z; pnb = old.cd[oc].z;
+            }
+        } else {
+            fr = sqrtf(m1.z * m2.z);  // arbiter.rs:128
+        }
+        cur.bodies[a] = make_int2(b1, b2);
+        cur.meta[a] = make_int2(n, coff);
+        cur.partner[a] = pr.y;
+        cur.friction[a] = fr;
+        cur.color[a] = color;
+        for (int k = 0; k < n; k++) {
+            float4 ta = tmp_a[(size_t)p * MAXC + k];
+            float2 tb = tmp_b[(size_t)p * MAXC + k];
+            cur.ca[coff + k] = make_float4(ta.z, ta.w, 0.0f, 0.0f);
+            cur.cb[coff + k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            cur.cc[coff + k] = make_float4(0.0f, pn, pt, tb.x);
+            cur.cd[coff + k] = make_float4(ta.x, ta.y, pnb, tb.y);
+        }
+        if (color >= 0) {
+            if (!(bflags[b1] & FLAG_STATIC)) atomicOr(&used[b1], 1u << color);
+            if (!(bflags[b2] & FLAG_STATIC)) atomicOr(&used[b2], 1u << color);
+            atomicAdd(&cn->color_count[color], 1);
+        } else {
+            uncolored[atomicAdd(&cn->n_uncolored, 1)] = a;
+        }
+    }
+}
+
+__global__ void k_totals(Counters* cn, const int* row_total, const unsigned long long* pair_total, int which, int cap_pairs) {
+    if (which == 0) cn->n_pairs = *row_total;
+    else {
+        cn->n_arb = (int)(*pair_total >> 32);
+        cn->n_con = (int)(unsigned)(*pair_total);
+    }
+    if (which == 0 && *row_total > cap_pairs) cn->err = SYLT_ERR_CAPACITY;
+}
+
+// ------------------------------------------------------------------ solver (cooperative persistent kernel)
+__device__ __forceinline__ unsigned fmix32(unsigned h) {  // bijective mix: unique priority per arbiter index
+    h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
+    return h;
+}
+
+struct SolveArgs {
+    Counters* cn;
+    int B, cap_arb, cap_con, J, n_joint_colors, iterations;
+    int accumulate, warm, poscorr, run_solver;
+    float dt, inv_dt;
+    unsigned epoch_base;
+    float4 *pose, *vel, *force;
+    const float4* mp;
+    const float2* rotc;
+    const int* bflags;
+    ArbSet cur;
+    unsigned* used;
+    unsigned long long* claim;  // B * NC
+    int *uncolored, *prop, *order;
+    // joints
+    const int2* jbodies;
+    const float4* jla;       // (la1x, la1y, la2x, la2y)
+    const float2* jparam;    // (softness, bias_factor)
+    float2* jp;              // accumulated impulse
+    float4 *jr, *jm;         // (r1, r2), M
+    float2* jbias;
+    const int *jorder, *jcolor_start;
+};
+
+__device__ __forceinline__ Vel load_vel(const float4* vel, int b) {
+    float4 v = __ldcg(&vel[b]);
+    Vel o; o.v = mk(v.x, v.y); o.w = v.z;
+    return o;
+}
+__device__ __forceinline__ void store_vel(float4* vel, int b, const Vel& v) { __stcg(&vel[b], make_float4(v.v.x, v.v.y, v.w, 0.0f)); }
+
+__global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
+    cg::grid_group grid = cg::this_grid();
+    Counters* cn = a.cn;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int A = min(*(volatile int*)&cn->n_arb, a.cap_arb);
+    __shared__ int s_start[NC + 1];
+    __shared__ int s_ncolors;
+
+    // ---- 1. colour the arbiters that are new this step (persisting ones kept their colour in k_build)
+    const int nunc = *(volatile int*)&cn->n_uncolored;
+    if (nunc > 0) {
+        int round = 0;
+        for (; round < MAX_ROUNDS; round++) {
+            const unsigned long long ep = (unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32;
+            for (int k = tid; k < nunc; k += nth) {
+                int e = a.uncolored[k];
+                if (a.cur.color[e] >= 0) continue;
+                int2 b = a.cur.bodies[e];
+                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
+                unsigned m = (d1 ? __ldcg(&a.used[b.x]) : 0u) | (d2 ? __ldcg(&a.used[b.y]) : 0u);
+                unsigned fr = ~m;
+                if (!fr) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[e] = -1; continue; }
+                int nf = min(__popc(fr), SPREAD);
+                int r = (int)(fmix32((unsigned)e * 2654435761u + (unsigned)round) % (unsigned)nf);
+                int c = __fns(fr, 0, r + 1);  // (r+1)-th set bit
+                a.prop[e] = c;
+                unsigned long long val = ep | fmix32((unsigned)e);
+                if (d1) atomicMin(&a.claim[(size_t)b.x * NC + c], val);
+                if (d2) atomicMin(&a.claim[(size_t)b.y * NC + c], val);
+            }
+            grid.sync();
+            for (int k = tid; k < nunc; k += nth) {
+                int e = a.uncolored[k];
+                if (a.cur.color[e] >= 0) continue;
+                int c = a.prop[e];
+                if (c < 0) continue;
+                int2 b = a.cur.bodies[e];
+                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
+                unsigned long long val = ep | fmix32((unsigned)e);
+                bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NC + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NC + c]) == val);
+                if (win) {
+                    a.cur.color[e] = c;
+                    if (d1) atomicOr(&a.used[b.x], 1u << c);
+                    if (d2) atomicOr(&a.used[b.y], 1u << c);
+                    atomicAdd(&cn->color_count[c], 1);
+                } else {
+                    atomicAdd(&cn->remaining[round], 1);
+                }
+            }
+            grid.sync();
+            if (*(volatile int*)&cn->remaining[round] == 0) break;
+        }
+        if (tid == 0) cn->rounds = round + 1;
+    }
+
+    // ---- 2. colour-major order (within a colour the order is irrelevant: disjoint dynamic bodies)
+    if (threadIdx.x == 0) {
+        int run = 0, nc = 0;
+        for (int c = 0; c < NC; c++) {
+            s_start[c] = run;
+            int k = *(volatile int*)&cn->color_count[c];
+            if (k > 0) nc = c + 1;
+            run += k;
+        }
+        s_start[NC] = run;
+        s_ncolors = nc;
+        if (blockIdx.x == 0) {
+            for (int c = 0; c <= NC; c++) cn->color_start[c] = s_start[c];
+            cn->n_colors = nc;
+        }
+    }
+    __syncthreads();
+    for (int e0 = tid - (threadIdx.x & 31); e0 < A; e0 += nth) {  // warp-uniform trip count
+        const int lane = threadIdx.x & 31, e = e0 + lane;
+        int c = e < A ? a.cur.color[e] : -1;
+        unsigned act = __ballot_sync(0xffffffffu, c >= 0);
+        if (c >= 0) {  // warp-aggregated slot allocation per colour
+            unsigned peers = __match_any_sync(act, c);
+            int leader = __ffs(peers) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(&cn->color_fill[c], __popc(peers));
+            base = __shfl_sync(peers, base, leader);
+            a.order[s_start[c] + base + __popc(peers & ((1u << lane) - 1))] = e;
+        }
+    }
+    grid.sync();
+    if (!a.run_solver) return;
+    const int ncolors = s_ncolors;
+    const bool acc = a.accumulate != 0;
+    const float kbias = a.poscorr ? 0.2f : 0.0f;
+
+    // ---- 3. Arbiter::pre_step, colour by colour (warm-start impulses write body velocities)
+    for (int c = 0; c < ncolors; c++) {
+        for (int k = s_start[c] + tid; k < s_start[c + 1]; k += nth) {
+            int e = a.order[k];
+            int2 b = a.cur.bodies[e];
+            int2 mt = a.cur.meta[e];
+            float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
+            float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
+            Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
+            for (int q = 0; q < mt.x; q++) {
+                int ci = mt.y + q;
+                float4 ca = a.cur.ca[ci], cc = a.cur.cc[ci], cd = a.cur.cd[ci];
+                ContactConst k0;
+                contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, mk(p1.x, p1.y), mk(p2.x, p2.y), m1.x, m1.y, m2.x, m2.y,
+                                a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
+                a.cur.ca[ci] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
+                a.cur.cb[ci] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
+                a.cur.cc[ci] = make_float4(k0.bias, cc.y, cc.z, cc.w);
+            }
+            if (acc) {
+                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
+                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+            }
+        }
+        if (acc) grid.sync();
+    }
+    if (!acc) grid.sync();
+
+    // ---- 4. Joint::pre_step, joint colours (host-coloured, static graph)
+    for (int c = 0; c < a.n_joint_colors; c++) {
+        for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
+            int j = a.jorder[k];
+            int2 b = a.jbodies[j];
+            float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
+            float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
+            float2 r1c = a.rotc[b.x], r2c = a.rotc[b.y];
+            Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
+            float4 la = a.jla[j];
+            float2 pr = a.jparam[j];
+            float2 pa = a.jp[j];
+            V2 pacc = mk(pa.x, pa.y);
+            JointConst jc;
+            M2 bad;
+            bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), r1c.x, r1c.y, mk(p2.x, p2.y), r2c.x, r2c.y,
+                                    m1.x, m1.y, m2.x, m2.y, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, v1, v2, jc, &bad);
+            a.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
+            if (!ok) {  // quirk Q-15: NoInverse aborts the step before the iterations
+                if (atomicCAS(&cn->err, 0, SYLT_ERR_NO_INVERSE) == 0) {
+                    cn->err_joint = j;
+                    cn->badk[0] = bad.c1.x; cn->badk[1] = bad.c2.x; cn->badk[2] = bad.c1.y; cn->badk[3] = bad.c2.y;
+                }
+                continue;
+            }
+            a.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
+            a.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
+            a.jp[j] = make_float2(pacc.x, pacc.y);
+            if (a.warm) {
+                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
+                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+            }
+        }
+        grid.sync();
+    }
+    if (*(volatile int*)&cn->err == SYLT_ERR_NO_INVERSE) return;
+
+    // ---- 5. iterations x (arbiter colours, joint colours)   (world.rs:132-140)
+    for (int it = 0; it < a.iterations; it++) {
+        for (int c = 0; c < ncolors; c++) {
+            for (int k = s_start[c] + tid; k < s_start[c + 1]; k += nth) {
+                int e = a.order[k];
+                int2 b = a.cur.bodies[e];
+                int2 mt = a.cur.meta[e];
+                float fr = a.cur.friction[e];
+                float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
+                Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
+                for (int q = 0; q < mt.x; q++) {
+                    int ci = mt.y + q;
+                    float4 ca = a.cur.ca[ci], cb = a.cur.cb[ci], cc = a.cur.cc[ci];
+                    ContactConst k0;
+                    k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
+                    k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
+                    float pn = cc.y, pt = cc.z;
+                    contact_apply(k0, fr, m1.x, m1.y, m2.x, m2.y, acc, pn, pt, v1, v2);
+                    if (acc) a.cur.cc[ci] = make_float4(cc.x, pn, pt, cc.w);
+                }
+                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
+                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+            }
+            grid.sync();
+        }
+        for (int c = 0; c < a.n_joint_colors; c++) {
+            for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
+                int j = a.jorder[k];
+                int2 b = a.jbodies[j];
+                float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
+                Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
+                float4 r = a.jr[j], mm = a.jm[j];
+                float2 bs = a.jbias[j], pa = a.jp[j];
+                JointConst jc;
+                jc.r1 = mk(r.x, r.y); jc.r2 = mk(r.z, r.w); jc.bias = mk(bs.x, bs.y);
+                jc.m = mk(mk(mm.x, mm.z), mk(mm.y, mm.w));
+                jc.softness = a.jparam[j].x;
+                V2 pacc = mk(pa.x, pa.y);
+                joint_apply(jc, m1.x, m1.y, m2.x, m2.y, pacc, v1, v2);
+                a.jp[j] = make_float2(pacc.x, pacc.y);
+                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
+                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+            }
+            grid.sync();
+        }
+    }
+
+    // ---- 6. integrate positions, clear forces (world.rs:143-150; static bodies too, quirk Q-16)
+    for (int i = tid; i < a.B; i += nth) {
+        float4 p = a.pose[i];
+        float4 v = __ldcg(&a.vel[i]);
+        V2 np = mk(p.x, p.y) + mk(v.x, v.y) * a.dt;
+        p.x = np.x; p.y = np.y;
+        p.z += v.z * a.dt;
+        a.pose[i] = p;
+        a.force[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+}
+
+__global__ void k_collide_pairs(int n, const SyltBodyDesc* A, const SyltBodyDesc* Bd, const float2* lverts, const int* loff,
+                                SyltContact* out, int cap, int* counts) {
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    const SyltBodyDesc a = A[p], b = Bd[p];
+    ContactOut o[MAX_MANIFOLD];
+    float ca = sylt_cosf(a.rotation), sa = sylt_sinf(a.rotation), cb = sylt_cosf(b.rotation), sb = sylt_sinf(b.rotation);
+    int m;
+    if (a.shape == SYLT_SHAPE_BOX && b.shape == SYLT_SHAPE_BOX) {
+        m = box_box(mk(a.x, a.y), ca, sa, mk(a.width_x, a.width_y), mk(b.x, b.y), cb, sb, mk(b.width_x, b.width_y), o);
+    } else {
+        V2 w0[MAX_POLY_VERTS], w1[MAX_POLY_VERTS];
+        int n0 = loff[4 * p + 1], n1 = loff[4 * p + 3];
+        M2 r0 = rot_cs(ca, sa), r1 = rot_cs(cb, sb);
+        for (int k = 0; k < n0; k++) { float2 l = lverts[loff[4 * p] + k]; w0[k] = r0 * mk(l.x, l.y) + mk(a.x, a.y); }
+        for (int k = 0; k < n1; k++) { float2 l = lverts[loff[4 * p + 2] + k]; w1[k] = r1 * mk(l.x, l.y) + mk(b.x, b.y); }
+        bool ovf = false;
+        m = poly_poly(w0, n0, w1, n1, o, &ovf);
+    }
+    counts[p] = m;
+    for (int k = 0; k < m && k < cap; k++) {
+        SyltContact c;
+        memset(&c, 0, sizeof c);
+        c.px = o[k].px; c.py = o[k].py; c.nx = o[k].nx; c.ny = o[k].ny; c.separation = o[k].sep;
+        c.in_edge_1 = o[k].feat & 0xff; c.out_edge_1 = (o[k].feat >> 8) & 0xff;
+        c.in_edge_2 = (o[k].feat >> 16) & 0xff; c.out_edge_2 = (o[k].feat >> 24) & 0xff;
+        out[(size_t)p * cap + k] = c;
+    }
+}
+
+__global__ void k_sincos(int n, const float* a, float* s, float* c) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) { c[i] = sylt_cosf(a[i]); s[i] = sylt_sinf(a[i]); }
+}
+
+}  // namespace
+
+// ====================================================================== host side
+struct HostJoint {
+    int b1, b2;
+    float la1x, la1y, la2x, la2y, softness, bias_factor;
+    int color;
+};
+
+struct SyltWorld {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float gx = 0, gy = 0;
+    uint32_t iterations = 10;
+    int accumulate = 1, warm = 0, poscorr = 1;  // World::new defaults (world.rs:38-42, quirk Q-4)
+    int64_t launches = 0;
+    int num_sms = 0, coop_blocks = 0;
+
+    // host mirror of construction-time data
+    std::vector<HostBody> hb;
+    std::vector<V2> hverts;
+    std::vector<SyltBodyState> pending;  // initial states of bodies not yet uploaded
+    std::vector<HostJoint> hj;
+    int uploaded = 0;        // bodies already on the device
+    bool class_dirty = true; // grid classification / flags need recomputing
+    bool joints_dirty = true;
+    bool any_poly = false;
+    int n_large = 0;
+    GridParams gp{1.0f, 1023};
+    int buckets = 1024;
+
+    // device state
+    DBuf<float4> pose, vel, force, mp, geom, aabb;
+    DBuf<float2> rotc, lverts;
+    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, cell_bodies, large, row_count, row_start;
+    DBuf<int4> cinfo;
+    DBuf<int2> pairs;
+    DBuf<unsigned long long> info, pscan, claim, spart64;
+    DBuf<int> spart32;
+    DBuf<float4> tmp_a;
+    DBuf<float2> tmp_b;
+    DBuf<unsigned> used;
+    DBuf<int> uncolored, prop, order;
+    DBuf<Counters> counters;
+    DBuf<int> tot32;
+    DBuf<unsigned long long> tot64;
+    // arbiters, double buffered
+    struct ArbBufs {
+        DBuf<int2> bodies, meta;
+        DBuf<int> partner, color, row_start;
+        DBuf<float> friction;
+        DBuf<float4> ca, cb, cc, cd;
+    } arb[2];
+    int cur = 0;             // index being built next
+    bool have_old = false;   // an arbiter set from a previous step/broad phase exists
+    int B_old = 0;
+    bool flags_stale = false, inflight = false, inflight_full = false;
+    // joints
+    DBuf<int2> jbodies;
+    DBuf<float4> jla, jr, jm;
+    DBuf<float2> jparam, jp, jbias;
+    DBuf<int> jorder, jcolor_start;
+    int n_joint_colors = 0;
+    std::vector<int> h_jorder;
+
+    int64_t cap_pairs = 0, cap_arb = 0, cap_con = 0;
+    int64_t user_pairs = 0, user_arb = 0, user_con = 0;
+    unsigned epoch = 1;
+    Counters last{};         // counters of the last completed step
+    bool have_last = false;
+    int sticky_err = 0;
+    uint32_t last_iterations = 0;
+    bool last_was_step = false;
+
+    ArbSet set(int k) {
+        ArbSet s;
+        ArbBufs& b = arb[k];
+        s.bodies = b.bodies.p; s.meta = b.meta.p; s.partner = b.partner.p; s.friction = b.friction.p; s.color = b.color.p;
+        s.row_start = b.row_start.p; s.ca = b.ca.p; s.cb = b.cb.p; s.cc = b.cc.p; s.cd = b.cd.p;
+        return s;
+    }
+};
+
+namespace {
+
+int use_device(SyltWorld* w) {
+    SYLT_CUDA(cudaSetDevice(w->device));
+    return SYLT_OK;
+}
+
+template <typename T>
+int run_scan(SyltWorld* w, const T* in, T* out, int n_bound, const int* n_dev, T* partial, T* total) {
+    int nb = (n_bound + SCAN_TILE - 1) / SCAN_TILE;
+    if (nb < 1) nb = 1;
+    k_scan_reduce<T><<<nb, SCAN_THREADS, 0, w->stream>>>(in, n_bound, n_dev, partial);
+    k_scan_partials<T><<<1, SCAN_THREADS, 0, w->stream>>>(partial, n_bound, n_dev, total);
+    k_scan_apply<T><<<nb, SCAN_THREADS, 0, w->stream>>>(in, out, n_bound, n_dev, partial, total);
+    w->launches += 3;
+    SYLT_CUDA(cudaGetLastError());
+    return SYLT_OK;
+}
+
+// Host-side greedy colouring of the (static) joint graph, in joint index order.
+void color_joints(SyltWorld* w) {
+    size_t J = w->hj.size();
+    std::vector<uint64_t> used(w->hb.size(), 0);
+    int ncol = 0;
+    for (size_t j = 0; j < J; j++) {
+        HostJoint& q = w->hj[j];
+        bool d1 = w->hb[(size_t)q.b1].inv_mass != 0.0f || w->hb[(size_t)q.b1].inv_moi != 0.0f;
+        bool d2 = w->hb[(size_t)q.b2].inv_mass != 0.0f || w->hb[(size_t)q.b2].inv_moi != 0.0f;
+        uint64_t m = (d1 ? used[(size_t)q.b1] : 0) | (d2 ? used[(size_t)q.b2] : 0);
+        int c = 0;
+        while (c < 63 && (m >> c) & 1) c++;
+        q.color = c;
+        if (d1) used[(size_t)q.b1] |= 1ull << c;
+        if (d2) used[(size_t)q.b2] |= 1ull << c;
+        ncol = std::max(ncol, c + 1);
+    }
+    w->n_joint_colors = J ? ncol : 0;
+    std::vector<int> start((size_t)w->n_joint_colors + 1, 0);
+    for (auto& q : w->hj) start[(size_t)q.color + 1]++;
+    for (int c = 0; c < w->n_joint_colors; c++) start[(size_t)c + 1] += start[(size_t)c];
+    w->h_jorder.assign(J, 0);
+    std::vector<int> fill(start.begin(), start.end());
+    for (size_t j = 0; j < J; j++) w->h_jorder[(size_t)fill[(size_t)w->hj[j].color]++] = (int)j;
+    // upload
+    w->jorder.ensure(J + 1);
+    w->jcolor_start.ensure((size_t)w->n_joint_colors + 2);
+    if (J) cudaMemcpyAsync(w->jorder.p, w->h_jorder.data(), J * sizeof(int), cudaMemcpyHostToDevice, w->stream);
+    cudaMemcpyAsync(w->jcolor_start.p, start.data(), start.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream);
+    cudaStreamSynchronize(w->stream);
+}
+
+// Upload newly added bodies / joints and (re)compute the static grid classification.
+int finish(SyltWorld* w);
+int flush(SyltWorld* w) {
+    int e = use_device(w);
+    if (e) return e;
+    if (w->inflight) finish(w);  // buffers may be reallocated below: drain the queue and read the counters first
+    const size_t B = w->hb.size();
+    if ((size_t)w->uploaded < B) {
+        const size_t keep = (size_t)w->uploaded, add = B - keep;
+        SYLT_CUDA(w->pose.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->vel.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->force.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->mp.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->geom.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->bflags_old.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->bflags.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->aabb.ensure(B));
+        SYLT_CUDA(w->rotc.ensure(B));
+        SYLT_CUDA(w->rank.ensure(B));
+        SYLT_CUDA(w->cinfo.ensure(B));
+        SYLT_CUDA(w->cell_bodies.ensure(B));
+        SYLT_CUDA(w->row_count.ensure(B + 1));
+        SYLT_CUDA(w->row_start.ensure(B + 2));
+        SYLT_CUDA(w->used.ensure(B));
+        SYLT_CUDA(w->large.ensure(B));
+        for (int k = 0; k < 2; k++) SYLT_CUDA(w->arb[k].row_start.ensure(B + 2, (size_t)w->B_old + 1, w->stream));
+        {   // claims: all ones == "no claim"
+            size_t oldcap = w->claim.cap;
+            SYLT_CUDA(w->claim.ensure(B * NC));
+            if (w->claim.cap != oldcap) SYLT_CUDA(cudaMemsetAsync(w->claim.p, 0xff, w->claim.cap * sizeof(unsigned long long), w->stream));
+        }
+        std::vector<float4> hp(add), hv(add), hf(add), hm(add), hg(add);
+        for (size_t k = 0; k < add; k++) {
+            const HostBody& b = w->hb[keep + k];
+            const SyltBodyState& s = w->pending[k];
+            hp[k] = make_float4(s.x, s.y, s.rotation, 0.0f);
+            hv[k] = make_float4(s.vx, s.vy, s.angular_velocity, 0.0f);
+            hf[k] = make_float4(s.fx, s.fy, s.torque, 0.0f);
+            hm[k] = make_float4(b.inv_mass, b.inv_moi, b.friction, 0.0f);
+            float off;
+            int o = b.vert_offset;
+            memcpy(&off, &o, 4);
+            hg[k] = make_float4(b.width_x, b.width_y, off, b.radius);
+        }
+        SYLT_CUDA(cudaMemcpyAsync(w->pose.p + keep, hp.data(), add * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaMemcpyAsync(w->vel.p + keep, hv.data(), add * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaMemcpyAsync(w->force.p + keep, hf.data(), add * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaMemcpyAsync(w->mp.p + keep, hm.data(), add * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaMemcpyAsync(w->geom.p + keep, hg.data(), add * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(w->lverts.ensure(w->hverts.size() + 1));
+        if (!w->hverts.empty())
+            SYLT_CUDA(cudaMemcpyAsync(w->lverts.p, w->hverts.data(), w->hverts.size() * sizeof(float2), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaStreamSynchronize(w->stream));
+        w->pending.clear();
+        w->uploaded = (int)B;
+        w->class_dirty = true;
+    }
+    if (w->class_dirty && B > 0) {
+        // static classification: cell = slightly more than the largest "small" bounding diameter; bodies above go to the large list
+        std::vector<float> d;
+        for (const HostBody& b : w->hb)
+            if (b.inv_mass != 0.0f) d.push_back(2.0f * b.radius);
+        float cell = 1.0f;
+        if (!d.empty()) {
+            std::vector<float> t = d;
+            std::nth_element(t.begin(), t.begin() + (long)(t.size() / 2), t.end());
+            float med = t[t.size() / 2], mx = 0.0f;
+            for (float x : d)
+                if (x <= 4.0f * med && x > mx) mx = x;
+            if (mx > 0.0f) cell = mx;
+        }
+        cell = 1.1f * cell + 0.1f;
+        std::vector<int> fl(B), large;
+        for (size_t i = 0; i < B; i++) {
+            const HostBody& b = w->hb[i];
+            int f = (b.shape == SYLT_SHAPE_POLYGON ? FLAG_POLY : 0) | (b.inv_mass == 0.0f ? FLAG_STATIC : 0) | (b.nverts << 8);
+            if (2.2f * b.radius + 0.1f > cell || !(b.radius == b.radius)) { f |= FLAG_LARGE; large.push_back((int)i); }
+            fl[i] = f;
+        }
+        w->n_large = (int)large.size();
+        int buckets = 1024;
+        while ((size_t)buckets < 2 * B) buckets <<= 1;
+        w->buckets = buckets;
+        w->gp.cell = cell;
+        w->gp.mask = buckets - 1;
+        SYLT_CUDA(w->cell_count.ensure((size_t)buckets + 1));
+        SYLT_CUDA(w->cell_start.ensure((size_t)buckets + 2));
+        size_t sp = ((size_t)std::max<size_t>(buckets, B + 1) + SCAN_TILE - 1) / SCAN_TILE + 1;
+        SYLT_CUDA(w->spart32.ensure(sp));
+        SYLT_CUDA(w->tot32.ensure(4));
+        SYLT_CUDA(w->tot64.ensure(4));
+        SYLT_CUDA(w->counters.ensure(1));
+        if (w->have_old && w->B_old > 0)  // keep the flags the last step used for the next arbiter match
+            SYLT_CUDA(cudaMemcpyAsync(w->bflags_old.p, w->bflags.p, (size_t)w->B_old * sizeof(int), cudaMemcpyDeviceToDevice, w->stream));
+        SYLT_CUDA(cudaMemcpyAsync(w->bflags.p, fl.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+        w->flags_stale = true;
+        if (!large.empty()) SYLT_CUDA(cudaMemcpyAsync(w->large.p, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+        // capacities
+        int64_t cp = w->user_pairs ? w->user_pairs : std::max<int64_t>(16 * (int64_t)B, 4096);
+        int64_t ca = w->user_arb ? w->user_arb : std::max<int64_t>(8 * (int64_t)B, 2048);
+        int64_t cc = w->user_con ? w->user_con : std::max<int64_t>(16 * (int64_t)B, 4096);
+        if (w->any_poly && !w->user_con) cc *= 2;
+        const int maxc = w->any_poly ? MAX_MANIFOLD : 2;
+        SYLT_CUDA(w->pairs.ensure((size_t)cp));
+        SYLT_CUDA(w->info.ensure((size_t)cp + 1));
+        SYLT_CUDA(w->pscan.ensure((size_t)cp + 2));
+        SYLT_CUDA(w->spart64.ensure((size_t)cp / SCAN_TILE + 2));
+        SYLT_CUDA(w->tmp_a.ensure((size_t)cp * maxc));
+        SYLT_CUDA(w->tmp_b.ensure((size_t)cp * maxc));
+        SYLT_CUDA(w->uncolored.ensure((size_t)ca));
+        SYLT_CUDA(w->prop.ensure((size_t)ca));
+        SYLT_CUDA(w->order.ensure((size_t)ca));
+        for (int k = 0; k < 2; k++) {
+            SyltWorld::ArbBufs& a = w->arb[k];
+            const bool keep_set = (k != w->cur) && w->have_old && w->have_last;  // last step's arbiters survive a regrow
+            size_t ka = keep_set ? (size_t)std::min<int64_t>(w->last.n_arb, w->cap_arb) : 0;
+            size_t kc = keep_set ? (size_t)std::min<int64_t>(w->last.n_con, w->cap_con) : 0;
+            SYLT_CUDA(a.bodies.ensure((size_t)ca, ka, w->stream));
+            SYLT_CUDA(a.meta.ensure((size_t)ca, ka, w->stream));
+            SYLT_CUDA(a.partner.ensure((size_t)ca, ka, w->stream));
+            SYLT_CUDA(a.color.ensure((size_t)ca, ka, w->stream));
+            SYLT_CUDA(a.friction.ensure((size_t)ca, ka, w->stream));
+            SYLT_CUDA(a.ca.ensure((size_t)cc, kc, w->stream));
+            SYLT_CUDA(a.cb.ensure((size_t)cc, kc, w->stream));
+            SYLT_CUDA(a.cc.ensure((size_t)cc, kc, w->stream));
+            SYLT_CUDA(a.cd.ensure((size_t)cc, kc, w->stream));
+        }
+        w->cap_pairs = (int64_t)std::min<size_t>(w->pairs.cap, (size_t)cp);
+        w->cap_arb = ca;
+        w->cap_con = cc;
+        SYLT_CUDA(cudaStreamSynchronize(w->stream));
+        w->class_dirty = false;
+    }
+    if (w->joints_dirty) {
+        size_t J = w->hj.size();
+        SYLT_CUDA(w->jbodies.ensure(J + 1));
+        SYLT_CUDA(w->jla.ensure(J + 1));
+        SYLT_CUDA(w->jparam.ensure(J + 1));
+        SYLT_CUDA(w->jr.ensure(J + 1));
+        SYLT_CUDA(w->jm.ensure(J + 1));
+        SYLT_CUDA(w->jbias.ensure(J + 1));
+        std::vector<int2> jb(J);
+        std::vector<float4> la(J);
+        std::vector<float2> pr(J);
+        for (size_t j = 0; j < J; j++) {
+            jb[j] = make_int2(w->hj[j].b1, w->hj[j].b2);
+            la[j] = make_float4(w->hj[j].la1x, w->hj[j].la1y, w->hj[j].la2x, w->hj[j].la2y);
+            pr[j] = make_float2(w->hj[j].softness, w->hj[j].bias_factor);
+        }
+        if (J) {
+            SYLT_CUDA(cudaMemcpyAsync(w->jbodies.p, jb.data(), J * sizeof(int2), cudaMemcpyHostToDevice, w->stream));
+            SYLT_CUDA(cudaMemcpyAsync(w->jla.p, la.data(), J * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+            SYLT_CUDA(cudaMemcpyAsync(w->jparam.p, pr.data(), J * sizeof(float2), cudaMemcpyHostToDevice, w->stream));
+        }
+        color_joints(w);
+        SYLT_CUDA(cudaStreamSynchronize(w->stream));
+        w->joints_dirty = false;
+    }
+    return SYLT_OK;
+}
+
+// Enqueue one step (or one broad phase only) on the stream.  No host synchronisation.
+int enqueue_step(SyltWorld* w, float dt, bool full_step) {
+    const int B = (int)w->hb.size();
+    cudaStream_t st = w->stream;
+    Counters* cn = w->counters.p;
+    SYLT_CUDA(cudaMemsetAsync(&cn->n_pairs, 0, sizeof(Counters) - offsetof(Counters, n_pairs), st));
+    if (B == 0) return SYLT_OK;
+    SYLT_CUDA(cudaMemsetAsync(w->cell_count.p, 0, (size_t)w->buckets * sizeof(int), st));
+    SYLT_CUDA(cudaMemsetAsync(w->used.p, 0, (size_t)B * sizeof(unsigned), st));
+    const int nbB = (B + 255) / 256;
+    k_prepare<<<nbB, 256, 0, st>>>(B, w->pose.p, w->vel.p, w->force.p, w->mp.p, w->geom.p, w->bflags.p, w->lverts.p, w->rotc.p, w->aabb.p,
+                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn);
+    w->launches++;
+    int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->tot32.p);
+    if (e) return e;
+    k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->rank.p, w->cell_start.p, w->cell_bodies.p, w->gp);
+    const int nbR = (B + 127) / 128;
+    k_rows<false><<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
+                                       w->row_count.p, nullptr, nullptr, 0, cn);
+    w->launches += 2;
+    e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->tot32.p + 1);
+    if (e) return e;
+    k_totals<<<1, 1, 0, st>>>(cn, w->tot32.p + 1, nullptr, 0, (int)w->cap_pairs);
+    k_rows<true><<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
+                                      nullptr, w->row_start.p, w->pairs.p, (int)w->cap_pairs, cn);
+    w->launches += 2;
+    const int gridP = w->num_sms * 8;
+    if (w->any_poly)
+        k_narrow<MAX_MANIFOLD><<<gridP, 128, 0, st>>>(cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p, w->lverts.p,
+                                                      w->info.p, w->tmp_a.p, w->tmp_b.p, cn);
+    else
+        k_narrow<2><<<gridP, 128, 0, st>>>(cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p, w->lverts.p,
+                                           w->info.p, w->tmp_a.p, w->tmp_b.p, cn);
+    w->launches++;
+    e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->tot64.p);
+    if (e) return e;
+    k_totals<<<1, 1, 0, st>>>(cn, nullptr, w->tot64.p, 1, 0);
+    ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
+    if (w->any_poly)
+        k_build<MAX_MANIFOLD><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p,
+                                                              w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p,
+                                                              w->bflags_old.p, cur, old, w->warm, w->used.p, w->uncolored.p);
+    else
+        k_build<2><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p, w->info.p,
+                                                   w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur,
+                                                   old, w->warm, w->used.p, w->uncolored.p);
+    w->launches += 2;
+    SYLT_CUDA(cudaGetLastError());
+
+    SolveArgs a;
+    memset(&a, 0, sizeof a);
+    a.cn = cn; a.B = B; a.cap_arb = (int)w->cap_arb; a.cap_con = (int)w->cap_con;
+    a.J = (int)w->hj.size(); a.n_joint_colors = w->n_joint_colors; a.iterations = (int)w->iterations;
+    a.accumulate = w->accumulate; a.warm = w->warm; a.poscorr = w->poscorr; a.run_solver = full_step ? 1 : 0;
+    a.dt = dt; a.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;  // world.rs:108
+    a.epoch_base = w->epoch;
+    w->epoch += MAX_ROUNDS;
+    if (w->epoch > 0xf0000000u) {  // wrap: forget all claims
+        SYLT_CUDA(cudaMemsetAsync(w->claim.p, 0xff, w->claim.cap * sizeof(unsigned long long), st));
+        w->epoch = 1;
+    }
+    a.pose = w->pose.p; a.vel = w->vel.p; a.force = w->force.p; a.mp = w->mp.p; a.rotc = w->rotc.p; a.bflags = w->bflags.p;
+    a.cur = cur; a.used = w->used.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.prop = w->prop.p; a.order = w->order.p;
+    a.jbodies = w->jbodies.p; a.jla = w->jla.p; a.jparam = w->jparam.p; a.jp = w->jp.p; a.jr = w->jr.p; a.jm = w->jm.p; a.jbias = w->jbias.p;
+    a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
+    void* args[] = {&a};
+    SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3(256), args, 0, st));
+    w->launches++;
+    // the set just built becomes "last step's"
+    w->cur ^= 1;
+    return SYLT_OK;
+}
+
+// After the queue drains: read the counters of the last step and update host-side bookkeeping.
+int finish(SyltWorld* w) {
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    if (!w->inflight) return w->have_last ? w->last.err : SYLT_OK;
+    SYLT_CUDA(cudaMemcpy(&w->last, w->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
+    w->inflight = false;
+    w->have_last = true;
+    w->last_was_step = w->inflight_full;
+    w->last_iterations = w->iterations;
+    return w->last.err;
+}
+
+int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
+    if (!w) return SYLT_ERR_INVALID;
+    int e = flush(w);
+    if (e) return e;
+    if (body_order_violated(w->hb)) return SYLT_ERR_BODY_ORDER;
+    if (!w->inflight) SYLT_CUDA(cudaMemsetAsync(w->counters.p, 0, offsetof(Counters, n_pairs), w->stream));  // sticky error fields
+    const int B = (int)w->hb.size();
+    for (int s = 0; s < n; s++) {
+        e = enqueue_step(w, dt, full);
+        if (e) return e;
+        w->inflight = true;
+        w->inflight_full = full;
+        if (B > 0) {
+            w->have_old = true;  // the set just built is what the next step matches against
+            w->B_old = B;
+            if (w->flags_stale) {  // the flags this step used become the "old" flags of the next one
+                SYLT_CUDA(cudaMemcpyAsync(w->bflags_old.p, w->bflags.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, w->stream));
+                w->flags_stale = false;
+            }
+        }
+    }
+    if (!wait) return SYLT_OK;
+    return finish(w);
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+const char* sylt_last_error_string(void) { return g_last_error.c_str(); }
+
+int sylt_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltWorld** out) {
+    if (!out) return SYLT_ERR_INVALID;
+    *out = nullptr;
+    int n = 0;
+    SYLT_CUDA(cudaGetDeviceCount(&n));
+    if (device < 0 || device >= n) { set_last_error("no such CUDA device"); return SYLT_ERR_CUDA; }
+    SYLT_CUDA(cudaSetDevice(device));
+    SyltWorld* w = new SyltWorld();
+    w->device = device; w->gx = gx; w->gy = gy; w->iterations = iterations;
+    cudaDeviceProp prop;
+    SYLT_CUDA(cudaGetDeviceProperties(&prop, device));
+    w->num_sms = prop.multiProcessorCount;
+    int coop = 0;
+    SYLT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) { delete w; set_last_error("device lacks cooperative launch"); return SYLT_ERR_CUDA; }
+    int per_sm = 0;
+    SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0));
+    if (per_sm < 1) { delete w; set_last_error("k_solve does not fit on an SM"); return SYLT_ERR_CUDA; }
+    w->coop_blocks = w->num_sms * std::min(per_sm, 2);
+    SYLT_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
+    SYLT_CUDA(cudaEventCreate(&w->ev0));
+    SYLT_CUDA(cudaEventCreate(&w->ev1));
+    SYLT_CUDA(w->counters.ensure(1));
+    SYLT_CUDA(cudaMemset(w->counters.p, 0, sizeof(Counters)));
+    *out = w;
+    return SYLT_OK;
+}
+
+static void free_all(SyltWorld* w) {
+    w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
+    w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
+    w->cell_count.release(); w->cell_start.release(); w->cell_bodies.release(); w->large.release(); w->row_count.release();
+    w->row_start.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
+    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->uncolored.release();
+    w->prop.release(); w->order.release(); w->tot32.release(); w->tot64.release();
+    for (int k = 0; k < 2; k++) {
+        auto& a = w->arb[k];
+        a.bodies.release(); a.meta.release(); a.partner.release(); a.color.release(); a.row_start.release(); a.friction.release();
+        a.ca.release(); a.cb.release(); a.cc.release(); a.cd.release();
+    }
+    w->jbodies.release(); w->jla.release(); w->jr.release(); w->jm.release(); w->jparam.release(); w->jp.release(); w->jbias.release();
+    w->jorder.release(); w->jcolor_start.release();
+}
+
+int sylt_world_destroy(SyltWorld* w) {
+    if (!w) return SYLT_OK;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    free_all(w);
+    w->counters.release();
+    cudaEventDestroy(w->ev0); cudaEventDestroy(w->ev1);
+    cudaStreamDestroy(w->stream);
+    delete w;
+    return SYLT_OK;
+}
+
+int sylt_world_clear(SyltWorld* w) {  // world.rs:67-71
+    if (!w) return SYLT_ERR_INVALID;
+    cudaSetDevice(w->device);
+    cudaStreamSynchronize(w->stream);
+    w->hb.clear(); w->hverts.clear(); w->pending.clear(); w->hj.clear(); w->h_jorder.clear();
+    w->uploaded = 0; w->class_dirty = true; w->joints_dirty = true; w->any_poly = false; w->n_large = 0;
+    w->have_old = false; w->B_old = 0; w->have_last = false; w->n_joint_colors = 0; w->inflight = false; w->flags_stale = false;
+    memset(&w->last, 0, sizeof w->last);
+    return SYLT_OK;
+}
+
+int sylt_world_set_context(SyltWorld* w, int acc, int warm, int pc) {
+    if (!w) return SYLT_ERR_INVALID;
+    w->accumulate = acc != 0; w->warm = warm != 0; w->poscorr = pc != 0;
+    return SYLT_OK;
+}
+int sylt_world_set_iterations(SyltWorld* w, uint32_t it) {
+    if (!w) return SYLT_ERR_INVALID;
+    w->iterations = it;
+    return SYLT_OK;
+}
+int sylt_world_set_capacity(SyltWorld* w, int64_t p, int64_t a, int64_t c) {
+    if (!w || p < 0 || a < 0 || c < 0) return SYLT_ERR_INVALID;
+    if (p) w->user_pairs = p;
+    if (a) w->user_arb = a;
+    if (c) w->user_con = c;
+    w->class_dirty = true;
+    return SYLT_OK;
+}
+
+int sylt_world_add_bodies(SyltWorld* w, const SyltBodyDesc* bodies, int32_t n, const float* verts_xy, int32_t n_verts) {
+    if (!w || n < 0 || (n > 0 && !bodies)) return SYLT_ERR_INVALID;
+    size_t b0 = w->hb.size(), v0 = w->hverts.size();
+    for (int i = 0; i < n; i++) {
+        HostBody hb;
+        int e = make_host_body(bodies[i], verts_xy, n_verts, &hb, &w->hverts);
+        if (e) { w->hb.resize(b0); w->hverts.resize(v0); w->pending.resize(b0 - (size_t)w->uploaded); return e; }
+        if (hb.shape == SYLT_SHAPE_POLYGON) w->any_poly = true;
+        w->hb.push_back(hb);
+        SyltBodyState s = {bodies[i].x, bodies[i].y, bodies[i].rotation, bodies[i].vx, bodies[i].vy, bodies[i].angular_velocity, 0.0f, 0.0f, 0.0f};
+        w->pending.push_back(s);
+    }
+    return SYLT_OK;
+}
+int sylt_world_add_box(SyltWorld* w, uint64_t id, float wx, float wy, float mass, float friction, float x, float y, float rot,
+                       float vx, float vy, float om, int32_t* out_index) {
+    SyltBodyDesc d;
+    memset(&d, 0, sizeof d);
+    d.id = id; d.shape = SYLT_SHAPE_BOX; d.width_x = wx; d.width_y = wy; d.mass = mass; d.friction = friction;
+    d.x = x; d.y = y; d.rotation = rot; d.vx = vx; d.vy = vy; d.angular_velocity = om;
+    int e = sylt_world_add_bodies(w, &d, 1, nullptr, 0);
+    if (!e && out_index) *out_index = (int32_t)w->hb.size() - 1;
+    return e;
+}
+int sylt_world_add_polygon(SyltWorld* w, uint64_t id, const float* verts_xy, int32_t nv, float mass, float friction, float x, float y,
+                           float rot, float vx, float vy, float om, int32_t* out_index) {
+    SyltBodyDesc d;
+    memset(&d, 0, sizeof d);
+    d.id = id; d.shape = SYLT_SHAPE_POLYGON; d.vert_offset = 0; d.vert_count = nv; d.mass = mass; d.friction = friction;
+    d.x = x; d.y = y; d.rotation = rot; d.vx = vx; d.vy = vy; d.angular_velocity = om;
+    int e = sylt_world_add_bodies(w, &d, 1, verts_xy, nv);
+    if (!e && out_index) *out_index = (int32_t)w->hb.size() - 1;
+    return e;
+}
+
+static int find_body(SyltWorld* w, uint64_t id) {  // joint.rs:27-36: first body with this id
+    for (size_t i = 0; i < w->hb.size(); i++)
+        if (w->hb[i].id == id) return (int)i;
+    return -1;
+}
+
+static int add_joint_impl(SyltWorld* w, const SyltJointDesc& d, const std::vector<SyltBodyState>* states) {
+    int b1 = find_body(w, d.id1), b2 = find_body(w, d.id2);
+    if (b1 < 0 || b2 < 0) return SYLT_ERR_BODY_NOT_FOUND;
+    const SyltBodyState& s1 = (*states)[(size_t)b1];
+    const SyltBodyState& s2 = (*states)[(size_t)b2];
+    // Joint::new (joint.rs:37-40): local anchors from the bodies' current pose
+    M2 rt1 = transpose(rot_angle(s1.rotation)), rt2 = transpose(rot_angle(s2.rotation));
+    V2 anchor = mk(d.anchor_x, d.anchor_y);
+    V2 la1 = rt1 * (anchor - mk(s1.x, s1.y)), la2 = rt2 * (anchor - mk(s2.x, s2.y));
+    HostJoint j = {b1, b2, la1.x, la1.y, la2.x, la2.y, d.softness, d.bias_factor, 0};
+    w->hj.push_back(j);
+    return SYLT_OK;
+}
+
+int sylt_world_get_bodies(SyltWorld* w, SyltBodyState* out, int32_t cap);
+
+int sylt_world_add_joints(SyltWorld* w, const SyltJointDesc* joints, int32_t n) {
+    if (!w || n < 0 || (n > 0 && !joints)) return SYLT_ERR_INVALID;
+    if (n == 0) return SYLT_OK;
+    // current poses: device state for uploaded bodies, pending states for the rest
+    std::vector<SyltBodyState> st(w->hb.size());
+    if (w->uploaded > 0) {
+        int e = sylt_world_get_bodies(w, st.data(), w->uploaded);
+        if (e < 0) return -e;
+    }
+    for (size_t k = 0; k < w->pending.size(); k++) st[(size_t)w->uploaded + k] = w->pending[k];
+    size_t j0 = w->hj.size();
+    for (int i = 0; i < n; i++) {
+        int e = add_joint_impl(w, joints[i], &st);
+        if (e) { w->hj.resize(j0); return e; }
+    }
+    // accumulated impulses of the new joints start at zero; existing ones are kept
+    cudaSetDevice(w->device);
+    size_t J = w->hj.size();
+    SYLT_CUDA(w->jp.ensure(J + 1, j0, w->stream));
+    SYLT_CUDA(cudaMemsetAsync(w->jp.p + j0, 0, (J - j0) * sizeof(float2), w->stream));
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    w->joints_dirty = true;
+    return SYLT_OK;
+}
+int sylt_world_add_joint(SyltWorld* w, uint64_t id1, uint64_t id2, float ax, float ay, int32_t* out_index) {
+    SyltJointDesc d = {id1, id2, ax, ay, 0.0f, 0.2f};  // joint.rs:47-48 defaults
+    int e = sylt_world_add_joints(w, &d, 1);
+    if (!e && out_index) *out_index = (int32_t)w->hj.size() - 1;
+    return e;
+}
+int sylt_world_set_joint_params(SyltWorld* w, int32_t j, float softness, float bias_factor) {
+    if (!w || j < 0 || (size_t)j >= w->hj.size()) return SYLT_ERR_INVALID;
+    w->hj[(size_t)j].softness = softness;
+    w->hj[(size_t)j].bias_factor = bias_factor;
+    w->joints_dirty = true;
+    return SYLT_OK;
+}
+
+int sylt_world_add_force(SyltWorld* w, int32_t body, float fx, float fy) {  // body.rs:286-288
+    if (!w || body < 0 || (size_t)body >= w->hb.size()) return SYLT_ERR_INVALID;
+    if (body >= w->uploaded) {
+        SyltBodyState& s = w->pending[(size_t)(body - w->uploaded)];
+        s.fx = s.fx + fx; s.fy = s.fy + fy;
+        return SYLT_OK;
+    }
+    cudaSetDevice(w->device);
+    float4 f;
+    SYLT_CUDA(cudaMemcpyAsync(&f, w->force.p + body, sizeof f, cudaMemcpyDeviceToHost, w->stream));
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    f.x = f.x + fx; f.y = f.y + fy;
+    SYLT_CUDA(cudaMemcpyAsync(w->force.p + body, &f, sizeof f, cudaMemcpyHostToDevice, w->stream));
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    return SYLT_OK;
+}
+
+int sylt_world_num_bodies(SyltWorld* w) { return w ? (int)w->hb.size() : 0; }
+int sylt_world_num_joints(SyltWorld* w) { return w ? (int)w->hj.size() : 0; }
+int sylt_world_num_arbiters(SyltWorld* w) { return (w && w->have_last) ? (int)std::min<int64_t>(w->last.n_arb, w->cap_arb) : 0; }
+int sylt_world_num_contacts(SyltWorld* w) { return (w && w->have_last) ? (int)std::min<int64_t>(w->last.n_con, w->cap_con) : 0; }
+
+int sylt_world_get_bodies(SyltWorld* w, SyltBodyState* out, int32_t cap) {
+    if (!w || (!out && cap > 0)) return -SYLT_ERR_INVALID;
+    int n = std::min<int>(cap, (int)w->hb.size());
+    int nd = std::min(n, w->uploaded);
+    if (nd > 0) {
+        if (cudaSetDevice(w->device) != cudaSuccess) return -SYLT_ERR_CUDA;
+        std::vector<float4> p((size_t)nd), v((size_t)nd), f((size_t)nd);
+        cudaError_t e = cudaMemcpyAsync(p.data(), w->pose.p, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(v.data(), w->vel.p, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(f.data(), w->force.p, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
+        if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -SYLT_ERR_CUDA; }
+        for (int i = 0; i < nd; i++) {
+            SyltBodyState s = {p[(size_t)i].x, p[(size_t)i].y, p[(size_t)i].z, v[(size_t)i].x, v[(size_t)i].y, v[(size_t)i].z,
+                               f[(size_t)i].x, f[(size_t)i].y, f[(size_t)i].z};
+            out[i] = s;
+        }
+    }
+    for (int i = nd; i < n; i++) out[i] = w->pending[(size_t)(i - w->uploaded)];
+    return n;
+}
+
+int sylt_world_set_bodies(SyltWorld* w, int32_t first, int32_t count, const SyltBodyState* in) {
+    if (!w || first < 0 || count < 0 || (size_t)first + (size_t)count > w->hb.size() || (count > 0 && !in)) return SYLT_ERR_INVALID;
+    int e = flush(w);
+    if (e) return e;
+    std::vector<float4> p((size_t)count), v((size_t)count), f((size_t)count);
+    for (int i = 0; i < count; i++) {
+        p[(size_t)i] = make_float4(in[i].x, in[i].y, in[i].rotation, 0.0f);
+        v[(size_t)i] = make_float4(in[i].vx, in[i].vy, in[i].angular_velocity, 0.0f);
+        f[(size_t)i] = make_float4(in[i].fx, in[i].fy, in[i].torque, 0.0f);
+    }
+    if (count) {
+        SYLT_CUDA(cudaMemcpyAsync(w->pose.p + first, p.data(), (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaMemcpyAsync(w->vel.p + first, v.data(), (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaMemcpyAsync(w->force.p + first, f.data(), (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+        SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    }
+    return SYLT_OK;
+}
+
+int sylt_world_get_body_props(SyltWorld* w, float* o, int32_t cap) {
+    if (!w) return -SYLT_ERR_INVALID;
+    int n = std::min<int>(cap, (int)w->hb.size());
+    for (int i = 0; i < n; i++) {
+        const HostBody& b = w->hb[(size_t)i];
+        float* p = o + 8 * i;
+        p[0] = b.mass; p[1] = b.inv_mass; p[2] = b.moi; p[3] = b.inv_moi; p[4] = b.width_x; p[5] = b.width_y; p[6] = b.friction; p[7] = (float)b.shape;
+    }
+    return n;
+}
+
+int sylt_world_get_arbiters(SyltWorld* w, SyltArbiterInfo* arbiters, int32_t arbiter_cap, SyltContact* contacts, int32_t contact_cap) {
+    if (!w) return -SYLT_ERR_INVALID;
+    int A = sylt_world_num_arbiters(w), Cn = sylt_world_num_contacts(w);
+    if (A > arbiter_cap || Cn > contact_cap) return -SYLT_ERR_CAPACITY;
+    if (A == 0) return 0;
+    if (cudaSetDevice(w->device) != cudaSuccess) return -SYLT_ERR_CUDA;
+    SyltWorld::ArbBufs& ab = w->arb[w->cur ^ 1];  // last completed step
+    std::vector<int2> bodies((size_t)A), meta((size_t)A);
+    std::vector<float> fr((size_t)A);
+    std::vector<int> col((size_t)A);
+    std::vector<float4> ca((size_t)Cn), cb((size_t)Cn), cc((size_t)Cn), cd((size_t)Cn);
+    cudaMemcpyAsync(bodies.data(), ab.bodies.p, (size_t)A * sizeof(int2), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(meta.data(), ab.meta.p, (size_t)A * sizeof(int2), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(fr.data(), ab.friction.p, (size_t)A * sizeof(float), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(col.data(), ab.color.p, (size_t)A * sizeof(int), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(ca.data(), ab.ca.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(cb.data(), ab.cb.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(cc.data(), ab.cc.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(cd.data(), ab.cd.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+    cudaError_t e = cudaStreamSynchronize(w->stream);
+    if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -SYLT_ERR_CUDA; }
+    std::vector<int> idx((size_t)A);
+    for (int i = 0; i < A; i++) idx[(size_t)i] = i;
+    std::sort(idx.begin(), idx.end(), [&](int x, int y) {
+        const int2 &a = bodies[(size_t)x], &b = bodies[(size_t)y];
+        return a.x != b.x ? a.x < b.x : a.y < b.y;
+    });
+    const bool zero_r = !w->last_was_step || w->last_iterations == 0;  // r1/r2 are only stored by apply_impulse (arbiter.rs:236-237)
+    int co = 0;
+    for (int k = 0; k < A; k++) {
+        int a = idx[(size_t)k];
+        SyltArbiterInfo& o = arbiters[k];
+        o.body1 = bodies[(size_t)a].x; o.body2 = bodies[(size_t)a].y;
+        o.id1 = w->hb[(size_t)o.body1].id; o.id2 = w->hb[(size_t)o.body2].id;
+        o.friction = fr[(size_t)a]; o.num_contacts = meta[(size_t)a].x; o.contact_offset = co; o.color = col[(size_t)a];
+        for (int q = 0; q < meta[(size_t)a].x; q++) {
+            size_t ci = (size_t)(meta[(size_t)a].y + q);
+            SyltContact& c = contacts[co++];
+            c.px = cd[ci].x; c.py = cd[ci].y; c.nx = ca[ci].x; c.ny = ca[ci].y;
+            c.r1x = zero_r ? 0.0f : ca[ci].z; c.r1y = zero_r ? 0.0f : ca[ci].w; c.r2x = zero_r ? 0.0f : cb[ci].x; c.r2y = zero_r ? 0.0f : cb[ci].y;
+            c.separation = cc[ci].w; c.pn = cc[ci].y; c.pt = cc[ci].z; c.pnb = cd[ci].z;
+            c.mass_normal = cb[ci].z; c.mass_tangent = cb[ci].w; c.bias = cc[ci].x;
+            uint32_t ft;
+            memcpy(&ft, &cd[ci].w, 4);
+            c.in_edge_1 = ft & 0xff; c.out_edge_1 = (ft >> 8) & 0xff; c.in_edge_2 = (ft >> 16) & 0xff; c.out_edge_2 = (ft >> 24) & 0xff;
+            c.feature_value = 0;
+        }
+    }
+    return A;
+}
+
+int sylt_world_get_joints(SyltWorld* w, SyltJointState* out, int32_t cap) {
+    if (!w) return -SYLT_ERR_INVALID;
+    int e = flush(w);
+    if (e) return -e;
+    int J = std::min<int>(cap, (int)w->hj.size());
+    if (J == 0) return 0;
+    std::vector<float2> p((size_t)J), bs((size_t)J);
+    std::vector<float4> r((size_t)J), m((size_t)J);
+    cudaMemcpyAsync(p.data(), w->jp.p, (size_t)J * sizeof(float2), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(bs.data(), w->jbias.p, (size_t)J * sizeof(float2), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(r.data(), w->jr.p, (size_t)J * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+    cudaMemcpyAsync(m.data(), w->jm.p, (size_t)J * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+    cudaError_t ce = cudaStreamSynchronize(w->stream);
+    if (ce != cudaSuccess) { set_last_error(cudaGetErrorString(ce)); return -SYLT_ERR_CUDA; }
+    const bool stepped = w->have_last && w->last_was_step;
+    for (int j = 0; j < J; j++) {
+        const HostJoint& h = w->hj[(size_t)j];
+        SyltJointState s;
+        memset(&s, 0, sizeof s);
+        if (stepped) {
+            s.px = p[(size_t)j].x; s.py = p[(size_t)j].y; s.bias_x = bs[(size_t)j].x; s.bias_y = bs[(size_t)j].y;
+            s.r1x = r[(size_t)j].x; s.r1y = r[(size_t)j].y; s.r2x = r[(size_t)j].z; s.r2y = r[(size_t)j].w;
+            s.m11 = m[(size_t)j].x; s.m12 = m[(size_t)j].y; s.m21 = m[(size_t)j].z; s.m22 = m[(size_t)j].w;
+        }
+        s.bias_factor = h.bias_factor; s.softness = h.softness; s.la1x = h.la1x; s.la1y = h.la1y; s.la2x = h.la2x; s.la2y = h.la2y;
+        s.body1 = h.b1; s.body2 = h.b2;
+        out[j] = s;
+    }
+    return J;
+}
+
+int sylt_world_get_joint_order(SyltWorld* w, int32_t* out, int32_t cap) {
+    if (!w) return -SYLT_ERR_INVALID;
+    int e = flush(w);
+    if (e) return -e;
+    int J = std::min<int>(cap, (int)w->h_jorder.size());
+    for (int j = 0; j < J; j++) out[j] = w->h_jorder[(size_t)j];
+    return J;
+}
+
+int sylt_world_get_stats(SyltWorld* w, SyltStepStats* o) {
+    if (!w || !o) return SYLT_ERR_INVALID;
+    memset(o, 0, sizeof *o);
+    o->bodies = (int)w->hb.size();
+    o->joints = (int)w->hj.size();
+    o->joint_colors = w->n_joint_colors;
+    if (w->have_last) {
+        o->candidate_pairs = w->last.n_pairs; o->arbiters = w->last.n_arb; o->contacts = w->last.n_con;
+        o->colors = w->last.n_colors; o->color_rounds = w->last.rounds;
+    }
+    return SYLT_OK;
+}
+
+int sylt_world_last_error_matrix(SyltWorld* w, float* o) {
+    if (!w || !o) return -1;
+    for (int k = 0; k < 4; k++) o[k] = w->last.badk[k];
+    return w->last.err == SYLT_ERR_NO_INVERSE ? w->last.err_joint : -1;
+}
+
+int sylt_world_broad_phase(SyltWorld* w) { return do_steps(w, 0.0f, 1, false, true); }
+int sylt_world_step(SyltWorld* w, float dt) { return do_steps(w, dt, 1, true, true); }
+int sylt_world_step_n(SyltWorld* w, float dt, int32_t n) { return n < 0 ? SYLT_ERR_INVALID : (n == 0 ? SYLT_OK : do_steps(w, dt, n, true, true)); }
+int sylt_world_step_n_async(SyltWorld* w, float dt, int32_t n) { return n < 0 ? SYLT_ERR_INVALID : (n == 0 ? SYLT_OK : do_steps(w, dt, n, true, false)); }
+int sylt_world_sync(SyltWorld* w) {
+    if (!w) return SYLT_ERR_INVALID;
+    if (cudaSetDevice(w->device) != cudaSuccess) return SYLT_ERR_CUDA;
+    return finish(w);
+}
+int sylt_world_timer_start(SyltWorld* w) {
+    if (!w) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(w->device));
+    SYLT_CUDA(cudaEventRecord(w->ev0, w->stream));
+    return SYLT_OK;
+}
+int sylt_world_timer_stop(SyltWorld* w, float* ms) {
+    if (!w || !ms) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(w->device));
+    SYLT_CUDA(cudaEventRecord(w->ev1, w->stream));
+    SYLT_CUDA(cudaEventSynchronize(w->ev1));
+    SYLT_CUDA(cudaEventElapsedTime(ms, w->ev0, w->ev1));
+    return SYLT_OK;
+}
+int64_t sylt_world_launch_count(SyltWorld* w) { return w ? w->launches : 0; }
+
+int sylt_collide_pairs(int device, const SyltBodyDesc* a, const SyltBodyDesc* b, int32_t n, const float* verts_xy, int32_t n_verts,
+                       SyltContact* out, int32_t cap, int32_t* out_counts) {
+    if (n < 0 || cap < 0 || (n > 0 && (!a || !b || !out || !out_counts))) return SYLT_ERR_INVALID;
+    if (n == 0) return SYLT_OK;
+    SYLT_CUDA(cudaSetDevice(device));
+    std::vector<V2> lv;
+    std::vector<int> loff((size_t)n * 4);
+    for (int i = 0; i < n; i++) {
+        HostBody ha, hb2;
+        int e = make_host_body(a[i], verts_xy, n_verts, &ha, &lv);
+        if (e) return e;
+        e = make_host_body(b[i], verts_xy, n_verts, &hb2, &lv);
+        if (e) return e;
+        loff[(size_t)i * 4] = ha.vert_offset; loff[(size_t)i * 4 + 1] = ha.nverts;
+        loff[(size_t)i * 4 + 2] = hb2.vert_offset; loff[(size_t)i * 4 + 3] = hb2.nverts;
+    }
+    SyltBodyDesc *da = nullptr, *db = nullptr;
+    float2* dl = nullptr;
+    int *dof = nullptr, *dcnt = nullptr;
+    SyltContact* dout = nullptr;
+    SYLT_CUDA(cudaMalloc(&da, (size_t)n * sizeof *da));
+    SYLT_CUDA(cudaMalloc(&db, (size_t)n * sizeof *db));
+    SYLT_CUDA(cudaMalloc(&dl, (lv.size() + 1) * sizeof(float2)));
+    SYLT_CUDA(cudaMalloc(&dof, loff.size() * sizeof(int)));
+    SYLT_CUDA(cudaMalloc(&dcnt, (size_t)n * sizeof(int)));
+    SYLT_CUDA(cudaMalloc(&dout, ((size_t)n * cap + 1) * sizeof(SyltContact)));
+    SYLT_CUDA(cudaMemcpy(da, a, (size_t)n * sizeof *da, cudaMemcpyHostToDevice));
+    SYLT_CUDA(cudaMemcpy(db, b, (size_t)n * sizeof *db, cudaMemcpyHostToDevice));
+    if (!lv.empty()) SYLT_CUDA(cudaMemcpy(dl, lv.data(), lv.size() * sizeof(float2), cudaMemcpyHostToDevice));
+    SYLT_CUDA(cudaMemcpy(dof, loff.data(), loff.size() * sizeof(int), cudaMemcpyHostToDevice));
+    k_collide_pairs<<<(n + 127) / 128, 128>>>(n, da, db, dl, dof, dout, cap, dcnt);
+    SYLT_CUDA(cudaGetLastError());
+    SYLT_CUDA(cudaMemcpy(out_counts, dcnt, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    SYLT_CUDA(cudaMemcpy(out, dout, (size_t)n * cap * sizeof(SyltContact), cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(db); cudaFree(dl); cudaFree(dof); cudaFree(dcnt); cudaFree(dout);
+    return SYLT_OK;
+}
+
+int sylt_sincos(int device, const float* angles, int32_t n, float* out_sin, float* out_cos) {
+    if (n < 0 || (n > 0 && (!angles || !out_sin || !out_cos))) return SYLT_ERR_INVALID;
+    if (n == 0) return SYLT_OK;
+    SYLT_CUDA(cudaSetDevice(device));
+    float *da, *ds, *dc;
+    SYLT_CUDA(cudaMalloc(&da, (size_t)n * 4));
+    SYLT_CUDA(cudaMalloc(&ds, (size_t)n * 4));
+    SYLT_CUDA(cudaMalloc(&dc, (size_t)n * 4));
+    SYLT_CUDA(cudaMemcpy(da, angles, (size_t)n * 4, cudaMemcpyHostToDevice));
+    k_sincos<<<(n + 255) / 256, 256>>>(n, da, ds, dc);
+    SYLT_CUDA(cudaGetLastError());
+    SYLT_CUDA(cudaMemcpy(out_sin, ds, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    SYLT_CUDA(cudaMemcpy(out_cos, dc, (size_t)n * 4, cudaMemcpyDeviceToHost));
+    cudaFree(da); cudaFree(ds); cudaFree(dc);
+    return SYLT_OK;
+}
+
+}  // extern "C"

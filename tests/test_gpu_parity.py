@@ -1,0 +1,431 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Gates:
+  * arbiter key set + per-key contact count after the broad phase: bit-exact vs the oracle's all-pairs loop
+  * contacts (position / normal / separation / feature edges) from identical state: bit-exact (tolerance 0;
+    the north star allows 1e-5)
+  * single-step and multi-step solver output, oracle replaying the GPU's colour order: bit-exact (tolerance 0;
+    the north star allows a stated tolerance)
+  * colour order vs canonical (id1,id2) order: stated looser tolerance + long-run penetration / energy
+"""
+import numpy as np
+import pytest
+
+from oracle import orc
+from sylt2d_b200 import scenes
+
+pytestmark = pytest.mark.gpu
+
+STATE_FIELDS = ("x", "y", "rotation", "vx", "vy", "angular_velocity")
+CONTACT_GEOM = ("px", "py", "nx", "ny", "separation", "in_edge_1", "out_edge_1", "in_edge_2", "out_edge_2")
+CONTACT_SOLVE = ("pn", "pt", "pnb", "mass_normal", "mass_tangent", "bias", "r1x", "r1y", "r2x", "r2y")
+
+
+def _mk(scene, **kw):
+    from sylt2d_b200 import World
+    w = World(scene.gravity, scene.iterations, device=0)
+    w.load_scene(scene)
+    o = orc.OracleWorld(scene.gravity, scene.iterations, sincos_mode=1)
+    o.load_scene(scene)
+    return w, o
+
+
+def _assert_states_equal(g, r, what=""):
+    for f in STATE_FIELDS:
+        bad = np.nonzero(~((g[f] == r[f]) | (np.isnan(g[f]) & np.isnan(r[f]))))[0]
+        assert bad.size == 0, f"{what}: field {f} differs at bodies {bad[:8]}: gpu {g[f][bad[:4]]} oracle {r[f][bad[:4]]}"
+
+
+def _assert_arbiters_equal(w, o, solve_fields=True, what=""):
+    ga, gc = w.get_arbiters()
+    ra, rc = o.get_arbiters()
+    assert ga.shape[0] == ra.shape[0], f"{what}: arbiter count {ga.shape[0]} vs oracle {ra.shape[0]}"
+    assert np.array_equal(ga["id1"], ra["id1"]) and np.array_equal(ga["id2"], ra["id2"]), f"{what}: arbiter key sets differ"
+    assert np.array_equal(ga["num_contacts"], ra["num_contacts"]), f"{what}: contact counts differ"
+    assert np.array_equal(ga["friction"], ra["friction"]), f"{what}: friction differs"
+    for f in CONTACT_GEOM + (CONTACT_SOLVE if solve_fields else ()):
+        ok = (gc[f] == rc[f]) | (np.isnan(gc[f].astype(np.float64)) & np.isnan(rc[f].astype(np.float64)))
+        assert ok.all(), f"{what}: contact field {f} differs at {np.nonzero(~ok)[0][:6]}: {gc[f][~ok][:4]} vs {rc[f][~ok][:4]}"
+    return ga
+
+
+def _run_lockstep(scene, steps, check_every=1, ctx=None):
+    w, o = _mk(scene)
+    if ctx is not None:
+        from sylt2d_b200 import WorldContext
+        w.world_context = WorldContext(*ctx)
+        o.set_context(*ctx)
+    for s in range(steps):
+        w.step(scene.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(scene.dt, keys, jo)
+        if s % check_every == 0 or s == steps - 1:
+            _assert_states_equal(w.get_bodies(), o.get_bodies(), f"{scene.name} step {s}")
+            ga = _assert_arbiters_equal(w, o, what=f"{scene.name} step {s}")
+            # a proper colouring: no two arbiters of one colour share a dynamic body
+            props = w.get_body_props()
+            for c in np.unique(ga["color"]):
+                sel = ga[ga["color"] == c]
+                b = np.concatenate([sel["body1"], sel["body2"]])
+                b = b[props[b, 1] != 0.0]
+                assert np.unique(b).size == b.size, f"colour {c} is not an independent set"
+    gj, rj = w.get_joints(), o.get_joints()
+    for f in gj.dtype.names:
+        assert np.array_equal(gj[f], rj[f]), f"{scene.name}: joint field {f} differs"
+    return w, o
+
+
+def test_device_sincos_matches_host_bitwise():
+    import ctypes as C
+    from sylt2d_b200 import device_sincos
+    rng = np.random.default_rng(0)
+    a = np.concatenate([rng.uniform(-10, 10, 200000), rng.uniform(-1e4, 1e4, 100000), rng.uniform(-1e-3, 1e-3, 1000),
+                        np.array([0.0, -0.0, 0.75, 0.785398, 119.99, 120.0, 121.0, 1e6, -1e6, 3.4e38, 1e-40, np.pi, -np.pi / 2])]).astype(np.float32)
+    s, c = device_sincos(a)
+    L = orc.lib()
+    hs, hc = np.zeros_like(a), np.zeros_like(a)
+    ss, cc = C.c_float(), C.c_float()
+    for i in range(0, a.shape[0], 7):  # subsample for speed
+        L.orc_sincos(1, float(a[i]), C.byref(ss), C.byref(cc))
+        hs[i], hc[i] = ss.value, cc.value
+    idx = np.arange(0, a.shape[0], 7)
+    assert np.array_equal(s[idx].view(np.uint32), hs[idx].view(np.uint32))
+    assert np.array_equal(c[idx].view(np.uint32), hc[idx].view(np.uint32))
+
+
+def _desc(shape, w=(0, 0), pos=(0, 0), rot=0.0, voff=0, vcnt=0):
+    d = np.zeros(1, dtype=scenes.BODY_DESC)
+    d["id"], d["shape"], d["vert_offset"], d["vert_count"] = 1, shape, voff, vcnt
+    d["width_x"], d["width_y"], d["mass"], d["x"], d["y"], d["rotation"] = w[0], w[1], 1.0, pos[0], pos[1], rot
+    return d
+
+
+def test_narrow_phase_boxes_bit_exact():
+    from sylt2d_b200 import collide_pairs
+    rng = np.random.default_rng(3)
+    n = 4000
+    A = np.zeros(n, dtype=scenes.BODY_DESC)
+    B = np.zeros(n, dtype=scenes.BODY_DESC)
+    for D in (A, B):
+        D["mass"] = 1.0
+        D["width_x"], D["width_y"] = rng.uniform(0.3, 3.0, n), rng.uniform(0.3, 3.0, n)
+        D["rotation"] = rng.uniform(-7, 7, n)
+    A["x"], A["y"] = rng.uniform(-50, 50, n), rng.uniform(-50, 50, n)
+    B["x"], B["y"] = A["x"] + rng.uniform(-2.5, 2.5, n), A["y"] + rng.uniform(-2.5, 2.5, n)
+    out, cnt = collide_pairs(A, B, cap=4)
+    hits = 0
+    for i in range(n):
+        exp = orc.collide_pair(dict(shape=0, width=(A["width_x"][i], A["width_y"][i]), pos=(A["x"][i], A["y"][i]), rot=A["rotation"][i]),
+                               dict(shape=0, width=(B["width_x"][i], B["width_y"][i]), pos=(B["x"][i], B["y"][i]), rot=B["rotation"][i]),
+                               sincos_mode=1)
+        assert cnt[i] == len(exp), i
+        for f in CONTACT_GEOM:
+            assert np.array_equal(out[i, :cnt[i]][f], exp[f]), (i, f)
+        hits += cnt[i] > 0
+    assert hits > 500
+
+
+def test_narrow_phase_polygons_bit_exact():
+    from sylt2d_b200 import collide_pairs
+    rng = np.random.default_rng(5)
+    n = 1500
+    verts, A, B = [], np.zeros(n, dtype=scenes.BODY_DESC), np.zeros(n, dtype=scenes.BODY_DESC)
+    nv = 0
+    descs = []
+    for i in range(n):
+        pa = rng.uniform(-20, 20, 2)
+        pb = pa + rng.uniform(-1.5, 1.5, 2)
+        pair = []
+        for D, p, force_poly in ((A, pa, True), (B, pb, i % 3 != 0)):
+            D["mass"][i], D["x"][i], D["y"][i], D["rotation"][i] = 1.0, p[0], p[1], rng.uniform(-7, 7)
+            if force_poly:
+                k = int(rng.integers(3, 9))
+                ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+                r = rng.uniform(0.4, 1.2)
+                v = np.stack([r * np.cos(ang), r * np.sin(ang)], 1).astype(np.float32)
+                D["shape"][i], D["vert_offset"][i], D["vert_count"][i] = 1, nv, k
+                verts.append(v)
+                nv += k
+                pair.append(dict(shape=1, verts=v, pos=(D["x"][i], D["y"][i]), rot=D["rotation"][i]))
+            else:
+                D["width_x"][i], D["width_y"][i] = rng.uniform(0.4, 2.0, 2)
+                pair.append(dict(shape=0, width=(D["width_x"][i], D["width_y"][i]), pos=(D["x"][i], D["y"][i]), rot=D["rotation"][i]))
+        descs.append(pair)
+    V = np.concatenate(verts)
+    out, cnt = collide_pairs(A, B, V, cap=16)
+    hits = 0
+    for i in range(n):
+        exp = orc.collide_pair(descs[i][0], descs[i][1], sincos_mode=1)
+        assert cnt[i] == len(exp), i
+        for f in CONTACT_GEOM:
+            assert np.array_equal(out[i, :cnt[i]][f], exp[f]), (i, f)
+        hits += cnt[i] > 0
+    assert hits > 300
+
+
+@pytest.mark.parametrize("name,steps", [("pyramid6", 120), ("demo1", 150), ("demo2", 80), ("demo3", 150), ("demo4", 120), ("demo6", 150),
+                                        ("demo8", 120), ("demo10", 100), ("bridge", 100), ("multi_pendulum", 100)])
+def test_world_step_bit_exact_in_gpu_order(name, steps):
+    sc = scenes.pyramid(6, 10) if name == "pyramid6" else getattr(scenes, name)(10)
+    _run_lockstep(sc, steps)
+
+
+@pytest.mark.parametrize("ctx", [(a, w, p) for a in (True, False) for w in (True, False) for p in (True, False)])
+def test_world_context_flag_combinations(ctx):
+    # quirks Q-4 / Q-5: three independent flags, all 8 combinations
+    sc = scenes.demo6(10)
+    _run_lockstep(sc, 60, ctx=ctx)
+    _run_lockstep(scenes.pyramid(4, 10), 60, ctx=ctx)
+
+
+def test_reference_literal_pyramid_12_rows_100_iterations():
+    # the reference's own demo5 settings (quirk Q-14)
+    sc = scenes.pyramid(12, 100)
+    _run_lockstep(sc, 40, check_every=10)
+
+
+def _random_scene(n, seed, polys=True, span=30.0):
+    rng = np.random.default_rng(seed)
+    b = scenes._Builder()
+    b.box(2 * span + 10, 2.0, scenes.F32_MAX, 0.4, (0.0, -1.0))
+    b.box(2.0, 40.0, scenes.F32_MAX, 0.4, (-span - 4.0, 18.0))
+    b.box(2.0, 40.0, scenes.F32_MAX, 0.4, (span + 4.0, 18.0))
+    for _ in range(n):
+        pos = (rng.uniform(-span, span), rng.uniform(0.5, 12.0))
+        rot = rng.uniform(-np.pi, np.pi)
+        if polys and rng.random() < 0.5:
+            k = int(rng.integers(3, 9))
+            b.polygon(scenes.regular_ngon(k, rng.uniform(0.3, 0.8)), rng.uniform(1, 20), rng.uniform(0.1, 0.6), pos, rot,
+                      vel=(rng.uniform(-2, 2), rng.uniform(-2, 2)), omega=rng.uniform(-3, 3))
+        else:
+            b.box(rng.uniform(0.4, 1.6), rng.uniform(0.4, 1.6), rng.uniform(1, 20), rng.uniform(0.1, 0.6), pos, rot,
+                  vel=(rng.uniform(-2, 2), rng.uniform(-2, 2)), omega=rng.uniform(-3, 3))
+    return b.scene(f"random{n}_{seed}", iterations=10)
+
+
+@pytest.mark.parametrize("seed,polys", [(1, False), (2, True), (3, True)])
+def test_broad_phase_pair_set_bit_exact_vs_all_pairs(seed, polys):
+    # grid broad phase (GPU) vs the reference's all-pairs loop (oracle): same arbiter keys, same contacts
+    sc = _random_scene(700, seed, polys)
+    w, o = _mk(sc)
+    w.broad_phase()
+    o.broad_phase()
+    ga = _assert_arbiters_equal(w, o, solve_fields=False, what=sc.name)
+    assert ga.shape[0] > 300
+    st = w.get_stats()
+    assert st["candidate_pairs"] >= st["arbiters"]
+
+
+@pytest.mark.parametrize("seed,polys", [(11, False), (12, True)])
+def test_random_pile_steps_bit_exact(seed, polys):
+    sc = _random_scene(400, seed, polys)
+    _run_lockstep(sc, 40, check_every=5)
+
+
+def test_bodies_added_between_steps_and_clear():
+    # launch_bomb (examples/samples/src/main.rs:56-64): add_body between steps; World::clear + reload
+    from sylt2d_b200 import Body, Vec2
+    sc = scenes.pyramid(5, 10)
+    w, o = _mk(sc)
+    nid = int(sc.bodies["id"].max()) + 1
+    for s in range(60):
+        if s in (10, 25):
+            bomb = Body.new(Vec2(1.0, 1.0), 50.0)
+            bomb.id = nid
+            bomb.friction = 0.2
+            bomb.position = Vec2(-3.0 + 0.3 * s, 15.0)
+            bomb.rotation = 0.3
+            bomb.velocity = Vec2(bomb.position.x * -1.5, 15.0 * -1.5)
+            bomb.angular_velocity = 7.0
+            w.add_body(bomb)
+            o.add_box(nid, (1.0, 1.0), 50.0, 0.2, tuple(bomb.position), 0.3, tuple(bomb.velocity), 7.0)
+            nid += 1
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"bomb step {s}")
+    _assert_arbiters_equal(w, o, what="bomb")
+    w.clear()
+    o.clear()
+    assert w.num_bodies == 0
+    sc2 = scenes.demo3(10)
+    w.load_scene(sc2)
+    o.load_scene(sc2)
+    for s in range(30):
+        w.step(sc2.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc2.dt, keys, jo)
+    _assert_states_equal(w.get_bodies(), o.get_bodies(), "after clear")
+
+
+def test_mutating_pub_fields_between_steps():
+    sc = scenes.demo4(10)
+    w, o = _mk(sc)
+    for s in range(40):
+        if s == 15:
+            st = w.get_bodies()
+            st["vx"][3] = 4.0
+            st["angular_velocity"][5] = -2.0
+            w.set_bodies(st)
+            o.set_bodies(st)
+            w.add_force(2, (30.0, 5.0))
+            o.add_force(2, (30.0, 5.0))
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"mutate step {s}")
+
+
+def test_errors_match_reference_contract():
+    from sylt2d_b200 import World, Body, Joint, Vec2, SyltError
+    # NoInverse mid-step (quirk Q-15): joint between two static bodies
+    w = World((0, -10), 10)
+    a, b = Body.new(Vec2(1, 1), scenes.F32_MAX), Body.new(Vec2(1, 1), scenes.F32_MAX)
+    b.position = Vec2(3, 0)
+    w.add_body(a)
+    w.add_body(b)
+    w.add_joint(Joint.new(a, b, Vec2(1.5, 0.0), w))
+    with pytest.raises(SyltError) as ei:
+        w.step(1 / 60)
+    assert ei.value.code == 1
+    j, m = w.last_error_matrix()
+    assert j == 0 and list(m) == [0, 0, 0, 0]
+    # out-of-order ids (quirk Q-6): the reference panics, the ABI returns SYLT_ERR_BODY_ORDER
+    w2 = World((0, -10), 10)
+    c, d = Body.new(Vec2(1, 1), 1.0), Body.new(Vec2(1, 1), 1.0)
+    w2.add_body(d)
+    w2.add_body(c)
+    with pytest.raises(SyltError) as ei:
+        w2.step(1 / 60)
+    assert ei.value.code == 3
+    # Joint::new on a body that is not in the world (joint.rs:31 `expect`)
+    with pytest.raises(SyltError) as ei:
+        Joint.new(a, c, Vec2(0, 0), w)
+    assert ei.value.code == 4
+    # empty world steps fine
+    w3 = World((0, -10), 10)
+    w3.step(1 / 60)
+    assert w3.num_arbiters == 0
+
+
+def test_step_n_equals_n_steps_and_is_deterministic():
+    sc = scenes.pyramid(8, 10)
+    from sylt2d_b200 import World
+    res = []
+    for mode in range(3):
+        w = World(sc.gravity, sc.iterations)
+        w.load_scene(sc)
+        if mode == 0:
+            for _ in range(50):
+                w.step(sc.dt)
+        elif mode == 1:
+            w.step_n(sc.dt, 50)
+        else:
+            w.step_n_async(sc.dt, 20)
+            w.step_n_async(sc.dt, 30)
+            w.sync()
+        res.append(w.get_bodies())
+    _assert_states_equal(res[0], res[1], "step vs step_n")
+    _assert_states_equal(res[0], res[2], "step vs async")
+
+
+def test_colour_order_vs_canonical_order_tolerance_and_long_run():
+    """The reference's own arbiter order is a randomised HashMap order (quirk Q-1), so any order is "the reference";
+    canonical ascending-key order is what BASELINE.md calls reference keying.  Single step: |dv| <= 5e-2 m/s on a
+    settled 20-row pyramid under g=10 (stated looser tolerance).  Long run: penetration and energy stay in family."""
+    sc = scenes.pyramid(20, 10)
+    w, o = _mk(sc)
+    for s in range(300):
+        w.step(sc.dt)
+    o_can = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=1)
+    o_can.load_scene(sc)
+    for s in range(300):
+        o_can.step(sc.dt)
+    g, r = w.get_bodies(), o_can.get_bodies()
+    ke_g = float((g["vx"] ** 2 + g["vy"] ** 2).sum())
+    ke_r = float((r["vx"] ** 2 + r["vy"] ** 2).sum())
+    assert ke_g < 1.0 and ke_r < 1.0, (ke_g, ke_r)                      # both settle
+    assert abs(g["y"].max() - r["y"].max()) < 0.1                        # same stack height
+    _, gc = w.get_arbiters()
+    _, rc = o_can.get_arbiters()
+    assert gc["separation"].min() > -0.05 and rc["separation"].min() > -0.05
+    assert abs(gc.shape[0] - rc.shape[0]) <= 0.1 * rc.shape[0]
+    # single step from identical state, different order
+    st = o_can.get_bodies()
+    w2, o2 = _mk(sc)
+    w2.set_bodies(st)
+    o2.set_bodies(st)
+    w2.step(sc.dt)
+    o2.step(sc.dt)  # canonical order
+    a, b = w2.get_bodies(), o2.get_bodies()
+    assert np.abs(a["vx"] - b["vx"]).max() < 5e-2 and np.abs(a["vy"] - b["vy"]).max() < 5e-2
+
+
+# ------------------------------------------------------------------ batched worlds
+def _batch_lockstep(scene, n_worlds, steps, x_jitter=0.0, omega_jitter=0.0, check_worlds=(0, 1)):
+    from sylt2d_b200 import Batch
+    bodies, boff, joints, joff = scenes.tile_worlds(scene, n_worlds, seed=7, x_jitter=x_jitter, omega_jitter=omega_jitter)
+    b = Batch(bodies, boff, joints, joff, scene.gravity, scene.iterations, device=0, ctx=scene.ctx)
+    nb = scene.num_bodies
+    oracles = {}
+    for wi in check_worlds:
+        sc = scenes.Scene(scene.name, bodies[wi * nb:(wi + 1) * nb], scene.joints, scene.verts, scene.gravity, scene.iterations, scene.dt, scene.ctx)
+        o = orc.OracleWorld(scene.gravity, scene.iterations, sincos_mode=1)
+        o.load_scene(sc)
+        oracles[wi] = o
+    for s in range(steps):
+        b.step_n(scene.dt, 1)
+        for wi, o in oracles.items():
+            keys, jo = b.solve_order(wi)
+            o.step_ordered(scene.dt, keys, jo)
+            _assert_states_equal(b.get_bodies(wi, 1), o.get_bodies(), f"batch {scene.name} world {wi} step {s}")
+    for wi, o in oracles.items():
+        ga, gc = b.get_arbiters(wi)
+        ra, rc = o.get_arbiters()
+        assert np.array_equal(ga["id1"], ra["id1"]) and np.array_equal(ga["id2"], ra["id2"])
+        for f in CONTACT_GEOM + CONTACT_SOLVE:
+            assert np.array_equal(gc[f], rc[f]), f
+        gj, rj = b.get_joints(wi), o.get_joints()
+        for f in gj.dtype.names:
+            assert np.array_equal(gj[f], rj[f]), f
+    assert not b.get_errors().any()
+    return b
+
+
+def test_batch_pyramid_bit_exact():
+    _batch_lockstep(scenes.pyramid(8, 10), 6, 80, x_jitter=0.01, check_worlds=(0, 5))
+
+
+def test_batch_pyramid20_config5_world():
+    _batch_lockstep(scenes.pyramid(20, 10), 3, 40, x_jitter=0.01, check_worlds=(1,))
+
+
+def test_batch_bridge_and_pendulum_bit_exact():
+    _batch_lockstep(scenes.bridge(10), 5, 80, omega_jitter=1.0, check_worlds=(0, 4))
+    _batch_lockstep(scenes.multi_pendulum(10), 5, 80, omega_jitter=1.0, check_worlds=(0, 3))
+    _batch_lockstep(scenes.demo8(10), 2, 60, check_worlds=(1,))
+
+
+def test_batch_multi_step_launch_equals_single_steps_and_shards():
+    # world results must not depend on how worlds are sharded over GPUs nor on steps per launch
+    from sylt2d_b200 import Batch, shard_range
+    sc = scenes.pyramid(6, 10)
+    n = 9
+    bodies, boff, joints, joff = scenes.tile_worlds(sc, n, seed=3, x_jitter=0.01)
+    full = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, ctx=sc.ctx)
+    full.step_n(sc.dt, 45)
+    ref = full.get_bodies()
+    nb = sc.num_bodies
+    for ws in (2, 4):
+        parts = []
+        for r in range(ws):
+            lo, hi = shard_range(n, r, ws)
+            if hi <= lo:
+                continue
+            sb = Batch(bodies[lo * nb:hi * nb], boff[lo:hi + 1] - boff[lo], joints[:0], joff[lo:hi + 1] - joff[lo], sc.gravity, sc.iterations, ctx=sc.ctx)
+            for _ in range(45):
+                sb.step_n(sc.dt, 1)
+            parts.append(sb.get_bodies())
+        _assert_states_equal(np.concatenate(parts), ref, f"shards={ws}")
+    st = full.stats()
+    assert st["body_steps"] == n * nb * 45 and st["errors"] == 0 and st["contacts"] > 0
