@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py — body-steps/s of the World::step hot path (BASELINE.json metric).
+
+Workload (config.workload): BASELINE.json config 5 — 32768 independent 20-row pyramid worlds (211 bodies each,
+dt = 1/60, 10 iterations, warm-starting on), sharded over the ranks in contiguous blocks with NO per-step
+communication (strong scaling: the 32768 worlds are split over N GPUs).  A "step" is one World::step of every world
+the job owns.  Worlds are first settled (untimed, stated in config.settle_steps) so the timed steps run at the steady
+contact count; then W warm-up steps and exactly K timed steps, barrier + synchronize on both sides, device time by
+CUDA events on the launching stream, max over ranks.
+
+  value  : device-resident throughput (state stays in HBM; one k_batch_step launch per step)
+  e2e    : the same metric through the C ABI with HOST buffers: every step uploads all body states from pinned host
+           memory (sylt_batch_set_bodies), steps, and reads all body states back (sylt_batch_get_bodies)
+  roofline: algorithmic bytes of SURVEY.md §8(d)  (116 B + 56 P + 152 C + 144 J + I (120 C + 124 J)) per launch
+           over the kernel's average launch duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
+  cpu_baseline: the CPU oracle (C++ restatement of the Rust reference; the reference itself cannot be built here)
+           on all host cores, one world per thread, on a bounded sample of the same worlds
+
+`--impl reference` times that CPU path alone (the reference arm).  At N=1 the line also carries `world100k`:
+ms/step of the single 100k-body world (BASELINE.json config 3), which does not shard ("replicas only").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_WORLDS = 32768
+ROWS = 20
+ITER = 10
+METRIC = "body_steps_per_sec"
+UNIT = "body-steps/s"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.rows, self.p = [], None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(index)],
+                                      stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.p = None
+
+    def _read(self):
+        for line in self.p.stdout:
+            self.rows.append((time.time(), [x.strip() for x in line.split(",")]))
+
+    def stop(self, t0, t1):
+        if self.p is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.p.terminate()
+        rows = [r for t, r in self.rows if t0 - 0.05 <= t <= t1 + 0.15 and len(r) >= 6] or [r for _, r in self.rows if len(r) >= 6]
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm = sorted(float(r[0]) for r in rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for k, n in enumerate(names) if any(r[2 + k].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
+
+
+def settled_oracle_worlds(scene, n, threads, settle):
+    from oracle import orc
+    from sylt2d_b200 import scenes
+    bodies, boff, joints, joff = scenes.tile_worlds(scene, n, seed=0, x_jitter=0.01)
+    nb = scene.num_bodies
+    ws = []
+    for k in range(n):
+        w = orc.OracleWorld(scene.gravity, scene.iterations, sincos_mode=0, broadphase=0)  # faithful: libm trig, all-pairs broad phase
+        w.load_scene(scenes.Scene(scene.name, bodies[k * nb:(k + 1) * nb], scene.joints, scene.verts, scene.gravity, scene.iterations, scene.dt, scene.ctx))
+        ws.append(w)
+    if settle:
+        orc.step_worlds_mt(ws, scene.dt, settle, threads)
+    return ws
+
+
+def cpu_time_sample(scene, n, steps, threads, settle, states=None):
+    """body-steps/s of the CPU oracle: n worlds x steps, worlds spread over `threads` host threads."""
+    from oracle import orc
+    ws = settled_oracle_worlds(scene, n, threads, 0 if states is not None else settle)
+    if states is not None:
+        nb = scene.num_bodies
+        for k, w in enumerate(ws):
+            w.set_bodies(states[k * nb:(k + 1) * nb])
+        orc.step_worlds_mt(ws, scene.dt, 5, threads)
+    t0 = time.perf_counter()
+    orc.step_worlds_mt(ws, scene.dt, steps, threads)
+    dt = time.perf_counter() - t0
+    return n * scene.num_bodies * steps / dt, dt
+
+
+def reference_arm(args, rank):
+    """--impl reference: the reference's CPU implementation of the path (oracle port; rustc/cargo are absent)."""
+    if rank != 0:
+        return
+    from oracle import orc
+    from sylt2d_b200 import scenes
+    orc.build()
+    scene = scenes.pyramid(ROWS, ITER)
+    cores = os.cpu_count() or 1
+    n = max(cores * 8, 64)
+    ws = settled_oracle_worlds(scene, n, cores, args.settle)
+    per = 25  # world-steps per world per bench "step" (a bounded sample: ~0.2 s of all-core CPU work per step)
+    for _ in range(args.warmup):
+        orc.step_worlds_mt(ws, scene.dt, per, cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.step_worlds_mt(ws, scene.dt, per, cores)
+    el = time.perf_counter() - t0
+    v = n * scene.num_bodies * per * args.steps / el
+    sample = f"{n} of {N_WORLDS} pyramid{ROWS} worlds x {per} world-steps per step, one world per host thread"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{N_WORLDS} independent pyramid{ROWS} worlds (BASELINE.json config 5), CPU sample", "bodies_per_world": scene.num_bodies,
+                   "iterations": ITER, "dt": scene.dt, "settle_steps": args.settle},
+        "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}), flush=True)
+
+
+def bench_world100k(device, steps):
+    """ms/step of one 100k-body world (config 3) in the falling and the settled phase; single GPU by construction."""
+    from sylt2d_b200 import World, scenes
+    sc = scenes.box_drop(100000, seed=42, iterations=ITER)
+    w = World(sc.gravity, sc.iterations, device=device)
+    w.load_scene(sc)
+    out = {"bodies": sc.num_bodies}
+    w.step_n(sc.dt, 5)
+    w.timer_start()
+    w.step_n_async(sc.dt, 55)
+    ms = w.timer_stop()
+    w.sync()
+    out["falling_ms_per_step"] = ms / 55
+    w.step_n(sc.dt, 540)
+    l0 = w.launch_count
+    w.timer_start()
+    w.step_n_async(sc.dt, steps)
+    ms = w.timer_stop()
+    w.sync()
+    st = w.get_stats()
+    out["settled_ms_per_step"] = ms / steps
+    out["launches_per_step"] = (w.launch_count - l0) / steps
+    out["stats"] = st
+    B, P, C, J = st["bodies"], st["candidate_pairs"], st["contacts"], st["joints"]
+    by = 116 * B + 56 * P + 152 * C + 144 * J + ITER * (120 * C + 124 * J)
+    peak, _ = peaks()
+    out["algorithmic_bytes_per_step"] = by
+    out["roofline_frac_whole_step"] = by / (ms / steps * 1e-3) / 1e9 / peak
+    out["body_steps_per_sec"] = B * steps / (ms * 1e-3)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--worlds", type=int, default=N_WORLDS)
+    ap.add_argument("--settle", type=int, default=150)
+    ap.add_argument("--skip-world100k", action="store_true")
+    ap.add_argument("--skip-cpu", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        reference_arm(args, rank)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from sylt2d_b200 import Batch, scenes, shard_range
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    use_dist = world_size > 1
+    if use_dist:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if use_dist:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    scene = scenes.pyramid(ROWS, ITER)
+    nb = scene.num_bodies
+    lo, hi = shard_range(args.worlds, rank, world_size)
+    bodies, boff, joints, joff = scenes.tile_worlds(scene, args.worlds, seed=0, x_jitter=0.01)
+    bodies = bodies[lo * nb:hi * nb]
+    boff = boff[lo:hi + 1] - boff[lo]
+    joff = joff[lo:hi + 1] - joff[lo]
+    batch = Batch(bodies, boff, joints[:0], joff, scene.gravity, scene.iterations, device=local_rank, ctx=scene.ctx)
+    my_worlds = hi - lo
+    my_bodies = my_worlds * nb
+    batch.step_n(scene.dt, args.settle)  # untimed: reach the steady contact count
+    for _ in range(args.warmup):
+        batch.step_n(scene.dt, 1)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.25)
+    l0 = batch.launch_count
+    barrier()
+    t0 = time.time()
+    batch.timer_start()
+    for _ in range(args.steps):
+        batch.step_n_async(scene.dt, 1)
+    ms = batch.timer_stop()
+    barrier()
+    t1 = time.time()
+    launches = batch.launch_count - l0
+    clocks = sampler.stop(t0, t1) if sampler else None
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_max = float(t.item())
+    total_bodies = args.worlds * nb
+    value = total_bodies * args.steps / (ms_max * 1e-3)
+    st = batch.stats()
+
+    # ---- e2e: host buffers in, host buffers out, every step (pinned memory; the C ABI does one DMA each way)
+    host_in = torch.empty(my_bodies * 9, dtype=torch.float32, pin_memory=True)
+    host_out = torch.empty(my_bodies * 9, dtype=torch.float32, pin_memory=True)
+    from sylt2d_b200._ffi import BODY_STATE
+    hin = host_in.numpy().view(BODY_STATE)
+    hin[:] = batch.get_bodies()
+    L, h = batch.L, batch.h
+    import ctypes as C
+    pin, pout = C.c_void_p(host_in.data_ptr()), C.c_void_p(host_out.data_ptr())
+
+    bufs = [pin, pout]
+
+    def e2e_step():
+        # the caller's state for the next step is the result of this one: the two pinned buffers alternate roles
+        assert L.sylt_batch_set_bodies(h, 0, my_worlds, bufs[0], my_bodies) == 0
+        assert L.sylt_batch_step_n(h, scene.dt, 1) == 0
+        assert L.sylt_batch_get_bodies(h, 0, my_worlds, bufs[1], my_bodies) == my_bodies
+        bufs.reverse()
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    tw0 = time.perf_counter()
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(e2e_steps):
+        e2e_step()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - tw0  # host-side wall time: the copies are synchronous C-ABI calls on the library's stream
+    barrier()
+    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = total_bodies * e2e_steps / float(te.item())
+
+    # ---- whole-job stats: the only cross-GPU reduction of the run (<= 64 bytes per rank)
+    red = torch.tensor([st["contacts"], st["errors"], st["kinetic_energy"], st["body_steps"]], dtype=torch.float64, device="cuda")
+    mx = torch.tensor([st["max_penetration"]], dtype=torch.float64, device="cuda")
+    if use_dist:
+        dist.all_reduce(red, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    contacts_total, errors_total = int(red[0].item()), int(red[1].item())
+
+    # ---- roofline of the dominant kernel (k_batch_step, one launch per step)
+    peak, peak_src = peaks()
+    arb = batch.get_arbiters(0)[0]
+    C_w = st["contacts"] / max(my_worlds, 1)
+    P_w = float(arb.shape[0]) if arb.shape[0] else C_w / 2  # candidate slots ~ arbiters in a settled pyramid
+    bytes_world = 116 * nb + 56 * P_w + 152 * C_w + ITER * 120 * C_w
+    bytes_launch = bytes_world * my_worlds
+    achieved = bytes_launch / (ms / args.steps * 1e-3) / 1e9
+    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+            "kernel": "k_batch_step", "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
+            "note": "effective bandwidth: worlds are shared-memory resident for the whole step, so the algorithmic bytes of SURVEY.md 8(d) "
+                    "are served on-chip; DRAM traffic per launch is in profiles/ (ncu)"}
+    tp = os.path.join(ROOT, "profiles", "batch_step_traffic.json")
+    if os.path.exists(tp):
+        try:
+            with open(tp) as f:
+                tj = json.load(f)
+            roof["traffic"] = tj.get("dram_bytes_per_launch_per_world", 0) * my_worlds
+        except Exception:
+            pass
+
+    out = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{args.worlds} independent pyramid{ROWS} worlds (BASELINE.json config 5), one CTA per world",
+                   "bodies_per_world": nb, "iterations": ITER, "dt": scene.dt, "warm_starting": True, "settle_steps": args.settle,
+                   "parallelism": f"worlds sharded over {world_size} GPU(s), no per-step communication",
+                   "l2": "per-GPU state (bodies + per-world slot cache) exceeds the 126 MB L2 at N<=2; smaller shards are L2-resident by nature of strong scaling",
+                   "contacts_per_world": C_w, "errors": errors_total},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": my_bodies * 36 * world_size, "d2h_bytes_per_step": my_bodies * 36 * world_size,
+                "steps": e2e_steps, "api": "sylt_batch_set_bodies + sylt_batch_step_n(1) + sylt_batch_get_bodies, pinned host buffers"},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "clocks": clocks,
+        "stats": {"contacts": contacts_total, "errors": errors_total, "kinetic_energy": float(red[2].item()), "max_penetration": float(mx.item())},
+    }
+    if rank == 0 and world_size == 1:
+        if not args.skip_cpu:
+            from oracle import orc
+            orc.build()
+            cores = os.cpu_count() or 1
+            n = min(args.worlds, max(cores * 8, 64))
+            states = batch.get_bodies(0, n)
+            _, el0 = cpu_time_sample(scene, n, 10, cores, 0, states=states)           # calibration
+            cs = int(min(2000, max(20, 12.0 / max(el0 / 10, 1e-6))))                    # ~12 s of CPU work
+            v, el = cpu_time_sample(scene, n, cs, cores, 0, states=states)
+            out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+                                   "sample": f"{n} of {args.worlds} settled pyramid{ROWS} worlds x {cs} steps ({el:.1f} s), one world per host thread, "
+                                             "C++ restatement of the Rust reference (no Rust toolchain), all-pairs broad phase, libm trig"}
+            s1 = int(min(4000, max(20, 4.0 / max(el0 / 10 * cores / n * 2, 1e-6))))     # ~4 s on one thread
+            v1, el1 = cpu_time_sample(scene, 2, s1, 1, 0, states=states[:2 * nb])
+            out["cpu_baseline"]["single_thread_value"] = v1
+            out["cpu_baseline"]["single_thread_sample"] = f"2 worlds x {s1} steps ({el1:.1f} s), 1 thread"
+        if not args.skip_world100k:
+            try:
+                out["world100k"] = bench_world100k(local_rank, 100)
+            except Exception as e:  # reported, never hidden
+                out["world100k"] = {"error": repr(e)}
+    if rank == 0:
+        print(json.dumps(out), flush=True)
+    if use_dist:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -145,7 +145,7 @@ __device__ __forceinline__ bool overlap4(float4 a, float4 b) { return !(a.x > b.
 __device__ __forceinline__ Vel ld_vel(const float4* v, int b) { float4 t = v[b]; Vel o; o.v = mk(t.x, t.y); o.w = t.z; return o; }
 __device__ __forceinline__ void st_vel(float4* v, int b, const Vel& x) { v[b] = make_float4(x.v.x, x.v.y, x.w, 0.0f); }
 
-__global__ void __launch_bounds__(256) k_batch_step(BatchArgs a) {
+__global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wld = blockIdx.x;
     if (wld >= a.n_worlds) return;
@@ -499,6 +499,22 @@ __global__ void __launch_bounds__(256) k_batch_step(BatchArgs a) {
     }
 }
 
+// AoS (SyltBodyState, the ABI record) <-> SoA (pose, vel) on the device, so host buffers move with ONE DMA each way
+__global__ void k_unpack_states(int n, const SyltBodyState* in, float4* pose, float4* vel) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    SyltBodyState s = in[i];
+    pose[i] = make_float4(s.x, s.y, s.rotation, 0.0f);
+    vel[i] = make_float4(s.vx, s.vy, s.angular_velocity, 0.0f);
+}
+__global__ void k_pack_states(int n, const float4* pose, const float4* vel, SyltBodyState* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pose[i], v = vel[i];
+    SyltBodyState s = {p.x, p.y, p.z, v.x, v.y, v.z, 0.0f, 0.0f, 0.0f};
+    out[i] = s;
+}
+
 struct StatsOut {
     unsigned long long contacts, errors;
     double ke;
@@ -573,6 +589,7 @@ struct SyltBatch {
     DBuf<unsigned char> c_color;
     DBuf<SlotExport> exp_slots;
     DBuf<StatsOut> stats;
+    DBuf<SyltBodyState> stage;
 };
 
 namespace {
@@ -583,7 +600,7 @@ void batch_free(SyltBatch* b) {
     b->exp_count.release(); b->pose.release(); b->vel.release(); b->mp.release(); b->jla.release(); b->jr.release(); b->jm.release();
     b->w_badk.release(); b->wh.release(); b->jparam.release(); b->jp.release(); b->jbias.release(); b->mass_moi.release();
     b->c_fric.release(); b->c_pn.release(); b->c_pt.release(); b->w_maxpen.release(); b->jbodies.release(); b->c_key.release();
-    b->c_color.release(); b->exp_slots.release(); b->stats.release();
+    b->c_color.release(); b->exp_slots.release(); b->stats.release(); b->stage.release();
 }
 
 template <typename T>
@@ -822,15 +839,12 @@ int sylt_batch_get_bodies(SyltBatch* b, int32_t first, int32_t nw, SyltBodyState
     if (n > cap) return -SYLT_ERR_CAPACITY;
     if (n == 0) return 0;
     if (cudaSetDevice(b->device) != cudaSuccess) return -SYLT_ERR_CUDA;
-    std::vector<float4> p((size_t)n), v((size_t)n);
-    cudaMemcpyAsync(p.data(), b->pose.p + o0, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, b->stream);
-    cudaMemcpyAsync(v.data(), b->vel.p + o0, (size_t)n * sizeof(float4), cudaMemcpyDeviceToHost, b->stream);
-    cudaError_t ce = cudaStreamSynchronize(b->stream);
+    if (b->stage.ensure((size_t)n) != cudaSuccess) return -SYLT_ERR_CUDA;
+    k_pack_states<<<(n + 255) / 256, 256, 0, b->stream>>>(n, b->pose.p + o0, b->vel.p + o0, b->stage.p);
+    b->launches++;
+    cudaError_t ce = cudaMemcpyAsync(out, b->stage.p, (size_t)n * sizeof(SyltBodyState), cudaMemcpyDeviceToHost, b->stream);
+    if (ce == cudaSuccess) ce = cudaStreamSynchronize(b->stream);
     if (ce != cudaSuccess) { set_last_error(cudaGetErrorString(ce)); return -SYLT_ERR_CUDA; }
-    for (int i = 0; i < n; i++) {
-        SyltBodyState s = {p[(size_t)i].x, p[(size_t)i].y, p[(size_t)i].z, v[(size_t)i].x, v[(size_t)i].y, v[(size_t)i].z, 0.0f, 0.0f, 0.0f};
-        out[i] = s;
-    }
     return n;
 }
 
@@ -841,13 +855,10 @@ int sylt_batch_set_bodies(SyltBatch* b, int32_t first, int32_t nw, const SyltBod
     if (count != n) return SYLT_ERR_INVALID;
     if (n == 0) return SYLT_OK;
     SYLT_CUDA(cudaSetDevice(b->device));
-    std::vector<float4> p((size_t)n), v((size_t)n);
-    for (int i = 0; i < n; i++) {
-        p[(size_t)i] = make_float4(in[i].x, in[i].y, in[i].rotation, 0.0f);
-        v[(size_t)i] = make_float4(in[i].vx, in[i].vy, in[i].angular_velocity, 0.0f);
-    }
-    SYLT_CUDA(cudaMemcpyAsync(b->pose.p + o0, p.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, b->stream));
-    SYLT_CUDA(cudaMemcpyAsync(b->vel.p + o0, v.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice, b->stream));
+    SYLT_CUDA(b->stage.ensure((size_t)n));
+    SYLT_CUDA(cudaMemcpyAsync(b->stage.p, in, (size_t)n * sizeof(SyltBodyState), cudaMemcpyHostToDevice, b->stream));
+    k_unpack_states<<<(n + 255) / 256, 256, 0, b->stream>>>(n, b->stage.p, b->pose.p + o0, b->vel.p + o0);
+    b->launches++;
     SYLT_CUDA(cudaStreamSynchronize(b->stream));
     return SYLT_OK;
 }
