@@ -26,6 +26,7 @@
 // oracle can replay it.
 #include <cooperative_groups.h>
 #include <algorithm>
+#include <cstdlib>
 #include <mutex>
 #include "common.h"
 #include "narrow.cuh"
@@ -49,7 +50,6 @@ namespace {
 
 constexpr int NC = 32;          // max arbiter colours
 constexpr int MAX_ROUNDS = 256; // colouring rounds per step (only new arbiters take part)
-constexpr int SPREAD = 4;       // new arbiters propose one of their first SPREAD free colours
 constexpr int FLAG_POLY = 1, FLAG_LARGE = 2, FLAG_STATIC = 4;
 
 struct Counters {
@@ -63,6 +63,7 @@ struct Counters {
     int color_start[NC + 1];
     int color_fill[NC];
     int remaining[MAX_ROUNDS];
+    unsigned bar;  // grid barrier arrivals of this step's k_solve
 };
 
 // ------------------------------------------------------------------ device-wide exclusive scan (3 kernels)
@@ -232,25 +233,13 @@ __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, co
 
 // Row i = partners body i owns: small-small pairs belong to the lower index, small-large pairs to the small
 // body, large-large pairs to the lower index.  Partners are emitted sorted ascending.
-template <bool EMIT>
-__global__ void __launch_bounds__(128) k_rows(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int* cell_bodies,
-                                              const int* large, int n_large, GridParams gp, int* row_count, const int* row_start,
-                                              int2* pairs, int cap_pairs, Counters* cn) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    float4 my = aabb[i];
-    int4 ci = cinfo[i];
+// The count pass remembers the first ROWTMP partners it finds so that the emit pass does not repeat the grid walk.
+constexpr int ROWTMP = 16;
+
+template <typename F>
+__device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, const float4* aabb, const int4* cinfo, const int* cell_start,
+                                           const int* cell_bodies, const int* large, int n_large, GridParams gp, F&& found) {
     const bool st_i = (ci.z & FLAG_STATIC) != 0;
-    int n = 0;
-    int base = 0;
-    if (EMIT) {
-        base = row_start[i];
-        int end = row_start[i + 1];
-        if (end > cap_pairs) {  // whole row does not fit: flag and drop (k_scan already clamped the total)
-            atomicExch(&cn->err, SYLT_ERR_CAPACITY);
-            return;
-        }
-    }
     if (!(ci.z & FLAG_LARGE)) {
         int x0 = cell_coord(my.x - 0.5f * gp.cell, gp.cell), x1 = cell_coord(my.z + 0.5f * gp.cell, gp.cell);
         int y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell), y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
@@ -265,16 +254,14 @@ __global__ void __launch_bounds__(128) k_rows(int B, const float4* aabb, const i
                     if (cj.x != cx || cj.y != cy) continue;  // another cell sharing the bucket
                     if (st_i && (cj.z & FLAG_STATIC)) continue;
                     if (!aabb_overlap(my, aabb[j])) continue;
-                    if (EMIT) pairs[base + n] = make_int2(i, j);
-                    n++;
+                    found(j);
                 }
             }
         for (int k = 0; k < n_large; k++) {
             int j = large[k];
             if (st_i && (cinfo[j].z & FLAG_STATIC)) continue;
             if (!aabb_overlap(my, aabb[j])) continue;
-            if (EMIT) pairs[base + n] = make_int2(i, j);
-            n++;
+            found(j);
         }
     } else {
         for (int k = 0; k < n_large; k++) {
@@ -282,19 +269,55 @@ __global__ void __launch_bounds__(128) k_rows(int B, const float4* aabb, const i
             if (j <= i) continue;
             if (st_i && (cinfo[j].z & FLAG_STATIC)) continue;
             if (!aabb_overlap(my, aabb[j])) continue;
-            if (EMIT) pairs[base + n] = make_int2(i, j);
-            n++;
+            found(j);
         }
     }
-    if (EMIT) {
+}
+
+__global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int* cell_bodies,
+                                                    const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int n = 0;
+    int* tmp = row_tmp + (size_t)i * ROWTMP;
+    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cell_bodies, large, n_large, gp, [&](int j) {
+        if (n < ROWTMP) tmp[n] = j;
+        n++;
+    });
+    row_count[i] = n;
+}
+
+__global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int* cell_bodies,
+                                                   const int* large, int n_large, GridParams gp, const int* row_start, const int* row_tmp,
+                                                   int2* pairs, int cap_pairs, Counters* cn) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    const int base = row_start[i], end = row_start[i + 1], n = end - base;
+    if (n == 0) return;
+    if (end > cap_pairs) {  // the row does not fit: flag and drop
+        atomicExch(&cn->err, SYLT_ERR_CAPACITY);
+        return;
+    }
+    if (n <= ROWTMP) {
+        const int* tmp = row_tmp + (size_t)i * ROWTMP;
+        int v[ROWTMP];
+#pragma unroll
+        for (int a = 0; a < ROWTMP; a++) v[a] = a < n ? tmp[a] : 0x7fffffff;
         for (int a = 1; a < n; a++) {  // insertion sort by partner (rows are short)
-            int2 v = pairs[base + a];
-            int b = a - 1;
-            while (b >= 0 && pairs[base + b].y > v.y) { pairs[base + b + 1] = pairs[base + b]; b--; }
-            pairs[base + b + 1] = v;
+            int x = v[a], b = a - 1;
+            while (b >= 0 && v[b] > x) { v[b + 1] = v[b]; b--; }
+            v[b + 1] = x;
         }
-    } else {
-        row_count[i] = n;
+        for (int a = 0; a < n; a++) pairs[base + a] = make_int2(i, v[a]);
+        return;
+    }
+    int m = 0;
+    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cell_bodies, large, n_large, gp, [&](int j) { pairs[base + m++] = make_int2(i, j); });
+    for (int a = 1; a < n; a++) {
+        int2 x = pairs[base + a];
+        int b = a - 1;
+        while (b >= 0 && pairs[base + b].y > x.y) { pairs[base + b + 1] = pairs[base + b]; b--; }
+        pairs[base + b + 1] = x;
     }
 }
 
@@ -360,6 +383,9 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                unsigned* used, int* uncolored) {
     int P = min(cn->n_pairs, cap_pairs);
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    __shared__ int s_hist[NC];
+    if (threadIdx.x < NC) s_hist[threadIdx.x] = 0;
+    __syncthreads();
     for (int i = tid; i <= B; i += nth) {
         int rs = i < B ? min(row_start[i], P) : P;
         cur.row_start[i] = (int)(scan[rs] >> 32);
@@ -412,11 +438,13 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         if (color >= 0) {
             if (!(bflags[b1] & FLAG_STATIC)) atomicOr(&used[b1], 1u << color);
             if (!(bflags[b2] & FLAG_STATIC)) atomicOr(&used[b2], 1u << color);
-            atomicAdd(&cn->color_count[color], 1);
+            atomicAdd(&s_hist[color], 1);
         } else {
             uncolored[atomicAdd(&cn->n_uncolored, 1)] = a;
         }
     }
+    __syncthreads();
+    if (threadIdx.x < NC && s_hist[threadIdx.x]) atomicAdd(&cn->color_count[threadIdx.x], s_hist[threadIdx.x]);
 }
 
 __global__ void k_totals(Counters* cn, const int* row_total, const unsigned long long* pair_total, int which, int cap_pairs) {
@@ -440,6 +468,8 @@ struct SolveArgs {
     int accumulate, warm, poscorr, run_solver;
     float dt, inv_dt;
     unsigned epoch_base;
+    int smem_slots, smem_contacts;  // shared-memory residency budget per CTA
+    int spread;                     // new arbiters propose one of their first `spread` free colours
     float4 *pose, *vel, *force;
     const float4* mp;
     const float2* rotc;
@@ -465,13 +495,54 @@ __device__ __forceinline__ Vel load_vel(const float4* vel, int b) {
 }
 __device__ __forceinline__ void store_vel(float4* vel, int b, const Vel& v) { __stcg(&vel[b], make_float4(v.v.x, v.v.y, v.w, 0.0f)); }
 
-__global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
-    cg::grid_group grid = cg::this_grid();
+// ---- light grid barrier: one monotonic counter, release-add on arrival, acquire-poll until everybody arrived.
+// (cg::grid.sync() cost ~5 us per colour phase here: profiles/r01_k_solve_lines.txt.)  All CTAs of the cooperative
+// launch are co-resident, all threads call it the same number of times; `target` lives in a register of every thread.
+__device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target) {
+    target += gridDim.x;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
+        unsigned v;
+        do {
+            asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+        __threadfence();  // acquire side: one gpu-scope fence after the poll loop (also drops this SM's stale L1 lines)
+    }
+    __syncthreads();
+}
+
+constexpr int SOLVE_THREADS = 512;
+
+// One arbiter as the solver sees it in a colour phase: either resident in this CTA's shared memory for the whole
+// solve (record + contact constants) or, when the CTA's share of the world exceeds the shared-memory budget, in the
+// global arrays.
+struct SlotView {
+    int b1, b2, n;
+    float fr, im1, ii1, im2, ii2;
+    float4 *ca, *cb, *cc;  // generic pointers (shared or global)
+};
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
     Counters* cn = a.cn;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int T = blockDim.x, G = gridDim.x, bid = blockIdx.x, lt = threadIdx.x;
     const int A = min(*(volatile int*)&cn->n_arb, a.cap_arb);
-    __shared__ int s_start[NC + 1];
+    unsigned bar_target = 0;
+    unsigned* bar = &cn->bar;
+    __shared__ int s_start[NC + 1];   // global colour-major start of colour c
+    __shared__ int s_lo[NC + 1];      // first slot of colour c this CTA owns (relative to s_start[c])
+    __shared__ int s_lbase[NC + 1];   // local index of that slot
     __shared__ int s_ncolors;
+    __shared__ int s_scan[34];
+    // shared-memory carve-up: records (2 x float4 per slot), slot contact counts (scan scratch), contacts (3 x float4)
+    const int SLOTCAP = a.smem_slots, CONCAP = a.smem_contacts;
+    float4* s_rec = (float4*)sm_raw;
+    int* s_n = (int*)(s_rec + 2 * (size_t)SLOTCAP);
+    float4* s_ca = (float4*)(s_n + ((SLOTCAP + 3) & ~3));
+    float4* s_cb = s_ca + CONCAP;
+    float4* s_cc = s_cb + CONCAP;
 
     // ---- 1. colour the arbiters that are new this step (persisting ones kept their colour in k_build)
     const int nunc = *(volatile int*)&cn->n_uncolored;
@@ -481,21 +552,21 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
             const unsigned long long ep = (unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32;
             for (int k = tid; k < nunc; k += nth) {
                 int e = a.uncolored[k];
-                if (a.cur.color[e] >= 0) continue;
+                if (a.cur.color[e] >= 0) continue;  // written by this same thread in an earlier round
                 int2 b = a.cur.bodies[e];
                 bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
                 unsigned m = (d1 ? __ldcg(&a.used[b.x]) : 0u) | (d2 ? __ldcg(&a.used[b.y]) : 0u);
                 unsigned fr = ~m;
                 if (!fr) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[e] = -1; continue; }
-                int nf = min(__popc(fr), SPREAD);
-                int r = (int)(fmix32((unsigned)e * 2654435761u + (unsigned)round) % (unsigned)nf);
-                int c = __fns(fr, 0, r + 1);  // (r+1)-th set bit
+                int nf = min(__popc(fr), a.spread);
+                int r = nf > 1 ? (int)(fmix32((unsigned)e * 2654435761u + (unsigned)round) % (unsigned)nf) : 0;
+                int c = __fns(fr, 0, r + 1);  // (r+1)-th free colour
                 a.prop[e] = c;
                 unsigned long long val = ep | fmix32((unsigned)e);
                 if (d1) atomicMin(&a.claim[(size_t)b.x * NC + c], val);
                 if (d2) atomicMin(&a.claim[(size_t)b.y * NC + c], val);
             }
-            grid.sync();
+            grid_barrier(bar, bar_target);
             for (int k = tid; k < nunc; k += nth) {
                 int e = a.uncolored[k];
                 if (a.cur.color[e] >= 0) continue;
@@ -514,32 +585,39 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
                     atomicAdd(&cn->remaining[round], 1);
                 }
             }
-            grid.sync();
+            grid_barrier(bar, bar_target);
             if (*(volatile int*)&cn->remaining[round] == 0) break;
         }
         if (tid == 0) cn->rounds = round + 1;
     }
 
-    // ---- 2. colour-major order (within a colour the order is irrelevant: disjoint dynamic bodies)
-    if (threadIdx.x == 0) {
-        int run = 0, nc = 0;
+    // ---- 2. colour-major order (within a colour the order is irrelevant: disjoint dynamic bodies) and this CTA's share
+    if (lt == 0) {
+        int run = 0, nc = 0, lrun = 0;
         for (int c = 0; c < NC; c++) {
             s_start[c] = run;
             int k = *(volatile int*)&cn->color_count[c];
             if (k > 0) nc = c + 1;
+            int chunk = (k + G - 1) / G;
+            int lo = min(k, bid * chunk), hi = min(k, lo + chunk);
+            s_lo[c] = lo;
+            s_lbase[c] = lrun;
+            lrun += hi - lo;
             run += k;
         }
         s_start[NC] = run;
+        s_lo[NC] = 0;
+        s_lbase[NC] = lrun;
         s_ncolors = nc;
-        if (blockIdx.x == 0) {
+        if (bid == 0) {
             for (int c = 0; c <= NC; c++) cn->color_start[c] = s_start[c];
             cn->n_colors = nc;
         }
     }
     __syncthreads();
-    for (int e0 = tid - (threadIdx.x & 31); e0 < A; e0 += nth) {  // warp-uniform trip count
-        const int lane = threadIdx.x & 31, e = e0 + lane;
-        int c = e < A ? a.cur.color[e] : -1;
+    for (int e0 = tid - (lt & 31); e0 < A; e0 += nth) {  // warp-uniform trip count
+        const int lane = lt & 31, e = e0 + lane;
+        int c = e < A ? __ldcg(&a.cur.color[e]) : -1;
         unsigned act = __ballot_sync(0xffffffffu, c >= 0);
         if (c >= 0) {  // warp-aggregated slot allocation per colour
             unsigned peers = __match_any_sync(act, c);
@@ -550,41 +628,110 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
             a.order[s_start[c] + base + __popc(peers & ((1u << lane) - 1))] = e;
         }
     }
-    grid.sync();
+    grid_barrier(bar, bar_target);
     if (!a.run_solver) return;
     const int ncolors = s_ncolors;
+    const int L = s_lbase[NC];  // slots this CTA owns
     const bool acc = a.accumulate != 0;
     const float kbias = a.poscorr ? 0.2f : 0.0f;
 
-    // ---- 3. Arbiter::pre_step, colour by colour (warm-start impulses write body velocities)
+    // ---- 3. residency: load the records of the owned slots; contacts get shared-memory room by an exclusive scan
+    const int Ls = min(L, SLOTCAP);
     for (int c = 0; c < ncolors; c++) {
-        for (int k = s_start[c] + tid; k < s_start[c + 1]; k += nth) {
-            int e = a.order[k];
+        const int cnt = s_lbase[c + 1] - s_lbase[c];
+        for (int i = lt; i < cnt; i += T) {
+            int ls = s_lbase[c] + i;
+            if (ls >= SLOTCAP) continue;
+            int e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
+            s_n[ls] = a.cur.meta[e].x;
+        }
+    }
+    __syncthreads();
+    {   // in-place exclusive scan of s_n[0..Ls)
+        const int chunk = (Ls + T - 1) / T, q0 = min(lt * chunk, Ls), q1 = min(q0 + chunk, Ls);
+        int sum = 0;
+        for (int k = q0; k < q1; k++) sum += s_n[k];
+        int tot;
+        int ex = block_excl_scan<int>(sum, &tot, s_scan);
+        for (int k = q0; k < q1; k++) { int t = s_n[k]; s_n[k] = ex; ex += t; }
+    }
+    __syncthreads();
+    for (int c = 0; c < ncolors; c++) {
+        const int cnt = s_lbase[c + 1] - s_lbase[c];
+        for (int i = lt; i < cnt; i += T) {
+            int ls = s_lbase[c] + i;
+            if (ls >= SLOTCAP) continue;
+            int e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
             int2 b = a.cur.bodies[e];
             int2 mt = a.cur.meta[e];
             float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
-            float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
-            Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
-            for (int q = 0; q < mt.x; q++) {
-                int ci = mt.y + q;
-                float4 ca = a.cur.ca[ci], cc = a.cur.cc[ci], cd = a.cur.cd[ci];
-                ContactConst k0;
-                contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, mk(p1.x, p1.y), mk(p2.x, p2.y), m1.x, m1.y, m2.x, m2.y,
-                                a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
-                a.cur.ca[ci] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
-                a.cur.cb[ci] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
-                a.cur.cc[ci] = make_float4(k0.bias, cc.y, cc.z, cc.w);
-            }
-            if (acc) {
-                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
-                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+            int lc = s_n[ls];
+            const bool res = lc + mt.x <= CONCAP;
+            s_rec[2 * ls] = make_float4(__int_as_float(b.x), __int_as_float(b.y), __int_as_float(res ? (lc << 8) | mt.x : -1), a.cur.friction[e]);
+            s_rec[2 * ls + 1] = make_float4(m1.x, m1.y, m2.x, m2.y);
+            if (res)
+                for (int q = 0; q < mt.x; q++) {
+                    s_ca[lc + q] = a.cur.ca[mt.y + q];
+                    s_cc[lc + q] = a.cur.cc[mt.y + q];
+                }
+        }
+    }
+    __syncthreads();
+
+    auto view = [&](int c, int i, SlotView& v) -> int {  // returns the arbiter index e when the slot lives in global memory, else -1
+        int ls = s_lbase[c] + i;
+        if (ls < SLOTCAP) {
+            float4 r0 = s_rec[2 * ls];
+            int pk = __float_as_int(r0.z);
+            if (pk >= 0) {
+                float4 r1 = s_rec[2 * ls + 1];
+                v.b1 = __float_as_int(r0.x); v.b2 = __float_as_int(r0.y); v.n = pk & 0xff; v.fr = r0.w;
+                v.im1 = r1.x; v.ii1 = r1.y; v.im2 = r1.z; v.ii2 = r1.w;
+                int lc = pk >> 8;
+                v.ca = s_ca + lc; v.cb = s_cb + lc; v.cc = s_cc + lc;
+                return -1;
             }
         }
-        if (acc) grid.sync();
-    }
-    if (!acc) grid.sync();
+        int e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
+        int2 b = a.cur.bodies[e];
+        int2 mt = a.cur.meta[e];
+        float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
+        v.b1 = b.x; v.b2 = b.y; v.n = mt.x; v.fr = a.cur.friction[e];
+        v.im1 = m1.x; v.ii1 = m1.y; v.im2 = m2.x; v.ii2 = m2.y;
+        v.ca = a.cur.ca + mt.y; v.cb = a.cur.cb + mt.y; v.cc = a.cur.cc + mt.y;
+        return e;
+    };
 
-    // ---- 4. Joint::pre_step, joint colours (host-coloured, static graph)
+    // ---- 4. Arbiter::pre_step, colour by colour (warm-start impulses write body velocities)
+    for (int c = 0; c < ncolors; c++) {
+        const int cnt = s_lbase[c + 1] - s_lbase[c];
+        for (int i = lt; i < cnt; i += T) {
+            SlotView v;
+            int e = view(c, i, v);
+            int coff = 0;
+            if (e < 0) e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
+            coff = a.cur.meta[e].y;
+            float4 p1 = a.pose[v.b1], p2 = a.pose[v.b2];
+            Vel v1 = load_vel(a.vel, v.b1), v2 = load_vel(a.vel, v.b2);
+            for (int q = 0; q < v.n; q++) {
+                float4 ca = v.ca[q], cc = v.cc[q], cd = a.cur.cd[coff + q];
+                ContactConst k0;
+                contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, mk(p1.x, p1.y), mk(p2.x, p2.y), v.im1, v.ii1, v.im2, v.ii2,
+                                a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
+                v.ca[q] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
+                v.cb[q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
+                v.cc[q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
+            }
+            if (acc) {
+                if (v.im1 != 0.0f || v.ii1 != 0.0f) store_vel(a.vel, v.b1, v1);
+                if (v.im2 != 0.0f || v.ii2 != 0.0f) store_vel(a.vel, v.b2, v2);
+            }
+        }
+        if (acc) grid_barrier(bar, bar_target);
+    }
+    if (!acc) grid_barrier(bar, bar_target);
+
+    // ---- 5. Joint::pre_step, joint colours (host-coloured, static graph)
     for (int c = 0; c < a.n_joint_colors; c++) {
         for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
             int j = a.jorder[k];
@@ -617,34 +764,31 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
                 if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
             }
         }
-        grid.sync();
+        grid_barrier(bar, bar_target);
     }
-    if (*(volatile int*)&cn->err == SYLT_ERR_NO_INVERSE) return;
+    const bool aborted = *(volatile int*)&cn->err == SYLT_ERR_NO_INVERSE;
 
-    // ---- 5. iterations x (arbiter colours, joint colours)   (world.rs:132-140)
-    for (int it = 0; it < a.iterations; it++) {
+    // ---- 6. iterations x (arbiter colours, joint colours)   (world.rs:132-140)
+    for (int it = 0; it < (aborted ? 0 : a.iterations); it++) {
         for (int c = 0; c < ncolors; c++) {
-            for (int k = s_start[c] + tid; k < s_start[c + 1]; k += nth) {
-                int e = a.order[k];
-                int2 b = a.cur.bodies[e];
-                int2 mt = a.cur.meta[e];
-                float fr = a.cur.friction[e];
-                float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
-                Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
-                for (int q = 0; q < mt.x; q++) {
-                    int ci = mt.y + q;
-                    float4 ca = a.cur.ca[ci], cb = a.cur.cb[ci], cc = a.cur.cc[ci];
+            const int cnt = s_lbase[c + 1] - s_lbase[c];
+            for (int i = lt; i < cnt; i += T) {
+                SlotView v;
+                view(c, i, v);
+                Vel v1 = load_vel(a.vel, v.b1), v2 = load_vel(a.vel, v.b2);
+                for (int q = 0; q < v.n; q++) {
+                    float4 ca = v.ca[q], cb = v.cb[q], cc = v.cc[q];
                     ContactConst k0;
                     k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
                     k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
                     float pn = cc.y, pt = cc.z;
-                    contact_apply(k0, fr, m1.x, m1.y, m2.x, m2.y, acc, pn, pt, v1, v2);
-                    if (acc) a.cur.cc[ci] = make_float4(cc.x, pn, pt, cc.w);
+                    contact_apply(k0, v.fr, v.im1, v.ii1, v.im2, v.ii2, acc, pn, pt, v1, v2);
+                    if (acc) v.cc[q] = make_float4(cc.x, pn, pt, cc.w);
                 }
-                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
-                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+                if (v.im1 != 0.0f || v.ii1 != 0.0f) store_vel(a.vel, v.b1, v1);
+                if (v.im2 != 0.0f || v.ii2 != 0.0f) store_vel(a.vel, v.b2, v2);
             }
-            grid.sync();
+            grid_barrier(bar, bar_target);
         }
         for (int c = 0; c < a.n_joint_colors; c++) {
             for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
@@ -664,11 +808,30 @@ __global__ void __launch_bounds__(256) k_solve(SolveArgs a) {
                 if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
                 if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
             }
-            grid.sync();
+            grid_barrier(bar, bar_target);
         }
     }
 
-    // ---- 6. integrate positions, clear forces (world.rs:143-150; static bodies too, quirk Q-16)
+    // ---- 7. write the shared-memory resident contacts back (warm start of the next step, read-back)
+    for (int c = 0; c < ncolors; c++) {
+        const int cnt = s_lbase[c + 1] - s_lbase[c];
+        for (int i = lt; i < cnt; i += T) {
+            int ls = s_lbase[c] + i;
+            if (ls >= SLOTCAP) continue;
+            int pk = __float_as_int(s_rec[2 * ls].z);
+            if (pk < 0) continue;
+            int e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
+            int coff = a.cur.meta[e].y, lc = pk >> 8, n = pk & 0xff;
+            for (int q = 0; q < n; q++) {
+                a.cur.ca[coff + q] = s_ca[lc + q];
+                a.cur.cb[coff + q] = s_cb[lc + q];
+                a.cur.cc[coff + q] = s_cc[lc + q];
+            }
+        }
+    }
+    if (aborted) return;
+
+    // ---- 8. integrate positions, clear forces (world.rs:143-150; static bodies too, quirk Q-16)
     for (int i = tid; i < a.B; i += nth) {
         float4 p = a.pose[i];
         float4 v = __ldcg(&a.vel[i]);
@@ -732,7 +895,9 @@ struct SyltWorld {
     uint32_t iterations = 10;
     int accumulate = 1, warm = 0, poscorr = 1;  // World::new defaults (world.rs:38-42, quirk Q-4)
     int64_t launches = 0;
-    int num_sms = 0, coop_blocks = 0;
+    int num_sms = 0, coop_blocks = 0, smem_slots = 0, smem_contacts = 0;
+    size_t solve_smem = 0;
+    int spread = 2;
 
     // host mirror of construction-time data
     std::vector<HostBody> hb;
@@ -750,7 +915,7 @@ struct SyltWorld {
     // device state
     DBuf<float4> pose, vel, force, mp, geom, aabb;
     DBuf<float2> rotc, lverts;
-    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, cell_bodies, large, row_count, row_start;
+    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, cell_bodies, large, row_count, row_start, row_tmp;
     DBuf<int4> cinfo;
     DBuf<int2> pairs;
     DBuf<unsigned long long> info, pscan, claim, spart64;
@@ -873,6 +1038,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->cell_bodies.ensure(B));
         SYLT_CUDA(w->row_count.ensure(B + 1));
         SYLT_CUDA(w->row_start.ensure(B + 2));
+        SYLT_CUDA(w->row_tmp.ensure(B * ROWTMP));
         SYLT_CUDA(w->used.ensure(B));
         SYLT_CUDA(w->large.ensure(B));
         for (int k = 0; k < 2; k++) SYLT_CUDA(w->arb[k].row_start.ensure(B + 2, (size_t)w->B_old + 1, w->stream));
@@ -1028,14 +1194,14 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (e) return e;
     k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->rank.p, w->cell_start.p, w->cell_bodies.p, w->gp);
     const int nbR = (B + 127) / 128;
-    k_rows<false><<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
-                                       w->row_count.p, nullptr, nullptr, 0, cn);
+    k_rows_count<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
+                                      w->row_count.p, w->row_tmp.p);
     w->launches += 2;
     e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->tot32.p + 1);
     if (e) return e;
     k_totals<<<1, 1, 0, st>>>(cn, w->tot32.p + 1, nullptr, 0, (int)w->cap_pairs);
-    k_rows<true><<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
-                                      nullptr, w->row_start.p, w->pairs.p, (int)w->cap_pairs, cn);
+    k_rows_emit<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
+                                     w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn);
     w->launches += 2;
     const int gridP = w->num_sms * 8;
     if (w->any_poly)
@@ -1077,7 +1243,8 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     a.jbodies = w->jbodies.p; a.jla = w->jla.p; a.jparam = w->jparam.p; a.jp = w->jp.p; a.jr = w->jr.p; a.jm = w->jm.p; a.jbias = w->jbias.p;
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
     void* args[] = {&a};
-    SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3(256), args, 0, st));
+    a.smem_slots = w->smem_slots; a.smem_contacts = w->smem_contacts; a.spread = w->spread;
+    SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3(SOLVE_THREADS), args, w->solve_smem, st));
     w->launches++;
     // the set just built becomes "last step's"
     w->cur ^= 1;
@@ -1149,10 +1316,25 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     int coop = 0;
     SYLT_CUDA(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     if (!coop) { delete w; set_last_error("device lacks cooperative launch"); return SYLT_ERR_CUDA; }
+    // k_solve: one persistent CTA per SM; its shared memory holds the CTA's share of arbiter records and contact constants
+    int max_smem = 0;
+    SYLT_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+    cudaFuncAttributes fa;
+    SYLT_CUDA(cudaFuncGetAttributes(&fa, k_solve));
+    size_t budget = (size_t)max_smem - fa.sharedSizeBytes - 1024;
+    w->smem_slots = 1792;
+    if (const char* ev = getenv("SYLT_COLOR_SPREAD")) w->spread = std::min(8, std::max(1, atoi(ev)));
+    if (const char* ev = getenv("SYLT_SOLVER_SMEM_SLOTS")) w->smem_slots = std::max(0, atoi(ev));  // tests: force the global-memory path
+    size_t fixed = (size_t)w->smem_slots * 32 + (((size_t)w->smem_slots + 3) & ~(size_t)3) * 4;
+    if (fixed + 48 > budget) { w->smem_slots = 0; fixed = 0; }
+    w->smem_contacts = w->smem_slots ? (int)((budget - fixed) / 48) : 0;
+    if (const char* ev = getenv("SYLT_SOLVER_SMEM_CONTACTS")) w->smem_contacts = std::min(w->smem_contacts, std::max(0, atoi(ev)));
+    w->solve_smem = fixed + (size_t)w->smem_contacts * 48;
+    SYLT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_smem));
     int per_sm = 0;
-    SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, 256, 0));
+    SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, SOLVE_THREADS, w->solve_smem));
     if (per_sm < 1) { delete w; set_last_error("k_solve does not fit on an SM"); return SYLT_ERR_CUDA; }
-    w->coop_blocks = w->num_sms * std::min(per_sm, 2);
+    w->coop_blocks = w->num_sms;
     SYLT_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     SYLT_CUDA(cudaEventCreate(&w->ev0));
     SYLT_CUDA(cudaEventCreate(&w->ev1));
@@ -1166,7 +1348,7 @@ static void free_all(SyltWorld* w) {
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cell_bodies.release(); w->large.release(); w->row_count.release();
-    w->row_start.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
+    w->row_start.release(); w->row_tmp.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
     w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->uncolored.release();
     w->prop.release(); w->order.release(); w->tot32.release(); w->tot64.release();
     for (int k = 0; k < 2; k++) {

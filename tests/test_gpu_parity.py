@@ -433,3 +433,59 @@ def test_batch_multi_step_launch_equals_single_steps_and_shards():
         _assert_states_equal(np.concatenate(parts), ref, f"shards={ws}")
     st = full.stats()
     assert st["body_steps"] == n * nb * 45 and st["errors"] == 0 and st["contacts"] > 0
+
+
+# ------------------------------------------------------------------ BASELINE.json full-size configurations
+def _lockstep_big(sc, settle, steps):
+    from sylt2d_b200 import World
+    w = World(sc.gravity, sc.iterations, device=0)
+    w.load_scene(sc)
+    w.step_n(sc.dt, settle)                       # get into the interesting regime on the GPU ...
+    o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=1, broadphase=1)   # grid candidates == all-pairs set (CPU test)
+    o.load_scene(sc)
+    st = w.get_bodies()
+    o.set_bodies(st)                              # ... then hand the same state to both and compare from there
+    w2 = World(sc.gravity, sc.iterations, device=0)
+    w2.load_scene(sc)
+    w2.set_bodies(st)
+    for s in range(steps):
+        w2.step(sc.dt)
+        keys, jo = w2.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w2.get_bodies(), o.get_bodies(), f"{sc.name} step {s}")
+    _assert_arbiters_equal(w2, o, what=sc.name)
+    return w2
+
+
+def test_config2_mixed_pile_10k_bit_exact():
+    sc = scenes.mixed_pile(10000, seed=1234)
+    w = _lockstep_big(sc, 150, 4)
+    st = w.get_stats()
+    assert st["arbiters"] > 3000 and st["contacts"] > st["arbiters"]
+
+
+def test_config3_box_drop_100k_bit_exact():
+    sc = scenes.box_drop(100000, seed=42)
+    w = _lockstep_big(sc, 200, 3)
+    st = w.get_stats()
+    assert st["bodies"] == 100003 and st["arbiters"] > 50000
+
+
+def test_config4_joint_worlds_batch_properties():
+    # 8192 joint worlds (4096 bridge + 4096 multi-pendulum): size-independent properties at full size —
+    # no errors, finite state, planks stay attached (bounded distance from their anchors), identical worlds stay identical
+    from sylt2d_b200 import Batch
+    for sc, jit in ((scenes.bridge(10), 0.0), (scenes.multi_pendulum(10), 1.0)):
+        n = 4096
+        bodies, boff, joints, joff = scenes.tile_worlds(sc, n, seed=5, omega_jitter=jit)
+        b = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, ctx=sc.ctx)
+        b.step_n(sc.dt, 120)
+        st = b.get_bodies()
+        assert not b.get_errors().any()
+        assert np.isfinite(st["x"]).all() and np.isfinite(st["y"]).all()
+        nb = sc.num_bodies
+        if jit == 0.0:  # unperturbed copies must be bit-identical across the batch
+            first = st[:nb].tobytes()
+            for k in (1, 777, n - 1):
+                assert st[k * nb:(k + 1) * nb].tobytes() == first
+        assert np.abs(st["x"]).max() < 60 and st["y"].min() > -30

@@ -220,3 +220,22 @@ def test_collision_debug_polygon_setups():
     exp = narrow_np.collide_polys(HEXAGON, (0, 0), 0.0, narrow_np.BOX_VERTS((2.0, 2.0)), (1.0, 0.5), 0.3, sc)
     assert len(got) >= 3
     _same_contacts(got, exp)
+
+
+# ------------------------------------------------------------------ oracle self-consistency at scale
+@pytest.mark.parametrize("seed", [1, 2])
+def test_oracle_grid_broad_phase_equals_all_pairs(seed):
+    """The oracle's grid candidate mode (used for full-size parity runs and the algorithm-matched CPU number) must
+    produce exactly the arbiter set of the reference's all-pairs loop (src/world.rs:74-103)."""
+    from sylt2d_b200 import scenes
+    sc = scenes.mixed_pile(600, seed=seed, across=30)
+    a = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=0, broadphase=0)
+    b = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=0, broadphase=1)
+    a.load_scene(sc)
+    b.load_scene(sc)
+    for s in range(110):
+        a.step(sc.dt)
+        b.step(sc.dt)
+    assert a.get_bodies().tobytes() == b.get_bodies().tobytes()
+    (aa, ac), (ba, bc) = a.get_arbiters(), b.get_arbiters()
+    assert aa.shape[0] > 100 and aa.tobytes() == ba.tobytes() and ac.tobytes() == bc.tobytes()
