@@ -1,9 +1,10 @@
-//! sylt-2d with World::step on a B200 (libsylt2d_b200).  Module layout mirrors the reference crate
-//! (/root/reference/src/lib.rs:1-9); `draw` (terminal ASCII renderer) is out of scope.
+//! sylt-2d with World::step on a B200 (libsylt2d_b200).  Public module paths are those of the crate being replaced;
+//! `draw` (terminal ASCII renderer) is out of scope.  NOT COMPILED in this repository's environment (no rustc).
 pub mod arbiter;
 pub mod body;
-pub mod errors;
 pub mod ffi;
 pub mod joint;
-pub mod math_utils;
+mod types;
 pub mod world;
+pub mod math_utils { pub use crate::types::{Cross, Mat2x2, MathErrors, Vec2}; }
+pub mod errors { pub use crate::types::Sylt2DErrors; }
