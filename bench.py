@@ -10,7 +10,7 @@ CUDA events on the launching stream, max over ranks.
 
   value  : device-resident throughput (state stays in HBM; one k_batch_step launch per step)
   e2e    : the same metric through the C ABI with HOST buffers: every step uploads all body states from pinned host
-           memory (sylt_batch_set_bodies), steps, and reads all body states back (sylt_batch_get_bodies)
+           memory, steps, and reads all body states back (sylt_batch_step_host)
   roofline: algorithmic bytes of SURVEY.md §8(d)  (116 B + 56 P + 152 C + 144 J + I (120 C + 124 J)) per launch
            over the kernel's average launch duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
   cpu_baseline: the CPU oracle (C++ restatement of the Rust reference; the reference itself cannot be built here)
@@ -257,9 +257,7 @@ def main():
 
     def e2e_step():
         # the caller's state for the next step is the result of this one: the two pinned buffers alternate roles
-        assert L.sylt_batch_set_bodies(h, 0, my_worlds, bufs[0], my_bodies) == 0
-        assert L.sylt_batch_step_n(h, scene.dt, 1) == 0
-        assert L.sylt_batch_get_bodies(h, 0, my_worlds, bufs[1], my_bodies) == my_bodies
+        assert L.sylt_batch_step_host(h, scene.dt, 1, bufs[0], bufs[1]) == 0
         bufs.reverse()
 
     for _ in range(3):
@@ -316,7 +314,7 @@ def main():
                    "l2": "per-GPU state (bodies + per-world slot cache) exceeds the 126 MB L2 at N<=2; smaller shards are L2-resident by nature of strong scaling",
                    "contacts_per_world": C_w, "errors": errors_total},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": my_bodies * 36 * world_size, "d2h_bytes_per_step": my_bodies * 36 * world_size,
-                "steps": e2e_steps, "api": "sylt_batch_set_bodies + sylt_batch_step_n(1) + sylt_batch_get_bodies, pinned host buffers"},
+                "steps": e2e_steps, "api": "sylt_batch_step_host(dt, 1, in, out): all body states H2D + step + all body states D2H per step, pinned host buffers, world chunks pipelined over 4 streams"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "clocks": clocks,

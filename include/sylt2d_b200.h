@@ -191,6 +191,10 @@ int sylt_batch_set_context(SyltBatch* b, int accumulate_impulse, int warm_starti
 int sylt_batch_step_n(SyltBatch* b, float dt, int32_t n);
 int sylt_batch_step_n_async(SyltBatch* b, float dt, int32_t n);
 int sylt_batch_sync(SyltBatch* b);
+/* step_n with HOST buffers (pinned memory recommended): upload every body state from `in` (NULL: keep device state), run n
+ * steps, download every body state to `out` (NULL: skip).  World chunks are pipelined over several streams so that the
+ * H2D copy, the kernels and the D2H copy overlap.  Equivalent to set_bodies + step_n + get_bodies. */
+int sylt_batch_step_host(SyltBatch* b, float dt, int32_t n, const SyltBodyState* in, SyltBodyState* out);
 int sylt_batch_timer_start(SyltBatch* b);
 int sylt_batch_timer_stop(SyltBatch* b, float* out_ms);
 int64_t sylt_batch_launch_count(SyltBatch* b);

@@ -56,6 +56,14 @@ class Batch:
     def sync(self):
         check(self.L.sylt_batch_sync(self.h))
 
+    def step_host(self, dt, n, states_in=None, states_out=None):
+        """set_bodies + step_n + get_bodies in one pipelined call on HOST arrays (BODY_STATE, ideally pinned)."""
+        nb = self.num_bodies
+        for a in (states_in, states_out):
+            assert a is None or (a.dtype == BODY_STATE and a.shape[0] == nb and a.flags["C_CONTIGUOUS"])
+        check(self.L.sylt_batch_step_host(self.h, dt, n, ptr(states_in), ptr(states_out)))
+        return states_out
+
     def timer_start(self):
         check(self.L.sylt_batch_timer_start(self.h))
 

@@ -29,6 +29,7 @@ namespace {
 constexpr int BNC = 32;        // colours per world
 constexpr int MAX_JC = 16;     // joint colours per world
 constexpr unsigned char NO_COLOR = 0xff;
+constexpr int ROWT = 8;         // partners remembered per row between the count and the emit pass
 
 struct SlotExport {  // full record of one arbiter slot, written for worlds in the export range only
     unsigned key;    // body1 << 16 | body2 (indices local to the world)
@@ -41,14 +42,15 @@ struct SlotExport {  // full record of one arbiter slot, written for worlds in t
 };
 
 struct BatchArgs {
-    int n_worlds, n_steps, iterations, accumulate, warm, poscorr;
-    float dt, inv_dt, gx, gy;
-    int Bmax, Jmax, cap;
+    int n_worlds, world_begin, n_steps, iterations, accumulate, warm, poscorr;
+    float dt, inv_dt, gx, gy, cell;
+    int Bmax, Jmax, cap, nbk;
     int export_first, export_count;
     const int *body_off, *joint_off;
     float4 *pose, *vel;              // (x,y,rot,_), (vx,vy,w,_)
     const float4* mp;                // (inv_mass, inv_moi, friction, _)
     const float2* wh;                // Body.width
+    const unsigned char* bflags;     // bit0 static, bit1 large (bypasses the grid)
     const int2* jbodies;             // world-local body indices
     const float4* jla;
     const float2* jparam;
@@ -72,14 +74,15 @@ struct BatchArgs {
 };
 
 struct Smem {
-    float2* pos; float* rot; float2* cs; float4* vel; float2* inv; float2* wh; float* fric; float4* aabb; unsigned char* stat;
+    float2* pos; float* rot; float2* cs; float4* vel; float2* inv; float4* aabb; unsigned char* stat;
     unsigned* used;
     int* rowcnt;                       // Bmax + 1
+    int2* cxy; int* bstart; unsigned short* cellb; unsigned short* rank; unsigned short* rowtmp; unsigned short* large;
     // slots
-    unsigned* key; float* sfric; float2* nrm; unsigned char* cnt; unsigned char* color; unsigned* feat; float* con;  // con: cap*2*9
+    unsigned* key; float* sfric; float2* nrm; unsigned char* cnt; unsigned char* color; float* con;  // con: cap*2*9
     unsigned short* order;
     // old cache
-    unsigned* okey; float* ofric; float* opn; float* opt; unsigned char* ocolor;
+    unsigned* okey; unsigned char* ocolor;  // last step's slots: keys + colours here, (friction, pn0, pt0) stay in global memory
     // joints
     int2* jb; float4* jla; float2* jparam; float2* jp; float4* jr; float4* jm; float2* jbias; unsigned short* jorder;
     int* misc;                         // scan scratch (40) + colour bins
@@ -88,21 +91,33 @@ struct Smem {
 __host__ __device__ inline size_t align16(size_t x) { return (x + 15) & ~(size_t)15; }
 
 // identical carve-up on host (size only) and device
-__host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int B, int J, int cap) {
+__host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int B, int J, int cap, int nbk) {
     size_t o = 0;
 #define TAKE(field, type, n)                          \
     do {                                              \
         if (s) s->field = (type*)(base + o);          \
         o = align16(o + sizeof(type) * (size_t)(n)); \
     } while (0)
-    TAKE(pos, float2, B); TAKE(rot, float, B); TAKE(cs, float2, B); TAKE(vel, float4, B); TAKE(inv, float2, B); TAKE(wh, float2, B);
-    TAKE(fric, float, B); TAKE(aabb, float4, B); TAKE(stat, unsigned char, B); TAKE(used, unsigned, B); TAKE(rowcnt, int, B + 1);
+    TAKE(pos, float2, B); TAKE(rot, float, B); TAKE(cs, float2, B); TAKE(vel, float4, B); TAKE(inv, float2, B);
+    TAKE(stat, unsigned char, B); TAKE(used, unsigned, B); TAKE(large, unsigned short, B + 1);
     TAKE(key, unsigned, cap); TAKE(sfric, float, cap); TAKE(nrm, float2, cap); TAKE(cnt, unsigned char, cap); TAKE(color, unsigned char, cap);
-    TAKE(feat, unsigned, 2 * cap); TAKE(con, float, 18 * cap); TAKE(order, unsigned short, cap);
-    TAKE(okey, unsigned, cap); TAKE(ofric, float, cap); TAKE(opn, float, cap); TAKE(opt, float, cap); TAKE(ocolor, unsigned char, cap);
+    // the contact-constant region doubles as broad-phase scratch (dead before the narrow phase writes contacts)
+    const size_t scratch = align16(sizeof(float4) * (size_t)B) + align16(sizeof(int) * (size_t)(B + 1)) + align16(sizeof(int2) * (size_t)B) +
+                           align16(sizeof(int) * (size_t)(nbk + 1)) + 2 * align16(sizeof(unsigned short) * (size_t)B) +
+                           align16(sizeof(unsigned short) * (size_t)B * ROWT);
+    const size_t con_floats = (size_t)18 * cap > scratch / 4 ? (size_t)18 * cap : scratch / 4;
+    const size_t con_at = o;
+    TAKE(con, float, con_floats);
+    TAKE(order, unsigned short, cap);
+    TAKE(okey, unsigned, cap); TAKE(ocolor, unsigned char, cap);
     TAKE(jb, int2, J + 1); TAKE(jla, float4, J + 1); TAKE(jparam, float2, J + 1); TAKE(jp, float2, J + 1); TAKE(jr, float4, J + 1);
     TAKE(jm, float4, J + 1); TAKE(jbias, float2, J + 1); TAKE(jorder, unsigned short, J + 1);
     TAKE(misc, int, 40 + 3 * BNC + 8);
+    const size_t total = o;
+    o = con_at;
+    TAKE(aabb, float4, B); TAKE(rowcnt, int, B + 1); TAKE(cxy, int2, B); TAKE(bstart, int, nbk + 1); TAKE(cellb, unsigned short, B);
+    TAKE(rank, unsigned short, B); TAKE(rowtmp, unsigned short, B * ROWT);
+    o = total;
 #undef TAKE
     return o;
 }
@@ -140,21 +155,29 @@ __device__ int block_scan_inplace(int* a, int n, int* sh /* 34 ints */) {
     return total;
 }
 
+// slot key = owner << 16 | partner (slot order); body1 = lower index (Arbiter::new, arbiter.rs:120-122)
+__device__ __forceinline__ void key_bodies(unsigned key, int& b1, int& b2) {
+    int x = (int)(key >> 16), y = (int)(key & 0xffffu);
+    b1 = min(x, y); b2 = max(x, y);
+}
+__device__ __forceinline__ int cellc(float x, float cell) { return (int)fminf(fmaxf(floorf(x / cell), -1.0e9f), 1.0e9f); }
+__device__ __forceinline__ int cellh(int cx, int cy, int mask) { return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u)) & mask; }
+
 __device__ __forceinline__ bool overlap4(float4 a, float4 b) { return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w); }
 
 __device__ __forceinline__ Vel ld_vel(const float4* v, int b) { float4 t = v[b]; Vel o; o.v = mk(t.x, t.y); o.w = t.z; return o; }
 __device__ __forceinline__ void st_vel(float4* v, int b, const Vel& x) { v[b] = make_float4(x.v.x, x.v.y, x.w, 0.0f); }
 
-__global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
+__global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    const int wld = blockIdx.x;
+    const int wld = blockIdx.x + a.world_begin;
     if (wld >= a.n_worlds) return;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
     const int b0 = a.body_off[wld], B = a.body_off[wld + 1] - b0;
     const int j0 = a.joint_off[wld], J = a.joint_off[wld + 1] - j0;
     const int cap = a.cap;
     Smem s;
-    carve(&s, smem_raw, a.Bmax, a.Jmax, cap);
+    carve(&s, smem_raw, a.Bmax, a.Jmax, cap, a.nbk);
     int* scan_sh = s.misc;           // 34
     int* s_P = s.misc + 36;          // current candidate count
     int* s_Pold = s.misc + 37;
@@ -166,9 +189,8 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
     // ---- load the world
     for (int i = tid; i < B; i += T) {
         float4 p = a.pose[b0 + i], v = a.vel[b0 + i], m = a.mp[b0 + i];
-        s.pos[i] = make_float2(p.x, p.y); s.rot[i] = p.z; s.vel[i] = v; s.inv[i] = make_float2(m.x, m.y); s.fric[i] = m.z;
-        s.wh[i] = a.wh[b0 + i];
-        s.stat[i] = (m.x == 0.0f) ? 1 : 0;
+        s.pos[i] = make_float2(p.x, p.y); s.rot[i] = p.z; s.vel[i] = v; s.inv[i] = make_float2(m.x, m.y);
+        s.stat[i] = a.bflags[b0 + i];
     }
     for (int j = tid; j < J; j += T) {
         s.jb[j] = a.jbodies[j0 + j]; s.jla[j] = a.jla[j0 + j]; s.jparam[j] = a.jparam[j0 + j]; s.jp[j] = a.jp[j0 + j];
@@ -178,9 +200,15 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
     const int Pold0 = min(a.c_count[wld], cap);
     for (int k = tid; k < Pold0; k += T) {
         size_t g = (size_t)wld * cap + k;
-        s.okey[k] = a.c_key[g]; s.ofric[k] = a.c_fric[g]; s.opn[k] = a.c_pn[g]; s.opt[k] = a.c_pt[g]; s.ocolor[k] = a.c_color[g];
+        s.okey[k] = a.c_key[g]; s.ocolor[k] = a.c_color[g];
     }
-    if (tid == 0) { *s_Pold = Pold0; *s_err = a.w_err[wld]; *s_P = 0; }
+    if (tid == 0) {
+        *s_Pold = Pold0; *s_err = a.w_err[wld]; *s_P = 0;
+        int nl = 0;
+        for (int i = 0; i < B; i++)
+            if (a.bflags[b0 + i] & 2) s.large[nl++] = (unsigned short)i;
+        s.misc[34] = nl;
+    }
     const int njc = a.n_jcolors[wld];
     const int* jcs = a.jcolor_start + (size_t)wld * (MAX_JC + 1);
     __syncthreads();
@@ -198,7 +226,7 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
             float r = s.rot[i];
             float c = sylt_cosf(r), sn = sylt_sinf(r);
             s.cs[i] = make_float2(c, sn);
-            float2 p = s.pos[i], w = s.wh[i];
+            float2 p = s.pos[i], w = a.wh[b0 + i];
             float hx = w.x * 0.5f, hy = w.y * 0.5f;
             float ex = fabsf(c) * hx + fabsf(sn) * hy, ey = fabsf(sn) * hx + fabsf(c) * hy;
             float mg = 1.0e-6f * (fabsf(p.x) + fabsf(p.y)) + 2.0e-5f * (ex + ey) + 1.0e-6f;
@@ -215,17 +243,64 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
         }
         for (int c = tid; c < 3 * BNC + 1; c += T) ccount[c] = 0;
         __syncthreads();
-        // ---- 2. candidate rows (warp per row, lanes over j): count, scan, emit in (i, j) order
-        for (int i = warp; i < B; i += nwarps) {
-            float4 my = s.aabb[i];
-            const bool st = s.stat[i] != 0;
-            int n = 0;
-            for (int jb = i + 1; jb < B; jb += 32) {
-                int j = jb + lane;
-                bool hit = j < B && !(st && s.stat[j]) && overlap4(my, s.aabb[j]);
-                n += __popc(__ballot_sync(0xffffffffu, hit));
+        // ---- 2. candidate rows through a hashed uniform grid in shared memory (large bodies bypass it):
+        //         bucket counts -> scan -> fill; thread per body: count (remembering partners) -> scan -> emit sorted.
+        //         A pair is owned by its lower index, a small-large pair by the small body (slot order = (owner, partner)).
+        const int nbk = a.nbk, nl = s.misc[34];
+        for (int k = tid; k <= nbk; k += T) s.bstart[k] = 0;
+        __syncthreads();
+        for (int i = tid; i < B; i += T) {
+            if (s.stat[i] & 2) continue;
+            float4 ab = s.aabb[i];
+            int cx = cellc(0.5f * (ab.x + ab.z), a.cell), cy = cellc(0.5f * (ab.y + ab.w), a.cell);
+            s.cxy[i] = make_int2(cx, cy);
+            s.rank[i] = (unsigned short)atomicAdd(&s.bstart[cellh(cx, cy, nbk - 1)], 1);
+        }
+        __syncthreads();
+        block_scan_inplace(s.bstart, nbk + 1, scan_sh);
+        for (int i = tid; i < B; i += T) {
+            if (s.stat[i] & 2) continue;
+            int2 c = s.cxy[i];
+            s.cellb[s.bstart[cellh(c.x, c.y, nbk - 1)] + s.rank[i]] = (unsigned short)i;
+        }
+        __syncthreads();
+        auto row_search = [&](int i, auto&& found) {
+            const float4 my = s.aabb[i];
+            const int fl = s.stat[i];
+            if (!(fl & 2)) {
+                int x0 = cellc(my.x - 0.5f * a.cell, a.cell), x1 = cellc(my.z + 0.5f * a.cell, a.cell);
+                int y0 = cellc(my.y - 0.5f * a.cell, a.cell), y1 = cellc(my.w + 0.5f * a.cell, a.cell);
+                for (int cy = y0; cy <= y1; cy++)
+                    for (int cx = x0; cx <= x1; cx++) {
+                        int h = cellh(cx, cy, nbk - 1);
+                        for (int k = s.bstart[h]; k < s.bstart[h + 1]; k++) {
+                            int j = s.cellb[k];
+                            if (j <= i) continue;
+                            int2 cj = s.cxy[j];
+                            if (cj.x != cx || cj.y != cy) continue;
+                            if ((fl & 1) && (s.stat[j] & 1)) continue;
+                            if (overlap4(my, s.aabb[j])) found(j);
+                        }
+                    }
+                for (int k = 0; k < nl; k++) {
+                    int j = s.large[k];
+                    if ((fl & 1) && (s.stat[j] & 1)) continue;
+                    if (overlap4(my, s.aabb[j])) found(j);
+                }
+            } else {
+                for (int k = 0; k < nl; k++) {
+                    int j = s.large[k];
+                    if (j <= i) continue;
+                    if ((fl & 1) && (s.stat[j] & 1)) continue;
+                    if (overlap4(my, s.aabb[j])) found(j);
+                }
             }
-            if (lane == 0) s.rowcnt[i] = n;
+        };
+        for (int i = tid; i < B; i += T) {
+            int n = 0;
+            unsigned short* tmp = s.rowtmp + i * ROWT;
+            row_search(i, [&](int j) { if (n < ROWT) tmp[n] = (unsigned short)j; n++; });
+            s.rowcnt[i] = n;
         }
         __syncthreads();
         P = block_scan_inplace(s.rowcnt, B, scan_sh);
@@ -234,16 +309,31 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
             __syncthreads();
             break;
         }
-        for (int i = warp; i < B; i += nwarps) {
-            float4 my = s.aabb[i];
-            const bool st = s.stat[i] != 0;
-            int base = s.rowcnt[i];
-            for (int jb = i + 1; jb < B; jb += 32) {
-                int j = jb + lane;
-                bool hit = j < B && !(st && s.stat[j]) && overlap4(my, s.aabb[j]);
-                unsigned m = __ballot_sync(0xffffffffu, hit);
-                if (hit) s.key[base + __popc(m & ((1u << lane) - 1))] = ((unsigned)i << 16) | (unsigned)j;
-                base += __popc(m);
+        for (int i = tid; i < B; i += T) {
+            const int base = s.rowcnt[i], n = (i + 1 < B ? s.rowcnt[i + 1] : P) - base;
+            if (n == 0) continue;
+            if (n <= ROWT) {
+                unsigned short v[ROWT];
+                const unsigned short* tmp = s.rowtmp + i * ROWT;
+#pragma unroll
+                for (int q = 0; q < ROWT; q++) v[q] = q < n ? tmp[q] : (unsigned short)0xffff;
+#pragma unroll
+                for (int q = 1; q < ROWT; q++) {  // insertion sort by partner
+                    unsigned short x = v[q];
+                    int r = q - 1;
+                    while (r >= 0 && v[r] > x) { v[r + 1] = v[r]; r--; }
+                    v[r + 1] = x;
+                }
+                for (int q = 0; q < n; q++) s.key[base + q] = ((unsigned)i << 16) | (unsigned)v[q];
+            } else {
+                int m = 0;
+                row_search(i, [&](int j) { s.key[base + m++] = ((unsigned)i << 16) | (unsigned)j; });
+                for (int q = 1; q < n; q++) {
+                    unsigned x = s.key[base + q];
+                    int r = q - 1;
+                    while (r >= 0 && s.key[base + r] > x) { s.key[base + r + 1] = s.key[base + r]; r--; }
+                    s.key[base + r + 1] = x;
+                }
             }
         }
         __syncthreads();
@@ -251,9 +341,10 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
         const int Pold = *s_Pold;
         for (int p = tid; p < P; p += T) {
             unsigned key = s.key[p];
-            int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
+            int b1, b2;
+            key_bodies(key, b1, b2);
             ContactOut out[2];
-            float2 p1 = s.pos[b1], p2 = s.pos[b2], c1 = s.cs[b1], c2 = s.cs[b2], w1 = s.wh[b1], w2 = s.wh[b2];
+            float2 p1 = s.pos[b1], p2 = s.pos[b2], c1 = s.cs[b1], c2 = s.cs[b2], w1 = a.wh[b0 + b1], w2 = a.wh[b0 + b2];
             int n = box_box(mk(p1.x, p1.y), c1.x, c1.y, mk(w1.x, w1.y), mk(p2.x, p2.y), c2.x, c2.y, mk(w2.x, w2.y), out);
             s.cnt[p] = (unsigned char)n;
             unsigned char color = NO_COLOR;
@@ -262,29 +353,30 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (s.okey[mid] < key) lo = mid + 1; else hi = mid; }
                 float fr, pn = 0.0f, pt = 0.0f;
                 if (lo < Pold && s.okey[lo] == key && s.ocolor[lo] != NO_COLOR) {  // Arbiter::update (arbiter.rs:137-181)
-                    fr = s.ofric[lo];             // quirk Q-17
+                    const size_t g = (size_t)wld * cap + lo;  // written by this CTA at the end of the previous step
+                    fr = a.c_fric[g];              // quirk Q-17
                     color = s.ocolor[lo];
-                    if (warm) { pn = s.opn[lo]; pt = s.opt[lo]; }  // quirk Q-2: all contacts inherit old contact 0
+                    if (warm) { pn = a.c_pn[g]; pt = a.c_pt[g]; }  // quirk Q-2: all contacts inherit old contact 0
                 } else {
-                    fr = sqrtf(s.fric[b1] * s.fric[b2]);  // arbiter.rs:128
+                    fr = sqrtf(a.mp[b0 + b1].z * a.mp[b0 + b2].z);  // arbiter.rs:128
                 }
                 s.sfric[p] = fr;
                 s.nrm[p] = make_float2(out[0].nx, out[0].ny);
                 for (int q = 0; q < n; q++) {
                     float* cc = s.con + (size_t)(2 * p + q) * 9;
                     cc[0] = out[q].px; cc[1] = out[q].py; cc[6] = out[q].sep; cc[7] = pn; cc[8] = pt;
-                    s.feat[2 * p + q] = out[q].feat;
                 }
                 if (color != NO_COLOR) {
-                    if (!s.stat[b1]) atomicOr(&s.used[b1], 1u << color);
-                    if (!s.stat[b2]) atomicOr(&s.used[b2], 1u << color);
+                    if (!(s.stat[b1] & 1)) atomicOr(&s.used[b1], 1u << color);
+                    if (!(s.stat[b2] & 1)) atomicOr(&s.used[b2], 1u << color);
                     atomicAdd(&ccount[color], 1);
                 }
             }
             s.color[p] = color;
             if (exporting && step == a.n_steps - 1) {
                 SlotExport* e = &a.exp_slots[(size_t)(wld - a.export_first) * cap + p];
-                e->key = key; e->count = n; e->nx = n > 0 ? out[0].nx : 0.0f; e->ny = n > 0 ? out[0].ny : 0.0f;
+                { int kb1, kb2; key_bodies(key, kb1, kb2); e->key = ((unsigned)kb1 << 16) | (unsigned)kb2; }
+                e->count = n; e->nx = n > 0 ? out[0].nx : 0.0f; e->ny = n > 0 ? out[0].ny : 0.0f;
                 for (int q = 0; q < 2; q++) {
                     e->geo[q][0] = q < n ? out[q].px : 0.0f; e->geo[q][1] = q < n ? out[q].py : 0.0f; e->geo[q][2] = q < n ? out[q].sep : 0.0f;
                     e->feat[q] = q < n ? out[q].feat : 0u;
@@ -303,14 +395,15 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
                         int q = pb + __ffs(m) - 1;
                         m &= m - 1;
                         unsigned key = s.key[q];
-                        int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
-                        unsigned um = (s.stat[b1] ? 0u : s.used[b1]) | (s.stat[b2] ? 0u : s.used[b2]);
+                        int b1, b2;
+            key_bodies(key, b1, b2);
+                        unsigned um = ((s.stat[b1] & 1) ? 0u : s.used[b1]) | ((s.stat[b2] & 1) ? 0u : s.used[b2]);
                         unsigned fr = ~um;
                         if (!fr) { *s_err = SYLT_ERR_CAPACITY; continue; }
                         int c = __ffs(fr) - 1;
                         s.color[q] = (unsigned char)c;
-                        if (!s.stat[b1]) s.used[b1] |= 1u << c;
-                        if (!s.stat[b2]) s.used[b2] |= 1u << c;
+                        if (!(s.stat[b1] & 1)) s.used[b1] |= 1u << c;
+                        if (!(s.stat[b2] & 1)) s.used[b2] |= 1u << c;
                         ccount[c]++;
                     }
                 }
@@ -334,7 +427,8 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
             for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
                 int p = s.order[k];
                 unsigned key = s.key[p];
-                int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
+                int b1, b2;
+            key_bodies(key, b1, b2);
                 float2 i1 = s.inv[b1], i2 = s.inv[b2], p1 = s.pos[b1], p2 = s.pos[b2], nn = s.nrm[p];
                 Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
                 int n = s.cnt[p];
@@ -393,7 +487,8 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
                 for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
                     int p = s.order[k];
                     unsigned key = s.key[p];
-                    int b1 = (int)(key >> 16), b2 = (int)(key & 0xffffu);
+                    int b1, b2;
+            key_bodies(key, b1, b2);
                     float2 i1 = s.inv[b1], i2 = s.inv[b2], nn = s.nrm[p];
                     float fr = s.sfric[p];
                     Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
@@ -446,7 +541,10 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
             s.okey[p] = s.key[p];
             unsigned char col = s.cnt[p] > 0 ? s.color[p] : NO_COLOR;
             s.ocolor[p] = col;
-            if (col != NO_COLOR) { s.ofric[p] = s.sfric[p]; s.opn[p] = s.con[(size_t)(2 * p) * 9 + 7]; s.opt[p] = s.con[(size_t)(2 * p) * 9 + 8]; }
+            if (col != NO_COLOR) {
+                const size_t g = (size_t)wld * cap + p;
+                a.c_fric[g] = s.sfric[p]; a.c_pn[g] = s.con[(size_t)(2 * p) * 9 + 7]; a.c_pt[g] = s.con[(size_t)(2 * p) * 9 + 8];
+            }
         }
         if (tid == 0) *s_Pold = P;
         __syncthreads();
@@ -467,7 +565,7 @@ __global__ void __launch_bounds__(256, 3) k_batch_step(BatchArgs a) {
     int ncon = 0, narb = 0;
     for (int k = tid; k < Pn; k += T) {
         size_t g = (size_t)wld * cap + k;
-        a.c_key[g] = s.okey[k]; a.c_fric[g] = s.ofric[k]; a.c_pn[g] = s.opn[k]; a.c_pt[g] = s.opt[k]; a.c_color[g] = s.ocolor[k];
+        a.c_key[g] = s.okey[k]; a.c_color[g] = s.ocolor[k];
         if (!err && k < P && s.cnt[k] > 0) { ncon += s.cnt[k]; narb++; }
     }
     // block reductions of (ncon, narb, maxpen) through shared memory atomics
@@ -565,7 +663,8 @@ struct SyltBatch {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    int n_worlds = 0, Bmax = 0, Jmax = 0, cap = 0, threads = 256;
+    int n_worlds = 0, Bmax = 0, Jmax = 0, cap = 0, threads = 256, nbk = 64;
+    float cell = 1.0f;
     int64_t n_bodies = 0, n_joints = 0;
     float gx = 0, gy = 0;
     uint32_t iterations = 10;
@@ -586,10 +685,12 @@ struct SyltBatch {
     DBuf<float> mass_moi, c_fric, c_pn, c_pt, w_maxpen;
     DBuf<int2> jbodies;
     DBuf<unsigned> c_key;
-    DBuf<unsigned char> c_color;
+    DBuf<unsigned char> c_color, bflags;
     DBuf<SlotExport> exp_slots;
     DBuf<StatsOut> stats;
     DBuf<SyltBodyState> stage;
+    static constexpr int NS = 4;
+    cudaStream_t xs[NS] = {nullptr, nullptr, nullptr, nullptr};  // copy/compute pipeline of sylt_batch_step_host
 };
 
 namespace {
@@ -600,7 +701,7 @@ void batch_free(SyltBatch* b) {
     b->exp_count.release(); b->pose.release(); b->vel.release(); b->mp.release(); b->jla.release(); b->jr.release(); b->jm.release();
     b->w_badk.release(); b->wh.release(); b->jparam.release(); b->jp.release(); b->jbias.release(); b->mass_moi.release();
     b->c_fric.release(); b->c_pn.release(); b->c_pt.release(); b->w_maxpen.release(); b->jbodies.release(); b->c_key.release();
-    b->c_color.release(); b->exp_slots.release(); b->stats.release(); b->stage.release();
+    b->c_color.release(); b->bflags.release(); b->exp_slots.release(); b->stats.release(); b->stage.release();
 }
 
 template <typename T>
@@ -616,13 +717,15 @@ int zeroed(DBuf<T>& d, size_t n) {
     return SYLT_OK;
 }
 
-int batch_enqueue(SyltBatch* b, float dt, int n) {
+int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaStream_t st = nullptr) {
+    if (w1 < 0) w1 = b->n_worlds;
+    if (!st) st = b->stream;
     BatchArgs a;
     memset(&a, 0, sizeof a);
-    a.n_worlds = b->n_worlds; a.n_steps = n; a.iterations = (int)b->iterations;
+    a.n_worlds = w1; a.world_begin = w0; a.n_steps = n; a.iterations = (int)b->iterations;
     a.accumulate = b->accumulate; a.warm = b->warm; a.poscorr = b->poscorr;
     a.dt = dt; a.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;  // world.rs:108
-    a.gx = b->gx; a.gy = b->gy; a.Bmax = b->Bmax; a.Jmax = b->Jmax; a.cap = b->cap;
+    a.gx = b->gx; a.gy = b->gy; a.Bmax = b->Bmax; a.Jmax = b->Jmax; a.cap = b->cap; a.nbk = b->nbk; a.cell = b->cell; a.bflags = b->bflags.p;
     a.export_first = b->export_first; a.export_count = b->export_count;
     a.body_off = b->body_off.p; a.joint_off = b->joint_off.p; a.pose = b->pose.p; a.vel = b->vel.p; a.mp = b->mp.p; a.wh = b->wh.p;
     a.jbodies = b->jbodies.p; a.jla = b->jla.p; a.jparam = b->jparam.p; a.jp = b->jp.p; a.jr = b->jr.p; a.jm = b->jm.p; a.jbias = b->jbias.p;
@@ -630,10 +733,10 @@ int batch_enqueue(SyltBatch* b, float dt, int n) {
     a.c_count = b->c_count.p; a.c_key = b->c_key.p; a.c_fric = b->c_fric.p; a.c_pn = b->c_pn.p; a.c_pt = b->c_pt.p; a.c_color = b->c_color.p;
     a.w_err = b->w_err.p; a.w_ncon = b->w_ncon.p; a.w_narb = b->w_narb.p; a.w_ncolors = b->w_ncolors.p; a.w_errjoint = b->w_errjoint.p;
     a.w_maxpen = b->w_maxpen.p; a.w_badk = b->w_badk.p; a.exp_slots = b->exp_slots.p; a.exp_count = b->exp_count.p;
-    k_batch_step<<<b->n_worlds, b->threads, b->smem, b->stream>>>(a);
+    k_batch_step<<<w1 - w0, b->threads, b->smem, st>>>(a);
     SYLT_CUDA(cudaGetLastError());
     b->launches++;
-    b->body_steps += (uint64_t)b->n_bodies * (uint64_t)n;
+    b->body_steps += (uint64_t)(b->h_body_off[(size_t)w1] - b->h_body_off[(size_t)w0]) * (uint64_t)n;
     b->last_steps = n;
     b->inflight = true;
     return SYLT_OK;
@@ -662,7 +765,7 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
     else b->h_joint_off.assign((size_t)n_worlds + 1, 0);
     std::vector<float4> pose((size_t)NB), vel((size_t)NB), mp((size_t)NB);
     std::vector<float2> wh((size_t)NB);
-    std::vector<float> mm((size_t)NB * 2);
+    std::vector<float> mm((size_t)NB * 2), radius((size_t)NB);
     b->h_ids.resize((size_t)NB);
     int Bmax = 0, Jmax = 0;
     std::vector<V2> scratch;
@@ -685,11 +788,37 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
             mp[(size_t)i] = make_float4(hb.inv_mass, hb.inv_moi, hb.friction, 0.0f);
             wh[(size_t)i] = make_float2(hb.width_x, hb.width_y);
             mm[(size_t)i * 2] = hb.mass; mm[(size_t)i * 2 + 1] = hb.moi;
+            radius[(size_t)i] = hb.radius;
             b->h_ids[(size_t)i] = d.id;
         }
         if (body_order_violated(hbs)) { delete b; return SYLT_ERR_BODY_ORDER; }  // quirk Q-6
     }
     if (Bmax > 4096) { delete b; return SYLT_ERR_UNSUPPORTED; }
+    // grid classification shared by all worlds of the batch: cell just above the largest "small" bounding diameter
+    std::vector<unsigned char> fl((size_t)NB, 0);
+    {
+        std::vector<float> d;
+        for (int64_t i = 0; i < NB; i++)
+            if (mp[(size_t)i].x != 0.0f) d.push_back(2.0f * radius[(size_t)i]);
+        float cell = 1.0f;
+        if (!d.empty()) {
+            std::vector<float> t = d;
+            std::nth_element(t.begin(), t.begin() + (long)(t.size() / 2), t.end());
+            float med = t[t.size() / 2], mx = 0.0f;
+            for (float x : d)
+                if (x <= 4.0f * med && x > mx) mx = x;
+            if (mx > 0.0f) cell = mx;
+        }
+        b->cell = 1.1f * cell + 0.1f;
+        for (int64_t i = 0; i < NB; i++) {
+            unsigned char f = mp[(size_t)i].x == 0.0f ? 1 : 0;
+            if (2.2f * radius[(size_t)i] + 0.1f > b->cell || !(radius[(size_t)i] == radius[(size_t)i])) f |= 2;
+            fl[(size_t)i] = f;
+        }
+        int nbk = 64;
+        while (nbk < Bmax && nbk < 4096) nbk <<= 1;
+        b->nbk = nbk;
+    }
     // joints: Joint::new (joint.rs:26-55) per world, then a greedy colouring of each world's joint graph
     std::vector<int2> jb((size_t)NJ);
     std::vector<float4> jla((size_t)NJ);
@@ -741,7 +870,7 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
     b->Bmax = Bmax; b->Jmax = Jmax;
     b->cap = std::max(32, 2 * Bmax + 32);
     if (b->cap > 65535) b->cap = 65535;
-    b->smem = carve(nullptr, nullptr, Bmax, Jmax, b->cap);
+    b->smem = carve(nullptr, nullptr, Bmax, Jmax, b->cap, b->nbk);
     int max_smem = 0;
     SYLT_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     if (b->smem > (size_t)max_smem) {
@@ -756,9 +885,10 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
     SYLT_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     SYLT_CUDA(cudaEventCreate(&b->ev0));
     SYLT_CUDA(cudaEventCreate(&b->ev1));
+    for (int k = 0; k < SyltBatch::NS; k++) SYLT_CUDA(cudaStreamCreateWithFlags(&b->xs[k], cudaStreamNonBlocking));
     int e = 0;
     if ((e = upload(b->body_off, b->h_body_off)) || (e = upload(b->joint_off, b->h_joint_off)) || (e = upload(b->pose, pose)) ||
-        (e = upload(b->vel, vel)) || (e = upload(b->mp, mp)) || (e = upload(b->wh, wh)) || (e = upload(b->mass_moi, mm)) ||
+        (e = upload(b->vel, vel)) || (e = upload(b->mp, mp)) || (e = upload(b->bflags, fl)) || (e = upload(b->wh, wh)) || (e = upload(b->mass_moi, mm)) ||
         (e = upload(b->jbodies, jb)) || (e = upload(b->jla, jla)) || (e = upload(b->jparam, jparam)) || (e = upload(b->jorder, jorder)) ||
         (e = upload(b->jcolor_start, jcs)) || (e = upload(b->n_jcolors, njc))) { sylt_batch_destroy(b); return e; }
     const size_t W = (size_t)n_worlds, WC = W * (size_t)b->cap;
@@ -785,6 +915,8 @@ int sylt_batch_destroy(SyltBatch* b) {
     if (b->ev0) cudaEventDestroy(b->ev0);
     if (b->ev1) cudaEventDestroy(b->ev1);
     if (b->stream) cudaStreamDestroy(b->stream);
+    for (int k = 0; k < SyltBatch::NS; k++)
+        if (b->xs[k]) cudaStreamDestroy(b->xs[k]);
     delete b;
     return SYLT_OK;
 }
@@ -813,6 +945,41 @@ int sylt_batch_step_n(SyltBatch* b, float dt, int32_t n) {
     if (e) return e;
     return sylt_batch_sync(b);
 }
+// One step_n with HOST buffers: upload all body states, step, download all body states — chunked over worlds and
+// pipelined on several streams so the two DMA directions overlap the kernels (pinned host memory recommended).
+int sylt_batch_step_host(SyltBatch* b, float dt, int32_t n, const SyltBodyState* in, SyltBodyState* out) {
+    if (!b || n < 0) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    SYLT_CUDA(cudaStreamSynchronize(b->stream));
+    SYLT_CUDA(b->stage.ensure((size_t)b->n_bodies));
+    const int W = b->n_worlds;
+    int chunks = std::max(1, std::min(16, W / 512));
+    const int per = (W + chunks - 1) / chunks;
+    for (int c = 0; c < chunks; c++) {
+        const int w0 = std::min(W, c * per), w1 = std::min(W, w0 + per);
+        if (w1 <= w0) continue;
+        cudaStream_t st = b->xs[c % SyltBatch::NS];
+        const int o0 = b->h_body_off[(size_t)w0], cnt = b->h_body_off[(size_t)w1] - o0;
+        if (in && cnt) {
+            SYLT_CUDA(cudaMemcpyAsync(b->stage.p + o0, in + o0, (size_t)cnt * sizeof(SyltBodyState), cudaMemcpyHostToDevice, st));
+            k_unpack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->stage.p + o0, b->pose.p + o0, b->vel.p + o0);
+            b->launches++;
+        }
+        if (n > 0) {
+            int e = batch_enqueue(b, dt, n, w0, w1, st);
+            if (e) return e;
+        }
+        if (out && cnt) {
+            k_pack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->pose.p + o0, b->vel.p + o0, b->stage.p + o0);
+            b->launches++;
+            SYLT_CUDA(cudaMemcpyAsync(out + o0, b->stage.p + o0, (size_t)cnt * sizeof(SyltBodyState), cudaMemcpyDeviceToHost, st));
+        }
+    }
+    for (int k = 0; k < SyltBatch::NS; k++) SYLT_CUDA(cudaStreamSynchronize(b->xs[k]));
+    b->inflight = false;
+    return SYLT_OK;
+}
+
 int sylt_batch_timer_start(SyltBatch* b) {
     if (!b) return SYLT_ERR_INVALID;
     SYLT_CUDA(cudaSetDevice(b->device));
@@ -876,8 +1043,11 @@ int sylt_batch_get_arbiters(SyltBatch* b, int32_t world, SyltArbiterInfo* arbite
         return -SYLT_ERR_CUDA;
     const int o0 = b->h_body_off[(size_t)world];
     int na = 0, nc = 0;
-    for (int p = 0; p < P; p++) {
-        const SlotExport& e = sl[(size_t)p];
+    std::vector<int> ord((size_t)P);
+    for (int p = 0; p < P; p++) ord[(size_t)p] = p;
+    std::sort(ord.begin(), ord.end(), [&](int x, int y) { return sl[(size_t)x].key < sl[(size_t)y].key; });
+    for (int pi = 0; pi < P; pi++) {
+        const SlotExport& e = sl[(size_t)ord[(size_t)pi]];
         if (e.count <= 0) continue;
         if (na >= arbiter_cap || nc + e.count > contact_cap) return -SYLT_ERR_CAPACITY;
         SyltArbiterInfo& o = arbiters[na++];

@@ -489,3 +489,24 @@ def test_config4_joint_worlds_batch_properties():
             for k in (1, 777, n - 1):
                 assert st[k * nb:(k + 1) * nb].tobytes() == first
         assert np.abs(st["x"]).max() < 60 and st["y"].min() > -30
+
+
+def test_batch_step_host_equals_set_step_get():
+    from sylt2d_b200 import Batch
+    sc = scenes.pyramid(6, 10)
+    n = 1100   # > 2 pipeline chunks
+    bodies, boff, joints, joff = scenes.tile_worlds(sc, n, seed=9, x_jitter=0.01)
+    a = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, ctx=sc.ctx)
+    b = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, ctx=sc.ctx)
+    a.step_n(sc.dt, 30)
+    b.step_n(sc.dt, 30)
+    st = a.get_bodies()
+    st["vx"][5::7] += 0.25          # the caller mutated some state on the host
+    out = np.zeros_like(st)
+    for _ in range(3):
+        a.set_bodies(st)
+        a.step_n(sc.dt, 1)
+        ref = a.get_bodies()
+        b.step_host(sc.dt, 1, st, out)
+        _assert_states_equal(out, ref, "step_host")
+        st = ref.copy()
