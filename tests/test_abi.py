@@ -101,3 +101,21 @@ def test_tile_worlds_and_shard_range():
         flat = [k for lo, hi in got for k in range(lo, hi)]
         assert flat == list(range(10))
         cover.append(got)
+
+
+def _build_cpp_example(tmpdir):
+    import subprocess
+    exe = os.path.join(tmpdir, "pyramid_cpp")
+    lib = os.path.join(ROOT, "sylt2d_b200")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-I", os.path.join(ROOT, "include"), os.path.join(ROOT, "examples", "pyramid.cpp"),
+                    "-L", lib, "-lsylt2d_b200", f"-Wl,-rpath,{lib}", "-o", exe], check=True)
+    return exe
+
+
+def test_cpp_mirror_compiles_and_links(built, tmp_path):
+    import subprocess
+    exe = _build_cpp_example(str(tmp_path))
+    L = built.lib()
+    if L.sylt_device_count() == 0:
+        r = subprocess.run([exe, "3"], capture_output=True, text=True)
+        assert r.returncode == 2 and "error 6" in r.stderr  # SYLT_ERR_CUDA surfaced as sylt2d::Error, no CPU fallback

@@ -8,6 +8,8 @@ Gates:
     the north star allows a stated tolerance)
   * colour order vs canonical (id1,id2) order: stated looser tolerance + long-run penetration / energy
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -510,3 +512,17 @@ def test_batch_step_host_equals_set_step_get():
         b.step_host(sc.dt, 1, st, out)
         _assert_states_equal(out, ref, "step_host")
         st = ref.copy()
+
+
+def test_cpp_mirror_and_headless_runner(tmp_path):
+    import subprocess
+    import sys
+    from tests.test_abi import _build_cpp_example, ROOT
+    import __graft_entry__ as g
+    g.build()
+    exe = _build_cpp_example(str(tmp_path))
+    r = subprocess.run([exe, "300"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr          # the reference's demo5 settles to an ~11.4 high pyramid
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "examples", "run_demo.py"), "demo8", "--steps", "120", "--bombs", "2", "--iterations", "10"],
+                       capture_output=True, text=True)
+    assert r.returncode == 0 and "demo8" in r.stdout, r.stdout + r.stderr
