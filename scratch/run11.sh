@@ -1,0 +1,3 @@
+timeout 300 python -m pytest tests -m gpu -x -q 2>&1 | tail -5
+SYLT_SOLVER_SMEM_SLOTS=40 SYLT_SOLVER_SMEM_CONTACTS=50 timeout 200 python -m pytest tests -m gpu -x -q -k "world_step or random_pile" 2>&1 | tail -3
+timeout 120 python scratch/prof_world.py 100000 600 100

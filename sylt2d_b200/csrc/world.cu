@@ -175,7 +175,7 @@ __device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
 __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* vel, const float4* force, const float4* mp, const float4* geom,
                                                  const int* bflags, const float2* lverts, float2* rotc, float4* aabb, int4* cinfo,
                                                  int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
-                                                 Counters* cn) {
+                                                 Counters* cn, ulonglong2* vrec) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     float4 p = pose[i];
@@ -184,13 +184,19 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* ve
     int fl = bflags[i];
     float c = sylt_cosf(p.z), s = sylt_sinf(p.z);
     rotc[i] = make_float2(c, s);
-    if (integrate && m.x != 0.0f) {  // world.rs:113-120
+    {
         float4 v = vel[i];
-        float4 f = force[i];
-        V2 nv = mk(v.x, v.y) + (mk(gx, gy) + mk(f.x, f.y) * m.x) * dt;
-        v.x = nv.x; v.y = nv.y;
-        v.z += m.y * f.z * dt;
-        vel[i] = v;
+        if (integrate && m.x != 0.0f) {  // world.rs:113-120
+            float4 f = force[i];
+            V2 nv = mk(v.x, v.y) + (mk(gx, gy) + mk(f.x, f.y) * m.x) * dt;
+            v.x = nv.x; v.y = nv.y;
+            v.z += m.y * f.z * dt;
+            vel[i] = v;
+        }
+        // versioned velocity record of the dataflow solver: (vx|ver, vy|ver), (w|ver, inv_mass|inv_moi), ver = 0
+        vrec[2 * (size_t)i] = make_ulonglong2((unsigned long long)__float_as_uint(v.x), (unsigned long long)__float_as_uint(v.y));
+        vrec[2 * (size_t)i + 1] = make_ulonglong2((unsigned long long)__float_as_uint(v.z),
+                                                  (unsigned long long)__float_as_uint(m.x) | ((unsigned long long)__float_as_uint(m.y) << 32));
     }
     float minx, miny, maxx, maxy;
     if (fl & FLAG_POLY) {
@@ -469,7 +475,6 @@ struct SolveArgs {
     float dt, inv_dt;
     unsigned epoch_base;
     int smem_slots, smem_contacts;  // shared-memory residency budget per CTA
-    int spread;                     // new arbiters propose one of their first `spread` free colours
     float4 *pose, *vel, *force;
     const float4* mp;
     const float2* rotc;
@@ -478,6 +483,11 @@ struct SolveArgs {
     unsigned* used;
     unsigned long long* claim;  // B * NC
     int *uncolored, *prop, *order;
+    ulonglong2* vrec;           // 2 per body: versioned velocities (see k_prepare)
+    int sleep_ns;               // back-off between polls of the dataflow wait (0 = spin)
+    unsigned long long* dbg;    // optional: globaltimer stamps of CTA 0 at the section boundaries (SYLT_SOLVER_TIMING=1)
+    const int* jdeg;            // joints touching each body
+    const int2* jrank;          // per joint: its rank among the joints of body1 / body2 (joint solve order)
     // joints
     const int2* jbodies;
     const float4* jla;       // (la1x, la1y, la2x, la2y)
@@ -514,13 +524,57 @@ __device__ __forceinline__ void grid_barrier(unsigned* counter, unsigned& target
 
 constexpr int SOLVE_THREADS = 512;
 
-// One arbiter as the solver sees it in a colour phase: either resident in this CTA's shared memory for the whole
-// solve (record + contact constants) or, when the CTA's share of the world exceeds the shared-memory budget, in the
-// global arrays.
+constexpr int VSTATIC = 0x40000000;  // body reference flag: static body (never written, never waited for)
+
+// One arbiter as the solver sees it: record + contact constants either resident in this CTA's shared memory for the
+// whole solve or, when the CTA's share of the world exceeds the shared-memory budget, in the global arrays.
 struct SlotView {
-    int b1, b2, n;
-    float fr, im1, ii1, im2, ii2;
+    int r1, r2, n;         // body index | VSTATIC
+    unsigned ord;          // D1 | r1 << 8 | D2 << 16 | r2 << 24  (see "residency")
+    float fr;
     float4 *ca, *cb, *cc;  // generic pointers (shared or global)
+};
+
+// Versioned velocity records in global memory (L2): per body two 16-byte halves
+//   { vx | ver << 32,  vy | ver << 32 }   { w | ver << 32,  inv_mass | inv_moi << 32 }
+// Every 64-bit word carries its own copy of the version, each word is read and written with a single-copy-atomic
+// 64-bit access (relaxed, gpu scope: served by L2, never by L1), so a reader needs no fence: it simply retries until
+// all three words show the version it expects (the protocol NCCL's LL transport uses).
+struct BodyIO {
+    ulonglong2* vrec;
+    int sleep_ns;
+    __device__ __forceinline__ static ulonglong2 ld(const ulonglong2* p) {
+        ulonglong2 r;
+        asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
+        return r;
+    }
+    __device__ __forceinline__ bool try_get(int b, unsigned expect, bool check, Vel& v, float& im, float& ii) const {
+        ulonglong2 lo = ld(vrec + 2 * (size_t)b), hi = ld(vrec + 2 * (size_t)b + 1);
+        v.v = mk(__uint_as_float((unsigned)lo.x), __uint_as_float((unsigned)lo.y));
+        v.w = __uint_as_float((unsigned)hi.x);
+        im = __uint_as_float((unsigned)hi.y);
+        ii = __uint_as_float((unsigned)(hi.y >> 32));
+        return !check || ((unsigned)(lo.x >> 32) == expect && (unsigned)(lo.y >> 32) == expect && (unsigned)(hi.x >> 32) == expect);
+    }
+    __device__ __forceinline__ void get(int b, Vel& v, float& im, float& ii) const { try_get(b, 0u, false, v, im, ii); }
+    // wait for both bodies of a constraint (static bodies are read once and never waited for)
+    __device__ __forceinline__ void wait2(int r1, unsigned e1, Vel& v1, float& im1, float& ii1, int r2, unsigned e2, Vel& v2, float& im2,
+                                          float& ii2) const {
+        const int b1 = r1 & ~VSTATIC, b2 = r2 & ~VSTATIC;
+        bool ok1 = false, ok2 = false;
+        for (;;) {
+            if (!ok1) ok1 = try_get(b1, e1, !(r1 & VSTATIC), v1, im1, ii1);
+            if (!ok2) ok2 = try_get(b2, e2, !(r2 & VSTATIC), v2, im2, ii2);
+            if (ok1 && ok2) break;
+            if (sleep_ns) __nanosleep(sleep_ns);
+        }
+    }
+    __device__ __forceinline__ void put(int b, const Vel& v, unsigned ver) const {
+        unsigned long long t = (unsigned long long)ver << 32;
+        unsigned long long x = t | __float_as_uint(v.v.x), y = t | __float_as_uint(v.v.y), w = t | __float_as_uint(v.w);
+        asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(vrec + 2 * (size_t)b), "l"(x), "l"(y) : "memory");
+        asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"((unsigned long long*)(vrec + 2 * (size_t)b + 1)), "l"(w) : "memory");
+    }
 };
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
@@ -531,6 +585,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     const int A = min(*(volatile int*)&cn->n_arb, a.cap_arb);
     unsigned bar_target = 0;
     unsigned* bar = &cn->bar;
+    auto stamp = [&](int k) {
+        if (a.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[k] = t; }
+    };
+    stamp(0);
     __shared__ int s_start[NC + 1];   // global colour-major start of colour c
     __shared__ int s_lo[NC + 1];      // first slot of colour c this CTA owns (relative to s_start[c])
     __shared__ int s_lbase[NC + 1];   // local index of that slot
@@ -558,11 +616,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                 unsigned m = (d1 ? __ldcg(&a.used[b.x]) : 0u) | (d2 ? __ldcg(&a.used[b.y]) : 0u);
                 unsigned fr = ~m;
                 if (!fr) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[e] = -1; continue; }
-                int nf = min(__popc(fr), a.spread);
-                int r = nf > 1 ? (int)(fmix32((unsigned)e * 2654435761u + (unsigned)round) % (unsigned)nf) : 0;
-                int c = __fns(fr, 0, r + 1);  // (r+1)-th free colour
+                int c = __ffs((int)fr) - 1;  // lowest free colour
                 a.prop[e] = c;
-                unsigned long long val = ep | fmix32((unsigned)e);
+                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
                 if (d1) atomicMin(&a.claim[(size_t)b.x * NC + c], val);
                 if (d2) atomicMin(&a.claim[(size_t)b.y * NC + c], val);
             }
@@ -574,7 +630,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                 if (c < 0) continue;
                 int2 b = a.cur.bodies[e];
                 bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
-                unsigned long long val = ep | fmix32((unsigned)e);
+                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
                 bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NC + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NC + c]) == val);
                 if (win) {
                     a.cur.color[e] = c;
@@ -591,6 +647,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
         if (tid == 0) cn->rounds = round + 1;
     }
 
+    stamp(1);
     // ---- 2. colour-major order (within a colour the order is irrelevant: disjoint dynamic bodies) and this CTA's share
     if (lt == 0) {
         int run = 0, nc = 0, lrun = 0;
@@ -630,12 +687,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     }
     grid_barrier(bar, bar_target);
     if (!a.run_solver) return;
+    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // e.g. an arbiter without a free colour: no solve, error reported
     const int ncolors = s_ncolors;
     const int L = s_lbase[NC];  // slots this CTA owns
     const bool acc = a.accumulate != 0;
     const float kbias = a.poscorr ? 0.2f : 0.0f;
 
-    // ---- 3. residency: load the records of the owned slots; contacts get shared-memory room by an exclusive scan
+    stamp(2);
+    // ---- 3. residency: load the records of the owned slots; contacts get shared-memory room by an exclusive scan.
+    //         Each record also gets, per dynamic body, (D, r): D = constraints touching the body, r = how many of them
+    //         precede this arbiter in the solve order (colours are distinct around a body, so r = popc(used & lower bits)).
     const int Ls = min(L, SLOTCAP);
     for (int c = 0; c < ncolors; c++) {
         const int cnt = s_lbase[c + 1] - s_lbase[c];
@@ -656,6 +717,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
         for (int k = q0; k < q1; k++) { int t = s_n[k]; s_n[k] = ex; ex += t; }
     }
     __syncthreads();
+    auto order_pack = [&](int b1, int b2, int c) -> unsigned {  // D1 | r1 << 8 | D2 << 16 | r2 << 24
+        unsigned u1 = __ldcg(&a.used[b1]), u2 = __ldcg(&a.used[b2]);
+        unsigned lower = (1u << c) - 1u;
+        unsigned d1 = (unsigned)(__popc(u1) + a.jdeg[b1]), d2 = (unsigned)(__popc(u2) + a.jdeg[b2]);
+        return (d1 & 0xffu) | ((unsigned)__popc(u1 & lower) << 8) | ((d2 & 0xffu) << 16) | ((unsigned)__popc(u2 & lower) << 24);
+    };
     for (int c = 0; c < ncolors; c++) {
         const int cnt = s_lbase[c + 1] - s_lbase[c];
         for (int i = lt; i < cnt; i += T) {
@@ -664,11 +731,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
             int e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
             int2 b = a.cur.bodies[e];
             int2 mt = a.cur.meta[e];
-            float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
             int lc = s_n[ls];
             const bool res = lc + mt.x <= CONCAP;
-            s_rec[2 * ls] = make_float4(__int_as_float(b.x), __int_as_float(b.y), __int_as_float(res ? (lc << 8) | mt.x : -1), a.cur.friction[e]);
-            s_rec[2 * ls + 1] = make_float4(m1.x, m1.y, m2.x, m2.y);
+            int r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0), r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
+            s_rec[2 * ls] = make_float4(__int_as_float(r1), __int_as_float(r2), __int_as_float(res ? (lc << 8) | mt.x : -1), a.cur.friction[e]);
+            s_rec[2 * ls + 1] = make_float4(__uint_as_float(order_pack(b.x, b.y, c)), 0.0f, 0.0f, 0.0f);
             if (res)
                 for (int q = 0; q < mt.x; q++) {
                     s_ca[lc + q] = a.cur.ca[mt.y + q];
@@ -678,124 +745,184 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     }
     __syncthreads();
 
-    auto view = [&](int c, int i, SlotView& v) -> int {  // returns the arbiter index e when the slot lives in global memory, else -1
+    auto view = [&](int c, int i, SlotView& v) {
         int ls = s_lbase[c] + i;
         if (ls < SLOTCAP) {
             float4 r0 = s_rec[2 * ls];
             int pk = __float_as_int(r0.z);
             if (pk >= 0) {
-                float4 r1 = s_rec[2 * ls + 1];
-                v.b1 = __float_as_int(r0.x); v.b2 = __float_as_int(r0.y); v.n = pk & 0xff; v.fr = r0.w;
-                v.im1 = r1.x; v.ii1 = r1.y; v.im2 = r1.z; v.ii2 = r1.w;
+                v.r1 = __float_as_int(r0.x); v.r2 = __float_as_int(r0.y); v.n = pk & 0xff; v.fr = r0.w;
+                v.ord = __float_as_uint(s_rec[2 * ls + 1].x);
                 int lc = pk >> 8;
                 v.ca = s_ca + lc; v.cb = s_cb + lc; v.cc = s_cc + lc;
-                return -1;
+                return;
             }
         }
         int e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
         int2 b = a.cur.bodies[e];
         int2 mt = a.cur.meta[e];
-        float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
-        v.b1 = b.x; v.b2 = b.y; v.n = mt.x; v.fr = a.cur.friction[e];
-        v.im1 = m1.x; v.ii1 = m1.y; v.im2 = m2.x; v.ii2 = m2.y;
+        v.r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0); v.r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
+        v.n = mt.x; v.fr = a.cur.friction[e];
+        v.ord = order_pack(b.x, b.y, c);
         v.ca = a.cur.ca + mt.y; v.cb = a.cur.cb + mt.y; v.cc = a.cur.cc + mt.y;
-        return e;
     };
 
-    // ---- 4. Arbiter::pre_step, colour by colour (warm-start impulses write body velocities)
+    // Dataflow Gauss-Seidel: no barrier between colours.  A constraint of pass t (0 = pre_step, 1..I = iterations) waits
+    // until both of its dynamic bodies carry version t*D + r, i.e. until every constraint that precedes it in the
+    // sequential (pass, colour) order has written them, then writes them back with version + 1.  Threads walk their
+    // slots in (pass, colour) order and all CTAs are co-resident, so the globally smallest unfinished constraint can
+    // always run: no deadlock.  The result is exactly the sequential sweep in (colour, then joint colour) order.
+    BodyIO io{a.vrec, a.sleep_ns};
+    // Polling throttle, CTA-local: s_done counts the slots this CTA has finished (all passes).  Before a warp starts its
+    // slots of (pass, colour) it waits (on shared memory only) until the CTA has finished as many slots as precede that
+    // phase locally, i.e. the CTA walks the phases roughly in step without bar.sync, and different CTAs drift freely.
+    // Cross-CTA ordering is carried by the versions alone; only threads of a CTA's current phase ever poll L2.
+    // (With all ~75k threads polling L2 at once the poll traffic itself was the bottleneck; a global progress counter
+    // serialises on one L2 address.)  Exactness never depends on this counter, only on the versions.
+    __shared__ unsigned s_done;
+    if (lt == 0) s_done = 0u;
+    __syncthreads();
+    const int lane = lt & 31;
+    auto wait_progress = [&](unsigned need) {
+        if (lane == 0) {
+            while (*(volatile unsigned*)&s_done < need) {}
+        }
+        __syncwarp();
+    };
+    auto add_progress = [&](bool did) {
+        unsigned m = __ballot_sync(0xffffffffu, did);
+        if (lane == 0 && m) atomicAdd(&s_done, (unsigned)__popc(m));
+    };
+    auto prestep_slot = [&](int c, int i) {
+        SlotView v;
+        view(c, i, v);
+        int e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
+        int coff = a.cur.meta[e].y;
+        const int b1 = v.r1 & ~VSTATIC, b2 = v.r2 & ~VSTATIC;
+        float4 p1 = a.pose[b1], p2 = a.pose[b2];
+        const unsigned e1 = (v.ord >> 8) & 0xffu, e2 = v.ord >> 24;  // pass 0: expected version = rank
+        Vel v1, v2;
+        float im1, ii1, im2, ii2;
+        io.wait2(v.r1, e1, v1, im1, ii1, v.r2, e2, v2, im2, ii2);
+        for (int q = 0; q < v.n; q++) {
+            float4 ca = v.ca[q], cc = v.cc[q], cd = a.cur.cd[coff + q];
+            ContactConst k0;
+            contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, mk(p1.x, p1.y), mk(p2.x, p2.y), im1, ii1, im2, ii2,
+                            a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
+            v.ca[q] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
+            v.cb[q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
+            v.cc[q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
+        }
+        if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1);
+        if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1);
+    };
+    auto apply_slot = [&](int c, int i, unsigned pass) {
+        SlotView v;
+        view(c, i, v);
+        const int b1 = v.r1 & ~VSTATIC, b2 = v.r2 & ~VSTATIC;
+        const unsigned e1 = pass * (v.ord & 0xffu) + ((v.ord >> 8) & 0xffu), e2 = pass * ((v.ord >> 16) & 0xffu) + (v.ord >> 24);
+        Vel v1, v2;
+        float im1, ii1, im2, ii2;
+        io.wait2(v.r1, e1, v1, im1, ii1, v.r2, e2, v2, im2, ii2);
+        for (int q = 0; q < v.n; q++) {
+            float4 ca = v.ca[q], cb = v.cb[q], cc = v.cc[q];
+            ContactConst k0;
+            k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
+            k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
+            float pn = cc.y, pt = cc.z;
+            contact_apply(k0, v.fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
+            if (acc) v.cc[q] = make_float4(cc.x, pn, pt, cc.w);
+        }
+        if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1);
+        if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1);
+    };
+    auto joint_expect = [&](int j, int2 b, unsigned pass, unsigned& e1, unsigned& e2) {
+        int2 jr = a.jrank[j];
+        unsigned da1 = (unsigned)__popc(__ldcg(&a.used[b.x])), da2 = (unsigned)__popc(__ldcg(&a.used[b.y]));
+        e1 = pass * (da1 + (unsigned)a.jdeg[b.x]) + da1 + (unsigned)jr.x;
+        e2 = pass * (da2 + (unsigned)a.jdeg[b.y]) + da2 + (unsigned)jr.y;
+    };
+
+    stamp(3);
+    // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228) then Joint::pre_step (joint.rs:57-115)
     for (int c = 0; c < ncolors; c++) {
         const int cnt = s_lbase[c + 1] - s_lbase[c];
-        for (int i = lt; i < cnt; i += T) {
-            SlotView v;
-            int e = view(c, i, v);
-            int coff = 0;
-            if (e < 0) e = __ldcg(&a.order[s_start[c] + s_lo[c] + i]);
-            coff = a.cur.meta[e].y;
-            float4 p1 = a.pose[v.b1], p2 = a.pose[v.b2];
-            Vel v1 = load_vel(a.vel, v.b1), v2 = load_vel(a.vel, v.b2);
-            for (int q = 0; q < v.n; q++) {
-                float4 ca = v.ca[q], cc = v.cc[q], cd = a.cur.cd[coff + q];
-                ContactConst k0;
-                contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, mk(p1.x, p1.y), mk(p2.x, p2.y), v.im1, v.ii1, v.im2, v.ii2,
-                                a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
-                v.ca[q] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
-                v.cb[q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
-                v.cc[q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
-            }
-            if (acc) {
-                if (v.im1 != 0.0f || v.ii1 != 0.0f) store_vel(a.vel, v.b1, v1);
-                if (v.im2 != 0.0f || v.ii2 != 0.0f) store_vel(a.vel, v.b2, v2);
-            }
+        for (int i0 = lt - lane; i0 < cnt; i0 += T) {  // warp-uniform trip count
+            const bool did = i0 + lane < cnt;
+            wait_progress((unsigned)s_lbase[c]);
+            if (did) prestep_slot(c, i0 + lane);
+            add_progress(did);
         }
-        if (acc) grid_barrier(bar, bar_target);
     }
-    if (!acc) grid_barrier(bar, bar_target);
-
-    // ---- 5. Joint::pre_step, joint colours (host-coloured, static graph)
     for (int c = 0; c < a.n_joint_colors; c++) {
-        for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
+        for (int k0 = a.jcolor_start[c] + tid - lane; k0 < a.jcolor_start[c + 1]; k0 += nth) {
+            const int k = k0 + lane;
+            const bool did = k < a.jcolor_start[c + 1];
+            if (did) {
             int j = a.jorder[k];
             int2 b = a.jbodies[j];
-            float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
             float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
             float2 r1c = a.rotc[b.x], r2c = a.rotc[b.y];
-            Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
+            const int r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0), r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
+            unsigned e1, e2;
+            joint_expect(j, b, 0u, e1, e2);
+            Vel v1, v2;
+            float im1, ii1, im2, ii2;
+            io.wait2(r1, e1, v1, im1, ii1, r2, e2, v2, im2, ii2);
             float4 la = a.jla[j];
             float2 pr = a.jparam[j];
             float2 pa = a.jp[j];
             V2 pacc = mk(pa.x, pa.y);
             JointConst jc;
             M2 bad;
+            Vel w1 = v1, w2 = v2;
             bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), r1c.x, r1c.y, mk(p2.x, p2.y), r2c.x, r2c.y,
-                                    m1.x, m1.y, m2.x, m2.y, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, v1, v2, jc, &bad);
+                                    im1, ii1, im2, ii2, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, w1, w2, jc, &bad);
             a.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
             if (!ok) {  // quirk Q-15: NoInverse aborts the step before the iterations
                 if (atomicCAS(&cn->err, 0, SYLT_ERR_NO_INVERSE) == 0) {
                     cn->err_joint = j;
                     cn->badk[0] = bad.c1.x; cn->badk[1] = bad.c2.x; cn->badk[2] = bad.c1.y; cn->badk[3] = bad.c2.y;
                 }
-                continue;
+                w1 = v1; w2 = v2;  // velocities untouched, versions still advance so that nobody waits forever
+            } else {
+                a.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
+                a.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
+                a.jp[j] = make_float2(pacc.x, pacc.y);
             }
-            a.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
-            a.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
-            a.jp[j] = make_float2(pacc.x, pacc.y);
-            if (a.warm) {
-                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
-                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+            if (!(r1 & VSTATIC)) io.put(b.x, w1, e1 + 1);
+            if (!(r2 & VSTATIC)) io.put(b.y, w2, e2 + 1);
             }
         }
-        grid_barrier(bar, bar_target);
     }
+    grid_barrier(bar, bar_target);
     const bool aborted = *(volatile int*)&cn->err == SYLT_ERR_NO_INVERSE;
+    stamp(4);
 
-    // ---- 6. iterations x (arbiter colours, joint colours)   (world.rs:132-140)
-    for (int it = 0; it < (aborted ? 0 : a.iterations); it++) {
+    // ---- 5. passes 1..I: iterations x (arbiter colours, joint colours)   (world.rs:132-140)
+    for (int it = 1; it <= (aborted ? 0 : a.iterations); it++) {
         for (int c = 0; c < ncolors; c++) {
             const int cnt = s_lbase[c + 1] - s_lbase[c];
-            for (int i = lt; i < cnt; i += T) {
-                SlotView v;
-                view(c, i, v);
-                Vel v1 = load_vel(a.vel, v.b1), v2 = load_vel(a.vel, v.b2);
-                for (int q = 0; q < v.n; q++) {
-                    float4 ca = v.ca[q], cb = v.cb[q], cc = v.cc[q];
-                    ContactConst k0;
-                    k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
-                    k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
-                    float pn = cc.y, pt = cc.z;
-                    contact_apply(k0, v.fr, v.im1, v.ii1, v.im2, v.ii2, acc, pn, pt, v1, v2);
-                    if (acc) v.cc[q] = make_float4(cc.x, pn, pt, cc.w);
-                }
-                if (v.im1 != 0.0f || v.ii1 != 0.0f) store_vel(a.vel, v.b1, v1);
-                if (v.im2 != 0.0f || v.ii2 != 0.0f) store_vel(a.vel, v.b2, v2);
+            for (int i0 = lt - lane; i0 < cnt; i0 += T) {
+                const bool did = i0 + lane < cnt;
+                wait_progress((unsigned)it * (unsigned)L + (unsigned)s_lbase[c]);
+                if (did) apply_slot(c, i0 + lane, (unsigned)it);
+                add_progress(did);
             }
-            grid_barrier(bar, bar_target);
         }
         for (int c = 0; c < a.n_joint_colors; c++) {
-            for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
+            for (int k0 = a.jcolor_start[c] + tid - lane; k0 < a.jcolor_start[c + 1]; k0 += nth) {
+                const int k = k0 + lane;
+                const bool did = k < a.jcolor_start[c + 1];
+                if (did) {
                 int j = a.jorder[k];
                 int2 b = a.jbodies[j];
-                float4 m1 = a.mp[b.x], m2 = a.mp[b.y];
-                Vel v1 = load_vel(a.vel, b.x), v2 = load_vel(a.vel, b.y);
+                const int r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0), r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
+                unsigned e1, e2;
+                joint_expect(j, b, (unsigned)it, e1, e2);
+                Vel v1, v2;
+                float im1, ii1, im2, ii2;
+                io.wait2(r1, e1, v1, im1, ii1, r2, e2, v2, im2, ii2);
                 float4 r = a.jr[j], mm = a.jm[j];
                 float2 bs = a.jbias[j], pa = a.jp[j];
                 JointConst jc;
@@ -803,16 +930,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                 jc.m = mk(mk(mm.x, mm.z), mk(mm.y, mm.w));
                 jc.softness = a.jparam[j].x;
                 V2 pacc = mk(pa.x, pa.y);
-                joint_apply(jc, m1.x, m1.y, m2.x, m2.y, pacc, v1, v2);
+                joint_apply(jc, im1, ii1, im2, ii2, pacc, v1, v2);
                 a.jp[j] = make_float2(pacc.x, pacc.y);
-                if (m1.x != 0.0f || m1.y != 0.0f) store_vel(a.vel, b.x, v1);
-                if (m2.x != 0.0f || m2.y != 0.0f) store_vel(a.vel, b.y, v2);
+                if (!(r1 & VSTATIC)) io.put(b.x, v1, e1 + 1);
+                if (!(r2 & VSTATIC)) io.put(b.y, v2, e2 + 1);
+                }
             }
-            grid_barrier(bar, bar_target);
         }
     }
 
-    // ---- 7. write the shared-memory resident contacts back (warm start of the next step, read-back)
+    stamp(5);
+    // ---- 6. write the shared-memory resident contacts back (warm start of the next step, read-back)
     for (int c = 0; c < ncolors; c++) {
         const int cnt = s_lbase[c + 1] - s_lbase[c];
         for (int i = lt; i < cnt; i += T) {
@@ -829,18 +957,25 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
             }
         }
     }
-    if (aborted) return;
+    grid_barrier(bar, bar_target);
 
-    // ---- 8. integrate positions, clear forces (world.rs:143-150; static bodies too, quirk Q-16)
+    stamp(6);
+    // ---- 7. velocities out of the versioned records; integrate positions, clear forces (world.rs:143-150; static
+    //         bodies too, quirk Q-16).  After a NoInverse the step stops before the integration (quirk Q-15).
     for (int i = tid; i < a.B; i += nth) {
+        Vel v;
+        float im, ii;
+        io.get(i, v, im, ii);
+        a.vel[i] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
+        if (aborted) continue;
         float4 p = a.pose[i];
-        float4 v = __ldcg(&a.vel[i]);
-        V2 np = mk(p.x, p.y) + mk(v.x, v.y) * a.dt;
+        V2 np = mk(p.x, p.y) + v.v * a.dt;
         p.x = np.x; p.y = np.y;
-        p.z += v.z * a.dt;
+        p.z += v.w * a.dt;
         a.pose[i] = p;
         a.force[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+    stamp(7);
 }
 
 __global__ void k_collide_pairs(int n, const SyltBodyDesc* A, const SyltBodyDesc* Bd, const float2* lverts, const int* loff,
@@ -897,7 +1032,6 @@ struct SyltWorld {
     int64_t launches = 0;
     int num_sms = 0, coop_blocks = 0, smem_slots = 0, smem_contacts = 0;
     size_t solve_smem = 0;
-    int spread = 2;
 
     // host mirror of construction-time data
     std::vector<HostBody> hb;
@@ -923,6 +1057,12 @@ struct SyltWorld {
     DBuf<float4> tmp_a;
     DBuf<float2> tmp_b;
     DBuf<unsigned> used;
+    DBuf<ulonglong2> vrec;
+    int sleep_ns = 0, ctas_per_sm = 1, solve_threads = 512;
+    bool timing = false;
+    DBuf<unsigned long long> dbg;
+    DBuf<int> jdeg;
+    DBuf<int2> jrank;
     DBuf<int> uncolored, prop, order;
     DBuf<Counters> counters;
     DBuf<int> tot32;
@@ -1007,6 +1147,20 @@ void color_joints(SyltWorld* w) {
     w->h_jorder.assign(J, 0);
     std::vector<int> fill(start.begin(), start.end());
     for (size_t j = 0; j < J; j++) w->h_jorder[(size_t)fill[(size_t)w->hj[j].color]++] = (int)j;
+    // per joint: rank among the joints of each of its bodies in solve order; per body: number of joints (dataflow solver)
+    std::vector<int> jdeg(w->hb.size() + 1, 0);
+    std::vector<int2> jrank(J + 1, make_int2(0, 0));
+    for (size_t k = 0; k < J; k++) {
+        int j = w->h_jorder[k];
+        const HostJoint& q = w->hj[(size_t)j];
+        jrank[(size_t)j] = make_int2(jdeg[(size_t)q.b1], jdeg[(size_t)q.b2] + (q.b1 == q.b2 ? 1 : 0));
+        jdeg[(size_t)q.b1]++;
+        jdeg[(size_t)q.b2]++;
+    }
+    w->jdeg.ensure(w->hb.size() + 1);
+    w->jrank.ensure(J + 1);
+    cudaMemcpyAsync(w->jdeg.p, jdeg.data(), jdeg.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream);
+    cudaMemcpyAsync(w->jrank.p, jrank.data(), jrank.size() * sizeof(int2), cudaMemcpyHostToDevice, w->stream);
     // upload
     w->jorder.ensure(J + 1);
     w->jcolor_start.ensure((size_t)w->n_joint_colors + 2);
@@ -1040,6 +1194,8 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->row_start.ensure(B + 2));
         SYLT_CUDA(w->row_tmp.ensure(B * ROWTMP));
         SYLT_CUDA(w->used.ensure(B));
+        SYLT_CUDA(w->vrec.ensure(2 * B));
+        w->joints_dirty = true;  // jdeg is per body
         SYLT_CUDA(w->large.ensure(B));
         for (int k = 0; k < 2; k++) SYLT_CUDA(w->arb[k].row_start.ensure(B + 2, (size_t)w->B_old + 1, w->stream));
         {   // claims: all ones == "no claim"
@@ -1188,7 +1344,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     SYLT_CUDA(cudaMemsetAsync(w->used.p, 0, (size_t)B * sizeof(unsigned), st));
     const int nbB = (B + 255) / 256;
     k_prepare<<<nbB, 256, 0, st>>>(B, w->pose.p, w->vel.p, w->force.p, w->mp.p, w->geom.p, w->bflags.p, w->lverts.p, w->rotc.p, w->aabb.p,
-                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn);
+                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p);
     w->launches++;
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->tot32.p);
     if (e) return e;
@@ -1243,8 +1399,9 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     a.jbodies = w->jbodies.p; a.jla = w->jla.p; a.jparam = w->jparam.p; a.jp = w->jp.p; a.jr = w->jr.p; a.jm = w->jm.p; a.jbias = w->jbias.p;
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
     void* args[] = {&a};
-    a.smem_slots = w->smem_slots; a.smem_contacts = w->smem_contacts; a.spread = w->spread;
-    SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3(SOLVE_THREADS), args, w->solve_smem, st));
+    a.smem_slots = w->smem_slots; a.smem_contacts = w->smem_contacts;
+    a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.dbg = w->timing ? w->dbg.p : nullptr;
+    SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_smem, st));
     w->launches++;
     // the set just built becomes "last step's"
     w->cur ^= 1;
@@ -1258,6 +1415,13 @@ int finish(SyltWorld* w) {
     SYLT_CUDA(cudaMemcpy(&w->last, w->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
     w->inflight = false;
     w->have_last = true;
+    if (w->timing) {  // diagnostics: k_solve section times of the last step (CTA 0's view)
+        unsigned long long t[8];
+        if (cudaMemcpy(t, w->dbg.p, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess)
+            fprintf(stderr, "k_solve sections [us]: colour %.1f order %.1f residency %.1f pass0 %.1f iterations %.1f writeback %.1f integrate %.1f total %.1f\n",
+                    (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3,
+                    (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
+    }
     w->last_was_step = w->inflight_full;
     w->last_iterations = w->iterations;
     return w->last.err;
@@ -1321,9 +1485,14 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     SYLT_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
     cudaFuncAttributes fa;
     SYLT_CUDA(cudaFuncGetAttributes(&fa, k_solve));
-    size_t budget = (size_t)max_smem - fa.sharedSizeBytes - 1024;
-    w->smem_slots = 1792;
-    if (const char* ev = getenv("SYLT_COLOR_SPREAD")) w->spread = std::min(8, std::max(1, atoi(ev)));
+    w->ctas_per_sm = 1;
+    if (const char* ev = getenv("SYLT_SOLVER_CTAS_PER_SM")) w->ctas_per_sm = std::min(4, std::max(1, atoi(ev)));
+    w->solve_threads = SOLVE_THREADS / w->ctas_per_sm;
+    size_t budget = ((size_t)max_smem + 1024) / (size_t)w->ctas_per_sm - fa.sharedSizeBytes - 2048;  // 1 KB per CTA is reserved by the system
+    w->smem_slots = 1792 / w->ctas_per_sm;
+    if (const char* ev = getenv("SYLT_SOLVER_SLEEP_NS")) w->sleep_ns = std::max(0, atoi(ev));
+    if (const char* ev = getenv("SYLT_SOLVER_TIMING")) w->timing = atoi(ev) != 0;
+    SYLT_CUDA(w->dbg.ensure(16));
     if (const char* ev = getenv("SYLT_SOLVER_SMEM_SLOTS")) w->smem_slots = std::max(0, atoi(ev));  // tests: force the global-memory path
     size_t fixed = (size_t)w->smem_slots * 32 + (((size_t)w->smem_slots + 3) & ~(size_t)3) * 4;
     if (fixed + 48 > budget) { w->smem_slots = 0; fixed = 0; }
@@ -1332,9 +1501,9 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     w->solve_smem = fixed + (size_t)w->smem_contacts * 48;
     SYLT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_smem));
     int per_sm = 0;
-    SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, SOLVE_THREADS, w->solve_smem));
-    if (per_sm < 1) { delete w; set_last_error("k_solve does not fit on an SM"); return SYLT_ERR_CUDA; }
-    w->coop_blocks = w->num_sms;
+    SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, w->solve_threads, w->solve_smem));
+    if (per_sm < w->ctas_per_sm) { delete w; set_last_error("k_solve does not fit on an SM"); return SYLT_ERR_CUDA; }
+    w->coop_blocks = w->num_sms * w->ctas_per_sm;
     SYLT_CUDA(cudaStreamCreateWithFlags(&w->stream, cudaStreamNonBlocking));
     SYLT_CUDA(cudaEventCreate(&w->ev0));
     SYLT_CUDA(cudaEventCreate(&w->ev1));
@@ -1349,7 +1518,7 @@ static void free_all(SyltWorld* w) {
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cell_bodies.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
-    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->uncolored.release();
+    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release();
     w->prop.release(); w->order.release(); w->tot32.release(); w->tot64.release();
     for (int k = 0; k < 2; k++) {
         auto& a = w->arb[k];
