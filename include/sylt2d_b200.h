@@ -47,6 +47,7 @@ extern "C" {
 #define SYLT_ERR_CUDA 6           /* CUDA runtime error / no device; sylt_last_error_string() has the text */
 #define SYLT_ERR_INVALID 7        /* bad argument */
 #define SYLT_ERR_UNSUPPORTED 8    /* e.g. polygons with > SYLT_MAX_POLY_VERTS vertices */
+#define SYLT_ERR_INTERNAL 9       /* solver watchdog: an ordered wait never completed (a bug; the step result is invalid) */
 
 #define SYLT_MAX_POLY_VERTS 8     /* per polygon; manifolds hold up to 2*SYLT_MAX_POLY_VERTS contacts (reference: unbounded) */
 #define SYLT_SHAPE_BOX 0

@@ -15,7 +15,7 @@ LIB_PATH = os.path.join(_HERE, "libsylt2d_b200.so")
 
 SYLT_OK, ERR_NO_INVERSE, ERR_ARBITER, ERR_BODY_ORDER, ERR_BODY_NOT_FOUND, ERR_CAPACITY, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED = range(9)
 ERROR_NAMES = {1: "NoInverse (Sylt2DErrors::MathOperations)", 2: "Arbiter", 3: "BodyOrder", 4: "BodyNotFound", 5: "Capacity",
-               6: "CUDA", 7: "Invalid", 8: "Unsupported"}
+               6: "CUDA", 7: "Invalid", 8: "Unsupported", 9: "Internal (solver watchdog)"}
 
 BODY_STATE = np.dtype([(n, "<f4") for n in ("x", "y", "rotation", "vx", "vy", "angular_velocity", "fx", "fy", "torque")])
 CONTACT = np.dtype([(n, "<f4") for n in ("px", "py", "nx", "ny", "r1x", "r1y", "r2x", "r2y", "separation", "pn", "pt", "pnb",

@@ -23,11 +23,12 @@ struct ContactConst {  // what apply_impulse needs every iteration
     float mass_n, mass_t, bias;
 };
 
-// Arbiter::pre_step for one contact (arbiter.rs:191-223).  p1/p2 are the body positions.
-// flags: accumulate_impulse gates the warm-start application (quirk Q-5).
-SYLT_HD void contact_prestep(V2 cpos, V2 n, float separation, V2 p1, V2 p2, float im1, float ii1, float im2, float ii2,
-                             float inv_dt, float k_bias_factor, bool accumulate, float pn, float pt,
-                             Vel& b1, Vel& b2, ContactConst& cc) {
+// Arbiter::pre_step for one contact (arbiter.rs:191-223), in two halves so that a caller can compute the constants
+// ahead of time (they do not depend on velocities) and keep only the warm start inside the ordered sweep.
+//   contact_constants : r1, r2, mass_normal, mass_tangent, bias          (arbiter.rs:192-215)
+//   contact_warmstart : apply P = n*pn + t*pt to both bodies when accumulate_impulse (arbiter.rs:216-223, quirk Q-5)
+SYLT_HD void contact_constants(V2 cpos, V2 n, float separation, V2 p1, V2 p2, float im1, float ii1, float im2, float ii2,
+                               float inv_dt, float k_bias_factor, ContactConst& cc) {
     const float k_allowed_penetration = 0.01f;
     V2 r1 = cpos - p1, r2 = cpos - p2;
     float rn1 = dot(r1, n), rn2 = dot(r2, n);
@@ -41,13 +42,20 @@ SYLT_HD void contact_prestep(V2 cpos, V2 n, float separation, V2 p1, V2 p2, floa
     cc.mass_t = 1.0f / k_tangent;
     cc.bias = -k_bias_factor * inv_dt * fminf(0.0f, separation + k_allowed_penetration);
     cc.n = n; cc.r1 = r1; cc.r2 = r2;  // apply_impulse recomputes the same r1/r2 (arbiter.rs:236-237): positions do not move during a step
-    if (accumulate) {
-        V2 p = n * pn + t * pt;
-        b1.v = b1.v - p * im1;
-        b1.w -= ii1 * cross(r1, p);
-        b2.v = b2.v + p * im2;
-        b2.w += ii2 * cross(r2, p);
-    }
+}
+SYLT_HD void contact_warmstart(const ContactConst& cc, float im1, float ii1, float im2, float ii2, float pn, float pt, Vel& b1, Vel& b2) {
+    V2 t = cross(cc.n, 1.0f);
+    V2 p = cc.n * pn + t * pt;
+    b1.v = b1.v - p * im1;
+    b1.w -= ii1 * cross(cc.r1, p);
+    b2.v = b2.v + p * im2;
+    b2.w += ii2 * cross(cc.r2, p);
+}
+SYLT_HD void contact_prestep(V2 cpos, V2 n, float separation, V2 p1, V2 p2, float im1, float ii1, float im2, float ii2,
+                             float inv_dt, float k_bias_factor, bool accumulate, float pn, float pt,
+                             Vel& b1, Vel& b2, ContactConst& cc) {
+    contact_constants(cpos, n, separation, p1, p2, im1, ii1, im2, ii2, inv_dt, k_bias_factor, cc);
+    if (accumulate) contact_warmstart(cc, im1, ii1, im2, ii2, pn, pt, b1, b2);
 }
 
 // Arbiter::apply_impulse for one contact (arbiter.rs:233-297).  pn/pt are the accumulated impulses (read-modify-write).

@@ -229,12 +229,17 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* ve
     cinfo[i] = make_int4(cx, cy, fl, 0);
 }
 
-__global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, const int* rank, const int* cell_start, int* cell_bodies, GridParams gp) {
+// bodies grouped by cell: a cell-ordered COPY of (index, cell, flags) and of the AABB, so that the row search streams
+// contiguous 32-byte entries instead of chasing body indices
+__global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, const float4* aabb, const int* rank, const int* cell_start,
+                                                    int4* cent_info, float4* cent_aabb, GridParams gp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     int4 ci = cinfo[i];
     if (ci.z & FLAG_LARGE) return;
-    cell_bodies[cell_start[cell_hash(ci.x, ci.y, gp.mask)] + rank[i]] = i;
+    int pos = cell_start[cell_hash(ci.x, ci.y, gp.mask)] + rank[i];
+    cent_info[pos] = make_int4(i, ci.x, ci.y, ci.z);
+    cent_aabb[pos] = aabb[i];
 }
 
 // Row i = partners body i owns: small-small pairs belong to the lower index, small-large pairs to the small
@@ -244,25 +249,46 @@ constexpr int ROWTMP = 16;
 
 template <typename F>
 __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, const float4* aabb, const int4* cinfo, const int* cell_start,
-                                           const int* cell_bodies, const int* large, int n_large, GridParams gp, F&& found) {
+                                           const int4* cent_info, const float4* cent_aabb, const int* large, int n_large, GridParams gp, F&& found) {
     const bool st_i = (ci.z & FLAG_STATIC) != 0;
     if (!(ci.z & FLAG_LARGE)) {
         int x0 = cell_coord(my.x - 0.5f * gp.cell, gp.cell), x1 = cell_coord(my.z + 0.5f * gp.cell, gp.cell);
         int y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell), y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
-        for (int cy = y0; cy <= y1; cy++)
-            for (int cx = x0; cx <= x1; cx++) {
+        if (x1 - x0 <= 2 && y1 - y0 <= 2) {
+            // the usual 3x3 block: fetch all bucket ranges first (independent loads), then stream the entries
+            int k0[9], k1[9];
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                int cx = x0 + q % 3, cy = y0 + q / 3;
+                bool ok = cx <= x1 && cy <= y1;
                 int h = cell_hash(cx, cy, gp.mask);
-                int k1 = cell_start[h + 1];
-                for (int k = cell_start[h]; k < k1; k++) {
-                    int j = cell_bodies[k];
-                    if (j <= i) continue;
-                    int4 cj = cinfo[j];
-                    if (cj.x != cx || cj.y != cy) continue;  // another cell sharing the bucket
-                    if (st_i && (cj.z & FLAG_STATIC)) continue;
-                    if (!aabb_overlap(my, aabb[j])) continue;
-                    found(j);
+                k0[q] = ok ? cell_start[h] : 0;
+                k1[q] = ok ? cell_start[h + 1] : 0;
+            }
+#pragma unroll
+            for (int q = 0; q < 9; q++) {
+                int cx = x0 + q % 3, cy = y0 + q / 3;
+                for (int k = k0[q]; k < k1[q]; k++) {
+                    int4 cj = cent_info[k];
+                    float4 ab = cent_aabb[k];
+                    if (cj.x <= i || cj.y != cx || cj.z != cy) continue;  // lower index owns the pair; another cell may share the bucket
+                    if (st_i && (cj.w & FLAG_STATIC)) continue;
+                    if (aabb_overlap(my, ab)) found(cj.x);
                 }
             }
+        } else {
+            for (int cy = y0; cy <= y1; cy++)
+                for (int cx = x0; cx <= x1; cx++) {
+                    int h = cell_hash(cx, cy, gp.mask);
+                    int ke = cell_start[h + 1];
+                    for (int k = cell_start[h]; k < ke; k++) {
+                        int4 cj = cent_info[k];
+                        if (cj.x <= i || cj.y != cx || cj.z != cy) continue;
+                        if (st_i && (cj.w & FLAG_STATIC)) continue;
+                        if (aabb_overlap(my, cent_aabb[k])) found(cj.x);
+                    }
+                }
+        }
         for (int k = 0; k < n_large; k++) {
             int j = large[k];
             if (st_i && (cinfo[j].z & FLAG_STATIC)) continue;
@@ -280,21 +306,21 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
     }
 }
 
-__global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int* cell_bodies,
-                                                    const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp) {
+__global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
+                                                    const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     int n = 0;
     int* tmp = row_tmp + (size_t)i * ROWTMP;
-    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cell_bodies, large, n_large, gp, [&](int j) {
+    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) {
         if (n < ROWTMP) tmp[n] = j;
         n++;
     });
     row_count[i] = n;
 }
 
-__global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int* cell_bodies,
-                                                   const int* large, int n_large, GridParams gp, const int* row_start, const int* row_tmp,
+__global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
+                                                   const float4* cent_aabb, const int* large, int n_large, GridParams gp, const int* row_start, const int* row_tmp,
                                                    int2* pairs, int cap_pairs, Counters* cn) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
@@ -318,7 +344,7 @@ __global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, co
         return;
     }
     int m = 0;
-    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cell_bodies, large, n_large, gp, [&](int j) { pairs[base + m++] = make_int2(i, j); });
+    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) { pairs[base + m++] = make_int2(i, j); });
     for (int a = 1; a < n; a++) {
         int2 x = pairs[base + a];
         int b = a - 1;
@@ -482,9 +508,10 @@ struct SolveArgs {
     ArbSet cur;
     unsigned* used;
     unsigned long long* claim;  // B * NC
-    int *uncolored, *prop, *order;
+    int *uncolored, *uncolored2, *prop, *order;
     ulonglong2* vrec;           // 2 per body: versioned velocities (see k_prepare)
     int sleep_ns;               // back-off between polls of the dataflow wait (0 = spin)
+    int slack_pct;              // polling throttle slack (see wait_progress)
     unsigned long long* dbg;    // optional: globaltimer stamps of CTA 0 at the section boundaries (SYLT_SOLVER_TIMING=1)
     const int* jdeg;            // joints touching each body
     const int2* jrank;          // per joint: its rank among the joints of body1 / body2 (joint solve order)
@@ -543,6 +570,7 @@ struct SlotView {
 struct BodyIO {
     ulonglong2* vrec;
     int sleep_ns;
+    int* err;  // watchdog: a wait that never completes (a bug, never the data) flags SYLT_ERR_INTERNAL instead of hanging the GPU
     __device__ __forceinline__ static ulonglong2 ld(const ulonglong2* p) {
         ulonglong2 r;
         asm volatile("ld.relaxed.gpu.global.v2.b64 {%0, %1}, [%2];" : "=l"(r.x), "=l"(r.y) : "l"(p) : "memory");
@@ -562,11 +590,16 @@ struct BodyIO {
                                           float& ii2) const {
         const int b1 = r1 & ~VSTATIC, b2 = r2 & ~VSTATIC;
         bool ok1 = false, ok2 = false;
+        unsigned spins = 0;
         for (;;) {
             if (!ok1) ok1 = try_get(b1, e1, !(r1 & VSTATIC), v1, im1, ii1);
             if (!ok2) ok2 = try_get(b2, e2, !(r2 & VSTATIC), v2, im2, ii2);
             if (ok1 && ok2) break;
             if (sleep_ns) __nanosleep(sleep_ns);
+            if ((++spins & 0xfffu) == 0u) {
+                if (*(volatile int*)err == SYLT_ERR_INTERNAL) break;
+                if (spins > (1u << 23)) { atomicExch(err, SYLT_ERR_INTERNAL); break; }
+            }
         }
     }
     __device__ __forceinline__ void put(int b, const Vel& v, unsigned ver) const {
@@ -602,15 +635,27 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     float4* s_cb = s_ca + CONCAP;
     float4* s_cc = s_cb + CONCAP;
 
-    // ---- 1. colour the arbiters that are new this step (persisting ones kept their colour in k_build)
+    // ---- 1. colour the arbiters that are new this step (persisting ones kept their colour in k_build): lowest free
+    //         colour, conflicts between new arbiters resolved by a hashed priority (64-bit atomicMin claims per body
+    //         and colour, stamped with a round epoch so nothing is ever cleared).  A handful of new arbiters (the usual
+    //         case in a settled scene) is coloured by CTA 0 alone with block barriers; a flood (scene start) by the grid.
     const int nunc = *(volatile int*)&cn->n_uncolored;
     if (nunc > 0) {
+        // round r reads the list L[r & 1] (n entries); arbiters that lose a claim append themselves to the other list,
+        // whose length is counted in cn->remaining[r].  The grid runs the rounds while many arbiters are left, then
+        // CTA 0 finishes the stragglers alone with block barriers while the others wait at one grid barrier.
+        int* lists[2] = {a.uncolored, a.uncolored2};
+        int n = nunc;
+        bool solo = n <= T;  // block-uniform and identical in every CTA (one entry per thread of CTA 0)
         int round = 0;
         for (; round < MAX_ROUNDS; round++) {
+            if (solo && bid != 0) break;
+            const int ct = solo ? lt : tid, cs = solo ? T : nth;
+            const int* cur_list = lists[round & 1];
+            int* next_list = lists[(round + 1) & 1];
             const unsigned long long ep = (unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32;
-            for (int k = tid; k < nunc; k += nth) {
-                int e = a.uncolored[k];
-                if (a.cur.color[e] >= 0) continue;  // written by this same thread in an earlier round
+            for (int k = ct; k < n; k += cs) {
+                int e = __ldcg(&cur_list[k]);
                 int2 b = a.cur.bodies[e];
                 bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
                 unsigned m = (d1 ? __ldcg(&a.used[b.x]) : 0u) | (d2 ? __ldcg(&a.used[b.y]) : 0u);
@@ -622,11 +667,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                 if (d1) atomicMin(&a.claim[(size_t)b.x * NC + c], val);
                 if (d2) atomicMin(&a.claim[(size_t)b.y * NC + c], val);
             }
-            grid_barrier(bar, bar_target);
-            for (int k = tid; k < nunc; k += nth) {
-                int e = a.uncolored[k];
-                if (a.cur.color[e] >= 0) continue;
-                int c = a.prop[e];
+            if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
+            for (int k = ct; k < n; k += cs) {
+                int e = __ldcg(&cur_list[k]);
+                int c = __ldcg(&a.prop[e]);
                 if (c < 0) continue;
                 int2 b = a.cur.bodies[e];
                 bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
@@ -638,13 +682,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                     if (d2) atomicOr(&a.used[b.y], 1u << c);
                     atomicAdd(&cn->color_count[c], 1);
                 } else {
-                    atomicAdd(&cn->remaining[round], 1);
+                    next_list[atomicAdd(&cn->remaining[round], 1)] = e;
                 }
             }
-            grid_barrier(bar, bar_target);
-            if (*(volatile int*)&cn->remaining[round] == 0) break;
+            if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
+            n = *(volatile int*)&cn->remaining[round];
+            if (n == 0) break;
+            if (n <= T) solo = true;  // the stragglers are CTA 0's job; the others go and wait
         }
-        if (tid == 0) cn->rounds = round + 1;
+        if (bid == 0 && lt == 0) cn->rounds = round + 1;
+        if (solo) grid_barrier(bar, bar_target);  // everybody waits for CTA 0's colours
     }
 
     stamp(1);
@@ -772,7 +819,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     // sequential (pass, colour) order has written them, then writes them back with version + 1.  Threads walk their
     // slots in (pass, colour) order and all CTAs are co-resident, so the globally smallest unfinished constraint can
     // always run: no deadlock.  The result is exactly the sequential sweep in (colour, then joint colour) order.
-    BodyIO io{a.vrec, a.sleep_ns};
+    BodyIO io{a.vrec, a.sleep_ns, &cn->err};
     // Polling throttle, CTA-local: s_done counts the slots this CTA has finished (all passes).  Before a warp starts its
     // slots of (pass, colour) it waits (on shared memory only) until the CTA has finished as many slots as precede that
     // phase locally, i.e. the CTA walks the phases roughly in step without bar.sync, and different CTAs drift freely.
@@ -785,9 +832,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     const int lane = lt & 31;
     auto wait_progress = [&](unsigned need) {
         if (lane == 0) {
-            while (*(volatile unsigned*)&s_done < need) {}
+            unsigned spins = 0;
+            while (*(volatile unsigned*)&s_done < need)
+                if ((++spins & 0xffffu) == 0u && (*(volatile int*)&cn->err == SYLT_ERR_INTERNAL || spins > (1u << 28))) break;
         }
         __syncwarp();
+    };
+    auto slack_of = [&](int c) -> int {  // slots of the previous local phase that may still be unfinished when a warp moves on
+        int prev = c > 0 ? s_lbase[c] - s_lbase[c - 1] : s_lbase[ncolors] - s_lbase[ncolors - 1];
+        return prev * a.slack_pct / 100;
     };
     auto add_progress = [&](bool did) {
         unsigned m = __ballot_sync(0xffffffffu, did);
@@ -849,7 +902,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
         const int cnt = s_lbase[c + 1] - s_lbase[c];
         for (int i0 = lt - lane; i0 < cnt; i0 += T) {  // warp-uniform trip count
             const bool did = i0 + lane < cnt;
-            wait_progress((unsigned)s_lbase[c]);
+            wait_progress((unsigned)max(0, s_lbase[c] - slack_of(c)));
             if (did) prestep_slot(c, i0 + lane);
             add_progress(did);
         }
@@ -905,7 +958,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
             const int cnt = s_lbase[c + 1] - s_lbase[c];
             for (int i0 = lt - lane; i0 < cnt; i0 += T) {
                 const bool did = i0 + lane < cnt;
-                wait_progress((unsigned)it * (unsigned)L + (unsigned)s_lbase[c]);
+                wait_progress((unsigned)max(0, it * L + s_lbase[c] - slack_of(c)));
                 if (did) apply_slot(c, i0 + lane, (unsigned)it);
                 add_progress(did);
             }
@@ -1049,8 +1102,9 @@ struct SyltWorld {
     // device state
     DBuf<float4> pose, vel, force, mp, geom, aabb;
     DBuf<float2> rotc, lverts;
-    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, cell_bodies, large, row_count, row_start, row_tmp;
-    DBuf<int4> cinfo;
+    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, large, row_count, row_start, row_tmp;
+    DBuf<int4> cinfo, cent_info;
+    DBuf<float4> cent_aabb;
     DBuf<int2> pairs;
     DBuf<unsigned long long> info, pscan, claim, spart64;
     DBuf<int> spart32;
@@ -1058,12 +1112,12 @@ struct SyltWorld {
     DBuf<float2> tmp_b;
     DBuf<unsigned> used;
     DBuf<ulonglong2> vrec;
-    int sleep_ns = 0, ctas_per_sm = 1, solve_threads = 512;
+    int sleep_ns = 0, ctas_per_sm = 1, solve_threads = 512, slack_pct = 0;
     bool timing = false;
     DBuf<unsigned long long> dbg;
     DBuf<int> jdeg;
     DBuf<int2> jrank;
-    DBuf<int> uncolored, prop, order;
+    DBuf<int> uncolored, uncolored2, prop, order;
     DBuf<Counters> counters;
     DBuf<int> tot32;
     DBuf<unsigned long long> tot64;
@@ -1189,7 +1243,8 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->rotc.ensure(B));
         SYLT_CUDA(w->rank.ensure(B));
         SYLT_CUDA(w->cinfo.ensure(B));
-        SYLT_CUDA(w->cell_bodies.ensure(B));
+        SYLT_CUDA(w->cent_info.ensure(B));
+        SYLT_CUDA(w->cent_aabb.ensure(B));
         SYLT_CUDA(w->row_count.ensure(B + 1));
         SYLT_CUDA(w->row_start.ensure(B + 2));
         SYLT_CUDA(w->row_tmp.ensure(B * ROWTMP));
@@ -1282,6 +1337,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->tmp_a.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->tmp_b.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->uncolored.ensure((size_t)ca));
+        SYLT_CUDA(w->uncolored2.ensure((size_t)ca));
         SYLT_CUDA(w->prop.ensure((size_t)ca));
         SYLT_CUDA(w->order.ensure((size_t)ca));
         for (int k = 0; k < 2; k++) {
@@ -1348,15 +1404,15 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->launches++;
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->tot32.p);
     if (e) return e;
-    k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->rank.p, w->cell_start.p, w->cell_bodies.p, w->gp);
+    k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->gp);
     const int nbR = (B + 127) / 128;
-    k_rows_count<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
+    k_rows_count<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->large.p, w->n_large, w->gp,
                                       w->row_count.p, w->row_tmp.p);
     w->launches += 2;
     e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->tot32.p + 1);
     if (e) return e;
     k_totals<<<1, 1, 0, st>>>(cn, w->tot32.p + 1, nullptr, 0, (int)w->cap_pairs);
-    k_rows_emit<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cell_bodies.p, w->large.p, w->n_large, w->gp,
+    k_rows_emit<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->large.p, w->n_large, w->gp,
                                      w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn);
     w->launches += 2;
     const int gridP = w->num_sms * 8;
@@ -1395,12 +1451,12 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         w->epoch = 1;
     }
     a.pose = w->pose.p; a.vel = w->vel.p; a.force = w->force.p; a.mp = w->mp.p; a.rotc = w->rotc.p; a.bflags = w->bflags.p;
-    a.cur = cur; a.used = w->used.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.prop = w->prop.p; a.order = w->order.p;
+    a.cur = cur; a.used = w->used.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.uncolored2 = w->uncolored2.p; a.prop = w->prop.p; a.order = w->order.p;
     a.jbodies = w->jbodies.p; a.jla = w->jla.p; a.jparam = w->jparam.p; a.jp = w->jp.p; a.jr = w->jr.p; a.jm = w->jm.p; a.jbias = w->jbias.p;
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
     void* args[] = {&a};
     a.smem_slots = w->smem_slots; a.smem_contacts = w->smem_contacts;
-    a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.dbg = w->timing ? w->dbg.p : nullptr;
+    a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.slack_pct = w->slack_pct; a.dbg = w->timing ? w->dbg.p : nullptr;
     SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_smem, st));
     w->launches++;
     // the set just built becomes "last step's"
@@ -1491,6 +1547,7 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     size_t budget = ((size_t)max_smem + 1024) / (size_t)w->ctas_per_sm - fa.sharedSizeBytes - 2048;  // 1 KB per CTA is reserved by the system
     w->smem_slots = 1792 / w->ctas_per_sm;
     if (const char* ev = getenv("SYLT_SOLVER_SLEEP_NS")) w->sleep_ns = std::max(0, atoi(ev));
+    if (const char* ev = getenv("SYLT_SOLVER_SLACK")) w->slack_pct = std::max(0, atoi(ev));
     if (const char* ev = getenv("SYLT_SOLVER_TIMING")) w->timing = atoi(ev) != 0;
     SYLT_CUDA(w->dbg.ensure(16));
     if (const char* ev = getenv("SYLT_SOLVER_SMEM_SLOTS")) w->smem_slots = std::max(0, atoi(ev));  // tests: force the global-memory path
@@ -1516,9 +1573,9 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
 static void free_all(SyltWorld* w) {
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
-    w->cell_count.release(); w->cell_start.release(); w->cell_bodies.release(); w->large.release(); w->row_count.release();
+    w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->cent_aabb.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
-    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release();
+    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
     w->prop.release(); w->order.release(); w->tot32.release(); w->tot64.release();
     for (int k = 0; k < 2; k++) {
         auto& a = w->arb[k];
