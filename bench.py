@@ -8,7 +8,8 @@ the job owns.  Worlds are first settled (untimed, stated in config.settle_steps)
 contact count; then W warm-up steps and exactly K timed steps, barrier + synchronize on both sides, device time by
 CUDA events on the launching stream, max over ranks.
 
-  value  : device-resident throughput (state stays in HBM; one k_batch_step launch per step)
+  value  : device-resident throughput (state stays in HBM; sylt_batch_step_n(dt, K): one k_batch_step launch runs the K
+           steps, each world staying in shared memory across them)
   e2e    : the same metric through the C ABI with HOST buffers: every step uploads all body states from pinned host
            memory, steps, and reads all body states back (sylt_batch_step_host)
   roofline: algorithmic bytes of SURVEY.md §8(d)  (116 B + 56 P + 152 C + 144 J + I (120 C + 124 J)) per launch
@@ -142,7 +143,7 @@ def reference_arm(args, rank):
         "gpu_launches": 0}), flush=True)
 
 
-def bench_world100k(device, steps):
+def bench_world100k(device, steps, cpu=True):
     """ms/step of one 100k-body world (config 3) in the falling and the settled phase; single GPU by construction."""
     from sylt2d_b200 import World, scenes
     sc = scenes.box_drop(100000, seed=42, iterations=ITER)
@@ -170,7 +171,37 @@ def bench_world100k(device, steps):
     peak, _ = peaks()
     out["algorithmic_bytes_per_step"] = by
     out["roofline_frac_whole_step"] = by / (ms / steps * 1e-3) / 1e9 / peak
+    out["solver_bytes_per_step"] = ITER * 120 * C
     out["body_steps_per_sec"] = B * steps / (ms * 1e-3)
+    if cpu:
+        # CPU reference path on the same settled state, single thread (the reference is single-threaded):
+        #  * algorithm-matched: oracle with a uniform-grid candidate search (same arbiter set as all-pairs, tests/test_oracle_kat.py)
+        #  * faithful all-pairs (src/world.rs:74-77) is O(n^2): timed on the first n bodies for small n and extrapolated with t = a n^2
+        from oracle import orc
+        st = w.get_bodies()
+        o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=0, broadphase=1)
+        o.load_scene(sc)
+        o.set_bodies(st)
+        o.step(sc.dt)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            o.step(sc.dt)
+        cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
+        out["cpu_grid_ms_per_step_1thread"] = cpu_ms
+        out["speedup_vs_cpu_grid_1thread"] = cpu_ms / (ms / steps)
+        n_small = 4000
+        import numpy as _np
+        sub = scenes.Scene(sc.name, sc.bodies[:n_small], sc.joints, sc.verts, sc.gravity, sc.iterations, sc.dt, sc.ctx)
+        o2 = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=0, broadphase=0)
+        o2.load_scene(sub)
+        o2.set_bodies(st[:n_small])
+        o2.step(sc.dt)
+        t0 = time.perf_counter()
+        o2.step(sc.dt)
+        t_small = (time.perf_counter() - t0) * 1e3
+        out["cpu_allpairs_ms_per_step_1thread_n4000"] = t_small
+        out["cpu_allpairs_ms_per_step_1thread_extrapolated_100k"] = t_small * (B / n_small) ** 2
+        out["speedup_vs_cpu_allpairs_extrapolated"] = out["cpu_allpairs_ms_per_step_1thread_extrapolated_100k"] / (ms / steps)
     return out
 
 
@@ -228,8 +259,7 @@ def main():
     barrier()
     t0 = time.time()
     batch.timer_start()
-    for _ in range(args.steps):
-        batch.step_n_async(scene.dt, 1)
+    batch.step_n_async(scene.dt, args.steps)  # ONE launch runs the K steps: a world stays in shared memory across them
     ms = batch.timer_stop()
     barrier()
     t1 = time.time()
@@ -290,7 +320,8 @@ def main():
     P_w = float(arb.shape[0]) if arb.shape[0] else C_w / 2  # candidate slots ~ arbiters in a settled pyramid
     bytes_world = 116 * nb + 56 * P_w + 152 * C_w + ITER * 120 * C_w
     bytes_launch = bytes_world * my_worlds
-    achieved = bytes_launch / (ms / args.steps * 1e-3) / 1e9
+    bytes_launch *= args.steps  # the one launch of the timed region covers K steps
+    achieved = bytes_launch / (ms * 1e-3) / 1e9
     roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
             "kernel": "k_batch_step", "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
             "note": "effective bandwidth: worlds are shared-memory resident for the whole step, so the algorithmic bytes of SURVEY.md 8(d) "
@@ -339,7 +370,7 @@ def main():
             out["cpu_baseline"]["single_thread_sample"] = f"2 worlds x {s1} steps ({el1:.1f} s), 1 thread"
         if not args.skip_world100k:
             try:
-                out["world100k"] = bench_world100k(local_rank, 100)
+                out["world100k"] = bench_world100k(local_rank, 100, cpu=not args.skip_cpu)
             except Exception as e:  # reported, never hidden
                 out["world100k"] = {"error": repr(e)}
     if rank == 0:
