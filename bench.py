@@ -331,7 +331,7 @@ def main():
         try:
             with open(tp) as f:
                 tj = json.load(f)
-            roof["traffic"] = tj.get("dram_bytes_per_launch_per_world", 0) * my_worlds
+            roof["traffic"] = (tj.get("dram_bytes_per_world_base", 0) + tj.get("dram_bytes_per_world_per_step", 0) * args.steps) * my_worlds
         except Exception:
             pass
 
