@@ -130,6 +130,11 @@ int sylt_world_destroy(SyltWorld* w);
 int sylt_world_clear(SyltWorld* w);
 int sylt_world_set_context(SyltWorld* w, int accumulate_impulse, int warm_starting, int position_correction);
 int sylt_world_set_iterations(SyltWorld* w, uint32_t iterations);
+/* Opt-in corrected physics, default OFF (= bit-for-bit the reference).  fix_features: old and new contacts are matched by
+ * their packed feature edges (Box2D-lite) instead of the never-written FeaturePair.value, which makes every contact
+ * inherit old contact 0's impulses (arbiter.rs:145-176).  fix_inverse: Mat2x2 inverse scaled by 1/det instead of det
+ * (math_utils.rs:185-199), i.e. rigid instead of very soft joints. */
+int sylt_world_set_fixes(SyltWorld* w, int fix_features, int fix_inverse);
 /* 0 = keep; defaults: pairs 16*B, arbiters 8*B, contacts 16*B (grown automatically when bodies are added) */
 int sylt_world_set_capacity(SyltWorld* w, int64_t max_pairs, int64_t max_arbiters, int64_t max_contacts);
 
@@ -189,6 +194,8 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
                       float gravity_x, float gravity_y, uint32_t iterations, int device, SyltBatch** out);
 int sylt_batch_destroy(SyltBatch* b);
 int sylt_batch_set_context(SyltBatch* b, int accumulate_impulse, int warm_starting, int position_correction);
+/* see sylt_world_set_fixes; fix_features is not available for batches (SYLT_ERR_UNSUPPORTED) */
+int sylt_batch_set_fixes(SyltBatch* b, int fix_features, int fix_inverse);
 int sylt_batch_step_n(SyltBatch* b, float dt, int32_t n);
 int sylt_batch_step_n_async(SyltBatch* b, float dt, int32_t n);
 int sylt_batch_sync(SyltBatch* b);

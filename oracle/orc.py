@@ -51,6 +51,7 @@ def lib():
     L.orc_world_set_context.argtypes = [vp, i32, i32, i32]
     L.orc_world_set_mode.argtypes = [vp, i32, i32]
     L.orc_world_set_iterations.argtypes = [vp, C.c_uint32]
+    L.orc_world_set_fixes.argtypes = [vp, i32, i32]
     L.orc_world_add_box.argtypes = [vp, u64] + [f32] * 10
     L.orc_world_add_polygon.argtypes = [vp, u64, vp, i32] + [f32] * 8
     L.orc_world_add_joint.argtypes = [vp, u64, u64, f32, f32]
@@ -102,6 +103,9 @@ class OracleWorld:
 
     def set_mode(self, sincos_mode, broadphase):
         self.L.orc_world_set_mode(self.h, sincos_mode, broadphase)
+
+    def set_fixes(self, fix_features=False, fix_inverse=False):
+        self.L.orc_world_set_fixes(self.h, int(fix_features), int(fix_inverse))
 
     def clear(self):
         self.L.orc_world_clear(self.h)

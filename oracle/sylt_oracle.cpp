@@ -56,10 +56,12 @@ inline M2 rot_from_angle(float a, int mode) {                                  /
     return {{c, s}, {-s, c}};
 }
 // Q-3: multiplies the adjugate by det instead of 1/det (math_utils.rs:185-199)
-inline bool invert(const M2& m, M2* out) {
+// fix = true: the opt-in corrected mode (Box2D-lite's Mat22::Invert: scale by 1/det) — NOT the reference's behaviour
+inline bool invert(const M2& m, M2* out, bool fix = false) {
     float a = m.c1.x, b = m.c2.x, c = m.c1.y, d = m.c2.y;
     float det = a * d - b * c;
     if (det == 0.0f) return false;
+    if (fix) det = 1.0f / det;
     *out = {{det * d, -det * c}, {-det * b, det * a}};
     return true;
 }
@@ -392,7 +394,7 @@ struct Arbiter {
     std::vector<Contact> contacts;
     uint64_t stamp = 0;
 };
-struct Ctx { bool accumulate = true, warm = false, poscorr = true; };                        // world.rs:11-16,38-42 (Q-4)
+struct Ctx { bool accumulate = true, warm = false, poscorr = true; bool fix_features = false, fix_inverse = false; };                        // world.rs:11-16,38-42 (Q-4)
 
 int narrow(std::vector<Contact>& out, const Body& a, const Body& b, int mode) {              // arbiter.rs:124-127
     if (a.shape == 0 && b.shape == 0) return collide(out, a, b, mode);
@@ -403,8 +405,12 @@ void arbiter_update(Arbiter& arb, const std::vector<Contact>& nc, int num_new, c
     std::vector<Contact> merged;
     for (const Contact& c_new : nc) {
         int k = -1;
-        for (size_t j = 0; j < arb.contacts.size(); j++)
-            if (arb.contacts[j].feature.value == c_new.feature.value) { k = (int)j; break; }
+        auto packed = [](const Contact& c) { return (uint32_t)c.feature.e.in1 | ((uint32_t)c.feature.e.out1 << 8) | ((uint32_t)c.feature.e.in2 << 16) | ((uint32_t)c.feature.e.out2 << 24); };
+        for (size_t j = 0; j < arb.contacts.size(); j++) {
+            // reference: FeaturePair.value (never written => always equal, quirk Q-2); corrected mode: the packed edge ids
+            bool same = ctx.fix_features ? packed(arb.contacts[j]) == packed(c_new) : arb.contacts[j].feature.value == c_new.feature.value;
+            if (same) { k = (int)j; break; }
+        }
         if (k > -1) {
             const Contact& c_old = arb.contacts[(size_t)k];
             Contact c = c_new;
@@ -515,7 +521,7 @@ bool joint_pre_step(Joint& j, std::vector<Body>& bodies, const Ctx& ctx, float i
     M2 k = k1 + k2 + k3;
     k.c1.x += j.softness;
     k.c2.y += j.softness;
-    if (!invert(k, &j.m)) { *bad = k; return false; }  // Q-15: mid-step abort
+    if (!invert(k, &j.m, ctx.fix_inverse)) { *bad = k; return false; }  // Q-15: mid-step abort
     V2 p1 = body_1.position + j.r1, p2 = body_2.position + j.r2;
     V2 dp = p2 - p1;
     if (ctx.poscorr) j.bias = dp * inv_dt * j.bias_factor * -1.0f;
@@ -727,6 +733,7 @@ void orc_world_clear(OrcWorld* w) { w->bodies.clear(); w->joints.clear(); w->arb
 void orc_world_set_context(OrcWorld* w, int a, int ws, int pc) { w->ctx.accumulate = a != 0; w->ctx.warm = ws != 0; w->ctx.poscorr = pc != 0; }
 void orc_world_set_mode(OrcWorld* w, int sincos_mode, int broadphase) { w->sincos_mode = sincos_mode; w->broadphase = broadphase; }
 void orc_world_set_iterations(OrcWorld* w, uint32_t it) { w->iterations = it; }
+void orc_world_set_fixes(OrcWorld* w, int fix_features, int fix_inverse) { w->ctx.fix_features = fix_features != 0; w->ctx.fix_inverse = fix_inverse != 0; }
 
 static int push_body(OrcWorld* w, Body b, uint64_t id, float friction, float x, float y, float rot, float vx, float vy, float om) {
     b.id = id; b.friction = friction; b.position = {x, y}; b.rotation = rot; b.velocity = {vx, vy}; b.angular_velocity = om;

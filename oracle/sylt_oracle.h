@@ -56,6 +56,9 @@ void orc_world_set_context(OrcWorld* w, int accumulate_impulse, int warm_startin
  * broadphase : 0 = all pairs (reference, world.rs:74-77), 1 = uniform grid candidates (same pair set). */
 void orc_world_set_mode(OrcWorld* w, int sincos_mode, int broadphase);
 void orc_world_set_iterations(OrcWorld* w, uint32_t iterations);
+/* opt-in corrected physics (NOT the reference's behaviour; mirrors sylt_world_set_fixes): contact matching by packed
+ * feature edges instead of the never-written FeaturePair.value (quirk Q-2), Mat2x2 inverse scaled by 1/det (quirk Q-3) */
+void orc_world_set_fixes(OrcWorld* w, int fix_features, int fix_inverse);
 
 /* return body index >= 0, or -(error code) */
 int orc_world_add_box(OrcWorld* w, uint64_t id, float wx, float wy, float mass, float friction,

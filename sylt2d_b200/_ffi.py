@@ -36,13 +36,13 @@ assert STEP_STATS.itemsize == 32 and BATCH_STATS.itemsize == 40
 SYMBOLS = [
     "sylt_last_error_string", "sylt_device_count",
     "sylt_world_create", "sylt_world_destroy", "sylt_world_clear", "sylt_world_set_context", "sylt_world_set_iterations",
-    "sylt_world_set_capacity", "sylt_world_add_box", "sylt_world_add_polygon", "sylt_world_add_bodies", "sylt_world_add_joint",
+    "sylt_world_set_capacity", "sylt_world_set_fixes", "sylt_world_add_box", "sylt_world_add_polygon", "sylt_world_add_bodies", "sylt_world_add_joint",
     "sylt_world_add_joints", "sylt_world_set_joint_params", "sylt_world_add_force", "sylt_world_num_bodies", "sylt_world_num_joints",
     "sylt_world_num_arbiters", "sylt_world_num_contacts", "sylt_world_get_bodies", "sylt_world_set_bodies", "sylt_world_get_body_props",
     "sylt_world_get_arbiters", "sylt_world_get_joints", "sylt_world_get_joint_order", "sylt_world_get_stats",
     "sylt_world_last_error_matrix", "sylt_world_broad_phase", "sylt_world_step", "sylt_world_step_n", "sylt_world_step_n_async",
     "sylt_world_sync", "sylt_world_timer_start", "sylt_world_timer_stop", "sylt_world_launch_count", "sylt_collide_pairs", "sylt_sincos",
-    "sylt_batch_create", "sylt_batch_destroy", "sylt_batch_set_context", "sylt_batch_step_n", "sylt_batch_step_n_async",
+    "sylt_batch_create", "sylt_batch_destroy", "sylt_batch_set_context", "sylt_batch_set_fixes", "sylt_batch_step_n", "sylt_batch_step_n_async",
     "sylt_batch_sync", "sylt_batch_step_host", "sylt_batch_timer_start", "sylt_batch_timer_stop", "sylt_batch_launch_count", "sylt_batch_num_worlds",
     "sylt_batch_num_bodies", "sylt_batch_get_bodies", "sylt_batch_set_bodies", "sylt_batch_get_arbiters", "sylt_batch_get_joints",
     "sylt_batch_get_joint_order", "sylt_batch_get_errors", "sylt_batch_stats",
@@ -74,6 +74,8 @@ def lib():
         getattr(L, "sylt_world_" + n).argtypes = [vp]
     L.sylt_world_set_context.argtypes = [vp, i32, i32, i32]
     L.sylt_world_set_iterations.argtypes = [vp, u32]
+    L.sylt_world_set_fixes.argtypes = [vp, i32, i32]
+    L.sylt_batch_set_fixes.argtypes = [vp, i32, i32]
     L.sylt_world_set_capacity.argtypes = [vp, i64, i64, i64]
     L.sylt_world_add_box.argtypes = [vp, u64] + [f32] * 10 + [vp]
     L.sylt_world_add_polygon.argtypes = [vp, u64, vp, i32] + [f32] * 8 + [vp]

@@ -47,6 +47,9 @@ class Batch:
     def set_context(self, accumulate_impulse=True, warm_starting=False, position_correction=True):
         check(self.L.sylt_batch_set_context(self.h, int(accumulate_impulse), int(warm_starting), int(position_correction)))
 
+    def set_fixes(self, fix_features=False, fix_inverse=False):
+        check(self.L.sylt_batch_set_fixes(self.h, int(fix_features), int(fix_inverse)))
+
     def step_n(self, dt, n):
         check(self.L.sylt_batch_step_n(self.h, dt, n))
 

@@ -42,7 +42,7 @@ struct SlotExport {  // full record of one arbiter slot, written for worlds in t
 };
 
 struct BatchArgs {
-    int n_worlds, world_begin, n_steps, iterations, accumulate, warm, poscorr;
+    int n_worlds, world_begin, n_steps, iterations, accumulate, warm, poscorr, fix_inverse;
     float dt, inv_dt, gx, gy, cell;
     int Bmax, Jmax, cap, nbk;
     int export_first, export_count;
@@ -461,7 +461,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
                 JointConst jc;
                 M2 bad;
                 bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), c1.x, c1.y, mk(p2.x, p2.y), c2.x, c2.y,
-                                        i1.x, i1.y, i2.x, i2.y, a.inv_dt, poscorr, warm, pacc, v1, v2, jc, &bad);
+                                        i1.x, i1.y, i2.x, i2.y, a.inv_dt, poscorr, warm, pacc, v1, v2, jc, &bad, a.fix_inverse != 0);
                 s.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
                 if (!ok) {  // quirk Q-15
                     if (atomicCAS(s_err, 0, SYLT_ERR_NO_INVERSE) == 0) {
@@ -669,6 +669,7 @@ struct SyltBatch {
     float gx = 0, gy = 0;
     uint32_t iterations = 10;
     int accumulate = 1, warm = 0, poscorr = 1;  // World::new defaults (world.rs:38-42)
+    int fix_inverse = 0;                        // opt-in corrected Mat2x2 inverse, default off
     size_t smem = 0;
     int64_t launches = 0;
     uint64_t body_steps = 0;
@@ -723,7 +724,7 @@ int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaSt
     BatchArgs a;
     memset(&a, 0, sizeof a);
     a.n_worlds = w1; a.world_begin = w0; a.n_steps = n; a.iterations = (int)b->iterations;
-    a.accumulate = b->accumulate; a.warm = b->warm; a.poscorr = b->poscorr;
+    a.accumulate = b->accumulate; a.warm = b->warm; a.poscorr = b->poscorr; a.fix_inverse = b->fix_inverse;
     a.dt = dt; a.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;  // world.rs:108
     a.gx = b->gx; a.gy = b->gy; a.Bmax = b->Bmax; a.Jmax = b->Jmax; a.cap = b->cap; a.nbk = b->nbk; a.cell = b->cell; a.bflags = b->bflags.p;
     a.export_first = b->export_first; a.export_count = b->export_count;
@@ -924,6 +925,13 @@ int sylt_batch_destroy(SyltBatch* b) {
 int sylt_batch_set_context(SyltBatch* b, int acc, int warm, int pc) {
     if (!b) return SYLT_ERR_INVALID;
     b->accumulate = acc != 0; b->warm = warm != 0; b->poscorr = pc != 0;
+    return SYLT_OK;
+}
+
+int sylt_batch_set_fixes(SyltBatch* b, int fix_features, int fix_inverse) {
+    if (!b) return SYLT_ERR_INVALID;
+    if (fix_features) return SYLT_ERR_UNSUPPORTED;  // the per-world slot cache keeps contact 0's impulses only
+    b->fix_inverse = fix_inverse != 0;
     return SYLT_OK;
 }
 

@@ -107,7 +107,7 @@ struct JointConst {
 // Returns false (and the singular K in *bad) when K has no inverse (quirk Q-15).
 SYLT_HD bool joint_prestep(V2 la1, V2 la2, float softness, float bias_factor, V2 p1, float c1, float s1, V2 p2, float c2, float s2,
                            float im1, float ii1, float im2, float ii2, float inv_dt, bool position_correction, bool warm_starting,
-                           V2& p_acc, Vel& b1, Vel& b2, JointConst& jc, M2* bad) {
+                           V2& p_acc, Vel& b1, Vel& b2, JointConst& jc, M2* bad, bool true_inverse = false) {
     V2 r1 = rot_cs(c1, s1) * la1;
     V2 r2 = rot_cs(c2, s2) * la2;
     M2 k1 = mk(mk(im1 + im2, 0.0f), mk(0.0f, im1 + im2));
@@ -117,7 +117,7 @@ SYLT_HD bool joint_prestep(V2 la1, V2 la2, float softness, float bias_factor, V2
     k.c1.x += softness;
     k.c2.y += softness;
     jc.r1 = r1; jc.r2 = r2; jc.softness = softness;
-    if (!invert_q3(k, &jc.m)) { *bad = k; return false; }
+    if (!invert_q3(k, &jc.m, true_inverse)) { *bad = k; return false; }
     V2 a1 = p1 + r1, a2 = p2 + r2;
     V2 dp = a2 - a1;
     if (position_correction) jc.bias = dp * inv_dt * bias_factor * -1.0f;

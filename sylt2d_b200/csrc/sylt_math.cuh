@@ -41,10 +41,12 @@ SYLT_HD M2 rot_cs(float c, float s) { return mk(mk(c, s), mk(-s, c)); }
 SYLT_HD M2 rot_angle(float a) { return rot_cs(sylt_cosf(a), sylt_sinf(a)); }
 
 // Mat2x2::invert as the reference has it (quirk Q-3: adjugate * det, not / det)   // :185-199
-SYLT_HD bool invert_q3(M2 m, M2* out) {
+// true_inverse = true is the opt-in corrected mode (scale by 1/det, Box2D-lite's Mat22::Invert), not the reference.
+SYLT_HD bool invert_q3(M2 m, M2* out, bool true_inverse = false) {
     float a = m.c1.x, b = m.c2.x, c = m.c1.y, d = m.c2.y;
     float det = a * d - b * c;
     if (det == 0.0f) return false;
+    if (true_inverse) det = 1.0f / det;
     *out = mk(mk(det * d, -det * c), mk(-det * b, det * a));
     return true;
 }

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int2* pairs, const unsigned long long* info, const unsigned long long* scan,
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
-                                               unsigned* used, int* uncolored) {
+                                               unsigned* used, int* uncolored, int fix_features) {
     int P = min(cn->n_pairs, cap_pairs);
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     __shared__ int s_hist[NC];
@@ -462,6 +462,17 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         for (int k = 0; k < n; k++) {
             float4 ta = tmp_a[(size_t)p * MAXC + k];
             float2 tb = tmp_b[(size_t)p * MAXC + k];
+            if (fix_features && found >= 0) {  // opt-in (NOT the reference): match old contacts by their packed feature edges
+                pn = 0.0f; pt = 0.0f; pnb = 0.0f;
+                int2 om = old.meta[found];
+                for (int q = 0; q < om.x; q++) {
+                    float4 od = old.cd[om.y + q];
+                    if (__float_as_uint(od.w) == __float_as_uint(tb.y)) {
+                        if (warm) { float4 oc = old.cc[om.y + q]; pn = oc.y; pt = oc.z; pnb = od.z; }
+                        break;
+                    }
+                }
+            }
             cur.ca[coff + k] = make_float4(ta.z, ta.w, 0.0f, 0.0f);
             cur.cb[coff + k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
             cur.cc[coff + k] = make_float4(0.0f, pn, pt, tb.x);
@@ -511,6 +522,7 @@ struct SolveArgs {
     int *uncolored, *uncolored2, *prop, *order;
     ulonglong2* vrec;           // 2 per body: versioned velocities (see k_prepare)
     int sleep_ns;               // back-off between polls of the dataflow wait (0 = spin)
+    int fix_inverse;            // opt-in corrected Mat2x2 inverse (NOT the reference)
     int slack_pct;              // polling throttle slack (see wait_progress)
     unsigned long long* dbg;    // optional: globaltimer stamps of CTA 0 at the section boundaries (SYLT_SOLVER_TIMING=1)
     const int* jdeg;            // joints touching each body
@@ -930,7 +942,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
             M2 bad;
             Vel w1 = v1, w2 = v2;
             bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), r1c.x, r1c.y, mk(p2.x, p2.y), r2c.x, r2c.y,
-                                    im1, ii1, im2, ii2, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, w1, w2, jc, &bad);
+                                    im1, ii1, im2, ii2, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, w1, w2, jc, &bad, a.fix_inverse != 0);
             a.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
             if (!ok) {  // quirk Q-15: NoInverse aborts the step before the iterations
                 if (atomicCAS(&cn->err, 0, SYLT_ERR_NO_INVERSE) == 0) {
@@ -1082,6 +1094,7 @@ struct SyltWorld {
     float gx = 0, gy = 0;
     uint32_t iterations = 10;
     int accumulate = 1, warm = 0, poscorr = 1;  // World::new defaults (world.rs:38-42, quirk Q-4)
+    int fix_features = 0, fix_inverse = 0;      // opt-in corrected physics, default off (= the reference's behaviour)
     int64_t launches = 0;
     int num_sms = 0, coop_blocks = 0, smem_slots = 0, smem_contacts = 0;
     size_t solve_smem = 0;
@@ -1430,11 +1443,11 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (w->any_poly)
         k_build<MAX_MANIFOLD><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p,
                                                               w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p,
-                                                              w->bflags_old.p, cur, old, w->warm, w->used.p, w->uncolored.p);
+                                                              w->bflags_old.p, cur, old, w->warm, w->used.p, w->uncolored.p, w->fix_features);
     else
         k_build<2><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p, w->info.p,
                                                    w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur,
-                                                   old, w->warm, w->used.p, w->uncolored.p);
+                                                   old, w->warm, w->used.p, w->uncolored.p, w->fix_features);
     w->launches += 2;
     SYLT_CUDA(cudaGetLastError());
 
@@ -1456,7 +1469,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
     void* args[] = {&a};
     a.smem_slots = w->smem_slots; a.smem_contacts = w->smem_contacts;
-    a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.slack_pct = w->slack_pct; a.dbg = w->timing ? w->dbg.p : nullptr;
+    a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.slack_pct = w->slack_pct; a.fix_inverse = w->fix_inverse; a.dbg = w->timing ? w->dbg.p : nullptr;
     SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_smem, st));
     w->launches++;
     // the set just built becomes "last step's"
@@ -1612,6 +1625,11 @@ int sylt_world_clear(SyltWorld* w) {  // world.rs:67-71
 int sylt_world_set_context(SyltWorld* w, int acc, int warm, int pc) {
     if (!w) return SYLT_ERR_INVALID;
     w->accumulate = acc != 0; w->warm = warm != 0; w->poscorr = pc != 0;
+    return SYLT_OK;
+}
+int sylt_world_set_fixes(SyltWorld* w, int fix_features, int fix_inverse) {
+    if (!w) return SYLT_ERR_INVALID;
+    w->fix_features = fix_features != 0; w->fix_inverse = fix_inverse != 0;
     return SYLT_OK;
 }
 int sylt_world_set_iterations(SyltWorld* w, uint32_t it) {

@@ -169,6 +169,10 @@ class World:
     def set_capacity(self, max_pairs=0, max_arbiters=0, max_contacts=0):
         check(self.L.sylt_world_set_capacity(self.h, max_pairs, max_arbiters, max_contacts))
 
+    def set_fixes(self, fix_features=False, fix_inverse=False):
+        """Opt-in corrected physics (default off = the reference's behaviour): see sylt_world_set_fixes."""
+        check(self.L.sylt_world_set_fixes(self.h, int(fix_features), int(fix_inverse)))
+
     def set_iterations(self, iterations):
         check(self.L.sylt_world_set_iterations(self.h, iterations))
         self.iterations = iterations
