@@ -274,11 +274,13 @@ def main():
     st = batch.stats()
 
     # ---- e2e: host buffers in, host buffers out, every step (pinned memory; the C ABI does one DMA each way)
-    host_in = torch.empty(my_bodies * 9, dtype=torch.float32, pin_memory=True)
-    host_out = torch.empty(my_bodies * 9, dtype=torch.float32, pin_memory=True)
-    from sylt2d_b200._ffi import BODY_STATE
-    hin = host_in.numpy().view(BODY_STATE)
-    hin[:] = batch.get_bodies()
+    FPB = 6  # x, y, rotation, vx, vy, angular_velocity: the 24 bytes per body a caller mirrors every step
+    host_in = torch.empty(my_bodies * FPB, dtype=torch.float32, pin_memory=True)
+    host_out = torch.empty(my_bodies * FPB, dtype=torch.float32, pin_memory=True)
+    st0 = batch.get_bodies()
+    hin = host_in.numpy().reshape(my_bodies, FPB)
+    for k, f in enumerate(("x", "y", "rotation", "vx", "vy", "angular_velocity")):
+        hin[:, k] = st0[f]
     L, h = batch.L, batch.h
     import ctypes as C
     pin, pout = C.c_void_p(host_in.data_ptr()), C.c_void_p(host_out.data_ptr())
@@ -287,7 +289,7 @@ def main():
 
     def e2e_step():
         # the caller's state for the next step is the result of this one: the two pinned buffers alternate roles
-        assert L.sylt_batch_step_host(h, scene.dt, 1, bufs[0], bufs[1]) == 0
+        assert L.sylt_batch_step_host6(h, scene.dt, 1, bufs[0], bufs[1]) == 0
         bufs.reverse()
 
     for _ in range(3):
@@ -344,8 +346,8 @@ def main():
                    "parallelism": f"worlds sharded over {world_size} GPU(s), no per-step communication",
                    "l2": "per-GPU state (bodies + per-world slot cache) exceeds the 126 MB L2 at N<=2; smaller shards are L2-resident by nature of strong scaling",
                    "contacts_per_world": C_w, "errors": errors_total},
-        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": my_bodies * 36 * world_size, "d2h_bytes_per_step": my_bodies * 36 * world_size,
-                "steps": e2e_steps, "api": "sylt_batch_step_host(dt, 1, in, out): all body states H2D + step + all body states D2H per step, pinned host buffers, world chunks pipelined over 4 streams"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": my_bodies * 4 * FPB * world_size, "d2h_bytes_per_step": my_bodies * 4 * FPB * world_size,
+                "steps": e2e_steps, "api": "sylt_batch_step_host6(dt, 1, in, out): every body state (x, y, rotation, vx, vy, angular_velocity) H2D + one step + every body state D2H per step, pinned host buffers, world chunks pipelined over 4 streams"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "clocks": clocks,

@@ -203,6 +203,9 @@ int sylt_batch_sync(SyltBatch* b);
  * steps, download every body state to `out` (NULL: skip).  World chunks are pipelined over several streams so that the
  * H2D copy, the kernels and the D2H copy overlap.  Equivalent to set_bodies + step_n + get_bodies. */
 int sylt_batch_step_host(SyltBatch* b, float dt, int32_t n, const SyltBodyState* in, SyltBodyState* out);
+/* same with compact 24-byte records per body: x, y, rotation, vx, vy, angular_velocity (the fields a caller mirrors every
+ * step; a batch has no external forces) */
+int sylt_batch_step_host6(SyltBatch* b, float dt, int32_t n, const float* in6, float* out6);
 int sylt_batch_timer_start(SyltBatch* b);
 int sylt_batch_timer_stop(SyltBatch* b, float* out_ms);
 int64_t sylt_batch_launch_count(SyltBatch* b);

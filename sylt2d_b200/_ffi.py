@@ -43,7 +43,7 @@ SYMBOLS = [
     "sylt_world_last_error_matrix", "sylt_world_broad_phase", "sylt_world_step", "sylt_world_step_n", "sylt_world_step_n_async",
     "sylt_world_sync", "sylt_world_timer_start", "sylt_world_timer_stop", "sylt_world_launch_count", "sylt_collide_pairs", "sylt_sincos",
     "sylt_batch_create", "sylt_batch_destroy", "sylt_batch_set_context", "sylt_batch_set_fixes", "sylt_batch_step_n", "sylt_batch_step_n_async",
-    "sylt_batch_sync", "sylt_batch_step_host", "sylt_batch_timer_start", "sylt_batch_timer_stop", "sylt_batch_launch_count", "sylt_batch_num_worlds",
+    "sylt_batch_sync", "sylt_batch_step_host", "sylt_batch_step_host6", "sylt_batch_timer_start", "sylt_batch_timer_stop", "sylt_batch_launch_count", "sylt_batch_num_worlds",
     "sylt_batch_num_bodies", "sylt_batch_get_bodies", "sylt_batch_set_bodies", "sylt_batch_get_arbiters", "sylt_batch_get_joints",
     "sylt_batch_get_joint_order", "sylt_batch_get_errors", "sylt_batch_stats",
 ]
@@ -108,6 +108,7 @@ def lib():
     L.sylt_batch_step_n_async.argtypes = [vp, f32, i32]
     L.sylt_batch_timer_stop.argtypes = [vp, vp]
     L.sylt_batch_step_host.argtypes = [vp, f32, i32, vp, vp]
+    L.sylt_batch_step_host6.argtypes = [vp, f32, i32, vp, vp]
     L.sylt_batch_launch_count.argtypes = [vp]
     L.sylt_batch_launch_count.restype = i64
     L.sylt_batch_num_bodies.argtypes = [vp]

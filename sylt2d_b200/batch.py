@@ -47,6 +47,14 @@ class Batch:
     def set_context(self, accumulate_impulse=True, warm_starting=False, position_correction=True):
         check(self.L.sylt_batch_set_context(self.h, int(accumulate_impulse), int(warm_starting), int(position_correction)))
 
+    def step_host6(self, dt, n, states_in=None, states_out=None):
+        """step_host with compact float32 (n_bodies, 6) arrays: x, y, rotation, vx, vy, angular_velocity."""
+        nb = self.num_bodies
+        for a in (states_in, states_out):
+            assert a is None or (a.dtype == np.float32 and a.shape == (nb, 6) and a.flags["C_CONTIGUOUS"])
+        check(self.L.sylt_batch_step_host6(self.h, dt, n, ptr(states_in), ptr(states_out)))
+        return states_out
+
     def set_fixes(self, fix_features=False, fix_inverse=False):
         check(self.L.sylt_batch_set_fixes(self.h, int(fix_features), int(fix_inverse)))
 

@@ -613,6 +613,24 @@ __global__ void k_pack_states(int n, const float4* pose, const float4* vel, Sylt
     out[i] = s;
 }
 
+// compact 24-byte records (x, y, rotation, vx, vy, angular_velocity): what a caller mirrors every step; forces are
+// inputs only and a batch has none
+__global__ void k_unpack_states6(int n, const float* in, float4* pose, float4* vel) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float2* q = (const float2*)(in + 6 * (size_t)i);
+    float2 a = q[0], b = q[1], c = q[2];
+    pose[i] = make_float4(a.x, a.y, b.x, 0.0f);
+    vel[i] = make_float4(b.y, c.x, c.y, 0.0f);
+}
+__global__ void k_pack_states6(int n, const float4* pose, const float4* vel, float* out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 p = pose[i], v = vel[i];
+    float2* q = (float2*)(out + 6 * (size_t)i);
+    q[0] = make_float2(p.x, p.y); q[1] = make_float2(p.z, v.x); q[2] = make_float2(v.y, v.z);
+}
+
 struct StatsOut {
     unsigned long long contacts, errors;
     double ke;
@@ -955,11 +973,13 @@ int sylt_batch_step_n(SyltBatch* b, float dt, int32_t n) {
 }
 // One step_n with HOST buffers: upload all body states, step, download all body states — chunked over worlds and
 // pipelined on several streams so the two DMA directions overlap the kernels (pinned host memory recommended).
-int sylt_batch_step_host(SyltBatch* b, float dt, int32_t n, const SyltBodyState* in, SyltBodyState* out) {
+// floats_per_body: 9 (SyltBodyState) or 6 (x, y, rotation, vx, vy, angular_velocity).
+static int step_host_impl(SyltBatch* b, float dt, int32_t n, const float* in, float* out, int fpb) {
     if (!b || n < 0) return SYLT_ERR_INVALID;
     SYLT_CUDA(cudaSetDevice(b->device));
     SYLT_CUDA(cudaStreamSynchronize(b->stream));
     SYLT_CUDA(b->stage.ensure((size_t)b->n_bodies));
+    float* stage = (float*)b->stage.p;  // 9 floats per body of room; the compact layout uses the first 6 * n_bodies floats
     const int W = b->n_worlds;
     int chunks = std::max(1, std::min(16, W / 512));
     const int per = (W + chunks - 1) / chunks;
@@ -968,9 +988,11 @@ int sylt_batch_step_host(SyltBatch* b, float dt, int32_t n, const SyltBodyState*
         if (w1 <= w0) continue;
         cudaStream_t st = b->xs[c % SyltBatch::NS];
         const int o0 = b->h_body_off[(size_t)w0], cnt = b->h_body_off[(size_t)w1] - o0;
+        float* sg = stage + (size_t)o0 * fpb;
         if (in && cnt) {
-            SYLT_CUDA(cudaMemcpyAsync(b->stage.p + o0, in + o0, (size_t)cnt * sizeof(SyltBodyState), cudaMemcpyHostToDevice, st));
-            k_unpack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->stage.p + o0, b->pose.p + o0, b->vel.p + o0);
+            SYLT_CUDA(cudaMemcpyAsync(sg, in + (size_t)o0 * fpb, (size_t)cnt * fpb * sizeof(float), cudaMemcpyHostToDevice, st));
+            if (fpb == 9) k_unpack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, (const SyltBodyState*)sg, b->pose.p + o0, b->vel.p + o0);
+            else k_unpack_states6<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, sg, b->pose.p + o0, b->vel.p + o0);
             b->launches++;
         }
         if (n > 0) {
@@ -978,15 +1000,20 @@ int sylt_batch_step_host(SyltBatch* b, float dt, int32_t n, const SyltBodyState*
             if (e) return e;
         }
         if (out && cnt) {
-            k_pack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->pose.p + o0, b->vel.p + o0, b->stage.p + o0);
+            if (fpb == 9) k_pack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->pose.p + o0, b->vel.p + o0, (SyltBodyState*)sg);
+            else k_pack_states6<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->pose.p + o0, b->vel.p + o0, sg);
             b->launches++;
-            SYLT_CUDA(cudaMemcpyAsync(out + o0, b->stage.p + o0, (size_t)cnt * sizeof(SyltBodyState), cudaMemcpyDeviceToHost, st));
+            SYLT_CUDA(cudaMemcpyAsync(out + (size_t)o0 * fpb, sg, (size_t)cnt * fpb * sizeof(float), cudaMemcpyDeviceToHost, st));
         }
     }
     for (int k = 0; k < SyltBatch::NS; k++) SYLT_CUDA(cudaStreamSynchronize(b->xs[k]));
     b->inflight = false;
     return SYLT_OK;
 }
+int sylt_batch_step_host(SyltBatch* b, float dt, int32_t n, const SyltBodyState* in, SyltBodyState* out) {
+    return step_host_impl(b, dt, n, (const float*)in, (float*)out, 9);
+}
+int sylt_batch_step_host6(SyltBatch* b, float dt, int32_t n, const float* in6, float* out6) { return step_host_impl(b, dt, n, in6, out6, 6); }
 
 int sylt_batch_timer_start(SyltBatch* b) {
     if (!b) return SYLT_ERR_INVALID;

@@ -664,3 +664,24 @@ def test_opt_in_corrected_physics_matches_oracle(fixes):
         b.set_fixes(False, True)
         b.step_n(sc.dt, 300)
         _assert_states_equal(b.get_bodies(1, 1), stiff.get_bodies(), "batch true inverse")
+
+
+def test_batch_step_host6_equals_step_host():
+    from sylt2d_b200 import Batch
+    sc = scenes.pyramid(5, 10)
+    n = 1300
+    bodies, boff, joints, joff = scenes.tile_worlds(sc, n, seed=2, x_jitter=0.01)
+    a = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, ctx=sc.ctx)
+    b = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, ctx=sc.ctx)
+    a.step_n(sc.dt, 20)
+    b.step_n(sc.dt, 20)
+    st = a.get_bodies()
+    names = ("x", "y", "rotation", "vx", "vy", "angular_velocity")
+    s6 = np.ascontiguousarray(np.stack([st[f] for f in names], axis=1))
+    out9, out6 = np.zeros_like(st), np.zeros_like(s6)
+    for _ in range(3):
+        a.step_host(sc.dt, 1, st, out9)
+        b.step_host6(sc.dt, 1, s6, out6)
+        for k, f in enumerate(names):
+            assert np.array_equal(out9[f], out6[:, k]), f
+        st, s6 = out9.copy(), out6.copy()
