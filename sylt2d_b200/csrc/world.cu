@@ -48,7 +48,7 @@ void set_last_error(const std::string& s) {
 
 namespace {
 
-constexpr int NC = 32;          // max arbiter colours
+constexpr int NC = 64;          // max arbiter colours (one bit each in the per-body 64-bit `used` mask)
 constexpr int MAX_ROUNDS = 256; // colouring rounds per step (only new arbiters take part)
 constexpr int FLAG_POLY = 1, FLAG_LARGE = 2, FLAG_STATIC = 4;
 
@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int2* pairs, const unsigned long long* info, const unsigned long long* scan,
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
-                                               unsigned* used, int* uncolored, int fix_features) {
+                                               unsigned long long* used, int* uncolored, int fix_features) {
     int P = min(cn->n_pairs, cap_pairs);
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     __shared__ int s_hist[NC];
@@ -479,8 +479,8 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
             cur.cd[coff + k] = make_float4(ta.x, ta.y, pnb, tb.y);
         }
         if (color >= 0) {
-            if (!(bflags[b1] & FLAG_STATIC)) atomicOr(&used[b1], 1u << color);
-            if (!(bflags[b2] & FLAG_STATIC)) atomicOr(&used[b2], 1u << color);
+            if (!(bflags[b1] & FLAG_STATIC)) atomicOr(&used[b1], 1ull << color);
+            if (!(bflags[b2] & FLAG_STATIC)) atomicOr(&used[b2], 1ull << color);
             atomicAdd(&s_hist[color], 1);
         } else {
             uncolored[atomicAdd(&cn->n_uncolored, 1)] = a;
@@ -517,7 +517,7 @@ struct SolveArgs {
     const float2* rotc;
     const int* bflags;
     ArbSet cur;
-    unsigned* used;
+    unsigned long long* used;
     unsigned long long* claim;  // B * NC
     int *uncolored, *uncolored2, *prop, *order;
     ulonglong2* vrec;           // 2 per body: versioned velocities (see k_prepare)
@@ -670,10 +670,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                 int e = __ldcg(&cur_list[k]);
                 int2 b = a.cur.bodies[e];
                 bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
-                unsigned m = (d1 ? __ldcg(&a.used[b.x]) : 0u) | (d2 ? __ldcg(&a.used[b.y]) : 0u);
-                unsigned fr = ~m;
+                unsigned long long m = (d1 ? __ldcg(&a.used[b.x]) : 0ull) | (d2 ? __ldcg(&a.used[b.y]) : 0ull);
+                unsigned long long fr = ~m;
                 if (!fr) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[e] = -1; continue; }
-                int c = __ffs((int)fr) - 1;  // lowest free colour
+                int c = __ffsll((long long)fr) - 1;  // lowest free colour
                 a.prop[e] = c;
                 unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
                 if (d1) atomicMin(&a.claim[(size_t)b.x * NC + c], val);
@@ -690,8 +690,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                 bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NC + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NC + c]) == val);
                 if (win) {
                     a.cur.color[e] = c;
-                    if (d1) atomicOr(&a.used[b.x], 1u << c);
-                    if (d2) atomicOr(&a.used[b.y], 1u << c);
+                    if (d1) atomicOr(&a.used[b.x], 1ull << c);
+                    if (d2) atomicOr(&a.used[b.y], 1ull << c);
                     atomicAdd(&cn->color_count[c], 1);
                 } else {
                     next_list[atomicAdd(&cn->remaining[round], 1)] = e;
@@ -777,10 +777,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     }
     __syncthreads();
     auto order_pack = [&](int b1, int b2, int c) -> unsigned {  // D1 | r1 << 8 | D2 << 16 | r2 << 24
-        unsigned u1 = __ldcg(&a.used[b1]), u2 = __ldcg(&a.used[b2]);
-        unsigned lower = (1u << c) - 1u;
-        unsigned d1 = (unsigned)(__popc(u1) + a.jdeg[b1]), d2 = (unsigned)(__popc(u2) + a.jdeg[b2]);
-        return (d1 & 0xffu) | ((unsigned)__popc(u1 & lower) << 8) | ((d2 & 0xffu) << 16) | ((unsigned)__popc(u2 & lower) << 24);
+        unsigned long long u1 = __ldcg(&a.used[b1]), u2 = __ldcg(&a.used[b2]);
+        unsigned long long lower = (1ull << c) - 1ull;
+        unsigned d1 = (unsigned)(__popcll(u1) + a.jdeg[b1]), d2 = (unsigned)(__popcll(u2) + a.jdeg[b2]);
+        return (d1 & 0xffu) | ((unsigned)__popcll(u1 & lower) << 8) | ((d2 & 0xffu) << 16) | ((unsigned)__popcll(u2 & lower) << 24);
     };
     for (int c = 0; c < ncolors; c++) {
         const int cnt = s_lbase[c + 1] - s_lbase[c];
@@ -903,7 +903,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     };
     auto joint_expect = [&](int j, int2 b, unsigned pass, unsigned& e1, unsigned& e2) {
         int2 jr = a.jrank[j];
-        unsigned da1 = (unsigned)__popc(__ldcg(&a.used[b.x])), da2 = (unsigned)__popc(__ldcg(&a.used[b.y]));
+        unsigned da1 = (unsigned)__popcll(__ldcg(&a.used[b.x])), da2 = (unsigned)__popcll(__ldcg(&a.used[b.y]));
         e1 = pass * (da1 + (unsigned)a.jdeg[b.x]) + da1 + (unsigned)jr.x;
         e2 = pass * (da2 + (unsigned)a.jdeg[b.y]) + da2 + (unsigned)jr.y;
     };
@@ -1123,7 +1123,7 @@ struct SyltWorld {
     DBuf<int> spart32;
     DBuf<float4> tmp_a;
     DBuf<float2> tmp_b;
-    DBuf<unsigned> used;
+    DBuf<unsigned long long> used;
     DBuf<ulonglong2> vrec;
     int sleep_ns = 0, ctas_per_sm = 1, solve_threads = 512, slack_pct = 0;
     bool timing = false;
@@ -1410,7 +1410,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     SYLT_CUDA(cudaMemsetAsync(&cn->n_pairs, 0, sizeof(Counters) - offsetof(Counters, n_pairs), st));
     if (B == 0) return SYLT_OK;
     SYLT_CUDA(cudaMemsetAsync(w->cell_count.p, 0, (size_t)w->buckets * sizeof(int), st));
-    SYLT_CUDA(cudaMemsetAsync(w->used.p, 0, (size_t)B * sizeof(unsigned), st));
+    SYLT_CUDA(cudaMemsetAsync(w->used.p, 0, (size_t)B * sizeof(unsigned long long), st));
     const int nbB = (B + 255) / 256;
     k_prepare<<<nbB, 256, 0, st>>>(B, w->pose.p, w->vel.p, w->force.p, w->mp.p, w->geom.p, w->bflags.p, w->lverts.p, w->rotc.p, w->aabb.p,
                                    w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p);

@@ -224,6 +224,20 @@ def test_random_pile_steps_bit_exact(seed, polys):
     _run_lockstep(sc, 40, check_every=5)
 
 
+def test_body_with_more_than_32_neighbours_uses_wide_colour_mask():
+    """A dynamic plank carrying 45 boxes needs 46 colours (one per arbiter on the plank); bit-exact vs the oracle."""
+    b = scenes._Builder()
+    scenes._ground(b)
+    b.box(60.0, 1.0, 500.0, 0.3, (0.0, 0.55))
+    for i in range(45):
+        b.box(1.0, 1.0, 5.0, 0.3, (-27.5 + 1.25 * i, 1.6))
+    sc = b.scene("plank45", iterations=10)
+    w, o = _run_lockstep(sc, 60, check_every=10)
+    assert w.get_stats()["colors"] >= 46
+    ga, _ = w.get_arbiters()
+    assert ga["color"].max() >= 32
+
+
 def test_bodies_added_between_steps_and_clear():
     # launch_bomb (examples/samples/src/main.rs:56-64): add_body between steps; World::clear + reload
     from sylt2d_b200 import Body, Vec2
