@@ -11,7 +11,8 @@ import numpy as np
 from .scenes import BODY_DESC, JOINT_DESC
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsylt2d_b200.so")
+# SYLT2D_B200_LIB: load another build of the same library (profiling builds under tools/profiling)
+LIB_PATH = os.environ.get("SYLT2D_B200_LIB") or os.path.join(_HERE, "libsylt2d_b200.so")
 
 SYLT_OK, ERR_NO_INVERSE, ERR_ARBITER, ERR_BODY_ORDER, ERR_BODY_NOT_FOUND, ERR_CAPACITY, ERR_CUDA, ERR_INVALID, ERR_UNSUPPORTED = range(9)
 ERROR_NAMES = {1: "NoInverse (Sylt2DErrors::MathOperations)", 2: "Arbiter", 3: "BodyOrder", 4: "BodyNotFound", 5: "Capacity",

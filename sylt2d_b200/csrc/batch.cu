@@ -77,9 +77,11 @@ struct Smem {
     float2* pos; float* rot; float2* cs; float4* vel; float2* inv; float4* aabb; unsigned char* stat;
     unsigned* used;
     int* rowcnt;                       // Bmax + 1
-    int2* cxy; int* bstart; unsigned short* cellb; unsigned short* rank; unsigned short* rowtmp; unsigned short* large;
+    float4* caabb; int* bcell; int* bstart; unsigned short* cellb; unsigned short* rank; unsigned short* rowtmp; unsigned short* large;
     // slots
-    unsigned* key; float* sfric; float2* nrm; unsigned char* cnt; unsigned char* color; float* con;  // con: cap*2*9
+    unsigned* key; float* sfric; float2* nrm; unsigned char* cnt; unsigned char* color;
+    // per contact (2 per slot): conA = (r1, r2), conB = (mass_normal, mass_tangent, bias, pn), conC = pt
+    float4* conA; float4* conB; float* conC;
     unsigned short* order;
     // old cache
     unsigned* okey; unsigned char* ocolor;  // last step's slots: keys + colours here, (friction, pn0, pt0) stay in global memory
@@ -102,12 +104,13 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int B, int
     TAKE(stat, unsigned char, B); TAKE(used, unsigned, B); TAKE(large, unsigned short, B + 1);
     TAKE(key, unsigned, cap); TAKE(sfric, float, cap); TAKE(nrm, float2, cap); TAKE(cnt, unsigned char, cap); TAKE(color, unsigned char, cap);
     // the contact-constant region doubles as broad-phase scratch (dead before the narrow phase writes contacts)
-    const size_t scratch = align16(sizeof(float4) * (size_t)B) + align16(sizeof(int) * (size_t)(B + 1)) + align16(sizeof(int2) * (size_t)B) +
+    const size_t scratch = 2 * align16(sizeof(float4) * (size_t)B) + align16(sizeof(int) * (size_t)(B + 1)) + align16(sizeof(int) * (size_t)B) +
                            align16(sizeof(int) * (size_t)(nbk + 1)) + 2 * align16(sizeof(unsigned short) * (size_t)B) +
                            align16(sizeof(unsigned short) * (size_t)B * ROWT);
     const size_t con_floats = (size_t)18 * cap > scratch / 4 ? (size_t)18 * cap : scratch / 4;
     const size_t con_at = o;
-    TAKE(con, float, con_floats);
+    if (s) { s->conA = (float4*)(base + o); s->conB = s->conA + 2 * (size_t)cap; s->conC = (float*)(s->conB + 2 * (size_t)cap); }
+    o = align16(o + sizeof(float) * con_floats);
     TAKE(order, unsigned short, cap);
     TAKE(okey, unsigned, cap); TAKE(ocolor, unsigned char, cap);
     TAKE(jb, int2, J + 1); TAKE(jla, float4, J + 1); TAKE(jparam, float2, J + 1); TAKE(jp, float2, J + 1); TAKE(jr, float4, J + 1);
@@ -115,7 +118,7 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int B, int
     TAKE(misc, int, 40 + 3 * BNC + 8);
     const size_t total = o;
     o = con_at;
-    TAKE(aabb, float4, B); TAKE(rowcnt, int, B + 1); TAKE(cxy, int2, B); TAKE(bstart, int, nbk + 1); TAKE(cellb, unsigned short, B);
+    TAKE(aabb, float4, B); TAKE(caabb, float4, B); TAKE(rowcnt, int, B + 1); TAKE(bcell, int, B); TAKE(bstart, int, nbk + 1); TAKE(cellb, unsigned short, B);
     TAKE(rank, unsigned short, B); TAKE(rowtmp, unsigned short, B * ROWT);
     o = total;
 #undef TAKE
@@ -161,12 +164,24 @@ __device__ __forceinline__ void key_bodies(unsigned key, int& b1, int& b2) {
     b1 = min(x, y); b2 = max(x, y);
 }
 __device__ __forceinline__ int cellc(float x, float cell) { return (int)fminf(fmaxf(floorf(x / cell), -1.0e9f), 1.0e9f); }
-__device__ __forceinline__ int cellh(int cx, int cy, int mask) { return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u)) & mask; }
+// bucket of cell (cx, cy): rows of cells are contiguous runs of buckets (mod the table size), so a row of a search window is
+// ONE range of the cell-ordered body list.  Two cells of a window (<= 3 x 3) never share a bucket: k * CELL_ROW_STRIDE mod 2^m
+// stays outside [-3, 3] for k = 1, 2, 3 and every table size 2^m >= 64.
+constexpr unsigned CELL_ROW_STRIDE = 37u;
+__device__ __forceinline__ unsigned cellh(int cx, int cy) { return (unsigned)cx + (unsigned)cy * CELL_ROW_STRIDE; }
 
 __device__ __forceinline__ bool overlap4(float4 a, float4 b) { return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w); }
 
 __device__ __forceinline__ Vel ld_vel(const float4* v, int b) { float4 t = v[b]; Vel o; o.v = mk(t.x, t.y); o.w = t.z; return o; }
 __device__ __forceinline__ void st_vel(float4* v, int b, const Vel& x) { v[b] = make_float4(x.v.x, x.v.y, x.w, 0.0f); }
+
+#ifdef SYLT_BATCH_TIMING
+// profiling build only (tools/profiling): cycles thread 0 of every CTA spends in each phase of the step
+__device__ unsigned long long g_phase_cycles[16];
+#define PHASE(i) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
+#else
+#define PHASE(i) do { } while (0)
+#endif
 
 __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -203,7 +218,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
         s.okey[k] = a.c_key[g]; s.ocolor[k] = a.c_color[g];
     }
     if (tid == 0) {
-        *s_Pold = Pold0; *s_err = a.w_err[wld]; *s_P = 0;
+        *s_Pold = Pold0; *s_err = a.w_err[wld]; *s_P = 0; s.misc[138] = 0; s.misc[139] = 0;
         int nl = 0;
         for (int i = 0; i < B; i++)
             if (a.bflags[b0 + i] & 2) s.large[nl++] = (unsigned short)i;
@@ -218,10 +233,15 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     float maxpen = 0.0f;
     const bool exporting = wld >= a.export_first && wld < a.export_first + a.export_count;
 
+#ifdef SYLT_BATCH_TIMING
+    long long t_last = clock64();
+#endif
     for (int step = 0; step < a.n_steps; step++) {
         if (*s_err) break;  // a world that raised an error stays frozen (block-uniform: read after a barrier)
         maxpen = 0.0f;
+        PHASE(0);
         // ---- 1. bodies: rotation cache, AABB, force integration (world.rs:113-120; no external forces in a batch)
+        float ext_max = 0.0f, abs_max = 0.0f;
         for (int i = tid; i < B; i += T) {
             float r = s.rot[i];
             float c = sylt_cosf(r), sn = sylt_sinf(r);
@@ -230,7 +250,12 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             float hx = w.x * 0.5f, hy = w.y * 0.5f;
             float ex = fabsf(c) * hx + fabsf(sn) * hy, ey = fabsf(sn) * hx + fabsf(c) * hy;
             float mg = 1.0e-6f * (fabsf(p.x) + fabsf(p.y)) + 2.0e-5f * (ex + ey) + 1.0e-6f;
-            s.aabb[i] = make_float4(p.x - ex - mg, p.y - ey - mg, p.x + ex + mg, p.y + ey + mg);
+            const float4 ab = make_float4(p.x - ex - mg, p.y - ey - mg, p.x + ex + mg, p.y + ey + mg);
+            s.aabb[i] = ab;
+            if (!(s.stat[i] & 2)) {
+                ext_max = fmaxf(ext_max, fmaxf(ab.z - ab.x, ab.w - ab.y));
+                abs_max = fmaxf(abs_max, fmaxf(fabsf(p.x), fabsf(p.y)));
+            }
             float2 iv = s.inv[i];
             if (iv.x != 0.0f) {
                 float4 v = s.vel[i];
@@ -242,46 +267,71 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             s.used[i] = 0u;
         }
         for (int c = tid; c < 3 * BNC + 1; c += T) ccount[c] = 0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            ext_max = fmaxf(ext_max, __shfl_xor_sync(0xffffffffu, ext_max, o));
+            abs_max = fmaxf(abs_max, __shfl_xor_sync(0xffffffffu, abs_max, o));
+        }
+        if (lane == 0) {  // non-negative floats order like their bit patterns
+            atomicMax(&s.misc[138], __float_as_int(fminf(ext_max, 3.0e38f)));
+            atomicMax(&s.misc[139], __float_as_int(fminf(abs_max, 3.0e38f)));
+        }
         __syncthreads();
+        PHASE(1);
         // ---- 2. candidate rows through a hashed uniform grid in shared memory (large bodies bypass it):
         //         bucket counts -> scan -> fill; thread per body: count (remembering partners) -> scan -> emit sorted.
         //         A pair is owned by its lower index, a small-large pair by the small body (slot order = (owner, partner)).
+        //         The cell is re-derived every step from the largest AABB the small bodies have NOW (a resting box spans
+        //         its width, not its bounding circle), with slack for the rounding of centres at large coordinates.
         const int nbk = a.nbk, nl = s.misc[34];
+        const unsigned bmask = (unsigned)nbk - 1u;
+        const float cell = fminf(a.cell, 1.05f * __int_as_float(s.misc[138]) + 0.01f + 1.0e-6f * __int_as_float(s.misc[139]));
         for (int k = tid; k <= nbk; k += T) s.bstart[k] = 0;
         __syncthreads();
         for (int i = tid; i < B; i += T) {
             if (s.stat[i] & 2) continue;
             float4 ab = s.aabb[i];
-            int cx = cellc(0.5f * (ab.x + ab.z), a.cell), cy = cellc(0.5f * (ab.y + ab.w), a.cell);
-            s.cxy[i] = make_int2(cx, cy);
-            s.rank[i] = (unsigned short)atomicAdd(&s.bstart[cellh(cx, cy, nbk - 1)], 1);
+            int h = (int)(cellh(cellc(0.5f * (ab.x + ab.z), cell), cellc(0.5f * (ab.y + ab.w), cell)) & bmask);
+            s.bcell[i] = h;
+            s.rank[i] = (unsigned short)atomicAdd(&s.bstart[h], 1);
         }
         __syncthreads();
+        PHASE(9);
         block_scan_inplace(s.bstart, nbk + 1, scan_sh);
         for (int i = tid; i < B; i += T) {
             if (s.stat[i] & 2) continue;
-            int2 c = s.cxy[i];
-            s.cellb[s.bstart[cellh(c.x, c.y, nbk - 1)] + s.rank[i]] = (unsigned short)i;
+            int k = s.bstart[s.bcell[i]] + s.rank[i];
+            s.cellb[k] = (unsigned short)(i | ((s.stat[i] & 1) << 15));  // body index (<= 4095) + static flag
+            s.caabb[k] = s.aabb[i];
         }
         __syncthreads();
+        PHASE(10);
         auto row_search = [&](int i, auto&& found) {
             const float4 my = s.aabb[i];
             const int fl = s.stat[i];
             if (!(fl & 2)) {
-                int x0 = cellc(my.x - 0.5f * a.cell, a.cell), x1 = cellc(my.z + 0.5f * a.cell, a.cell);
-                int y0 = cellc(my.y - 0.5f * a.cell, a.cell), y1 = cellc(my.w + 0.5f * a.cell, a.cell);
-                for (int cy = y0; cy <= y1; cy++)
-                    for (int cx = x0; cx <= x1; cx++) {
-                        int h = cellh(cx, cy, nbk - 1);
-                        for (int k = s.bstart[h]; k < s.bstart[h + 1]; k++) {
-                            int j = s.cellb[k];
-                            if (j <= i) continue;
-                            int2 cj = s.cxy[j];
-                            if (cj.x != cx || cj.y != cy) continue;
-                            if ((fl & 1) && (s.stat[j] & 1)) continue;
-                            if (overlap4(my, s.aabb[j])) found(j);
-                        }
+                const int x0 = cellc(my.x - 0.5f * cell, cell), x1 = cellc(my.z + 0.5f * cell, cell);
+                const int y0 = cellc(my.y - 0.5f * cell, cell), y1 = cellc(my.w + 0.5f * cell, cell);
+                const unsigned skip = (fl & 1) ? 0x8000u : 0u;  // static-static pairs are never candidates
+                auto scan = [&](int k0, int k1) {
+                    for (int k = k0; k < k1; k++) {
+                        const unsigned e = s.cellb[k];
+                        const int j = (int)(e & 0x7fffu);
+                        if (j <= i || (e & skip)) continue;
+                        if (overlap4(my, s.caabb[k])) found(j);
                     }
+                };
+                if (x1 - x0 <= 3 && y1 - y0 <= 3) {  // always, unless coordinates are so large that the AABB margin outgrows the cell
+                    const unsigned wx = (unsigned)(x1 - x0);
+                    for (int cy = y0; cy <= y1; cy++) {
+                        const unsigned hb = cellh(x0, cy);
+                        const int h0 = (int)(hb & bmask), h1 = (int)((hb + wx) & bmask);
+                        if (h1 >= h0) scan(s.bstart[h0], s.bstart[h1 + 1]);
+                        else { scan(s.bstart[h0], s.bstart[nbk]); scan(s.bstart[0], s.bstart[h1 + 1]); }
+                    }
+                } else {
+                    scan(0, s.bstart[nbk]);
+                }
                 for (int k = 0; k < nl; k++) {
                     int j = s.large[k];
                     if ((fl & 1) && (s.stat[j] & 1)) continue;
@@ -303,7 +353,9 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             s.rowcnt[i] = n;
         }
         __syncthreads();
+        PHASE(11);
         P = block_scan_inplace(s.rowcnt, B, scan_sh);
+        PHASE(12);
         if (P > cap) {  // block-uniform
             if (tid == 0) *s_err = SYLT_ERR_CAPACITY;
             __syncthreads();
@@ -337,6 +389,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             }
         }
         __syncthreads();
+        PHASE(2);
         // ---- 3. narrow phase + match with last step's slots, one thread per candidate slot
         const int Pold = *s_Pold;
         for (int p = tid; p < P; p += T) {
@@ -362,14 +415,20 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
                 }
                 s.sfric[p] = fr;
                 s.nrm[p] = make_float2(out[0].nx, out[0].ny);
+                // the velocity-independent half of Arbiter::pre_step (arbiter.rs:192-215) needs no ordering: do it here
+                const float2 i1 = s.inv[b1], i2 = s.inv[b2];
                 for (int q = 0; q < n; q++) {
-                    float* cc = s.con + (size_t)(2 * p + q) * 9;
-                    cc[0] = out[q].px; cc[1] = out[q].py; cc[6] = out[q].sep; cc[7] = pn; cc[8] = pt;
+                    ContactConst k0;
+                    contact_constants(mk(out[q].px, out[q].py), mk(out[0].nx, out[0].ny), out[q].sep, mk(p1.x, p1.y), mk(p2.x, p2.y),
+                                      i1.x, i1.y, i2.x, i2.y, a.inv_dt, kbias, k0);
+                    maxpen = fmaxf(maxpen, -out[q].sep);
+                    s.conA[2 * p + q] = make_float4(k0.r1.x, k0.r1.y, k0.r2.x, k0.r2.y);
+                    s.conB[2 * p + q] = make_float4(k0.mass_n, k0.mass_t, k0.bias, pn);
+                    s.conC[2 * p + q] = pt;
                 }
                 if (color != NO_COLOR) {
                     if (!(s.stat[b1] & 1)) atomicOr(&s.used[b1], 1u << color);
                     if (!(s.stat[b2] & 1)) atomicOr(&s.used[b2], 1u << color);
-                    atomicAdd(&ccount[color], 1);
                 }
             }
             s.color[p] = color;
@@ -384,70 +443,101 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             }
         }
         __syncthreads();
-        // ---- 4. colour the new arbiters: lowest free colour, in key order (warp 0 finds them, lane 0 assigns)
+        PHASE(3);
+        // ---- 4. colour the new arbiters: lowest free colour, in key order.  Every warp flags its slots into a bit mask
+        //         (parked in the not yet written `order` array); lane 0 of warp 0 walks the set bits — a settled world has few.
+        unsigned* newmask = reinterpret_cast<unsigned*>(s.order);
+        const int nwords = (P + 31) >> 5;
+        for (int pb = warp << 5; pb < P; pb += T) {
+            const int p = pb + lane;
+            const bool need = p < P && s.cnt[p] > 0 && s.color[p] == NO_COLOR;
+            const unsigned m = __ballot_sync(0xffffffffu, need);
+            if (lane == 0) newmask[pb >> 5] = m;
+        }
+        __syncthreads();
         if (warp == 0) {
-            for (int pb = 0; pb < P; pb += 32) {
-                int p = pb + lane;
-                bool need = p < P && s.cnt[p] > 0 && s.color[p] == NO_COLOR;
-                unsigned m = __ballot_sync(0xffffffffu, need);
-                if (lane == 0) {
-                    while (m) {
-                        int q = pb + __ffs(m) - 1;
-                        m &= m - 1;
-                        unsigned key = s.key[q];
-                        int b1, b2;
-            key_bodies(key, b1, b2);
-                        unsigned um = ((s.stat[b1] & 1) ? 0u : s.used[b1]) | ((s.stat[b2] & 1) ? 0u : s.used[b2]);
-                        unsigned fr = ~um;
-                        if (!fr) { *s_err = SYLT_ERR_CAPACITY; continue; }
-                        int c = __ffs(fr) - 1;
-                        s.color[q] = (unsigned char)c;
-                        if (!(s.stat[b1] & 1)) s.used[b1] |= 1u << c;
-                        if (!(s.stat[b2] & 1)) s.used[b2] |= 1u << c;
-                        ccount[c]++;
+            for (int wb = 0; wb < nwords; wb += 32) {
+                const unsigned mine = wb + lane < nwords ? newmask[wb + lane] : 0u;
+                unsigned nz = __ballot_sync(0xffffffffu, mine != 0u);
+                while (nz) {  // warp-uniform
+                    const int wi = __ffs(nz) - 1;
+                    nz &= nz - 1;
+                    unsigned m = __shfl_sync(0xffffffffu, mine, wi);
+                    if (lane == 0) {
+                        while (m) {
+                            const int q = ((wb + wi) << 5) + __ffs(m) - 1;
+                            m &= m - 1;
+                            int b1, b2;
+                            key_bodies(s.key[q], b1, b2);
+                            const unsigned um = ((s.stat[b1] & 1) ? 0u : s.used[b1]) | ((s.stat[b2] & 1) ? 0u : s.used[b2]);
+                            const unsigned fr = ~um;
+                            if (!fr) { *s_err = SYLT_ERR_CAPACITY; continue; }
+                            const int c = __ffs(fr) - 1;
+                            s.color[q] = (unsigned char)c;
+                            if (!(s.stat[b1] & 1)) s.used[b1] |= 1u << c;
+                            if (!(s.stat[b2] & 1)) s.used[b2] |= 1u << c;
+                        }
                     }
+                    __syncwarp();
                 }
-                __syncwarp();
-            }
-            if (lane == 0) {
-                int run = 0, nc = 0;
-                for (int c = 0; c < BNC; c++) { cstart[c] = run; if (ccount[c] > 0) nc = c + 1; run += ccount[c]; }
-                cstart[BNC] = run;
-                s.misc[35] = nc;
             }
         }
         __syncthreads();
         if (*s_err) break;
-        ncolors = s.misc[35];
-        for (int p = tid; p < P; p += T)
-            if (s.cnt[p] > 0) s.order[cstart[s.color[p]] + atomicAdd(&cfill[s.color[p]], 1)] = (unsigned short)p;
+        //         colour-major order: per-colour counts -> starts -> fill.  Lanes of a warp that share a colour are grouped with
+        //         match.any, so one shared-memory atomic per (warp, colour) replaces one per arbiter on 5-6 hot addresses.
+        for (int pb = warp << 5; pb < P; pb += T) {
+            const int p = pb + lane;
+            const unsigned col = (p < P && s.cnt[p] > 0) ? (unsigned)s.color[p] : (unsigned)NO_COLOR;
+            const unsigned grp = __match_any_sync(0xffffffffu, col);
+            if (col != NO_COLOR && (__ffs(grp) - 1) == lane) atomicAdd(&ccount[col], __popc(grp));
+        }
         __syncthreads();
-        // ---- 5. Arbiter::pre_step colour by colour
-        for (int c = 0; c < ncolors; c++) {
-            for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
-                int p = s.order[k];
-                unsigned key = s.key[p];
-                int b1, b2;
-            key_bodies(key, b1, b2);
-                float2 i1 = s.inv[b1], i2 = s.inv[b2], p1 = s.pos[b1], p2 = s.pos[b2], nn = s.nrm[p];
-                Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
-                int n = s.cnt[p];
-                for (int q = 0; q < n; q++) {
-                    float* cc = s.con + (size_t)(2 * p + q) * 9;
-                    ContactConst k0;
-                    contact_prestep(mk(cc[0], cc[1]), mk(nn.x, nn.y), cc[6], mk(p1.x, p1.y), mk(p2.x, p2.y), i1.x, i1.y, i2.x, i2.y,
-                                    a.inv_dt, kbias, acc, cc[7], cc[8], v1, v2, k0);
-                    maxpen = fmaxf(maxpen, -cc[6]);
-                    cc[0] = k0.r1.x; cc[1] = k0.r1.y; cc[2] = k0.r2.x; cc[3] = k0.r2.y; cc[4] = k0.mass_n; cc[5] = k0.mass_t; cc[6] = k0.bias;
-                }
-                if (acc) {
+        if (warp == 0) {
+            const int cntc = ccount[lane];  // BNC == 32 == warp size
+            const int incl = warp_incl_scan_i(cntc);
+            cstart[lane] = incl - cntc;
+            if (lane == 31) cstart[BNC] = incl;
+            const unsigned present = __ballot_sync(0xffffffffu, cntc > 0);
+            if (lane == 0) s.misc[35] = 32 - __clz(present);
+        }
+        __syncthreads();
+        ncolors = s.misc[35];
+        for (int pb = warp << 5; pb < P; pb += T) {
+            const int p = pb + lane;
+            const unsigned col = (p < P && s.cnt[p] > 0) ? (unsigned)s.color[p] : (unsigned)NO_COLOR;
+            const unsigned grp = __match_any_sync(0xffffffffu, col);
+            const int leader = __ffs(grp) - 1;
+            int base = 0;
+            if (col != NO_COLOR && leader == lane) base = atomicAdd(&cfill[col], __popc(grp));
+            base = __shfl_sync(0xffffffffu, base, leader);
+            if (col != NO_COLOR) s.order[cstart[col] + base + __popc(grp & ((1u << lane) - 1u))] = (unsigned short)p;
+        }
+        __syncthreads();
+        PHASE(4);
+        // ---- 5. the ordered half of Arbiter::pre_step (arbiter.rs:216-223): apply last step's impulses colour by colour
+        if (acc) {
+            for (int c = 0; c < ncolors; c++) {
+                for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
+                    const int p = s.order[k];
+                    int b1, b2;
+                    key_bodies(s.key[p], b1, b2);
+                    const float2 i1 = s.inv[b1], i2 = s.inv[b2], nn = s.nrm[p];
+                    Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
+                    const int n = s.cnt[p];
+                    for (int q = 0; q < n; q++) {
+                        const float4 ca = s.conA[2 * p + q];
+                        ContactConst k0;
+                        k0.n = mk(nn.x, nn.y); k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
+                        contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, s.conB[2 * p + q].w, s.conC[2 * p + q], v1, v2);
+                    }
                     if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b1, v1);
                     if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b2, v2);
                 }
+                __syncthreads();
             }
-            if (acc) __syncthreads();
         }
-        __syncthreads();
+        PHASE(5);
         // ---- 6. Joint::pre_step by joint colour
         for (int c = 0; c < njc; c++) {
             for (int k = jcs[c] + tid; k < jcs[c + 1]; k += T) {
@@ -481,6 +571,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             __syncthreads();
         }
         if (*s_err) break;
+        PHASE(6);
         // ---- 7. iterations (world.rs:132-140)
         for (int it = 0; it < a.iterations; it++) {
             for (int c = 0; c < ncolors; c++) {
@@ -494,13 +585,13 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
                     Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
                     int n = s.cnt[p];
                     for (int q = 0; q < n; q++) {
-                        float* cc = s.con + (size_t)(2 * p + q) * 9;
+                        const float4 ca = s.conA[2 * p + q], cb = s.conB[2 * p + q];
                         ContactConst k0;
-                        k0.n = mk(nn.x, nn.y); k0.r1 = mk(cc[0], cc[1]); k0.r2 = mk(cc[2], cc[3]);
-                        k0.mass_n = cc[4]; k0.mass_t = cc[5]; k0.bias = cc[6];
-                        float pn = cc[7], pt = cc[8];
+                        k0.n = mk(nn.x, nn.y); k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
+                        k0.mass_n = cb.x; k0.mass_t = cb.y; k0.bias = cb.z;
+                        float pn = cb.w, pt = s.conC[2 * p + q];
                         contact_apply(k0, fr, i1.x, i1.y, i2.x, i2.y, acc, pn, pt, v1, v2);
-                        if (acc) { cc[7] = pn; cc[8] = pt; }
+                        if (acc) { s.conB[2 * p + q].w = pn; s.conC[2 * p + q] = pt; }
                     }
                     if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b1, v1);
                     if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b2, v2);
@@ -528,6 +619,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
                 __syncthreads();
             }
         }
+        PHASE(7);
         // ---- 8. integrate positions (world.rs:143-150, all bodies)
         for (int i = tid; i < B; i += T) {
             float4 v = s.vel[i];
@@ -543,11 +635,12 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             s.ocolor[p] = col;
             if (col != NO_COLOR) {
                 const size_t g = (size_t)wld * cap + p;
-                a.c_fric[g] = s.sfric[p]; a.c_pn[g] = s.con[(size_t)(2 * p) * 9 + 7]; a.c_pt[g] = s.con[(size_t)(2 * p) * 9 + 8];
+                a.c_fric[g] = s.sfric[p]; a.c_pn[g] = s.conB[2 * p].w; a.c_pt[g] = s.conC[2 * p];
             }
         }
-        if (tid == 0) *s_Pold = P;
+        if (tid == 0) { *s_Pold = P; s.misc[138] = 0; s.misc[139] = 0; }
         __syncthreads();
+        PHASE(8);
     }
 
     // ---- store the world
@@ -591,7 +684,11 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             SlotExport* e = &a.exp_slots[(size_t)xw * cap + p];
             e->friction = s.sfric[p]; e->color = s.color[p];
             for (int q = 0; q < 2; q++)
-                for (int k = 0; k < 9; k++) e->sol[q][k] = s.con[(size_t)(2 * p + q) * 9 + k];
+            {
+                const float4 ca = s.conA[2 * p + q], cb = s.conB[2 * p + q];
+                float* o = e->sol[q];
+                o[0] = ca.x; o[1] = ca.y; o[2] = ca.z; o[3] = ca.w; o[4] = cb.x; o[5] = cb.y; o[6] = cb.z; o[7] = cb.w; o[8] = s.conC[2 * p + q];
+            }
         }
         if (tid == 0) a.exp_count[xw] = valid ? P : 0;
     }
@@ -1161,3 +1258,12 @@ int sylt_batch_stats(SyltBatch* b, SyltBatchStats* out) {
 }
 
 }  // extern "C"
+
+#ifdef SYLT_BATCH_TIMING
+extern "C" int sylt_batch_debug_phases(unsigned long long* out16, int reset) {
+    cudaDeviceSynchronize();
+    if (out16) cudaMemcpyFromSymbol(out16, g_phase_cycles, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {0}; cudaMemcpyToSymbol(g_phase_cycles, z, sizeof(z)); }
+    return 0;
+}
+#endif
