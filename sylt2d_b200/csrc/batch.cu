@@ -63,7 +63,9 @@ struct BatchArgs {
     // persistent per-world slot cache (cap entries per world)
     int* c_count;
     unsigned* c_key;
-    float *c_fric, *c_pn, *c_pt;
+    float4* c_cache[2];              // (friction, pn, pt, -) of contact 0 per slot, double buffered: a step reads [parity], writes [parity ^ 1]
+    int* c_par;                      // per world: which buffer holds the last finished step
+    float4 *c_stg0, *c_stg1;         // narrow-phase staging per slot: (px0,py0,sep0,nx), (px1,py1,sep1,ny)
     unsigned char* c_color;          // NO_COLOR = inactive slot (candidate without contacts)
     // per-world summary
     int *w_err, *w_ncon, *w_narb, *w_ncolors, *w_errjoint;
@@ -71,6 +73,9 @@ struct BatchArgs {
     float4* w_badk;
     SlotExport* exp_slots;           // export_count * cap
     int* exp_count;                  // export_count
+    // shared-memory layout: byte offset of every Smem array, computed once on the host (carve) and read from the constant
+    // bank, so that re-deriving a pointer inside a hot loop is one load + one add instead of the whole chain of align-ups
+    unsigned long long smem_off[48];
 };
 
 struct Smem {
@@ -79,10 +84,11 @@ struct Smem {
     int* rowcnt;                       // Bmax + 1
     float4* caabb; int* bcell; int* bstart; unsigned short* cellb; unsigned short* rank; unsigned short* rowtmp; unsigned short* large;
     // slots
-    unsigned* key; float* sfric; float2* nrm; unsigned char* cnt; unsigned char* color;
-    // per contact (2 per slot): conA = (r1, r2), conB = (mass_normal, mass_tangent, bias, pn), conC = pt
-    float4* conA; float4* conB; float* conC;
-    unsigned short* order;
+    unsigned* key; unsigned char* cnt; unsigned char* color;
+    unsigned short* order;             // colour-major position k -> slot
+    // solver records, indexed by colour-major position k so that the lanes of a warp read consecutive addresses:
+    //   kb = body1 | body2 << 12 | (contacts - 1) << 24;  per contact q: cA[q] = (r1, r2), cB[q] = (mass_normal, mass_tangent, bias, pn)
+    unsigned* kb; float2* nrmk; float* frk; float4* cA[2]; float4* cB[2]; float2* ptk;
     // old cache
     unsigned* okey; unsigned char* ocolor;  // last step's slots: keys + colours here, (friction, pn0, pt0) stay in global memory
     // joints
@@ -102,17 +108,21 @@ __host__ __device__ inline size_t carve(Smem* s, unsigned char* base, int B, int
     } while (0)
     TAKE(pos, float2, B); TAKE(rot, float, B); TAKE(cs, float2, B); TAKE(vel, float4, B); TAKE(inv, float2, B);
     TAKE(stat, unsigned char, B); TAKE(used, unsigned, B); TAKE(large, unsigned short, B + 1);
-    TAKE(key, unsigned, cap); TAKE(sfric, float, cap); TAKE(nrm, float2, cap); TAKE(cnt, unsigned char, cap); TAKE(color, unsigned char, cap);
+    TAKE(key, unsigned, cap); TAKE(kb, unsigned, cap); TAKE(nrmk, float2, cap); TAKE(cnt, unsigned char, cap); TAKE(color, unsigned char, cap);
     // the contact-constant region doubles as broad-phase scratch (dead before the narrow phase writes contacts)
     const size_t scratch = 2 * align16(sizeof(float4) * (size_t)B) + align16(sizeof(int) * (size_t)(B + 1)) + align16(sizeof(int) * (size_t)B) +
                            align16(sizeof(int) * (size_t)(nbk + 1)) + 2 * align16(sizeof(unsigned short) * (size_t)B) +
                            align16(sizeof(unsigned short) * (size_t)B * ROWT);
     const size_t con_floats = (size_t)18 * cap > scratch / 4 ? (size_t)18 * cap : scratch / 4;
     const size_t con_at = o;
-    if (s) { s->conA = (float4*)(base + o); s->conB = s->conA + 2 * (size_t)cap; s->conC = (float*)(s->conB + 2 * (size_t)cap); }
+    if (s) {
+        float4* f = (float4*)(base + o);
+        s->cA[0] = f; s->cA[1] = f + cap; s->cB[0] = f + 2 * (size_t)cap; s->cB[1] = f + 3 * (size_t)cap; s->ptk = (float2*)(f + 4 * (size_t)cap);
+    }
     o = align16(o + sizeof(float) * con_floats);
     TAKE(order, unsigned short, cap);
     TAKE(okey, unsigned, cap); TAKE(ocolor, unsigned char, cap);
+    if (s) s->frk = (float*)s->okey;  // last step's keys are dead between the narrow phase and the end of the step
     TAKE(jb, int2, J + 1); TAKE(jla, float4, J + 1); TAKE(jparam, float2, J + 1); TAKE(jp, float2, J + 1); TAKE(jr, float4, J + 1);
     TAKE(jm, float4, J + 1); TAKE(jbias, float2, J + 1); TAKE(jorder, unsigned short, J + 1);
     TAKE(misc, int, 40 + 3 * BNC + 8);
@@ -175,16 +185,77 @@ __device__ __forceinline__ bool overlap4(float4 a, float4 b) { return !(a.x > b.
 __device__ __forceinline__ Vel ld_vel(const float4* v, int b) { float4 t = v[b]; Vel o; o.v = mk(t.x, t.y); o.w = t.z; return o; }
 __device__ __forceinline__ void st_vel(float4* v, int b, const Vel& x) { v[b] = make_float4(x.v.x, x.v.y, x.w, 0.0f); }
 
+// The iterated part of the solver (world.rs:132-140, Arbiter::apply_impulse) for `iters` sweeps over the arbiter colours.
+// Deliberately NOT inlined: the step kernel around it keeps ~60 values alive, so inlined the compiler re-derives all ten
+// shared-memory base addresses on every colour hop; as a function of its own it keeps them in registers for the whole sweep.
+// (Byte offsets into the dynamic shared memory, not pointers: across a call the compiler would otherwise fall back to generic
+// 64-bit addressing.)
+struct HotOffsets {
+    unsigned kb, inv, nrmk, frk, ptk, vel, cA0, cA1, cB0, cB1, cstart;
+};
+struct HotArrays {
+    const unsigned* kb; const float2* inv; const float2* nrmk; const float* frk; float2* ptk; float4* vel;
+    const float4 *cA0, *cA1; float4 *cB0, *cB1;
+    const int* cstart;
+};
+extern __shared__ __align__(16) unsigned char smem_raw[];
+template <bool ACC>
+__device__ __noinline__ void contact_sweeps(HotOffsets o, int ncolors, int iters) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    HotArrays h;
+    h.kb = (const unsigned*)(smem_raw + o.kb); h.inv = (const float2*)(smem_raw + o.inv); h.nrmk = (const float2*)(smem_raw + o.nrmk);
+    h.frk = (const float*)(smem_raw + o.frk); h.ptk = (float2*)(smem_raw + o.ptk); h.vel = (float4*)(smem_raw + o.vel);
+    h.cA0 = (const float4*)(smem_raw + o.cA0); h.cA1 = (const float4*)(smem_raw + o.cA1);
+    h.cB0 = (float4*)(smem_raw + o.cB0); h.cB1 = (float4*)(smem_raw + o.cB1); h.cstart = (const int*)(smem_raw + o.cstart);
+    for (int it = 0; it < iters; it++) {
+        for (int c = 0; c < ncolors; c++) {
+            for (int k = h.cstart[c] + tid; k < h.cstart[c + 1]; k += T) {
+                const unsigned kbv = h.kb[k];
+                const int b1 = kbv & 0xfffu, b2 = (kbv >> 12) & 0xfffu;
+                const float4 ca0 = h.cA0[k], cb0 = h.cB0[k], ca1 = h.cA1[k], cb1 = h.cB1[k];  // contact 1: unused garbage when absent
+                const float2 i1 = h.inv[b1], i2 = h.inv[b2], nn = h.nrmk[k];
+                const float fr = h.frk[k];
+                float2 pt = h.ptk[k];
+                Vel v1 = ld_vel(h.vel, b1), v2 = ld_vel(h.vel, b2);
+                ContactConst k0;
+                k0.n = mk(nn.x, nn.y); k0.r1 = mk(ca0.x, ca0.y); k0.r2 = mk(ca0.z, ca0.w);
+                k0.mass_n = cb0.x; k0.mass_t = cb0.y; k0.bias = cb0.z;
+                float pn = cb0.w;
+                contact_apply(k0, fr, i1.x, i1.y, i2.x, i2.y, ACC, pn, pt.x, v1, v2);
+                if (ACC) h.cB0[k].w = pn;
+                if (kbv >> 24) {
+                    k0.r1 = mk(ca1.x, ca1.y); k0.r2 = mk(ca1.z, ca1.w);
+                    k0.mass_n = cb1.x; k0.mass_t = cb1.y; k0.bias = cb1.z;
+                    pn = cb1.w;
+                    contact_apply(k0, fr, i1.x, i1.y, i2.x, i2.y, ACC, pn, pt.y, v1, v2);
+                    if (ACC) h.cB1[k].w = pn;
+                }
+                if (ACC) h.ptk[k] = pt;
+                if (i1.x != 0.0f || i1.y != 0.0f) st_vel(h.vel, b1, v1);
+                if (i2.x != 0.0f || i2.y != 0.0f) st_vel(h.vel, b2, v2);
+            }
+            __syncthreads();
+        }
+    }
+}
+
 #ifdef SYLT_BATCH_TIMING
 // profiling build only (tools/profiling): cycles thread 0 of every CTA spends in each phase of the step
 __device__ unsigned long long g_phase_cycles[16];
 #define PHASE(i) do { if (tid == 0) { long long t_ = clock64(); atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_ - t_last)); t_last = t_; } } while (0)
+// inside a hop (-DSYLT_BATCH_TIMING=2; the probes themselves cost ~40 cycles each): the clock is read after `dep` is available
+#if SYLT_BATCH_TIMING < 2
+#define HOP(i, dep) do { } while (0)
+#else
+#define HOP(i, dep) do { if (tid == 0) { long long t_; asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "f"(dep) : "memory"); \
+                                         atomicAdd(&g_phase_cycles[i], (unsigned long long)(t_ - t_hop)); t_hop = t_; } } while (0)
+#endif
 #else
 #define PHASE(i) do { } while (0)
+#define HOP(i, dep) do { } while (0)
 #endif
 
 __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
     const int wld = blockIdx.x + a.world_begin;
     if (wld >= a.n_worlds) return;
     const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
@@ -192,7 +263,13 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     const int j0 = a.joint_off[wld], J = a.joint_off[wld + 1] - j0;
     const int cap = a.cap;
     Smem s;
-    carve(&s, smem_raw, a.Bmax, a.Jmax, cap, a.nbk);
+    static_assert(sizeof(Smem) % sizeof(void*) == 0 && sizeof(Smem) / sizeof(void*) <= 48, "Smem must be an array of pointers");
+    {
+        unsigned char* ptrs[sizeof(Smem) / sizeof(void*)];
+#pragma unroll
+        for (int i = 0; i < (int)(sizeof(Smem) / sizeof(void*)); i++) ptrs[i] = smem_raw + a.smem_off[i];
+        memcpy(&s, ptrs, sizeof(Smem));  // (not a cast: the fields have different pointer types)
+    }
     int* scan_sh = s.misc;           // 34
     int* s_P = s.misc + 36;          // current candidate count
     int* s_Pold = s.misc + 37;
@@ -212,6 +289,8 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
         s.jorder[j] = (unsigned short)a.jorder[j0 + j];
         s.jr[j] = make_float4(0, 0, 0, 0); s.jm[j] = make_float4(0, 0, 0, 0); s.jbias[j] = make_float2(0, 0);
     }
+    int par = a.c_par[wld];
+    const size_t gslot = (size_t)wld * cap;
     const int Pold0 = min(a.c_count[wld], cap);
     for (int k = tid; k < Pold0; k += T) {
         size_t g = (size_t)wld * cap + k;
@@ -234,7 +313,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     const bool exporting = wld >= a.export_first && wld < a.export_first + a.export_count;
 
 #ifdef SYLT_BATCH_TIMING
-    long long t_last = clock64();
+    long long t_last = clock64(), t_hop = 0;
 #endif
     for (int step = 0; step < a.n_steps; step++) {
         if (*s_err) break;  // a world that raised an error stays frozen (block-uniform: read after a barrier)
@@ -406,26 +485,18 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
                 while (lo < hi) { int mid = (lo + hi) >> 1; if (s.okey[mid] < key) lo = mid + 1; else hi = mid; }
                 float fr, pn = 0.0f, pt = 0.0f;
                 if (lo < Pold && s.okey[lo] == key && s.ocolor[lo] != NO_COLOR) {  // Arbiter::update (arbiter.rs:137-181)
-                    const size_t g = (size_t)wld * cap + lo;  // written by this CTA at the end of the previous step
-                    fr = a.c_fric[g];              // quirk Q-17
+                    const float4 oc = a.c_cache[par][gslot + lo];  // written by this CTA at the end of the previous step
+                    fr = oc.x;                     // quirk Q-17
                     color = s.ocolor[lo];
-                    if (warm) { pn = a.c_pn[g]; pt = a.c_pt[g]; }  // quirk Q-2: all contacts inherit old contact 0
+                    if (warm) { pn = oc.y; pt = oc.z; }  // quirk Q-2: all contacts inherit old contact 0
                 } else {
                     fr = sqrtf(a.mp[b0 + b1].z * a.mp[b0 + b2].z);  // arbiter.rs:128
                 }
-                s.sfric[p] = fr;
-                s.nrm[p] = make_float2(out[0].nx, out[0].ny);
-                // the velocity-independent half of Arbiter::pre_step (arbiter.rs:192-215) needs no ordering: do it here
-                const float2 i1 = s.inv[b1], i2 = s.inv[b2];
-                for (int q = 0; q < n; q++) {
-                    ContactConst k0;
-                    contact_constants(mk(out[q].px, out[q].py), mk(out[0].nx, out[0].ny), out[q].sep, mk(p1.x, p1.y), mk(p2.x, p2.y),
-                                      i1.x, i1.y, i2.x, i2.y, a.inv_dt, kbias, k0);
-                    maxpen = fmaxf(maxpen, -out[q].sep);
-                    s.conA[2 * p + q] = make_float4(k0.r1.x, k0.r1.y, k0.r2.x, k0.r2.y);
-                    s.conB[2 * p + q] = make_float4(k0.mass_n, k0.mass_t, k0.bias, pn);
-                    s.conC[2 * p + q] = pt;
-                }
+                // staged through (L2-resident) global memory: the solver records are laid out in colour order, which is only
+                // known after the new arbiters are coloured
+                a.c_stg0[gslot + p] = make_float4(out[0].px, out[0].py, out[0].sep, out[0].nx);
+                a.c_stg1[gslot + p] = n > 1 ? make_float4(out[1].px, out[1].py, out[1].sep, out[0].ny) : make_float4(0.0f, 0.0f, 0.0f, out[0].ny);
+                a.c_cache[par ^ 1][gslot + p] = make_float4(fr, pn, pt, 0.0f);
                 if (color != NO_COLOR) {
                     if (!(s.stat[b1] & 1)) atomicOr(&s.used[b1], 1u << color);
                     if (!(s.stat[b2] & 1)) atomicOr(&s.used[b2], 1u << color);
@@ -499,7 +570,10 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             cstart[lane] = incl - cntc;
             if (lane == 31) cstart[BNC] = incl;
             const unsigned present = __ballot_sync(0xffffffffu, cntc > 0);
-            if (lane == 0) s.misc[35] = 32 - __clz(present);
+            int mx = cntc;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            if (lane == 0) { s.misc[35] = 32 - __clz(present); s.misc[137] = mx; }
         }
         __syncthreads();
         ncolors = s.misc[35];
@@ -515,21 +589,50 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
         }
         __syncthreads();
         PHASE(4);
-        // ---- 5. the ordered half of Arbiter::pre_step (arbiter.rs:216-223): apply last step's impulses colour by colour
+        // ---- 5. Arbiter::pre_step.  (a) the velocity-independent half (arbiter.rs:192-215), one thread per arbiter, written as
+        //         colour-ordered solver records;  (b) the ordered half (arbiter.rs:216-223): last step's impulses, colour by colour
+        const int A = cstart[BNC];
+        for (int k = tid; k < A; k += T) {
+            const int p = s.order[k];
+            int b1, b2;
+            key_bodies(s.key[p], b1, b2);
+            const int n = s.cnt[p];
+            const float4 g0 = a.c_stg0[gslot + p], g1 = a.c_stg1[gslot + p], cw = a.c_cache[par ^ 1][gslot + p];
+            const float2 p1 = s.pos[b1], p2 = s.pos[b2], i1 = s.inv[b1], i2 = s.inv[b2];
+            const V2 nn = mk(g0.w, g1.w);
+            ContactConst k0;
+            contact_constants(mk(g0.x, g0.y), nn, g0.z, mk(p1.x, p1.y), mk(p2.x, p2.y), i1.x, i1.y, i2.x, i2.y, a.inv_dt, kbias, k0);
+            maxpen = fmaxf(maxpen, -g0.z);
+            s.cA[0][k] = make_float4(k0.r1.x, k0.r1.y, k0.r2.x, k0.r2.y);
+            s.cB[0][k] = make_float4(k0.mass_n, k0.mass_t, k0.bias, cw.y);
+            if (n > 1) {
+                contact_constants(mk(g1.x, g1.y), nn, g1.z, mk(p1.x, p1.y), mk(p2.x, p2.y), i1.x, i1.y, i2.x, i2.y, a.inv_dt, kbias, k0);
+                maxpen = fmaxf(maxpen, -g1.z);
+                s.cA[1][k] = make_float4(k0.r1.x, k0.r1.y, k0.r2.x, k0.r2.y);
+                s.cB[1][k] = make_float4(k0.mass_n, k0.mass_t, k0.bias, cw.y);
+            }
+            s.kb[k] = (unsigned)b1 | ((unsigned)b2 << 12) | ((unsigned)(n - 1) << 24);
+            s.nrmk[k] = make_float2(nn.x, nn.y);
+            s.frk[k] = cw.x;
+            s.ptk[k] = make_float2(cw.z, cw.z);
+        }
+        __syncthreads();
         if (acc) {
             for (int c = 0; c < ncolors; c++) {
                 for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
-                    const int p = s.order[k];
-                    int b1, b2;
-                    key_bodies(s.key[p], b1, b2);
-                    const float2 i1 = s.inv[b1], i2 = s.inv[b2], nn = s.nrm[p];
+                    const unsigned kbv = s.kb[k];
+                    const int b1 = kbv & 0xfffu, b2 = (kbv >> 12) & 0xfffu;
+                    const float2 i1 = s.inv[b1], i2 = s.inv[b2], nn = s.nrmk[k], pt = s.ptk[k];
                     Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
-                    const int n = s.cnt[p];
-                    for (int q = 0; q < n; q++) {
-                        const float4 ca = s.conA[2 * p + q];
-                        ContactConst k0;
-                        k0.n = mk(nn.x, nn.y); k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
-                        contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, s.conB[2 * p + q].w, s.conC[2 * p + q], v1, v2);
+                    ContactConst k0;
+                    k0.n = mk(nn.x, nn.y);
+                    float4 ca = s.cA[0][k];
+                    k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
+                    contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, s.cB[0][k].w, pt.x, v1, v2);
+                    if (kbv >> 24) {
+                        ca = s.cA[1][k];
+                        k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
+                        contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, s.cB[1][k].w, pt.y, v1, v2);
                     }
                     if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b1, v1);
                     if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b2, v2);
@@ -572,32 +675,8 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
         }
         if (*s_err) break;
         PHASE(6);
-        // ---- 7. iterations (world.rs:132-140)
-        for (int it = 0; it < a.iterations; it++) {
-            for (int c = 0; c < ncolors; c++) {
-                for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
-                    int p = s.order[k];
-                    unsigned key = s.key[p];
-                    int b1, b2;
-            key_bodies(key, b1, b2);
-                    float2 i1 = s.inv[b1], i2 = s.inv[b2], nn = s.nrm[p];
-                    float fr = s.sfric[p];
-                    Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
-                    int n = s.cnt[p];
-                    for (int q = 0; q < n; q++) {
-                        const float4 ca = s.conA[2 * p + q], cb = s.conB[2 * p + q];
-                        ContactConst k0;
-                        k0.n = mk(nn.x, nn.y); k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
-                        k0.mass_n = cb.x; k0.mass_t = cb.y; k0.bias = cb.z;
-                        float pn = cb.w, pt = s.conC[2 * p + q];
-                        contact_apply(k0, fr, i1.x, i1.y, i2.x, i2.y, acc, pn, pt, v1, v2);
-                        if (acc) { s.conB[2 * p + q].w = pn; s.conC[2 * p + q] = pt; }
-                    }
-                    if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b1, v1);
-                    if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b2, v2);
-                }
-                __syncthreads();
-            }
+        // Joint::apply_impulse by joint colour (all threads; barrier 0)
+        auto joint_hops = [&]() {
             for (int c = 0; c < njc; c++) {
                 for (int k = jcs[c] + tid; k < jcs[c + 1]; k += T) {
                     int j = s.jorder[k];
@@ -618,6 +697,18 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
                 }
                 __syncthreads();
             }
+        };
+        // ---- 7. iterations (world.rs:132-140): one thread per arbiter of the colour, records read by colour-major position
+        {
+            auto off = [&](const void* p) { return (unsigned)((const unsigned char*)p - smem_raw); };
+            HotOffsets h;
+            h.kb = off(s.kb); h.inv = off(s.inv); h.nrmk = off(s.nrmk); h.frk = off(s.frk); h.ptk = off(s.ptk); h.vel = off(s.vel);
+            h.cA0 = off(s.cA[0]); h.cA1 = off(s.cA[1]); h.cB0 = off(s.cB[0]); h.cB1 = off(s.cB[1]); h.cstart = off(cstart);
+            const int sweeps = njc > 0 ? 1 : a.iterations;  // joints are solved after the contacts inside every iteration
+            for (int it = 0; it < a.iterations; it += sweeps) {
+                if (acc) contact_sweeps<true>(h, ncolors, sweeps); else contact_sweeps<false>(h, ncolors, sweeps);
+                if (njc > 0) joint_hops();
+            }
         }
         PHASE(7);
         // ---- 8. integrate positions (world.rs:143-150, all bodies)
@@ -629,14 +720,13 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             s.rot[i] += v.z * a.dt;
         }
         // ---- 9. this step's slots become the cache of the next one
+        for (int k = tid; k < A; k += T)  // (friction, accumulated impulses of contact 0) by slot, for the next step's Arbiter::update
+            a.c_cache[par ^ 1][gslot + s.order[k]] = make_float4(s.frk[k], s.cB[0][k].w, s.ptk[k].x, 0.0f);
+        par ^= 1;
+        __syncthreads();  // frk aliases okey
         for (int p = tid; p < P; p += T) {
             s.okey[p] = s.key[p];
-            unsigned char col = s.cnt[p] > 0 ? s.color[p] : NO_COLOR;
-            s.ocolor[p] = col;
-            if (col != NO_COLOR) {
-                const size_t g = (size_t)wld * cap + p;
-                a.c_fric[g] = s.sfric[p]; a.c_pn[g] = s.conB[2 * p].w; a.c_pt[g] = s.conC[2 * p];
-            }
+            s.ocolor[p] = s.cnt[p] > 0 ? s.color[p] : NO_COLOR;
         }
         if (tid == 0) { *s_Pold = P; s.misc[138] = 0; s.misc[139] = 0; }
         __syncthreads();
@@ -670,6 +760,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     __syncthreads();
     if (tid == 0) {
         a.c_count[wld] = Pn;
+        a.c_par[wld] = par;
         a.w_err[wld] = err;
         a.w_ncon[wld] = s.misc[0];
         a.w_narb[wld] = s.misc[1];
@@ -680,14 +771,15 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     if (exporting) {
         const int xw = wld - a.export_first;
         const bool valid = !err && a.n_steps > 0;
-        for (int p = tid; p < (valid ? P : 0); p += T) {
+        for (int k = tid; k < (valid ? cstart[BNC] : 0); k += T) {
+            const int p = s.order[k];
             SlotExport* e = &a.exp_slots[(size_t)xw * cap + p];
-            e->friction = s.sfric[p]; e->color = s.color[p];
-            for (int q = 0; q < 2; q++)
-            {
-                const float4 ca = s.conA[2 * p + q], cb = s.conB[2 * p + q];
+            e->friction = a.c_cache[par][gslot + p].x; e->color = s.color[p];
+            const float2 pt = s.ptk[k];
+            for (int q = 0; q < 2; q++) {
+                const float4 ca = s.cA[q][k], cb = s.cB[q][k];
                 float* o = e->sol[q];
-                o[0] = ca.x; o[1] = ca.y; o[2] = ca.z; o[3] = ca.w; o[4] = cb.x; o[5] = cb.y; o[6] = cb.z; o[7] = cb.w; o[8] = s.conC[2 * p + q];
+                o[0] = ca.x; o[1] = ca.y; o[2] = ca.z; o[3] = ca.w; o[4] = cb.x; o[5] = cb.y; o[6] = cb.z; o[7] = cb.w; o[8] = q ? pt.y : pt.x;
             }
         }
         if (tid == 0) a.exp_count[xw] = valid ? P : 0;
@@ -798,7 +890,9 @@ struct SyltBatch {
     DBuf<int> body_off, joint_off, jorder, jcolor_start, n_jcolors, c_count, w_err, w_ncon, w_narb, w_ncolors, w_errjoint, exp_count;
     DBuf<float4> pose, vel, mp, jla, jr, jm, w_badk;
     DBuf<float2> wh, jparam, jp, jbias;
-    DBuf<float> mass_moi, c_fric, c_pn, c_pt, w_maxpen;
+    DBuf<float> mass_moi, w_maxpen;
+    DBuf<float4> c_cache0, c_cache1, c_stg0, c_stg1;
+    DBuf<int> c_par;
     DBuf<int2> jbodies;
     DBuf<unsigned> c_key;
     DBuf<unsigned char> c_color, bflags;
@@ -816,7 +910,7 @@ void batch_free(SyltBatch* b) {
     b->c_count.release(); b->w_err.release(); b->w_ncon.release(); b->w_narb.release(); b->w_ncolors.release(); b->w_errjoint.release();
     b->exp_count.release(); b->pose.release(); b->vel.release(); b->mp.release(); b->jla.release(); b->jr.release(); b->jm.release();
     b->w_badk.release(); b->wh.release(); b->jparam.release(); b->jp.release(); b->jbias.release(); b->mass_moi.release();
-    b->c_fric.release(); b->c_pn.release(); b->c_pt.release(); b->w_maxpen.release(); b->jbodies.release(); b->c_key.release();
+    b->c_cache0.release(); b->c_cache1.release(); b->c_stg0.release(); b->c_stg1.release(); b->c_par.release(); b->w_maxpen.release(); b->jbodies.release(); b->c_key.release();
     b->c_color.release(); b->bflags.release(); b->exp_slots.release(); b->stats.release(); b->stage.release();
 }
 
@@ -841,12 +935,20 @@ int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaSt
     a.n_worlds = w1; a.world_begin = w0; a.n_steps = n; a.iterations = (int)b->iterations;
     a.accumulate = b->accumulate; a.warm = b->warm; a.poscorr = b->poscorr; a.fix_inverse = b->fix_inverse;
     a.dt = dt; a.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;  // world.rs:108
+    {
+        Smem hs;
+        static unsigned char anchor[16];  // any non-null base: only the differences are used
+        carve(&hs, anchor, b->Bmax, b->Jmax, b->cap, b->nbk);
+        unsigned char* ptrs[sizeof(Smem) / sizeof(void*)];
+        memcpy(ptrs, &hs, sizeof(Smem));
+        for (size_t i = 0; i < sizeof(Smem) / sizeof(void*); i++) a.smem_off[i] = (unsigned long long)(ptrs[i] - anchor);
+    }
     a.gx = b->gx; a.gy = b->gy; a.Bmax = b->Bmax; a.Jmax = b->Jmax; a.cap = b->cap; a.nbk = b->nbk; a.cell = b->cell; a.bflags = b->bflags.p;
     a.export_first = b->export_first; a.export_count = b->export_count;
     a.body_off = b->body_off.p; a.joint_off = b->joint_off.p; a.pose = b->pose.p; a.vel = b->vel.p; a.mp = b->mp.p; a.wh = b->wh.p;
     a.jbodies = b->jbodies.p; a.jla = b->jla.p; a.jparam = b->jparam.p; a.jp = b->jp.p; a.jr = b->jr.p; a.jm = b->jm.p; a.jbias = b->jbias.p;
     a.jorder = b->jorder.p; a.jcolor_start = b->jcolor_start.p; a.n_jcolors = b->n_jcolors.p;
-    a.c_count = b->c_count.p; a.c_key = b->c_key.p; a.c_fric = b->c_fric.p; a.c_pn = b->c_pn.p; a.c_pt = b->c_pt.p; a.c_color = b->c_color.p;
+    a.c_count = b->c_count.p; a.c_key = b->c_key.p; a.c_cache[0] = b->c_cache0.p; a.c_cache[1] = b->c_cache1.p; a.c_par = b->c_par.p; a.c_stg0 = b->c_stg0.p; a.c_stg1 = b->c_stg1.p; a.c_color = b->c_color.p;
     a.w_err = b->w_err.p; a.w_ncon = b->w_ncon.p; a.w_narb = b->w_narb.p; a.w_ncolors = b->w_ncolors.p; a.w_errjoint = b->w_errjoint.p;
     a.w_maxpen = b->w_maxpen.p; a.w_badk = b->w_badk.p; a.exp_slots = b->exp_slots.p; a.exp_count = b->exp_count.p;
     k_batch_step<<<w1 - w0, b->threads, b->smem, st>>>(a);
@@ -1009,8 +1111,8 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
         (e = upload(b->jcolor_start, jcs)) || (e = upload(b->n_jcolors, njc))) { sylt_batch_destroy(b); return e; }
     const size_t W = (size_t)n_worlds, WC = W * (size_t)b->cap;
     if ((e = zeroed(b->jp, (size_t)NJ)) || (e = zeroed(b->jr, (size_t)NJ)) || (e = zeroed(b->jm, (size_t)NJ)) || (e = zeroed(b->jbias, (size_t)NJ)) ||
-        (e = zeroed(b->c_count, W)) || (e = zeroed(b->c_key, WC)) || (e = zeroed(b->c_fric, WC)) || (e = zeroed(b->c_pn, WC)) ||
-        (e = zeroed(b->c_pt, WC)) || (e = zeroed(b->c_color, WC)) || (e = zeroed(b->w_err, W)) || (e = zeroed(b->w_ncon, W)) ||
+        (e = zeroed(b->c_count, W)) || (e = zeroed(b->c_key, WC)) || (e = zeroed(b->c_cache0, WC)) || (e = zeroed(b->c_cache1, WC)) || (e = zeroed(b->c_stg0, WC)) || (e = zeroed(b->c_stg1, WC)) || (e = zeroed(b->c_par, W)) ||
+        (e = zeroed(b->c_color, WC)) || (e = zeroed(b->w_err, W)) || (e = zeroed(b->w_ncon, W)) ||
         (e = zeroed(b->w_narb, W)) || (e = zeroed(b->w_ncolors, W)) || (e = zeroed(b->w_errjoint, W)) || (e = zeroed(b->w_maxpen, W)) ||
         (e = zeroed(b->w_badk, W)) || (e = zeroed(b->stats, 1))) { sylt_batch_destroy(b); return e; }
     b->export_first = 0;

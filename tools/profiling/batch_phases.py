@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 if "--build" in sys.argv:
     from sylt2d_b200 import build as B
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    subprocess.run(["nvcc"] + B.NVCC_FLAGS + ["-DSYLT_BATCH_TIMING", "-o", LIB] + B.SOURCES, cwd=B.CSRC, check=True)
+    subprocess.run(["nvcc"] + B.NVCC_FLAGS + ["-DSYLT_BATCH_TIMING=" + ("2" if "--hops" in sys.argv else "1"), "-o", LIB] + B.SOURCES, cwd=B.CSRC, check=True)
     print(LIB)
     sys.exit(0)
 
@@ -46,3 +46,7 @@ print(f"{worlds} worlds x {steps} steps: {ms / steps:.3f} ms/step, {worlds * sc.
 for i, n in enumerate(names):
     print(f"  {n:20s} {out[i] / (worlds * steps):10.0f} cycles/world-step  {100.0 * out[i] / tot:5.1f} %")
 print(f"  total {tot / (worlds * steps):.0f} cycles/world-step")
+hops = worlds * steps * sc.iterations
+print("inside the iteration phase, thread 0, cycles per ITERATION (sum over its colours):")
+for i, n in ((13, "hop: indices + body loads"), (14, "hop: contact loads + arithmetic"), (15, "hop: stores + barrier")):
+    print(f"  {n:34s} {out[i] / hops:8.0f}")
