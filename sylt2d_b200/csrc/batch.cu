@@ -239,6 +239,38 @@ __device__ __noinline__ void contact_sweeps(HotOffsets o, int ncolors, int iters
     }
 }
 
+// The ordered half of Arbiter::pre_step (arbiter.rs:216-223): apply last step's accumulated impulses, colour by colour.
+__device__ __noinline__ void warm_sweep(HotOffsets o, int ncolors) {
+    const int tid = threadIdx.x, T = blockDim.x;
+    const unsigned* kb = (const unsigned*)(smem_raw + o.kb);
+    const float2 *inv = (const float2*)(smem_raw + o.inv), *nrmk = (const float2*)(smem_raw + o.nrmk), *ptk = (const float2*)(smem_raw + o.ptk);
+    float4* vel = (float4*)(smem_raw + o.vel);
+    const float4 *cA0 = (const float4*)(smem_raw + o.cA0), *cA1 = (const float4*)(smem_raw + o.cA1);
+    const float4 *cB0 = (const float4*)(smem_raw + o.cB0), *cB1 = (const float4*)(smem_raw + o.cB1);
+    const int* cstart = (const int*)(smem_raw + o.cstart);
+    for (int c = 0; c < ncolors; c++) {
+        for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
+            const unsigned kbv = kb[k];
+            const int b1 = kbv & 0xfffu, b2 = (kbv >> 12) & 0xfffu;
+            const float2 i1 = inv[b1], i2 = inv[b2], nn = nrmk[k], pt = ptk[k];
+            Vel v1 = ld_vel(vel, b1), v2 = ld_vel(vel, b2);
+            ContactConst k0;
+            k0.n = mk(nn.x, nn.y);
+            float4 ca = cA0[k];
+            k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
+            contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, cB0[k].w, pt.x, v1, v2);
+            if (kbv >> 24) {
+                ca = cA1[k];
+                k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
+                contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, cB1[k].w, pt.y, v1, v2);
+            }
+            if (i1.x != 0.0f || i1.y != 0.0f) st_vel(vel, b1, v1);
+            if (i2.x != 0.0f || i2.y != 0.0f) st_vel(vel, b2, v2);
+        }
+        __syncthreads();
+    }
+}
+
 #ifdef SYLT_BATCH_TIMING
 // profiling build only (tools/profiling): cycles thread 0 of every CTA spends in each phase of the step
 __device__ unsigned long long g_phase_cycles[16];
@@ -592,6 +624,12 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
         // ---- 5. Arbiter::pre_step.  (a) the velocity-independent half (arbiter.rs:192-215), one thread per arbiter, written as
         //         colour-ordered solver records;  (b) the ordered half (arbiter.rs:216-223): last step's impulses, colour by colour
         const int A = cstart[BNC];
+        HotOffsets hot;
+        {
+            auto off = [&](const void* p) { return (unsigned)((const unsigned char*)p - smem_raw); };
+            hot.kb = off(s.kb); hot.inv = off(s.inv); hot.nrmk = off(s.nrmk); hot.frk = off(s.frk); hot.ptk = off(s.ptk); hot.vel = off(s.vel);
+            hot.cA0 = off(s.cA[0]); hot.cA1 = off(s.cA[1]); hot.cB0 = off(s.cB[0]); hot.cB1 = off(s.cB[1]); hot.cstart = off(cstart);
+        }
         for (int k = tid; k < A; k += T) {
             const int p = s.order[k];
             int b1, b2;
@@ -617,29 +655,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             s.ptk[k] = make_float2(cw.z, cw.z);
         }
         __syncthreads();
-        if (acc) {
-            for (int c = 0; c < ncolors; c++) {
-                for (int k = cstart[c] + tid; k < cstart[c + 1]; k += T) {
-                    const unsigned kbv = s.kb[k];
-                    const int b1 = kbv & 0xfffu, b2 = (kbv >> 12) & 0xfffu;
-                    const float2 i1 = s.inv[b1], i2 = s.inv[b2], nn = s.nrmk[k], pt = s.ptk[k];
-                    Vel v1 = ld_vel(s.vel, b1), v2 = ld_vel(s.vel, b2);
-                    ContactConst k0;
-                    k0.n = mk(nn.x, nn.y);
-                    float4 ca = s.cA[0][k];
-                    k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
-                    contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, s.cB[0][k].w, pt.x, v1, v2);
-                    if (kbv >> 24) {
-                        ca = s.cA[1][k];
-                        k0.r1 = mk(ca.x, ca.y); k0.r2 = mk(ca.z, ca.w);
-                        contact_warmstart(k0, i1.x, i1.y, i2.x, i2.y, s.cB[1][k].w, pt.y, v1, v2);
-                    }
-                    if (i1.x != 0.0f || i1.y != 0.0f) st_vel(s.vel, b1, v1);
-                    if (i2.x != 0.0f || i2.y != 0.0f) st_vel(s.vel, b2, v2);
-                }
-                __syncthreads();
-            }
-        }
+        if (acc) warm_sweep(hot, ncolors);
         PHASE(5);
         // ---- 6. Joint::pre_step by joint colour
         for (int c = 0; c < njc; c++) {
@@ -700,13 +716,9 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
         };
         // ---- 7. iterations (world.rs:132-140): one thread per arbiter of the colour, records read by colour-major position
         {
-            auto off = [&](const void* p) { return (unsigned)((const unsigned char*)p - smem_raw); };
-            HotOffsets h;
-            h.kb = off(s.kb); h.inv = off(s.inv); h.nrmk = off(s.nrmk); h.frk = off(s.frk); h.ptk = off(s.ptk); h.vel = off(s.vel);
-            h.cA0 = off(s.cA[0]); h.cA1 = off(s.cA[1]); h.cB0 = off(s.cB[0]); h.cB1 = off(s.cB[1]); h.cstart = off(cstart);
             const int sweeps = njc > 0 ? 1 : a.iterations;  // joints are solved after the contacts inside every iteration
             for (int it = 0; it < a.iterations; it += sweeps) {
-                if (acc) contact_sweeps<true>(h, ncolors, sweeps); else contact_sweeps<false>(h, ncolors, sweeps);
+                if (acc) contact_sweeps<true>(hot, ncolors, sweeps); else contact_sweeps<false>(hot, ncolors, sweeps);
                 if (njc > 0) joint_hops();
             }
         }
@@ -1033,8 +1045,9 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
             if (2.2f * radius[(size_t)i] + 0.1f > b->cell || !(radius[(size_t)i] == radius[(size_t)i])) f |= 2;
             fl[(size_t)i] = f;
         }
+        // >= 4 buckets per body: with CELL_ROW_STRIDE = 37 two rows of cells only share buckets when they are >= nbk / 37 rows apart
         int nbk = 64;
-        while (nbk < Bmax && nbk < 4096) nbk <<= 1;
+        while (nbk < 4 * Bmax && nbk < 4096) nbk <<= 1;
         b->nbk = nbk;
     }
     // joints: Joint::new (joint.rs:26-55) per world, then a greedy colouring of each world's joint graph
