@@ -194,6 +194,11 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
                       float gravity_x, float gravity_y, uint32_t iterations, int device, SyltBatch** out);
 int sylt_batch_destroy(SyltBatch* b);
 int sylt_batch_set_context(SyltBatch* b, int accumulate_impulse, int warm_starting, int position_correction);
+/* Candidate-pair slots per world (AABB-overlapping pairs a step may see; default 2 * max bodies per world + 32, 0 restores it).
+ * A step that finds more raises SYLT_ERR_CAPACITY for that world (sylt_batch_get_errors) and freezes it.  The slots live in
+ * shared memory (97 B each): SYLT_ERR_UNSUPPORTED when a world no longer fits one CTA.  Drops the contact history (next step
+ * starts cold), so call it before stepping.  The reference has no such limit (HashMap, world.rs:24). */
+int sylt_batch_set_capacity(SyltBatch* b, int32_t slots_per_world);
 /* see sylt_world_set_fixes; fix_features is not available for batches (SYLT_ERR_UNSUPPORTED) */
 int sylt_batch_set_fixes(SyltBatch* b, int fix_features, int fix_inverse);
 int sylt_batch_step_n(SyltBatch* b, float dt, int32_t n);

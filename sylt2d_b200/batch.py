@@ -55,6 +55,10 @@ class Batch:
         check(self.L.sylt_batch_step_host6(self.h, dt, n, ptr(states_in), ptr(states_out)))
         return states_out
 
+    def set_capacity(self, slots_per_world=0):
+        """Candidate-pair slots per world (0 = default 2 * max bodies + 32); drops the contact history."""
+        check(self.L.sylt_batch_set_capacity(self.h, int(slots_per_world)))
+
     def set_fixes(self, fix_features=False, fix_inverse=False):
         check(self.L.sylt_batch_set_fixes(self.h, int(fix_features), int(fix_inverse)))
 

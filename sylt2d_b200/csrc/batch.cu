@@ -939,6 +939,32 @@ int zeroed(DBuf<T>& d, size_t n) {
     return SYLT_OK;
 }
 
+// Everything that depends on the per-world candidate-slot capacity: shared-memory size, CTA width, the per-world slot caches
+// (zeroed: last step's contact history is dropped) and the export buffers.
+int batch_set_cap(SyltBatch* b, int cap) {
+    cap = std::min(65535, std::max(32, (cap + 1) & ~1));
+    const size_t smem = carve(nullptr, nullptr, b->Bmax, b->Jmax, cap, b->nbk);
+    int max_smem = 0;
+    SYLT_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, b->device));
+    if (smem > (size_t)max_smem) {
+        set_last_error("world too large for the one-CTA-per-world path (shared memory)");
+        return SYLT_ERR_UNSUPPORTED;
+    }
+    SYLT_CUDA(cudaFuncSetAttribute(k_batch_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    b->cap = cap;
+    b->smem = smem;
+    int t = std::max(b->Bmax, (cap + 1) / 2);
+    t = ((t + 31) / 32) * 32;
+    b->threads = std::min(256, std::max(32, t));
+    const size_t W = (size_t)b->n_worlds, WC = W * (size_t)cap;
+    int e = 0;
+    if ((e = zeroed(b->c_count, W)) || (e = zeroed(b->c_key, WC)) || (e = zeroed(b->c_cache0, WC)) || (e = zeroed(b->c_cache1, WC)) ||
+        (e = zeroed(b->c_stg0, WC)) || (e = zeroed(b->c_stg1, WC)) || (e = zeroed(b->c_par, W)) || (e = zeroed(b->c_color, WC)) ||
+        (e = zeroed(b->exp_slots, (size_t)b->export_count * (size_t)cap)) || (e = zeroed(b->exp_count, (size_t)std::max(1, b->export_count))))
+        return e;
+    return SYLT_OK;
+}
+
 int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaStream_t st = nullptr) {
     if (w1 < 0) w1 = b->n_worlds;
     if (!st) st = b->stream;
@@ -1099,20 +1125,10 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
     }
     b->h_jorder = jorder;
     b->Bmax = Bmax; b->Jmax = Jmax;
-    b->cap = std::max(32, 2 * Bmax + 32);
-    if (b->cap > 65535) b->cap = 65535;
-    b->smem = carve(nullptr, nullptr, Bmax, Jmax, b->cap, b->nbk);
-    int max_smem = 0;
-    SYLT_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
-    if (b->smem > (size_t)max_smem) {
-        delete b;
-        set_last_error("world too large for the one-CTA-per-world path (shared memory)");
-        return SYLT_ERR_UNSUPPORTED;
-    }
-    SYLT_CUDA(cudaFuncSetAttribute(k_batch_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b->smem));
-    int t = std::max(Bmax, (b->cap + 1) / 2);
-    t = ((t + 31) / 32) * 32;
-    b->threads = std::min(256, std::max(32, t));
+    b->export_first = 0;
+    b->export_count = std::min(n_worlds, 64);
+    // default slot capacity: two candidate pairs per body (a pyramid or a chain has fewer); sylt_batch_set_capacity raises it
+    { int e0 = batch_set_cap(b, 2 * Bmax + 32); if (e0) { sylt_batch_destroy(b); return e0; } }
     SYLT_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
     SYLT_CUDA(cudaEventCreate(&b->ev0));
     SYLT_CUDA(cudaEventCreate(&b->ev1));
@@ -1122,18 +1138,11 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
         (e = upload(b->vel, vel)) || (e = upload(b->mp, mp)) || (e = upload(b->bflags, fl)) || (e = upload(b->wh, wh)) || (e = upload(b->mass_moi, mm)) ||
         (e = upload(b->jbodies, jb)) || (e = upload(b->jla, jla)) || (e = upload(b->jparam, jparam)) || (e = upload(b->jorder, jorder)) ||
         (e = upload(b->jcolor_start, jcs)) || (e = upload(b->n_jcolors, njc))) { sylt_batch_destroy(b); return e; }
-    const size_t W = (size_t)n_worlds, WC = W * (size_t)b->cap;
+    const size_t W = (size_t)n_worlds;
     if ((e = zeroed(b->jp, (size_t)NJ)) || (e = zeroed(b->jr, (size_t)NJ)) || (e = zeroed(b->jm, (size_t)NJ)) || (e = zeroed(b->jbias, (size_t)NJ)) ||
-        (e = zeroed(b->c_count, W)) || (e = zeroed(b->c_key, WC)) || (e = zeroed(b->c_cache0, WC)) || (e = zeroed(b->c_cache1, WC)) || (e = zeroed(b->c_stg0, WC)) || (e = zeroed(b->c_stg1, WC)) || (e = zeroed(b->c_par, W)) ||
-        (e = zeroed(b->c_color, WC)) || (e = zeroed(b->w_err, W)) || (e = zeroed(b->w_ncon, W)) ||
+        (e = zeroed(b->w_err, W)) || (e = zeroed(b->w_ncon, W)) ||
         (e = zeroed(b->w_narb, W)) || (e = zeroed(b->w_ncolors, W)) || (e = zeroed(b->w_errjoint, W)) || (e = zeroed(b->w_maxpen, W)) ||
         (e = zeroed(b->w_badk, W)) || (e = zeroed(b->stats, 1))) { sylt_batch_destroy(b); return e; }
-    b->export_first = 0;
-    b->export_count = std::min(n_worlds, 64);
-    if ((e = zeroed(b->exp_slots, (size_t)b->export_count * (size_t)b->cap)) || (e = zeroed(b->exp_count, (size_t)b->export_count))) {
-        sylt_batch_destroy(b);
-        return e;
-    }
     *out = b;
     return SYLT_OK;
 }
@@ -1156,6 +1165,13 @@ int sylt_batch_set_context(SyltBatch* b, int acc, int warm, int pc) {
     if (!b) return SYLT_ERR_INVALID;
     b->accumulate = acc != 0; b->warm = warm != 0; b->poscorr = pc != 0;
     return SYLT_OK;
+}
+
+int sylt_batch_set_capacity(SyltBatch* b, int32_t slots_per_world) {
+    if (!b || slots_per_world < 0) return SYLT_ERR_INVALID;
+    SYLT_CUDA(cudaSetDevice(b->device));
+    SYLT_CUDA(cudaStreamSynchronize(b->stream));
+    return batch_set_cap(b, slots_per_world == 0 ? 2 * b->Bmax + 32 : slots_per_world);
 }
 
 int sylt_batch_set_fixes(SyltBatch* b, int fix_features, int fix_inverse) {

@@ -382,10 +382,12 @@ def test_colour_order_vs_canonical_order_tolerance_and_long_run():
 
 
 # ------------------------------------------------------------------ batched worlds
-def _batch_lockstep(scene, n_worlds, steps, x_jitter=0.0, omega_jitter=0.0, check_worlds=(0, 1)):
+def _batch_lockstep(scene, n_worlds, steps, x_jitter=0.0, omega_jitter=0.0, check_worlds=(0, 1), capacity=None):
     from sylt2d_b200 import Batch
     bodies, boff, joints, joff = scenes.tile_worlds(scene, n_worlds, seed=7, x_jitter=x_jitter, omega_jitter=omega_jitter)
     b = Batch(bodies, boff, joints, joff, scene.gravity, scene.iterations, device=0, ctx=scene.ctx)
+    if capacity is not None:
+        b.set_capacity(capacity)
     nb = scene.num_bodies
     oracles = {}
     for wi in check_worlds:
@@ -418,6 +420,37 @@ def test_batch_pyramid_bit_exact():
 
 def test_batch_pyramid20_config5_world():
     _batch_lockstep(scenes.pyramid(20, 10), 3, 40, x_jitter=0.01, check_worlds=(1,))
+
+
+def test_batch_large_world_colour_wider_than_the_cta():
+    """785 bodies in 28 stacks: two colours of ~380 arbiters each (more than the CTA has threads), slots span several rounds."""
+    bd = scenes._Builder()
+    scenes._ground(bd)
+    for c in range(28):
+        for r in range(28):  # slightly overlapping vertically: every box touches the one below from the first step
+            bd.box(1.0, 1.0, 10.0, 0.2, (-14.0 + 1.05 * c, 0.49 + 0.98 * r))
+    b = _batch_lockstep(bd.scene("stacks28", iterations=10), 2, 12, x_jitter=0.002, check_worlds=(1,))
+    arb, _ = b.get_arbiters(1, cap=8192)
+    assert arb.shape[0] > 700 and np.bincount(arb["color"]).max() > 256
+
+
+def test_batch_slot_capacity():
+    """A dense block has ~4 candidate pairs per body: over the default capacity (SYLT_ERR_CAPACITY, world frozen) until raised."""
+    from sylt2d_b200 import Batch, SyltError
+    bd = scenes._Builder()
+    scenes._ground(bd)
+    for r in range(12):
+        for c in range(12):
+            bd.box(1.0, 1.0, 10.0, 0.2, (-6.0 + 0.98 * c, 0.49 + 0.98 * r))
+    sc = bd.scene("block12", iterations=10)
+    small = Batch(*scenes.tile_worlds(sc, 2, seed=7, x_jitter=0.002), sc.gravity, sc.iterations, device=0, ctx=sc.ctx)
+    small.step_n(sc.dt, 1)
+    assert (small.get_errors() == 5).all()
+    with pytest.raises(SyltError):
+        small.set_capacity(60000)  # no longer fits the shared memory of one CTA
+    b = _batch_lockstep(sc, 2, 12, x_jitter=0.002, check_worlds=(0,), capacity=700)
+    arb, _ = b.get_arbiters(0)
+    assert arb.shape[0] > 250
 
 
 def test_batch_bridge_and_pendulum_bit_exact():
