@@ -5,7 +5,7 @@
 //
 //   k_prepare      body        (cos,sin) cache, conservative AABB, hashed uniform-grid cell, force integration
 //                              (world.rs:113-120)
-//   scan           bucket      counting-sort offsets of the grid (hand-written 3-kernel exclusive scan)
+//   scan           bucket      counting-sort offsets of the grid (hand-written single-pass look-back scan)
 //   k_fill_cells   body        bodies grouped by cell
 //   k_rows<count|emit>  body   candidate rows: for body i every AABB-overlapping partner it "owns", partner-sorted;
 //                              static-static pairs skipped (world.rs:79-81).  Large bodies (ground, walls) bypass
@@ -66,7 +66,7 @@ struct Counters {
     unsigned bar;  // grid barrier arrivals of this step's k_solve
 };
 
-// ------------------------------------------------------------------ device-wide exclusive scan (3 kernels)
+// ------------------------------------------------------------------ device-wide exclusive scan (single pass, k_scan_lookback)
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
 template <typename T>
@@ -98,62 +98,15 @@ __device__ __forceinline__ T block_excl_scan(T v, T* total, T* sh /* >= 33 */) {
     return r;
 }
 
+// Single-pass exclusive scan (decoupled look-back): one launch instead of reduce / partials / apply.  A tile publishes its
+// aggregate, then sums the published aggregates of its predecessors until it meets one whose inclusive prefix is known.
+// Tiles are handed out by an atomic ticket, so a tile only ever waits for tiles that are already running.  The flags carry
+// the launch's epoch: no reset between launches.  The last tile also turns the grand total into the step counters.
+//   flag[t] = epoch << 2 | state, state 1 = agg[t] valid, 2 = incl[t] valid
+struct Counters;
 template <typename T>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_reduce(const T* in, int n_host, const int* n_dev, T* partial) {
-    __shared__ T sh[33];
-    int n = n_dev ? min(*n_dev, n_host) : n_host;
-    int base = blockIdx.x * SCAN_TILE;
-    if (base >= n) return;
-    T s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int i = base + threadIdx.x * SCAN_ITEMS + k;
-        if (i < n) s += in[i];
-    }
-    T tot;
-    block_excl_scan(s, &tot, sh);
-    if (threadIdx.x == 0) partial[blockIdx.x] = tot;
-}
-template <typename T>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_partials(T* partial, int n_host, const int* n_dev, T* out_total) {
-    __shared__ T sh[33];
-    int n = n_dev ? min(*n_dev, n_host) : n_host;
-    int nb = (n + SCAN_TILE - 1) / SCAN_TILE;
-    T run = 0;
-    for (int base = 0; base < nb; base += SCAN_THREADS) {
-        int i = base + threadIdx.x;
-        T v = i < nb ? partial[i] : T(0);
-        T tot;
-        T ex = block_excl_scan(v, &tot, sh);
-        if (i < nb) partial[i] = run + ex;
-        run += tot;
-    }
-    if (threadIdx.x == 0 && out_total) *out_total = run;
-}
-template <typename T>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_apply(const T* in, T* out, int n_host, const int* n_dev, const T* partial, const T* total) {
-    __shared__ T sh[33];
-    int n = n_dev ? min(*n_dev, n_host) : n_host;
-    int base = blockIdx.x * SCAN_TILE;
-    if (blockIdx.x == 0 && threadIdx.x == 0) out[n] = *total;
-    if (base >= n) return;
-    T v[SCAN_ITEMS];
-    T s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int i = base + threadIdx.x * SCAN_ITEMS + k;
-        v[k] = i < n ? in[i] : T(0);
-        s += v[k];
-    }
-    T tot;
-    T ex = block_excl_scan(s, &tot, sh) + partial[blockIdx.x];
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        int i = base + threadIdx.x * SCAN_ITEMS + k;
-        if (i < n) out[i] = ex;
-        ex += v[k];
-    }
-}
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, int n_host, const int* n_dev, unsigned* flag, T* agg, T* incl,
+                                                                int* ticket, unsigned epoch, int zero_in, Counters* cn, int totals_mode, int cap_pairs);
 
 // ------------------------------------------------------------------ broad phase
 struct GridParams {
@@ -175,9 +128,10 @@ __device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
 __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* vel, const float4* force, const float4* mp, const float4* geom,
                                                  const int* bflags, const float2* lverts, float2* rotc, float4* aabb, int4* cinfo,
                                                  int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
-                                                 Counters* cn, ulonglong2* vrec) {
+                                                 Counters* cn, ulonglong2* vrec, unsigned long long* used) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
+    used[i] = 0ull;  // colours taken at this body: rebuilt by k_build / the colouring rounds every step
     float4 p = pose[i];
     float4 m = mp[i];
     float4 g = geom[i];
@@ -490,13 +444,83 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
     if (threadIdx.x < NC && s_hist[threadIdx.x]) atomicAdd(&cn->color_count[threadIdx.x], s_hist[threadIdx.x]);
 }
 
-__global__ void k_totals(Counters* cn, const int* row_total, const unsigned long long* pair_total, int which, int cap_pairs) {
-    if (which == 0) cn->n_pairs = *row_total;
-    else {
-        cn->n_arb = (int)(*pair_total >> 32);
-        cn->n_con = (int)(unsigned)(*pair_total);
+template <typename T>
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, int n_host, const int* n_dev, unsigned* flag, T* agg, T* incl,
+                                                                int* ticket, unsigned epoch, int zero_in, Counters* cn, int totals_mode, int cap_pairs) {
+    __shared__ T sh[33];
+    __shared__ int s_tile;
+    __shared__ T s_prefix;
+    const int n = n_dev ? min(*n_dev, n_host) : n_host;
+    if (threadIdx.x == 0) {
+        const int t = atomicAdd(ticket, 1);
+        if (t == (int)gridDim.x - 1) atomicExch(ticket, 0);  // every tile of this launch has its ticket: ready for the next launch
+        s_tile = t;
     }
-    if (which == 0 && *row_total > cap_pairs) cn->err = SYLT_ERR_CAPACITY;
+    __syncthreads();
+    const int tile = s_tile;
+    const int ntiles = max(1, (n + SCAN_TILE - 1) / SCAN_TILE);
+    if (tile >= ntiles) return;
+    const int base = tile * SCAN_TILE;
+    T v[SCAN_ITEMS];
+    T s = 0;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const int i = base + threadIdx.x * SCAN_ITEMS + k;
+        v[k] = i < n ? in[i] : T(0);
+        s += v[k];
+        if (zero_in && i < n) in[i] = T(0);
+    }
+    T tot;
+    T ex = block_excl_scan(s, &tot, sh);
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        T prefix = 0;
+        volatile unsigned* vflag = flag;
+        if (tile == 0) {
+            if (lane == 0) { incl[0] = tot; __threadfence(); vflag[0] = (epoch << 2) | 2u; }
+        } else {
+            if (lane == 0) { agg[tile] = tot; __threadfence(); vflag[tile] = (epoch << 2) | 1u; }
+            for (int look = tile - 1;; look -= 32) {
+                const int t = look - lane;
+                unsigned f = 2u;  // tiles before the first one: an inclusive prefix of 0
+                if (t >= 0) {
+                    do { f = vflag[t]; } while ((f >> 2) != epoch || (f & 3u) == 0u);
+                }
+                __threadfence();
+                const bool full = (f & 3u) == 2u;
+                T val = 0;
+                if (t >= 0) val = full ? __ldcg(&incl[t]) : __ldcg(&agg[t]);
+                const unsigned fm = __ballot_sync(0xffffffffu, full);
+                const int first = __ffs(fm) - 1;  // nearest predecessor with a complete prefix
+                T c = (fm == 0u || lane <= first) ? val : T(0);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+                prefix += c;
+                if (fm) break;
+            }
+            if (lane == 0) { incl[tile] = prefix + tot; __threadfence(); vflag[tile] = (epoch << 2) | 2u; }
+        }
+        if (lane == 0) s_prefix = prefix;
+    }
+    __syncthreads();
+    ex += s_prefix;
+#pragma unroll
+    for (int k = 0; k < SCAN_ITEMS; k++) {
+        const int i = base + threadIdx.x * SCAN_ITEMS + k;
+        if (i < n) out[i] = ex;
+        ex += v[k];
+    }
+    if (tile == ntiles - 1 && threadIdx.x == 0) {
+        const T total = s_prefix + tot;
+        out[n] = total;
+        if (totals_mode == 1) {  // candidate rows -> pairs
+            cn->n_pairs = (int)total;
+            if ((long long)total > (long long)cap_pairs) cn->err = SYLT_ERR_CAPACITY;
+        } else if (totals_mode == 2) {  // packed (arbiters << 32 | contacts)
+            cn->n_arb = (int)((unsigned long long)total >> 32);
+            cn->n_con = (int)(unsigned)total;
+        }
+    }
 }
 
 // ------------------------------------------------------------------ solver (cooperative persistent kernel)
@@ -842,6 +866,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     if (lt == 0) s_done = 0u;
     __syncthreads();
     const int lane = lt & 31;
+    // Slot i of a colour belongs to thread i (the write-back below relies on it: no barrier between the last pass and it).
+    // Dealing the slots round-robin to the warps instead (a few lanes in each of the 16 warps rather than a few full warps)
+    // was measured: iterations 252 -> 289 us at 100k bodies — more warps polling L2 costs more than shorter waits save.
+    const int slot_of_thread = lt;
     auto wait_progress = [&](unsigned need) {
         if (lane == 0) {
             unsigned spins = 0;
@@ -912,10 +940,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228) then Joint::pre_step (joint.rs:57-115)
     for (int c = 0; c < ncolors; c++) {
         const int cnt = s_lbase[c + 1] - s_lbase[c];
-        for (int i0 = lt - lane; i0 < cnt; i0 += T) {  // warp-uniform trip count
-            const bool did = i0 + lane < cnt;
+        for (int r0 = 0; r0 < cnt; r0 += T) {  // warp-uniform trip count
+            const int i = r0 + slot_of_thread;
+            const bool did = i < cnt;
             wait_progress((unsigned)max(0, s_lbase[c] - slack_of(c)));
-            if (did) prestep_slot(c, i0 + lane);
+            if (did) prestep_slot(c, i);
             add_progress(did);
         }
     }
@@ -968,10 +997,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     for (int it = 1; it <= (aborted ? 0 : a.iterations); it++) {
         for (int c = 0; c < ncolors; c++) {
             const int cnt = s_lbase[c + 1] - s_lbase[c];
-            for (int i0 = lt - lane; i0 < cnt; i0 += T) {
-                const bool did = i0 + lane < cnt;
+            for (int r0 = 0; r0 < cnt; r0 += T) {
+                const int i = r0 + slot_of_thread;
+                const bool did = i < cnt;
                 wait_progress((unsigned)max(0, it * L + s_lbase[c] - slack_of(c)));
-                if (did) apply_slot(c, i0 + lane, (unsigned)it);
+                if (did) apply_slot(c, i, (unsigned)it);
                 add_progress(did);
             }
         }
@@ -1132,8 +1162,11 @@ struct SyltWorld {
     DBuf<int2> jrank;
     DBuf<int> uncolored, uncolored2, prop, order;
     DBuf<Counters> counters;
-    DBuf<int> tot32;
-    DBuf<unsigned long long> tot64;
+    DBuf<int> sincl32, scan_ticket;
+    DBuf<unsigned long long> sincl64;
+    DBuf<unsigned> scan_flag;
+    unsigned scan_epoch = 0;
+    bool cells_clean = false;  // cell_count is all zero (the cell scan re-zeroes what it reads)
     // arbiters, double buffered
     struct ArbBufs {
         DBuf<int2> bodies, meta;
@@ -1179,13 +1212,16 @@ int use_device(SyltWorld* w) {
 }
 
 template <typename T>
-int run_scan(SyltWorld* w, const T* in, T* out, int n_bound, const int* n_dev, T* partial, T* total) {
+int run_scan(SyltWorld* w, T* in, T* out, int n_bound, const int* n_dev, T* agg, T* incl, int zero_in, int totals_mode) {
     int nb = (n_bound + SCAN_TILE - 1) / SCAN_TILE;
     if (nb < 1) nb = 1;
-    k_scan_reduce<T><<<nb, SCAN_THREADS, 0, w->stream>>>(in, n_bound, n_dev, partial);
-    k_scan_partials<T><<<1, SCAN_THREADS, 0, w->stream>>>(partial, n_bound, n_dev, total);
-    k_scan_apply<T><<<nb, SCAN_THREADS, 0, w->stream>>>(in, out, n_bound, n_dev, partial, total);
-    w->launches += 3;
+    if (w->scan_epoch >= 0x3ffffff0u) {  // 30-bit epochs: start over with clean flags
+        SYLT_CUDA(cudaMemsetAsync(w->scan_flag.p, 0, w->scan_flag.cap * sizeof(unsigned), w->stream));
+        w->scan_epoch = 0;
+    }
+    k_scan_lookback<T><<<nb, SCAN_THREADS, 0, w->stream>>>(in, out, n_bound, n_dev, w->scan_flag.p, agg, incl, w->scan_ticket.p, ++w->scan_epoch,
+                                                           zero_in, w->counters.p, totals_mode, (int)w->cap_pairs);
+    w->launches++;
     SYLT_CUDA(cudaGetLastError());
     return SYLT_OK;
 }
@@ -1325,12 +1361,16 @@ int flush(SyltWorld* w) {
         w->buckets = buckets;
         w->gp.cell = cell;
         w->gp.mask = buckets - 1;
+        if ((size_t)buckets + 1 > w->cell_count.cap) w->cells_clean = false;
         SYLT_CUDA(w->cell_count.ensure((size_t)buckets + 1));
         SYLT_CUDA(w->cell_start.ensure((size_t)buckets + 2));
         size_t sp = ((size_t)std::max<size_t>(buckets, B + 1) + SCAN_TILE - 1) / SCAN_TILE + 1;
         SYLT_CUDA(w->spart32.ensure(sp));
-        SYLT_CUDA(w->tot32.ensure(4));
-        SYLT_CUDA(w->tot64.ensure(4));
+        SYLT_CUDA(w->sincl32.ensure(sp));
+        if (!w->scan_ticket.p) {
+            SYLT_CUDA(w->scan_ticket.ensure(1));
+            SYLT_CUDA(cudaMemsetAsync(w->scan_ticket.p, 0, sizeof(int), w->stream));
+        }
         SYLT_CUDA(w->counters.ensure(1));
         if (w->have_old && w->B_old > 0)  // keep the flags the last step used for the next arbiter match
             SYLT_CUDA(cudaMemcpyAsync(w->bflags_old.p, w->bflags.p, (size_t)w->B_old * sizeof(int), cudaMemcpyDeviceToDevice, w->stream));
@@ -1347,6 +1387,15 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->info.ensure((size_t)cp + 1));
         SYLT_CUDA(w->pscan.ensure((size_t)cp + 2));
         SYLT_CUDA(w->spart64.ensure((size_t)cp / SCAN_TILE + 2));
+        SYLT_CUDA(w->sincl64.ensure((size_t)cp / SCAN_TILE + 2));
+        {
+            const size_t nf = std::max(sp, (size_t)cp / SCAN_TILE + 2);
+            if (nf > w->scan_flag.cap) {
+                SYLT_CUDA(w->scan_flag.ensure(nf));
+                SYLT_CUDA(cudaMemsetAsync(w->scan_flag.p, 0, w->scan_flag.cap * sizeof(unsigned), w->stream));
+                w->scan_epoch = 0;
+            }
+        }
         SYLT_CUDA(w->tmp_a.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->tmp_b.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->uncolored.ensure((size_t)ca));
@@ -1409,25 +1458,26 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     Counters* cn = w->counters.p;
     SYLT_CUDA(cudaMemsetAsync(&cn->n_pairs, 0, sizeof(Counters) - offsetof(Counters, n_pairs), st));
     if (B == 0) return SYLT_OK;
-    SYLT_CUDA(cudaMemsetAsync(w->cell_count.p, 0, (size_t)w->buckets * sizeof(int), st));
-    SYLT_CUDA(cudaMemsetAsync(w->used.p, 0, (size_t)B * sizeof(unsigned long long), st));
+    if (!w->cells_clean) {
+        SYLT_CUDA(cudaMemsetAsync(w->cell_count.p, 0, w->cell_count.cap * sizeof(int), st));
+        w->cells_clean = true;
+    }
     const int nbB = (B + 255) / 256;
     k_prepare<<<nbB, 256, 0, st>>>(B, w->pose.p, w->vel.p, w->force.p, w->mp.p, w->geom.p, w->bflags.p, w->lverts.p, w->rotc.p, w->aabb.p,
-                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p);
+                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p, w->used.p);
     w->launches++;
-    int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->tot32.p);
+    int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
     if (e) return e;
     k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->gp);
     const int nbR = (B + 127) / 128;
     k_rows_count<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->large.p, w->n_large, w->gp,
                                       w->row_count.p, w->row_tmp.p);
     w->launches += 2;
-    e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->tot32.p + 1);
+    e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->sincl32.p, 0, 1);
     if (e) return e;
-    k_totals<<<1, 1, 0, st>>>(cn, w->tot32.p + 1, nullptr, 0, (int)w->cap_pairs);
     k_rows_emit<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->large.p, w->n_large, w->gp,
                                      w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn);
-    w->launches += 2;
+    w->launches += 1;
     const int gridP = w->num_sms * 8;
     if (w->any_poly)
         k_narrow<MAX_MANIFOLD><<<gridP, 128, 0, st>>>(cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p, w->lverts.p,
@@ -1436,9 +1486,8 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         k_narrow<2><<<gridP, 128, 0, st>>>(cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p, w->lverts.p,
                                            w->info.p, w->tmp_a.p, w->tmp_b.p, cn);
     w->launches++;
-    e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->tot64.p);
+    e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->sincl64.p, 0, 2);
     if (e) return e;
-    k_totals<<<1, 1, 0, st>>>(cn, nullptr, w->tot64.p, 1, 0);
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
     if (w->any_poly)
         k_build<MAX_MANIFOLD><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p,
@@ -1448,7 +1497,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         k_build<2><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p, w->info.p,
                                                    w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur,
                                                    old, w->warm, w->used.p, w->uncolored.p, w->fix_features);
-    w->launches += 2;
+    w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
 
     SolveArgs a;
@@ -1589,7 +1638,7 @@ static void free_all(SyltWorld* w) {
     w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->cent_aabb.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
     w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
-    w->prop.release(); w->order.release(); w->tot32.release(); w->tot64.release();
+    w->prop.release(); w->order.release(); w->sincl32.release(); w->sincl64.release(); w->scan_flag.release(); w->scan_ticket.release();
     for (int k = 0; k < 2; k++) {
         auto& a = w->arb[k];
         a.bodies.release(); a.meta.release(); a.partner.release(); a.color.release(); a.row_start.release(); a.friction.release();
