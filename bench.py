@@ -336,6 +336,18 @@ def main():
             roof["traffic"] = (tj.get("dram_bytes_per_world_base", 0) + tj.get("dram_bytes_per_world_per_step", 0) * args.steps) * my_worlds
         except Exception:
             pass
+    # what actually limits the kernel is on-chip: quote the ncu utilisations of the committed capture beside the HBM figure
+    sp = os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")
+    if os.path.exists(sp):
+        try:
+            with open(sp) as f:
+                sj = json.load(f)
+            kb = next(v for k, v in sj.items() if k.startswith("k_batch_step"))
+            roof["on_chip"] = {"issue_slots_busy_pct": float(kb["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
+                               "shared_memory_pipe_busy_pct": float(kb["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0]),
+                               "source": "profiles/r02_ncu_full_summary.json (ncu --set full, 4096 worlds x 4 steps)"}
+        except Exception:
+            pass
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
