@@ -239,3 +239,66 @@ def test_oracle_grid_broad_phase_equals_all_pairs(seed):
     assert a.get_bodies().tobytes() == b.get_bodies().tobytes()
     (aa, ac), (ba, bc) = a.get_arbiters(), b.get_arbiters()
     assert aa.shape[0] > 100 and aa.tobytes() == ba.tobytes() and ac.tobytes() == bc.tobytes()
+
+
+# ------------------------------------------------------------------ World::step: C++ oracle vs the numpy-f32 restatement
+def _np_vs_cpp(scene, steps, mode=1, ctx=None):
+    """Both restatements step the same scene in canonical (id1, id2) order; every body state and every contact's
+    accumulated impulses must agree bit for bit after every step."""
+    from oracle import step_np
+    if ctx is not None:
+        scene.ctx = ctx
+    o = orc.OracleWorld(scene.gravity, scene.iterations, sincos_mode=mode)
+    o.load_scene(scene)
+    w = step_np.NpWorld(scene.gravity, scene.iterations, _sincos(mode), scene.ctx)
+    w.load_scene(scene, o.get_body_props())
+    n_contacts = 0
+    for s in range(steps):
+        o.step(scene.dt)
+        assert w.step(scene.dt)
+        got = o.get_bodies()
+        exp = w.state()
+        for k, f in enumerate(("x", "y", "rotation", "vx", "vy", "angular_velocity")):
+            assert np.array_equal(got[f].view(np.uint32), exp[:, k].view(np.uint32)), (scene.name, s, f)
+        arb, con = o.get_arbiters()
+        keys = sorted(w.arbiters)
+        assert [tuple(k) for k in zip(arb["id1"].tolist(), arb["id2"].tolist())] == keys, (scene.name, s)
+        flat = [c for k in keys for c in w.arbiters[k]["contacts"]]
+        assert len(flat) == con.shape[0]
+        for f in ("pn", "pt", "mass_normal", "mass_tangent", "bias", "separation"):
+            src = {"mass_normal": "mass_n", "mass_tangent": "mass_t", "separation": "sep"}.get(f, f)
+            exp_f = np.array([c[src] for c in flat], dtype=np.float32)
+            assert np.array_equal(con[f].view(np.uint32), exp_f.view(np.uint32)), (scene.name, s, f)
+        n_contacts = max(n_contacts, len(flat))
+    return n_contacts
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_step_pyramid_bit_exact_vs_numpy(mode):
+    from sylt2d_b200 import scenes
+    assert _np_vs_cpp(scenes.pyramid(4, 10), 70, mode) >= 16
+
+
+@pytest.mark.parametrize("ctx", [(True, False, True), (False, True, True), (True, True, False), (False, False, False)])
+def test_step_context_flags_bit_exact_vs_numpy(ctx):
+    from sylt2d_b200 import scenes
+    assert _np_vs_cpp(scenes.pyramid(3, 6), 60, 1, ctx) >= 8
+
+
+def test_step_joints_bit_exact_vs_numpy():
+    from sylt2d_b200 import scenes
+    _np_vs_cpp(scenes.bridge(10, omega0=0.5), 40)
+    _np_vs_cpp(scenes.multi_pendulum(10, omega0=0.7), 40)
+    _np_vs_cpp(scenes.demo2(10), 40)  # single pendulum, hard joint
+
+
+def test_step_polygons_and_boxes_bit_exact_vs_numpy():
+    from sylt2d_b200 import scenes
+    b = scenes._Builder()
+    scenes._ground(b)
+    b.polygon(scenes.HEXAGON, 5.0, 0.3, (-2.0, 1.2), 0.1)
+    b.box(1.0, 1.0, 10.0, 0.2, (0.0, 0.6), 0.0)
+    b.polygon(scenes.PENTAGON, 4.0, 0.4, (0.2, 2.3), -0.3, (0.0, -1.0), 0.5)
+    b.box(1.5, 0.5, 6.0, 0.5, (2.0, 0.4), 0.05)
+    b.polygon(scenes.regular_ngon(3, 0.8), 3.0, 0.2, (2.1, 1.6), 0.4)
+    assert _np_vs_cpp(b.scene("mixed", iterations=10), 60) >= 4
