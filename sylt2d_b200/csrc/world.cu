@@ -49,6 +49,8 @@ void set_last_error(const std::string& s) {
 namespace {
 
 constexpr int NC = 64;          // max arbiter colours (one bit each in the per-body 64-bit `used` mask)
+constexpr int GEN_BIT = 32;     // region solver: colours [0, GEN_BIT) are interior colours (bits of `used_int`), colour GEN_BIT + k is bit k of `used`
+constexpr int NCX = NC + GEN_BIT;
 constexpr int MAX_ROUNDS = 256; // colouring rounds per step (only new arbiters take part)
 constexpr int FLAG_POLY = 1, FLAG_LARGE = 2, FLAG_STATIC = 4;
 
@@ -59,11 +61,16 @@ struct Counters {
     // per step (reset by enqueue_step):
     int n_pairs, n_arb, n_con;
     int n_colors, rounds, n_uncolored, warn_ext;
-    int color_count[NC];
+    int color_count[NCX];
     int color_start[NC + 1];
     int color_fill[NC];
     int remaining[MAX_ROUNDS];
     unsigned bar;  // grid barrier arrivals of this step's k_solve
+    // region solver (k_solve_regions):
+    int order_alloc;                // next free entry of the `order` array (every CTA takes one private segment)
+    int n_generic;                  // arbiters solved through the versioned records in L2 (cross-region and overflow colours)
+    unsigned long long color_mask;  // generic colours in use
+    unsigned color_mask_int;        // interior colours in use
 };
 
 // ------------------------------------------------------------------ device-wide exclusive scan (single pass, k_scan_lookback)
@@ -128,10 +135,11 @@ __device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
 __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* vel, const float4* force, const float4* mp, const float4* geom,
                                                  const int* bflags, const float2* lverts, float2* rotc, float4* aabb, int4* cinfo,
                                                  int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
-                                                 Counters* cn, ulonglong2* vrec, unsigned long long* used) {
+                                                 Counters* cn, ulonglong2* vrec, unsigned long long* used, unsigned* used_int) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     used[i] = 0ull;  // colours taken at this body: rebuilt by k_build / the colouring rounds every step
+    used_int[i] = 0u;
     float4 p = pose[i];
     float4 m = mp[i];
     float4 g = geom[i];
@@ -366,11 +374,11 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int2* pairs, const unsigned long long* info, const unsigned long long* scan,
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
-                                               unsigned long long* used, int* uncolored, int fix_features) {
+                                               unsigned long long* used, int* uncolored, int fix_features, int keep_colors, unsigned* used_int, int regions) {
     int P = min(cn->n_pairs, cap_pairs);
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    __shared__ int s_hist[NC];
-    if (threadIdx.x < NC) s_hist[threadIdx.x] = 0;
+    __shared__ int s_hist[NCX];
+    if (threadIdx.x < NCX) s_hist[threadIdx.x] = 0;
     __syncthreads();
     for (int i = tid; i <= B; i += nth) {
         int rs = i < B ? min(row_start[i], P) : P;
@@ -399,7 +407,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         int color = -1;
         if (found >= 0) {
             fr = old.friction[found];  // quirk Q-17: friction fixed at first insertion
-            color = old.color[found];
+            if (keep_colors) color = old.color[found];  // dropped once after every repartition (the colour carries the arbiter's class)
             if (warm) {                // quirk Q-2: every new contact inherits old contact 0
                 int oc = old.meta[found].y;
                 float4 c = old.cc[oc];
@@ -433,15 +441,22 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
             cur.cd[coff + k] = make_float4(ta.x, ta.y, pnb, tb.y);
         }
         if (color >= 0) {
-            if (!(bflags[b1] & FLAG_STATIC)) atomicOr(&used[b1], 1ull << color);
-            if (!(bflags[b2] & FLAG_STATIC)) atomicOr(&used[b2], 1ull << color);
+            const bool d1 = !(bflags[b1] & FLAG_STATIC), d2 = !(bflags[b2] & FLAG_STATIC);
+            if (regions && color < GEN_BIT) {
+                if (d1) atomicOr(&used_int[b1], 1u << color);
+                if (d2) atomicOr(&used_int[b2], 1u << color);
+            } else {
+                const int bit = regions ? color - GEN_BIT : color;
+                if (d1) atomicOr(&used[b1], 1ull << bit);
+                if (d2) atomicOr(&used[b2], 1ull << bit);
+            }
             atomicAdd(&s_hist[color], 1);
         } else {
             uncolored[atomicAdd(&cn->n_uncolored, 1)] = a;
         }
     }
     __syncthreads();
-    if (threadIdx.x < NC && s_hist[threadIdx.x]) atomicAdd(&cn->color_count[threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x < NCX && s_hist[threadIdx.x]) atomicAdd(&cn->color_count[threadIdx.x], s_hist[threadIdx.x]);
 }
 
 template <typename T>
@@ -542,7 +557,8 @@ struct SolveArgs {
     const int* bflags;
     ArbSet cur;
     unsigned long long* used;
-    unsigned long long* claim;  // B * NC
+    unsigned* used_int;         // region solver: interior colours taken at a body
+    unsigned long long* claim;  // B * NCX
     int *uncolored, *uncolored2, *prop, *order;
     ulonglong2* vrec;           // 2 per body: versioned velocities (see k_prepare)
     int sleep_ns;               // back-off between polls of the dataflow wait (0 = spin)
@@ -559,6 +575,9 @@ struct SolveArgs {
     float4 *jr, *jm;         // (r1, r2), M
     float2* jbias;
     const int *jorder, *jcolor_start;
+    // regions (k_solve_regions): every body belongs to one region, region r is solved by CTA r
+    const int *region_of, *lidx, *reg_start, *reg_bodies;  // body -> region, body -> index inside its region, CSR of the regions
+    int n_regions, rbcap;                                  // rbcap: shared-memory room for the bodies of one region
 };
 
 __device__ __forceinline__ Vel load_vel(const float4* vel, int b) {
@@ -646,6 +665,92 @@ struct BodyIO {
     }
 };
 
+// Colour the arbiters that are new this step (persisting ones kept their colour in k_build): lowest free colour,
+// conflicts between new arbiters resolved by a hashed priority (64-bit atomicMin claims per body and colour, stamped
+// with a round epoch so nothing is ever cleared).  A handful of new arbiters (the usual case in a settled scene) is
+// coloured by CTA 0 alone with block barriers; a flood (scene start) by the grid.  On return every CTA sees the final
+// colours and `used` masks.
+// REGIONS: colours below GEN_BIT are "interior" colours, reserved for arbiters whose dynamic bodies all live in the
+// region of the pair's owner body (k_solve_regions solves those in shared memory); every other arbiter, and an interior
+// candidate that finds no free interior colour, takes a colour >= GEN_BIT ("generic": solved through the versioned
+// records in L2).  The class of an arbiter IS its colour range, so it persists with the colour.
+template <bool REGIONS>
+__device__ __forceinline__ void color_new_arbiters(const SolveArgs& a, Counters* cn, unsigned* bar, unsigned& bar_target) {
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int T = blockDim.x, bid = blockIdx.x, lt = threadIdx.x;
+    const int nunc = *(volatile int*)&cn->n_uncolored;
+    if (nunc > 0) {
+        // round r reads the list L[r & 1] (n entries); arbiters that lose a claim append themselves to the other list,
+        // whose length is counted in cn->remaining[r].  The grid runs the rounds while many arbiters are left, then
+        // CTA 0 finishes the stragglers alone with block barriers while the others wait at one grid barrier.
+        int* lists[2] = {a.uncolored, a.uncolored2};
+        int n = nunc;
+        bool solo = n <= T;  // block-uniform and identical in every CTA (one entry per thread of CTA 0)
+        int round = 0;
+        for (; round < MAX_ROUNDS; round++) {
+            if (solo && bid != 0) break;
+            const int ct = solo ? lt : tid, cs = solo ? T : nth;
+            const int* cur_list = lists[round & 1];
+            int* next_list = lists[(round + 1) & 1];
+            const unsigned long long ep = (unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32;
+            for (int k = ct; k < n; k += cs) {
+                int e = __ldcg(&cur_list[k]);
+                int2 b = a.cur.bodies[e];
+                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
+                unsigned long long m = (d1 ? __ldcg(&a.used[b.x]) : 0ull) | (d2 ? __ldcg(&a.used[b.y]) : 0ull);
+                unsigned long long fr = ~m;
+                int c = -1;
+                if (REGIONS) {
+                    const int owner = a.cur.partner[e] == b.x ? b.y : b.x;
+                    const int R = a.region_of[owner];
+                    const bool interior = (!d1 || a.region_of[b.x] == R) && (!d2 || a.region_of[b.y] == R);
+                    const unsigned fi = interior ? ~((d1 ? __ldcg(&a.used_int[b.x]) : 0u) | (d2 ? __ldcg(&a.used_int[b.y]) : 0u)) : 0u;
+                    if (fi) c = __ffs((int)fi) - 1;                             // lowest free interior colour
+                    else if (fr) c = GEN_BIT + __ffsll((long long)fr) - 1;      // lowest free generic colour
+                } else if (fr) {
+                    c = __ffsll((long long)fr) - 1;  // lowest free colour
+                }
+                if (c < 0) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[e] = -1; continue; }
+                a.prop[e] = c;
+                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
+                if (d1) atomicMin(&a.claim[(size_t)b.x * NCX + c], val);
+                if (d2) atomicMin(&a.claim[(size_t)b.y * NCX + c], val);
+            }
+            if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
+            for (int k = ct; k < n; k += cs) {
+                int e = __ldcg(&cur_list[k]);
+                int c = __ldcg(&a.prop[e]);
+                if (c < 0) continue;
+                int2 b = a.cur.bodies[e];
+                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
+                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
+                bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NCX + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NCX + c]) == val);
+                if (win) {
+                    a.cur.color[e] = c;
+                    if (REGIONS && c < GEN_BIT) {
+                        if (d1) atomicOr(&a.used_int[b.x], 1u << c);
+                        if (d2) atomicOr(&a.used_int[b.y], 1u << c);
+                    } else {
+                        const int bit = REGIONS ? c - GEN_BIT : c;
+                        if (d1) atomicOr(&a.used[b.x], 1ull << bit);
+                        if (d2) atomicOr(&a.used[b.y], 1ull << bit);
+                    }
+                    atomicAdd(&cn->color_count[c], 1);
+                } else {
+                    next_list[atomicAdd(&cn->remaining[round], 1)] = e;
+                }
+            }
+            if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
+            n = *(volatile int*)&cn->remaining[round];
+            if (n == 0) break;
+            if (n <= T) solo = true;  // the stragglers are CTA 0's job; the others go and wait
+        }
+        if (bid == 0 && lt == 0) cn->rounds = round + 1;
+        if (solo) grid_barrier(bar, bar_target);  // everybody waits for CTA 0's colours
+    }
+
+}
+
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     Counters* cn = a.cn;
@@ -671,64 +776,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     float4* s_cb = s_ca + CONCAP;
     float4* s_cc = s_cb + CONCAP;
 
-    // ---- 1. colour the arbiters that are new this step (persisting ones kept their colour in k_build): lowest free
-    //         colour, conflicts between new arbiters resolved by a hashed priority (64-bit atomicMin claims per body
-    //         and colour, stamped with a round epoch so nothing is ever cleared).  A handful of new arbiters (the usual
-    //         case in a settled scene) is coloured by CTA 0 alone with block barriers; a flood (scene start) by the grid.
-    const int nunc = *(volatile int*)&cn->n_uncolored;
-    if (nunc > 0) {
-        // round r reads the list L[r & 1] (n entries); arbiters that lose a claim append themselves to the other list,
-        // whose length is counted in cn->remaining[r].  The grid runs the rounds while many arbiters are left, then
-        // CTA 0 finishes the stragglers alone with block barriers while the others wait at one grid barrier.
-        int* lists[2] = {a.uncolored, a.uncolored2};
-        int n = nunc;
-        bool solo = n <= T;  // block-uniform and identical in every CTA (one entry per thread of CTA 0)
-        int round = 0;
-        for (; round < MAX_ROUNDS; round++) {
-            if (solo && bid != 0) break;
-            const int ct = solo ? lt : tid, cs = solo ? T : nth;
-            const int* cur_list = lists[round & 1];
-            int* next_list = lists[(round + 1) & 1];
-            const unsigned long long ep = (unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32;
-            for (int k = ct; k < n; k += cs) {
-                int e = __ldcg(&cur_list[k]);
-                int2 b = a.cur.bodies[e];
-                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
-                unsigned long long m = (d1 ? __ldcg(&a.used[b.x]) : 0ull) | (d2 ? __ldcg(&a.used[b.y]) : 0ull);
-                unsigned long long fr = ~m;
-                if (!fr) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[e] = -1; continue; }
-                int c = __ffsll((long long)fr) - 1;  // lowest free colour
-                a.prop[e] = c;
-                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
-                if (d1) atomicMin(&a.claim[(size_t)b.x * NC + c], val);
-                if (d2) atomicMin(&a.claim[(size_t)b.y * NC + c], val);
-            }
-            if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
-            for (int k = ct; k < n; k += cs) {
-                int e = __ldcg(&cur_list[k]);
-                int c = __ldcg(&a.prop[e]);
-                if (c < 0) continue;
-                int2 b = a.cur.bodies[e];
-                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
-                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
-                bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NC + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NC + c]) == val);
-                if (win) {
-                    a.cur.color[e] = c;
-                    if (d1) atomicOr(&a.used[b.x], 1ull << c);
-                    if (d2) atomicOr(&a.used[b.y], 1ull << c);
-                    atomicAdd(&cn->color_count[c], 1);
-                } else {
-                    next_list[atomicAdd(&cn->remaining[round], 1)] = e;
-                }
-            }
-            if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
-            n = *(volatile int*)&cn->remaining[round];
-            if (n == 0) break;
-            if (n <= T) solo = true;  // the stragglers are CTA 0's job; the others go and wait
-        }
-        if (bid == 0 && lt == 0) cn->rounds = round + 1;
-        if (solo) grid_barrier(bar, bar_target);  // everybody waits for CTA 0's colours
-    }
+    color_new_arbiters<false>(a, cn, bar, bar_target);
 
     stamp(1);
     // ---- 2. colour-major order (within a colour the order is irrelevant: disjoint dynamic bodies) and this CTA's share
@@ -1073,6 +1121,418 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     stamp(7);
 }
 
+// ------------------------------------------------------------------ region solver
+// The same sequential sweep as k_solve — passes x (colours ascending, then joints) — with a different execution plan.
+// Bodies are partitioned into compact spatial regions (host side, `repartition`), region r belongs to CTA r for the
+// whole solve and its body velocities live in that CTA's shared memory.  Per pass a CTA
+//   1. imports its boundary bodies (bodies that also carry generic constraints) from their versioned L2 records,
+//   2. sweeps its interior colours (< GEN_BIT) in shared memory, one __syncthreads() per colour,
+//   3. exports the boundary bodies (version + 1),
+//   4. solves its generic arbiters (colours >= GEN_BIT: cross-region pairs) and its share of the joints through the
+//      versioned records, exactly as k_solve does for everything.
+// Interior arbiters of different regions touch disjoint dynamic bodies, so running the regions side by side IS the
+// sequential (pass, colour) order; only ~ the cross-region colours of a pass are L2-latency hops.  Version of a
+// boundary body with Dg generic constraints: pass*(Dg+1) at the start of a pass, +1 by the export, +1 per generic
+// constraint in colour order.
+struct RSlot {
+    int r1, r2, n;         // interior: index into the region's bodies | VSTATIC; generic: global body index | VSTATIC
+    unsigned ord;          // generic: Dv1 | rank1 << 8 | Dv2 << 16 | rank2 << 24
+    float fr;
+    float svx, svy, svw, sii;  // interior: velocity and inv_moi of the static body of the pair (if any)
+    float4 *ca, *cb, *cc;
+};
+
+__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    Counters* cn = a.cn;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    const int T = blockDim.x, bid = blockIdx.x, lt = threadIdx.x, lane = lt & 31;
+    const int A = min(*(volatile int*)&cn->n_arb, a.cap_arb);
+    unsigned bar_target = 0;
+    unsigned* bar = &cn->bar;
+    auto stamp = [&](int k) {
+        if (a.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[k] = t; }
+    };
+    stamp(0);
+    __shared__ int s_cnt[NCX], s_fill[NCX], s_cstart[NCX + 1], s_clist[NCX];
+    __shared__ int s_ncl, s_nint, s_nbnd, s_obase, s_L;
+    __shared__ int s_scan[34];
+    // shared-memory carve-up: region bodies, boundary list, slot records, contact scan scratch, contacts
+    const int RBCAP = a.rbcap, SLOTCAP = a.smem_slots, CONCAP = a.smem_contacts;
+    float4* s_bv = (float4*)sm_raw;                       // (vx, vy, w, -)
+    float2* s_bm = (float2*)(s_bv + RBCAP);               // (inv_mass, inv_moi)
+    int* s_bnd = (int*)(s_bm + RBCAP);                    // boundary bodies: local index | Dv << 20
+    int* s_bndg = s_bnd + RBCAP;                          //                  global index
+    float4* s_rec = (float4*)(s_bndg + RBCAP);
+    int* s_n = (int*)(s_rec + 2 * (size_t)SLOTCAP);
+    float4* s_ca = (float4*)(s_n + ((SLOTCAP + 3) & ~3));
+    float4* s_cb = s_ca + CONCAP;
+    float4* s_cc = s_cb + CONCAP;
+
+    color_new_arbiters<true>(a, cn, bar, bar_target);
+    stamp(1);
+
+    // ---- 2. the region's bodies into shared memory; its arbiters (the rows its bodies own) binned by colour
+    BodyIO io{a.vrec, a.sleep_ns, &cn->err};
+    const int rb0 = bid < a.n_regions ? a.reg_start[bid] : 0;
+    const int nb = bid < a.n_regions ? a.reg_start[bid + 1] - rb0 : 0;
+    if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; }
+    if (lt == 0) s_nbnd = 0;
+    __syncthreads();
+    for (int lb = lt; lb < nb; lb += T) {
+        const int b = a.reg_bodies[rb0 + lb];
+        Vel v;
+        float im, ii;
+        io.get(b, v, im, ii);
+        const bool dyn = !(a.bflags[b] & FLAG_STATIC);
+        const int dg = dyn ? __popcll(__ldcg(&a.used[b])) + a.jdeg[b] : 0;
+        s_bv[lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
+        s_bm[lb] = make_float2(im, ii);
+        if (dg) {
+            const int k = atomicAdd(&s_nbnd, 1);
+            s_bnd[k] = lb | ((dg + 1) << 20);
+            s_bndg[k] = b;
+        }
+        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
+        for (int e = e0; e < e1; e++) {
+            const int c = __ldcg(&a.cur.color[e]);
+            if (c >= 0) atomicAdd(&s_cnt[c], 1);
+        }
+    }
+    __syncthreads();
+    if (lt == 0) {
+        int run = 0, ncl = 0, nint = 0, ngen = 0;
+        unsigned long long mask = 0ull;
+        unsigned mask_int = 0u;
+        for (int c = 0; c < NCX; c++) {
+            s_cstart[c] = run;
+            if (s_cnt[c]) {
+                if (c < GEN_BIT) mask_int |= 1u << c; else mask |= 1ull << (c - GEN_BIT);
+                s_clist[ncl++] = c;
+                if (c < GEN_BIT) nint++; else ngen += s_cnt[c];
+            }
+            run += s_cnt[c];
+        }
+        s_cstart[NCX] = run;
+        s_ncl = ncl; s_nint = nint; s_L = run;
+        s_obase = run ? atomicAdd(&cn->order_alloc, run) : 0;
+        if (mask) atomicOr(&cn->color_mask, mask);
+        if (mask_int) atomicOr(&cn->color_mask_int, mask_int);
+        if (ngen) atomicAdd(&cn->n_generic, ngen);
+    }
+    __syncthreads();
+    if (!a.run_solver) return;
+    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // e.g. an arbiter without a free colour: no solve, error reported
+    const int L = s_L, ncl = s_ncl, nint = s_nint, nbnd = s_nbnd;
+    int* order = a.order + s_obase;  // this CTA's slots, colour-major (within a colour the order is irrelevant)
+    for (int lb = lt; lb < nb; lb += T) {
+        const int b = a.reg_bodies[rb0 + lb];
+        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
+        for (int e = e0; e < e1; e++) {
+            const int c = __ldcg(&a.cur.color[e]);
+            if (c >= 0) order[s_cstart[c] + atomicAdd(&s_fill[c], 1)] = e;
+        }
+    }
+    __syncthreads();
+    const bool acc = a.accumulate != 0;
+    const float kbias = a.poscorr ? 0.2f : 0.0f;
+
+    stamp(2);
+    // ---- 3. residency: slot records and contact constants of the owned slots into shared memory
+    const int Ls = min(L, SLOTCAP);
+    for (int ls = lt; ls < Ls; ls += T) s_n[ls] = a.cur.meta[__ldcg(&order[ls])].x;
+    __syncthreads();
+    {   // in-place exclusive scan of s_n[0..Ls)
+        const int chunk = (Ls + T - 1) / T, q0 = min(lt * chunk, Ls), q1 = min(q0 + chunk, Ls);
+        int sum = 0;
+        for (int k = q0; k < q1; k++) sum += s_n[k];
+        int tot;
+        int ex = block_excl_scan<int>(sum, &tot, s_scan);
+        for (int k = q0; k < q1; k++) { int t = s_n[k]; s_n[k] = ex; ex += t; }
+    }
+    __syncthreads();
+    // what a slot needs besides its contacts (from the global arrays)
+    auto describe = [&](int e, int c, RSlot& v) {
+        const int2 b = a.cur.bodies[e];
+        const bool st1 = (a.bflags[b.x] & FLAG_STATIC) != 0, st2 = (a.bflags[b.y] & FLAG_STATIC) != 0;
+        v.n = a.cur.meta[e].x;
+        v.fr = a.cur.friction[e];
+        v.ord = 0u; v.svx = v.svy = v.svw = v.sii = 0.0f;
+        if (c < GEN_BIT) {
+            v.r1 = st1 ? VSTATIC : a.lidx[b.x];
+            v.r2 = st2 ? VSTATIC : a.lidx[b.y];
+            if (st1 || st2) {
+                Vel sv;
+                float sim;
+                io.get(st1 ? b.x : b.y, sv, sim, v.sii);
+                v.svx = sv.v.x; v.svy = sv.v.y; v.svw = sv.w;
+            }
+        } else {
+            v.r1 = b.x | (st1 ? VSTATIC : 0);
+            v.r2 = b.y | (st2 ? VSTATIC : 0);
+            const unsigned long long u1 = __ldcg(&a.used[b.x]), u2 = __ldcg(&a.used[b.y]);
+            const unsigned long long lower = (1ull << (c - GEN_BIT)) - 1ull;
+            const unsigned d1 = (unsigned)(__popcll(u1) + a.jdeg[b.x] + 1), d2 = (unsigned)(__popcll(u2) + a.jdeg[b.y] + 1);
+            v.ord = (d1 & 0xffu) | ((unsigned)__popcll(u1 & lower) << 8) | ((d2 & 0xffu) << 16) | ((unsigned)__popcll(u2 & lower) << 24);
+        }
+    };
+    for (int k = 0; k < ncl; k++) {
+        const int c = s_clist[k], cnt = s_cnt[c];
+        for (int i = lt; i < cnt; i += T) {
+            const int ls = s_cstart[c] + i;
+            if (ls >= SLOTCAP) continue;
+            const int e = __ldcg(&order[ls]);
+            RSlot v;
+            describe(e, c, v);
+            const int coff = a.cur.meta[e].y, lc = s_n[ls];
+            const bool res = lc + v.n <= CONCAP;
+            s_rec[2 * ls] = make_float4(__int_as_float(v.r1), __int_as_float(v.r2), __int_as_float(res ? (lc << 8) | v.n : -1), v.fr);
+            s_rec[2 * ls + 1] = c < GEN_BIT ? make_float4(v.svx, v.svy, v.svw, v.sii) : make_float4(__uint_as_float(v.ord), 0.0f, 0.0f, 0.0f);
+            if (res)
+                for (int q = 0; q < v.n; q++) {
+                    s_ca[lc + q] = a.cur.ca[coff + q];
+                    s_cc[lc + q] = a.cur.cc[coff + q];
+                }
+        }
+    }
+    __syncthreads();
+
+    auto view = [&](int c, int ls, RSlot& v) {
+        if (ls < SLOTCAP) {
+            const float4 r0 = s_rec[2 * ls];
+            const int pk = __float_as_int(r0.z);
+            if (pk >= 0) {
+                v.r1 = __float_as_int(r0.x); v.r2 = __float_as_int(r0.y); v.n = pk & 0xff; v.fr = r0.w;
+                if (c < GEN_BIT) {
+                    if ((v.r1 | v.r2) & VSTATIC) { const float4 r1 = s_rec[2 * ls + 1]; v.svx = r1.x; v.svy = r1.y; v.svw = r1.z; v.sii = r1.w; }
+                } else {
+                    v.ord = __float_as_uint(s_rec[2 * ls + 1].x);
+                }
+                const int lc = pk >> 8;
+                v.ca = s_ca + lc; v.cb = s_cb + lc; v.cc = s_cc + lc;
+                return;
+            }
+        }
+        const int e = __ldcg(&order[ls]);
+        describe(e, c, v);
+        const int coff = a.cur.meta[e].y;
+        v.ca = a.cur.ca + coff; v.cb = a.cur.cb + coff; v.cc = a.cur.cc + coff;
+    };
+    // body access of an interior slot: shared memory, or the constant velocity of a static body
+    auto iget = [&](const RSlot& v, int r, Vel& o, float& im, float& ii) {
+        if (r & VSTATIC) { o.v = mk(v.svx, v.svy); o.w = v.svw; im = 0.0f; ii = v.sii; }
+        else { const float4 q = s_bv[r]; const float2 m = s_bm[r]; o.v = mk(q.x, q.y); o.w = q.z; im = m.x; ii = m.y; }
+    };
+    auto iput = [&](int r, const Vel& o) {
+        if (!(r & VSTATIC)) s_bv[r] = make_float4(o.v.x, o.v.y, o.w, 0.0f);
+    };
+    auto prestep_contacts = [&](const RSlot& v, int e, float im1, float ii1, float im2, float ii2, Vel& v1, Vel& v2) {
+        const int2 b = a.cur.bodies[e];
+        const int coff = a.cur.meta[e].y;
+        const float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
+        for (int q = 0; q < v.n; q++) {
+            const float4 ca = v.ca[q], cc = v.cc[q], cd = a.cur.cd[coff + q];
+            ContactConst k0;
+            contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, mk(p1.x, p1.y), mk(p2.x, p2.y), im1, ii1, im2, ii2,
+                            a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
+            v.ca[q] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
+            v.cb[q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
+            v.cc[q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
+        }
+    };
+    auto apply_contacts = [&](const RSlot& v, float im1, float ii1, float im2, float ii2, Vel& v1, Vel& v2) {
+        for (int q = 0; q < v.n; q++) {
+            const float4 ca = v.ca[q], cb = v.cb[q], cc = v.cc[q];
+            ContactConst k0;
+            k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
+            k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
+            float pn = cc.y, pt = cc.z;
+            contact_apply(k0, v.fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
+            if (acc) v.cc[q] = make_float4(cc.x, pn, pt, cc.w);
+        }
+    };
+    // one pass over this CTA's slots: interior colours in shared memory, export, generic colours through L2
+    const bool probe = a.dbg != nullptr && bid == (int)gridDim.x / 2 && lt == 0;
+    int pk_ = 16;
+    auto pstamp = [&](unsigned pass) {
+        if (probe && pass == 5u && pk_ < 64) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[pk_++] = t; }
+    };
+    auto sweep = [&](unsigned pass) {
+        pstamp(pass);
+        for (int k = 0; k < nint; k++) {
+            const int c = s_clist[k], cnt = s_cnt[c], base = s_cstart[c];
+            for (int i = lt; i < cnt; i += T) {
+                RSlot v;
+                view(c, base + i, v);
+                Vel v1, v2;
+                float im1, ii1, im2, ii2;
+                iget(v, v.r1, v1, im1, ii1);
+                iget(v, v.r2, v2, im2, ii2);
+                if (pass == 0u) prestep_contacts(v, __ldcg(&order[base + i]), im1, ii1, im2, ii2, v1, v2);
+                else apply_contacts(v, im1, ii1, im2, ii2, v1, v2);
+                iput(v.r1, v1);
+                iput(v.r2, v2);
+            }
+            __syncthreads();
+        }
+        pstamp(pass);
+        for (int k = lt; k < nbnd; k += T) {  // export: version pass*Dv + 1
+            const int pk = s_bnd[k], lb = pk & 0xfffff;
+            const float4 q = s_bv[lb];
+            Vel o; o.v = mk(q.x, q.y); o.w = q.z;
+            io.put(s_bndg[k], o, pass * (unsigned)(pk >> 20) + 1u);
+        }
+        for (int k = nint; k < ncl; k++) {
+            const int c = s_clist[k], cnt = s_cnt[c], base = s_cstart[c];
+            for (int i = lt; i < cnt; i += T) {
+                RSlot v;
+                view(c, base + i, v);
+                const int b1 = v.r1 & ~VSTATIC, b2 = v.r2 & ~VSTATIC;
+                const unsigned e1 = pass * (v.ord & 0xffu) + 1u + ((v.ord >> 8) & 0xffu), e2 = pass * ((v.ord >> 16) & 0xffu) + 1u + (v.ord >> 24);
+                Vel v1, v2;
+                float im1, ii1, im2, ii2;
+                io.wait2(v.r1, e1, v1, im1, ii1, v.r2, e2, v2, im2, ii2);
+                if (pass == 0u) prestep_contacts(v, __ldcg(&order[base + i]), im1, ii1, im2, ii2, v1, v2);
+                else apply_contacts(v, im1, ii1, im2, ii2, v1, v2);
+                if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1u);
+                if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1u);
+            }
+            pstamp(pass);
+        }
+    };
+    // import: the boundary bodies as the generic constraints (and joints) of the previous pass left them
+    auto import_boundary = [&](unsigned pass) {
+        for (int k = lt; k < nbnd; k += T) {
+            const int pk = s_bnd[k], lb = pk & 0xfffff, b = s_bndg[k];
+            const unsigned expect = pass * (unsigned)(pk >> 20);
+            Vel o;
+            float im, ii;
+            unsigned spins = 0;
+            while (!io.try_get(b, expect, true, o, im, ii)) {
+                if ((++spins & 0xfffu) == 0u) {
+                    if (*(volatile int*)&cn->err == SYLT_ERR_INTERNAL) break;
+                    if (spins > (1u << 23)) { atomicExch(&cn->err, SYLT_ERR_INTERNAL); break; }
+                }
+            }
+            s_bv[lb] = make_float4(o.v.x, o.v.y, o.w, 0.0f);
+        }
+        __syncthreads();
+    };
+    auto joint_expect = [&](int j, int2 b, unsigned pass, unsigned& e1, unsigned& e2) {
+        const int2 jr = a.jrank[j];
+        const unsigned da1 = (unsigned)__popcll(__ldcg(&a.used[b.x])), da2 = (unsigned)__popcll(__ldcg(&a.used[b.y]));
+        e1 = pass * (da1 + (unsigned)a.jdeg[b.x] + 1u) + 1u + da1 + (unsigned)jr.x;
+        e2 = pass * (da2 + (unsigned)a.jdeg[b.y] + 1u) + 1u + da2 + (unsigned)jr.y;
+    };
+
+    stamp(3);
+    // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228) then Joint::pre_step (joint.rs:57-115)
+    sweep(0u);
+    for (int c = 0; c < a.n_joint_colors; c++) {
+        for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
+            const int j = a.jorder[k];
+            const int2 b = a.jbodies[j];
+            const float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
+            const float2 r1c = a.rotc[b.x], r2c = a.rotc[b.y];
+            const int r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0), r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
+            unsigned e1, e2;
+            joint_expect(j, b, 0u, e1, e2);
+            Vel v1, v2;
+            float im1, ii1, im2, ii2;
+            io.wait2(r1, e1, v1, im1, ii1, r2, e2, v2, im2, ii2);
+            const float4 la = a.jla[j];
+            const float2 pr = a.jparam[j];
+            const float2 pa = a.jp[j];
+            V2 pacc = mk(pa.x, pa.y);
+            JointConst jc;
+            M2 bad;
+            Vel w1 = v1, w2 = v2;
+            const bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), r1c.x, r1c.y, mk(p2.x, p2.y), r2c.x, r2c.y,
+                                          im1, ii1, im2, ii2, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, w1, w2, jc, &bad, a.fix_inverse != 0);
+            a.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
+            if (!ok) {  // quirk Q-15: NoInverse aborts the step before the iterations
+                if (atomicCAS(&cn->err, 0, SYLT_ERR_NO_INVERSE) == 0) {
+                    cn->err_joint = j;
+                    cn->badk[0] = bad.c1.x; cn->badk[1] = bad.c2.x; cn->badk[2] = bad.c1.y; cn->badk[3] = bad.c2.y;
+                }
+                w1 = v1; w2 = v2;  // velocities untouched, versions still advance so that nobody waits forever
+            } else {
+                a.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
+                a.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
+                a.jp[j] = make_float2(pacc.x, pacc.y);
+            }
+            if (!(r1 & VSTATIC)) io.put(b.x, w1, e1 + 1u);
+            if (!(r2 & VSTATIC)) io.put(b.y, w2, e2 + 1u);
+        }
+    }
+    grid_barrier(bar, bar_target);
+    const bool aborted = *(volatile int*)&cn->err == SYLT_ERR_NO_INVERSE;
+    const int passes = aborted ? 0 : a.iterations;
+    stamp(4);
+
+    // ---- 5. passes 1..I: iterations x (arbiter colours, joint colours)   (world.rs:132-140)
+    for (int it = 1; it <= passes; it++) {
+        pstamp((unsigned)it);
+        import_boundary((unsigned)it);
+        sweep((unsigned)it);
+        for (int c = 0; c < a.n_joint_colors; c++) {
+            for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
+                const int j = a.jorder[k];
+                const int2 b = a.jbodies[j];
+                const int r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0), r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
+                unsigned e1, e2;
+                joint_expect(j, b, (unsigned)it, e1, e2);
+                Vel v1, v2;
+                float im1, ii1, im2, ii2;
+                io.wait2(r1, e1, v1, im1, ii1, r2, e2, v2, im2, ii2);
+                const float4 r = a.jr[j], mm = a.jm[j];
+                const float2 bs = a.jbias[j], pa = a.jp[j];
+                JointConst jc;
+                jc.r1 = mk(r.x, r.y); jc.r2 = mk(r.z, r.w); jc.bias = mk(bs.x, bs.y);
+                jc.m = mk(mk(mm.x, mm.z), mk(mm.y, mm.w));
+                jc.softness = a.jparam[j].x;
+                V2 pacc = mk(pa.x, pa.y);
+                joint_apply(jc, im1, ii1, im2, ii2, pacc, v1, v2);
+                a.jp[j] = make_float2(pacc.x, pacc.y);
+                if (!(r1 & VSTATIC)) io.put(b.x, v1, e1 + 1u);
+                if (!(r2 & VSTATIC)) io.put(b.y, v2, e2 + 1u);
+            }
+        }
+    }
+    import_boundary((unsigned)(passes + 1));
+
+    stamp(5);
+    // ---- 6. write the shared-memory resident contacts back (warm start of the next step, read-back)
+    for (int ls = lt; ls < Ls; ls += T) {
+        const int pk = __float_as_int(s_rec[2 * ls].z);
+        if (pk < 0) continue;
+        const int e = __ldcg(&order[ls]);
+        const int coff = a.cur.meta[e].y, lc = pk >> 8, n = pk & 0xff;
+        for (int q = 0; q < n; q++) {
+            a.cur.ca[coff + q] = s_ca[lc + q];
+            a.cur.cb[coff + q] = s_cb[lc + q];
+            a.cur.cc[coff + q] = s_cc[lc + q];
+        }
+    }
+
+    stamp(6);
+    // ---- 7. integrate the region's bodies (world.rs:143-150; static bodies too, quirk Q-16).  After a NoInverse the
+    //         step stops before the integration (quirk Q-15).
+    for (int lb = lt; lb < nb; lb += T) {
+        const int b = a.reg_bodies[rb0 + lb];
+        const float4 q = s_bv[lb];
+        a.vel[b] = make_float4(q.x, q.y, q.z, 0.0f);
+        if (aborted) continue;
+        float4 p = a.pose[b];
+        V2 np = mk(p.x, p.y) + mk(q.x, q.y) * a.dt;
+        p.x = np.x; p.y = np.y;
+        p.z += q.z * a.dt;
+        a.pose[b] = p;
+        a.force[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    }
+    stamp(7);
+}
+
 __global__ void k_collide_pairs(int n, const SyltBodyDesc* A, const SyltBodyDesc* Bd, const float2* lverts, const int* loff,
                                 SyltContact* out, int cap, int* counts) {
     int p = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1154,6 +1614,7 @@ struct SyltWorld {
     DBuf<float4> tmp_a;
     DBuf<float2> tmp_b;
     DBuf<unsigned long long> used;
+    DBuf<unsigned> used_int;
     DBuf<ulonglong2> vrec;
     int sleep_ns = 0, ctas_per_sm = 1, solve_threads = 512, slack_pct = 0;
     bool timing = false;
@@ -1185,6 +1646,20 @@ struct SyltWorld {
     DBuf<int> jorder, jcolor_start;
     int n_joint_colors = 0;
     std::vector<int> h_jorder;
+
+    // regions (k_solve_regions): spatial partition of the bodies, recomputed on the host when bodies were added or the
+    // share of cross-region arbiters has grown
+    DBuf<int> region_of, lidx, reg_start, reg_bodies;
+    int regions_mode = 0;            // SYLT_REGIONS: 0 = never (default: experimental), 1 = worlds of at least regions_min_bodies, 2 = always
+    int regions_min_bodies = 8192, regions_count = 0, regions_period = 64;
+    bool regions_on = false;         // the partition on the device is valid for the current bodies
+    bool part_dirty = true;          // bodies were added / the mode may have changed
+    bool last_regions = false;       // the last enqueued step ran k_solve_regions
+    bool recolor_all = false;        // next step: ignore last step's colours (they encode the old partition)
+    int n_regions = 0, rbcap = 0, reg_smem_contacts = 0;
+    int64_t steps_since_part = 0;
+    double generic_after_part = -1.0;  // share of generic arbiters on the first step after the last repartition
+    size_t solve_budget = 0;
 
     int64_t cap_pairs = 0, cap_arb = 0, cap_con = 0;
     int64_t user_pairs = 0, user_arb = 0, user_con = 0;
@@ -1298,13 +1773,14 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->row_start.ensure(B + 2));
         SYLT_CUDA(w->row_tmp.ensure(B * ROWTMP));
         SYLT_CUDA(w->used.ensure(B));
+        SYLT_CUDA(w->used_int.ensure(B));
         SYLT_CUDA(w->vrec.ensure(2 * B));
         w->joints_dirty = true;  // jdeg is per body
         SYLT_CUDA(w->large.ensure(B));
         for (int k = 0; k < 2; k++) SYLT_CUDA(w->arb[k].row_start.ensure(B + 2, (size_t)w->B_old + 1, w->stream));
         {   // claims: all ones == "no claim"
             size_t oldcap = w->claim.cap;
-            SYLT_CUDA(w->claim.ensure(B * NC));
+            SYLT_CUDA(w->claim.ensure(B * NCX));
             if (w->claim.cap != oldcap) SYLT_CUDA(cudaMemsetAsync(w->claim.p, 0xff, w->claim.cap * sizeof(unsigned long long), w->stream));
         }
         std::vector<float4> hp(add), hv(add), hf(add), hm(add), hg(add);
@@ -1332,6 +1808,7 @@ int flush(SyltWorld* w) {
         w->pending.clear();
         w->uploaded = (int)B;
         w->class_dirty = true;
+        w->part_dirty = true;
     }
     if (w->class_dirty && B > 0) {
         // static classification: cell = slightly more than the largest "small" bounding diameter; bodies above go to the large list
@@ -1451,6 +1928,86 @@ int flush(SyltWorld* w) {
     return SYLT_OK;
 }
 
+// Spatial partition of the bodies into `G` compact regions of equal body count: strips of equal count along x, every
+// strip cut along y, the regions are consecutive runs of that order.  Any assignment is valid (the class of an arbiter
+// follows from it, k_solve_regions); compactness only decides how many arbiters cross regions.  Host side: it runs when
+// bodies were added and, rarely, when the bodies have mixed.
+int repartition(SyltWorld* w) {
+    const size_t B = w->hb.size();
+    w->part_dirty = false;
+    w->steps_since_part = 0;
+    w->generic_after_part = -1.0;
+    const bool was_on = w->regions_on;
+    int G = w->regions_count > 0 ? std::min(w->regions_count, w->coop_blocks) : w->coop_blocks;
+    bool on = w->regions_mode == 2 || (w->regions_mode == 1 && B >= (size_t)w->regions_min_bodies);
+    if (B == 0 || G < 1) on = false;
+    const size_t per = on ? (B + (size_t)G - 1) / (size_t)G : 0;
+    const size_t rbcap = (per + 3) & ~(size_t)3;
+    // shared memory: 32 bytes per body of the region, the slot records, the rest holds contacts
+    const size_t fixed = rbcap * 32 + (size_t)w->smem_slots * 32 + (((size_t)w->smem_slots + 3) & ~(size_t)3) * 4;
+    if (on && (per >= (1u << 20) || fixed + 4096 > w->solve_budget)) on = false;  // regions too large for an SM: the plain dataflow solver
+    if (!on) {
+        w->regions_on = false;
+        if (was_on) w->recolor_all = true;
+        return SYLT_OK;
+    }
+    if (w->inflight) finish(w);
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    std::vector<float4> hp(B);
+    SYLT_CUDA(cudaMemcpy(hp.data(), w->pose.p, B * sizeof(float4), cudaMemcpyDeviceToHost));
+    std::vector<float> kx(B), ky(B);
+    float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
+    for (size_t i = 0; i < B; i++) {
+        float x = hp[i].x, y = hp[i].y;
+        if (!(x == x) || x > 1.0e30f || x < -1.0e30f) x = 0.0f;
+        if (!(y == y) || y > 1.0e30f || y < -1.0e30f) y = 0.0f;
+        kx[i] = x; ky[i] = y;
+        const HostBody& b = w->hb[i];
+        if (b.inv_mass != 0.0f) { x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y); }
+    }
+    const double xs = x1 > x0 ? (double)x1 - x0 : 1.0, ys = y1 > y0 ? (double)y1 - y0 : 1.0;
+    int SX = (int)std::lround(std::sqrt((double)G * xs / ys));
+    SX = std::max(1, std::min(G, SX));
+    std::vector<int> idx(B);
+    for (size_t i = 0; i < B; i++) idx[i] = (int)i;
+    std::sort(idx.begin(), idx.end(), [&](int p, int q) { return kx[(size_t)p] != kx[(size_t)q] ? kx[(size_t)p] < kx[(size_t)q] : p < q; });
+    for (int sx = 0; sx < SX; sx++) {
+        size_t lo = B * (size_t)sx / (size_t)SX, hi = B * (size_t)(sx + 1) / (size_t)SX;
+        std::sort(idx.begin() + (long)lo, idx.begin() + (long)hi,
+                  [&](int p, int q) { return ky[(size_t)p] != ky[(size_t)q] ? ky[(size_t)p] < ky[(size_t)q] : p < q; });
+    }
+    std::vector<int> region_of(B), lidx(B), reg_start((size_t)G + 1, 0), reg_bodies(B);
+    for (size_t r = 0; r < B; r++) {
+        const int reg = (int)(r * (size_t)G / B);
+        region_of[(size_t)idx[r]] = reg;
+        reg_start[(size_t)reg + 1]++;
+    }
+    size_t maxper = 0;
+    for (int g = 0; g < G; g++) { maxper = std::max(maxper, (size_t)reg_start[(size_t)g + 1]); reg_start[(size_t)g + 1] += reg_start[(size_t)g]; }
+    std::vector<int> fill(reg_start.begin(), reg_start.end() - 1);
+    for (size_t i = 0; i < B; i++) {  // bodies of a region in ascending index order
+        const int reg = region_of[i];
+        lidx[i] = fill[(size_t)reg] - reg_start[(size_t)reg];
+        reg_bodies[(size_t)fill[(size_t)reg]++] = (int)i;
+    }
+    if (maxper > rbcap) { w->regions_on = false; if (was_on) w->recolor_all = true; return SYLT_OK; }
+    SYLT_CUDA(w->region_of.ensure(B));
+    SYLT_CUDA(w->lidx.ensure(B));
+    SYLT_CUDA(w->reg_bodies.ensure(B));
+    SYLT_CUDA(w->reg_start.ensure((size_t)G + 1));
+    SYLT_CUDA(cudaMemcpyAsync(w->region_of.p, region_of.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    SYLT_CUDA(cudaMemcpyAsync(w->lidx.p, lidx.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    SYLT_CUDA(cudaMemcpyAsync(w->reg_bodies.p, reg_bodies.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    SYLT_CUDA(cudaMemcpyAsync(w->reg_start.p, reg_start.data(), ((size_t)G + 1) * sizeof(int), cudaMemcpyHostToDevice, w->stream));
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    w->n_regions = G;
+    w->rbcap = (int)rbcap;
+    w->reg_smem_contacts = (int)((w->solve_budget - fixed) / 48);
+    w->regions_on = true;
+    w->recolor_all = true;
+    return SYLT_OK;
+}
+
 // Enqueue one step (or one broad phase only) on the stream.  No host synchronisation.
 int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     const int B = (int)w->hb.size();
@@ -1464,7 +2021,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     }
     const int nbB = (B + 255) / 256;
     k_prepare<<<nbB, 256, 0, st>>>(B, w->pose.p, w->vel.p, w->force.p, w->mp.p, w->geom.p, w->bflags.p, w->lverts.p, w->rotc.p, w->aabb.p,
-                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p, w->used.p);
+                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p, w->used.p, w->used_int.p);
     w->launches++;
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
     if (e) return e;
@@ -1489,14 +2046,16 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->sincl64.p, 0, 2);
     if (e) return e;
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
+    const int keep_colors = w->recolor_all ? 0 : 1;
+    w->recolor_all = false;
     if (w->any_poly)
         k_build<MAX_MANIFOLD><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p,
                                                               w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p,
-                                                              w->bflags_old.p, cur, old, w->warm, w->used.p, w->uncolored.p, w->fix_features);
+                                                              w->bflags_old.p, cur, old, w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0);
     else
         k_build<2><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p, w->info.p,
                                                    w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur,
-                                                   old, w->warm, w->used.p, w->uncolored.p, w->fix_features);
+                                                   old, w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0);
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
 
@@ -1513,13 +2072,22 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         w->epoch = 1;
     }
     a.pose = w->pose.p; a.vel = w->vel.p; a.force = w->force.p; a.mp = w->mp.p; a.rotc = w->rotc.p; a.bflags = w->bflags.p;
-    a.cur = cur; a.used = w->used.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.uncolored2 = w->uncolored2.p; a.prop = w->prop.p; a.order = w->order.p;
+    a.cur = cur; a.used = w->used.p; a.used_int = w->used_int.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.uncolored2 = w->uncolored2.p; a.prop = w->prop.p; a.order = w->order.p;
     a.jbodies = w->jbodies.p; a.jla = w->jla.p; a.jparam = w->jparam.p; a.jp = w->jp.p; a.jr = w->jr.p; a.jm = w->jm.p; a.jbias = w->jbias.p;
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
     void* args[] = {&a};
     a.smem_slots = w->smem_slots; a.smem_contacts = w->smem_contacts;
     a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.slack_pct = w->slack_pct; a.fix_inverse = w->fix_inverse; a.dbg = w->timing ? w->dbg.p : nullptr;
-    SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_smem, st));
+    if (w->regions_on) {
+        a.region_of = w->region_of.p; a.lidx = w->lidx.p; a.reg_start = w->reg_start.p; a.reg_bodies = w->reg_bodies.p;
+        a.n_regions = w->n_regions; a.rbcap = w->rbcap; a.smem_contacts = w->reg_smem_contacts;
+        SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_regions, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_budget, st));
+        w->steps_since_part++;
+        w->last_regions = true;
+    } else {
+        w->last_regions = false;
+        SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_smem, st));
+    }
     w->launches++;
     // the set just built becomes "last step's"
     w->cur ^= 1;
@@ -1533,12 +2101,22 @@ int finish(SyltWorld* w) {
     SYLT_CUDA(cudaMemcpy(&w->last, w->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
     w->inflight = false;
     w->have_last = true;
+    if (w->last_regions) {
+        w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
+        if (w->generic_after_part < 0.0 && w->last.n_arb > 0) w->generic_after_part = (double)w->last.n_generic / (double)w->last.n_arb;
+    }
     if (w->timing) {  // diagnostics: k_solve section times of the last step (CTA 0's view)
-        unsigned long long t[8];
-        if (cudaMemcpy(t, w->dbg.p, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess)
+        unsigned long long t[64];
+        if (cudaMemcpy(t, w->dbg.p, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess) {
+            if (w->last_regions && t[16]) {  // pass 5 of a CTA in the middle of the grid: import | interior colours | export + first generic colour | further generic colours
+                fprintf(stderr, "k_solve_regions pass 5 [us]:");
+                for (int k = 17; k < 64 && t[k]; k++) fprintf(stderr, " %.2f", (t[k] - t[k - 1]) * 1e-3);
+                fprintf(stderr, "\n");
+            }
             fprintf(stderr, "k_solve sections [us]: colour %.1f order %.1f residency %.1f pass0 %.1f iterations %.1f writeback %.1f integrate %.1f total %.1f\n",
                     (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3,
                     (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
+        }
     }
     w->last_was_step = w->inflight_full;
     w->last_iterations = w->iterations;
@@ -1550,6 +2128,19 @@ int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
     int e = flush(w);
     if (e) return e;
     if (body_order_violated(w->hb)) return SYLT_ERR_BODY_ORDER;
+    {   // regions: (re)partition when bodies were added, or when the bodies have mixed: the share of cross-region arbiters
+        // has grown well beyond what the last partition started with (checked between step_n calls only)
+        bool again = w->part_dirty;
+        if (!again && w->regions_on && w->have_last && w->last_regions && w->steps_since_part >= w->regions_period && w->last.n_arb > 0 &&
+            w->generic_after_part >= 0.0) {
+            const double share = (double)w->last.n_generic / (double)w->last.n_arb;
+            again = share > 1.5 * w->generic_after_part + 0.05;
+        }
+        if (again) {
+            e = repartition(w);
+            if (e) return e;
+        }
+    }
     if (!w->inflight) SYLT_CUDA(cudaMemsetAsync(w->counters.p, 0, offsetof(Counters, n_pairs), w->stream));  // sticky error fields
     const int B = (int)w->hb.size();
     for (int s = 0; s < n; s++) {
@@ -1611,7 +2202,8 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     if (const char* ev = getenv("SYLT_SOLVER_SLEEP_NS")) w->sleep_ns = std::max(0, atoi(ev));
     if (const char* ev = getenv("SYLT_SOLVER_SLACK")) w->slack_pct = std::max(0, atoi(ev));
     if (const char* ev = getenv("SYLT_SOLVER_TIMING")) w->timing = atoi(ev) != 0;
-    SYLT_CUDA(w->dbg.ensure(16));
+    SYLT_CUDA(w->dbg.ensure(64));
+    SYLT_CUDA(cudaMemset(w->dbg.p, 0, 64 * sizeof(unsigned long long)));
     if (const char* ev = getenv("SYLT_SOLVER_SMEM_SLOTS")) w->smem_slots = std::max(0, atoi(ev));  // tests: force the global-memory path
     size_t fixed = (size_t)w->smem_slots * 32 + (((size_t)w->smem_slots + 3) & ~(size_t)3) * 4;
     if (fixed + 48 > budget) { w->smem_slots = 0; fixed = 0; }
@@ -1619,6 +2211,20 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     if (const char* ev = getenv("SYLT_SOLVER_SMEM_CONTACTS")) w->smem_contacts = std::min(w->smem_contacts, std::max(0, atoi(ev)));
     w->solve_smem = fixed + (size_t)w->smem_contacts * 48;
     SYLT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_smem));
+    {   // k_solve_regions: same budget, carved per partition (bodies of the region, slot records, contacts)
+        cudaFuncAttributes fr;
+        SYLT_CUDA(cudaFuncGetAttributes(&fr, k_solve_regions));
+        const size_t b2 = (size_t)max_smem + 1024 - 1024 - fr.sharedSizeBytes - 1024;
+        w->solve_budget = b2 & ~(size_t)15;
+        SYLT_CUDA(cudaFuncSetAttribute(k_solve_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_budget));
+        int per2 = 0;
+        SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_solve_regions, SOLVE_THREADS, w->solve_budget));
+        if (const char* ev = getenv("SYLT_REGIONS")) w->regions_mode = std::min(2, std::max(0, atoi(ev)));
+        if (const char* ev = getenv("SYLT_REGIONS_MIN_BODIES")) w->regions_min_bodies = std::max(1, atoi(ev));
+        if (const char* ev = getenv("SYLT_REGIONS_COUNT")) w->regions_count = std::max(0, atoi(ev));
+        if (const char* ev = getenv("SYLT_REGIONS_PERIOD")) w->regions_period = std::max(1, atoi(ev));
+        if (per2 < 1 || w->ctas_per_sm != 1) w->regions_mode = 0;
+    }
     int per_sm = 0;
     SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, w->solve_threads, w->solve_smem));
     if (per_sm < w->ctas_per_sm) { delete w; set_last_error("k_solve does not fit on an SM"); return SYLT_ERR_CUDA; }
@@ -1637,7 +2243,7 @@ static void free_all(SyltWorld* w) {
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->cent_aabb.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
-    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
+    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
     w->prop.release(); w->order.release(); w->sincl32.release(); w->sincl64.release(); w->scan_flag.release(); w->scan_ticket.release();
     for (int k = 0; k < 2; k++) {
         auto& a = w->arb[k];
@@ -1646,6 +2252,7 @@ static void free_all(SyltWorld* w) {
     }
     w->jbodies.release(); w->jla.release(); w->jr.release(); w->jm.release(); w->jparam.release(); w->jp.release(); w->jbias.release();
     w->jorder.release(); w->jcolor_start.release();
+    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release();
 }
 
 int sylt_world_destroy(SyltWorld* w) {
@@ -1667,6 +2274,7 @@ int sylt_world_clear(SyltWorld* w) {  // world.rs:67-71
     w->hb.clear(); w->hverts.clear(); w->pending.clear(); w->hj.clear(); w->h_jorder.clear();
     w->uploaded = 0; w->class_dirty = true; w->joints_dirty = true; w->any_poly = false; w->n_large = 0;
     w->have_old = false; w->B_old = 0; w->have_last = false; w->n_joint_colors = 0; w->inflight = false; w->flags_stale = false;
+    w->regions_on = false; w->part_dirty = true; w->recolor_all = false; w->last_regions = false;
     memset(&w->last, 0, sizeof w->last);
     return SYLT_OK;
 }
