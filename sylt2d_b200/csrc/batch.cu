@@ -290,7 +290,7 @@ __device__ unsigned long long g_phase_cycles[16];
 __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     const int wld = blockIdx.x + a.world_begin;
     if (wld >= a.n_worlds) return;
-    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5, nwarps = T >> 5;
+    const int tid = threadIdx.x, T = blockDim.x, lane = tid & 31, warp = tid >> 5;
     const int b0 = a.body_off[wld], B = a.body_off[wld + 1] - b0;
     const int j0 = a.joint_off[wld], J = a.joint_off[wld + 1] - j0;
     const int cap = a.cap;

@@ -68,7 +68,10 @@ struct Counters {
     unsigned bar;  // grid barrier arrivals of this step's k_solve
     // region solver (k_solve_regions):
     int order_alloc;                // next free entry of the `order` array (every CTA takes one private segment)
-    int n_generic;                  // arbiters solved through the versioned records in L2 (cross-region and overflow colours)
+    int n_generic;                  // arbiters of the generic colours (cross-region pairs, interior overflow)
+    int n_ghost;                    // replicas of generic arbiters replayed by neighbouring regions
+    int max_slots, n_nonres;        // load of the busiest CTA; slots whose records / contacts did not fit into shared memory
+    int why;                        // diagnostics: bit mask of what overflowed in k_solve_regions
     unsigned long long color_mask;  // generic colours in use
     unsigned color_mask_int;        // interior colours in use
 };
@@ -577,15 +580,11 @@ struct SolveArgs {
     const int *jorder, *jcolor_start;
     // regions (k_solve_regions): every body belongs to one region, region r is solved by CTA r
     const int *region_of, *lidx, *reg_start, *reg_bodies;  // body -> region, body -> index inside its region, CSR of the regions
-    int n_regions, rbcap;                                  // rbcap: shared-memory room for the bodies of one region
+    int n_regions, rbcap, ghost_cap;                       // shared-memory room for the bodies of one region / its ghost bodies
+    int *gadj, *cone_buf;                                  // per body: its generic arbiters; per CTA: ghost arbiters
+    ulonglong2* xrec;                                      // export planes (one per pass) of versioned boundary-body velocities
+    unsigned step_tag;
 };
-
-__device__ __forceinline__ Vel load_vel(const float4* vel, int b) {
-    float4 v = __ldcg(&vel[b]);
-    Vel o; o.v = mk(v.x, v.y); o.w = v.z;
-    return o;
-}
-__device__ __forceinline__ void store_vel(float4* vel, int b, const Vel& v) { __stcg(&vel[b], make_float4(v.v.x, v.v.y, v.w, 0.0f)); }
 
 // ---- light grid barrier: one monotonic counter, release-add on arrival, acquire-poll until everybody arrived.
 // (cg::grid.sync() cost ~5 us per colour phase here: profiles/r01_k_solve_lines.txt.)  All CTAs of the cooperative
@@ -1122,31 +1121,34 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
 }
 
 // ------------------------------------------------------------------ region solver
-// The same sequential sweep as k_solve — passes x (colours ascending, then joints) — with a different execution plan.
-// Bodies are partitioned into compact spatial regions (host side, `repartition`), region r belongs to CTA r for the
-// whole solve and its body velocities live in that CTA's shared memory.  Per pass a CTA
-//   1. imports its boundary bodies (bodies that also carry generic constraints) from their versioned L2 records,
-//   2. sweeps its interior colours (< GEN_BIT) in shared memory, one __syncthreads() per colour,
-//   3. exports the boundary bodies (version + 1),
-//   4. solves its generic arbiters (colours >= GEN_BIT: cross-region pairs) and its share of the joints through the
-//      versioned records, exactly as k_solve does for everything.
-// Interior arbiters of different regions touch disjoint dynamic bodies, so running the regions side by side IS the
-// sequential (pass, colour) order; only ~ the cross-region colours of a pass are L2-latency hops.  Version of a
-// boundary body with Dg generic constraints: pass*(Dg+1) at the start of a pass, +1 by the export, +1 per generic
-// constraint in colour order.
-struct RSlot {
-    int r1, r2, n;         // interior: index into the region's bodies | VSTATIC; generic: global body index | VSTATIC
-    unsigned ord;          // generic: Dv1 | rank1 << 8 | Dv2 << 16 | rank2 << 24
-    float fr;
-    float svx, svy, svw, sii;  // interior: velocity and inv_moi of the static body of the pair (if any)
-    float4 *ca, *cb, *cc;
-};
+// The same sequential sweep as k_solve — passes x colours ascending — with a different execution plan.
+// Bodies are partitioned into compact spatial regions (host side, `repartition`); region r belongs to CTA r for the
+// whole solve and its body velocities live in that CTA's shared memory.  Arbiters come in two classes (the colour
+// range IS the class, see color_new_arbiters): interior (colour < GEN_BIT: all dynamic bodies in the owner's region)
+// and generic (cross-region pairs).  Interior arbiters of different regions touch disjoint dynamic bodies, so the
+// regions sweep their interior colours side by side with one __syncthreads() per colour.
+// The generic colours are solved by REDUNDANT computation instead of communication: what a region needs from the
+// generic phase of a pass is the final state of its own boundary bodies, and that depends only on the generic arbiters
+// reachable from its own through "a generic arbiter of a lower colour shares a dynamic body" — a cone that is closed
+// after at most (number of generic colours) steps and stays near the region's border.  Every CTA collects that cone
+// (a breadth-first walk over a per-body table of generic arbiters), imports the "ghost" bodies the cone touches once
+// per pass — their state after the owner's interior sweep, exported through a per-pass plane of versioned records in
+// L2 — and replays the cone in colour order in its own shared memory.  f32 arithmetic is deterministic, so every
+// replica of a generic arbiter computes the same bits; a pass costs ONE L2 hand-off instead of one per generic colour.
+// Only the owner writes an arbiter's contacts back.  Worlds with joints use k_solve.
+constexpr int GADJ = NC;              // per body: its generic arbiters, indexed by the rank of their colour in `used`
+constexpr int GHOST_FLAG = 0x40000000;
+constexpr int CONE_CAP = 2048;        // ghost arbiters a CTA may replay
+constexpr int HASH_CAP = 4096;        // open-addressing tables of the cone walk (alias the contact area during set-up)
+constexpr int MAX_PLANES = 16;        // export planes: one per pass (iterations + 1)
+
+__device__ __forceinline__ unsigned hash_u32(unsigned x) { return fmix32(x * 2654435761u); }
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a) {
     extern __shared__ __align__(16) unsigned char sm_raw[];
     Counters* cn = a.cn;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
-    const int T = blockDim.x, bid = blockIdx.x, lt = threadIdx.x, lane = lt & 31;
+    const int T = blockDim.x, bid = blockIdx.x, lt = threadIdx.x;
     const int A = min(*(volatile int*)&cn->n_arb, a.cap_arb);
     unsigned bar_target = 0;
     unsigned* bar = &cn->bar;
@@ -1155,76 +1157,200 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     };
     stamp(0);
     __shared__ int s_cnt[NCX], s_fill[NCX], s_cstart[NCX + 1], s_clist[NCX];
-    __shared__ int s_ncl, s_nint, s_nbnd, s_obase, s_L;
+    __shared__ int s_ncl, s_nint, s_nbnd, s_obase, s_L, s_ngh, s_ngb, s_bad;
     __shared__ int s_scan[34];
-    // shared-memory carve-up: region bodies, boundary list, slot records, contact scan scratch, contacts
-    const int RBCAP = a.rbcap, SLOTCAP = a.smem_slots, CONCAP = a.smem_contacts;
+    // shared-memory carve-up: bodies (own, then ghosts; 32 bytes each), boundary / ghost lists, slot records (12 bytes),
+    // contacts (36 bytes).  During set-up the hash tables of the cone walk alias the contact area.
+    const int RBCAP = a.rbcap, GBCAP = a.ghost_cap, SLOTCAP = a.smem_slots, CONCAP = a.smem_contacts;
     float4* s_bv = (float4*)sm_raw;                       // (vx, vy, w, -)
-    float2* s_bm = (float2*)(s_bv + RBCAP);               // (inv_mass, inv_moi)
-    int* s_bnd = (int*)(s_bm + RBCAP);                    // boundary bodies: local index | Dv << 20
-    int* s_bndg = s_bnd + RBCAP;                          //                  global index
-    float4* s_rec = (float4*)(s_bndg + RBCAP);
-    int* s_n = (int*)(s_rec + 2 * (size_t)SLOTCAP);
-    float4* s_ca = (float4*)(s_n + ((SLOTCAP + 3) & ~3));
-    float4* s_cb = s_ca + CONCAP;
-    float4* s_cc = s_cb + CONCAP;
+    float4* s_bp = s_bv + RBCAP + GBCAP;                  // (x, y, inv_mass, inv_moi): constant during the solve
+    float4* s_c0 = s_bp + RBCAP + GBCAP;                  // contact: (position, normal)
+    float4* s_c1 = s_c0 + CONCAP;                         //          (mass_normal, mass_tangent, bias, pn); before pre_step: (-, -, separation, pn)
+    float* s_c2 = (float*)(s_c1 + CONCAP);                //          pt
+    int* s_bnd = (int*)(s_c2 + CONCAP);                   // own boundary bodies: local index
+    int* s_bndg = s_bnd + RBCAP;                          //                      global index
+    int* s_gb = s_bndg + RBCAP;                           // ghost bodies: global index | GHOST_FLAG if static (never imported again)
+    int* s_sb = s_gb + GBCAP;                             // slot: body refs, r1 | r2 << 16; ref = index into s_bv | SREF_STATIC
+    int* s_sc = s_sb + SLOTCAP;                           //       contact offset << 8 | count, or -1: contacts in the global arrays
+    float* s_sf = (float*)(s_sc + SLOTCAP);               //       friction
+    int* h_arb = (int*)s_c0;                              // set-up only: set of ghost arbiters (key = arbiter + 1)
+    int* h_body = h_arb + HASH_CAP;                       // set-up only: ghost body -> index (key = body + 1, value)
+    int* h_bval = h_body + HASH_CAP;
 
     color_new_arbiters<true>(a, cn, bar, bar_target);
     stamp(1);
+    const int R = bid;
+    auto dynamic = [&](int b) { return !(a.bflags[b] & FLAG_STATIC); };
+    auto owner_region = [&](int e, int2 b) { return a.region_of[a.cur.partner[e] == b.x ? b.y : b.x]; };
 
-    // ---- 2. the region's bodies into shared memory; its arbiters (the rows its bodies own) binned by colour
+    // ---- 2a. per-body table of the generic arbiters (colours are distinct around a body: the slot is the colour's rank)
+    for (int e = tid; e < A; e += nth) {
+        const int c = __ldcg(&a.cur.color[e]);
+        if (c < GEN_BIT) continue;
+        const int2 b = a.cur.bodies[e];
+        const unsigned long long lower = (1ull << (c - GEN_BIT)) - 1ull;
+        if (dynamic(b.x)) a.gadj[(size_t)b.x * GADJ + __popcll(__ldcg(&a.used[b.x]) & lower)] = e;
+        if (dynamic(b.y)) a.gadj[(size_t)b.y * GADJ + __popcll(__ldcg(&a.used[b.y]) & lower)] = e;
+    }
+    grid_barrier(bar, bar_target);
+
+    // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) counted by colour
     BodyIO io{a.vrec, a.sleep_ns, &cn->err};
-    const int rb0 = bid < a.n_regions ? a.reg_start[bid] : 0;
-    const int nb = bid < a.n_regions ? a.reg_start[bid + 1] - rb0 : 0;
+    const int rb0 = R < a.n_regions ? a.reg_start[R] : 0;
+    const int nb = R < a.n_regions ? a.reg_start[R + 1] - rb0 : 0;
     if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; }
-    if (lt == 0) s_nbnd = 0;
+    if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_bad = nb > RBCAP ? 1 : 0; }
+    for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
     __syncthreads();
-    for (int lb = lt; lb < nb; lb += T) {
+    int* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA, in discovery order
+    auto arb_insert = [&](int f) -> bool {  // true: f is new
+        unsigned h = hash_u32((unsigned)f) & (HASH_CAP - 1);
+        for (int probe = 0; probe < HASH_CAP; probe++) {
+            const int old = atomicCAS(&h_arb[h], 0, f + 1);
+            if (old == 0) return true;
+            if (old == f + 1) return false;
+            h = (h + 1) & (HASH_CAP - 1);
+        }
+        s_bad = 1;
+        return false;
+    };
+    auto add_ghost = [&](int f, int c) {
+        if (!arb_insert(f)) return;
+        const int g = atomicAdd(&s_ngh, 1);
+        if (g < CONE_CAP) { ghosts[g] = f; atomicAdd(&s_cnt[c], 1); }
+        else s_bad = 1;
+    };
+    // everything arbiter e (generic, colour c) depends on inside one generic phase: lower-coloured generic arbiters at its bodies
+    auto expand = [&](int e) {
+        const int c = __ldcg(&a.cur.color[e]);
+        const int2 b = a.cur.bodies[e];
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const int z = side ? b.y : b.x;
+            if (!dynamic(z)) continue;
+            const unsigned long long uz = __ldcg(&a.used[z]);
+            unsigned long long m = uz & ((1ull << (c - GEN_BIT)) - 1ull);
+            while (m) {
+                const int k = __ffsll((long long)m) - 1;
+                m &= m - 1ull;
+                const int f = __ldcg(&a.gadj[(size_t)z * GADJ + __popcll(uz & ((1ull << k) - 1ull))]);
+                if (owner_region(f, a.cur.bodies[f]) != R) add_ghost(f, GEN_BIT + k);  // (an own arbiter is a root of the walk anyway)
+            }
+        }
+    };
+    for (int lb = lt; lb < min(nb, RBCAP); lb += T) {
         const int b = a.reg_bodies[rb0 + lb];
         Vel v;
         float im, ii;
         io.get(b, v, im, ii);
-        const bool dyn = !(a.bflags[b] & FLAG_STATIC);
-        const int dg = dyn ? __popcll(__ldcg(&a.used[b])) + a.jdeg[b] : 0;
+        const float4 p = a.pose[b];
         s_bv[lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
-        s_bm[lb] = make_float2(im, ii);
-        if (dg) {
+        s_bp[lb] = make_float4(p.x, p.y, im, ii);
+        const unsigned long long ub = dynamic(b) ? __ldcg(&a.used[b]) : 0ull;
+        if (ub != 0ull) {  // a boundary body: exported every pass; every generic arbiter at it is replayed here, whoever owns it
             const int k = atomicAdd(&s_nbnd, 1);
-            s_bnd[k] = lb | ((dg + 1) << 20);
+            s_bnd[k] = lb;
             s_bndg[k] = b;
+            const int ng = __popcll(ub);
+            for (int r = 0; r < ng; r++) {
+                const int f = __ldcg(&a.gadj[(size_t)b * GADJ + r]);
+                if (owner_region(f, a.cur.bodies[f]) != R) add_ghost(f, __ldcg(&a.cur.color[f]));
+            }
         }
         const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
         for (int e = e0; e < e1; e++) {
             const int c = __ldcg(&a.cur.color[e]);
-            if (c >= 0) atomicAdd(&s_cnt[c], 1);
+            if (c < 0) continue;
+            atomicAdd(&s_cnt[c], 1);
+            if (c >= GEN_BIT) expand(e);  // level 0 of the cone walk: the region's own generic arbiters are roots
         }
     }
     __syncthreads();
+    // ---- 2c. cone walk: ghost arbiters found in one level are expanded in the next, until nothing new turns up
+    for (int f0 = 0;;) {
+        const int f1 = min(s_ngh, CONE_CAP);
+        __syncthreads();
+        if (f1 == f0) break;
+        for (int g = f0 + lt; g < f1; g += T) expand(__ldcg(&ghosts[g]));
+        __syncthreads();
+        f0 = f1;
+    }
+    const int ngh = min(s_ngh, CONE_CAP);
+    // ---- 2d. ghost bodies: bodies of other regions that this CTA's slots touch (dynamic: re-imported every pass; static: once)
+    auto body_insert = [&](int z) {
+        unsigned h = hash_u32((unsigned)z ^ 0x9e3779b9u) & (HASH_CAP - 1);
+        for (int probe = 0; probe < HASH_CAP; probe++) {
+            const int old = atomicCAS(&h_body[h], 0, z + 1);
+            if (old == 0) {
+                const int g = atomicAdd(&s_ngb, 1);
+                h_bval[h] = g;
+                if (g < GBCAP) s_gb[g] = z | (dynamic(z) ? 0 : GHOST_FLAG); else s_bad = 1;
+                return;
+            }
+            if (old == z + 1) return;
+            h = (h + 1) & (HASH_CAP - 1);
+        }
+        s_bad = 1;
+    };
+    auto body_lookup = [&](int z) -> int {
+        unsigned h = hash_u32((unsigned)z ^ 0x9e3779b9u) & (HASH_CAP - 1);
+        for (int probe = 0; probe < HASH_CAP; probe++) {
+            const int key = h_body[h];
+            if (key == z + 1) return h_bval[h];
+            if (key == 0) break;
+            h = (h + 1) & (HASH_CAP - 1);
+        }
+        s_bad = 1;
+        return 0;
+    };
+    auto ghost_bodies_of = [&](int e) {
+        const int2 b = a.cur.bodies[e];
+        if (a.region_of[b.x] != R) body_insert(b.x);
+        if (a.region_of[b.y] != R) body_insert(b.y);
+    };
+    for (int lb = lt; lb < nb; lb += T) {
+        const int b = a.reg_bodies[rb0 + lb];
+        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
+        for (int e = e0; e < e1; e++)
+            if (__ldcg(&a.cur.color[e]) >= 0) ghost_bodies_of(e);
+    }
+    for (int g = lt; g < ngh; g += T) ghost_bodies_of(__ldcg(&ghosts[g]));
+    __syncthreads();
+    const int ngb = min(s_ngb, GBCAP);
+    for (int g = lt; g < ngb; g += T) {  // positions, inverse masses (and, for static ghosts, the velocity) once; dynamic velocities arrive every pass
+        const int z = s_gb[g] & ~GHOST_FLAG;
+        Vel v;
+        float im, ii;
+        io.get(z, v, im, ii);
+        const float4 p = a.pose[z];
+        s_bv[nb + g] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
+        s_bp[nb + g] = make_float4(p.x, p.y, im, ii);
+    }
+    // ---- 2e. slot layout: generic colours first (their contacts must be shared-memory resident), then the interior colours
     if (lt == 0) {
         int run = 0, ncl = 0, nint = 0, ngen = 0;
         unsigned long long mask = 0ull;
         unsigned mask_int = 0u;
-        for (int c = 0; c < NCX; c++) {
-            s_cstart[c] = run;
-            if (s_cnt[c]) {
-                if (c < GEN_BIT) mask_int |= 1u << c; else mask |= 1ull << (c - GEN_BIT);
-                s_clist[ncl++] = c;
-                if (c < GEN_BIT) nint++; else ngen += s_cnt[c];
-            }
-            run += s_cnt[c];
-        }
+        for (int c = GEN_BIT; c < NCX; c++) { s_cstart[c] = run; run += s_cnt[c]; if (s_cnt[c]) { mask |= 1ull << (c - GEN_BIT); ngen += s_cnt[c]; } }
+        for (int c = 0; c < GEN_BIT; c++) { s_cstart[c] = run; run += s_cnt[c]; if (s_cnt[c]) { mask_int |= 1u << c; s_clist[ncl++] = c; nint++; } }
+        for (int c = GEN_BIT; c < NCX; c++) if (s_cnt[c]) s_clist[ncl++] = c;
         s_cstart[NCX] = run;
         s_ncl = ncl; s_nint = nint; s_L = run;
         s_obase = run ? atomicAdd(&cn->order_alloc, run) : 0;
         if (mask) atomicOr(&cn->color_mask, mask);
         if (mask_int) atomicOr(&cn->color_mask_int, mask_int);
-        if (ngen) atomicAdd(&cn->n_generic, ngen);
+        if (ngen) atomicAdd(&cn->n_generic, ngen - ngh);
+        if (ngh) atomicAdd(&cn->n_ghost, ngh);
+        atomicMax(&cn->max_slots, run);
+        if (s_bad || run > SLOTCAP) {  // more slots / a larger cone than the tables hold
+            atomicExch(&cn->err, SYLT_ERR_CAPACITY);
+            atomicOr(&cn->why, (s_bad ? 1 : 0) | (run > SLOTCAP ? 2 : 0) | (s_ngh > CONE_CAP ? 4 : 0) | (s_ngb > GBCAP ? 8 : 0) | (nb > RBCAP ? 16 : 0));
+        }
     }
     __syncthreads();
     if (!a.run_solver) return;
-    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // e.g. an arbiter without a free colour: no solve, error reported
-    const int L = s_L, ncl = s_ncl, nint = s_nint, nbnd = s_nbnd;
-    int* order = a.order + s_obase;  // this CTA's slots, colour-major (within a colour the order is irrelevant)
+    const int L = min(s_L, SLOTCAP), ncl = s_ncl, nint = s_nint, nbnd = s_nbnd;
+    int* order = a.order + s_obase;  // this CTA's slots by colour (within a colour the order is irrelevant); ghosts carry GHOST_FLAG
     for (int lb = lt; lb < nb; lb += T) {
         const int b = a.reg_bodies[rb0 + lb];
         const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
@@ -1233,296 +1359,199 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
             if (c >= 0) order[s_cstart[c] + atomicAdd(&s_fill[c], 1)] = e;
         }
     }
+    for (int g = lt; g < ngh; g += T) {
+        const int f = __ldcg(&ghosts[g]);
+        const int c = __ldcg(&a.cur.color[f]);
+        order[s_cstart[c] + atomicAdd(&s_fill[c], 1)] = f | GHOST_FLAG;
+    }
     __syncthreads();
     const bool acc = a.accumulate != 0;
     const float kbias = a.poscorr ? 0.2f : 0.0f;
 
     stamp(2);
-    // ---- 3. residency: slot records and contact constants of the owned slots into shared memory
-    const int Ls = min(L, SLOTCAP);
-    for (int ls = lt; ls < Ls; ls += T) s_n[ls] = a.cur.meta[__ldcg(&order[ls])].x;
-    __syncthreads();
-    {   // in-place exclusive scan of s_n[0..Ls)
-        const int chunk = (Ls + T - 1) / T, q0 = min(lt * chunk, Ls), q1 = min(q0 + chunk, Ls);
+    // ---- 3. residency: slot records (the bodies' shared-memory indices need the hash tables), then the contacts (which
+    //         overwrite the tables)
+    constexpr int SREF_STATIC = 0x8000;
+    auto body_ref = [&](int z) -> int {
+        return (a.region_of[z] == R ? a.lidx[z] : nb + body_lookup(z)) | (dynamic(z) ? 0 : SREF_STATIC);
+    };
+    for (int ls = lt; ls < L; ls += T) {
+        const int e = __ldcg(&order[ls]) & ~GHOST_FLAG;
+        const int2 b = a.cur.bodies[e];
+        s_sb[ls] = body_ref(b.x) | (body_ref(b.y) << 16);
+        s_sc[ls] = a.cur.meta[e].x;
+        s_sf[ls] = a.cur.friction[e];
+    }
+    __syncthreads();  // the hash tables are dead from here on
+    {   // in-place exclusive scan of the contact counts
+        const int chunk = (L + T - 1) / T, q0 = min(lt * chunk, L), q1 = min(q0 + chunk, L);
         int sum = 0;
-        for (int k = q0; k < q1; k++) sum += s_n[k];
+        for (int k = q0; k < q1; k++) sum += s_sc[k];
         int tot;
         int ex = block_excl_scan<int>(sum, &tot, s_scan);
-        for (int k = q0; k < q1; k++) { int t = s_n[k]; s_n[k] = ex; ex += t; }
+        for (int k = q0; k < q1; k++) { int t = s_sc[k]; s_sc[k] = ex; ex += t; }
     }
     __syncthreads();
-    // what a slot needs besides its contacts (from the global arrays)
-    auto describe = [&](int e, int c, RSlot& v) {
-        const int2 b = a.cur.bodies[e];
-        const bool st1 = (a.bflags[b.x] & FLAG_STATIC) != 0, st2 = (a.bflags[b.y] & FLAG_STATIC) != 0;
-        v.n = a.cur.meta[e].x;
-        v.fr = a.cur.friction[e];
-        v.ord = 0u; v.svx = v.svy = v.svw = v.sii = 0.0f;
-        if (c < GEN_BIT) {
-            v.r1 = st1 ? VSTATIC : a.lidx[b.x];
-            v.r2 = st2 ? VSTATIC : a.lidx[b.y];
-            if (st1 || st2) {
-                Vel sv;
-                float sim;
-                io.get(st1 ? b.x : b.y, sv, sim, v.sii);
-                v.svx = sv.v.x; v.svy = sv.v.y; v.svw = sv.w;
+    const int n_generic_slots = s_cstart[0];  // generic colours come first in the layout
+    for (int ls = lt; ls < L; ls += T) {
+        const int e = __ldcg(&order[ls]) & ~GHOST_FLAG;
+        const int2 mt = a.cur.meta[e];
+        const int lc = s_sc[ls];
+        const bool res = lc + mt.x <= CONCAP;
+        if (!res) {
+            atomicAdd(&cn->n_nonres, 1);
+            if (ls < n_generic_slots) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); atomicOr(&cn->why, 32); }  // a replica has no global working storage
+        }
+        s_sc[ls] = res ? (lc << 8) | mt.x : -1;
+        if (res)
+            for (int q = 0; q < mt.x; q++) {
+                const float4 ca = a.cur.ca[mt.y + q], cc = a.cur.cc[mt.y + q], cd = a.cur.cd[mt.y + q];
+                s_c0[lc + q] = make_float4(cd.x, cd.y, ca.x, ca.y);
+                s_c1[lc + q] = make_float4(0.0f, 0.0f, cc.w, cc.y);
+                s_c2[lc + q] = cc.z;
             }
-        } else {
-            v.r1 = b.x | (st1 ? VSTATIC : 0);
-            v.r2 = b.y | (st2 ? VSTATIC : 0);
-            const unsigned long long u1 = __ldcg(&a.used[b.x]), u2 = __ldcg(&a.used[b.y]);
-            const unsigned long long lower = (1ull << (c - GEN_BIT)) - 1ull;
-            const unsigned d1 = (unsigned)(__popcll(u1) + a.jdeg[b.x] + 1), d2 = (unsigned)(__popcll(u2) + a.jdeg[b.y] + 1);
-            v.ord = (d1 & 0xffu) | ((unsigned)__popcll(u1 & lower) << 8) | ((d2 & 0xffu) << 16) | ((unsigned)__popcll(u2 & lower) << 24);
-        }
-    };
-    for (int k = 0; k < ncl; k++) {
-        const int c = s_clist[k], cnt = s_cnt[c];
-        for (int i = lt; i < cnt; i += T) {
-            const int ls = s_cstart[c] + i;
-            if (ls >= SLOTCAP) continue;
-            const int e = __ldcg(&order[ls]);
-            RSlot v;
-            describe(e, c, v);
-            const int coff = a.cur.meta[e].y, lc = s_n[ls];
-            const bool res = lc + v.n <= CONCAP;
-            s_rec[2 * ls] = make_float4(__int_as_float(v.r1), __int_as_float(v.r2), __int_as_float(res ? (lc << 8) | v.n : -1), v.fr);
-            s_rec[2 * ls + 1] = c < GEN_BIT ? make_float4(v.svx, v.svy, v.svw, v.sii) : make_float4(__uint_as_float(v.ord), 0.0f, 0.0f, 0.0f);
-            if (res)
-                for (int q = 0; q < v.n; q++) {
-                    s_ca[lc + q] = a.cur.ca[coff + q];
-                    s_cc[lc + q] = a.cur.cc[coff + q];
-                }
-        }
     }
-    __syncthreads();
+    if (a.dbg && lt == 0) {  // diagnostics: the CTA's load
+        int mxc = 0;
+        for (int k = 0; k < ncl; k++) mxc = max(mxc, s_cnt[s_clist[k]]);
+        unsigned long long* d = a.dbg + 64 + 4 * 1024 + bid * 4;
+        d[0] = (unsigned long long)L;
+        d[1] = (unsigned long long)nint | ((unsigned long long)(ncl - nint) << 32);
+        d[2] = (unsigned long long)ngh | ((unsigned long long)ngb << 32);
+        d[3] = (unsigned long long)nb | ((unsigned long long)mxc << 32);
+    }
+    grid_barrier(bar, bar_target);  // errors are in; every CTA agrees on going on
+    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;
 
-    auto view = [&](int c, int ls, RSlot& v) {
-        if (ls < SLOTCAP) {
-            const float4 r0 = s_rec[2 * ls];
-            const int pk = __float_as_int(r0.z);
-            if (pk >= 0) {
-                v.r1 = __float_as_int(r0.x); v.r2 = __float_as_int(r0.y); v.n = pk & 0xff; v.fr = r0.w;
-                if (c < GEN_BIT) {
-                    if ((v.r1 | v.r2) & VSTATIC) { const float4 r1 = s_rec[2 * ls + 1]; v.svx = r1.x; v.svy = r1.y; v.svw = r1.z; v.sii = r1.w; }
+    // One slot of one colour hop.  Bodies and (normally) contacts are in shared memory; r1, r2 are recomputed from the
+    // contact position exactly as Arbiter::pre_step / apply_impulse do (arbiter.rs:192-193, 236-237).
+    auto solve_slot = [&](int ls, unsigned pass) {
+        const int sb = s_sb[ls], sc = s_sc[ls];
+        const float fr = s_sf[ls];
+        const int r1 = sb & 0xffff, r2 = (sb >> 16) & 0xffff;
+        const int i1 = r1 & ~SREF_STATIC, i2 = r2 & ~SREF_STATIC;
+        const float4 q1 = s_bv[i1], q2 = s_bv[i2], m1 = s_bp[i1], m2 = s_bp[i2];
+        Vel v1, v2;
+        v1.v = mk(q1.x, q1.y); v1.w = q1.z; v2.v = mk(q2.x, q2.y); v2.w = q2.z;
+        const V2 p1 = mk(m1.x, m1.y), p2 = mk(m2.x, m2.y);
+        const float im1 = m1.z, ii1 = m1.w, im2 = m2.z, ii2 = m2.w;
+        if (sc >= 0) {
+            const int lc = sc >> 8, n = sc & 0xff;
+            for (int q = 0; q < n; q++) {
+                const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
+                const float pt0 = s_c2[lc + q];
+                ContactConst k0;
+                if (pass == 0u) {
+                    contact_prestep(mk(c0.x, c0.y), mk(c0.z, c0.w), c1.z, p1, p2, im1, ii1, im2, ii2, a.inv_dt, kbias, acc, c1.w, pt0, v1, v2, k0);
+                    s_c1[lc + q] = make_float4(k0.mass_n, k0.mass_t, k0.bias, c1.w);
                 } else {
-                    v.ord = __float_as_uint(s_rec[2 * ls + 1].x);
+                    k0.n = mk(c0.z, c0.w); k0.r1 = mk(c0.x, c0.y) - p1; k0.r2 = mk(c0.x, c0.y) - p2;
+                    k0.mass_n = c1.x; k0.mass_t = c1.y; k0.bias = c1.z;
+                    float pn = c1.w, pt = pt0;
+                    contact_apply(k0, fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
+                    if (acc) { s_c1[lc + q].w = pn; s_c2[lc + q] = pt; }
                 }
-                const int lc = pk >> 8;
-                v.ca = s_ca + lc; v.cb = s_cb + lc; v.cc = s_cc + lc;
-                return;
+            }
+        } else {  // an own interior slot beyond the shared-memory budget: the global contact arrays are its working storage
+            const int2 mt = a.cur.meta[__ldcg(&order[ls])];
+            for (int q = 0; q < mt.x; q++) {
+                const float4 ca = a.cur.ca[mt.y + q], cc = a.cur.cc[mt.y + q];
+                ContactConst k0;
+                if (pass == 0u) {
+                    const float4 cd = a.cur.cd[mt.y + q];
+                    contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, p1, p2, im1, ii1, im2, ii2, a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
+                    a.cur.ca[mt.y + q] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
+                    a.cur.cb[mt.y + q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
+                    a.cur.cc[mt.y + q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
+                } else {
+                    const float4 cb = a.cur.cb[mt.y + q];
+                    k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
+                    k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
+                    float pn = cc.y, pt = cc.z;
+                    contact_apply(k0, fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
+                    if (acc) a.cur.cc[mt.y + q] = make_float4(cc.x, pn, pt, cc.w);
+                }
             }
         }
-        const int e = __ldcg(&order[ls]);
-        describe(e, c, v);
-        const int coff = a.cur.meta[e].y;
-        v.ca = a.cur.ca + coff; v.cb = a.cur.cb + coff; v.cc = a.cur.cc + coff;
+        if (!(r1 & SREF_STATIC)) s_bv[i1] = make_float4(v1.v.x, v1.v.y, v1.w, 0.0f);
+        if (!(r2 & SREF_STATIC)) s_bv[i2] = make_float4(v2.v.x, v2.v.y, v2.w, 0.0f);
     };
-    // body access of an interior slot: shared memory, or the constant velocity of a static body
-    auto iget = [&](const RSlot& v, int r, Vel& o, float& im, float& ii) {
-        if (r & VSTATIC) { o.v = mk(v.svx, v.svy); o.w = v.svw; im = 0.0f; ii = v.sii; }
-        else { const float4 q = s_bv[r]; const float2 m = s_bm[r]; o.v = mk(q.x, q.y); o.w = q.z; im = m.x; ii = m.y; }
+    int pa_ = 0;
+    auto pstamp = [&](unsigned pass) {  // diagnostics: the phases of pass 5 in every CTA
+        if (a.dbg && lt == 0 && pass == 5u && pa_ < 4) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[64 + bid * 4 + pa_++] = t; }
     };
-    auto iput = [&](int r, const Vel& o) {
-        if (!(r & VSTATIC)) s_bv[r] = make_float4(o.v.x, o.v.y, o.w, 0.0f);
-    };
-    auto prestep_contacts = [&](const RSlot& v, int e, float im1, float ii1, float im2, float ii2, Vel& v1, Vel& v2) {
-        const int2 b = a.cur.bodies[e];
-        const int coff = a.cur.meta[e].y;
-        const float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
-        for (int q = 0; q < v.n; q++) {
-            const float4 ca = v.ca[q], cc = v.cc[q], cd = a.cur.cd[coff + q];
-            ContactConst k0;
-            contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, mk(p1.x, p1.y), mk(p2.x, p2.y), im1, ii1, im2, ii2,
-                            a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
-            v.ca[q] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
-            v.cb[q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
-            v.cc[q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
-        }
-    };
-    auto apply_contacts = [&](const RSlot& v, float im1, float ii1, float im2, float ii2, Vel& v1, Vel& v2) {
-        for (int q = 0; q < v.n; q++) {
-            const float4 ca = v.ca[q], cb = v.cb[q], cc = v.cc[q];
-            ContactConst k0;
-            k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
-            k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
-            float pn = cc.y, pt = cc.z;
-            contact_apply(k0, v.fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
-            if (acc) v.cc[q] = make_float4(cc.x, pn, pt, cc.w);
-        }
-    };
-    // one pass over this CTA's slots: interior colours in shared memory, export, generic colours through L2
-    const bool probe = a.dbg != nullptr && bid == (int)gridDim.x / 2 && lt == 0;
-    int pk_ = 16;
-    auto pstamp = [&](unsigned pass) {
-        if (probe && pass == 5u && pk_ < 64) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[pk_++] = t; }
-    };
-    auto sweep = [&](unsigned pass) {
-        pstamp(pass);
-        for (int k = 0; k < nint; k++) {
+    auto colours = [&](unsigned pass, int k0, int k1) {  // colour hops k0..k1 of the list
+        for (int k = k0; k < k1; k++) {
             const int c = s_clist[k], cnt = s_cnt[c], base = s_cstart[c];
-            for (int i = lt; i < cnt; i += T) {
-                RSlot v;
-                view(c, base + i, v);
-                Vel v1, v2;
-                float im1, ii1, im2, ii2;
-                iget(v, v.r1, v1, im1, ii1);
-                iget(v, v.r2, v2, im2, ii2);
-                if (pass == 0u) prestep_contacts(v, __ldcg(&order[base + i]), im1, ii1, im2, ii2, v1, v2);
-                else apply_contacts(v, im1, ii1, im2, ii2, v1, v2);
-                iput(v.r1, v1);
-                iput(v.r2, v2);
-            }
+            for (int i = lt; i < cnt; i += T) solve_slot(base + i, pass);
             __syncthreads();
         }
-        pstamp(pass);
-        for (int k = lt; k < nbnd; k += T) {  // export: version pass*Dv + 1
-            const int pk = s_bnd[k], lb = pk & 0xfffff;
-            const float4 q = s_bv[lb];
-            Vel o; o.v = mk(q.x, q.y); o.w = q.z;
-            io.put(s_bndg[k], o, pass * (unsigned)(pk >> 20) + 1u);
-        }
-        for (int k = nint; k < ncl; k++) {
-            const int c = s_clist[k], cnt = s_cnt[c], base = s_cstart[c];
-            for (int i = lt; i < cnt; i += T) {
-                RSlot v;
-                view(c, base + i, v);
-                const int b1 = v.r1 & ~VSTATIC, b2 = v.r2 & ~VSTATIC;
-                const unsigned e1 = pass * (v.ord & 0xffu) + 1u + ((v.ord >> 8) & 0xffu), e2 = pass * ((v.ord >> 16) & 0xffu) + 1u + (v.ord >> 24);
-                Vel v1, v2;
-                float im1, ii1, im2, ii2;
-                io.wait2(v.r1, e1, v1, im1, ii1, v.r2, e2, v2, im2, ii2);
-                if (pass == 0u) prestep_contacts(v, __ldcg(&order[base + i]), im1, ii1, im2, ii2, v1, v2);
-                else apply_contacts(v, im1, ii1, im2, ii2, v1, v2);
-                if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1u);
-                if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1u);
-            }
-            pstamp(pass);
-        }
     };
-    // import: the boundary bodies as the generic constraints (and joints) of the previous pass left them
-    auto import_boundary = [&](unsigned pass) {
+    // One pass: interior colours; boundary bodies out (plane `pass` of the export records); ghosts in; generic colours.
+    auto sweep = [&](unsigned pass) {
+        pstamp(pass);
+        colours(pass, 0, nint);
+        pstamp(pass);
+        BodyIO xio{a.xrec + (size_t)pass * 2 * (size_t)a.B, a.sleep_ns, &cn->err};
+        const unsigned tag = (a.step_tag << 8) | pass;
         for (int k = lt; k < nbnd; k += T) {
-            const int pk = s_bnd[k], lb = pk & 0xfffff, b = s_bndg[k];
-            const unsigned expect = pass * (unsigned)(pk >> 20);
+            const float4 q = s_bv[s_bnd[k]];
+            Vel o; o.v = mk(q.x, q.y); o.w = q.z;
+            xio.put(s_bndg[k], o, tag);
+        }
+        for (int g = lt; g < ngb; g += T) {
+            const int z = s_gb[g];
+            if (z & GHOST_FLAG) continue;  // static
             Vel o;
             float im, ii;
             unsigned spins = 0;
-            while (!io.try_get(b, expect, true, o, im, ii)) {
+            while (!xio.try_get(z, tag, true, o, im, ii)) {
                 if ((++spins & 0xfffu) == 0u) {
                     if (*(volatile int*)&cn->err == SYLT_ERR_INTERNAL) break;
                     if (spins > (1u << 23)) { atomicExch(&cn->err, SYLT_ERR_INTERNAL); break; }
                 }
             }
-            s_bv[lb] = make_float4(o.v.x, o.v.y, o.w, 0.0f);
+            s_bv[nb + g] = make_float4(o.v.x, o.v.y, o.w, 0.0f);
         }
         __syncthreads();
-    };
-    auto joint_expect = [&](int j, int2 b, unsigned pass, unsigned& e1, unsigned& e2) {
-        const int2 jr = a.jrank[j];
-        const unsigned da1 = (unsigned)__popcll(__ldcg(&a.used[b.x])), da2 = (unsigned)__popcll(__ldcg(&a.used[b.y]));
-        e1 = pass * (da1 + (unsigned)a.jdeg[b.x] + 1u) + 1u + da1 + (unsigned)jr.x;
-        e2 = pass * (da2 + (unsigned)a.jdeg[b.y] + 1u) + 1u + da2 + (unsigned)jr.y;
+        pstamp(pass);
+        colours(pass, nint, ncl);
+        pstamp(pass);
     };
 
     stamp(3);
-    // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228) then Joint::pre_step (joint.rs:57-115)
+    // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228).  The barrier keeps every read of the global contact arrays and
+    //         of the poses by a replica ahead of the owner's later writes.
     sweep(0u);
-    for (int c = 0; c < a.n_joint_colors; c++) {
-        for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
-            const int j = a.jorder[k];
-            const int2 b = a.jbodies[j];
-            const float4 p1 = a.pose[b.x], p2 = a.pose[b.y];
-            const float2 r1c = a.rotc[b.x], r2c = a.rotc[b.y];
-            const int r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0), r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
-            unsigned e1, e2;
-            joint_expect(j, b, 0u, e1, e2);
-            Vel v1, v2;
-            float im1, ii1, im2, ii2;
-            io.wait2(r1, e1, v1, im1, ii1, r2, e2, v2, im2, ii2);
-            const float4 la = a.jla[j];
-            const float2 pr = a.jparam[j];
-            const float2 pa = a.jp[j];
-            V2 pacc = mk(pa.x, pa.y);
-            JointConst jc;
-            M2 bad;
-            Vel w1 = v1, w2 = v2;
-            const bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), r1c.x, r1c.y, mk(p2.x, p2.y), r2c.x, r2c.y,
-                                          im1, ii1, im2, ii2, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, w1, w2, jc, &bad, a.fix_inverse != 0);
-            a.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
-            if (!ok) {  // quirk Q-15: NoInverse aborts the step before the iterations
-                if (atomicCAS(&cn->err, 0, SYLT_ERR_NO_INVERSE) == 0) {
-                    cn->err_joint = j;
-                    cn->badk[0] = bad.c1.x; cn->badk[1] = bad.c2.x; cn->badk[2] = bad.c1.y; cn->badk[3] = bad.c2.y;
-                }
-                w1 = v1; w2 = v2;  // velocities untouched, versions still advance so that nobody waits forever
-            } else {
-                a.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
-                a.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
-                a.jp[j] = make_float2(pacc.x, pacc.y);
-            }
-            if (!(r1 & VSTATIC)) io.put(b.x, w1, e1 + 1u);
-            if (!(r2 & VSTATIC)) io.put(b.y, w2, e2 + 1u);
-        }
-    }
     grid_barrier(bar, bar_target);
-    const bool aborted = *(volatile int*)&cn->err == SYLT_ERR_NO_INVERSE;
-    const int passes = aborted ? 0 : a.iterations;
     stamp(4);
-
-    // ---- 5. passes 1..I: iterations x (arbiter colours, joint colours)   (world.rs:132-140)
-    for (int it = 1; it <= passes; it++) {
-        pstamp((unsigned)it);
-        import_boundary((unsigned)it);
-        sweep((unsigned)it);
-        for (int c = 0; c < a.n_joint_colors; c++) {
-            for (int k = a.jcolor_start[c] + tid; k < a.jcolor_start[c + 1]; k += nth) {
-                const int j = a.jorder[k];
-                const int2 b = a.jbodies[j];
-                const int r1 = b.x | ((a.bflags[b.x] & FLAG_STATIC) ? VSTATIC : 0), r2 = b.y | ((a.bflags[b.y] & FLAG_STATIC) ? VSTATIC : 0);
-                unsigned e1, e2;
-                joint_expect(j, b, (unsigned)it, e1, e2);
-                Vel v1, v2;
-                float im1, ii1, im2, ii2;
-                io.wait2(r1, e1, v1, im1, ii1, r2, e2, v2, im2, ii2);
-                const float4 r = a.jr[j], mm = a.jm[j];
-                const float2 bs = a.jbias[j], pa = a.jp[j];
-                JointConst jc;
-                jc.r1 = mk(r.x, r.y); jc.r2 = mk(r.z, r.w); jc.bias = mk(bs.x, bs.y);
-                jc.m = mk(mk(mm.x, mm.z), mk(mm.y, mm.w));
-                jc.softness = a.jparam[j].x;
-                V2 pacc = mk(pa.x, pa.y);
-                joint_apply(jc, im1, ii1, im2, ii2, pacc, v1, v2);
-                a.jp[j] = make_float2(pacc.x, pacc.y);
-                if (!(r1 & VSTATIC)) io.put(b.x, v1, e1 + 1u);
-                if (!(r2 & VSTATIC)) io.put(b.y, v2, e2 + 1u);
-            }
-        }
-    }
-    import_boundary((unsigned)(passes + 1));
+    // ---- 5. passes 1..I: apply_impulse (world.rs:132-140)
+    for (int it = 1; it <= a.iterations; it++) sweep((unsigned)it);
 
     stamp(5);
-    // ---- 6. write the shared-memory resident contacts back (warm start of the next step, read-back)
-    for (int ls = lt; ls < Ls; ls += T) {
-        const int pk = __float_as_int(s_rec[2 * ls].z);
-        if (pk < 0) continue;
+    // ---- 6. the owner writes its shared-memory resident contacts back (warm start of the next step, read-back)
+    for (int ls = lt; ls < L; ls += T) {
+        const int sc = s_sc[ls];
         const int e = __ldcg(&order[ls]);
-        const int coff = a.cur.meta[e].y, lc = pk >> 8, n = pk & 0xff;
+        if (sc < 0 || (e & GHOST_FLAG)) continue;
+        const int sb = s_sb[ls];
+        const float4 m1 = s_bp[sb & 0x7fff], m2 = s_bp[(sb >> 16) & 0x7fff];
+        const int coff = a.cur.meta[e].y, lc = sc >> 8, n = sc & 0xff;
         for (int q = 0; q < n; q++) {
-            a.cur.ca[coff + q] = s_ca[lc + q];
-            a.cur.cb[coff + q] = s_cb[lc + q];
-            a.cur.cc[coff + q] = s_cc[lc + q];
+            const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
+            const V2 r1 = mk(c0.x, c0.y) - mk(m1.x, m1.y), r2 = mk(c0.x, c0.y) - mk(m2.x, m2.y);
+            a.cur.ca[coff + q] = make_float4(c0.z, c0.w, r1.x, r1.y);
+            a.cur.cb[coff + q] = make_float4(r2.x, r2.y, c1.x, c1.y);
+            a.cur.cc[coff + q] = make_float4(c1.z, c1.w, s_c2[lc + q], a.cur.cc[coff + q].w);
         }
     }
 
     stamp(6);
-    // ---- 7. integrate the region's bodies (world.rs:143-150; static bodies too, quirk Q-16).  After a NoInverse the
-    //         step stops before the integration (quirk Q-15).
+    // ---- 7. integrate the region's bodies (world.rs:143-150; static bodies too, quirk Q-16)
     for (int lb = lt; lb < nb; lb += T) {
         const int b = a.reg_bodies[rb0 + lb];
         const float4 q = s_bv[lb];
         a.vel[b] = make_float4(q.x, q.y, q.z, 0.0f);
-        if (aborted) continue;
         float4 p = a.pose[b];
         V2 np = mk(p.x, p.y) + mk(q.x, q.y) * a.dt;
         p.x = np.x; p.y = np.y;
@@ -1531,6 +1560,44 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         a.force[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
     stamp(7);
+}
+
+// Re-cut the regions along the stored spatial order of the bodies (`perm`, from the last host-side partition) so that
+// every region gets the same share of the work: weight of a body = 1 + 2 x (arbiters it owned last step), floored at the
+// average weight so that no region gets more than twice the average number of bodies (the shared-memory room `rbcap`).
+// Regions are consecutive runs of `perm`, so perm itself is the CSR body list.  One CTA; runs every `regions_period` steps.
+constexpr int REBAL_THREADS = 1024;
+__global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const int* perm, const int* old_row_start, int* region_of, int* lidx,
+                                                            int* reg_start) {
+    __shared__ long long sh[34];
+    __shared__ int s_first[1025];
+    const int lt = threadIdx.x, T = blockDim.x;
+    const int chunk = (B + T - 1) / T, q0 = min(lt * chunk, B), q1 = min(q0 + chunk, B);
+    for (int g = lt; g <= G; g += T) s_first[g] = B;
+    long long sum = 0;
+    for (int i = q0; i < q1; i++) { const int b = perm[i]; sum += 1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b]); }
+    long long total;
+    block_excl_scan<long long>(sum, &total, sh);
+    const long long wmin = (total + B - 1) / max(B, 1);
+    long long esum = 0;
+    for (int i = q0; i < q1; i++) { const int b = perm[i]; esum += max((long long)(1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b])), wmin); }
+    long long etotal;
+    long long ex = block_excl_scan<long long>(esum, &etotal, sh);
+    for (int i = q0; i < q1; i++) {
+        const int b = perm[i];
+        const int reg = (int)min((long long)(G - 1), ex * (long long)G / max(etotal, 1ll));
+        ex += max((long long)(1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b])), wmin);
+        region_of[b] = reg;
+        atomicMin(&s_first[reg], i);
+    }
+    __syncthreads();
+    if (lt == 0) {  // empty regions start where the next one starts
+        s_first[G] = B;
+        for (int g = G - 1; g >= 0; g--) if (s_first[g] > s_first[g + 1]) s_first[g] = s_first[g + 1];
+    }
+    __syncthreads();
+    for (int g = lt; g <= G; g += T) reg_start[g] = s_first[g];
+    for (int i = q0; i < q1; i++) { const int b = perm[i]; lidx[b] = i - s_first[region_of[b]]; }
 }
 
 __global__ void k_collide_pairs(int n, const SyltBodyDesc* A, const SyltBodyDesc* Bd, const float2* lverts, const int* loff,
@@ -1649,16 +1716,18 @@ struct SyltWorld {
 
     // regions (k_solve_regions): spatial partition of the bodies, recomputed on the host when bodies were added or the
     // share of cross-region arbiters has grown
-    DBuf<int> region_of, lidx, reg_start, reg_bodies;
+    DBuf<int> region_of, lidx, reg_start, reg_bodies, gadj, cone_buf;
+    DBuf<ulonglong2> xrec;
+    int ghost_cap = 512, region_slots = 4096;
+    unsigned step_tag = 0;
     int regions_mode = 0;            // SYLT_REGIONS: 0 = never (default: experimental), 1 = worlds of at least regions_min_bodies, 2 = always
-    int regions_min_bodies = 8192, regions_count = 0, regions_period = 64;
+    int regions_min_bodies = 8192, regions_count = 0, regions_period = 64, regions_resort = 4096;
     bool regions_on = false;         // the partition on the device is valid for the current bodies
     bool part_dirty = true;          // bodies were added / the mode may have changed
     bool last_regions = false;       // the last enqueued step ran k_solve_regions
     bool recolor_all = false;        // next step: ignore last step's colours (they encode the old partition)
     int n_regions = 0, rbcap = 0, reg_smem_contacts = 0;
-    int64_t steps_since_part = 0;
-    double generic_after_part = -1.0;  // share of generic arbiters on the first step after the last repartition
+    int64_t steps_since_part = 0, steps_since_sort = 0;
     size_t solve_budget = 0;
 
     int64_t cap_pairs = 0, cap_arb = 0, cap_con = 0;
@@ -1878,7 +1947,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->uncolored.ensure((size_t)ca));
         SYLT_CUDA(w->uncolored2.ensure((size_t)ca));
         SYLT_CUDA(w->prop.ensure((size_t)ca));
-        SYLT_CUDA(w->order.ensure((size_t)ca));
+        SYLT_CUDA(w->order.ensure((size_t)ca + (size_t)w->coop_blocks * CONE_CAP));  // + the ghost slots of k_solve_regions
         for (int k = 0; k < 2; k++) {
             SyltWorld::ArbBufs& a = w->arb[k];
             const bool keep_set = (k != w->cur) && w->have_old && w->have_last;  // last step's arbiters survive a regrow
@@ -1936,16 +2005,12 @@ int repartition(SyltWorld* w) {
     const size_t B = w->hb.size();
     w->part_dirty = false;
     w->steps_since_part = 0;
-    w->generic_after_part = -1.0;
+    w->steps_since_sort = 0;
     const bool was_on = w->regions_on;
-    int G = w->regions_count > 0 ? std::min(w->regions_count, w->coop_blocks) : w->coop_blocks;
+    int G = std::min(1024, w->regions_count > 0 ? std::min(w->regions_count, w->coop_blocks) : w->coop_blocks);
     bool on = w->regions_mode == 2 || (w->regions_mode == 1 && B >= (size_t)w->regions_min_bodies);
-    if (B == 0 || G < 1) on = false;
-    const size_t per = on ? (B + (size_t)G - 1) / (size_t)G : 0;
-    const size_t rbcap = (per + 3) & ~(size_t)3;
-    // shared memory: 32 bytes per body of the region, the slot records, the rest holds contacts
-    const size_t fixed = rbcap * 32 + (size_t)w->smem_slots * 32 + (((size_t)w->smem_slots + 3) & ~(size_t)3) * 4;
-    if (on && (per >= (1u << 20) || fixed + 4096 > w->solve_budget)) on = false;  // regions too large for an SM: the plain dataflow solver
+    if (B == 0 || G < 1 || !w->hj.empty() || w->iterations + 1 > (uint32_t)MAX_PLANES) on = false;  // joints / long solves: k_solve
+    if (on && (B + (size_t)G - 1) / (size_t)G > 2048) on = false;  // regions too large for an SM: k_solve
     if (!on) {
         w->regions_on = false;
         if (was_on) w->recolor_all = true;
@@ -1968,41 +2033,82 @@ int repartition(SyltWorld* w) {
     const double xs = x1 > x0 ? (double)x1 - x0 : 1.0, ys = y1 > y0 ? (double)y1 - y0 : 1.0;
     int SX = (int)std::lround(std::sqrt((double)G * xs / ys));
     SX = std::max(1, std::min(G, SX));
+    // weight of a body = the shared memory it will need: its own record plus the slots and contacts of the arbiters it owns
+    // (last step's rows; a fresh scene has none and splits by body count)
+    std::vector<double> wt(B, 1.0);
+    if (w->have_old && w->B_old > 0) {
+        const size_t Bo = std::min(B, (size_t)w->B_old);
+        std::vector<int> rs(Bo + 1);
+        SYLT_CUDA(cudaMemcpy(rs.data(), w->arb[w->cur ^ 1].row_start.p, (Bo + 1) * sizeof(int), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < Bo; i++) wt[i] = 1.0 + 2.0 * (double)std::max(0, rs[i + 1] - rs[i]);
+    }
     std::vector<int> idx(B);
     for (size_t i = 0; i < B; i++) idx[i] = (int)i;
     std::sort(idx.begin(), idx.end(), [&](int p, int q) { return kx[(size_t)p] != kx[(size_t)q] ? kx[(size_t)p] < kx[(size_t)q] : p < q; });
-    for (int sx = 0; sx < SX; sx++) {
-        size_t lo = B * (size_t)sx / (size_t)SX, hi = B * (size_t)(sx + 1) / (size_t)SX;
-        std::sort(idx.begin() + (long)lo, idx.begin() + (long)hi,
-                  [&](int p, int q) { return ky[(size_t)p] != ky[(size_t)q] ? ky[(size_t)p] < ky[(size_t)q] : p < q; });
+    double total = 0.0;
+    for (size_t i = 0; i < B; i++) total += wt[i];
+    {   // strips of equal weight along x, each sorted along y
+        size_t lo = 0;
+        double acc = 0.0;
+        for (int sx = 0; sx < SX; sx++) {
+            size_t hi = lo;
+            const double upto = total * (double)(sx + 1) / (double)SX;
+            while (hi < B && (sx == SX - 1 || acc + wt[(size_t)idx[hi]] <= upto)) acc += wt[(size_t)idx[hi++]];
+            std::sort(idx.begin() + (long)lo, idx.begin() + (long)hi,
+                      [&](int p, int q) { return ky[(size_t)p] != ky[(size_t)q] ? ky[(size_t)p] < ky[(size_t)q] : p < q; });
+            lo = hi;
+        }
     }
-    std::vector<int> region_of(B), lidx(B), reg_start((size_t)G + 1, 0), reg_bodies(B);
-    for (size_t r = 0; r < B; r++) {
-        const int reg = (int)(r * (size_t)G / B);
-        region_of[(size_t)idx[r]] = reg;
-        reg_start[(size_t)reg + 1]++;
+    // regions = consecutive runs of equal weight in that order; the order itself is the CSR body list and stays on the device
+    // for k_rebalance.  A body weighs at least the average, so no region holds more than twice the average number of bodies.
+    std::vector<int> region_of(B), lidx(B), reg_start((size_t)G + 1, 0);
+    const std::vector<int>& reg_bodies = idx;
+    size_t maxper = 2 * ((B + (size_t)G - 1) / (size_t)G) + 16;
+    {
+        const double wmin = total / (double)B;
+        double etotal = 0.0;
+        for (size_t i = 0; i < B; i++) etotal += std::max(wt[i], wmin);
+        double acc = 0.0;
+        std::vector<int> cnt((size_t)G, 0);
+        for (size_t r = 0; r < B; r++) {
+            const int reg = std::min(G - 1, (int)(acc * (double)G / etotal));
+            acc += std::max(wt[(size_t)idx[r]], wmin);
+            region_of[(size_t)idx[r]] = reg;
+            lidx[(size_t)idx[r]] = cnt[(size_t)reg]++;
+        }
+        for (int g = 0; g < G; g++) { reg_start[(size_t)g + 1] = reg_start[(size_t)g] + cnt[(size_t)g]; maxper = std::max(maxper, (size_t)cnt[(size_t)g]); }
     }
-    size_t maxper = 0;
-    for (int g = 0; g < G; g++) { maxper = std::max(maxper, (size_t)reg_start[(size_t)g + 1]); reg_start[(size_t)g + 1] += reg_start[(size_t)g]; }
-    std::vector<int> fill(reg_start.begin(), reg_start.end() - 1);
-    for (size_t i = 0; i < B; i++) {  // bodies of a region in ascending index order
-        const int reg = region_of[i];
-        lidx[i] = fill[(size_t)reg] - reg_start[(size_t)reg];
-        reg_bodies[(size_t)fill[(size_t)reg]++] = (int)i;
-    }
-    if (maxper > rbcap) { w->regions_on = false; if (was_on) w->recolor_all = true; return SYLT_OK; }
+    // shared memory: 40 bytes per body of the region, 36 per ghost body, 12 per slot; the rest holds contacts (36 bytes each) and,
+    // during set-up, the three hash tables of the cone walk
+    const size_t rbcap = (maxper + 3) & ~(size_t)3;
+    if (rbcap + (size_t)w->ghost_cap > 32768) { w->regions_on = false; if (was_on) w->recolor_all = true; return SYLT_OK; }
+    const size_t fixed = rbcap * 40 + (size_t)w->ghost_cap * 36 + (size_t)w->region_slots * 12 + 64;
+    if (fixed + (size_t)3 * HASH_CAP * 4 + 4096 > w->solve_budget) { w->regions_on = false; if (was_on) w->recolor_all = true; return SYLT_OK; }
     SYLT_CUDA(w->region_of.ensure(B));
     SYLT_CUDA(w->lidx.ensure(B));
     SYLT_CUDA(w->reg_bodies.ensure(B));
     SYLT_CUDA(w->reg_start.ensure((size_t)G + 1));
+    SYLT_CUDA(w->gadj.ensure(B * (size_t)GADJ));
+    SYLT_CUDA(w->cone_buf.ensure((size_t)w->coop_blocks * CONE_CAP));
+    {   // export planes: a record is valid when its tag matches (step_tag, pass); fresh memory must not hold a look-alike
+        const size_t oldcap = w->xrec.cap;
+        SYLT_CUDA(w->xrec.ensure((size_t)MAX_PLANES * 2 * B));
+        if (w->xrec.cap != oldcap) SYLT_CUDA(cudaMemsetAsync(w->xrec.p, 0, w->xrec.cap * sizeof(ulonglong2), w->stream));
+    }
     SYLT_CUDA(cudaMemcpyAsync(w->region_of.p, region_of.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
     SYLT_CUDA(cudaMemcpyAsync(w->lidx.p, lidx.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
     SYLT_CUDA(cudaMemcpyAsync(w->reg_bodies.p, reg_bodies.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
     SYLT_CUDA(cudaMemcpyAsync(w->reg_start.p, reg_start.data(), ((size_t)G + 1) * sizeof(int), cudaMemcpyHostToDevice, w->stream));
     SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    if (w->timing) {
+        std::vector<double> rw((size_t)G, 0.0);
+        for (size_t i = 0; i < B; i++) rw[(size_t)region_of[i]] += wt[i];
+        fprintf(stderr, "repartition: %d regions (%d strips), bodies per region <= %zu, weight max/avg %.2f, contacts room %zu\n", G, SX, maxper,
+                *std::max_element(rw.begin(), rw.end()) / (total / G), (w->solve_budget - fixed) / 36);
+    }
     w->n_regions = G;
     w->rbcap = (int)rbcap;
-    w->reg_smem_contacts = (int)((w->solve_budget - fixed) / 48);
+    w->reg_smem_contacts = (int)(((w->solve_budget - fixed) / 36) & ~(size_t)3);
     w->regions_on = true;
     w->recolor_all = true;
     return SYLT_OK;
@@ -2046,6 +2152,13 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->sincl64.p, 0, 2);
     if (e) return e;
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
+    if (w->regions_on && full_step && w->have_old && w->B_old == B && w->steps_since_part >= w->regions_period) {
+        // re-cut the regions by last step's load (device side, no synchronisation); the colours encode the old cut
+        k_rebalance<<<1, REBAL_THREADS, 0, st>>>(B, w->n_regions, w->reg_bodies.p, old.row_start, w->region_of.p, w->lidx.p, w->reg_start.p);
+        w->launches++;
+        w->steps_since_part = 0;
+        w->recolor_all = true;
+    }
     const int keep_colors = w->recolor_all ? 0 : 1;
     w->recolor_all = false;
     if (w->any_poly)
@@ -2080,9 +2193,16 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.slack_pct = w->slack_pct; a.fix_inverse = w->fix_inverse; a.dbg = w->timing ? w->dbg.p : nullptr;
     if (w->regions_on) {
         a.region_of = w->region_of.p; a.lidx = w->lidx.p; a.reg_start = w->reg_start.p; a.reg_bodies = w->reg_bodies.p;
-        a.n_regions = w->n_regions; a.rbcap = w->rbcap; a.smem_contacts = w->reg_smem_contacts;
+        a.n_regions = w->n_regions; a.rbcap = w->rbcap; a.smem_contacts = w->reg_smem_contacts; a.ghost_cap = w->ghost_cap; a.smem_slots = w->region_slots;
+        a.gadj = w->gadj.p; a.cone_buf = w->cone_buf.p; a.xrec = w->xrec.p;
+        if (++w->step_tag > 0xfffff0u) {  // 24-bit tags: start over with clean planes
+            SYLT_CUDA(cudaMemsetAsync(w->xrec.p, 0, w->xrec.cap * sizeof(ulonglong2), st));
+            w->step_tag = 1;
+        }
+        a.step_tag = w->step_tag;
         SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_regions, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_budget, st));
         w->steps_since_part++;
+        w->steps_since_sort++;
         w->last_regions = true;
     } else {
         w->last_regions = false;
@@ -2094,6 +2214,41 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     return SYLT_OK;
 }
 
+// SYLT_SOLVER_TIMING=1: section times of the last step's solver kernel (%globaltimer stamps of CTA 0) and, for
+// k_solve_regions, the phases of pass 5 over all CTAs plus the load of the slowest / median / fastest CTA.
+void print_solver_timing(SyltWorld* w) {
+    if (w->last.err)
+        fprintf(stderr, "step error %d (why %d, max slots %d, ghosts %d, uncoloured %d)\n", w->last.err, w->last.why, w->last.max_slots, w->last.n_ghost,
+                w->last.n_uncolored);
+    const int G = w->coop_blocks;
+    std::vector<unsigned long long> t(64 + 8 * 1024);
+    if (cudaMemcpy(t.data(), w->dbg.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    if (w->last_regions && t[64] && G <= 1024) {
+        const unsigned long long *pc = &t[64], *ld = &t[64 + 4 * 1024];  // per CTA: 4 stamps of pass 5; 4 words of load figures
+        double mn[3] = {1e30, 1e30, 1e30}, mx[3] = {0, 0, 0}, sm[3] = {0, 0, 0};
+        for (int c = 0; c < G; c++)
+            for (int k = 0; k < 3; k++) {
+                const double d = (double)(pc[c * 4 + k + 1] - pc[c * 4 + k]) * 1e-3;
+                mn[k] = std::min(mn[k], d); mx[k] = std::max(mx[k], d); sm[k] += d;
+            }
+        std::vector<int> ord((size_t)G);
+        for (int c = 0; c < G; c++) ord[(size_t)c] = c;
+        std::sort(ord.begin(), ord.end(), [&](int x, int y) { return pc[x * 4 + 1] - pc[x * 4] > pc[y * 4 + 1] - pc[y * 4]; });
+        for (int q : {0, G / 2, G - 1}) {
+            const int c = ord[(size_t)q];
+            const unsigned long long* d = &ld[c * 4];
+            fprintf(stderr, "  CTA %3d: interior %.2f us | %llu slots, %llu + %llu colours, ghosts %llu arbiters / %llu bodies, %llu own bodies, widest colour %llu\n", c,
+                    (double)(pc[c * 4 + 1] - pc[c * 4]) * 1e-3, d[0], d[1] & 0xffffffffull, d[1] >> 32, d[2] & 0xffffffffull, d[2] >> 32,
+                    d[3] & 0xffffffffull, d[3] >> 32);
+        }
+        fprintf(stderr, "  pass 5, all CTAs [us] min/avg/max: interior %.2f/%.2f/%.2f  export+import %.2f/%.2f/%.2f  generic %.2f/%.2f/%.2f\n", mn[0], sm[0] / G, mx[0],
+                mn[1], sm[1] / G, mx[1], mn[2], sm[2] / G, mx[2]);
+    }
+    fprintf(stderr, "k_solve sections [us]: colour %.1f order %.1f residency %.1f pass0 %.1f iterations %.1f writeback %.1f integrate %.1f total %.1f\n",
+            (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3,
+            (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
+}
+
 // After the queue drains: read the counters of the last step and update host-side bookkeeping.
 int finish(SyltWorld* w) {
     SYLT_CUDA(cudaStreamSynchronize(w->stream));
@@ -2103,21 +2258,8 @@ int finish(SyltWorld* w) {
     w->have_last = true;
     if (w->last_regions) {
         w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
-        if (w->generic_after_part < 0.0 && w->last.n_arb > 0) w->generic_after_part = (double)w->last.n_generic / (double)w->last.n_arb;
     }
-    if (w->timing) {  // diagnostics: k_solve section times of the last step (CTA 0's view)
-        unsigned long long t[64];
-        if (cudaMemcpy(t, w->dbg.p, sizeof t, cudaMemcpyDeviceToHost) == cudaSuccess) {
-            if (w->last_regions && t[16]) {  // pass 5 of a CTA in the middle of the grid: import | interior colours | export + first generic colour | further generic colours
-                fprintf(stderr, "k_solve_regions pass 5 [us]:");
-                for (int k = 17; k < 64 && t[k]; k++) fprintf(stderr, " %.2f", (t[k] - t[k - 1]) * 1e-3);
-                fprintf(stderr, "\n");
-            }
-            fprintf(stderr, "k_solve sections [us]: colour %.1f order %.1f residency %.1f pass0 %.1f iterations %.1f writeback %.1f integrate %.1f total %.1f\n",
-                    (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3,
-                    (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
-        }
-    }
+    if (w->timing) print_solver_timing(w);
     w->last_was_step = w->inflight_full;
     w->last_iterations = w->iterations;
     return w->last.err;
@@ -2128,18 +2270,11 @@ int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
     int e = flush(w);
     if (e) return e;
     if (body_order_violated(w->hb)) return SYLT_ERR_BODY_ORDER;
-    {   // regions: (re)partition when bodies were added, or when the bodies have mixed: the share of cross-region arbiters
-        // has grown well beyond what the last partition started with (checked between step_n calls only)
-        bool again = w->part_dirty;
-        if (!again && w->regions_on && w->have_last && w->last_regions && w->steps_since_part >= w->regions_period && w->last.n_arb > 0 &&
-            w->generic_after_part >= 0.0) {
-            const double share = (double)w->last.n_generic / (double)w->last.n_arb;
-            again = share > 1.5 * w->generic_after_part + 0.05;
-        }
-        if (again) {
-            e = repartition(w);
-            if (e) return e;
-        }
+    // regions: partition on the host (a spatial sort) when bodies were added and, rarely, to refresh the spatial order the
+    // device-side k_rebalance cuts along
+    if (w->part_dirty || (w->regions_on && w->steps_since_sort >= w->regions_resort)) {
+        e = repartition(w);
+        if (e) return e;
     }
     if (!w->inflight) SYLT_CUDA(cudaMemsetAsync(w->counters.p, 0, offsetof(Counters, n_pairs), w->stream));  // sticky error fields
     const int B = (int)w->hb.size();
@@ -2202,8 +2337,8 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     if (const char* ev = getenv("SYLT_SOLVER_SLEEP_NS")) w->sleep_ns = std::max(0, atoi(ev));
     if (const char* ev = getenv("SYLT_SOLVER_SLACK")) w->slack_pct = std::max(0, atoi(ev));
     if (const char* ev = getenv("SYLT_SOLVER_TIMING")) w->timing = atoi(ev) != 0;
-    SYLT_CUDA(w->dbg.ensure(64));
-    SYLT_CUDA(cudaMemset(w->dbg.p, 0, 64 * sizeof(unsigned long long)));
+    SYLT_CUDA(w->dbg.ensure(64 + 8 * 1024));
+    SYLT_CUDA(cudaMemset(w->dbg.p, 0, (64 + 8 * 1024) * sizeof(unsigned long long)));
     if (const char* ev = getenv("SYLT_SOLVER_SMEM_SLOTS")) w->smem_slots = std::max(0, atoi(ev));  // tests: force the global-memory path
     size_t fixed = (size_t)w->smem_slots * 32 + (((size_t)w->smem_slots + 3) & ~(size_t)3) * 4;
     if (fixed + 48 > budget) { w->smem_slots = 0; fixed = 0; }
@@ -2223,6 +2358,7 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
         if (const char* ev = getenv("SYLT_REGIONS_MIN_BODIES")) w->regions_min_bodies = std::max(1, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_COUNT")) w->regions_count = std::max(0, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_PERIOD")) w->regions_period = std::max(1, atoi(ev));
+        if (const char* ev = getenv("SYLT_REGIONS_RESORT")) w->regions_resort = std::max(1, atoi(ev));
         if (per2 < 1 || w->ctas_per_sm != 1) w->regions_mode = 0;
     }
     int per_sm = 0;
@@ -2252,7 +2388,7 @@ static void free_all(SyltWorld* w) {
     }
     w->jbodies.release(); w->jla.release(); w->jr.release(); w->jm.release(); w->jparam.release(); w->jp.release(); w->jbias.release();
     w->jorder.release(); w->jcolor_start.release();
-    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release();
+    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release(); w->gadj.release(); w->cone_buf.release(); w->xrec.release();
 }
 
 int sylt_world_destroy(SyltWorld* w) {
@@ -2291,6 +2427,7 @@ int sylt_world_set_fixes(SyltWorld* w, int fix_features, int fix_inverse) {
 }
 int sylt_world_set_iterations(SyltWorld* w, uint32_t it) {
     if (!w) return SYLT_ERR_INVALID;
+    if (w->iterations != it) w->part_dirty = true;  // the region solver is limited to MAX_PLANES - 1 iterations
     w->iterations = it;
     return SYLT_OK;
 }
@@ -2382,6 +2519,7 @@ int sylt_world_add_joints(SyltWorld* w, const SyltJointDesc* joints, int32_t n) 
     SYLT_CUDA(cudaMemsetAsync(w->jp.p + j0, 0, (J - j0) * sizeof(float2), w->stream));
     SYLT_CUDA(cudaStreamSynchronize(w->stream));
     w->joints_dirty = true;
+    w->part_dirty = true;  // worlds with joints use k_solve
     return SYLT_OK;
 }
 int sylt_world_add_joint(SyltWorld* w, uint64_t id1, uint64_t id2, float ax, float ay, int32_t* out_index) {

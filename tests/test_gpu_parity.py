@@ -732,3 +732,22 @@ def test_batch_step_host6_equals_step_host():
         for k, f in enumerate(names):
             assert np.array_equal(out9[f], out6[:, k]), f
         st, s6 = out9.copy(), out6.copy()
+
+
+# ------------------------------------------------------------------ experimental region solver (k_solve_regions, opt-in)
+@pytest.mark.parametrize("count,period", [(5, 3), (0, 4)])
+def test_region_solver_bit_exact(monkeypatch, count, period):
+    """SYLT_REGIONS=2 routes joint-free worlds through k_solve_regions (bodies partitioned into regions that live in shared
+    memory, cross-region arbiters replayed redundantly from ghost bodies, device-side re-cut every `period` steps): the
+    result must still be bit-identical to the oracle replaying the reported colour order.  count = regions (0: one per SM)."""
+    monkeypatch.setenv("SYLT_REGIONS", "2")
+    monkeypatch.setenv("SYLT_REGIONS_COUNT", str(count))
+    monkeypatch.setenv("SYLT_REGIONS_PERIOD", str(period))
+    w, _ = _run_lockstep(scenes.pyramid(7, 10), 90, check_every=3)
+    ga, _ = w.get_arbiters()
+    assert (ga["color"] < 32).any() and (ga["color"] >= 32).any()  # both classes occur: interior (e.g. box on the static ground) and cross-region
+    _run_lockstep(scenes.demo8(10), 60, check_every=3)                               # polygons
+    _run_lockstep(scenes.demo4(10), 60, check_every=3, ctx=(False, True, True))      # no accumulation
+    w = _lockstep_big(scenes.mixed_pile(3000, seed=7), 120, 3)                       # boxes + polygons, a few thousand bodies
+    assert w.get_stats()["arbiters"] > 1000
+    _run_lockstep(scenes.bridge(10), 20)                                             # joints: falls back to k_solve
