@@ -580,7 +580,7 @@ struct SolveArgs {
     const int *jorder, *jcolor_start;
     // regions (k_solve_regions): every body belongs to one region, region r is solved by CTA r
     const int *region_of, *lidx, *reg_start, *reg_bodies;  // body -> region, body -> index inside its region, CSR of the regions
-    int n_regions, rbcap, ghost_cap;                       // shared-memory room for the bodies of one region / its ghost bodies
+    int n_regions, smem_bytes;                             // dynamic shared memory of k_solve_regions
     int *gadj, *cone_buf;                                  // per body: its generic arbiters; per CTA: ghost arbiters
     ulonglong2* xrec;                                      // export planes (one per pass) of versioned boundary-body velocities
     unsigned step_tag;
@@ -1139,7 +1139,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
 constexpr int GADJ = NC;              // per body: its generic arbiters, indexed by the rank of their colour in `used`
 constexpr int GHOST_FLAG = 0x40000000;
 constexpr int CONE_CAP = 2048;        // ghost arbiters a CTA may replay
-constexpr int HASH_CAP = 4096;        // open-addressing tables of the cone walk (alias the contact area during set-up)
+constexpr int HASH_CAP = 4096;        // open-addressing tables of the cone walk (set-up scratch at the top of shared memory)
+constexpr int GB_MAX = 2048;          // ghost bodies of a CTA
+constexpr int OWN_MAX = 4096;         // arbiters a region may own
 constexpr int MAX_PLANES = 16;        // export planes: one per pass (iterations + 1)
 
 __device__ __forceinline__ unsigned hash_u32(unsigned x) { return fmix32(x * 2654435761u); }
@@ -1157,29 +1159,26 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     };
     stamp(0);
     __shared__ int s_cnt[NCX], s_fill[NCX], s_cstart[NCX + 1], s_clist[NCX];
-    __shared__ int s_ncl, s_nint, s_nbnd, s_obase, s_L, s_ngh, s_ngb, s_bad;
+    __shared__ int s_ncl, s_nint, s_nbnd, s_obase, s_L, s_ngh, s_ngb, s_nown, s_bad;
     __shared__ int s_scan[34];
-    // shared-memory carve-up: bodies (own, then ghosts; 32 bytes each), boundary / ghost lists, slot records (12 bytes),
-    // contacts (36 bytes).  During set-up the hash tables of the cone walk alias the contact area.
-    const int RBCAP = a.rbcap, GBCAP = a.ghost_cap, SLOTCAP = a.smem_slots, CONCAP = a.smem_contacts;
-    float4* s_bv = (float4*)sm_raw;                       // (vx, vy, w, -)
-    float4* s_bp = s_bv + RBCAP + GBCAP;                  // (x, y, inv_mass, inv_moi): constant during the solve
-    float4* s_c0 = s_bp + RBCAP + GBCAP;                  // contact: (position, normal)
-    float4* s_c1 = s_c0 + CONCAP;                         //          (mass_normal, mass_tangent, bias, pn); before pre_step: (-, -, separation, pn)
-    float* s_c2 = (float*)(s_c1 + CONCAP);                //          pt
-    int* s_bnd = (int*)(s_c2 + CONCAP);                   // own boundary bodies: local index
-    int* s_bndg = s_bnd + RBCAP;                          //                      global index
-    int* s_gb = s_bndg + RBCAP;                           // ghost bodies: global index | GHOST_FLAG if static (never imported again)
-    int* s_sb = s_gb + GBCAP;                             // slot: body refs, r1 | r2 << 16; ref = index into s_bv | SREF_STATIC
-    int* s_sc = s_sb + SLOTCAP;                           //       contact offset << 8 | count, or -1: contacts in the global arrays
-    float* s_sf = (float*)(s_sc + SLOTCAP);               //       friction
-    int* h_arb = (int*)s_c0;                              // set-up only: set of ghost arbiters (key = arbiter + 1)
-    int* h_body = h_arb + HASH_CAP;                       // set-up only: ghost body -> index (key = body + 1, value)
+    // Shared memory, carved as the sizes become known: boundary lists [nb], bodies (32 bytes each: own, then ghosts), ghost
+    // list, slot records (12 bytes), contacts (36 bytes, all that is left).  During set-up the top of the area holds the
+    // scratch of the cone walk: hash tables, the ghost ids, the (arbiter, colour) list of the own arbiters.
+    const int R = bid;
+    const int rb0 = R < a.n_regions ? a.reg_start[R] : 0;
+    const int nb = R < a.n_regions ? a.reg_start[R + 1] - rb0 : 0;
+    int* s_bnd = (int*)sm_raw;                            // own boundary bodies: local index
+    int* s_bndg = s_bnd + nb;                             //                      global index
+    float4* s_body = (float4*)(sm_raw + (((size_t)nb * 8 + 15) & ~(size_t)15));  // [2i] = (vx, vy, w, -), [2i+1] = (x, y, inv_mass, inv_moi)
+    int* h_arb = (int*)(sm_raw + a.smem_bytes) - 3 * HASH_CAP;  // set of ghost arbiters (key = arbiter + 1)
+    int* h_body = h_arb + HASH_CAP;                       // ghost body -> index (key = body + 1, value)
     int* h_bval = h_body + HASH_CAP;
+    int* t_gb = h_arb - GB_MAX;                           // ghost bodies in discovery order
+    int2* t_own = (int2*)t_gb - OWN_MAX;                  // (arbiter, colour) of the arbiters this region owns
+    const unsigned char* scratch_lo = (const unsigned char*)t_own;
 
     color_new_arbiters<true>(a, cn, bar, bar_target);
     stamp(1);
-    const int R = bid;
     auto dynamic = [&](int b) { return !(a.bflags[b] & FLAG_STATIC); };
     auto owner_region = [&](int e, int2 b) { return a.region_of[a.cur.partner[e] == b.x ? b.y : b.x]; };
 
@@ -1194,14 +1193,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     }
     grid_barrier(bar, bar_target);
 
-    // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) counted by colour
+    // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) listed and counted by colour
     BodyIO io{a.vrec, a.sleep_ns, &cn->err};
-    const int rb0 = R < a.n_regions ? a.reg_start[R] : 0;
-    const int nb = R < a.n_regions ? a.reg_start[R + 1] - rb0 : 0;
     if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; }
-    if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_bad = nb > RBCAP ? 1 : 0; }
+    if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_nown = 0; s_bad = (const unsigned char*)(s_body + 2 * (size_t)nb) > scratch_lo ? 1 : 0; }
     for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
     __syncthreads();
+    const bool fits = !s_bad;  // the region's bodies alone must leave room for the scratch (the host sizes the regions accordingly)
     int* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA, in discovery order
     auto arb_insert = [&](int f) -> bool {  // true: f is new
         unsigned h = hash_u32((unsigned)f) & (HASH_CAP - 1);
@@ -1221,8 +1219,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         else s_bad = 1;
     };
     // everything arbiter e (generic, colour c) depends on inside one generic phase: lower-coloured generic arbiters at its bodies
-    auto expand = [&](int e) {
-        const int c = __ldcg(&a.cur.color[e]);
+    auto expand = [&](int e, int c) {
         const int2 b = a.cur.bodies[e];
 #pragma unroll
         for (int side = 0; side < 2; side++) {
@@ -1238,14 +1235,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
             }
         }
     };
-    for (int lb = lt; lb < min(nb, RBCAP); lb += T) {
+    for (int lb = lt; lb < nb && fits; lb += T) {
         const int b = a.reg_bodies[rb0 + lb];
         Vel v;
         float im, ii;
         io.get(b, v, im, ii);
         const float4 p = a.pose[b];
-        s_bv[lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
-        s_bp[lb] = make_float4(p.x, p.y, im, ii);
+        s_body[2 * lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
+        s_body[2 * lb + 1] = make_float4(p.x, p.y, im, ii);
         const unsigned long long ub = dynamic(b) ? __ldcg(&a.used[b]) : 0ull;
         if (ub != 0ull) {  // a boundary body: exported every pass; every generic arbiter at it is replayed here, whoever owns it
             const int k = atomicAdd(&s_nbnd, 1);
@@ -1262,7 +1259,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
             const int c = __ldcg(&a.cur.color[e]);
             if (c < 0) continue;
             atomicAdd(&s_cnt[c], 1);
-            if (c >= GEN_BIT) expand(e);  // level 0 of the cone walk: the region's own generic arbiters are roots
+            const int k = atomicAdd(&s_nown, 1);
+            if (k < OWN_MAX) t_own[k] = make_int2(e, c); else s_bad = 1;
+            if (c >= GEN_BIT) expand(e, c);  // level 0 of the cone walk: the region's own generic arbiters are roots
         }
     }
     __syncthreads();
@@ -1271,11 +1270,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         const int f1 = min(s_ngh, CONE_CAP);
         __syncthreads();
         if (f1 == f0) break;
-        for (int g = f0 + lt; g < f1; g += T) expand(__ldcg(&ghosts[g]));
+        for (int g = f0 + lt; g < f1; g += T) { const int f = __ldcg(&ghosts[g]); expand(f, __ldcg(&a.cur.color[f])); }
         __syncthreads();
         f0 = f1;
     }
-    const int ngh = min(s_ngh, CONE_CAP);
+    const int ngh = min(s_ngh, CONE_CAP), nown = min(s_nown, OWN_MAX);
     // ---- 2d. ghost bodies: bodies of other regions that this CTA's slots touch (dynamic: re-imported every pass; static: once)
     auto body_insert = [&](int z) {
         unsigned h = hash_u32((unsigned)z ^ 0x9e3779b9u) & (HASH_CAP - 1);
@@ -1284,7 +1283,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
             if (old == 0) {
                 const int g = atomicAdd(&s_ngb, 1);
                 h_bval[h] = g;
-                if (g < GBCAP) s_gb[g] = z | (dynamic(z) ? 0 : GHOST_FLAG); else s_bad = 1;
+                if (g < GB_MAX) t_gb[g] = z | (dynamic(z) ? 0 : GHOST_FLAG); else s_bad = 1;
                 return;
             }
             if (old == z + 1) return;
@@ -1308,25 +1307,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         if (a.region_of[b.x] != R) body_insert(b.x);
         if (a.region_of[b.y] != R) body_insert(b.y);
     };
-    for (int lb = lt; lb < nb; lb += T) {
-        const int b = a.reg_bodies[rb0 + lb];
-        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
-        for (int e = e0; e < e1; e++)
-            if (__ldcg(&a.cur.color[e]) >= 0) ghost_bodies_of(e);
-    }
+    for (int k = lt; k < nown; k += T) ghost_bodies_of(t_own[k].x);
     for (int g = lt; g < ngh; g += T) ghost_bodies_of(__ldcg(&ghosts[g]));
     __syncthreads();
-    const int ngb = min(s_ngb, GBCAP);
-    for (int g = lt; g < ngb; g += T) {  // positions, inverse masses (and, for static ghosts, the velocity) once; dynamic velocities arrive every pass
-        const int z = s_gb[g] & ~GHOST_FLAG;
-        Vel v;
-        float im, ii;
-        io.get(z, v, im, ii);
-        const float4 p = a.pose[z];
-        s_bv[nb + g] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
-        s_bp[nb + g] = make_float4(p.x, p.y, im, ii);
-    }
+    const int ngb = min(s_ngb, GB_MAX);
     // ---- 2e. slot layout: generic colours first (their contacts must be shared-memory resident), then the interior colours
+    int* s_gb = (int*)(s_body + 2 * ((size_t)nb + ngb));  // ghost bodies: global index | GHOST_FLAG if static (never imported again)
     if (lt == 0) {
         int run = 0, ncl = 0, nint = 0, ngen = 0;
         unsigned long long mask = 0ull;
@@ -1342,47 +1328,59 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         if (ngen) atomicAdd(&cn->n_generic, ngen - ngh);
         if (ngh) atomicAdd(&cn->n_ghost, ngh);
         atomicMax(&cn->max_slots, run);
-        if (s_bad || run > SLOTCAP) {  // more slots / a larger cone than the tables hold
+        // everything but the contacts must fit below the scratch; bodies are referenced through 15-bit indices
+        const bool room = (const unsigned char*)(s_gb + ngb + 3 * (size_t)run) <= scratch_lo && nb + ngb < 0x8000;
+        if (s_bad || !room) {
+            s_bad = 1;
             atomicExch(&cn->err, SYLT_ERR_CAPACITY);
-            atomicOr(&cn->why, (s_bad ? 1 : 0) | (run > SLOTCAP ? 2 : 0) | (s_ngh > CONE_CAP ? 4 : 0) | (s_ngb > GBCAP ? 8 : 0) | (nb > RBCAP ? 16 : 0));
+            atomicOr(&cn->why, 1 | (!room ? 2 : 0) | (s_ngh > CONE_CAP ? 4 : 0) | (s_ngb > GB_MAX ? 8 : 0) | (!fits ? 16 : 0) | (s_nown > OWN_MAX ? 64 : 0));
         }
     }
     __syncthreads();
     if (!a.run_solver) return;
-    const int L = min(s_L, SLOTCAP), ncl = s_ncl, nint = s_nint, nbnd = s_nbnd;
+    const bool bad = s_bad != 0;  // this CTA cannot solve; the error is flagged, the grid barrier below is still joined
+    const int L = bad ? 0 : s_L, ncl = s_ncl, nint = s_nint, nbnd = s_nbnd;
+    int* s_sb = s_gb + ngb;                               // slot: body refs, r1 | r2 << 16; ref = index into s_body | SREF_STATIC
+    int* s_sc = s_sb + L;                                 //       contact offset << 8 | count, or -1: contacts in the global arrays
+    float* s_sf = (float*)(s_sc + L);                     //       friction
+    float4* s_c0 = (float4*)(((size_t)(s_sf + L) + 15) & ~(size_t)15);  // contact: (position, normal)
+    const int CONCAP = bad ? 0 : (int)(((sm_raw + a.smem_bytes - (unsigned char*)s_c0) / 36) & ~(size_t)3);
+    float4* s_c1 = s_c0 + CONCAP;                         //          (mass_normal, mass_tangent, bias, pn); before pre_step: (-, -, separation, pn)
+    float* s_c2 = (float*)(s_c1 + CONCAP);                //          pt
+    for (int g = lt; g < ngb && !bad; g += T) {  // ghosts: positions, inverse masses (and, for static ones, the velocity) once; dynamic velocities arrive every pass
+        const int zf = t_gb[g], z = zf & ~GHOST_FLAG;
+        s_gb[g] = zf;
+        Vel v;
+        float im, ii;
+        io.get(z, v, im, ii);
+        const float4 p = a.pose[z];
+        s_body[2 * (nb + g)] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
+        s_body[2 * (nb + g) + 1] = make_float4(p.x, p.y, im, ii);
+    }
     int* order = a.order + s_obase;  // this CTA's slots by colour (within a colour the order is irrelevant); ghosts carry GHOST_FLAG
-    for (int lb = lt; lb < nb; lb += T) {
-        const int b = a.reg_bodies[rb0 + lb];
-        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
-        for (int e = e0; e < e1; e++) {
-            const int c = __ldcg(&a.cur.color[e]);
-            if (c >= 0) order[s_cstart[c] + atomicAdd(&s_fill[c], 1)] = e;
-        }
-    }
-    for (int g = lt; g < ngh; g += T) {
-        const int f = __ldcg(&ghosts[g]);
-        const int c = __ldcg(&a.cur.color[f]);
-        order[s_cstart[c] + atomicAdd(&s_fill[c], 1)] = f | GHOST_FLAG;
-    }
-    __syncthreads();
     const bool acc = a.accumulate != 0;
     const float kbias = a.poscorr ? 0.2f : 0.0f;
 
     stamp(2);
-    // ---- 3. residency: slot records (the bodies' shared-memory indices need the hash tables), then the contacts (which
-    //         overwrite the tables)
+    // ---- 3. slots: position by colour, record (the bodies' shared-memory indices come from the hash table), then the contacts
+    //         (which overwrite the scratch)
     constexpr int SREF_STATIC = 0x8000;
     auto body_ref = [&](int z) -> int {
         return (a.region_of[z] == R ? a.lidx[z] : nb + body_lookup(z)) | (dynamic(z) ? 0 : SREF_STATIC);
     };
-    for (int ls = lt; ls < L; ls += T) {
-        const int e = __ldcg(&order[ls]) & ~GHOST_FLAG;
+    auto place = [&](int e, int c, int flag) {
+        const int ls = s_cstart[c] + atomicAdd(&s_fill[c], 1);
         const int2 b = a.cur.bodies[e];
+        order[ls] = e | flag;
         s_sb[ls] = body_ref(b.x) | (body_ref(b.y) << 16);
         s_sc[ls] = a.cur.meta[e].x;
         s_sf[ls] = a.cur.friction[e];
+    };
+    if (!bad) {
+        for (int k = lt; k < nown; k += T) { const int2 ec = t_own[k]; place(ec.x, ec.y, 0); }
+        for (int g = lt; g < ngh; g += T) { const int f = __ldcg(&ghosts[g]); place(f, __ldcg(&a.cur.color[f]), GHOST_FLAG); }
     }
-    __syncthreads();  // the hash tables are dead from here on
+    __syncthreads();  // the scratch is dead from here on
     {   // in-place exclusive scan of the contact counts
         const int chunk = (L + T - 1) / T, q0 = min(lt * chunk, L), q1 = min(q0 + chunk, L);
         int sum = 0;
@@ -1430,7 +1428,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         const float fr = s_sf[ls];
         const int r1 = sb & 0xffff, r2 = (sb >> 16) & 0xffff;
         const int i1 = r1 & ~SREF_STATIC, i2 = r2 & ~SREF_STATIC;
-        const float4 q1 = s_bv[i1], q2 = s_bv[i2], m1 = s_bp[i1], m2 = s_bp[i2];
+        const float4 q1 = s_body[2 * i1], q2 = s_body[2 * i2], m1 = s_body[2 * i1 + 1], m2 = s_body[2 * i2 + 1];
         Vel v1, v2;
         v1.v = mk(q1.x, q1.y); v1.w = q1.z; v2.v = mk(q2.x, q2.y); v2.w = q2.z;
         const V2 p1 = mk(m1.x, m1.y), p2 = mk(m2.x, m2.y);
@@ -1473,8 +1471,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
                 }
             }
         }
-        if (!(r1 & SREF_STATIC)) s_bv[i1] = make_float4(v1.v.x, v1.v.y, v1.w, 0.0f);
-        if (!(r2 & SREF_STATIC)) s_bv[i2] = make_float4(v2.v.x, v2.v.y, v2.w, 0.0f);
+        if (!(r1 & SREF_STATIC)) s_body[2 * i1] = make_float4(v1.v.x, v1.v.y, v1.w, 0.0f);
+        if (!(r2 & SREF_STATIC)) s_body[2 * i2] = make_float4(v2.v.x, v2.v.y, v2.w, 0.0f);
     };
     int pa_ = 0;
     auto pstamp = [&](unsigned pass) {  // diagnostics: the phases of pass 5 in every CTA
@@ -1495,7 +1493,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         BodyIO xio{a.xrec + (size_t)pass * 2 * (size_t)a.B, a.sleep_ns, &cn->err};
         const unsigned tag = (a.step_tag << 8) | pass;
         for (int k = lt; k < nbnd; k += T) {
-            const float4 q = s_bv[s_bnd[k]];
+            const float4 q = s_body[2 * s_bnd[k]];
             Vel o; o.v = mk(q.x, q.y); o.w = q.z;
             xio.put(s_bndg[k], o, tag);
         }
@@ -1511,7 +1509,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
                     if (spins > (1u << 23)) { atomicExch(&cn->err, SYLT_ERR_INTERNAL); break; }
                 }
             }
-            s_bv[nb + g] = make_float4(o.v.x, o.v.y, o.w, 0.0f);
+            s_body[2 * (nb + g)] = make_float4(o.v.x, o.v.y, o.w, 0.0f);
         }
         __syncthreads();
         pstamp(pass);
@@ -1535,7 +1533,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         const int e = __ldcg(&order[ls]);
         if (sc < 0 || (e & GHOST_FLAG)) continue;
         const int sb = s_sb[ls];
-        const float4 m1 = s_bp[sb & 0x7fff], m2 = s_bp[(sb >> 16) & 0x7fff];
+        const float4 m1 = s_body[2 * (sb & 0x7fff) + 1], m2 = s_body[2 * ((sb >> 16) & 0x7fff) + 1];
         const int coff = a.cur.meta[e].y, lc = sc >> 8, n = sc & 0xff;
         for (int q = 0; q < n; q++) {
             const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
@@ -1550,7 +1548,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     // ---- 7. integrate the region's bodies (world.rs:143-150; static bodies too, quirk Q-16)
     for (int lb = lt; lb < nb; lb += T) {
         const int b = a.reg_bodies[rb0 + lb];
-        const float4 q = s_bv[lb];
+        const float4 q = s_body[2 * lb];
         a.vel[b] = make_float4(q.x, q.y, q.z, 0.0f);
         float4 p = a.pose[b];
         V2 np = mk(p.x, p.y) + mk(q.x, q.y) * a.dt;
@@ -1564,7 +1562,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
 
 // Re-cut the regions along the stored spatial order of the bodies (`perm`, from the last host-side partition) so that
 // every region gets the same share of the work: weight of a body = 1 + 2 x (arbiters it owned last step), floored at the
-// average weight so that no region gets more than twice the average number of bodies (the shared-memory room `rbcap`).
+// average weight so that no region gets more than twice the average number of bodies (k_solve_regions keeps a region's bodies in shared memory).
 // Regions are consecutive runs of `perm`, so perm itself is the CSR body list.  One CTA; runs every `regions_period` steps.
 constexpr int REBAL_THREADS = 1024;
 __global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const int* perm, const int* old_row_start, int* region_of, int* lidx,
@@ -1718,7 +1716,6 @@ struct SyltWorld {
     // share of cross-region arbiters has grown
     DBuf<int> region_of, lidx, reg_start, reg_bodies, gadj, cone_buf;
     DBuf<ulonglong2> xrec;
-    int ghost_cap = 512, region_slots = 4096;
     unsigned step_tag = 0;
     int regions_mode = 0;            // SYLT_REGIONS: 0 = never (default: experimental), 1 = worlds of at least regions_min_bodies, 2 = always
     int regions_min_bodies = 8192, regions_count = 0, regions_period = 64, regions_resort = 4096;
@@ -1726,7 +1723,7 @@ struct SyltWorld {
     bool part_dirty = true;          // bodies were added / the mode may have changed
     bool last_regions = false;       // the last enqueued step ran k_solve_regions
     bool recolor_all = false;        // next step: ignore last step's colours (they encode the old partition)
-    int n_regions = 0, rbcap = 0, reg_smem_contacts = 0;
+    int n_regions = 0;
     int64_t steps_since_part = 0, steps_since_sort = 0;
     size_t solve_budget = 0;
 
@@ -2010,7 +2007,7 @@ int repartition(SyltWorld* w) {
     int G = std::min(1024, w->regions_count > 0 ? std::min(w->regions_count, w->coop_blocks) : w->coop_blocks);
     bool on = w->regions_mode == 2 || (w->regions_mode == 1 && B >= (size_t)w->regions_min_bodies);
     if (B == 0 || G < 1 || !w->hj.empty() || w->iterations + 1 > (uint32_t)MAX_PLANES) on = false;  // joints / long solves: k_solve
-    if (on && (B + (size_t)G - 1) / (size_t)G > 2048) on = false;  // regions too large for an SM: k_solve
+    if (on && (B + (size_t)G - 1) / (size_t)G > 1024) on = false;  // regions too large for an SM: k_solve
     if (!on) {
         w->regions_on = false;
         if (was_on) w->recolor_all = true;
@@ -2078,12 +2075,12 @@ int repartition(SyltWorld* w) {
         }
         for (int g = 0; g < G; g++) { reg_start[(size_t)g + 1] = reg_start[(size_t)g] + cnt[(size_t)g]; maxper = std::max(maxper, (size_t)cnt[(size_t)g]); }
     }
-    // shared memory: 40 bytes per body of the region, 36 per ghost body, 12 per slot; the rest holds contacts (36 bytes each) and,
-    // during set-up, the three hash tables of the cone walk
-    const size_t rbcap = (maxper + 3) & ~(size_t)3;
-    if (rbcap + (size_t)w->ghost_cap > 32768) { w->regions_on = false; if (was_on) w->recolor_all = true; return SYLT_OK; }
-    const size_t fixed = rbcap * 40 + (size_t)w->ghost_cap * 36 + (size_t)w->region_slots * 12 + 64;
-    if (fixed + (size_t)3 * HASH_CAP * 4 + 4096 > w->solve_budget) { w->regions_on = false; if (was_on) w->recolor_all = true; return SYLT_OK; }
+    // shared memory of a solver CTA: 40 bytes per body of the region must leave room for the set-up scratch and the slots
+    if (maxper * 40 + (size_t)3 * HASH_CAP * 4 + (size_t)GB_MAX * 4 + (size_t)OWN_MAX * 8 + 32768 > w->solve_budget) {
+        w->regions_on = false;
+        if (was_on) w->recolor_all = true;
+        return SYLT_OK;
+    }
     SYLT_CUDA(w->region_of.ensure(B));
     SYLT_CUDA(w->lidx.ensure(B));
     SYLT_CUDA(w->reg_bodies.ensure(B));
@@ -2103,12 +2100,10 @@ int repartition(SyltWorld* w) {
     if (w->timing) {
         std::vector<double> rw((size_t)G, 0.0);
         for (size_t i = 0; i < B; i++) rw[(size_t)region_of[i]] += wt[i];
-        fprintf(stderr, "repartition: %d regions (%d strips), bodies per region <= %zu, weight max/avg %.2f, contacts room %zu\n", G, SX, maxper,
-                *std::max_element(rw.begin(), rw.end()) / (total / G), (w->solve_budget - fixed) / 36);
+        fprintf(stderr, "repartition: %d regions (%d strips), bodies per region <= %zu, weight max/avg %.2f\n", G, SX, maxper,
+                *std::max_element(rw.begin(), rw.end()) / (total / G));
     }
     w->n_regions = G;
-    w->rbcap = (int)rbcap;
-    w->reg_smem_contacts = (int)(((w->solve_budget - fixed) / 36) & ~(size_t)3);
     w->regions_on = true;
     w->recolor_all = true;
     return SYLT_OK;
@@ -2193,7 +2188,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.slack_pct = w->slack_pct; a.fix_inverse = w->fix_inverse; a.dbg = w->timing ? w->dbg.p : nullptr;
     if (w->regions_on) {
         a.region_of = w->region_of.p; a.lidx = w->lidx.p; a.reg_start = w->reg_start.p; a.reg_bodies = w->reg_bodies.p;
-        a.n_regions = w->n_regions; a.rbcap = w->rbcap; a.smem_contacts = w->reg_smem_contacts; a.ghost_cap = w->ghost_cap; a.smem_slots = w->region_slots;
+        a.n_regions = w->n_regions; a.smem_bytes = (int)w->solve_budget;
         a.gadj = w->gadj.p; a.cone_buf = w->cone_buf.p; a.xrec = w->xrec.p;
         if (++w->step_tag > 0xfffff0u) {  // 24-bit tags: start over with clean planes
             SYLT_CUDA(cudaMemsetAsync(w->xrec.p, 0, w->xrec.cap * sizeof(ulonglong2), st));
