@@ -1560,31 +1560,96 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     stamp(7);
 }
 
-// Re-cut the regions along the stored spatial order of the bodies (`perm`, from the last host-side partition) so that
-// every region gets the same share of the work: weight of a body = 1 + 2 x (arbiters it owned last step), floored at the
-// average weight so that no region gets more than twice the average number of bodies (k_solve_regions keeps a region's bodies in shared memory).
-// Regions are consecutive runs of `perm`, so perm itself is the CSR body list.  One CTA; runs every `regions_period` steps.
-constexpr int REBAL_THREADS = 1024;
-__global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const int* perm, const int* old_row_start, int* region_of, int* lidx,
+// Spatial order of the bodies for the region solver: a counting sort by the Z-order (Morton) index of a 128 x 128 grid laid
+// over the bounding box of the bodies, then by body index inside a cell (so the order, and with it the solve order, is
+// reproducible).  Consecutive runs of that order are compact blobs; k_rebalance cuts it into regions.  One CTA, every
+// `regions_period` steps; any order is valid, compactness only decides how many arbiters cross regions.
+constexpr int REBAL_THREADS = 1024, SORT_BITS = 7, SORT_CELLS = 1 << (2 * SORT_BITS);
+__device__ __forceinline__ unsigned morton_spread(unsigned v) {  // 0b abcdefg -> 0b 0a0b0c0d0e0f0g
+    v = (v | (v << 4)) & 0x0f0fu;
+    v = (v | (v << 2)) & 0x3333u;
+    v = (v | (v << 1)) & 0x5555u;
+    return v;
+}
+__global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* pose, int* perm, int* key_tmp) {
+    extern __shared__ int s_hist[];  // SORT_CELLS + 1
+    __shared__ float s_red[4][32];
+    __shared__ int s_scan2[34];
+    const int lt = threadIdx.x, T = blockDim.x, lane = lt & 31, wid = lt >> 5;
+    float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
+    for (int i = lt; i < B; i += T) {
+        const float4 p = pose[i];
+        if (fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f) { x0 = fminf(x0, p.x); x1 = fmaxf(x1, p.x); y0 = fminf(y0, p.y); y1 = fmaxf(y1, p.y); }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+    }
+    if (lane == 0) { s_red[0][wid] = x0; s_red[1][wid] = x1; s_red[2][wid] = y0; s_red[3][wid] = y1; }
+    for (int k = lt; k <= SORT_CELLS; k += T) s_hist[k] = 0;
+    __syncthreads();
+    for (int k = 0; k < (T >> 5); k++) { x0 = fminf(x0, s_red[0][k]); x1 = fmaxf(x1, s_red[1][k]); y0 = fminf(y0, s_red[2][k]); y1 = fmaxf(y1, s_red[3][k]); }
+    const float span = fmaxf(fmaxf(x1 - x0, y1 - y0), 1.0e-3f);
+    const float inv = (float)(1 << SORT_BITS) / (span * 1.0001f);
+    auto key_of = [&](float4 p) -> int {
+        if (!(fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f)) return 0;
+        const int cx = min((1 << SORT_BITS) - 1, max(0, (int)((p.x - x0) * inv))), cy = min((1 << SORT_BITS) - 1, max(0, (int)((p.y - y0) * inv)));
+        return (int)(morton_spread((unsigned)cx) | (morton_spread((unsigned)cy) << 1));
+    };
+    for (int i = lt; i < B; i += T) {
+        const int k = key_of(pose[i]);
+        key_tmp[i] = k;
+        atomicAdd(&s_hist[k], 1);
+    }
+    __syncthreads();
+    {   // exclusive scan of the histogram: s_hist[k] = first position of cell k
+        const int per = SORT_CELLS / REBAL_THREADS, q0 = lt * per;
+        int sum = 0;
+        for (int k = 0; k < per; k++) sum += s_hist[q0 + k];
+        int tot;
+        int ex = block_excl_scan<int>(sum, &tot, s_scan2);
+        for (int k = 0; k < per; k++) { const int t = s_hist[q0 + k]; s_hist[q0 + k] = ex; ex += t; }
+    }
+    __syncthreads();
+    for (int i = lt; i < B; i += T) perm[atomicAdd(&s_hist[key_tmp[i]], 1)] = i;  // now s_hist[k] = end of cell k
+    __syncthreads();
+    for (int k = lt; k < SORT_CELLS; k += T) {  // ascending body index inside a cell (cells hold a handful of bodies)
+        const int lo = k ? s_hist[k - 1] : 0, hi = s_hist[k];
+        if (hi - lo > 256) continue;  // a degenerate pile-up in one cell: leave it unordered rather than sort it on one thread
+        for (int a2 = lo + 1; a2 < hi; a2++) {
+            const int x = perm[a2];
+            int b2 = a2 - 1;
+            while (b2 >= lo && perm[b2] > x) { perm[b2 + 1] = perm[b2]; b2--; }
+            perm[b2 + 1] = x;
+        }
+    }
+}
+
+// Cut the spatial order `perm` into G regions of equal load: weight of a body = 1 + 2 x (arbiters it owned last step),
+// floored at the average weight so that no region gets more than twice the average number of bodies (k_solve_regions
+// keeps a region's bodies in shared memory).  Regions are consecutive runs of `perm`, so perm itself is the CSR body list.
+__global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const int* perm, const int* old_row_start, int B_old, int* region_of, int* lidx,
                                                             int* reg_start) {
     __shared__ long long sh[34];
     __shared__ int s_first[1025];
     const int lt = threadIdx.x, T = blockDim.x;
     const int chunk = (B + T - 1) / T, q0 = min(lt * chunk, B), q1 = min(q0 + chunk, B);
+    auto weight = [&](int b) -> long long { return (old_row_start && b < B_old) ? 1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b]) : 1; };
     for (int g = lt; g <= G; g += T) s_first[g] = B;
     long long sum = 0;
-    for (int i = q0; i < q1; i++) { const int b = perm[i]; sum += 1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b]); }
+    for (int i = q0; i < q1; i++) sum += weight(perm[i]);
     long long total;
     block_excl_scan<long long>(sum, &total, sh);
     const long long wmin = (total + B - 1) / max(B, 1);
     long long esum = 0;
-    for (int i = q0; i < q1; i++) { const int b = perm[i]; esum += max((long long)(1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b])), wmin); }
+    for (int i = q0; i < q1; i++) esum += max(weight(perm[i]), wmin);
     long long etotal;
     long long ex = block_excl_scan<long long>(esum, &etotal, sh);
     for (int i = q0; i < q1; i++) {
         const int b = perm[i];
         const int reg = (int)min((long long)(G - 1), ex * (long long)G / max(etotal, 1ll));
-        ex += max((long long)(1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b])), wmin);
+        ex += max(weight(b), wmin);
         region_of[b] = reg;
         atomicMin(&s_first[reg], i);
     }
@@ -1714,17 +1779,18 @@ struct SyltWorld {
 
     // regions (k_solve_regions): spatial partition of the bodies, recomputed on the host when bodies were added or the
     // share of cross-region arbiters has grown
-    DBuf<int> region_of, lidx, reg_start, reg_bodies, gadj, cone_buf;
+    DBuf<int> region_of, lidx, reg_start, reg_bodies, sort_keys, gadj, cone_buf;
     DBuf<ulonglong2> xrec;
     unsigned step_tag = 0;
-    int regions_mode = 0;            // SYLT_REGIONS: 0 = never (default: experimental), 1 = worlds of at least regions_min_bodies, 2 = always
-    int regions_min_bodies = 8192, regions_count = 0, regions_period = 64, regions_resort = 4096;
+    int regions_mode = 1;            // SYLT_REGIONS: 0 = never (k_solve only), 1 = joint-free worlds of at least regions_min_bodies (default), 2 = always
+    int regions_min_bodies = 8192, regions_count = 0, regions_period = 128;
     bool regions_on = false;         // the partition on the device is valid for the current bodies
     bool part_dirty = true;          // bodies were added / the mode may have changed
     bool last_regions = false;       // the last enqueued step ran k_solve_regions
     bool recolor_all = false;        // next step: ignore last step's colours (they encode the old partition)
     int n_regions = 0;
-    int64_t steps_since_part = 0, steps_since_sort = 0;
+    int64_t steps_since_part = 0;
+    bool resort_pending = false;     // the partition of the current bodies has not been computed yet
     size_t solve_budget = 0;
 
     int64_t cap_pairs = 0, cap_arb = 0, cap_con = 0;
@@ -1994,96 +2060,26 @@ int flush(SyltWorld* w) {
     return SYLT_OK;
 }
 
-// Spatial partition of the bodies into `G` compact regions of equal body count: strips of equal count along x, every
-// strip cut along y, the regions are consecutive runs of that order.  Any assignment is valid (the class of an arbiter
-// follows from it, k_solve_regions); compactness only decides how many arbiters cross regions.  Host side: it runs when
-// bodies were added and, rarely, when the bodies have mixed.
+// Region solver on / off for the current bodies, and its buffers.  The partition itself (k_resort + k_rebalance) is enqueued
+// with the next step; nothing here synchronises with the device beyond (re)allocation.
 int repartition(SyltWorld* w) {
     const size_t B = w->hb.size();
     w->part_dirty = false;
-    w->steps_since_part = 0;
-    w->steps_since_sort = 0;
     const bool was_on = w->regions_on;
-    int G = std::min(1024, w->regions_count > 0 ? std::min(w->regions_count, w->coop_blocks) : w->coop_blocks);
+    const int G = std::min(1024, w->regions_count > 0 ? std::min(w->regions_count, w->coop_blocks) : w->coop_blocks);
     bool on = w->regions_mode == 2 || (w->regions_mode == 1 && B >= (size_t)w->regions_min_bodies);
     if (B == 0 || G < 1 || !w->hj.empty() || w->iterations + 1 > (uint32_t)MAX_PLANES) on = false;  // joints / long solves: k_solve
-    if (on && (B + (size_t)G - 1) / (size_t)G > 1024) on = false;  // regions too large for an SM: k_solve
-    if (!on) {
-        w->regions_on = false;
-        if (was_on) w->recolor_all = true;
-        return SYLT_OK;
-    }
-    if (w->inflight) finish(w);
-    SYLT_CUDA(cudaStreamSynchronize(w->stream));
-    std::vector<float4> hp(B);
-    SYLT_CUDA(cudaMemcpy(hp.data(), w->pose.p, B * sizeof(float4), cudaMemcpyDeviceToHost));
-    std::vector<float> kx(B), ky(B);
-    float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
-    for (size_t i = 0; i < B; i++) {
-        float x = hp[i].x, y = hp[i].y;
-        if (!(x == x) || x > 1.0e30f || x < -1.0e30f) x = 0.0f;
-        if (!(y == y) || y > 1.0e30f || y < -1.0e30f) y = 0.0f;
-        kx[i] = x; ky[i] = y;
-        const HostBody& b = w->hb[i];
-        if (b.inv_mass != 0.0f) { x0 = std::min(x0, x); x1 = std::max(x1, x); y0 = std::min(y0, y); y1 = std::max(y1, y); }
-    }
-    const double xs = x1 > x0 ? (double)x1 - x0 : 1.0, ys = y1 > y0 ? (double)y1 - y0 : 1.0;
-    int SX = (int)std::lround(std::sqrt((double)G * xs / ys));
-    SX = std::max(1, std::min(G, SX));
-    // weight of a body = the shared memory it will need: its own record plus the slots and contacts of the arbiters it owns
-    // (last step's rows; a fresh scene has none and splits by body count)
-    std::vector<double> wt(B, 1.0);
-    if (w->have_old && w->B_old > 0) {
-        const size_t Bo = std::min(B, (size_t)w->B_old);
-        std::vector<int> rs(Bo + 1);
-        SYLT_CUDA(cudaMemcpy(rs.data(), w->arb[w->cur ^ 1].row_start.p, (Bo + 1) * sizeof(int), cudaMemcpyDeviceToHost));
-        for (size_t i = 0; i < Bo; i++) wt[i] = 1.0 + 2.0 * (double)std::max(0, rs[i + 1] - rs[i]);
-    }
-    std::vector<int> idx(B);
-    for (size_t i = 0; i < B; i++) idx[i] = (int)i;
-    std::sort(idx.begin(), idx.end(), [&](int p, int q) { return kx[(size_t)p] != kx[(size_t)q] ? kx[(size_t)p] < kx[(size_t)q] : p < q; });
-    double total = 0.0;
-    for (size_t i = 0; i < B; i++) total += wt[i];
-    {   // strips of equal weight along x, each sorted along y
-        size_t lo = 0;
-        double acc = 0.0;
-        for (int sx = 0; sx < SX; sx++) {
-            size_t hi = lo;
-            const double upto = total * (double)(sx + 1) / (double)SX;
-            while (hi < B && (sx == SX - 1 || acc + wt[(size_t)idx[hi]] <= upto)) acc += wt[(size_t)idx[hi++]];
-            std::sort(idx.begin() + (long)lo, idx.begin() + (long)hi,
-                      [&](int p, int q) { return ky[(size_t)p] != ky[(size_t)q] ? ky[(size_t)p] < ky[(size_t)q] : p < q; });
-            lo = hi;
-        }
-    }
-    // regions = consecutive runs of equal weight in that order; the order itself is the CSR body list and stays on the device
-    // for k_rebalance.  A body weighs at least the average, so no region holds more than twice the average number of bodies.
-    std::vector<int> region_of(B), lidx(B), reg_start((size_t)G + 1, 0);
-    const std::vector<int>& reg_bodies = idx;
-    size_t maxper = 2 * ((B + (size_t)G - 1) / (size_t)G) + 16;
-    {
-        const double wmin = total / (double)B;
-        double etotal = 0.0;
-        for (size_t i = 0; i < B; i++) etotal += std::max(wt[i], wmin);
-        double acc = 0.0;
-        std::vector<int> cnt((size_t)G, 0);
-        for (size_t r = 0; r < B; r++) {
-            const int reg = std::min(G - 1, (int)(acc * (double)G / etotal));
-            acc += std::max(wt[(size_t)idx[r]], wmin);
-            region_of[(size_t)idx[r]] = reg;
-            lidx[(size_t)idx[r]] = cnt[(size_t)reg]++;
-        }
-        for (int g = 0; g < G; g++) { reg_start[(size_t)g + 1] = reg_start[(size_t)g] + cnt[(size_t)g]; maxper = std::max(maxper, (size_t)cnt[(size_t)g]); }
-    }
-    // shared memory of a solver CTA: 40 bytes per body of the region must leave room for the set-up scratch and the slots
-    if (maxper * 40 + (size_t)3 * HASH_CAP * 4 + (size_t)GB_MAX * 4 + (size_t)OWN_MAX * 8 + 32768 > w->solve_budget) {
-        w->regions_on = false;
-        if (was_on) w->recolor_all = true;
-        return SYLT_OK;
-    }
+    // a region may hold twice the average number of bodies (k_rebalance); 40 bytes each must leave room for the set-up scratch and the slots
+    const size_t maxper = 2 * ((B + (size_t)G - 1) / (size_t)std::max(G, 1)) + 16;
+    if (on && maxper * 40 + (size_t)3 * HASH_CAP * 4 + (size_t)GB_MAX * 4 + (size_t)OWN_MAX * 8 + 32768 > w->solve_budget) on = false;
+    if (on != was_on) w->recolor_all = true;  // the colour ranges mean something else
+    w->regions_on = on;
+    if (!on) return SYLT_OK;
+    if (w->inflight) finish(w);  // buffers may move
     SYLT_CUDA(w->region_of.ensure(B));
     SYLT_CUDA(w->lidx.ensure(B));
     SYLT_CUDA(w->reg_bodies.ensure(B));
+    SYLT_CUDA(w->sort_keys.ensure(B));
     SYLT_CUDA(w->reg_start.ensure((size_t)G + 1));
     SYLT_CUDA(w->gadj.ensure(B * (size_t)GADJ));
     SYLT_CUDA(w->cone_buf.ensure((size_t)w->coop_blocks * CONE_CAP));
@@ -2092,20 +2088,8 @@ int repartition(SyltWorld* w) {
         SYLT_CUDA(w->xrec.ensure((size_t)MAX_PLANES * 2 * B));
         if (w->xrec.cap != oldcap) SYLT_CUDA(cudaMemsetAsync(w->xrec.p, 0, w->xrec.cap * sizeof(ulonglong2), w->stream));
     }
-    SYLT_CUDA(cudaMemcpyAsync(w->region_of.p, region_of.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-    SYLT_CUDA(cudaMemcpyAsync(w->lidx.p, lidx.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-    SYLT_CUDA(cudaMemcpyAsync(w->reg_bodies.p, reg_bodies.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-    SYLT_CUDA(cudaMemcpyAsync(w->reg_start.p, reg_start.data(), ((size_t)G + 1) * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-    SYLT_CUDA(cudaStreamSynchronize(w->stream));
-    if (w->timing) {
-        std::vector<double> rw((size_t)G, 0.0);
-        for (size_t i = 0; i < B; i++) rw[(size_t)region_of[i]] += wt[i];
-        fprintf(stderr, "repartition: %d regions (%d strips), bodies per region <= %zu, weight max/avg %.2f\n", G, SX, maxper,
-                *std::max_element(rw.begin(), rw.end()) / (total / G));
-    }
     w->n_regions = G;
-    w->regions_on = true;
-    w->recolor_all = true;
+    w->resort_pending = true;
     return SYLT_OK;
 }
 
@@ -2147,11 +2131,16 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->sincl64.p, 0, 2);
     if (e) return e;
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
-    if (w->regions_on && full_step && w->have_old && w->B_old == B && w->steps_since_part >= w->regions_period) {
-        // re-cut the regions by last step's load (device side, no synchronisation); the colours encode the old cut
-        k_rebalance<<<1, REBAL_THREADS, 0, st>>>(B, w->n_regions, w->reg_bodies.p, old.row_start, w->region_of.p, w->lidx.p, w->reg_start.p);
-        w->launches++;
+    if (w->regions_on && (w->resort_pending || (full_step && w->steps_since_part >= w->regions_period))) {
+        // (re)partition by the current positions and last step's load (device side, no synchronisation); the colours encode the old cut
+        k_resort<<<1, REBAL_THREADS, (SORT_CELLS + 1) * sizeof(int), st>>>(B, w->pose.p, w->reg_bodies.p, w->sort_keys.p);
+        SYLT_CUDA(cudaGetLastError());
+        k_rebalance<<<1, REBAL_THREADS, 0, st>>>(B, w->n_regions, w->reg_bodies.p, w->have_old ? old.row_start : nullptr, w->B_old, w->region_of.p,
+                                                 w->lidx.p, w->reg_start.p);
+        SYLT_CUDA(cudaGetLastError());
+        w->launches += 2;
         w->steps_since_part = 0;
+        w->resort_pending = false;
         w->recolor_all = true;
     }
     const int keep_colors = w->recolor_all ? 0 : 1;
@@ -2197,7 +2186,6 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         a.step_tag = w->step_tag;
         SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_regions, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_budget, st));
         w->steps_since_part++;
-        w->steps_since_sort++;
         w->last_regions = true;
     } else {
         w->last_regions = false;
@@ -2265,9 +2253,7 @@ int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
     int e = flush(w);
     if (e) return e;
     if (body_order_violated(w->hb)) return SYLT_ERR_BODY_ORDER;
-    // regions: partition on the host (a spatial sort) when bodies were added and, rarely, to refresh the spatial order the
-    // device-side k_rebalance cuts along
-    if (w->part_dirty || (w->regions_on && w->steps_since_sort >= w->regions_resort)) {
+    if (w->part_dirty) {  // bodies / joints / iterations changed: region solver on or off, buffers
         e = repartition(w);
         if (e) return e;
     }
@@ -2347,13 +2333,13 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
         const size_t b2 = (size_t)max_smem + 1024 - 1024 - fr.sharedSizeBytes - 1024;
         w->solve_budget = b2 & ~(size_t)15;
         SYLT_CUDA(cudaFuncSetAttribute(k_solve_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_budget));
+        SYLT_CUDA(cudaFuncSetAttribute(k_resort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SORT_CELLS + 1) * sizeof(int))));
         int per2 = 0;
         SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_solve_regions, SOLVE_THREADS, w->solve_budget));
         if (const char* ev = getenv("SYLT_REGIONS")) w->regions_mode = std::min(2, std::max(0, atoi(ev)));
         if (const char* ev = getenv("SYLT_REGIONS_MIN_BODIES")) w->regions_min_bodies = std::max(1, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_COUNT")) w->regions_count = std::max(0, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_PERIOD")) w->regions_period = std::max(1, atoi(ev));
-        if (const char* ev = getenv("SYLT_REGIONS_RESORT")) w->regions_resort = std::max(1, atoi(ev));
         if (per2 < 1 || w->ctas_per_sm != 1) w->regions_mode = 0;
     }
     int per_sm = 0;
@@ -2383,7 +2369,7 @@ static void free_all(SyltWorld* w) {
     }
     w->jbodies.release(); w->jla.release(); w->jr.release(); w->jm.release(); w->jparam.release(); w->jp.release(); w->jbias.release();
     w->jorder.release(); w->jcolor_start.release();
-    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release(); w->gadj.release(); w->cone_buf.release(); w->xrec.release();
+    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release(); w->sort_keys.release(); w->gadj.release(); w->cone_buf.release(); w->xrec.release();
 }
 
 int sylt_world_destroy(SyltWorld* w) {
