@@ -67,7 +67,6 @@ struct Counters {
     int remaining[MAX_ROUNDS];
     unsigned bar;  // grid barrier arrivals of this step's k_solve
     // region solver (k_solve_regions):
-    int order_alloc;                // next free entry of the `order` array (every CTA takes one private segment)
     int n_generic;                  // arbiters of the generic colours (cross-region pairs, interior overflow)
     int n_ghost;                    // replicas of generic arbiters replayed by neighbouring regions
     int max_slots, n_nonres;        // load of the busiest CTA; slots whose records / contacts did not fit into shared memory
@@ -581,9 +580,10 @@ struct SolveArgs {
     // regions (k_solve_regions): every body belongs to one region, region r is solved by CTA r
     const int *region_of, *lidx, *reg_start, *reg_bodies;  // body -> region, body -> index inside its region, CSR of the regions
     int n_regions, smem_bytes;                             // dynamic shared memory of k_solve_regions
-    int *gadj, *cone_buf;                                  // per body: its generic arbiters; per CTA: ghost arbiters
+    int2 *gadj, *cone_buf;                                 // per body: its generic arbiters (arbiter, owner region | colour << 16); per CTA: ghost arbiters (arbiter, colour)
     ulonglong2* xrec;                                      // export planes (one per pass) of versioned boundary-body velocities
     unsigned step_tag;
+    int probe_cta;                                         // diagnostics: the CTA whose set-up phases are stamped
 };
 
 // ---- light grid barrier: one monotonic counter, release-add on arrival, acquire-poll until everybody arrived.
@@ -1159,7 +1159,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     };
     stamp(0);
     __shared__ int s_cnt[NCX], s_fill[NCX], s_cstart[NCX + 1], s_clist[NCX];
-    __shared__ int s_ncl, s_nint, s_nbnd, s_obase, s_L, s_ngh, s_ngb, s_nown, s_bad;
+    __shared__ int s_ncl, s_nint, s_nbnd, s_L, s_ngh, s_ngb, s_nown, s_bad;
     __shared__ int s_scan[34];
     // Shared memory, carved as the sizes become known: boundary lists [nb], bodies (32 bytes each: own, then ghosts), ghost
     // list, slot records (12 bytes), contacts (36 bytes, all that is left).  During set-up the top of the area holds the
@@ -1177,8 +1177,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     int2* t_own = (int2*)t_gb - OWN_MAX;                  // (arbiter, colour) of the arbiters this region owns
     const unsigned char* scratch_lo = (const unsigned char*)t_own;
 
+    int tq_ = 32;
+    auto tstamp = [&]() { if (a.dbg && bid == a.probe_cta && lt == 0 && tq_ < 48) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[tq_++] = t; } };
     color_new_arbiters<true>(a, cn, bar, bar_target);
     stamp(1);
+    tstamp();
     auto dynamic = [&](int b) { return !(a.bflags[b] & FLAG_STATIC); };
     auto owner_region = [&](int e, int2 b) { return a.region_of[a.cur.partner[e] == b.x ? b.y : b.x]; };
 
@@ -1188,10 +1191,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         if (c < GEN_BIT) continue;
         const int2 b = a.cur.bodies[e];
         const unsigned long long lower = (1ull << (c - GEN_BIT)) - 1ull;
-        if (dynamic(b.x)) a.gadj[(size_t)b.x * GADJ + __popcll(__ldcg(&a.used[b.x]) & lower)] = e;
-        if (dynamic(b.y)) a.gadj[(size_t)b.y * GADJ + __popcll(__ldcg(&a.used[b.y]) & lower)] = e;
+        const int2 entry = make_int2(e, owner_region(e, b) | (c << 16));  // what the cone walk needs to know about e without touching it
+        if (dynamic(b.x)) a.gadj[(size_t)b.x * GADJ + __popcll(__ldcg(&a.used[b.x]) & lower)] = entry;
+        if (dynamic(b.y)) a.gadj[(size_t)b.y * GADJ + __popcll(__ldcg(&a.used[b.y]) & lower)] = entry;
     }
     grid_barrier(bar, bar_target);
+    tstamp();
+    unsigned long long t_setup0 = 0;
+    if (a.dbg && lt == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_setup0));
 
     // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) listed and counted by colour
     BodyIO io{a.vrec, a.sleep_ns, &cn->err};
@@ -1200,7 +1207,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
     __syncthreads();
     const bool fits = !s_bad;  // the region's bodies alone must leave room for the scratch (the host sizes the regions accordingly)
-    int* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA, in discovery order
+    int2* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA (arbiter, colour), in discovery order
     auto arb_insert = [&](int f) -> bool {  // true: f is new
         unsigned h = hash_u32((unsigned)f) & (HASH_CAP - 1);
         for (int probe = 0; probe < HASH_CAP; probe++) {
@@ -1215,7 +1222,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     auto add_ghost = [&](int f, int c) {
         if (!arb_insert(f)) return;
         const int g = atomicAdd(&s_ngh, 1);
-        if (g < CONE_CAP) { ghosts[g] = f; atomicAdd(&s_cnt[c], 1); }
+        if (g < CONE_CAP) { ghosts[g] = make_int2(f, c); atomicAdd(&s_cnt[c], 1); }
         else s_bad = 1;
     };
     // everything arbiter e (generic, colour c) depends on inside one generic phase: lower-coloured generic arbiters at its bodies
@@ -1230,51 +1237,63 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
             while (m) {
                 const int k = __ffsll((long long)m) - 1;
                 m &= m - 1ull;
-                const int f = __ldcg(&a.gadj[(size_t)z * GADJ + __popcll(uz & ((1ull << k) - 1ull))]);
-                if (owner_region(f, a.cur.bodies[f]) != R) add_ghost(f, GEN_BIT + k);  // (an own arbiter is a root of the walk anyway)
+                const int2 f = __ldcg(&a.gadj[(size_t)z * GADJ + __popcll(uz & ((1ull << k) - 1ull))]);
+                if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + k);  // (an own arbiter is a root of the walk anyway)
             }
         }
     };
-    for (int lb = lt; lb < nb && fits; lb += T) {
+    for (int lb = lt; lb < nb && fits; lb += T) {  // bodies: state, boundary list, the arbiters of the body's row
         const int b = a.reg_bodies[rb0 + lb];
         Vel v;
         float im, ii;
         io.get(b, v, im, ii);
         const float4 p = a.pose[b];
+        const unsigned long long ub = dynamic(b) ? __ldcg(&a.used[b]) : 0ull;
+        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
         s_body[2 * lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
         s_body[2 * lb + 1] = make_float4(p.x, p.y, im, ii);
-        const unsigned long long ub = dynamic(b) ? __ldcg(&a.used[b]) : 0ull;
-        if (ub != 0ull) {  // a boundary body: exported every pass; every generic arbiter at it is replayed here, whoever owns it
+        if (ub != 0ull) {  // a boundary body: exported every pass
             const int k = atomicAdd(&s_nbnd, 1);
             s_bnd[k] = lb;
             s_bndg[k] = b;
-            const int ng = __popcll(ub);
-            for (int r = 0; r < ng; r++) {
-                const int f = __ldcg(&a.gadj[(size_t)b * GADJ + r]);
-                if (owner_region(f, a.cur.bodies[f]) != R) add_ghost(f, __ldcg(&a.cur.color[f]));
-            }
         }
-        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
-        for (int e = e0; e < e1; e++) {
-            const int c = __ldcg(&a.cur.color[e]);
-            if (c < 0) continue;
-            atomicAdd(&s_cnt[c], 1);
-            const int k = atomicAdd(&s_nown, 1);
-            if (k < OWN_MAX) t_own[k] = make_int2(e, c); else s_bad = 1;
-            if (c >= GEN_BIT) expand(e, c);  // level 0 of the cone walk: the region's own generic arbiters are roots
+        if (e1 > e0) {
+            const int k = atomicAdd(&s_nown, e1 - e0);
+            for (int e = e0; e < e1; e++)
+                if (k + e - e0 < OWN_MAX) t_own[k + e - e0] = make_int2(e, -1); else s_bad = 1;
+        }
+    }
+    __syncthreads();
+    const int nown = min(s_nown, OWN_MAX);
+    for (int k = lt; k < nown; k += T) {  // own arbiters: colour; the generic ones are the roots of the cone walk (level 0)
+        const int e = t_own[k].x;
+        const int c = __ldcg(&a.cur.color[e]);
+        t_own[k].y = c;
+        if (c < 0) continue;
+        atomicAdd(&s_cnt[c], 1);
+        if (c >= GEN_BIT) expand(e, c);
+    }
+    for (int k = lt; k < s_nbnd; k += T) {  // every generic arbiter at a boundary body is replayed here, whoever owns it
+        const int b = s_bndg[k];
+        const int ng = __popcll(__ldcg(&a.used[b]));
+        for (int r = 0; r < ng; r++) {
+            const int2 f = __ldcg(&a.gadj[(size_t)b * GADJ + r]);
+            if ((f.y & 0xffff) != R) add_ghost(f.x, f.y >> 16);
         }
     }
     __syncthreads();
     // ---- 2c. cone walk: ghost arbiters found in one level are expanded in the next, until nothing new turns up
-    for (int f0 = 0;;) {
+    int levels = 0;
+    for (int f0 = 0;; levels++) {
         const int f1 = min(s_ngh, CONE_CAP);
         __syncthreads();
         if (f1 == f0) break;
-        for (int g = f0 + lt; g < f1; g += T) { const int f = __ldcg(&ghosts[g]); expand(f, __ldcg(&a.cur.color[f])); }
+        for (int g = f0 + lt; g < f1; g += T) { const int2 f = __ldcg(&ghosts[g]); expand(f.x, f.y); }
         __syncthreads();
         f0 = f1;
     }
-    const int ngh = min(s_ngh, CONE_CAP), nown = min(s_nown, OWN_MAX);
+    const int ngh = min(s_ngh, CONE_CAP);
+    tstamp();
     // ---- 2d. ghost bodies: bodies of other regions that this CTA's slots touch (dynamic: re-imported every pass; static: once)
     auto body_insert = [&](int z) {
         unsigned h = hash_u32((unsigned)z ^ 0x9e3779b9u) & (HASH_CAP - 1);
@@ -1307,10 +1326,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         if (a.region_of[b.x] != R) body_insert(b.x);
         if (a.region_of[b.y] != R) body_insert(b.y);
     };
-    for (int k = lt; k < nown; k += T) ghost_bodies_of(t_own[k].x);
-    for (int g = lt; g < ngh; g += T) ghost_bodies_of(__ldcg(&ghosts[g]));
+    for (int k = lt; k < nown; k += T) if (t_own[k].y >= 0) ghost_bodies_of(t_own[k].x);
+    for (int g = lt; g < ngh; g += T) ghost_bodies_of(__ldcg(&ghosts[g]).x);
     __syncthreads();
     const int ngb = min(s_ngb, GB_MAX);
+    tstamp();
     // ---- 2e. slot layout: generic colours first (their contacts must be shared-memory resident), then the interior colours
     int* s_gb = (int*)(s_body + 2 * ((size_t)nb + ngb));  // ghost bodies: global index | GHOST_FLAG if static (never imported again)
     if (lt == 0) {
@@ -1322,14 +1342,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         for (int c = GEN_BIT; c < NCX; c++) if (s_cnt[c]) s_clist[ncl++] = c;
         s_cstart[NCX] = run;
         s_ncl = ncl; s_nint = nint; s_L = run;
-        s_obase = run ? atomicAdd(&cn->order_alloc, run) : 0;
         if (mask) atomicOr(&cn->color_mask, mask);
         if (mask_int) atomicOr(&cn->color_mask_int, mask_int);
         if (ngen) atomicAdd(&cn->n_generic, ngen - ngh);
         if (ngh) atomicAdd(&cn->n_ghost, ngh);
         atomicMax(&cn->max_slots, run);
         // everything but the contacts must fit below the scratch; bodies are referenced through 15-bit indices
-        const bool room = (const unsigned char*)(s_gb + ngb + 3 * (size_t)run) <= scratch_lo && nb + ngb < 0x8000;
+        const bool room = (const unsigned char*)(s_gb + ngb + 4 * (size_t)run) <= scratch_lo && nb + ngb < 0x8000;
         if (s_bad || !room) {
             s_bad = 1;
             atomicExch(&cn->err, SYLT_ERR_CAPACITY);
@@ -1341,9 +1360,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     const bool bad = s_bad != 0;  // this CTA cannot solve; the error is flagged, the grid barrier below is still joined
     const int L = bad ? 0 : s_L, ncl = s_ncl, nint = s_nint, nbnd = s_nbnd;
     int* s_sb = s_gb + ngb;                               // slot: body refs, r1 | r2 << 16; ref = index into s_body | SREF_STATIC
-    int* s_sc = s_sb + L;                                 //       contact offset << 8 | count, or -1: contacts in the global arrays
+    int* s_sc = s_sb + L;                                 //       contact offset << 8 | count, or -1 - count: contacts in the global arrays
     float* s_sf = (float*)(s_sc + L);                     //       friction
-    float4* s_c0 = (float4*)(((size_t)(s_sf + L) + 15) & ~(size_t)15);  // contact: (position, normal)
+    int* s_so = (int*)(s_sf + L);                         //       first contact in the global arrays
+    float4* s_c0 = (float4*)(((size_t)(s_so + L) + 15) & ~(size_t)15);  // contact: (position, normal)
     const int CONCAP = bad ? 0 : (int)(((sm_raw + a.smem_bytes - (unsigned char*)s_c0) / 36) & ~(size_t)3);
     float4* s_c1 = s_c0 + CONCAP;                         //          (mass_normal, mass_tangent, bias, pn); before pre_step: (-, -, separation, pn)
     float* s_c2 = (float*)(s_c1 + CONCAP);                //          pt
@@ -1357,11 +1377,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         s_body[2 * (nb + g)] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
         s_body[2 * (nb + g) + 1] = make_float4(p.x, p.y, im, ii);
     }
-    int* order = a.order + s_obase;  // this CTA's slots by colour (within a colour the order is irrelevant); ghosts carry GHOST_FLAG
     const bool acc = a.accumulate != 0;
     const float kbias = a.poscorr ? 0.2f : 0.0f;
 
     stamp(2);
+    tstamp();
     // ---- 3. slots: position by colour, record (the bodies' shared-memory indices come from the hash table), then the contacts
     //         (which overwrite the scratch)
     constexpr int SREF_STATIC = 0x8000;
@@ -1371,54 +1391,74 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     auto place = [&](int e, int c, int flag) {
         const int ls = s_cstart[c] + atomicAdd(&s_fill[c], 1);
         const int2 b = a.cur.bodies[e];
-        order[ls] = e | flag;
+        const int2 mt = a.cur.meta[e];
         s_sb[ls] = body_ref(b.x) | (body_ref(b.y) << 16);
-        s_sc[ls] = a.cur.meta[e].x;
+        s_sc[ls] = mt.x;
+        s_so[ls] = mt.y | flag;  // contact offsets stay below 2^30
         s_sf[ls] = a.cur.friction[e];
     };
     if (!bad) {
-        for (int k = lt; k < nown; k += T) { const int2 ec = t_own[k]; place(ec.x, ec.y, 0); }
-        for (int g = lt; g < ngh; g += T) { const int f = __ldcg(&ghosts[g]); place(f, __ldcg(&a.cur.color[f]), GHOST_FLAG); }
+        for (int k = lt; k < nown; k += T) { const int2 ec = t_own[k]; if (ec.y >= 0) place(ec.x, ec.y, 0); }
+        for (int g = lt; g < ngh; g += T) { const int2 f = __ldcg(&ghosts[g]); place(f.x, f.y, GHOST_FLAG); }
     }
     __syncthreads();  // the scratch is dead from here on
-    {   // in-place exclusive scan of the contact counts
+    tstamp();
+    {   // in-place exclusive scan of the contact counts: count -> offset << 8 | count
         const int chunk = (L + T - 1) / T, q0 = min(lt * chunk, L), q1 = min(q0 + chunk, L);
         int sum = 0;
         for (int k = q0; k < q1; k++) sum += s_sc[k];
         int tot;
         int ex = block_excl_scan<int>(sum, &tot, s_scan);
-        for (int k = q0; k < q1; k++) { int t = s_sc[k]; s_sc[k] = ex; ex += t; }
+        for (int k = q0; k < q1; k++) { const int t = s_sc[k]; s_sc[k] = (ex << 8) | t; ex += t; }
     }
     __syncthreads();
+    tstamp();
     const int n_generic_slots = s_cstart[0];  // generic colours come first in the layout
     for (int ls = lt; ls < L; ls += T) {
-        const int e = __ldcg(&order[ls]) & ~GHOST_FLAG;
-        const int2 mt = a.cur.meta[e];
-        const int lc = s_sc[ls];
-        const bool res = lc + mt.x <= CONCAP;
+        const int sc = s_sc[ls], lc = sc >> 8, n = sc & 0xff, coff = s_so[ls] & ~GHOST_FLAG;
+        const bool res = lc + n <= CONCAP;
+        float4 ca[2], cc[2], cd[2];
+        if (res && n <= 2) {  // the usual case (box contacts): all loads in flight at once
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                if (q < n) { ca[q] = a.cur.ca[coff + q]; cc[q] = a.cur.cc[coff + q]; cd[q] = a.cur.cd[coff + q]; }
+        }
         if (!res) {
+            s_sc[ls] = -1 - n;  // contacts stay in the global arrays
             atomicAdd(&cn->n_nonres, 1);
             if (ls < n_generic_slots) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); atomicOr(&cn->why, 32); }  // a replica has no global working storage
-        }
-        s_sc[ls] = res ? (lc << 8) | mt.x : -1;
-        if (res)
-            for (int q = 0; q < mt.x; q++) {
-                const float4 ca = a.cur.ca[mt.y + q], cc = a.cur.cc[mt.y + q], cd = a.cur.cd[mt.y + q];
-                s_c0[lc + q] = make_float4(cd.x, cd.y, ca.x, ca.y);
-                s_c1[lc + q] = make_float4(0.0f, 0.0f, cc.w, cc.y);
-                s_c2[lc + q] = cc.z;
+        } else if (n <= 2) {
+#pragma unroll
+            for (int q = 0; q < 2; q++)
+                if (q < n) {
+                    s_c0[lc + q] = make_float4(cd[q].x, cd[q].y, ca[q].x, ca[q].y);
+                    s_c1[lc + q] = make_float4(0.0f, 0.0f, cc[q].w, cc[q].y);
+                    s_c2[lc + q] = cc[q].z;
+                }
+        } else {
+            for (int q = 0; q < n; q++) {
+                const float4 xa = a.cur.ca[coff + q], xc = a.cur.cc[coff + q], xd = a.cur.cd[coff + q];
+                s_c0[lc + q] = make_float4(xd.x, xd.y, xa.x, xa.y);
+                s_c1[lc + q] = make_float4(0.0f, 0.0f, xc.w, xc.y);
+                s_c2[lc + q] = xc.z;
             }
+        }
     }
     if (a.dbg && lt == 0) {  // diagnostics: the CTA's load
         int mxc = 0;
         for (int k = 0; k < ncl; k++) mxc = max(mxc, s_cnt[s_clist[k]]);
+        unsigned long long t_setup1;
+        asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_setup1));
         unsigned long long* d = a.dbg + 64 + 4 * 1024 + bid * 4;
-        d[0] = (unsigned long long)L;
+        d[0] = (unsigned long long)L | ((unsigned long long)levels << 24) | ((t_setup1 - t_setup0) << 32);
         d[1] = (unsigned long long)nint | ((unsigned long long)(ncl - nint) << 32);
         d[2] = (unsigned long long)ngh | ((unsigned long long)ngb << 32);
         d[3] = (unsigned long long)nb | ((unsigned long long)mxc << 32);
     }
+    __syncthreads();
+    tstamp();
     grid_barrier(bar, bar_target);  // errors are in; every CTA agrees on going on
+    tstamp();
     if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;
 
     // One slot of one colour hop.  Bodies and (normally) contacts are in shared memory; r1, r2 are recomputed from the
@@ -1451,7 +1491,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
                 }
             }
         } else {  // an own interior slot beyond the shared-memory budget: the global contact arrays are its working storage
-            const int2 mt = a.cur.meta[__ldcg(&order[ls])];
+            const int2 mt = make_int2(-1 - sc, s_so[ls]);
             for (int q = 0; q < mt.x; q++) {
                 const float4 ca = a.cur.ca[mt.y + q], cc = a.cur.cc[mt.y + q];
                 ContactConst k0;
@@ -1529,12 +1569,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     stamp(5);
     // ---- 6. the owner writes its shared-memory resident contacts back (warm start of the next step, read-back)
     for (int ls = lt; ls < L; ls += T) {
-        const int sc = s_sc[ls];
-        const int e = __ldcg(&order[ls]);
-        if (sc < 0 || (e & GHOST_FLAG)) continue;
+        const int sc = s_sc[ls], so = s_so[ls];
+        if (sc < 0 || (so & GHOST_FLAG)) continue;
         const int sb = s_sb[ls];
         const float4 m1 = s_body[2 * (sb & 0x7fff) + 1], m2 = s_body[2 * ((sb >> 16) & 0x7fff) + 1];
-        const int coff = a.cur.meta[e].y, lc = sc >> 8, n = sc & 0xff;
+        const int coff = so, lc = sc >> 8, n = sc & 0xff;
         for (int q = 0; q < n; q++) {
             const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
             const V2 r1 = mk(c0.x, c0.y) - mk(m1.x, m1.y), r2 = mk(c0.x, c0.y) - mk(m2.x, m2.y);
@@ -1779,7 +1818,8 @@ struct SyltWorld {
 
     // regions (k_solve_regions): spatial partition of the bodies, recomputed on the host when bodies were added or the
     // share of cross-region arbiters has grown
-    DBuf<int> region_of, lidx, reg_start, reg_bodies, sort_keys, gadj, cone_buf;
+    DBuf<int> region_of, lidx, reg_start, reg_bodies, sort_keys;
+    DBuf<int2> gadj, cone_buf;
     DBuf<ulonglong2> xrec;
     unsigned step_tag = 0;
     int regions_mode = 1;            // SYLT_REGIONS: 0 = never (k_solve only), 1 = joint-free worlds of at least regions_min_bodies (default), 2 = always
@@ -2010,7 +2050,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->uncolored.ensure((size_t)ca));
         SYLT_CUDA(w->uncolored2.ensure((size_t)ca));
         SYLT_CUDA(w->prop.ensure((size_t)ca));
-        SYLT_CUDA(w->order.ensure((size_t)ca + (size_t)w->coop_blocks * CONE_CAP));  // + the ghost slots of k_solve_regions
+        SYLT_CUDA(w->order.ensure((size_t)ca));
         for (int k = 0; k < 2; k++) {
             SyltWorld::ArbBufs& a = w->arb[k];
             const bool keep_set = (k != w->cur) && w->have_old && w->have_last;  // last step's arbiters survive a regrow
@@ -2184,6 +2224,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
             w->step_tag = 1;
         }
         a.step_tag = w->step_tag;
+        a.probe_cta = getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->coop_blocks / 2;
         SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_regions, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_budget, st));
         w->steps_since_part++;
         w->last_regions = true;
@@ -2206,6 +2247,11 @@ void print_solver_timing(SyltWorld* w) {
     const int G = w->coop_blocks;
     std::vector<unsigned long long> t(64 + 8 * 1024);
     if (cudaMemcpy(t.data(), w->dbg.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
+    if (w->last_regions && t[32]) {
+        fprintf(stderr, "  set-up of one CTA [us]: gadj+barrier | bodies+rows | cone walk | ghost bodies | layout+ghost data | place | scan | contacts | barrier:");
+        for (int k = 33; k < 48 && t[k]; k++) fprintf(stderr, " %.1f", (t[k] - t[k - 1]) * 1e-3);
+        fprintf(stderr, "\n");
+    }
     if (w->last_regions && t[64] && G <= 1024) {
         const unsigned long long *pc = &t[64], *ld = &t[64 + 4 * 1024];  // per CTA: 4 stamps of pass 5; 4 words of load figures
         double mn[3] = {1e30, 1e30, 1e30}, mx[3] = {0, 0, 0}, sm[3] = {0, 0, 0};
@@ -2216,12 +2262,12 @@ void print_solver_timing(SyltWorld* w) {
             }
         std::vector<int> ord((size_t)G);
         for (int c = 0; c < G; c++) ord[(size_t)c] = c;
-        std::sort(ord.begin(), ord.end(), [&](int x, int y) { return pc[x * 4 + 1] - pc[x * 4] > pc[y * 4 + 1] - pc[y * 4]; });
-        for (int q : {0, G / 2, G - 1}) {
+        std::sort(ord.begin(), ord.end(), [&](int x, int y) { return (ld[x * 4] >> 32) > (ld[y * 4] >> 32); });  // slowest set-up first
+        for (int q : {0, 1, 2, G / 2, G - 1}) {
             const int c = ord[(size_t)q];
             const unsigned long long* d = &ld[c * 4];
-            fprintf(stderr, "  CTA %3d: interior %.2f us | %llu slots, %llu + %llu colours, ghosts %llu arbiters / %llu bodies, %llu own bodies, widest colour %llu\n", c,
-                    (double)(pc[c * 4 + 1] - pc[c * 4]) * 1e-3, d[0], d[1] & 0xffffffffull, d[1] >> 32, d[2] & 0xffffffffull, d[2] >> 32,
+            fprintf(stderr, "  CTA %3d: interior %.2f us | set-up %.1f us, cone walk %llu levels | %llu slots, %llu + %llu colours, ghosts %llu arbiters / %llu bodies, %llu own bodies, widest colour %llu\n", c,
+                    (double)(pc[c * 4 + 1] - pc[c * 4]) * 1e-3, (double)(d[0] >> 32) * 1e-3, (d[0] >> 24) & 0xffull, d[0] & 0xffffffull, d[1] & 0xffffffffull, d[1] >> 32, d[2] & 0xffffffffull, d[2] >> 32,
                     d[3] & 0xffffffffull, d[3] >> 32);
         }
         fprintf(stderr, "  pass 5, all CTAs [us] min/avg/max: interior %.2f/%.2f/%.2f  export+import %.2f/%.2f/%.2f  generic %.2f/%.2f/%.2f\n", mn[0], sm[0] / G, mx[0],
