@@ -1282,6 +1282,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         }
     }
     __syncthreads();
+    tstamp();
     // ---- 2c. cone walk: ghost arbiters found in one level are expanded in the next, until nothing new turns up
     int levels = 0;
     for (int f0 = 0;; levels++) {
@@ -1823,7 +1824,7 @@ struct SyltWorld {
     DBuf<ulonglong2> xrec;
     unsigned step_tag = 0;
     int regions_mode = 1;            // SYLT_REGIONS: 0 = never (k_solve only), 1 = joint-free worlds of at least regions_min_bodies (default), 2 = always
-    int regions_min_bodies = 8192, regions_count = 0, regions_period = 128;
+    int regions_min_bodies = 1000, regions_count = 0, regions_period = 128;
     bool regions_on = false;         // the partition on the device is valid for the current bodies
     bool part_dirty = true;          // bodies were added / the mode may have changed
     bool last_regions = false;       // the last enqueued step ran k_solve_regions
