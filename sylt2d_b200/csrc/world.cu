@@ -1458,9 +1458,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     }
     __syncthreads();
     tstamp();
-    grid_barrier(bar, bar_target);  // errors are in; every CTA agrees on going on
-    tstamp();
-    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;
+    // No grid barrier here: a CTA starts its passes as soon as it is set up and from then on only ever waits for the exports
+    // of its neighbours.  (A CTA that could not set itself up has flagged the error; whoever waits for it gives up, see the
+    // import loop, and nothing is written back.)
 
     // One slot of one colour hop.  Bodies and (normally) contacts are in shared memory; r1, r2 are recomputed from the
     // contact position exactly as Arbiter::pre_step / apply_impulse do (arbiter.rs:192-193, 236-237).
@@ -1545,8 +1545,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
             float im, ii;
             unsigned spins = 0;
             while (!xio.try_get(z, tag, true, o, im, ii)) {
-                if ((++spins & 0xfffu) == 0u) {
-                    if (*(volatile int*)&cn->err == SYLT_ERR_INTERNAL) break;
+                if ((++spins & 0x3ffu) == 0u) {
+                    if (*(volatile int*)&cn->err != 0) break;  // a failed step: the owner may never export
                     if (spins > (1u << 23)) { atomicExch(&cn->err, SYLT_ERR_INTERNAL); break; }
                 }
             }
@@ -1559,16 +1559,18 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     };
 
     stamp(3);
-    // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228).  The barrier keeps every read of the global contact arrays and
-    //         of the poses by a replica ahead of the owner's later writes.
+    // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228)
     sweep(0u);
-    grid_barrier(bar, bar_target);
     stamp(4);
     // ---- 5. passes 1..I: apply_impulse (world.rs:132-140)
     for (int it = 1; it <= a.iterations; it++) sweep((unsigned)it);
 
     stamp(5);
-    // ---- 6. the owner writes its shared-memory resident contacts back (warm start of the next step, read-back)
+    // ---- 6. the owner writes its shared-memory resident contacts back (warm start of the next step, read-back).
+    //         The one barrier of the solve: every replica has read the global contact arrays and the poses (set-up) before
+    //         any owner overwrites them.
+    grid_barrier(bar, bar_target);
+    if (*(volatile int*)&cn->err != 0) return;
     for (int ls = lt; ls < L; ls += T) {
         const int sc = s_sc[ls], so = s_so[ls];
         if (sc < 0 || (so & GHOST_FLAG)) continue;
