@@ -16,9 +16,12 @@
 //                              (Arbiter::update, arbiter.rs:137-181 incl. quirk Q-2; friction persistence Q-17);
 //                              persisting arbiters keep their colour
 //   k_solve        cooperative persistent kernel: incremental graph colouring of new arbiters, then
-//                              Arbiter::pre_step / Joint::pre_step / iterations x apply_impulse per colour with grid
-//                              barriers (arbiter.rs:182-298, joint.rs:57-130), then position integration
-//                              (world.rs:143-150)
+//                              Arbiter::pre_step / Joint::pre_step / iterations x apply_impulse in colour order as a
+//                              version-gated dataflow sweep through L2 (arbiter.rs:182-298, joint.rs:57-130), then
+//                              position integration (world.rs:143-150).  Worlds with joints, small worlds.
+//   k_solve_regions            the same sweep for joint-free worlds of >= 1000 bodies: bodies partitioned into regions
+//                              (k_resort, k_rebalance) that live in shared memory, cross-region arbiters replayed
+//                              redundantly from ghost bodies (see the comment at the kernel)
 //
 // Gauss-Seidel order: arbiter colours ascending, then joint colours ascending (within a colour constraints touch
 // disjoint dynamic bodies, so the result equals the sequential sweep in that order bit for bit; static bodies
