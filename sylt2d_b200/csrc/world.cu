@@ -205,8 +205,8 @@ __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, co
     int4 ci = cinfo[i];
     if (ci.z & FLAG_LARGE) return;
     int pos = cell_start[cell_hash(ci.x, ci.y, gp.mask)] + rank[i];
-    cent_info[pos] = make_int4(i, ci.x, ci.y, ci.z);
-    cent_aabb[pos] = aabb[i];
+    cent_info[2 * pos] = make_int4(i, ci.x, ci.y, ci.z);  // info and AABB of an entry share one 32-byte sector
+    cent_aabb[2 * pos] = aabb[i];
 }
 
 // Row i = partners body i owns: small-small pairs belong to the lower index, small-large pairs to the small
@@ -236,8 +236,8 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
             for (int q = 0; q < 9; q++) {
                 int cx = x0 + q % 3, cy = y0 + q / 3;
                 for (int k = k0[q]; k < k1[q]; k++) {
-                    int4 cj = cent_info[k];
-                    float4 ab = cent_aabb[k];
+                    int4 cj = cent_info[2 * k];
+                    float4 ab = cent_aabb[2 * k];
                     if (cj.x <= i || cj.y != cx || cj.z != cy) continue;  // lower index owns the pair; another cell may share the bucket
                     if (st_i && (cj.w & FLAG_STATIC)) continue;
                     if (aabb_overlap(my, ab)) found(cj.x);
@@ -249,10 +249,10 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
                     int h = cell_hash(cx, cy, gp.mask);
                     int ke = cell_start[h + 1];
                     for (int k = cell_start[h]; k < ke; k++) {
-                        int4 cj = cent_info[k];
+                        int4 cj = cent_info[2 * k];
                         if (cj.x <= i || cj.y != cx || cj.z != cy) continue;
                         if (st_i && (cj.w & FLAG_STATIC)) continue;
-                        if (aabb_overlap(my, cent_aabb[k])) found(cj.x);
+                        if (aabb_overlap(my, cent_aabb[2 * k])) found(cj.x);
                     }
                 }
         }
@@ -273,17 +273,79 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
     }
 }
 
+// Count pass: ROW_LANES lanes per body.  In the usual case (the body's search window is a 3 x 3 block of cells) the nine cells
+// and the large list are dealt to the lanes, so the dependent loads of a row search (bucket range -> entries) of several cells
+// run side by side; the lanes' counts are combined with shuffles and the partners land in row_tmp in lane order (k_rows_emit
+// sorts them anyway).  Anything else (a large body, a wider window) is searched by lane 0 alone.  Bodies are taken in cell
+// order, so neighbouring groups search the same buckets.  (16 lanes are fastest up to ~20k bodies but issue-bound at 100k —
+// 32 M warp instructions —, one lane is latency-bound everywhere; 4 is the compromise.)
+constexpr int ROW_LANES = 4;
 __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
                                                     const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    int n = 0;
+    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
+    const int g = gi / ROW_LANES, sub = gi % ROW_LANES;
+    if (g >= B) return;  // (the lanes of a body leave together; the masks below name only those lanes)
+    const unsigned gmask = ((1u << ROW_LANES) - 1u) << (threadIdx.x & 31 & ~(ROW_LANES - 1));
+    const int i = g < B - n_large ? cent_info[2 * g].x : large[g - (B - n_large)];
+    const float4 my = aabb[i];
+    const int4 ci = cinfo[i];
+    const bool st_i = (ci.z & FLAG_STATIC) != 0;
     int* tmp = row_tmp + (size_t)i * ROWTMP;
-    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) {
-        if (n < ROWTMP) tmp[n] = j;
-        n++;
-    });
-    row_count[i] = n;
+    int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
+    bool fast = false;
+    if (!(ci.z & FLAG_LARGE)) {
+        x0 = cell_coord(my.x - 0.5f * gp.cell, gp.cell); x1 = cell_coord(my.z + 0.5f * gp.cell, gp.cell);
+        y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell); y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
+        fast = x1 - x0 <= 2 && y1 - y0 <= 2;
+    }
+    // one walk over this lane's share; `pre` < 0: count only, otherwise write the partners from position `pre` on
+    auto walk = [&](int pre) -> int {
+        int cnt = 0;
+        int k0[3], k1[3];
+#pragma unroll
+        for (int q = 0; q < 3; q++) {  // bucket ranges first (independent loads), then the entries
+            const int cell = sub + q * ROW_LANES, cx = x0 + cell % 3, cy = y0 + cell / 3;
+            const bool ok = cell < 9 && cx <= x1 && cy <= y1;
+            const int h = cell_hash(cx, cy, gp.mask);
+            k0[q] = ok ? cell_start[h] : 0;
+            k1[q] = ok ? cell_start[h + 1] : 0;
+        }
+#pragma unroll
+        for (int q = 0; q < 3; q++) {
+            const int cell = sub + q * ROW_LANES, cx = x0 + cell % 3, cy = y0 + cell / 3;
+            for (int k = k0[q]; k < k1[q]; k++) {
+                const int4 cj = cent_info[2 * k];
+                const float4 ab = cent_aabb[2 * k];
+                if (cj.x <= i || cj.y != cx || cj.z != cy) continue;  // lower index owns the pair; another cell may share the bucket
+                if (st_i && (cj.w & FLAG_STATIC)) continue;
+                if (aabb_overlap(my, ab)) { if (pre >= 0 && pre + cnt < ROWTMP) tmp[pre + cnt] = cj.x; cnt++; }
+            }
+        }
+        if (sub == ROW_LANES - 1)
+            for (int k = 0; k < n_large; k++) {
+                const int j = large[k];
+                if (st_i && (cinfo[j].z & FLAG_STATIC)) continue;
+                if (aabb_overlap(my, aabb[j])) { if (pre >= 0 && pre + cnt < ROWTMP) tmp[pre + cnt] = j; cnt++; }
+            }
+        return cnt;
+    };
+    int cnt = 0;
+    if (fast) cnt = walk(-1);
+    else if (sub == 0)
+        row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) {
+            if (cnt < ROWTMP) tmp[cnt] = j;
+            cnt++;
+        });
+    int pre = cnt;  // inclusive prefix over the lanes of the body
+#pragma unroll
+    for (int o = 1; o < ROW_LANES; o <<= 1) {
+        const int u = __shfl_up_sync(gmask, pre, o, ROW_LANES);
+        if (sub >= o) pre += u;
+    }
+    const int total = __shfl_sync(gmask, pre, ROW_LANES - 1, ROW_LANES);
+    pre -= cnt;
+    if (fast && cnt > 0 && pre < ROWTMP) walk(pre);  // second walk over the (now cached) entries: write the partners
+    if (sub == 0) row_count[i] = total;
 }
 
 __global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
@@ -1781,8 +1843,7 @@ struct SyltWorld {
     DBuf<float4> pose, vel, force, mp, geom, aabb;
     DBuf<float2> rotc, lverts;
     DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, large, row_count, row_start, row_tmp;
-    DBuf<int4> cinfo, cent_info;
-    DBuf<float4> cent_aabb;
+    DBuf<int4> cinfo, cent_info;  // cent_info: interleaved (info, AABB) entries of the cell-ordered copy
     DBuf<int2> pairs;
     DBuf<unsigned long long> info, pscan, claim, spart64;
     DBuf<int> spart32;
@@ -1945,8 +2006,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->rotc.ensure(B));
         SYLT_CUDA(w->rank.ensure(B));
         SYLT_CUDA(w->cinfo.ensure(B));
-        SYLT_CUDA(w->cent_info.ensure(B));
-        SYLT_CUDA(w->cent_aabb.ensure(B));
+        SYLT_CUDA(w->cent_info.ensure(2 * B));
         SYLT_CUDA(w->row_count.ensure(B + 1));
         SYLT_CUDA(w->row_start.ensure(B + 2));
         SYLT_CUDA(w->row_tmp.ensure(B * ROWTMP));
@@ -2156,14 +2216,14 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->launches++;
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
     if (e) return e;
-    k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->gp);
+    k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp);
     const int nbR = (B + 127) / 128;
-    k_rows_count<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->large.p, w->n_large, w->gp,
+    k_rows_count<<<(B * ROW_LANES + 127) / 128, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp,
                                       w->row_count.p, w->row_tmp.p);
     w->launches += 2;
     e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->sincl32.p, 0, 1);
     if (e) return e;
-    k_rows_emit<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, w->cent_aabb.p, w->large.p, w->n_large, w->gp,
+    k_rows_emit<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp,
                                      w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn);
     w->launches += 1;
     const int gridP = w->num_sms * 8;
@@ -2410,7 +2470,7 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
 static void free_all(SyltWorld* w) {
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
-    w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->cent_aabb.release(); w->large.release(); w->row_count.release();
+    w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
     w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
     w->prop.release(); w->order.release(); w->sincl32.release(); w->sincl64.release(); w->scan_flag.release(); w->scan_ticket.release();
