@@ -1244,9 +1244,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
 
     int tq_ = 32;
     auto tstamp = [&]() { if (a.dbg && bid == a.probe_cta && lt == 0 && tq_ < 48) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[tq_++] = t; } };
+    // a step that already failed in the broad phase (capacity) has holes in its arbiter arrays: nothing to solve, error reported
+    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;
     color_new_arbiters<true>(a, cn, bar, bar_target);
     stamp(1);
     tstamp();
+    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // an arbiter without a free colour (every CTA sees it: the colouring ends with a barrier)
     auto dynamic = [&](int b) { return !(a.bflags[b] & FLAG_STATIC); };
     auto owner_region = [&](int e, int2 b) { return a.region_of[a.cur.partner[e] == b.x ? b.y : b.x]; };
 
@@ -1395,10 +1398,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     for (int k = lt; k < nown; k += T) if (t_own[k].y >= 0) ghost_bodies_of(t_own[k].x);
     for (int g = lt; g < ngh; g += T) ghost_bodies_of(__ldcg(&ghosts[g]).x);
     __syncthreads();
-    const int ngb = min(s_ngb, GB_MAX);
+    const int ngb_found = min(s_ngb, GB_MAX);
     tstamp();
     // ---- 2e. slot layout: generic colours first (their contacts must be shared-memory resident), then the interior colours
-    int* s_gb = (int*)(s_body + 2 * ((size_t)nb + ngb));  // ghost bodies: global index | GHOST_FLAG if static (never imported again)
+    int* s_gb = (int*)(s_body + 2 * ((size_t)nb + ngb_found));  // ghost bodies: global index | GHOST_FLAG if static (never imported again)
     if (lt == 0) {
         int run = 0, ncl = 0, nint = 0, ngen = 0;
         unsigned long long mask = 0ull;
@@ -1414,7 +1417,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         if (ngh) atomicAdd(&cn->n_ghost, ngh);
         atomicMax(&cn->max_slots, run);
         // everything but the contacts must fit below the scratch; bodies are referenced through 15-bit indices
-        const bool room = (const unsigned char*)(s_gb + ngb + 4 * (size_t)run) <= scratch_lo && nb + ngb < 0x8000;
+        const bool room = (const unsigned char*)(s_gb + ngb_found + 4 * (size_t)run) <= scratch_lo && nb + ngb_found < 0x8000;
         if (s_bad || !room) {
             s_bad = 1;
             atomicExch(&cn->err, SYLT_ERR_CAPACITY);
@@ -1424,7 +1427,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     __syncthreads();
     if (!a.run_solver) return;
     const bool bad = s_bad != 0;  // this CTA cannot solve; the error is flagged, the grid barrier below is still joined
-    const int L = bad ? 0 : s_L, ncl = s_ncl, nint = s_nint, nbnd = s_nbnd;
+    const int ngb = bad ? 0 : ngb_found;
+    const int L = bad ? 0 : s_L, ncl = bad ? 0 : s_ncl, nint = bad ? 0 : s_nint, nbnd = bad ? 0 : s_nbnd;  // (a CTA that cannot solve idles through the passes)
     int* s_sb = s_gb + ngb;                               // slot: body refs, r1 | r2 << 16; ref = index into s_body | SREF_STATIC
     int* s_sc = s_sb + L;                                 //       contact offset << 8 | count, or -1 - count: contacts in the global arrays
     float* s_sf = (float*)(s_sc + L);                     //       friction
@@ -1456,6 +1460,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     };
     auto place = [&](int e, int c, int flag) {
         const int ls = s_cstart[c] + atomicAdd(&s_fill[c], 1);
+        if (ls >= s_cstart[c] + s_cnt[c]) { atomicExch(&cn->err, SYLT_ERR_INTERNAL); atomicOr(&cn->why, 128); return; }  // (never: counted and placed from the same lists)
         const int2 b = a.cur.bodies[e];
         const int2 mt = a.cur.meta[e];
         s_sb[ls] = body_ref(b.x) | (body_ref(b.y) << 16);
@@ -1556,7 +1561,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
                     if (acc) { s_c1[lc + q].w = pn; s_c2[lc + q] = pt; }
                 }
             }
-        } else {  // an own interior slot beyond the shared-memory budget: the global contact arrays are its working storage
+        } else if (!(s_so[ls] & GHOST_FLAG)) {  // an own slot beyond the shared-memory budget: the global contact arrays are its working
+            // storage (a replica in that situation has failed the step, SYLT_ERR_CAPACITY, and is skipped: it must not touch them)
             const int2 mt = make_int2(-1 - sc, s_so[ls]);
             for (int q = 0; q < mt.x; q++) {
                 const float4 ca = a.cur.ca[mt.y + q], cc = a.cur.cc[mt.y + q];
@@ -1697,6 +1703,41 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* p
     for (int k = lt; k <= SORT_CELLS; k += T) s_hist[k] = 0;
     __syncthreads();
     for (int k = 0; k < (T >> 5); k++) { x0 = fminf(x0, s_red[0][k]); x1 = fmaxf(x1, s_red[1][k]); y0 = fminf(y0, s_red[2][k]); y1 = fmaxf(y1, s_red[3][k]); }
+    // A body that has been shot far away must not blow the grid up to one cell for everybody else: trim the box to the
+    // 0.1 % .. 99.9 % range of the coordinates (1024-bin histograms), again while that shrinks it a lot.  Bodies outside
+    // land in the edge cells.
+    for (int trim = 0; trim < 4; trim++) {
+        __syncthreads();
+        for (int k = lt; k < 2048; k += T) s_hist[k] = 0;
+        __syncthreads();
+        const float sx = 1024.0f / fmaxf(x1 - x0, 1.0e-6f), sy = 1024.0f / fmaxf(y1 - y0, 1.0e-6f);
+        for (int i = lt; i < B; i += T) {
+            const float4 p = pose[i];
+            if (!(fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f)) continue;
+            atomicAdd(&s_hist[min(1023, max(0, (int)((p.x - x0) * sx)))], 1);
+            atomicAdd(&s_hist[1024 + min(1023, max(0, (int)((p.y - y0) * sy)))], 1);
+        }
+        __syncthreads();
+        if (lt < 2) {  // lane 0: x, lane 1: y
+            const int* h = s_hist + 1024 * lt;
+            const int q = max(1, B / 1000);
+            int lo = 0, hi = 1023, acc = 0;
+            for (acc = h[0]; acc <= q && lo < 1023; acc += h[++lo]) {}
+            for (acc = h[1023]; acc <= q && hi > 0; acc += h[--hi]) {}
+            if (hi < lo) hi = lo;
+            s_red[lt][0] = (float)lo;
+            s_red[lt][1] = (float)(hi + 1);
+        }
+        __syncthreads();
+        const float wx = (x1 - x0) / 1024.0f, wy = (y1 - y0) / 1024.0f;
+        const float nx0 = x0 + s_red[0][0] * wx, nx1 = x0 + s_red[0][1] * wx, ny0 = y0 + s_red[1][0] * wy, ny1 = y0 + s_red[1][1] * wy;
+        const bool shrunk = (nx1 - nx0) < 0.25f * (x1 - x0) || (ny1 - ny0) < 0.25f * (y1 - y0);
+        if (!shrunk) break;
+        x0 = nx0; x1 = nx1; y0 = ny0; y1 = ny1;
+    }
+    __syncthreads();
+    for (int k = lt; k <= SORT_CELLS; k += T) s_hist[k] = 0;
+    __syncthreads();
     const float span = fmaxf(fmaxf(x1 - x0, y1 - y0), 1.0e-3f);
     const float inv = (float)(1 << SORT_BITS) / (span * 1.0001f);
     auto key_of = [&](float4 p) -> int {
@@ -2308,8 +2349,9 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
 // k_solve_regions, the phases of pass 5 over all CTAs plus the load of the slowest / median / fastest CTA.
 void print_solver_timing(SyltWorld* w) {
     if (w->last.err)
-        fprintf(stderr, "step error %d (why %d, max slots %d, ghosts %d, uncoloured %d)\n", w->last.err, w->last.why, w->last.max_slots, w->last.n_ghost,
-                w->last.n_uncolored);
+        fprintf(stderr, "step error %d (why %d, max slots %d, ghosts %d, uncoloured %d; pairs %d / %lld, arbiters %d / %lld, contacts %d / %lld, colouring rounds %d)\n",
+                w->last.err, w->last.why, w->last.max_slots, w->last.n_ghost, w->last.n_uncolored, w->last.n_pairs, (long long)w->cap_pairs, w->last.n_arb,
+                (long long)w->cap_arb, w->last.n_con, (long long)w->cap_con, w->last.rounds);
     const int G = w->coop_blocks;
     std::vector<unsigned long long> t(64 + 8 * 1024);
     if (cudaMemcpy(t.data(), w->dbg.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
@@ -2352,6 +2394,10 @@ int finish(SyltWorld* w) {
     w->inflight = false;
     w->have_last = true;
     if (w->last_regions) {
+        if (w->last.err == SYLT_ERR_CAPACITY && w->last.why != 0) {  // a region outgrew k_solve_regions' tables: this world goes on with k_solve
+            w->regions_mode = 0;
+            w->part_dirty = true;
+        }
         w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
     }
     if (w->timing) print_solver_timing(w);
