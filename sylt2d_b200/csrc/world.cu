@@ -2356,7 +2356,7 @@ void print_solver_timing(SyltWorld* w) {
     std::vector<unsigned long long> t(64 + 8 * 1024);
     if (cudaMemcpy(t.data(), w->dbg.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
     if (w->last_regions && t[32]) {
-        fprintf(stderr, "  set-up of one CTA [us]: gadj+barrier | bodies+rows | cone walk | ghost bodies | layout+ghost data | place | scan | contacts | barrier:");
+        fprintf(stderr, "  set-up of CTA %d [us]: generic table + barrier | bodies, rows, cone roots | cone walk | ghost bodies | layout, ghost data | slot records | scan | contacts:", getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->coop_blocks / 2);
         for (int k = 33; k < 48 && t[k]; k++) fprintf(stderr, " %.1f", (t[k] - t[k - 1]) * 1e-3);
         fprintf(stderr, "\n");
     }
