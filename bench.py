@@ -205,6 +205,34 @@ def bench_world100k(device, steps, cpu=True):
     return out
 
 
+def bench_other_configs(device):
+    """BASELINE.json configs 2 and 4 (parity-test cases, timed here for reference; single GPU):
+    ms/step of the 10k mixed box + polygon pile, body-steps/s of 8192 joint worlds (4096 bridges + 4096 multi-pendulums)."""
+    from sylt2d_b200 import World, Batch, scenes
+    out = {}
+    sc = scenes.mixed_pile(10000, seed=1234, iterations=ITER)
+    w = World(sc.gravity, sc.iterations, device=device)
+    w.load_scene(sc)
+    w.step_n(sc.dt, 150)  # the pile has landed; (much later the reference's correction-free polygon contacts, quirk Q-10, let it interpenetrate)
+    w.timer_start()
+    w.step_n_async(sc.dt, 100)
+    ms = w.timer_stop()
+    w.sync()
+    out["mixed_pile_10k"] = {"ms_per_step": ms / 100, "stats": w.get_stats()}
+    for name, scene, jit in (("bridge", scenes.bridge(ITER), 0.0), ("multi_pendulum", scenes.multi_pendulum(ITER), 1.0)):
+        n = 4096
+        bodies, boff, joints, joff = scenes.tile_worlds(scene, n, seed=5, omega_jitter=jit)
+        b = Batch(bodies, boff, joints, joff, scene.gravity, scene.iterations, device=device, ctx=scene.ctx)
+        b.step_n(scene.dt, 50)
+        b.timer_start()
+        b.step_n_async(scene.dt, 100)
+        ms = b.timer_stop()
+        b.sync()
+        out[f"joint_worlds_{name}_4096"] = {"ms_per_step": ms / 100, "bodies_per_world": scene.num_bodies, "joints_per_world": int(scene.joints.shape[0]),
+                                            "body_steps_per_sec": n * scene.num_bodies * 100 / (ms * 1e-3)}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -387,6 +415,10 @@ def main():
                 out["world100k"] = bench_world100k(local_rank, 100, cpu=not args.skip_cpu)
             except Exception as e:  # reported, never hidden
                 out["world100k"] = {"error": repr(e)}
+            try:
+                out["other_configs"] = bench_other_configs(local_rank)
+            except Exception as e:
+                out["other_configs"] = {"error": repr(e)}
     if rank == 0:
         print(json.dumps(out), flush=True)
     if use_dist:
