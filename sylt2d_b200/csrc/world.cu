@@ -78,6 +78,24 @@ struct Counters {
     unsigned color_mask_int;        // interior colours in use
 };
 
+// ------------------------------------------------------------------ programmatic dependent launch
+// The kernels of a step form one dependent chain of short launches.  Launched with the programmatic-serialization
+// attribute, the next kernel's CTAs may be scheduled while the previous kernel is still draining; pdl_wait() at the top of
+// every kernel is the actual dependency (it returns once the previous kernel has completed and its writes are visible),
+// pdl_trigger() lets the successor start scheduling early.  Without the attribute both are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // ------------------------------------------------------------------ device-wide exclusive scan (single pass, k_scan_lookback)
 constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
@@ -141,6 +159,7 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* ve
                                                  const int* bflags, const float2* lverts, float2* rotc, float4* aabb, int4* cinfo,
                                                  int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
                                                  Counters* cn, ulonglong2* vrec, unsigned long long* used, unsigned* used_int) {
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     used[i] = 0ull;  // colours taken at this body: rebuilt by k_build / the colouring rounds every step
@@ -200,6 +219,8 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* ve
 // contiguous 32-byte entries instead of chasing body indices
 __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, const float4* aabb, const int* rank, const int* cell_start,
                                                     int4* cent_info, float4* cent_aabb, GridParams gp) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     int4 ci = cinfo[i];
@@ -282,6 +303,8 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
 constexpr int ROW_LANES = 4;
 __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
                                                     const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp) {
+    pdl_wait();
+    pdl_trigger();
     const int gi = blockIdx.x * blockDim.x + threadIdx.x;
     const int g = gi / ROW_LANES, sub = gi % ROW_LANES;
     if (g >= B) return;  // (the lanes of a body leave together; the masks below name only those lanes)
@@ -351,6 +374,8 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
 __global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
                                                    const float4* cent_aabb, const int* large, int n_large, GridParams gp, const int* row_start, const int* row_tmp,
                                                    int2* pairs, int cap_pairs, Counters* cn) {
+    pdl_wait();
+    pdl_trigger();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const int base = row_start[i], end = row_start[i + 1], n = end - base;
@@ -387,6 +412,8 @@ template <int MAXC>
 __global__ void __launch_bounds__(128) k_narrow(const Counters* cn, int cap_pairs, const int2* pairs, const float4* pose, const float2* rotc,
                                                 const float4* geom, const int* bflags, const float2* lverts,
                                                 unsigned long long* info, float4* tmp_a, float2* tmp_b, Counters* cnw) {
+    pdl_wait();
+    pdl_trigger();
     int P = min(cn->n_pairs, cap_pairs);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         int2 pr = pairs[p];
@@ -442,6 +469,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
                                                unsigned long long* used, int* uncolored, int fix_features, int keep_colors, unsigned* used_int, int regions) {
+    pdl_wait();
     int P = min(cn->n_pairs, cap_pairs);
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     __shared__ int s_hist[NCX];
@@ -532,6 +560,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, i
     __shared__ T sh[33];
     __shared__ int s_tile;
     __shared__ T s_prefix;
+    pdl_wait();
+    pdl_trigger();
     const int n = n_dev ? min(*n_dev, n_host) : n_host;
     if (threadIdx.x == 0) {
         const int t = atomicAdd(ticket, 1);
@@ -1974,8 +2004,8 @@ int run_scan(SyltWorld* w, T* in, T* out, int n_bound, const int* n_dev, T* agg,
         SYLT_CUDA(cudaMemsetAsync(w->scan_flag.p, 0, w->scan_flag.cap * sizeof(unsigned), w->stream));
         w->scan_epoch = 0;
     }
-    k_scan_lookback<T><<<nb, SCAN_THREADS, 0, w->stream>>>(in, out, n_bound, n_dev, w->scan_flag.p, agg, incl, w->scan_ticket.p, ++w->scan_epoch,
-                                                           zero_in, w->counters.p, totals_mode, (int)w->cap_pairs);
+    SYLT_CUDA(launch_pdl(k_scan_lookback<T>, dim3((unsigned)nb), dim3(SCAN_THREADS), 0, w->stream, in, out, n_bound, n_dev, w->scan_flag.p, agg, incl, w->scan_ticket.p,
+                         ++w->scan_epoch, zero_in, w->counters.p, totals_mode, (int)w->cap_pairs));
     w->launches++;
     SYLT_CUDA(cudaGetLastError());
     return SYLT_OK;
@@ -2257,23 +2287,23 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->launches++;
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
     if (e) return e;
-    k_fill_cells<<<nbB, 256, 0, st>>>(B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp);
+    SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp));
     const int nbR = (B + 127) / 128;
-    k_rows_count<<<(B * ROW_LANES + 127) / 128, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp,
-                                      w->row_count.p, w->row_tmp.p);
+    SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B * ROW_LANES + 127) / 128)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
+                         (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p));
     w->launches += 2;
     e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->sincl32.p, 0, 1);
     if (e) return e;
-    k_rows_emit<<<nbR, 128, 0, st>>>(B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp,
-                                     w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn);
+    SYLT_CUDA(launch_pdl(k_rows_emit, dim3((unsigned)nbR), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1),
+                         w->large.p, w->n_large, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn));
     w->launches += 1;
     const int gridP = w->num_sms * 8;
     if (w->any_poly)
-        k_narrow<MAX_MANIFOLD><<<gridP, 128, 0, st>>>(cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p, w->lverts.p,
-                                                      w->info.p, w->tmp_a.p, w->tmp_b.p, cn);
+        SYLT_CUDA(launch_pdl(k_narrow<MAX_MANIFOLD>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p,
+                             w->bflags.p, w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn));
     else
-        k_narrow<2><<<gridP, 128, 0, st>>>(cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p, w->lverts.p,
-                                           w->info.p, w->tmp_a.p, w->tmp_b.p, cn);
+        SYLT_CUDA(launch_pdl(k_narrow<2>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p,
+                             w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn));
     w->launches++;
     e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->sincl64.p, 0, 2);
     if (e) return e;
@@ -2293,13 +2323,13 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     const int keep_colors = w->recolor_all ? 0 : 1;
     w->recolor_all = false;
     if (w->any_poly)
-        k_build<MAX_MANIFOLD><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p,
-                                                              w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p,
-                                                              w->bflags_old.p, cur, old, w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0);
+        SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
+                             w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
+                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0));
     else
-        k_build<2><<<w->num_sms * 4, 256, 0, st>>>(cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old, w->have_old ? 1 : 0, w->pairs.p, w->info.p,
-                                                   w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur,
-                                                   old, w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0);
+        SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
+                             w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
+                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
 
