@@ -1217,7 +1217,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
 
 // ------------------------------------------------------------------ region solver
 // The same sequential sweep as k_solve — passes x colours ascending — with a different execution plan.
-// Bodies are partitioned into compact spatial regions (host side, `repartition`); region r belongs to CTA r for the
+// Bodies are partitioned into compact spatial regions (k_resort + k_rebalance, every `regions_period` steps); region r belongs to CTA r for the
 // whole solve and its body velocities live in that CTA's shared memory.  Arbiters come in two classes (the colour
 // range IS the class, see color_new_arbiters): interior (colour < GEN_BIT: all dynamic bodies in the owner's region)
 // and generic (cross-region pairs).  Interior arbiters of different regions touch disjoint dynamic bodies, so the
