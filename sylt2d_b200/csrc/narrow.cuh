@@ -123,7 +123,8 @@ SYLT_HD int box_box(V2 pos_a, float ca, float sa, V2 wa, V2 pos_b, float cb, flo
 
 // ------------------------------------------------------------------ polygons
 // ConvexPolygon::get_vertex with its +1 shift (body.rs:19-24, quirk Q-7)
-SYLT_HD V2 pv(const V2* w, int n, int i) { return w[(i + n + 1) % n]; }
+// (callers pass 0 <= i <= n: conditional wraps instead of an integer modulo, the same index)
+SYLT_HD V2 pv(const V2* w, int n, int i) { int k = i + 1; if (k >= n) k -= n; if (k >= n) k -= n; return w[k]; }  // (second wrap: a clipped polygon of one vertex)
 // get_normal (body.rs:34-41): (e.y, -e.x) of edge i
 SYLT_HD V2 pnormal(const V2* w, int n, int i) {
     V2 e = pv(w, n, i + 1) - pv(w, n, i);
@@ -188,16 +189,19 @@ SYLT_HD int poly_poly(const V2* c0, int n0, const V2* c1, int n1, ContactOut* ou
         np = nc;
     }
     // nearest-edge unit normal of c1 for every surviving vertex (collide_polygon.rs:127-149), contacts (:175-192)
+    V2 unit[MAX_POLY_VERTS];  // the unit normal of an edge does not depend on the vertex: once per edge (the reference recomputes it per vertex, same bits)
+    for (int j = 0; j < n1; j++) {
+        V2 e = pv(c1, n1, j + 1) - pv(c1, n1, j);
+        V2 nrm = mk(-e.y, e.x);
+        unit[j] = nrm * (1.0f / len(nrm));
+    }
     for (int k = 0; k < np; k++) {
         V2 vtx = poly[k];
         V2 best = mk(0.0f, 0.0f);
         float md = 3.402823466e+38f;
         for (int j = 0; j < n1; j++) {
-            V2 es = pv(c1, n1, j), ee = pv(c1, n1, j + 1);
-            V2 e = ee - es;
-            V2 nrm = mk(-e.y, e.x);
-            nrm = nrm * (1.0f / len(nrm));
-            float d = fabsf(dot(vtx - es, nrm));
+            V2 nrm = unit[j];
+            float d = fabsf(dot(vtx - pv(c1, n1, j), nrm));
             if (d < md) { md = d; best = nrm; }
         }
         out[k].px = vtx.x; out[k].py = vtx.y; out[k].nx = best.x; out[k].ny = best.y;
