@@ -1720,10 +1720,12 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* p
     __shared__ int s_scan2[34];
     const int lt = threadIdx.x, T = blockDim.x, lane = lt & 31, wid = lt >> 5;
     float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
-    for (int i = lt; i < B; i += T) {
-        const float4 p = pose[i];
+    auto for_bodies = [&](auto&& f) {
+        for (int i = lt; i < B; i += T) f(i, pose[i]);
+    };
+    for_bodies([&](int, float4 p) {
         if (fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f) { x0 = fminf(x0, p.x); x1 = fmaxf(x1, p.x); y0 = fminf(y0, p.y); y1 = fmaxf(y1, p.y); }
-    }
+    });
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
@@ -1741,12 +1743,11 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* p
         for (int k = lt; k < 2048; k += T) s_hist[k] = 0;
         __syncthreads();
         const float sx = 1024.0f / fmaxf(x1 - x0, 1.0e-6f), sy = 1024.0f / fmaxf(y1 - y0, 1.0e-6f);
-        for (int i = lt; i < B; i += T) {
-            const float4 p = pose[i];
-            if (!(fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f)) continue;
+        for_bodies([&](int, float4 p) {
+            if (!(fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f)) return;
             atomicAdd(&s_hist[min(1023, max(0, (int)((p.x - x0) * sx)))], 1);
             atomicAdd(&s_hist[1024 + min(1023, max(0, (int)((p.y - y0) * sy)))], 1);
-        }
+        });
         __syncthreads();
         if (lt < 2) {  // lane 0: x, lane 1: y
             const int* h = s_hist + 1024 * lt;
@@ -1775,11 +1776,11 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* p
         const int cx = min((1 << SORT_BITS) - 1, max(0, (int)((p.x - x0) * inv))), cy = min((1 << SORT_BITS) - 1, max(0, (int)((p.y - y0) * inv)));
         return (int)(morton_spread((unsigned)cx) | (morton_spread((unsigned)cy) << 1));
     };
-    for (int i = lt; i < B; i += T) {
-        const int k = key_of(pose[i]);
+    for_bodies([&](int i, float4 p) {
+        const int k = key_of(p);
         key_tmp[i] = k;
         atomicAdd(&s_hist[k], 1);
-    }
+    });
     __syncthreads();
     {   // exclusive scan of the histogram: s_hist[k] = first position of cell k
         const int per = SORT_CELLS / REBAL_THREADS, q0 = lt * per;
@@ -1813,7 +1814,7 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const
     __shared__ int s_first[1025];
     const int lt = threadIdx.x, T = blockDim.x;
     const int chunk = (B + T - 1) / T, q0 = min(lt * chunk, B), q1 = min(q0 + chunk, B);
-    auto weight = [&](int b) -> long long { return (old_row_start && b < B_old) ? 1 + 2 * max(0, old_row_start[b + 1] - old_row_start[b]) : 1; };
+    auto weight = [&](int b) -> long long { return (old_row_start && b < B_old) ? 1 + 2 * max(0, __ldg(&old_row_start[b + 1]) - __ldg(&old_row_start[b])) : 1; };
     for (int g = lt; g <= G; g += T) s_first[g] = B;
     long long sum = 0;
     for (int i = q0; i < q1; i++) sum += weight(perm[i]);
@@ -1969,6 +1970,8 @@ struct SyltWorld {
     int n_regions = 0;
     int64_t steps_since_part = 0;
     bool resort_pending = false;     // the partition of the current bodies has not been computed yet
+    cudaEvent_t kt_ev[16] = {};      // SYLT_KERNEL_TIMING
+    int kt_n = 0;
     size_t solve_budget = 0;
 
     int64_t cap_pairs = 0, cap_arb = 0, cap_con = 0;
@@ -2274,6 +2277,11 @@ int repartition(SyltWorld* w) {
 int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     const int B = (int)w->hb.size();
     cudaStream_t st = w->stream;
+    // SYLT_KERNEL_TIMING=1: events between the launches of every step (diagnostics; it serialises the launch chain)
+    static const bool ktime = getenv("SYLT_KERNEL_TIMING") && atoi(getenv("SYLT_KERNEL_TIMING"));
+    int kt_n = 0;
+    auto mark = [&]() { if (ktime && kt_n < 16) { if (!w->kt_ev[kt_n]) cudaEventCreate(&w->kt_ev[kt_n]); cudaEventRecord(w->kt_ev[kt_n++], st); } };
+    mark();
     Counters* cn = w->counters.p;
     SYLT_CUDA(cudaMemsetAsync(&cn->n_pairs, 0, sizeof(Counters) - offsetof(Counters, n_pairs), st));
     if (B == 0) return SYLT_OK;
@@ -2285,18 +2293,24 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     k_prepare<<<nbB, 256, 0, st>>>(B, w->pose.p, w->vel.p, w->force.p, w->mp.p, w->geom.p, w->bflags.p, w->lverts.p, w->rotc.p, w->aabb.p,
                                    w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p, w->used.p, w->used_int.p);
     w->launches++;
+    mark();
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
     if (e) return e;
+    mark();
     SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp));
+    mark();
     const int nbR = (B + 127) / 128;
     SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B * ROW_LANES + 127) / 128)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
                          (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p));
     w->launches += 2;
+    mark();
     e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->sincl32.p, 0, 1);
     if (e) return e;
+    mark();
     SYLT_CUDA(launch_pdl(k_rows_emit, dim3((unsigned)nbR), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1),
                          w->large.p, w->n_large, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn));
     w->launches += 1;
+    mark();
     const int gridP = w->num_sms * 8;
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_narrow<MAX_MANIFOLD>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p,
@@ -2305,8 +2319,10 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         SYLT_CUDA(launch_pdl(k_narrow<2>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p,
                              w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn));
     w->launches++;
+    mark();
     e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->sincl64.p, 0, 2);
     if (e) return e;
+    mark();
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
     if (w->regions_on && (w->resort_pending || (full_step && w->steps_since_part >= w->regions_period))) {
         // (re)partition by the current positions and last step's load (device side, no synchronisation); the colours encode the old cut
@@ -2332,6 +2348,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
                              w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
+    mark();
 
     SolveArgs a;
     memset(&a, 0, sizeof a);
@@ -2370,6 +2387,8 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_smem, st));
     }
     w->launches++;
+    mark();
+    w->kt_n = kt_n;
     // the set just built becomes "last step's"
     w->cur ^= 1;
     return SYLT_OK;
@@ -2431,6 +2450,16 @@ int finish(SyltWorld* w) {
         w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
     }
     if (w->timing) print_solver_timing(w);
+    if (w->kt_n > 1) {  // SYLT_KERNEL_TIMING: the last step's launches
+        static const char* names[] = {"prepare", "scan cells", "fill cells", "rows count", "scan rows", "rows emit", "narrow", "scan pairs", "(re-cut +) build", "solve"};
+        fprintf(stderr, "kernels [us]:");
+        for (int k = 1; k < w->kt_n; k++) {
+            float ms = 0.0f;
+            cudaEventElapsedTime(&ms, w->kt_ev[k - 1], w->kt_ev[k]);
+            fprintf(stderr, " %s %.1f", k - 1 < 10 ? names[k - 1] : "?", ms * 1e3f);
+        }
+        fprintf(stderr, "\n");
+    }
     w->last_was_step = w->inflight_full;
     w->last_iterations = w->iterations;
     return w->last.err;
