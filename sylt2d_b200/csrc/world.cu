@@ -294,24 +294,32 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
     }
 }
 
-// Count pass: ROW_LANES lanes per body.  In the usual case (the body's search window is a 3 x 3 block of cells) the nine cells
-// and the large list are dealt to the lanes, so the dependent loads of a row search (bucket range -> entries) of several cells
-// run side by side; the lanes' counts are combined with shuffles and the partners land in row_tmp in lane order (k_rows_emit
-// sorts them anyway).  Anything else (a large body, a wider window) is searched by lane 0 alone.  Bodies are taken in cell
-// order, so neighbouring groups search the same buckets.  (16 lanes are fastest up to ~20k bodies but issue-bound at 100k —
-// 32 M warp instructions —, one lane is latency-bound everywhere; 4 is the compromise.)
-constexpr int ROW_LANES = 4;
+// Count pass: one warp per body, one lane per candidate ENTRY.  In the usual case (the body's search window is a 3 x 3 block of
+// cells) lanes 0..8 fetch the bucket ranges of the nine cells and lane 9 stands for the large list; a prefix over those ten
+// counts numbers all entries of the window, every lane takes entry base + lane (one 32-byte load, one test) and a ballot
+// packs the hits into row_tmp — two dependent memory round trips per body, no per-lane loops, no divergence.  Anything else
+// (a large body, a wider window) is searched by lane 0 alone.  Bodies are taken in cell order, so neighbouring warps search the
+// same buckets.  (Measured at 100k bodies: one thread per body 36 us, 16 lanes with a cell each 49 us — issue-bound, 32 M warp
+// instructions —, 4 lanes 39 us with 40 % of the lanes active.)
 __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
                                                     const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp) {
     pdl_wait();
     pdl_trigger();
-    const int gi = blockIdx.x * blockDim.x + threadIdx.x;
-    const int g = gi / ROW_LANES, sub = gi % ROW_LANES;
-    if (g >= B) return;  // (the lanes of a body leave together; the masks below name only those lanes)
-    const unsigned gmask = ((1u << ROW_LANES) - 1u) << (threadIdx.x & 31 & ~(ROW_LANES - 1));
-    const int i = g < B - n_large ? cent_info[2 * g].x : large[g - (B - n_large)];
-    const float4 my = aabb[i];
-    const int4 ci = cinfo[i];
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (g >= B) return;
+    int i;
+    float4 my;
+    int4 ci;
+    if (g < B - n_large) {  // the cell-ordered entry already carries the body's index, cell, flags and AABB: one load level less
+        const int4 ce = cent_info[2 * g];
+        my = cent_aabb[2 * g];
+        i = ce.x;
+        ci = make_int4(ce.y, ce.z, ce.w, 0);
+    } else {
+        i = large[g - (B - n_large)];
+        my = aabb[i];
+        ci = cinfo[i];
+    }
     const bool st_i = (ci.z & FLAG_STATIC) != 0;
     int* tmp = row_tmp + (size_t)i * ROWTMP;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
@@ -321,54 +329,67 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
         y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell); y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
         fast = x1 - x0 <= 2 && y1 - y0 <= 2;
     }
-    // one walk over this lane's share; `pre` < 0: count only, otherwise write the partners from position `pre` on
-    auto walk = [&](int pre) -> int {
-        int cnt = 0;
-        int k0[3], k1[3];
-#pragma unroll
-        for (int q = 0; q < 3; q++) {  // bucket ranges first (independent loads), then the entries
-            const int cell = sub + q * ROW_LANES, cx = x0 + cell % 3, cy = y0 + cell / 3;
-            const bool ok = cell < 9 && cx <= x1 && cy <= y1;
-            const int h = cell_hash(cx, cy, gp.mask);
-            k0[q] = ok ? cell_start[h] : 0;
-            k1[q] = ok ? cell_start[h + 1] : 0;
+    if (!fast) {  // warp-uniform
+        if (lane == 0) {
+            int cnt = 0;
+            row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) {
+                if (cnt < ROWTMP) tmp[cnt] = j;
+                cnt++;
+            });
+            row_count[i] = cnt;
         }
+        return;
+    }
+    // segments: lanes 0..8 = the cells of the window, lane 9 = the large list
+    int seg_k0 = 0, seg_n = 0;
+    const int cx = x0 + lane % 3, cy = y0 + lane / 3;
+    if (lane < 9) {
+        if (cx <= x1 && cy <= y1) {
+            const int h = cell_hash(cx, cy, gp.mask);
+            seg_k0 = cell_start[h];
+            seg_n = cell_start[h + 1] - seg_k0;
+        }
+    } else if (lane == 9) {
+        seg_n = n_large;
+    }
+    int seg_end = seg_n;  // inclusive prefix
 #pragma unroll
-        for (int q = 0; q < 3; q++) {
-            const int cell = sub + q * ROW_LANES, cx = x0 + cell % 3, cy = y0 + cell / 3;
-            for (int k = k0[q]; k < k1[q]; k++) {
+    for (int o = 1; o < 16; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, seg_end, o);
+        if (lane >= o) seg_end += u;
+    }
+    const int total = __shfl_sync(0xffffffffu, seg_end, 9);
+    int found = 0;
+    for (int base = 0; base < total; base += 32) {
+        const int e = base + lane;
+        int seg = 0;  // the segment entry e belongs to: the number of segments that end at or before e
+#pragma unroll
+        for (int q = 0; q < 9; q++) seg += e >= __shfl_sync(0xffffffffu, seg_end, q);
+        const int s_end = __shfl_sync(0xffffffffu, seg_end, seg), s_n = __shfl_sync(0xffffffffu, seg_n, seg), s_k0 = __shfl_sync(0xffffffffu, seg_k0, seg);
+        bool hit = false;
+        int partner = 0;
+        if (e < total) {
+            const int off = e - (s_end - s_n);
+            if (seg < 9) {
+                const int k = s_k0 + off;
                 const int4 cj = cent_info[2 * k];
                 const float4 ab = cent_aabb[2 * k];
-                if (cj.x <= i || cj.y != cx || cj.z != cy) continue;  // lower index owns the pair; another cell may share the bucket
-                if (st_i && (cj.w & FLAG_STATIC)) continue;
-                if (aabb_overlap(my, ab)) { if (pre >= 0 && pre + cnt < ROWTMP) tmp[pre + cnt] = cj.x; cnt++; }
+                const int scx = x0 + seg % 3, scy = y0 + seg / 3;
+                // lower index owns the pair; another cell may share the bucket; static-static pairs are skipped (world.rs:79-81)
+                hit = cj.x > i && cj.y == scx && cj.z == scy && !(st_i && (cj.w & FLAG_STATIC)) && aabb_overlap(my, ab);
+                partner = cj.x;
+            } else {
+                const int j = large[off];
+                hit = !(st_i && (cinfo[j].z & FLAG_STATIC)) && aabb_overlap(my, aabb[j]);
+                partner = j;
             }
         }
-        if (sub == ROW_LANES - 1)
-            for (int k = 0; k < n_large; k++) {
-                const int j = large[k];
-                if (st_i && (cinfo[j].z & FLAG_STATIC)) continue;
-                if (aabb_overlap(my, aabb[j])) { if (pre >= 0 && pre + cnt < ROWTMP) tmp[pre + cnt] = j; cnt++; }
-            }
-        return cnt;
-    };
-    int cnt = 0;
-    if (fast) cnt = walk(-1);
-    else if (sub == 0)
-        row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) {
-            if (cnt < ROWTMP) tmp[cnt] = j;
-            cnt++;
-        });
-    int pre = cnt;  // inclusive prefix over the lanes of the body
-#pragma unroll
-    for (int o = 1; o < ROW_LANES; o <<= 1) {
-        const int u = __shfl_up_sync(gmask, pre, o, ROW_LANES);
-        if (sub >= o) pre += u;
+        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const int pos = found + __popc(m & ((1u << lane) - 1u));
+        if (hit && pos < ROWTMP) tmp[pos] = partner;
+        found += __popc(m);
     }
-    const int total = __shfl_sync(gmask, pre, ROW_LANES - 1, ROW_LANES);
-    pre -= cnt;
-    if (fast && cnt > 0 && pre < ROWTMP) walk(pre);  // second walk over the (now cached) entries: write the partners
-    if (sub == 0) row_count[i] = total;
+    if (lane == 0) row_count[i] = found;
 }
 
 __global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
@@ -2300,7 +2321,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp));
     mark();
     const int nbR = (B + 127) / 128;
-    SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B * ROW_LANES + 127) / 128)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
+    SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B + 3) / 4)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
                          (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p));
     w->launches += 2;
     mark();
