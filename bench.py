@@ -6,19 +6,27 @@ dt = 1/60, 10 iterations, warm-starting on), sharded over the ranks in contiguou
 communication (strong scaling: the 32768 worlds are split over N GPUs).  A "step" is one World::step of every world
 the job owns.  Worlds are first settled (untimed, stated in config.settle_steps) so the timed steps run at the steady
 contact count; then W warm-up steps and exactly K timed steps, barrier + synchronize on both sides, device time by
-CUDA events on the launching stream, max over ranks.
+CUDA events on the launching stream, max over ranks.  The timed region is repeated REPEATS = 5 times and the MEDIAN
+run is reported (`ms_per_step_runs` lists all five).
 
   value  : device-resident throughput (state stays in HBM; sylt_batch_step_n(dt, K): one k_batch_step launch runs the K
-           steps, each world staying in shared memory across them)
+           steps, each world staying in shared memory across them); `value_per_step_launch`: the same K steps as K launches
   e2e    : the same metric through the C ABI with HOST buffers: every step uploads all body states from pinned host
-           memory, steps, and reads all body states back (sylt_batch_step_host)
-  roofline: algorithmic bytes of SURVEY.md §8(d)  (116 B + 56 P + 152 C + 144 J + I (120 C + 124 J)) per launch
-           over the kernel's average launch duration, against the measured HBM copy peak (MEASURED_PEAKS.json)
+           memory, steps, and reads all body states back (sylt_batch_step_host6)
+  roofline: the bound of k_batch_step is INSTRUCTION ISSUE (its worlds live in shared memory; DRAM carries < 1 % of the
+           peak): achieved = warp-instructions per second (per-world-step count from the committed ncu capture named in
+           the line x worlds x steps / the launch duration measured here), peak = SMs x 4 schedulers x SM clock.
+           `hbm_effective` keeps the SURVEY.md §8(d) algorithmic-byte figure (116 B + 56 P + 152 C + 144 J + I (120 C + 124 J))
+           over the measured HBM copy peak — an effective bandwidth served on-chip, NOT a bound — and `dram` the actual
+           DRAM traffic fraction.
   cpu_baseline: the CPU oracle (C++ restatement of the Rust reference; the reference itself cannot be built here)
            on all host cores, one world per thread, on a bounded sample of the same worlds
 
 `--impl reference` times that CPU path alone (the reference arm).  At N=1 the line also carries `world100k`:
-ms/step of the single 100k-body world (BASELINE.json config 3), which does not shard ("replicas only").
+ms/step of the single 100k-body world (BASELINE.json config 3), which does not shard ("replicas only"), incl. its
+end-to-end cost with host read-back, and `other_configs` (configs 2 and 4).
+`--config 4` runs BASELINE.json config 4 instead (4096 bridge + 4096 multi-pendulum worlds, `--iterations` 10 or 100)
+under the same contract, so that its 1/2/4/8-GPU curve can be recorded too.
 """
 import argparse
 import json
@@ -39,14 +47,24 @@ ROWS = 20
 ITER = 10
 METRIC = "body_steps_per_sec"
 UNIT = "body-steps/s"
+REPEATS = 5
+FPB = 6  # x, y, rotation, vx, vy, angular_velocity: the 24 bytes per body a caller mirrors every step
+COUNTERS = os.path.join("profiles", "batch_step_counters.json")  # ncu counters of k_batch_step (tools/profiling/run_r04_prof.sh)
+
+
+def workload_name(config, worlds):
+    if config == 4:
+        return f"{worlds // 2} bridge + {worlds // 2} multi-pendulum joint worlds (BASELINE.json config 4)"
+    return f"{worlds} independent pyramid{ROWS} worlds (BASELINE.json config 5)"
 
 
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
         with open(p) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
-    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+            j = json.load(f)
+        return float(j["hbm_gbs"]), float(j.get("sm_max_mhz", 1965.0)), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, 1965.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
 class ClockSampler:
@@ -82,30 +100,51 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][1]), "reasons": reasons, "samples": len(rows)}
 
 
-def settled_oracle_worlds(scene, n, threads, settle):
+# ---------------------------------------------------------------------------------------------------- workloads
+def job_parts(config, worlds, iterations):
+    """The kinds of worlds a job consists of: [(scene, n_worlds, tile kwargs)]."""
+    from sylt2d_b200 import scenes
+    if config == 4:
+        half = worlds // 2
+        return [(scenes.bridge(iterations), half, dict(seed=5, omega_jitter=0.0)),
+                (scenes.multi_pendulum(iterations), half, dict(seed=5, omega_jitter=1.0))]
+    return [(scenes.pyramid(ROWS, iterations), worlds, dict(seed=0, x_jitter=0.01))]
+
+
+def shard_of(scene, n, kw, rank, world_size):
+    """This rank's contiguous block of the n tiled worlds (CSR arrays re-based to the shard)."""
+    from sylt2d_b200 import scenes, shard_range
+    lo, hi = shard_range(n, rank, world_size)
+    bodies, boff, joints, joff = scenes.tile_worlds(scene, n, **kw)
+    nb, nj = scene.num_bodies, int(scene.joints.shape[0])
+    return bodies[lo * nb:hi * nb], boff[lo:hi + 1] - boff[lo], joints[lo * nj:hi * nj], joff[lo:hi + 1] - joff[lo], hi - lo
+
+
+# ---------------------------------------------------------------------------------------------------- CPU (oracle) timing
+def oracle_worlds(scene, n, kw):
     from oracle import orc
     from sylt2d_b200 import scenes
-    bodies, boff, joints, joff = scenes.tile_worlds(scene, n, seed=0, x_jitter=0.01)
+    bodies, boff, joints, joff = scenes.tile_worlds(scene, n, **kw)
     nb = scene.num_bodies
     ws = []
     for k in range(n):
         w = orc.OracleWorld(scene.gravity, scene.iterations, sincos_mode=0, broadphase=0)  # faithful: libm trig, all-pairs broad phase
         w.load_scene(scenes.Scene(scene.name, bodies[k * nb:(k + 1) * nb], scene.joints, scene.verts, scene.gravity, scene.iterations, scene.dt, scene.ctx))
         ws.append(w)
-    if settle:
-        orc.step_worlds_mt(ws, scene.dt, settle, threads)
     return ws
 
 
-def cpu_time_sample(scene, n, steps, threads, settle, states=None):
+def cpu_time_sample(scene, kw, n, steps, threads, settle, states=None):
     """body-steps/s of the CPU oracle: n worlds x steps, worlds spread over `threads` host threads."""
     from oracle import orc
-    ws = settled_oracle_worlds(scene, n, threads, 0 if states is not None else settle)
+    ws = oracle_worlds(scene, n, kw)
     if states is not None:
         nb = scene.num_bodies
         for k, w in enumerate(ws):
             w.set_bodies(states[k * nb:(k + 1) * nb])
         orc.step_worlds_mt(ws, scene.dt, 5, threads)
+    elif settle:
+        orc.step_worlds_mt(ws, scene.dt, settle, threads)
     t0 = time.perf_counter()
     orc.step_worlds_mt(ws, scene.dt, steps, threads)
     dt = time.perf_counter() - t0
@@ -117,30 +156,60 @@ def reference_arm(args, rank):
     if rank != 0:
         return
     from oracle import orc
-    from sylt2d_b200 import scenes
     orc.build()
-    scene = scenes.pyramid(ROWS, ITER)
     cores = os.cpu_count() or 1
-    n = max(cores * 8, 64)
-    ws = settled_oracle_worlds(scene, n, cores, args.settle)
-    per = 25  # world-steps per world per bench "step" (a bounded sample: ~0.2 s of all-core CPU work per step)
+    parts = job_parts(args.config, args.worlds, args.iterations)
+    n_each = max(cores * 8 // len(parts), 64 // len(parts))
+    ws, bodies_total, dt = [], 0, parts[0][0].dt
+    for scene, _, kw in parts:
+        w = oracle_worlds(scene, n_each, kw)
+        ws += w
+        bodies_total += n_each * scene.num_bodies
+    if args.settle:
+        orc.step_worlds_mt(ws, dt, args.settle, cores)
+    per = 25 if args.iterations <= 10 else 5  # world-steps per world per bench "step" (a bounded sample: ~0.2 s of all-core CPU work per step)
     for _ in range(args.warmup):
-        orc.step_worlds_mt(ws, scene.dt, per, cores)
+        orc.step_worlds_mt(ws, dt, per, cores)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.step_worlds_mt(ws, scene.dt, per, cores)
+        orc.step_worlds_mt(ws, dt, per, cores)
     el = time.perf_counter() - t0
-    v = n * scene.num_bodies * per * args.steps / el
-    sample = f"{n} of {N_WORLDS} pyramid{ROWS} worlds x {per} world-steps per step, one world per host thread"
+    v = bodies_total * per * args.steps / el
+    sample = f"{len(ws)} of the {args.worlds} worlds x {per} world-steps per step, one world per host thread"
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": el / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{N_WORLDS} independent pyramid{ROWS} worlds (BASELINE.json config 5), CPU sample", "bodies_per_world": scene.num_bodies,
-                   "iterations": ITER, "dt": scene.dt, "settle_steps": args.settle},
+        "config": {"workload": workload_name(args.config, args.worlds), "bodies_per_world": [p[0].num_bodies for p in parts],
+                   "iterations": args.iterations, "dt": dt, "warm_starting": True, "settle_steps": args.settle,
+                   "implementation": "CPU sample: C++ restatement of the Rust reference (no Rust toolchain here), all-pairs broad phase, libm trig"},
         "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0}), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------- single 100k-body world
+def cpu_allpairs_fit(sc, st, B_target):
+    """the reference's all-pairs step (src/world.rs:74-77) timed on the first n bodies of the settled state
+    for n in {1k, 2k, 5k, 10k, 20k}, one thread; least-squares fit t = a n^2 + b n, extrapolated to the full world."""
+    from oracle import orc
+    from sylt2d_b200 import scenes
+    ns, ts = [1000, 2000, 5000, 10000, 20000], []
+    for n in ns:
+        sub = scenes.Scene(sc.name, sc.bodies[:n], sc.joints, sc.verts, sc.gravity, sc.iterations, sc.dt, sc.ctx)
+        o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=0, broadphase=0)
+        o.load_scene(sub)
+        o.set_bodies(st[:n])
+        o.step(sc.dt)  # builds the arbiters
+        reps = 3 if n <= 5000 else 1
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            o.step(sc.dt)
+        ts.append((time.perf_counter() - t0) / reps * 1e3)
+    A = np.stack([np.square(ns, dtype=np.float64), np.asarray(ns, dtype=np.float64)], axis=1)
+    (a, b), *_ = np.linalg.lstsq(A / np.asarray(ts)[:, None], np.ones(len(ns)), rcond=None)  # relative-error least squares
+    return {"n": ns, "ms_per_step": ts, "fit_a_ms_per_n2": float(a), "fit_b_ms_per_n": float(b),
+            "extrapolated_ms_per_step": float(a * B_target ** 2 + b * B_target)}
 
 
 def bench_world100k(device, steps, cpu=True):
@@ -157,26 +226,44 @@ def bench_world100k(device, steps, cpu=True):
     w.sync()
     out["falling_ms_per_step"] = ms / 55
     w.step_n(sc.dt, 540)
+    runs = []
     l0 = w.launch_count
-    w.timer_start()
-    w.step_n_async(sc.dt, steps)
-    ms = w.timer_stop()
-    w.sync()
+    for _ in range(REPEATS):
+        w.timer_start()
+        w.step_n_async(sc.dt, steps)
+        runs.append(w.timer_stop() / steps)
+        w.sync()
+    ms_step = float(np.median(runs))
     st = w.get_stats()
-    out["settled_ms_per_step"] = ms / steps
-    out["launches_per_step"] = (w.launch_count - l0) / steps
+    out["settled_ms_per_step"] = ms_step
+    out["settled_ms_per_step_runs"] = runs
+    out["launches_per_step"] = (w.launch_count - l0) / (steps * REPEATS)
     out["stats"] = st
     B, P, C, J = st["bodies"], st["candidate_pairs"], st["contacts"], st["joints"]
     by = 116 * B + 56 * P + 152 * C + 144 * J + ITER * (120 * C + 124 * J)
-    peak, _ = peaks()
+    peak, _, _ = peaks()
     out["algorithmic_bytes_per_step"] = by
-    out["roofline_frac_whole_step"] = by / (ms / steps * 1e-3) / 1e9 / peak
+    out["roofline_frac_whole_step"] = by / (ms_step * 1e-3) / 1e9 / peak
     out["solver_bytes_per_step"] = ITER * 120 * C
-    out["body_steps_per_sec"] = B * steps / (ms * 1e-3)
+    out["body_steps_per_sec"] = B / (ms_step * 1e-3)
+    # end to end: what a caller of World::step pays when it mirrors the world on the host after every step
+    t0 = time.perf_counter()
+    for _ in range(20):
+        w.step(sc.dt)
+        w.get_bodies()
+    out["e2e_ms_per_step_with_get_bodies"] = (time.perf_counter() - t0) / 20 * 1e3
+    t0 = time.perf_counter()
+    for _ in range(5):
+        w.step(sc.dt)
+        w.get_bodies()
+        w.get_arbiters()
+    out["e2e_ms_per_step_with_get_bodies_and_arbiters"] = (time.perf_counter() - t0) / 5 * 1e3
     if cpu:
         # CPU reference path on the same settled state, single thread (the reference is single-threaded):
-        #  * algorithm-matched: oracle with a uniform-grid candidate search (same arbiter set as all-pairs, tests/test_oracle_kat.py)
-        #  * faithful all-pairs (src/world.rs:74-77) is O(n^2): timed on the first n bodies for small n and extrapolated with t = a n^2
+        #  * algorithm-matched: the oracle with a uniform-grid candidate search.  That mode is NOT the reference's algorithm; it is
+        #    checked to produce the same arbiter set as all-pairs on 600-body scenes (tests/test_oracle_kat.py), and the speed-up
+        #    quoted against it rests on that restatement.
+        #  * faithful all-pairs (src/world.rs:74-77) is O(n^2): fit over n in {1k..20k}, extrapolated
         from oracle import orc
         st = w.get_bodies()
         o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=0, broadphase=1)
@@ -188,26 +275,17 @@ def bench_world100k(device, steps, cpu=True):
             o.step(sc.dt)
         cpu_ms = (time.perf_counter() - t0) / 3 * 1e3
         out["cpu_grid_ms_per_step_1thread"] = cpu_ms
-        out["speedup_vs_cpu_grid_1thread"] = cpu_ms / (ms / steps)
-        n_small = 4000
-        import numpy as _np
-        sub = scenes.Scene(sc.name, sc.bodies[:n_small], sc.joints, sc.verts, sc.gravity, sc.iterations, sc.dt, sc.ctx)
-        o2 = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=0, broadphase=0)
-        o2.load_scene(sub)
-        o2.set_bodies(st[:n_small])
-        o2.step(sc.dt)
-        t0 = time.perf_counter()
-        o2.step(sc.dt)
-        t_small = (time.perf_counter() - t0) * 1e3
-        out["cpu_allpairs_ms_per_step_1thread_n4000"] = t_small
-        out["cpu_allpairs_ms_per_step_1thread_extrapolated_100k"] = t_small * (B / n_small) ** 2
-        out["speedup_vs_cpu_allpairs_extrapolated"] = out["cpu_allpairs_ms_per_step_1thread_extrapolated_100k"] / (ms / steps)
+        out["speedup_vs_cpu_grid_1thread"] = cpu_ms / ms_step
+        out["cpu_grid_note"] = "oracle with a grid candidate search (not the reference's all-pairs loop; same arbiter set, tests/test_oracle_kat.py)"
+        fit = cpu_allpairs_fit(sc, st, B)
+        out["cpu_allpairs_fit_1thread"] = fit
+        out["speedup_vs_cpu_allpairs_extrapolated"] = fit["extrapolated_ms_per_step"] / ms_step
     return out
 
 
 def bench_other_configs(device):
     """BASELINE.json configs 2 and 4 (parity-test cases, timed here for reference; single GPU):
-    ms/step of the 10k mixed box + polygon pile, body-steps/s of 8192 joint worlds (4096 bridges + 4096 multi-pendulums)."""
+    ms/step of the 10k mixed box + polygon pile; body-steps/s of the joint worlds at I = 10 and I = 100."""
     from sylt2d_b200 import World, Batch, scenes
     out = {}
     sc = scenes.mixed_pile(10000, seed=1234, iterations=ITER)
@@ -219,31 +297,37 @@ def bench_other_configs(device):
     ms = w.timer_stop()
     w.sync()
     out["mixed_pile_10k"] = {"ms_per_step": ms / 100, "stats": w.get_stats()}
-    for name, scene, jit in (("bridge", scenes.bridge(ITER), 0.0), ("multi_pendulum", scenes.multi_pendulum(ITER), 1.0)):
-        n = 4096
-        bodies, boff, joints, joff = scenes.tile_worlds(scene, n, seed=5, omega_jitter=jit)
-        b = Batch(bodies, boff, joints, joff, scene.gravity, scene.iterations, device=device, ctx=scene.ctx)
-        b.step_n(scene.dt, 50)
-        b.timer_start()
-        b.step_n_async(scene.dt, 100)
-        ms = b.timer_stop()
-        b.sync()
-        out[f"joint_worlds_{name}_4096"] = {"ms_per_step": ms / 100, "bodies_per_world": scene.num_bodies, "joints_per_world": int(scene.joints.shape[0]),
-                                            "body_steps_per_sec": n * scene.num_bodies * 100 / (ms * 1e-3)}
+    for it in (10, 100):
+        for name, scene, jit in (("bridge", scenes.bridge(it), 0.0), ("multi_pendulum", scenes.multi_pendulum(it), 1.0)):
+            n = 4096
+            bodies, boff, joints, joff = scenes.tile_worlds(scene, n, seed=5, omega_jitter=jit)
+            b = Batch(bodies, boff, joints, joff, scene.gravity, scene.iterations, device=device, ctx=scene.ctx)
+            b.step_n(scene.dt, 50)
+            b.timer_start()
+            b.step_n_async(scene.dt, 100)
+            ms = b.timer_stop()
+            b.sync()
+            out[f"joint_worlds_{name}_4096_I{it}"] = {"ms_per_step": ms / 100, "bodies_per_world": scene.num_bodies, "joints_per_world": int(scene.joints.shape[0]),
+                                                       "iterations": it, "body_steps_per_sec": n * scene.num_bodies * 100 / (ms * 1e-3)}
     return out
 
 
+# ---------------------------------------------------------------------------------------------------- main arm
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--worlds", type=int, default=N_WORLDS)
+    ap.add_argument("--config", type=int, default=5, choices=[4, 5])
+    ap.add_argument("--iterations", type=int, default=ITER)
+    ap.add_argument("--worlds", type=int, default=None)
     ap.add_argument("--settle", type=int, default=150)
     ap.add_argument("--skip-world100k", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
     args = ap.parse_args()
+    if args.worlds is None:
+        args.worlds = N_WORLDS if args.config == 5 else 8192
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
@@ -253,7 +337,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from sylt2d_b200 import Batch, scenes, shard_range
+    from sylt2d_b200 import Batch
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
@@ -268,146 +352,174 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    scene = scenes.pyramid(ROWS, ITER)
-    nb = scene.num_bodies
-    lo, hi = shard_range(args.worlds, rank, world_size)
-    bodies, boff, joints, joff = scenes.tile_worlds(scene, args.worlds, seed=0, x_jitter=0.01)
-    bodies = bodies[lo * nb:hi * nb]
-    boff = boff[lo:hi + 1] - boff[lo]
-    joff = joff[lo:hi + 1] - joff[lo]
-    batch = Batch(bodies, boff, joints[:0], joff, scene.gravity, scene.iterations, device=local_rank, ctx=scene.ctx)
-    my_worlds = hi - lo
-    my_bodies = my_worlds * nb
-    batch.step_n(scene.dt, args.settle)  # untimed: reach the steady contact count
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if use_dist:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    parts = job_parts(args.config, args.worlds, args.iterations)
+    dt = parts[0][0].dt
+    batches, my_bodies, total_bodies, my_worlds = [], 0, 0, 0
+    for scene, n, kw in parts:
+        bodies, boff, joints, joff, mine = shard_of(scene, n, kw, rank, world_size)
+        batches.append((Batch(bodies, boff, joints, joff, scene.gravity, scene.iterations, device=local_rank, ctx=scene.ctx), scene, mine))
+        my_bodies += mine * scene.num_bodies
+        total_bodies += n * scene.num_bodies
+        my_worlds += mine
+    for b, scene, _ in batches:
+        b.step_n(dt, args.settle)  # untimed: reach the steady contact count
     for _ in range(args.warmup):
-        batch.step_n(scene.dt, 1)
+        for b, _, _ in batches:
+            b.step_n(dt, 1)
+
+    def timed(steps_per_launch, launches):
+        """Device time [ms] of launches x steps_per_launch steps of every batch of this rank (CUDA events on the launching stream)."""
+        barrier()
+        ms = 0.0
+        for b, _, _ in batches:  # (config 4: the bridge shard, then the pendulum shard)
+            b.timer_start()
+            for _ in range(launches):
+                b.step_n_async(dt, steps_per_launch)
+            ms += b.timer_stop()
+        barrier()
+        return max_over_ranks(ms)
+
     sampler = ClockSampler(local_rank) if rank == 0 else None
     time.sleep(0.25)
-    l0 = batch.launch_count
-    barrier()
+    l0 = sum(b.launch_count for b, _, _ in batches)
     t0 = time.time()
-    batch.timer_start()
-    batch.step_n_async(scene.dt, args.steps)  # ONE launch runs the K steps: a world stays in shared memory across them
-    ms = batch.timer_stop()
-    barrier()
+    runs = [timed(args.steps, 1) for _ in range(REPEATS)]  # ONE launch runs the K steps: a world stays in shared memory across them
     t1 = time.time()
-    launches = batch.launch_count - l0
+    launches = (sum(b.launch_count for b, _, _ in batches) - l0) // REPEATS
     clocks = sampler.stop(t0, t1) if sampler else None
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    if use_dist:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_max = float(t.item())
-    total_bodies = args.worlds * nb
-    value = total_bodies * args.steps / (ms_max * 1e-3)
-    st = batch.stats()
+    ms_med = float(np.median(runs))
+    value = total_bodies * args.steps / (ms_med * 1e-3)
+    ms_single = float(np.median([timed(1, args.steps) for _ in range(3)]))  # the same K steps as K launches of one step
+    stats = [b.stats() for b, _, _ in batches]
 
-    # ---- e2e: host buffers in, host buffers out, every step (pinned memory; the C ABI does one DMA each way)
-    FPB = 6  # x, y, rotation, vx, vy, angular_velocity: the 24 bytes per body a caller mirrors every step
-    host_in = torch.empty(my_bodies * FPB, dtype=torch.float32, pin_memory=True)
-    host_out = torch.empty(my_bodies * FPB, dtype=torch.float32, pin_memory=True)
-    st0 = batch.get_bodies()
-    hin = host_in.numpy().reshape(my_bodies, FPB)
-    for k, f in enumerate(("x", "y", "rotation", "vx", "vy", "angular_velocity")):
-        hin[:, k] = st0[f]
-    L, h = batch.L, batch.h
+    # ---- e2e: host buffers in, host buffers out, every step (pinned memory; world chunks pipelined inside the C ABI)
     import ctypes as C
-    pin, pout = C.c_void_p(host_in.data_ptr()), C.c_void_p(host_out.data_ptr())
-
-    bufs = [pin, pout]
+    e2e_bufs = []
+    for b, scene, mine in batches:
+        n = mine * scene.num_bodies
+        hin = torch.empty(n * FPB, dtype=torch.float32, pin_memory=True)
+        hout = torch.empty(n * FPB, dtype=torch.float32, pin_memory=True)
+        st0 = b.get_bodies()
+        h2 = hin.numpy().reshape(n, FPB)
+        for k, f in enumerate(("x", "y", "rotation", "vx", "vy", "angular_velocity")):
+            h2[:, k] = st0[f]
+        e2e_bufs.append([b, [C.c_void_p(hin.data_ptr()), C.c_void_p(hout.data_ptr())], (hin, hout)])
 
     def e2e_step():
         # the caller's state for the next step is the result of this one: the two pinned buffers alternate roles
-        assert L.sylt_batch_step_host6(h, scene.dt, 1, bufs[0], bufs[1]) == 0
-        bufs.reverse()
+        for ent in e2e_bufs:
+            b, bufs = ent[0], ent[1]
+            assert b.L.sylt_batch_step_host6(b.h, dt, 1, bufs[0], bufs[1]) == 0
+            bufs.reverse()
 
     for _ in range(3):
         e2e_step()
-    barrier()
-    tw0 = time.perf_counter()
     e2e_steps = max(3, min(args.steps, 10))
-    for _ in range(e2e_steps):
-        e2e_step()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - tw0  # host-side wall time: the copies are synchronous C-ABI calls on the library's stream
-    barrier()
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if use_dist:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = total_bodies * e2e_steps / float(te.item())
+    e2e_runs = []
+    for _ in range(3):
+        barrier()
+        tw0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            e2e_step()
+        torch.cuda.synchronize()
+        e2e_s = time.perf_counter() - tw0  # host-side wall time: the C-ABI call returns when the last D2H copy has landed
+        barrier()
+        e2e_runs.append(max_over_ranks(e2e_s))
+    e2e_value = total_bodies * e2e_steps / float(np.median(e2e_runs))
 
     # ---- whole-job stats: the only cross-GPU reduction of the run (<= 64 bytes per rank)
-    red = torch.tensor([st["contacts"], st["errors"], st["kinetic_energy"], st["body_steps"]], dtype=torch.float64, device="cuda")
-    mx = torch.tensor([st["max_penetration"]], dtype=torch.float64, device="cuda")
+    red = torch.tensor([sum(s["contacts"] for s in stats), sum(s["errors"] for s in stats), sum(s["kinetic_energy"] for s in stats),
+                        sum(s["body_steps"] for s in stats)], dtype=torch.float64, device="cuda")
+    mx = torch.tensor([max(s["max_penetration"] for s in stats)], dtype=torch.float64, device="cuda")
     if use_dist:
         dist.all_reduce(red, op=dist.ReduceOp.SUM)
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     contacts_total, errors_total = int(red[0].item()), int(red[1].item())
 
-    # ---- roofline of the dominant kernel (k_batch_step, one launch per step)
-    peak, peak_src = peaks()
-    arb = batch.get_arbiters(0)[0]
-    C_w = st["contacts"] / max(my_worlds, 1)
-    P_w = float(arb.shape[0]) if arb.shape[0] else C_w / 2  # candidate slots ~ arbiters in a settled pyramid
-    bytes_world = 116 * nb + 56 * P_w + 152 * C_w + ITER * 120 * C_w
-    bytes_launch = bytes_world * my_worlds
-    bytes_launch *= args.steps  # the one launch of the timed region covers K steps
-    achieved = bytes_launch / (ms * 1e-3) / 1e9
-    roof = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-            "kernel": "k_batch_step", "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_launch,
-            "note": "effective bandwidth: worlds are shared-memory resident for the whole step, so the algorithmic bytes of SURVEY.md 8(d) "
-                    "are served on-chip; DRAM traffic per launch is in profiles/ (ncu)"}
-    tp = os.path.join(ROOT, "profiles", "batch_step_traffic.json")
-    if os.path.exists(tp):
+    # ---- roofline of the dominant kernel (k_batch_step; the timed launch covers K steps of this rank's worlds)
+    peak, sm_mhz_max, peak_src = peaks()
+    ms_rank = ms_med  # max over ranks; every rank runs the same number of worlds
+    bytes_launch = 0.0
+    for (b, scene, mine), s in zip(batches, stats):
+        arb = b.get_arbiters(0)[0]
+        C_w = s["contacts"] / max(mine, 1)
+        J_w = int(scene.joints.shape[0])
+        P_w = float(arb.shape[0]) if arb.shape[0] else C_w / 2  # candidate slots ~ arbiters in a settled world
+        it = scene.iterations
+        bytes_launch += (116 * scene.num_bodies + 56 * P_w + 152 * C_w + 144 * J_w + it * (120 * C_w + 124 * J_w)) * mine * args.steps
+    eff = bytes_launch / (ms_rank * 1e-3) / 1e9
+    roof = {"kernel": "k_batch_step", "bound": "issue", "unit": "Gwarp-inst/s", "achieved": None, "peak": None, "frac": None, "traffic": None,
+            "hbm_effective": {"achieved": eff, "peak": peak, "unit": "GB/s", "frac": eff / peak, "algorithmic_bytes_per_launch": bytes_launch,
+                              "peak_source": peak_src,
+                              "note": "SURVEY.md 8(d) algorithmic bytes over the launch time: an EFFECTIVE bandwidth (the worlds are shared-memory "
+                                      "resident, the bytes are served on-chip), not a bound — it may exceed 1"},
+            "note": "k_batch_step is bound by instruction issue (and the shared-memory pipe), not by HBM: frac = warp-instructions issued per "
+                    "second / (SMs x 4 schedulers x max SM clock); instruction count per world-step from the committed ncu capture, launch time measured here"}
+    cp = os.path.join(ROOT, COUNTERS)
+    if os.path.exists(cp) and args.config == 5 and args.iterations == ITER:
         try:
-            with open(tp) as f:
-                tj = json.load(f)
-            roof["traffic"] = (tj.get("dram_bytes_per_world_base", 0) + tj.get("dram_bytes_per_world_per_step", 0) * args.steps) * my_worlds
-        except Exception:
-            pass
-    # what actually limits the kernel is on-chip: quote the ncu utilisations of the committed capture beside the HBM figure
-    sp = os.path.join(ROOT, "profiles", "r02_ncu_full_summary.json")
-    if os.path.exists(sp):
-        try:
-            with open(sp) as f:
-                sj = json.load(f)
-            kb = next(v for k, v in sj.items() if k.startswith("k_batch_step"))
-            roof["on_chip"] = {"issue_slots_busy_pct": float(kb["smsp__issue_active.avg.pct_of_peak_sustained_active"][0]),
-                               "shared_memory_pipe_busy_pct": float(kb["l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"][0]),
-                               "source": "profiles/r02_ncu_full_summary.json (ncu --set full, 4096 worlds x 4 steps)"}
-        except Exception:
-            pass
+            with open(cp) as f:
+                cj = json.load(f)
+            sms = torch.cuda.get_device_properties(local_rank).multi_processor_count
+            inst = float(cj["warp_instructions_per_world_step"]) * my_worlds * args.steps
+            ach = inst / (ms_rank * 1e-3) / 1e9
+            pk = sms * 4 * sm_mhz_max * 1e6 / 1e9
+            roof.update({"achieved": ach, "peak": pk, "frac": ach / pk, "warp_instructions_per_world_step": cj["warp_instructions_per_world_step"],
+                         "counters_source": cj.get("source"), "sms": sms, "sm_clock_mhz_peak": sm_mhz_max})
+            tr = (cj.get("dram_bytes_per_world_base", 0) + cj.get("dram_bytes_per_world_per_step", 0) * args.steps) * my_worlds
+            roof["traffic"] = tr
+            roof["dram"] = {"bytes_per_launch": tr, "achieved": tr / (ms_rank * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
+                            "frac": tr / (ms_rank * 1e-3) / 1e9 / peak}
+            roof["shared_memory_pipe_busy_pct_ncu"] = cj.get("shared_memory_pipe_busy_pct")
+            roof["issue_slots_busy_pct_ncu"] = cj.get("issue_slots_busy_pct")
+        except Exception as e:
+            roof["counters_error"] = repr(e)
 
     out = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world_size, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_max / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+        "ms_per_step": ms_med / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": f"{args.worlds} independent pyramid{ROWS} worlds (BASELINE.json config 5), one CTA per world",
-                   "bodies_per_world": nb, "iterations": ITER, "dt": scene.dt, "warm_starting": True, "settle_steps": args.settle,
+        "repeats": REPEATS, "ms_per_step_runs": [r / args.steps for r in runs], "aggregate": "median of the runs",
+        "value_per_step_launch": total_bodies * args.steps / (ms_single * 1e-3), "ms_per_step_per_step_launch": ms_single / args.steps,
+        "config": {"workload": workload_name(args.config, args.worlds), "bodies_per_world": [p[0].num_bodies for p in parts],
+                   "iterations": args.iterations, "dt": dt, "warm_starting": True, "settle_steps": args.settle,
+                   "implementation": "one CTA per world (k_batch_step), K steps per launch",
                    "parallelism": f"worlds sharded over {world_size} GPU(s), no per-step communication",
                    "l2": "per-GPU state (bodies + per-world slot cache) exceeds the 126 MB L2 at N<=2; smaller shards are L2-resident by nature of strong scaling",
-                   "contacts_per_world": C_w, "errors": errors_total},
+                   "contacts_per_world": contacts_total / max(args.worlds, 1), "errors": errors_total},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": my_bodies * 4 * FPB * world_size, "d2h_bytes_per_step": my_bodies * 4 * FPB * world_size,
-                "steps": e2e_steps, "api": "sylt_batch_step_host6(dt, 1, in, out): every body state (x, y, rotation, vx, vy, angular_velocity) H2D + one step + every body state D2H per step, pinned host buffers, world chunks pipelined over 4 streams"},
+                "steps": e2e_steps, "runs_s": e2e_runs,
+                "api": "sylt_batch_step_host6(dt, 1, in, out): every body state (x, y, rotation, vx, vy, angular_velocity) H2D + one step + every body "
+                       "state D2H per step, pinned host buffers, world chunks pipelined over several streams"},
         "gpu_launches": int(launches),
         "roofline": roof,
         "clocks": clocks,
         "stats": {"contacts": contacts_total, "errors": errors_total, "kinetic_energy": float(red[2].item()), "max_penetration": float(mx.item())},
     }
-    if rank == 0 and world_size == 1:
+    if rank == 0 and world_size == 1 and args.config == 5:
         if not args.skip_cpu:
             from oracle import orc
             orc.build()
+            b, scene, mine = batches[0]
+            kw = parts[0][2]
+            nb = scene.num_bodies
             cores = os.cpu_count() or 1
-            n = min(args.worlds, max(cores * 8, 64))
-            states = batch.get_bodies(0, n)
-            _, el0 = cpu_time_sample(scene, n, 10, cores, 0, states=states)           # calibration
-            cs = int(min(2000, max(20, 12.0 / max(el0 / 10, 1e-6))))                    # ~12 s of CPU work
-            v, el = cpu_time_sample(scene, n, cs, cores, 0, states=states)
+            n = min(mine, max(cores * 8, 64))
+            states = b.get_bodies(0, n)
+            _, el0 = cpu_time_sample(scene, kw, n, 10, cores, 0, states=states)           # calibration
+            cs = int(min(2000, max(20, 12.0 / max(el0 / 10, 1e-6))))                        # ~12 s of CPU work
+            v, el = cpu_time_sample(scene, kw, n, cs, cores, 0, states=states)
             out["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                                    "sample": f"{n} of {args.worlds} settled pyramid{ROWS} worlds x {cs} steps ({el:.1f} s), one world per host thread, "
                                              "C++ restatement of the Rust reference (no Rust toolchain), all-pairs broad phase, libm trig"}
-            s1 = int(min(4000, max(20, 4.0 / max(el0 / 10 * cores / n * 2, 1e-6))))     # ~4 s on one thread
-            v1, el1 = cpu_time_sample(scene, 2, s1, 1, 0, states=states[:2 * nb])
+            s1 = int(min(4000, max(20, 4.0 / max(el0 / 10 * cores / n * 2, 1e-6))))         # ~4 s on one thread
+            v1, el1 = cpu_time_sample(scene, kw, 2, s1, 1, 0, states=states[:2 * nb])
             out["cpu_baseline"]["single_thread_value"] = v1
             out["cpu_baseline"]["single_thread_sample"] = f"2 worlds x {s1} steps ({el1:.1f} s), 1 thread"
         if not args.skip_world100k:

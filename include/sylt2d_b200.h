@@ -199,6 +199,9 @@ int sylt_batch_set_context(SyltBatch* b, int accumulate_impulse, int warm_starti
  * shared memory (97 B each): SYLT_ERR_UNSUPPORTED when a world no longer fits one CTA.  Drops the contact history (next step
  * starts cold), so call it before stepping.  The reference has no such limit (HashMap, world.rs:24). */
 int sylt_batch_set_capacity(SyltBatch* b, int32_t slots_per_world);
+/* Worlds whose arbiters sylt_batch_get_arbiters can read back (<= 64; default: the first 64 worlds of the batch).  The
+ * choice takes effect with the next step.  Body states of every world are always readable (sylt_batch_get_bodies). */
+int sylt_batch_set_export_worlds(SyltBatch* b, const int32_t* worlds, int32_t n);
 /* see sylt_world_set_fixes; fix_features is not available for batches (SYLT_ERR_UNSUPPORTED) */
 int sylt_batch_set_fixes(SyltBatch* b, int fix_features, int fix_inverse);
 int sylt_batch_step_n(SyltBatch* b, float dt, int32_t n);

@@ -43,7 +43,7 @@ SYMBOLS = [
     "sylt_world_get_arbiters", "sylt_world_get_joints", "sylt_world_get_joint_order", "sylt_world_get_stats",
     "sylt_world_last_error_matrix", "sylt_world_broad_phase", "sylt_world_step", "sylt_world_step_n", "sylt_world_step_n_async",
     "sylt_world_sync", "sylt_world_timer_start", "sylt_world_timer_stop", "sylt_world_launch_count", "sylt_collide_pairs", "sylt_sincos",
-    "sylt_batch_create", "sylt_batch_destroy", "sylt_batch_set_context", "sylt_batch_set_capacity", "sylt_batch_set_fixes", "sylt_batch_step_n", "sylt_batch_step_n_async",
+    "sylt_batch_create", "sylt_batch_destroy", "sylt_batch_set_context", "sylt_batch_set_capacity", "sylt_batch_set_export_worlds", "sylt_batch_set_fixes", "sylt_batch_step_n", "sylt_batch_step_n_async",
     "sylt_batch_sync", "sylt_batch_step_host", "sylt_batch_step_host6", "sylt_batch_timer_start", "sylt_batch_timer_stop", "sylt_batch_launch_count", "sylt_batch_num_worlds",
     "sylt_batch_num_bodies", "sylt_batch_get_bodies", "sylt_batch_set_bodies", "sylt_batch_get_arbiters", "sylt_batch_get_joints",
     "sylt_batch_get_joint_order", "sylt_batch_get_errors", "sylt_batch_stats",
@@ -78,6 +78,7 @@ def lib():
     L.sylt_world_set_fixes.argtypes = [vp, i32, i32]
     L.sylt_batch_set_fixes.argtypes = [vp, i32, i32]
     L.sylt_batch_set_capacity.argtypes = [vp, i32]
+    L.sylt_batch_set_export_worlds.argtypes = [vp, vp, i32]
     L.sylt_world_set_capacity.argtypes = [vp, i64, i64, i64]
     L.sylt_world_add_box.argtypes = [vp, u64] + [f32] * 10 + [vp]
     L.sylt_world_add_polygon.argtypes = [vp, u64, vp, i32] + [f32] * 8 + [vp]

@@ -21,7 +21,9 @@ def shard_range(n_worlds, rank, world_size):
 
 class Batch:
     def __init__(self, bodies, body_offsets, joints=None, joint_offsets=None, gravity=(0.0, -10.0), iterations=10, device=0,
-                 ctx=(True, True, True)):
+                 ctx=None):
+        """ctx = (accumulate_impulse, warm_starting, position_correction); None keeps World::new's defaults
+        (true, false, true; src/world.rs:38-42), exactly like N default reference Worlds."""
         self.L = lib()
         self.bodies = np.ascontiguousarray(bodies, dtype=BODY_DESC)
         self.body_offsets = np.ascontiguousarray(body_offsets, dtype=np.int32)
@@ -37,7 +39,8 @@ class Batch:
                                        int(device), C.byref(h)))
         self.h = h
         self.n_worlds = n
-        self.set_context(*ctx)
+        if ctx is not None:
+            self.set_context(*ctx)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -58,6 +61,11 @@ class Batch:
     def set_capacity(self, slots_per_world=0):
         """Candidate-pair slots per world (0 = default 2 * max bodies + 32); drops the contact history."""
         check(self.L.sylt_batch_set_capacity(self.h, int(slots_per_world)))
+
+    def set_export_worlds(self, worlds):
+        """Worlds (<= 64) whose arbiters get_arbiters / solve_order can read back after the next step."""
+        w = np.ascontiguousarray(worlds, dtype=np.int32)
+        check(self.L.sylt_batch_set_export_worlds(self.h, ptr(w), w.shape[0]))
 
     def set_fixes(self, fix_features=False, fix_inverse=False):
         check(self.L.sylt_batch_set_fixes(self.h, int(fix_features), int(fix_inverse)))

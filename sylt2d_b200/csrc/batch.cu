@@ -29,6 +29,7 @@ namespace {
 constexpr int BNC = 32;        // colours per world
 constexpr int MAX_JC = 16;     // joint colours per world
 constexpr unsigned char NO_COLOR = 0xff;
+constexpr int MAX_EXPORT = 64;  // worlds whose arbiters are exported in full (parity tests / renderer read-back)
 constexpr int ROWT = 8;         // partners remembered per row between the count and the emit pass
 
 struct SlotExport {  // full record of one arbiter slot, written for worlds in the export range only
@@ -45,7 +46,7 @@ struct BatchArgs {
     int n_worlds, world_begin, n_steps, iterations, accumulate, warm, poscorr, fix_inverse;
     float dt, inv_dt, gx, gy, cell;
     int Bmax, Jmax, cap, nbk;
-    int export_first, export_count;
+    const int* exp_map;              // per world: export slot (full arbiter read-back, sylt_batch_set_export_worlds) or -1
     const int *body_off, *joint_off;
     float4 *pose, *vel;              // (x,y,rot,_), (vx,vy,w,_)
     const float4* mp;                // (inv_mass, inv_moi, friction, _)
@@ -71,8 +72,8 @@ struct BatchArgs {
     int *w_err, *w_ncon, *w_narb, *w_ncolors, *w_errjoint;
     float* w_maxpen;
     float4* w_badk;
-    SlotExport* exp_slots;           // export_count * cap
-    int* exp_count;                  // export_count
+    SlotExport* exp_slots;           // export slots * cap
+    int* exp_count;                  // per export slot
     // shared-memory layout: byte offset of every Smem array, computed once on the host (carve) and read from the constant
     // bank, so that re-deriving a pointer inside a hot loop is one load + one add instead of the whole chain of align-ups
     unsigned long long smem_off[48];
@@ -342,7 +343,8 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     const float kbias = poscorr ? 0.2f : 0.0f;
     int ncolors = 0, P = 0;
     float maxpen = 0.0f;
-    const bool exporting = wld >= a.export_first && wld < a.export_first + a.export_count;
+    const int xw = a.exp_map[wld];
+    const bool exporting = xw >= 0;
 
 #ifdef SYLT_BATCH_TIMING
     long long t_last = clock64(), t_hop = 0;
@@ -536,7 +538,7 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
             }
             s.color[p] = color;
             if (exporting && step == a.n_steps - 1) {
-                SlotExport* e = &a.exp_slots[(size_t)(wld - a.export_first) * cap + p];
+                SlotExport* e = &a.exp_slots[(size_t)xw * cap + p];
                 { int kb1, kb2; key_bodies(key, kb1, kb2); e->key = ((unsigned)kb1 << 16) | (unsigned)kb2; }
                 e->count = n; e->nx = n > 0 ? out[0].nx : 0.0f; e->ny = n > 0 ? out[0].ny : 0.0f;
                 for (int q = 0; q < 2; q++) {
@@ -781,7 +783,6 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     }
     // ---- optional full export of the last step's arbiters (parity tests / renderer read-back)
     if (exporting) {
-        const int xw = wld - a.export_first;
         const bool valid = !err && a.n_steps > 0;
         for (int k = tid; k < (valid ? cstart[BNC] : 0); k += T) {
             const int p = s.order[k];
@@ -892,7 +893,9 @@ struct SyltBatch {
     size_t smem = 0;
     int64_t launches = 0;
     uint64_t body_steps = 0;
-    int export_first = 0, export_count = 0;
+    int export_count = 0;             // worlds with full arbiter read-back (<= MAX_EXPORT)
+    std::vector<int> h_exp_map;       // per world: export slot or -1
+    DBuf<int> exp_map;
     int last_steps = 0;
     bool inflight = false;
     std::vector<int> h_body_off, h_joint_off, h_jorder;
@@ -923,7 +926,7 @@ void batch_free(SyltBatch* b) {
     b->exp_count.release(); b->pose.release(); b->vel.release(); b->mp.release(); b->jla.release(); b->jr.release(); b->jm.release();
     b->w_badk.release(); b->wh.release(); b->jparam.release(); b->jp.release(); b->jbias.release(); b->mass_moi.release();
     b->c_cache0.release(); b->c_cache1.release(); b->c_stg0.release(); b->c_stg1.release(); b->c_par.release(); b->w_maxpen.release(); b->jbodies.release(); b->c_key.release();
-    b->c_color.release(); b->bflags.release(); b->exp_slots.release(); b->stats.release(); b->stage.release();
+    b->c_color.release(); b->bflags.release(); b->exp_slots.release(); b->exp_map.release(); b->stats.release(); b->stage.release();
 }
 
 template <typename T>
@@ -982,7 +985,7 @@ int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaSt
         for (size_t i = 0; i < sizeof(Smem) / sizeof(void*); i++) a.smem_off[i] = (unsigned long long)(ptrs[i] - anchor);
     }
     a.gx = b->gx; a.gy = b->gy; a.Bmax = b->Bmax; a.Jmax = b->Jmax; a.cap = b->cap; a.nbk = b->nbk; a.cell = b->cell; a.bflags = b->bflags.p;
-    a.export_first = b->export_first; a.export_count = b->export_count;
+    a.exp_map = b->exp_map.p;
     a.body_off = b->body_off.p; a.joint_off = b->joint_off.p; a.pose = b->pose.p; a.vel = b->vel.p; a.mp = b->mp.p; a.wh = b->wh.p;
     a.jbodies = b->jbodies.p; a.jla = b->jla.p; a.jparam = b->jparam.p; a.jp = b->jp.p; a.jr = b->jr.p; a.jm = b->jm.p; a.jbias = b->jbias.p;
     a.jorder = b->jorder.p; a.jcolor_start = b->jcolor_start.p; a.n_jcolors = b->n_jcolors.p;
@@ -1125,8 +1128,10 @@ int sylt_batch_create(int32_t n_worlds, const int32_t* body_offsets, const SyltB
     }
     b->h_jorder = jorder;
     b->Bmax = Bmax; b->Jmax = Jmax;
-    b->export_first = 0;
-    b->export_count = std::min(n_worlds, 64);
+    b->export_count = std::min(n_worlds, MAX_EXPORT);  // default: the first worlds (sylt_batch_set_export_worlds picks others)
+    b->h_exp_map.assign((size_t)n_worlds, -1);
+    for (int k = 0; k < b->export_count; k++) b->h_exp_map[(size_t)k] = k;
+    { int e0 = upload(b->exp_map, b->h_exp_map); if (e0) { sylt_batch_destroy(b); return e0; } }
     // default slot capacity: two candidate pairs per body (a pyramid or a chain has fewer); sylt_batch_set_capacity raises it
     { int e0 = batch_set_cap(b, 2 * Bmax + 32); if (e0) { sylt_batch_destroy(b); return e0; } }
     SYLT_CUDA(cudaStreamCreateWithFlags(&b->stream, cudaStreamNonBlocking));
@@ -1172,6 +1177,23 @@ int sylt_batch_set_capacity(SyltBatch* b, int32_t slots_per_world) {
     SYLT_CUDA(cudaSetDevice(b->device));
     SYLT_CUDA(cudaStreamSynchronize(b->stream));
     return batch_set_cap(b, slots_per_world == 0 ? 2 * b->Bmax + 32 : slots_per_world);
+}
+
+int sylt_batch_set_export_worlds(SyltBatch* b, const int32_t* worlds, int32_t n) {
+    if (!b || n < 0 || n > MAX_EXPORT || (n > 0 && !worlds)) return SYLT_ERR_INVALID;
+    std::vector<int> m((size_t)b->n_worlds, -1);
+    for (int k = 0; k < n; k++) {
+        if (worlds[k] < 0 || worlds[k] >= b->n_worlds || m[(size_t)worlds[k]] >= 0) return SYLT_ERR_INVALID;
+        m[(size_t)worlds[k]] = k;
+    }
+    SYLT_CUDA(cudaSetDevice(b->device));
+    SYLT_CUDA(cudaStreamSynchronize(b->stream));
+    b->h_exp_map = m;
+    b->export_count = n;
+    int e = upload(b->exp_map, b->h_exp_map);
+    if (e) return e;
+    if ((e = zeroed(b->exp_slots, (size_t)n * (size_t)b->cap)) || (e = zeroed(b->exp_count, (size_t)std::max(1, n)))) return e;
+    return SYLT_OK;
 }
 
 int sylt_batch_set_fixes(SyltBatch* b, int fix_features, int fix_inverse) {
@@ -1295,9 +1317,9 @@ int sylt_batch_set_bodies(SyltBatch* b, int32_t first, int32_t nw, const SyltBod
 
 int sylt_batch_get_arbiters(SyltBatch* b, int32_t world, SyltArbiterInfo* arbiters, int32_t arbiter_cap, SyltContact* contacts, int32_t contact_cap) {
     if (!b || world < 0 || world >= b->n_worlds) return -SYLT_ERR_INVALID;
-    if (world < b->export_first || world >= b->export_first + b->export_count) return -SYLT_ERR_UNSUPPORTED;
+    if (b->h_exp_map[(size_t)world] < 0) return -SYLT_ERR_UNSUPPORTED;  // not in the export set (sylt_batch_set_export_worlds)
     if (cudaSetDevice(b->device) != cudaSuccess) return -SYLT_ERR_CUDA;
-    const int xw = world - b->export_first;
+    const int xw = b->h_exp_map[(size_t)world];
     int P = 0;
     cudaStreamSynchronize(b->stream);
     if (cudaMemcpy(&P, b->exp_count.p + xw, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return -SYLT_ERR_CUDA;

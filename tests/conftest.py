@@ -14,9 +14,11 @@ def pytest_configure(config):
 
 
 def _has_gpu():
+    """Asks the product itself (cudaGetDeviceCount behind sylt_device_count): no torch needed, and a box whose torch build
+    cannot see the GPU does not silently skip the parity tests."""
     try:
-        import torch
-        return torch.cuda.is_available()
+        from sylt2d_b200 import lib
+        return lib().sylt_device_count() > 0
     except Exception:
         return False
 
@@ -24,6 +26,8 @@ def _has_gpu():
 def pytest_collection_modifyitems(config, items):
     if _has_gpu():
         return
+    if os.environ.get("SYLT_REQUIRE_GPU", "0") not in ("", "0"):  # the GPU CI job: a missing device is a failure, not a skip
+        raise pytest.UsageError("SYLT_REQUIRE_GPU is set but libsylt2d_b200.so sees no CUDA device")
     skip = pytest.mark.skip(reason="no CUDA device in this container")
     for it in items:
         if "gpu" in it.keywords:

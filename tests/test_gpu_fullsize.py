@@ -1,0 +1,249 @@
+"""GPU parity at the FULL sizes of BASELINE.json's configurations ("Next round" item 1).
+
+  config 5   the 32 768-world pyramid batch exactly as bench.py builds it: sampled worlds (first, last, both sides of a
+             592-CTA wave boundary, the middle) in lock-step with the oracle through falling, landing and the settled regime;
+             every world error-free; one launch of K steps == K launches of one step for ALL worlds
+  config 4   4096 bridge + 4096 multi-pendulum worlds, sampled worlds bit-exact, at I = 10 and at the reference's I = 100
+  config 3   100k boxes: lock-step through the first steps, through the falling phase (mass arbiter creation, several
+             colouring rounds) and across forced region re-cuts (k_resort / k_rebalance on every other step)
+  solvers    one large world under SYLT_REGIONS = 0 / 1 / 2 (k_solve, default choice, k_solve_regions)
+
+Everything is compared bit for bit (tolerance 0) with the oracle replaying the GPU's reported colour order.
+"""
+import numpy as np
+import pytest
+
+from oracle import orc
+from sylt2d_b200 import scenes
+from tests.test_gpu_parity import CONTACT_GEOM, CONTACT_SOLVE, _assert_arbiters_equal, _assert_states_equal
+
+pytestmark = pytest.mark.gpu
+
+
+def _world_scene(scene, bodies, wi):
+    nb = scene.num_bodies
+    return scenes.Scene(scene.name, bodies[wi * nb:(wi + 1) * nb], scene.joints, scene.verts, scene.gravity, scene.iterations, scene.dt, scene.ctx)
+
+
+def _batch_sampled_lockstep(scene, n_worlds, sample, steps, seed, x_jitter=0.0, omega_jitter=0.0, check_every=1):
+    """Steps the whole batch one step per launch; the oracle follows the sampled worlds in the GPU's solve order."""
+    from sylt2d_b200 import Batch
+    bodies, boff, joints, joff = scenes.tile_worlds(scene, n_worlds, seed=seed, x_jitter=x_jitter, omega_jitter=omega_jitter)
+    b = Batch(bodies, boff, joints, joff, scene.gravity, scene.iterations, device=0, ctx=scene.ctx)
+    b.set_export_worlds(sample)
+    oracles = {}
+    for wi in sample:
+        o = orc.OracleWorld(scene.gravity, scene.iterations, sincos_mode=1)
+        o.load_scene(_world_scene(scene, bodies, wi))
+        oracles[wi] = o
+    for s in range(steps):
+        b.step_n(scene.dt, 1)
+        for wi, o in oracles.items():
+            keys, jo = b.solve_order(wi)
+            o.step_ordered(scene.dt, keys, jo)
+            if s % check_every == 0 or s == steps - 1:
+                _assert_states_equal(b.get_bodies(wi, 1), o.get_bodies(), f"{scene.name} x{n_worlds} world {wi} step {s}")
+    for wi, o in oracles.items():
+        ga, gc = b.get_arbiters(wi)
+        ra, rc = o.get_arbiters()
+        assert np.array_equal(ga["id1"], ra["id1"]) and np.array_equal(ga["id2"], ra["id2"]), f"world {wi}: arbiter keys"
+        assert np.array_equal(ga["friction"], ra["friction"])
+        for f in CONTACT_GEOM + CONTACT_SOLVE:
+            assert np.array_equal(gc[f], rc[f]), (wi, f)
+        gj, rj = b.get_joints(wi), o.get_joints()
+        for f in gj.dtype.names:
+            assert np.array_equal(gj[f], rj[f]), (wi, f)
+    err = b.get_errors()
+    assert err.shape[0] == n_worlds and not err.any(), f"worlds with errors: {np.nonzero(err)[0][:8]}"
+    return b, (bodies, boff, joints, joff)
+
+
+def test_config5_full_batch_sampled_worlds_bit_exact():
+    """32 768 pyramid20 worlds, built exactly like bench.py's timed batch (seed 0, x jitter 0.01, warm starting on)."""
+    from sylt2d_b200 import Batch
+    sc = scenes.pyramid(20, 10)
+    n = 32768
+    sample = [0, 591, 592, 1183, 1184, 16384, 32767]   # first, both sides of the first two 592-CTA wave boundaries, middle, last
+    steps = 170                                        # bench.py settles 150 steps, then times: covers landing + the settled regime
+    b, (bodies, boff, joints, joff) = _batch_sampled_lockstep(sc, n, sample, steps, seed=0, x_jitter=0.01, check_every=5)
+    st = b.stats()
+    assert st["errors"] == 0 and st["body_steps"] == n * sc.num_bodies * steps
+    assert st["contacts"] > 700 * n                    # every world has landed (~800 contacts per settled pyramid)
+    # one launch running all the steps (how bench.py times `value`) gives the same bytes for EVERY world
+    b2 = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, device=0, ctx=sc.ctx)
+    b2.step_n(sc.dt, steps)
+    assert b.get_bodies().tobytes() == b2.get_bodies().tobytes()
+    assert not b2.get_errors().any()
+
+
+@pytest.mark.parametrize("iterations", [10, 100])
+def test_config4_full_joint_batches_sampled_worlds_bit_exact(iterations):
+    """4096 bridge + 4096 multi-pendulum worlds (examples/samples/src/main.rs:206-239, 300-336), I = 10 and the samples' I = 100."""
+    sample = [0, 591, 592, 2047, 4095]
+    _batch_sampled_lockstep(scenes.bridge(iterations), 4096, sample, 60, seed=5, omega_jitter=0.0, check_every=4)
+    _batch_sampled_lockstep(scenes.multi_pendulum(iterations), 4096, sample, 60, seed=5, omega_jitter=1.0, check_every=4)
+
+
+def _lockstep_from(sc, w, o, steps, what):
+    for s in range(steps):
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"{what} step {s}")
+    _assert_arbiters_equal(w, o, what=what)
+
+
+def _fresh_pair(sc, state=None):
+    from sylt2d_b200 import World
+    w = World(sc.gravity, sc.iterations, device=0)
+    w.load_scene(sc)
+    o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=1, broadphase=1)  # grid candidates == the all-pairs set (tests/test_oracle_kat.py)
+    o.load_scene(sc)
+    if state is not None:
+        w.set_bodies(state)
+        o.set_bodies(state)
+    return w, o
+
+
+def test_config3_100k_first_steps_and_falling_phase_bit_exact():
+    from sylt2d_b200 import World
+    sc = scenes.box_drop(100000, seed=42)
+    w, o = _fresh_pair(sc)
+    _lockstep_from(sc, w, o, 6, "box_drop100k steps 0-5")
+    # the falling phase: thousands of arbiters are created per step, the colouring runs several grid-wide rounds
+    g = World(sc.gravity, sc.iterations, device=0)
+    g.load_scene(sc)
+    g.step_n(sc.dt, 55)
+    w, o = _fresh_pair(sc, g.get_bodies())
+    rounds = []
+    for s in range(6):
+        w.step(sc.dt)
+        rounds.append(w.get_stats()["color_rounds"])
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"box_drop100k step {55 + s}")
+    _assert_arbiters_equal(w, o, what="box_drop100k steps 55-60")
+    st = w.get_stats()
+    assert st["bodies"] == 100003 and st["arbiters"] > 10000 and max(rounds) >= 2, (st, rounds)
+
+
+def test_config3_100k_across_region_recuts_bit_exact(monkeypatch):
+    """SYLT_REGIONS_PERIOD=2: k_resort + k_rebalance re-cut the regions (and every arbiter is recoloured) on every other step."""
+    from sylt2d_b200 import World
+    monkeypatch.setenv("SYLT_REGIONS_PERIOD", "2")
+    sc = scenes.box_drop(100000, seed=42)
+    g = World(sc.gravity, sc.iterations, device=0)
+    g.load_scene(sc)
+    g.step_n(sc.dt, 200)
+    w, o = _fresh_pair(sc, g.get_bodies())
+    _lockstep_from(sc, w, o, 5, "box_drop100k re-cut")
+    ga, _ = w.get_arbiters()
+    assert ga.shape[0] > 50000 and (ga["color"] < 32).any() and (ga["color"] >= 32).any()  # the region solver ran: both colour classes
+
+
+@pytest.mark.parametrize("regions", ["0", "1", "2"])
+def test_large_world_both_solvers_bit_exact(monkeypatch, regions):
+    """The same 20k-body world under k_solve only (0), the default choice (1) and k_solve_regions forced (2)."""
+    from sylt2d_b200 import World
+    monkeypatch.setenv("SYLT_REGIONS", regions)
+    sc = scenes.box_drop(20000, seed=7)
+    g = World(sc.gravity, sc.iterations, device=0)
+    g.load_scene(sc)
+    g.step_n(sc.dt, 150)
+    w, o = _fresh_pair(sc, g.get_bodies())
+    _lockstep_from(sc, w, o, 4, f"box_drop20k SYLT_REGIONS={regions}")
+    ga, _ = w.get_arbiters()
+    assert ga.shape[0] > 10000
+    assert ((ga["color"] >= 32).any() and (ga["color"] < 32).any()) == (regions != "0")  # generic + interior classes only with regions
+
+
+def _energies(st, props, g):
+    dyn = props[:, 1] != 0.0
+    m, I = props[dyn, 0].astype(np.float64), props[dyn, 2].astype(np.float64)
+    ke = 0.5 * m * (st["vx"][dyn].astype(np.float64) ** 2 + st["vy"][dyn].astype(np.float64) ** 2) + 0.5 * I * st["angular_velocity"][dyn].astype(np.float64) ** 2
+    pe = -m * (g[0] * st["x"][dyn].astype(np.float64) + g[1] * st["y"][dyn].astype(np.float64))
+    return float(ke.sum()), float(pe.sum())
+
+
+# measured on a B200 (tools/measure_order_tolerance.py -> profiles/r04_order_tolerance.json); the gates are 2x the measurement
+ORDER_TOL = {
+    "pyramid20": {"dv": 5.0e-2, "ke_rel": 0.5, "ke_rest": 1.0e-2, "pen": 0.05},
+    "multi_pendulum": {"etot_rel": 0.5},
+}
+
+
+def measure_order_effects(steps=600):
+    """GPU colour order vs the canonical ascending-(id1, id2) oracle, from the same initial scenes: the differences of the
+    kinetic-energy / max-penetration / total-energy time series and of one step from an identical settled state."""
+    from sylt2d_b200 import World
+    out = {}
+    # ---- pyramid20: contacts
+    sc = scenes.pyramid(20, 10)
+    w = World(sc.gravity, sc.iterations, device=0)
+    w.load_scene(sc)
+    o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=1)
+    o.load_scene(sc)
+    props = w.get_body_props()
+    ke_g, ke_c, pen_g, pen_c = [], [], [], []
+    for s in range(steps):
+        w.step(sc.dt)
+        o.step(sc.dt)
+        ke_g.append(_energies(w.get_bodies(), props, sc.gravity)[0])
+        ke_c.append(_energies(o.get_bodies(), props, sc.gravity)[0])
+        if s % 10 == 9:
+            pen_g.append(max(0.0, -float(w.get_arbiters()[1]["separation"].min())))
+            pen_c.append(max(0.0, -float(o.get_arbiters()[1]["separation"].min())))
+    ke_g, ke_c, pen_g, pen_c = map(np.asarray, (ke_g, ke_c, pen_g, pen_c))
+    scale = float(ke_c.max())
+    out["pyramid20"] = {
+        "ke_max": scale, "ke_series_max_abs_diff_rel": float(np.abs(ke_g - ke_c).max() / scale),
+        "ke_last50_max_rel_gpu": float(ke_g[-50:].max() / scale), "ke_last50_max_rel_canonical": float(ke_c[-50:].max() / scale),
+        "pen_series_max_abs_diff": float(np.abs(pen_g - pen_c).max()), "pen_max_gpu": float(pen_g.max()), "pen_max_canonical": float(pen_c.max()),
+    }
+    # single step from an identical settled state, the two orders side by side
+    st = o.get_bodies()
+    w2 = World(sc.gravity, sc.iterations, device=0)
+    w2.load_scene(sc)
+    w2.set_bodies(st)
+    o2 = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=1)
+    o2.load_scene(sc)
+    o2.set_bodies(st)
+    w2.step(sc.dt)
+    o2.step(sc.dt)
+    a, b = w2.get_bodies(), o2.get_bodies()
+    out["pyramid20"]["single_step_max_abs_dv"] = float(max(np.abs(a["vx"] - b["vx"]).max(), np.abs(a["vy"] - b["vy"]).max()))
+    # ---- multi-pendulum: joints only; total energy (soft joints, quirk Q-3, let the chain stretch: compare, not conserve)
+    sc = scenes.multi_pendulum(10)
+    w = World(sc.gravity, sc.iterations, device=0)
+    w.load_scene(sc)
+    o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=1)
+    o.load_scene(sc)
+    props = w.get_body_props()
+    e_g, e_c = [], []
+    for s in range(steps):
+        w.step(sc.dt)
+        o.step(sc.dt)
+        e_g.append(sum(_energies(w.get_bodies(), props, sc.gravity)))
+        e_c.append(sum(_energies(o.get_bodies(), props, sc.gravity)))
+    e_g, e_c = np.asarray(e_g), np.asarray(e_c)
+    span = float(max(np.ptp(e_c), 1e-9))
+    out["multi_pendulum"] = {"etot_span": span, "etot_series_max_abs_diff_rel": float(np.abs(e_g - e_c).max() / span),
+                             "etot_drift_gpu": float(e_g[-1] - e_g[0]), "etot_drift_canonical": float(e_c[-1] - e_c[0])}
+    return out
+
+
+def test_long_run_energy_and_penetration_series_gpu_order_vs_canonical_order():
+    """north_star: "long runs must match on penetration and energy drift".  The GPU solves in colour order, the canonical
+    oracle in ascending (id1, id2) order (the reference's own order is a random HashMap order, quirk Q-1): 600 steps of the
+    20-row pyramid and of the multi-pendulum, kinetic-energy, max-penetration and total-energy time series side by side.
+    Gates = 2 x the values measured on a B200 (profiles/r04_order_tolerance.json, tools/measure_order_tolerance.py)."""
+    m = measure_order_effects(600)
+    print("order effects:", m)
+    p, t = m["pyramid20"], ORDER_TOL["pyramid20"]
+    assert p["ke_series_max_abs_diff_rel"] <= t["ke_rel"], p
+    assert p["ke_last50_max_rel_gpu"] <= t["ke_rest"] and p["ke_last50_max_rel_canonical"] <= t["ke_rest"], p  # at rest in the end: no drift
+    assert p["pen_series_max_abs_diff"] <= t["pen"] and p["pen_max_gpu"] <= p["pen_max_canonical"] + t["pen"], p
+    assert p["single_step_max_abs_dv"] <= t["dv"], p
+    q, t = m["multi_pendulum"], ORDER_TOL["multi_pendulum"]
+    assert q["etot_series_max_abs_diff_rel"] <= t["etot_rel"], q
+    assert abs(q["etot_drift_gpu"] - q["etot_drift_canonical"]) <= t["etot_rel"] * q["etot_span"], q
