@@ -132,6 +132,9 @@ class OracleWorld:
                                               0.2 if bias_factor is None else bias_factor)
         return j
 
+    def set_joint_params(self, joint_index, softness, bias_factor):
+        self.L.orc_world_set_joint_params(self.h, int(joint_index), softness, bias_factor)
+
     def add_force(self, body, f):
         self.L.orc_world_add_force(self.h, body, f[0], f[1])
 

@@ -698,8 +698,26 @@ struct OrcWorld {
         } else { jo.resize(joints.size()); for (size_t j = 0; j < jo.size(); j++) jo[j] = (int)j; }
 
         for (Arbiter* a : order) arbiter_pre_step(*a, bodies, inv_dt, ctx);                  // :123-125
-        for (int j : jo)                                                                     // :127-129
-            if (!joint_pre_step(joints[(size_t)j], bodies, ctx, inv_dt, sincos_mode, &bad)) { bad_joint = j; return ERR_NO_INVERSE; }
+        // :127-129  `for joint in self.joints.iter_mut() { joint.pre_step(..)?; }` returns at the FIRST joint in Vec order whose K
+        // has no inverse; joints behind it are never touched.  K depends on the poses only (joint.rs:67-94), so under an explicit
+        // replay order the same joints are pre-stepped (in the replayed order) and the same joint reports the error.
+        int jfail = 0x7fffffff;
+        if (jorder)
+            for (size_t j = 0; j < joints.size(); j++) {
+                Joint probe = joints[j];
+                std::vector<Body> two = {bodies[(size_t)probe.b1], bodies[(size_t)probe.b2]};
+                probe.b1 = 0; probe.b2 = 1;
+                M2 k;
+                if (!joint_pre_step(probe, two, ctx, inv_dt, sincos_mode, &k)) { jfail = (int)j; break; }
+            }
+        for (int j : jo) {
+            if (j > jfail) continue;
+            if (!joint_pre_step(joints[(size_t)j], bodies, ctx, inv_dt, sincos_mode, &bad)) {
+                bad_joint = j;
+                if (!jorder) return ERR_NO_INVERSE;  // canonical order == Vec order: the reference's loop, literally
+            }
+        }
+        if (jfail != 0x7fffffff) return ERR_NO_INVERSE;
         for (uint32_t it = 0; it < iterations; it++) {                                       // :132-140
             for (Arbiter* a : order) arbiter_apply_impulse(*a, bodies, ctx);
             for (int j : jo) joint_apply_impulse(joints[(size_t)j], bodies);

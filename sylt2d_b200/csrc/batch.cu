@@ -659,10 +659,23 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
         __syncthreads();
         if (acc) warm_sweep(hot, ncolors);
         PHASE(5);
-        // ---- 6. Joint::pre_step by joint colour
+        // ---- 6. Joint::pre_step by joint colour.  The reference's loop (world.rs:127-129) returns Err at the FIRST joint in Vec
+        //         order whose K is singular: joints behind it are never touched.  K depends on the poses only, so that joint is
+        //         found before anything is pre-stepped (s.misc[140] = J - index, 0 = none).
+        if (tid == 0) s.misc[140] = 0;
+        __syncthreads();
+        for (int j = tid; j < J; j += T) {
+            const int2 b = s.jb[j];
+            const float2 i1 = s.inv[b.x], i2 = s.inv[b.y], c1 = s.cs[b.x], c2 = s.cs[b.y];
+            const float4 la = s.jla[j];
+            if (joint_singular(mk(la.x, la.y), mk(la.z, la.w), s.jparam[j].x, c1.x, c1.y, c2.x, c2.y, i1.x, i1.y, i2.x, i2.y)) atomicMax(&s.misc[140], J - j);
+        }
+        __syncthreads();
+        const int jfail = s.misc[140] > 0 ? J - s.misc[140] : 0x7fffffff;
         for (int c = 0; c < njc; c++) {
             for (int k = jcs[c] + tid; k < jcs[c + 1]; k += T) {
                 int j = s.jorder[k];
+                if (j > jfail) continue;
                 int2 b = s.jb[j];
                 float2 i1 = s.inv[b.x], i2 = s.inv[b.y], p1 = s.pos[b.x], p2 = s.pos[b.y], c1 = s.cs[b.x], c2 = s.cs[b.y];
                 Vel v1 = ld_vel(s.vel, b.x), v2 = ld_vel(s.vel, b.y);

@@ -103,6 +103,22 @@ struct JointConst {
     float softness;
 };
 
+// The K matrix of Joint::pre_step (joint.rs:67-94) and whether Mat2x2::invert rejects it (math_utils.rs:190-193).  K depends on
+// the poses only, so the joint at which World::step aborts (world.rs:127-129: the FIRST singular joint in Vec order) is known
+// before any joint is pre-stepped.
+SYLT_HD bool joint_singular(V2 la1, V2 la2, float softness, float c1, float s1, float c2, float s2, float im1, float ii1, float im2, float ii2) {
+    V2 r1 = rot_cs(c1, s1) * la1;
+    V2 r2 = rot_cs(c2, s2) * la2;
+    M2 k1 = mk(mk(im1 + im2, 0.0f), mk(0.0f, im1 + im2));
+    M2 k2 = mk(mk(ii1 * r1.y * r1.y, -ii1 * r1.x * r1.y), mk(-ii1 * r1.x * r1.y, ii1 * r1.x * r1.x));
+    M2 k3 = mk(mk(ii2 * r2.y * r2.y, -ii2 * r2.x * r2.y), mk(-ii2 * r2.x * r2.y, ii2 * r2.x * r2.x));
+    M2 k = k1 + k2 + k3;
+    k.c1.x += softness;
+    k.c2.y += softness;
+    M2 dummy;
+    return !invert_q3(k, &dummy, false);  // det == 0 (the opt-in true inverse rejects the same matrices)
+}
+
 // Joint::pre_step (joint.rs:57-115).  (c1,s1),(c2,s2): cos/sin of the two body rotations.
 // Returns false (and the singular K in *bad) when K has no inverse (quirk Q-15).
 SYLT_HD bool joint_prestep(V2 la1, V2 la2, float softness, float bias_factor, V2 p1, float c1, float s1, V2 p2, float c2, float s2,

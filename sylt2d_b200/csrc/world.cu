@@ -58,9 +58,11 @@ constexpr int MAX_ROUNDS = 256; // colouring rounds per step (only new arbiters 
 constexpr int FLAG_POLY = 1, FLAG_LARGE = 2, FLAG_STATIC = 4;
 
 struct Counters {
-    // sticky across the steps of one step_n call (reset by do_steps):
+    // sticky across the steps of one step_n call (reset by do_steps).  Once err is set every kernel of the following steps
+    // returns at once: a failed step changes nothing (bodies, forces, last step's arbiters), later steps of the call do not run.
     int err, err_joint;
     float badk[4];
+    int steps_done;  // steps of this call that completed
     // per step (reset by enqueue_step):
     int n_pairs, n_arb, n_con;
     int n_colors, rounds, n_uncolored, warn_ext;
@@ -69,6 +71,7 @@ struct Counters {
     int color_fill[NC];
     int remaining[MAX_ROUNDS];
     unsigned bar;  // grid barrier arrivals of this step's k_solve
+    int jfail1;    // J - (index of the first joint in Vec order whose K is singular), 0 = none (world.rs:127-129)
     // region solver (k_solve_regions):
     int n_generic;                  // arbiters of the generic colours (cross-region pairs, interior overflow)
     int n_ghost;                    // replicas of generic arbiters replayed by neighbouring regions
@@ -85,6 +88,7 @@ struct Counters {
 // pdl_trigger() lets the successor start scheduling early.  Without the attribute both are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ bool step_failed(const Counters* cn) { return *(volatile const int*)&cn->err != 0; }
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -155,11 +159,12 @@ __device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
     return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w);
 }
 
-__global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* vel, const float4* force, const float4* mp, const float4* geom,
+__global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const float4* vel, const float4* force, const float4* mp, const float4* geom,
                                                  const int* bflags, const float2* lverts, float2* rotc, float4* aabb, int4* cinfo,
                                                  int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
                                                  Counters* cn, ulonglong2* vrec, unsigned long long* used, unsigned* used_int) {
     pdl_trigger();
+    if (step_failed(cn)) return;  // an earlier step of this call failed: nothing runs any more
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     used[i] = 0ull;  // colours taken at this body: rebuilt by k_build / the colouring rounds every step
@@ -177,7 +182,8 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* ve
             V2 nv = mk(v.x, v.y) + (mk(gx, gy) + mk(f.x, f.y) * m.x) * dt;
             v.x = nv.x; v.y = nv.y;
             v.z += m.y * f.z * dt;
-            vel[i] = v;
+            // NOT written to vel[]: the solver reads and writes velocities through vrec and stores vel[] when the step has
+            // succeeded, so a step that fails later on (capacity) leaves the bodies untouched
         }
         // versioned velocity record of the dataflow solver: (vx|ver, vy|ver), (w|ver, inv_mass|inv_moi), ver = 0
         vrec[2 * (size_t)i] = make_ulonglong2((unsigned long long)__float_as_uint(v.x), (unsigned long long)__float_as_uint(v.y));
@@ -218,9 +224,10 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, float4* ve
 // bodies grouped by cell: a cell-ordered COPY of (index, cell, flags) and of the AABB, so that the row search streams
 // contiguous 32-byte entries instead of chasing body indices
 __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, const float4* aabb, const int* rank, const int* cell_start,
-                                                    int4* cent_info, float4* cent_aabb, GridParams gp) {
+                                                    int4* cent_info, float4* cent_aabb, GridParams gp, const Counters* cn) {
     pdl_wait();
     pdl_trigger();
+    if (step_failed(cn)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     int4 ci = cinfo[i];
@@ -302,9 +309,11 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
 // same buckets.  (Measured at 100k bodies: one thread per body 36 us, 16 lanes with a cell each 49 us — issue-bound, 32 M warp
 // instructions —, 4 lanes 39 us with 40 % of the lanes active.)
 __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
-                                                    const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp) {
+                                                    const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp,
+                                                    const Counters* cn) {
     pdl_wait();
     pdl_trigger();
+    if (step_failed(cn)) return;
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g >= B) return;
     int i;
@@ -397,6 +406,7 @@ __global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, co
                                                    int2* pairs, int cap_pairs, Counters* cn) {
     pdl_wait();
     pdl_trigger();
+    if (step_failed(cn)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     const int base = row_start[i], end = row_start[i + 1], n = end - base;
@@ -435,6 +445,7 @@ __global__ void __launch_bounds__(128) k_narrow(const Counters* cn, int cap_pair
                                                 unsigned long long* info, float4* tmp_a, float2* tmp_b, Counters* cnw) {
     pdl_wait();
     pdl_trigger();
+    if (step_failed(cn)) return;
     int P = min(cn->n_pairs, cap_pairs);
     for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
         int2 pr = pairs[p];
@@ -491,6 +502,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
                                                unsigned long long* used, int* uncolored, int fix_features, int keep_colors, unsigned* used_int, int regions) {
     pdl_wait();
+    if (step_failed(cn)) return;
     int P = min(cn->n_pairs, cap_pairs);
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     __shared__ int s_hist[NCX];
@@ -590,6 +602,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, i
         s_tile = t;
     }
     __syncthreads();
+    if (step_failed(cn)) return;  // (after the ticket: the counter must be back at zero for the next launch; err cannot change while
+                                  //  tiles wait for one another — only the last tile of a scan ever sets it)
     const int tile = s_tile;
     const int ntiles = max(1, (n + SCAN_TILE - 1) / SCAN_TILE);
     if (tile >= ntiles) return;
@@ -878,6 +892,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
         if (a.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[k] = t; }
     };
     stamp(0);
+    if (step_failed(cn)) return;  // grid-uniform: err only changes inside this kernel from here on
+    // The first joint in Vec order whose K is singular is where World::step returns Err (world.rs:127-129, quirk Q-15); K depends
+    // on the poses only, so it is known before anything is pre-stepped.  (Visible to everybody after the barrier below.)
+    for (int j = tid; j < a.J; j += nth) {
+        const int2 b = a.jbodies[j];
+        const float4 la = a.jla[j], m1 = a.mp[b.x], m2 = a.mp[b.y];
+        const float2 c1 = a.rotc[b.x], c2 = a.rotc[b.y];
+        if (joint_singular(mk(la.x, la.y), mk(la.z, la.w), a.jparam[j].x, c1.x, c1.y, c2.x, c2.y, m1.x, m1.y, m2.x, m2.y)) atomicMax(&cn->jfail1, a.J - j);
+    }
     __shared__ int s_start[NC + 1];   // global colour-major start of colour c
     __shared__ int s_lo[NC + 1];      // first slot of colour c this CTA owns (relative to s_start[c])
     __shared__ int s_lbase[NC + 1];   // local index of that slot
@@ -932,8 +955,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
         }
     }
     grid_barrier(bar, bar_target);
-    if (!a.run_solver) return;
+    if (!a.run_solver) {
+        if (tid == 0 && !step_failed(cn)) cn->steps_done++;
+        return;
+    }
     if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // e.g. an arbiter without a free colour: no solve, error reported
+    const int jfail1 = *(volatile int*)&cn->jfail1;
+    const int jfail = jfail1 > 0 ? a.J - jfail1 : 0x7fffffff;
     const int ncolors = s_ncolors;
     const int L = s_lbase[NC];  // slots this CTA owns
     const bool acc = a.accumulate != 0;
@@ -1126,26 +1154,28 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
             Vel v1, v2;
             float im1, ii1, im2, ii2;
             io.wait2(r1, e1, v1, im1, ii1, r2, e2, v2, im2, ii2);
-            float4 la = a.jla[j];
-            float2 pr = a.jparam[j];
-            float2 pa = a.jp[j];
-            V2 pacc = mk(pa.x, pa.y);
-            JointConst jc;
-            M2 bad;
             Vel w1 = v1, w2 = v2;
-            bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), r1c.x, r1c.y, mk(p2.x, p2.y), r2c.x, r2c.y,
-                                    im1, ii1, im2, ii2, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, w1, w2, jc, &bad, a.fix_inverse != 0);
-            a.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);
-            if (!ok) {  // quirk Q-15: NoInverse aborts the step before the iterations
-                if (atomicCAS(&cn->err, 0, SYLT_ERR_NO_INVERSE) == 0) {
-                    cn->err_joint = j;
-                    cn->badk[0] = bad.c1.x; cn->badk[1] = bad.c2.x; cn->badk[2] = bad.c1.y; cn->badk[3] = bad.c2.y;
+            if (j <= jfail) {  // the reference's loop returns at joint `jfail`: later joints (Vec order) are never touched
+                float4 la = a.jla[j];
+                float2 pr = a.jparam[j];
+                float2 pa = a.jp[j];
+                V2 pacc = mk(pa.x, pa.y);
+                JointConst jc;
+                M2 bad;
+                bool ok = joint_prestep(mk(la.x, la.y), mk(la.z, la.w), pr.x, pr.y, mk(p1.x, p1.y), r1c.x, r1c.y, mk(p2.x, p2.y), r2c.x, r2c.y,
+                                        im1, ii1, im2, ii2, a.inv_dt, a.poscorr != 0, a.warm != 0, pacc, w1, w2, jc, &bad, a.fix_inverse != 0);
+                a.jr[j] = make_float4(jc.r1.x, jc.r1.y, jc.r2.x, jc.r2.y);  // self.r1 / self.r2 are stored before the `?` (joint.rs:67-68)
+                if (!ok) {  // quirk Q-15: NoInverse aborts the step before the iterations (only joint `jfail` gets here)
+                    if (atomicCAS(&cn->err, 0, SYLT_ERR_NO_INVERSE) == 0) {
+                        cn->err_joint = j;
+                        cn->badk[0] = bad.c1.x; cn->badk[1] = bad.c2.x; cn->badk[2] = bad.c1.y; cn->badk[3] = bad.c2.y;
+                    }
+                    w1 = v1; w2 = v2;  // velocities untouched, versions still advance so that nobody waits forever
+                } else {
+                    a.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
+                    a.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
+                    a.jp[j] = make_float2(pacc.x, pacc.y);
                 }
-                w1 = v1; w2 = v2;  // velocities untouched, versions still advance so that nobody waits forever
-            } else {
-                a.jm[j] = make_float4(jc.m.c1.x, jc.m.c2.x, jc.m.c1.y, jc.m.c2.y);
-                a.jbias[j] = make_float2(jc.bias.x, jc.bias.y);
-                a.jp[j] = make_float2(pacc.x, pacc.y);
             }
             if (!(r1 & VSTATIC)) io.put(b.x, w1, e1 + 1);
             if (!(r2 & VSTATIC)) io.put(b.y, w2, e2 + 1);
@@ -1233,6 +1263,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
         a.pose[i] = p;
         a.force[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+    if (tid == 0 && !aborted && *(volatile int*)&cn->err == 0) cn->steps_done++;
     stamp(7);
 }
 
@@ -1296,7 +1327,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     int tq_ = 32;
     auto tstamp = [&]() { if (a.dbg && bid == a.probe_cta && lt == 0 && tq_ < 48) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[tq_++] = t; } };
     // a step that already failed in the broad phase (capacity) has holes in its arbiter arrays: nothing to solve, error reported
-    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;
+    if (step_failed(cn)) return;
     color_new_arbiters<true>(a, cn, bar, bar_target);
     stamp(1);
     tstamp();
@@ -1476,7 +1507,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         }
     }
     __syncthreads();
-    if (!a.run_solver) return;
+    if (!a.run_solver) {
+        if (tid == 0 && !step_failed(cn)) cn->steps_done++;  // (a failed set-up is reported; nothing else depends on it here)
+        return;
+    }
     const bool bad = s_bad != 0;  // this CTA cannot solve; the error is flagged, the grid barrier below is still joined
     const int ngb = bad ? 0 : ngb_found;
     const int L = bad ? 0 : s_L, ncl = bad ? 0 : s_ncl, nint = bad ? 0 : s_nint, nbnd = bad ? 0 : s_nbnd;  // (a CTA that cannot solve idles through the passes)
@@ -1721,6 +1755,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         a.pose[b] = p;
         a.force[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
+    if (tid == 0) cn->steps_done++;  // (past the barrier above every CTA has seen err == 0)
     stamp(7);
 }
 
@@ -1735,8 +1770,9 @@ __device__ __forceinline__ unsigned morton_spread(unsigned v) {  // 0b abcdefg -
     v = (v | (v << 1)) & 0x5555u;
     return v;
 }
-__global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* pose, int* perm, int* key_tmp) {
+__global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* pose, int* perm, int* key_tmp, const Counters* cn) {
     extern __shared__ int s_hist[];  // SORT_CELLS + 1
+    if (step_failed(cn)) return;
     __shared__ float s_red[4][32];
     __shared__ int s_scan2[34];
     const int lt = threadIdx.x, T = blockDim.x, lane = lt & 31, wid = lt >> 5;
@@ -1830,9 +1866,10 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* p
 // floored at the average weight so that no region gets more than twice the average number of bodies (k_solve_regions
 // keeps a region's bodies in shared memory).  Regions are consecutive runs of `perm`, so perm itself is the CSR body list.
 __global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const int* perm, const int* old_row_start, int B_old, int* region_of, int* lidx,
-                                                            int* reg_start) {
+                                                            int* reg_start, const Counters* cn) {
     __shared__ long long sh[34];
     __shared__ int s_first[1025];
+    if (step_failed(cn)) return;
     const int lt = threadIdx.x, T = blockDim.x;
     const int chunk = (B + T - 1) / T, q0 = min(lt * chunk, B), q1 = min(q0 + chunk, B);
     auto weight = [&](int b) -> long long { return (old_row_start && b < B_old) ? 1 + 2 * max(0, __ldg(&old_row_start[b + 1]) - __ldg(&old_row_start[b])) : 1; };
@@ -1861,6 +1898,13 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const
     __syncthreads();
     for (int g = lt; g <= G; g += T) reg_start[g] = s_first[g];
     for (int i = q0; i < q1; i++) { const int b = perm[i]; lidx[b] = i - s_first[region_of[b]]; }
+}
+
+// the flags a step used become the "old" flags of the next one — unless the step failed (it will be repeated)
+__global__ void k_copy_flags(int B, const int* src, int* dst, const Counters* cn) {
+    if (step_failed(cn)) return;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < B) dst[i] = src[i];
 }
 
 __global__ void k_collide_pairs(int n, const SyltBodyDesc* A, const SyltBodyDesc* Bd, const float2* lverts, const int* loff,
@@ -1997,6 +2041,13 @@ struct SyltWorld {
 
     int64_t cap_pairs = 0, cap_arb = 0, cap_con = 0;
     int64_t user_pairs = 0, user_arb = 0, user_con = 0;
+    int64_t grow_pairs = 0, grow_arb = 0, grow_con = 0;  // raised automatically when a step overflowed (the step is then repeated)
+    // the steps enqueued since the last finish(): what to repeat when one of them fails for lack of capacity
+    struct Segment { float dt; int n; bool full; };
+    std::vector<Segment> segs;
+    int call_cur0 = 0, call_B_old0 = 0;
+    bool call_have_old0 = false, call_flags_stale0 = false;
+    int n_arb_valid = 0, n_con_valid = 0;  // size of the arbiter set sylt_world_get_arbiters reads (the last set that was completed)
     unsigned epoch = 1;
     Counters last{};         // counters of the last completed step
     bool have_last = false;
@@ -2182,8 +2233,8 @@ int flush(SyltWorld* w) {
             SYLT_CUDA(cudaMemsetAsync(w->scan_ticket.p, 0, sizeof(int), w->stream));
         }
         SYLT_CUDA(w->counters.ensure(1));
-        if (w->have_old && w->B_old > 0)  // keep the flags the last step used for the next arbiter match
-            SYLT_CUDA(cudaMemcpyAsync(w->bflags_old.p, w->bflags.p, (size_t)w->B_old * sizeof(int), cudaMemcpyDeviceToDevice, w->stream));
+        if (w->have_old && w->B_old > 0 && !w->flags_stale)  // keep the flags the last step used for the next arbiter match
+            SYLT_CUDA(cudaMemcpyAsync(w->bflags_old.p, w->bflags.p, (size_t)w->B_old * sizeof(int), cudaMemcpyDeviceToDevice, w->stream));  // (flags_stale: bflags_old already holds them)
         SYLT_CUDA(cudaMemcpyAsync(w->bflags.p, fl.data(), B * sizeof(int), cudaMemcpyHostToDevice, w->stream));
         w->flags_stale = true;
         if (!large.empty()) SYLT_CUDA(cudaMemcpyAsync(w->large.p, large.data(), large.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
@@ -2192,6 +2243,7 @@ int flush(SyltWorld* w) {
         int64_t ca = w->user_arb ? w->user_arb : std::max<int64_t>(8 * (int64_t)B, 2048);
         int64_t cc = w->user_con ? w->user_con : std::max<int64_t>(16 * (int64_t)B, 4096);
         if (w->any_poly && !w->user_con) cc *= 2;
+        cp = std::max(cp, w->grow_pairs); ca = std::max(ca, w->grow_arb); cc = std::max(cc, w->grow_con);  // a step overflowed before
         const int maxc = w->any_poly ? MAX_MANIFOLD : 2;
         SYLT_CUDA(w->pairs.ensure((size_t)cp));
         SYLT_CUDA(w->info.ensure((size_t)cp + 1));
@@ -2215,8 +2267,8 @@ int flush(SyltWorld* w) {
         for (int k = 0; k < 2; k++) {
             SyltWorld::ArbBufs& a = w->arb[k];
             const bool keep_set = (k != w->cur) && w->have_old && w->have_last;  // last step's arbiters survive a regrow
-            size_t ka = keep_set ? (size_t)std::min<int64_t>(w->last.n_arb, w->cap_arb) : 0;
-            size_t kc = keep_set ? (size_t)std::min<int64_t>(w->last.n_con, w->cap_con) : 0;
+            size_t ka = keep_set ? (size_t)std::min<int64_t>(w->n_arb_valid, w->cap_arb) : 0;
+            size_t kc = keep_set ? (size_t)std::min<int64_t>(w->n_con_valid, w->cap_con) : 0;
             SYLT_CUDA(a.bodies.ensure((size_t)ca, ka, w->stream));
             SYLT_CUDA(a.meta.ensure((size_t)ca, ka, w->stream));
             SYLT_CUDA(a.partner.ensure((size_t)ca, ka, w->stream));
@@ -2318,11 +2370,11 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
     if (e) return e;
     mark();
-    SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp));
+    SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp, cn));
     mark();
     const int nbR = (B + 127) / 128;
     SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B + 3) / 4)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
-                         (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p));
+                         (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p, cn));
     w->launches += 2;
     mark();
     e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->sincl32.p, 0, 1);
@@ -2347,10 +2399,10 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
     if (w->regions_on && (w->resort_pending || (full_step && w->steps_since_part >= w->regions_period))) {
         // (re)partition by the current positions and last step's load (device side, no synchronisation); the colours encode the old cut
-        k_resort<<<1, REBAL_THREADS, (SORT_CELLS + 1) * sizeof(int), st>>>(B, w->pose.p, w->reg_bodies.p, w->sort_keys.p);
+        k_resort<<<1, REBAL_THREADS, (SORT_CELLS + 1) * sizeof(int), st>>>(B, w->pose.p, w->reg_bodies.p, w->sort_keys.p, cn);
         SYLT_CUDA(cudaGetLastError());
         k_rebalance<<<1, REBAL_THREADS, 0, st>>>(B, w->n_regions, w->reg_bodies.p, w->have_old ? old.row_start : nullptr, w->B_old, w->region_of.p,
-                                                 w->lidx.p, w->reg_start.p);
+                                                 w->lidx.p, w->reg_start.p, cn);
         SYLT_CUDA(cudaGetLastError());
         w->launches += 2;
         w->steps_since_part = 0;
@@ -2456,38 +2508,114 @@ void print_solver_timing(SyltWorld* w) {
             (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
 }
 
-// After the queue drains: read the counters of the last step and update host-side bookkeeping.
-int finish(SyltWorld* w) {
-    SYLT_CUDA(cudaStreamSynchronize(w->stream));
-    if (!w->inflight) return w->have_last ? w->last.err : SYLT_OK;
-    SYLT_CUDA(cudaMemcpy(&w->last, w->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
-    w->inflight = false;
-    w->have_last = true;
-    if (w->last_regions) {
-        if (w->last.err == SYLT_ERR_CAPACITY && w->last.why != 0) {  // a region outgrew k_solve_regions' tables: this world goes on with k_solve
-            w->regions_mode = 0;
-            w->part_dirty = true;
+// Enqueue the steps of `segs` (no host synchronisation).
+int enqueue_segments(SyltWorld* w, const std::vector<SyltWorld::Segment>& segs) {
+    const int B = (int)w->hb.size();
+    for (const SyltWorld::Segment& sg : segs)
+        for (int s = 0; s < sg.n; s++) {
+            int e = enqueue_step(w, sg.dt, sg.full);
+            if (e) return e;
+            w->inflight = true;
+            w->inflight_full = sg.full;
+            if (B > 0) {
+                w->have_old = true;  // the set just built is what the next step matches against
+                w->B_old = B;
+                if (w->flags_stale) {  // the flags this step used become the "old" flags of the next one (unless the step fails)
+                    k_copy_flags<<<(B + 255) / 256, 256, 0, w->stream>>>(B, w->bflags.p, w->bflags_old.p, w->counters.p);
+                    SYLT_CUDA(cudaGetLastError());
+                    w->launches++;
+                    w->flags_stale = false;
+                }
+            }
         }
-        w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
-    }
-    if (w->timing) print_solver_timing(w);
-    if (w->kt_n > 1) {  // SYLT_KERNEL_TIMING: the last step's launches
-        static const char* names[] = {"prepare", "scan cells", "fill cells", "rows count", "scan rows", "rows emit", "narrow", "scan pairs", "(re-cut +) build", "solve"};
-        fprintf(stderr, "kernels [us]:");
-        for (int k = 1; k < w->kt_n; k++) {
-            float ms = 0.0f;
-            cudaEventElapsedTime(&ms, w->kt_ev[k - 1], w->kt_ev[k]);
-            fprintf(stderr, " %s %.1f", k - 1 < 10 ? names[k - 1] : "?", ms * 1e3f);
-        }
-        fprintf(stderr, "\n");
-    }
-    w->last_was_step = w->inflight_full;
-    w->last_iterations = w->iterations;
-    return w->last.err;
+    return SYLT_OK;
 }
 
-int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
-    if (!w) return SYLT_ERR_INVALID;
+int prepare_call(SyltWorld* w);
+
+// After the queue drains: read the counters of the last step and update host-side bookkeeping.  A step that failed for lack
+// of capacity changed nothing (every kernel after the overflow returned at once, and so did the steps enqueued behind it): the
+// buffers are grown from the counts the failed step reported and the remaining steps of the call are run again.  The reference
+// has no such limit (a HashMap, src/world.rs:24), so to the caller the overflow never happened.
+int finish(SyltWorld* w) {
+    for (int attempt = 0;; attempt++) {
+        SYLT_CUDA(cudaStreamSynchronize(w->stream));
+        if (!w->inflight) return w->have_last ? w->last.err : SYLT_OK;
+        SYLT_CUDA(cudaMemcpy(&w->last, w->counters.p, sizeof(Counters), cudaMemcpyDeviceToHost));
+        w->inflight = false;
+        w->have_last = true;
+        if (w->last_regions) w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
+        if (w->timing) print_solver_timing(w);
+        if (w->kt_n > 1) {  // SYLT_KERNEL_TIMING: the last step's launches
+            static const char* names[] = {"prepare", "scan cells", "fill cells", "rows count", "scan rows", "rows emit", "narrow", "scan pairs", "(re-cut +) build", "solve"};
+            fprintf(stderr, "kernels [us]:");
+            for (int k = 1; k < w->kt_n; k++) {
+                float ms = 0.0f;
+                cudaEventElapsedTime(&ms, w->kt_ev[k - 1], w->kt_ev[k]);
+                fprintf(stderr, " %s %.1f", k - 1 < 10 ? names[k - 1] : "?", ms * 1e3f);
+            }
+            fprintf(stderr, "\n");
+        }
+        w->last_was_step = w->inflight_full;
+        w->last_iterations = w->iterations;
+        const int err = w->last.err;
+        int total = 0;
+        for (const auto& sg : w->segs) total += sg.n;
+        if (err == SYLT_OK) {
+            w->n_arb_valid = (int)std::min<int64_t>(w->last.n_arb, w->cap_arb);
+            w->n_con_valid = (int)std::min<int64_t>(w->last.n_con, w->cap_con);
+            w->segs.clear();
+            return SYLT_OK;
+        }
+        // ---- a step of this call failed: the steps behind it did not run.  Put the host-side bookkeeping where the device is.
+        const int completed = std::max(0, std::min(w->last.steps_done, total));
+        const int ran = completed + (err == SYLT_ERR_NO_INVERSE ? 1 : 0);  // a NoInverse step keeps its arbiter set (world.rs:110-129 ran)
+        if (!w->hb.empty()) {
+            w->cur = w->call_cur0 ^ (ran & 1);
+            if (ran == 0) { w->have_old = w->call_have_old0; w->B_old = w->call_B_old0; w->flags_stale = w->call_flags_stale0; }
+        }
+        w->cells_clean = false;
+        if (w->regions_on) w->resort_pending = true;  // a re-cut enqueued behind the failure was skipped: cut (and recolour) again
+        if (err == SYLT_ERR_NO_INVERSE) {
+            w->n_arb_valid = (int)std::min<int64_t>(w->last.n_arb, w->cap_arb);
+            w->n_con_valid = (int)std::min<int64_t>(w->last.n_con, w->cap_con);
+        }
+        std::vector<SyltWorld::Segment> rest;  // the steps that did not run
+        {
+            int skip = completed;
+            for (const auto& sg : w->segs) {
+                const int take = std::min(skip, sg.n);
+                skip -= take;
+                if (sg.n > take) rest.push_back({sg.dt, sg.n - take, sg.full});
+            }
+        }
+        w->segs.clear();
+        if (err != SYLT_ERR_CAPACITY || attempt >= 8) return err;
+        bool grown = false;
+        if (w->last.n_pairs > w->cap_pairs) { w->grow_pairs = std::max<int64_t>(2 * w->cap_pairs, (int64_t)w->last.n_pairs * 3 / 2); grown = true; }
+        if (w->last.n_arb > w->cap_arb) { w->grow_arb = std::max<int64_t>(2 * w->cap_arb, (int64_t)w->last.n_arb * 3 / 2); grown = true; }
+        if (w->last.n_con > w->cap_con) { w->grow_con = std::max<int64_t>(2 * w->cap_con, (int64_t)w->last.n_con * 3 / 2); grown = true; }
+        if (w->last_regions && w->last.why != 0) {  // a region outgrew k_solve_regions' tables: this world goes on with k_solve
+            w->regions_mode = 0;
+            w->part_dirty = true;
+            grown = true;
+        }
+        if (w->user_pairs && w->grow_pairs > w->user_pairs) w->user_pairs = 0;  // an explicit capacity is a starting point, not a limit
+        if (w->user_arb && w->grow_arb > w->user_arb) w->user_arb = 0;
+        if (w->user_con && w->grow_con > w->user_con) w->user_con = 0;
+        if (!grown) return err;  // nothing a larger buffer would cure (> 64 colours at a body, a polygon manifold over the cap)
+        w->class_dirty = true;
+        int e = prepare_call(w);
+        if (e) return e;
+        w->segs = rest;
+        e = enqueue_segments(w, rest);
+        if (e) return e;
+    }
+}
+
+// Everything that has to happen on the host before steps are enqueued: uploads, (re)allocation, the solver choice; and the
+// snapshot of the bookkeeping a failed step restores.
+int prepare_call(SyltWorld* w) {
     int e = flush(w);
     if (e) return e;
     if (body_order_violated(w->hb)) return SYLT_ERR_BODY_ORDER;
@@ -2495,22 +2623,22 @@ int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
         e = repartition(w);
         if (e) return e;
     }
-    if (!w->inflight) SYLT_CUDA(cudaMemsetAsync(w->counters.p, 0, offsetof(Counters, n_pairs), w->stream));  // sticky error fields
-    const int B = (int)w->hb.size();
-    for (int s = 0; s < n; s++) {
-        e = enqueue_step(w, dt, full);
-        if (e) return e;
-        w->inflight = true;
-        w->inflight_full = full;
-        if (B > 0) {
-            w->have_old = true;  // the set just built is what the next step matches against
-            w->B_old = B;
-            if (w->flags_stale) {  // the flags this step used become the "old" flags of the next one
-                SYLT_CUDA(cudaMemcpyAsync(w->bflags_old.p, w->bflags.p, (size_t)B * sizeof(int), cudaMemcpyDeviceToDevice, w->stream));
-                w->flags_stale = false;
-            }
-        }
+    if (!w->inflight) {
+        SYLT_CUDA(cudaMemsetAsync(w->counters.p, 0, offsetof(Counters, n_pairs), w->stream));  // sticky error fields, steps_done
+        w->segs.clear();
+        w->call_cur0 = w->cur; w->call_have_old0 = w->have_old; w->call_B_old0 = w->B_old; w->call_flags_stale0 = w->flags_stale;
     }
+    return SYLT_OK;
+}
+
+int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
+    if (!w) return SYLT_ERR_INVALID;
+    int e = prepare_call(w);
+    if (e) return e;
+    std::vector<SyltWorld::Segment> sg = {{dt, n, full}};
+    w->segs.push_back(sg[0]);
+    e = enqueue_segments(w, sg);
+    if (e) return e;
     if (!wait) return SYLT_OK;
     return finish(w);
 }
@@ -2630,6 +2758,7 @@ int sylt_world_clear(SyltWorld* w) {  // world.rs:67-71
     w->uploaded = 0; w->class_dirty = true; w->joints_dirty = true; w->any_poly = false; w->n_large = 0;
     w->have_old = false; w->B_old = 0; w->have_last = false; w->n_joint_colors = 0; w->inflight = false; w->flags_stale = false;
     w->regions_on = false; w->part_dirty = true; w->recolor_all = false; w->last_regions = false;
+    w->segs.clear(); w->n_arb_valid = 0; w->n_con_valid = 0;
     memset(&w->last, 0, sizeof w->last);
     return SYLT_OK;
 }
@@ -2774,8 +2903,8 @@ int sylt_world_add_force(SyltWorld* w, int32_t body, float fx, float fy) {  // b
 
 int sylt_world_num_bodies(SyltWorld* w) { return w ? (int)w->hb.size() : 0; }
 int sylt_world_num_joints(SyltWorld* w) { return w ? (int)w->hj.size() : 0; }
-int sylt_world_num_arbiters(SyltWorld* w) { return (w && w->have_last) ? (int)std::min<int64_t>(w->last.n_arb, w->cap_arb) : 0; }
-int sylt_world_num_contacts(SyltWorld* w) { return (w && w->have_last) ? (int)std::min<int64_t>(w->last.n_con, w->cap_con) : 0; }
+int sylt_world_num_arbiters(SyltWorld* w) { return (w && w->have_last) ? w->n_arb_valid : 0; }
+int sylt_world_num_contacts(SyltWorld* w) { return (w && w->have_last) ? w->n_con_valid : 0; }
 
 int sylt_world_get_bodies(SyltWorld* w, SyltBodyState* out, int32_t cap) {
     if (!w || (!out && cap > 0)) return -SYLT_ERR_INVALID;

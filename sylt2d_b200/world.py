@@ -145,6 +145,10 @@ class World:
         check(self.L.sylt_world_set_joint_params(self.h, idx.value, joint.softness, joint.bias_factor))
         return idx.value
 
+    def set_joint_params(self, joint_index, softness, bias_factor):
+        """The pub fields Joint.softness / Joint.bias_factor of a joint already in the world (src/joint.rs:17-18)."""
+        check(self.L.sylt_world_set_joint_params(self.h, int(joint_index), softness, bias_factor))
+
     def load_scene(self, scene):
         """Bulk add (sylt_world_add_bodies / add_joints) of a scenes.Scene."""
         check(self.L.sylt_world_set_iterations(self.h, scene.iterations))

@@ -778,3 +778,137 @@ def test_region_solver_survives_a_body_shot_far_away(monkeypatch):
         _assert_states_equal(w.get_bodies(), o.get_bodies(), f"outlier step {s}")
     ga, _ = w.get_arbiters()
     assert ga.shape[0] > 2000 and (ga["color"] < 32).mean() > 0.6
+
+
+# ------------------------------------------------------------------ error paths: exact state after Err, transparent capacity growth
+def _bridge_with_static_joint(iterations=10, softness=1.0):
+    """The suspension bridge (16 plank-to-ground joints) with a joint between two STATIC bodies in the middle of the joint Vec:
+    with softness > 0 its K = softness * I is invertible, with softness == 0 it is the zero matrix (NoInverse, quirk Q-15)."""
+    sc = scenes.bridge(iterations)
+    bodies = np.concatenate([sc.bodies, sc.bodies[:1].copy()])
+    bodies["id"][-1] = bodies["id"].max() + 1
+    bodies["x"][-1], bodies["y"][-1] = 40.0, 30.0           # a second static body, far away from everything
+    extra = np.zeros(1, dtype=scenes.JOINT_DESC)
+    extra["id1"], extra["id2"] = bodies["id"][0], bodies["id"][-1]
+    extra["anchor_x"], extra["anchor_y"], extra["softness"], extra["bias_factor"] = 20.0, 10.0, softness, 0.2
+    joints = np.concatenate([sc.joints[:8], extra, sc.joints[8:]])
+    return scenes.Scene("bridge+static-joint", bodies, joints, sc.verts, sc.gravity, sc.iterations, sc.dt, sc.ctx), 8
+
+
+def _assert_joints_equal(gj, rj, what):
+    for f in gj.dtype.names:
+        assert np.array_equal(gj[f], rj[f]), f"{what}: joint field {f} differs: {gj[f]} vs {rj[f]}"
+
+
+def test_no_inverse_mid_step_state_matches_reference_semantics():
+    """World::step returns Err at the first joint (Vec order) whose K is singular (world.rs:127-129): force integration, every
+    arbiter pre-step and the joints BEFORE it have happened, the joints behind it, the iterations and the integration have not.
+    The state after the error — bodies, forces, every joint field, the matrix — must equal the oracle's, step after step."""
+    from sylt2d_b200 import SyltError
+    sc, jbad = _bridge_with_static_joint()
+    w, o = _mk(sc)
+    for s in range(25):                                    # warm starting is on: the joints accumulate impulses
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+    _assert_states_equal(w.get_bodies(), o.get_bodies(), "before the error")
+    w.set_joint_params(jbad, 0.0, 0.2)                     # the caller writes the pub field: K becomes the zero matrix
+    o.set_joint_params(jbad, 0.0, 0.2)
+    w.add_force(3, (5.0, -2.0))                            # forces are NOT cleared by a failed step (world.rs:148-149 is not reached)
+    o.add_force(3, (5.0, -2.0))
+    for rep in range(3):
+        with pytest.raises(SyltError) as ei:
+            w.step(sc.dt)
+        assert ei.value.code == 1
+        keys, jo = w.solve_order()
+        with pytest.raises(orc.OracleError) as eo:
+            o.step_ordered(sc.dt, keys, jo)
+        assert eo.value.code == 1
+        g, r = w.get_bodies(), o.get_bodies()
+        for f in g.dtype.names:                            # incl. fx, fy, torque
+            assert np.array_equal(g[f], r[f]), f"after Err #{rep}: {f}"
+        _assert_joints_equal(w.get_joints(), o.get_joints(), f"after Err #{rep}")
+        _assert_arbiters_equal(w, o, solve_fields=False, what=f"after Err #{rep}")
+        jg, mg = w.last_error_matrix()
+        jr_, mr = o.last_error_matrix()
+        assert jg == jr_ == jbad and np.array_equal(mg, mr)
+    # the joints behind the failing one kept the impulses of the last good step; the ones before it were warm-started again
+    gj = w.get_joints()
+    assert np.abs(gj["px"][jbad + 1:]).max() > 0 and np.abs(gj["px"][:jbad]).max() > 0
+    # step_n stops at the first Err, exactly like a caller's `for _ in 0..n { world.step(dt)?; }`
+    w2, o2 = _mk(sc)
+    w2.step_n(sc.dt, 25)
+    w2.set_joint_params(jbad, 0.0, 0.2)
+    w3, _ = _mk(sc)
+    w3.step_n(sc.dt, 25)
+    w3.set_joint_params(jbad, 0.0, 0.2)
+    with pytest.raises(SyltError):
+        w2.step_n(sc.dt, 4)
+    with pytest.raises(SyltError):
+        w3.step(sc.dt)
+    _assert_states_equal(w2.get_bodies(), w3.get_bodies(), "step_n after Err")
+    # the repaired world steps on (softness back to 1)
+    w.set_joint_params(jbad, 1.0, 0.2)
+    o.set_joint_params(jbad, 1.0, 0.2)
+    for s in range(5):
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"after the repair, step {s}")
+
+
+def test_no_inverse_in_a_batch_world_matches_oracle():
+    from sylt2d_b200 import Batch
+    sc, jbad = _bridge_with_static_joint(softness=0.0)     # singular from the first step
+    bodies, boff, joints, joff = scenes.tile_worlds(sc, 3, seed=1, omega_jitter=0.5)
+    b = Batch(bodies, boff, joints, joff, sc.gravity, sc.iterations, device=0, ctx=sc.ctx)
+    b.step_n(sc.dt, 2)
+    assert (b.get_errors() == 1).all()
+    nb = sc.num_bodies
+    for wi in range(3):
+        o = orc.OracleWorld(sc.gravity, sc.iterations, sincos_mode=1)
+        o.load_scene(scenes.Scene(sc.name, bodies[wi * nb:(wi + 1) * nb], sc.joints, sc.verts, sc.gravity, sc.iterations, sc.dt, sc.ctx))
+        with pytest.raises(orc.OracleError):
+            o.step_ordered(sc.dt, np.zeros((0, 2), dtype=np.uint64), b.get_joint_order(wi))
+        _assert_states_equal(b.get_bodies(wi, 1), o.get_bodies(), f"batch world {wi} after Err")
+        gj, rj = b.get_joints(wi), o.get_joints()
+        for f in ("r1x", "r1y", "r2x", "r2y", "px", "py", "bias_x", "bias_y"):
+            assert np.array_equal(gj[f], rj[f]), (wi, f)
+        assert np.abs(gj["r1x"][:jbad + 1]).max() > 0 and not gj["r1x"][jbad + 1:].any()  # joints behind the failing one: untouched
+
+
+def test_capacity_overflow_is_transparent():
+    """The reference's arbiter container is a HashMap (no limit).  Device buffers that turn out too small are grown and the step
+    is repeated; a failed attempt changes nothing, so the result is bit-identical to a world that never overflowed."""
+    from sylt2d_b200 import World
+    sc = scenes.pyramid(10, 10)
+    w, o = _mk(sc)
+    w.set_capacity(24, 12, 20)                             # far too small for 56 bodies
+    for s in range(70):
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"tiny capacity, step {s}")
+    _assert_arbiters_equal(w, o, what="tiny capacity")
+    assert w.get_stats()["arbiters"] > 60
+    # multi-step calls: the overflow happens in the middle of a step_n; the steps behind it are repeated too
+    ref = World(sc.gravity, sc.iterations)
+    ref.load_scene(sc)
+    ref.step_n(sc.dt, 70)
+    for chunks in ((70,), (20, 50), (5, 5, 60)):
+        v = World(sc.gravity, sc.iterations)
+        v.load_scene(sc)
+        v.set_capacity(24, 12, 20)
+        for n in chunks:
+            v.step_n(sc.dt, n)
+        _assert_states_equal(v.get_bodies(), ref.get_bodies(), f"tiny capacity, step_n chunks {chunks}")
+    # a bigger, region-solved world with polygons
+    sc = scenes.mixed_pile(1500, seed=3)
+    a, bb = World(sc.gravity, sc.iterations), World(sc.gravity, sc.iterations)
+    a.load_scene(sc)
+    bb.load_scene(sc)
+    bb.set_capacity(2000, 600, 900)
+    a.step_n(sc.dt, 90)
+    bb.step_n(sc.dt, 90)
+    _assert_states_equal(a.get_bodies(), bb.get_bodies(), "mixed pile, grown capacity")
+    assert a.get_stats()["arbiters"] == bb.get_stats()["arbiters"] > 600
