@@ -325,6 +325,7 @@ def main():
     ap.add_argument("--settle", type=int, default=150)
     ap.add_argument("--skip-world100k", action="store_true")
     ap.add_argument("--skip-cpu", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="leave the CPU affinity alone (default: bind the rank to its GPU's NUMA node)")
     args = ap.parse_args()
     if args.worlds is None:
         args.worlds = N_WORLDS if args.config == 5 else 8192
@@ -341,6 +342,9 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    # the e2e leg streams every body state through pinned host memory each step: run (and allocate) next to the GPU
+    from sylt2d_b200.numa import bind_to_gpu_numa
+    numa = {"bound": False} if args.no_numa_bind else bind_to_gpu_numa(local_rank)
     use_dist = world_size > 1
     if use_dist:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
@@ -494,7 +498,7 @@ def main():
                    "l2": "per-GPU state (bodies + per-world slot cache) exceeds the 126 MB L2 at N<=2; smaller shards are L2-resident by nature of strong scaling",
                    "contacts_per_world": contacts_total / max(args.worlds, 1), "errors": errors_total},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": my_bodies * 4 * FPB * world_size, "d2h_bytes_per_step": my_bodies * 4 * FPB * world_size,
-                "steps": e2e_steps, "runs_s": e2e_runs,
+                "steps": e2e_steps, "runs_s": e2e_runs, "numa": numa,
                 "api": "sylt_batch_step_host6(dt, 1, in, out): every body state (x, y, rotation, vx, vy, angular_velocity) H2D + one step + every body "
                        "state D2H per step, pinned host buffers, world chunks pipelined over several streams"},
         "gpu_launches": int(launches),

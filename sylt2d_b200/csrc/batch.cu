@@ -72,6 +72,12 @@ struct BatchArgs {
     int *w_err, *w_ncon, *w_narb, *w_ncolors, *w_errjoint;
     float* w_maxpen;
     float4* w_badk;
+    // optional host-format records (sylt_batch_step_host*): the kernel reads its world's bodies from `rec_in` instead of pose / vel
+    // and also writes the result to `rec_out` — rec_floats = 6 (x, y, rotation, vx, vy, w) or 9 (SyltBodyState) floats per body,
+    // indexed by the global body index: no separate unpack / pack launches around the step
+    const float* rec_in;
+    float* rec_out;
+    int rec_floats;
     SlotExport* exp_slots;           // export slots * cap
     int* exp_count;                  // per export slot
     // shared-memory layout: byte offset of every Smem array, computed once on the host (carve) and read from the constant
@@ -313,7 +319,15 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
 
     // ---- load the world
     for (int i = tid; i < B; i += T) {
-        float4 p = a.pose[b0 + i], v = a.vel[b0 + i], m = a.mp[b0 + i];
+        float4 p, v;
+        const float4 m = a.mp[b0 + i];
+        if (a.rec_in) {
+            const float* r = a.rec_in + (size_t)(b0 + i) * a.rec_floats;
+            p = make_float4(r[0], r[1], r[2], 0.0f);
+            v = make_float4(r[3], r[4], r[5], 0.0f);
+        } else {
+            p = a.pose[b0 + i]; v = a.vel[b0 + i];
+        }
         s.pos[i] = make_float2(p.x, p.y); s.rot[i] = p.z; s.vel[i] = v; s.inv[i] = make_float2(m.x, m.y);
         s.stat[i] = a.bflags[b0 + i];
     }
@@ -764,9 +778,16 @@ __global__ void __launch_bounds__(256, 4) k_batch_step(BatchArgs a) {
     __syncthreads();
     const int err = *s_err;
     for (int i = tid; i < B; i += T) {
-        float2 p = s.pos[i];
-        a.pose[b0 + i] = make_float4(p.x, p.y, s.rot[i], 0.0f);
-        a.vel[b0 + i] = s.vel[i];
+        const float2 p = s.pos[i];
+        const float4 v = s.vel[i];
+        const float rt = s.rot[i];
+        a.pose[b0 + i] = make_float4(p.x, p.y, rt, 0.0f);
+        a.vel[b0 + i] = v;
+        if (a.rec_out) {
+            float* r = a.rec_out + (size_t)(b0 + i) * a.rec_floats;
+            r[0] = p.x; r[1] = p.y; r[2] = rt; r[3] = v.x; r[4] = v.y; r[5] = v.z;
+            for (int k = 6; k < a.rec_floats; k++) r[k] = 0.0f;  // SyltBodyState: force / torque (a batch has no external forces)
+        }
     }
     for (int j = tid; j < J; j += T) {
         a.jp[j0 + j] = s.jp[j]; a.jr[j0 + j] = s.jr[j]; a.jm[j0 + j] = s.jm[j]; a.jbias[j0 + j] = s.jbias[j];
@@ -826,24 +847,6 @@ __global__ void k_pack_states(int n, const float4* pose, const float4* vel, Sylt
     float4 p = pose[i], v = vel[i];
     SyltBodyState s = {p.x, p.y, p.z, v.x, v.y, v.z, 0.0f, 0.0f, 0.0f};
     out[i] = s;
-}
-
-// compact 24-byte records (x, y, rotation, vx, vy, angular_velocity): what a caller mirrors every step; forces are
-// inputs only and a batch has none
-__global__ void k_unpack_states6(int n, const float* in, float4* pose, float4* vel) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    const float2* q = (const float2*)(in + 6 * (size_t)i);
-    float2 a = q[0], b = q[1], c = q[2];
-    pose[i] = make_float4(a.x, a.y, b.x, 0.0f);
-    vel[i] = make_float4(b.y, c.x, c.y, 0.0f);
-}
-__global__ void k_pack_states6(int n, const float4* pose, const float4* vel, float* out) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float4 p = pose[i], v = vel[i];
-    float2* q = (float2*)(out + 6 * (size_t)i);
-    q[0] = make_float2(p.x, p.y); q[1] = make_float2(p.z, v.x); q[2] = make_float2(v.y, v.z);
 }
 
 struct StatsOut {
@@ -909,7 +912,7 @@ struct SyltBatch {
     int export_count = 0;             // worlds with full arbiter read-back (<= MAX_EXPORT)
     std::vector<int> h_exp_map;       // per world: export slot or -1
     DBuf<int> exp_map;
-    int last_steps = 0;
+    int last_steps = 0, wave = 0;     // wave: CTAs of k_batch_step the device holds at once
     bool inflight = false;
     std::vector<int> h_body_off, h_joint_off, h_jorder;
     std::vector<uint64_t> h_ids;
@@ -969,6 +972,7 @@ int batch_set_cap(SyltBatch* b, int cap) {
     SYLT_CUDA(cudaFuncSetAttribute(k_batch_step, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     b->cap = cap;
     b->smem = smem;
+    b->wave = 0;
     int t = std::max(b->Bmax, (cap + 1) / 2);
     t = ((t + 31) / 32) * 32;
     b->threads = std::min(256, std::max(32, t));
@@ -981,7 +985,8 @@ int batch_set_cap(SyltBatch* b, int cap) {
     return SYLT_OK;
 }
 
-int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaStream_t st = nullptr) {
+int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaStream_t st = nullptr, const float* rec_in = nullptr,
+                  float* rec_out = nullptr, int rec_floats = 0) {
     if (w1 < 0) w1 = b->n_worlds;
     if (!st) st = b->stream;
     BatchArgs a;
@@ -997,6 +1002,7 @@ int batch_enqueue(SyltBatch* b, float dt, int n, int w0 = 0, int w1 = -1, cudaSt
         memcpy(ptrs, &hs, sizeof(Smem));
         for (size_t i = 0; i < sizeof(Smem) / sizeof(void*); i++) a.smem_off[i] = (unsigned long long)(ptrs[i] - anchor);
     }
+    a.rec_in = rec_in; a.rec_out = rec_out; a.rec_floats = rec_floats;
     a.gx = b->gx; a.gy = b->gy; a.Bmax = b->Bmax; a.Jmax = b->Jmax; a.cap = b->cap; a.nbk = b->nbk; a.cell = b->cell; a.bflags = b->bflags.p;
     a.exp_map = b->exp_map.p;
     a.body_off = b->body_off.p; a.joint_off = b->joint_off.p; a.pose = b->pose.p; a.vel = b->vel.p; a.mp = b->mp.p; a.wh = b->wh.p;
@@ -1244,7 +1250,14 @@ static int step_host_impl(SyltBatch* b, float dt, int32_t n, const float* in, fl
     SYLT_CUDA(b->stage.ensure((size_t)b->n_bodies));
     float* stage = (float*)b->stage.p;  // 9 floats per body of room; the compact layout uses the first 6 * n_bodies floats
     const int W = b->n_worlds;
-    int chunks = std::max(1, std::min(16, W / 512));
+    // chunks: each at least two resident waves of CTAs (a shorter launch leaves SMs idle at its tail), at most 16
+    if (b->wave <= 0) {
+        int per_sm = 1, sms = 1;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_batch_step, b->threads, b->smem);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
+        b->wave = std::max(1, per_sm) * std::max(1, sms);
+    }
+    const int chunks = std::max(1, std::min(16, W / (2 * b->wave)));
     const int per = (W + chunks - 1) / chunks;
     for (int c = 0; c < chunks; c++) {
         const int w0 = std::min(W, c * per), w1 = std::min(W, w0 + per);
@@ -1252,22 +1265,11 @@ static int step_host_impl(SyltBatch* b, float dt, int32_t n, const float* in, fl
         cudaStream_t st = b->xs[c % SyltBatch::NS];
         const int o0 = b->h_body_off[(size_t)w0], cnt = b->h_body_off[(size_t)w1] - o0;
         float* sg = stage + (size_t)o0 * fpb;
-        if (in && cnt) {
-            SYLT_CUDA(cudaMemcpyAsync(sg, in + (size_t)o0 * fpb, (size_t)cnt * fpb * sizeof(float), cudaMemcpyHostToDevice, st));
-            if (fpb == 9) k_unpack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, (const SyltBodyState*)sg, b->pose.p + o0, b->vel.p + o0);
-            else k_unpack_states6<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, sg, b->pose.p + o0, b->vel.p + o0);
-            b->launches++;
-        }
-        if (n > 0) {
-            int e = batch_enqueue(b, dt, n, w0, w1, st);
-            if (e) return e;
-        }
-        if (out && cnt) {
-            if (fpb == 9) k_pack_states<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->pose.p + o0, b->vel.p + o0, (SyltBodyState*)sg);
-            else k_pack_states6<<<(cnt + 255) / 256, 256, 0, st>>>(cnt, b->pose.p + o0, b->vel.p + o0, sg);
-            b->launches++;
-            SYLT_CUDA(cudaMemcpyAsync(out + (size_t)o0 * fpb, sg, (size_t)cnt * fpb * sizeof(float), cudaMemcpyDeviceToHost, st));
-        }
+        if (in && cnt) SYLT_CUDA(cudaMemcpyAsync(sg, in + (size_t)o0 * fpb, (size_t)cnt * fpb * sizeof(float), cudaMemcpyHostToDevice, st));
+        // the step kernel itself reads the host-format records and writes them back (n == 0: zero steps, i.e. a pure conversion)
+        int e = batch_enqueue(b, dt, n, w0, w1, st, (in && cnt) ? stage : nullptr, (out && cnt) ? stage : nullptr, fpb);
+        if (e) return e;
+        if (out && cnt) SYLT_CUDA(cudaMemcpyAsync(out + (size_t)o0 * fpb, sg, (size_t)cnt * fpb * sizeof(float), cudaMemcpyDeviceToHost, st));
     }
     for (int k = 0; k < SyltBatch::NS; k++) SYLT_CUDA(cudaStreamSynchronize(b->xs[k]));
     b->inflight = false;
