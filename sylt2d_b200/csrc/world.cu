@@ -63,6 +63,7 @@ struct Counters {
     int err, err_joint;
     float badk[4];
     int steps_done;  // steps of this call that completed
+    int good_n_arb, good_n_con;  // arbiters / contacts of the last completed step (the set a repeated step matches against)
     // per step (reset by enqueue_step):
     int n_pairs, n_arb, n_con;
     int n_colors, rounds, n_uncolored, warn_ext;
@@ -88,7 +89,15 @@ struct Counters {
 // pdl_trigger() lets the successor start scheduling early.  Without the attribute both are no-ops.
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// Once a step has failed, the kernels that would change persistent state (k_build: the arbiter sets; the solvers: bodies and
+// impulses; the counters) return at once.  The streaming kernels in front of them only write per-step scratch and are NOT gated: a
+// gate is a dependent load at the top of every short-lived warp (measured: +8 us on k_rows_count at 100k bodies).
 __device__ __forceinline__ bool step_failed(const Counters* cn) { return *(volatile const int*)&cn->err != 0; }
+__device__ __forceinline__ void step_completed(Counters* cn) {  // one thread, at the very end of a step
+    cn->steps_done++;
+    cn->good_n_arb = cn->n_arb;
+    cn->good_n_con = cn->n_con;
+}
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
     cudaLaunchConfig_t cfg = {};
@@ -142,6 +151,12 @@ template <typename T>
 __global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, int n_host, const int* n_dev, unsigned* flag, T* agg, T* incl,
                                                                 int* ticket, unsigned epoch, int zero_in, Counters* cn, int totals_mode, int cap_pairs);
 
+// The two prefix sums of the candidate chain (rows -> pairs, pairs -> arbiters / contacts) have no kernel of their own: the
+// producer leaves one total per block of ROW_BLK bodies / PAIR_TILE candidates, and every consumer block adds up the totals in
+// front of it (a few hundred coalesced loads) before the exclusive scan of its own block.
+constexpr int ROW_BLK = 128;     // bodies per k_rows_emit block
+constexpr int PAIR_TILE = 256;   // candidates per tile of k_narrow / k_build
+
 // ------------------------------------------------------------------ broad phase
 struct GridParams {
     float cell;
@@ -159,14 +174,22 @@ __device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
     return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w);
 }
 
+// per-step counters back to zero — unless an earlier step of the call failed: its counts are what the host grows the buffers from
+__global__ void k_reset_counters(Counters* cn) {
+    if (step_failed(cn)) return;
+    int* p = &cn->n_pairs;
+    const int n = (int)((sizeof(Counters) - offsetof(Counters, n_pairs)) / sizeof(int));
+    for (int k = threadIdx.x; k < n; k += blockDim.x) p[k] = 0;
+}
+
 __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const float4* vel, const float4* force, const float4* mp, const float4* geom,
                                                  const int* bflags, const float2* lverts, float2* rotc, float4* aabb, int4* cinfo,
                                                  int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
-                                                 Counters* cn, ulonglong2* vrec, unsigned long long* used, unsigned* used_int) {
+                                                 Counters* cn, ulonglong2* vrec, unsigned long long* used, unsigned* used_int, int* row_btot) {
     pdl_trigger();
-    if (step_failed(cn)) return;  // an earlier step of this call failed: nothing runs any more
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
+    if ((i & (ROW_BLK - 1)) == 0) row_btot[i / ROW_BLK] = 0;  // candidates per block of bodies: accumulated by k_rows_count
     used[i] = 0ull;  // colours taken at this body: rebuilt by k_build / the colouring rounds every step
     used_int[i] = 0u;
     float4 p = pose[i];
@@ -227,7 +250,6 @@ __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, co
                                                     int4* cent_info, float4* cent_aabb, GridParams gp, const Counters* cn) {
     pdl_wait();
     pdl_trigger();
-    if (step_failed(cn)) return;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     int4 ci = cinfo[i];
@@ -310,10 +332,9 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
 // instructions —, 4 lanes 39 us with 40 % of the lanes active.)
 __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
                                                     const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp,
-                                                    const Counters* cn) {
+                                                    const Counters* cn, int* row_btot) {
     pdl_wait();
     pdl_trigger();
-    if (step_failed(cn)) return;
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (g >= B) return;
     int i;
@@ -346,6 +367,7 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
                 cnt++;
             });
             row_count[i] = cnt;
+            if (cnt) atomicAdd(&row_btot[i / ROW_BLK], cnt);
         }
         return;
     }
@@ -398,21 +420,40 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
         if (hit && pos < ROWTMP) tmp[pos] = partner;
         found += __popc(m);
     }
-    if (lane == 0) row_count[i] = found;
+    if (lane == 0) {
+        row_count[i] = found;
+        if (found) atomicAdd(&row_btot[i / ROW_BLK], found);
+    }
 }
 
-__global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
-                                                   const float4* cent_aabb, const int* large, int n_large, GridParams gp, const int* row_start, const int* row_tmp,
-                                                   int2* pairs, int cap_pairs, Counters* cn) {
+__global__ void __launch_bounds__(ROW_BLK) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
+                                                       const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_start, const int* row_tmp,
+                                                       int2* pairs, int cap_pairs, Counters* cn, const int* row_count, const int* row_btot) {
+    __shared__ int sh[34];
     pdl_wait();
     pdl_trigger();
-    if (step_failed(cn)) return;
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int failed = __ldcg(&cn->err);  // (checked where the counters are written: the load overlaps the ones below)
+    const int i = blockIdx.x * ROW_BLK + threadIdx.x;
+    // row_start[i] = candidates owned by the bodies in front of i: the blocks in front of this one (their totals), then this block
+    int before = 0;
+    for (int k = threadIdx.x; k < (int)blockIdx.x; k += ROW_BLK) before += row_btot[k];
+    int blocks_before;
+    block_excl_scan<int>(before, &blocks_before, sh);
+    const int n = i < B ? row_count[i] : 0;
+    int block_total;
+    const int base = blocks_before + block_excl_scan<int>(n, &block_total, sh), end = base + n;
     if (i >= B) return;
-    const int base = row_start[i], end = row_start[i + 1], n = end - base;
+    row_start[i] = base;
+    if (i == B - 1) {  // the grand total (SyltStepStats.candidate_pairs)
+        row_start[B] = end;
+        if (!failed) {  // (a failed step's counts stay: the host grows the buffers from them)
+            cn->n_pairs = end;
+            if (end > cap_pairs) cn->err = SYLT_ERR_CAPACITY;
+        }
+    }
     if (n == 0) return;
     if (end > cap_pairs) {  // the row does not fit: flag and drop
-        atomicExch(&cn->err, SYLT_ERR_CAPACITY);
+        if (!failed) atomicExch(&cn->err, SYLT_ERR_CAPACITY);
         return;
     }
     if (n <= ROWTMP) {
@@ -442,12 +483,17 @@ __global__ void __launch_bounds__(128) k_rows_emit(int B, const float4* aabb, co
 template <int MAXC>
 __global__ void __launch_bounds__(128) k_narrow(const Counters* cn, int cap_pairs, const int2* pairs, const float4* pose, const float2* rotc,
                                                 const float4* geom, const int* bflags, const float2* lverts,
-                                                unsigned long long* info, float4* tmp_a, float2* tmp_b, Counters* cnw) {
+                                                unsigned long long* info, float4* tmp_a, float2* tmp_b, Counters* cnw, unsigned long long* pair_btot) {
+    __shared__ unsigned long long sh[34];
     pdl_wait();
     pdl_trigger();
-    if (step_failed(cn)) return;
-    int P = min(cn->n_pairs, cap_pairs);
-    for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < P; p += gridDim.x * blockDim.x) {
+    const int failed = __ldcg(&cn->err);  // same cache line as n_pairs: no extra round trip
+    int P = min(__ldcg(&cn->n_pairs), cap_pairs);
+    if (failed) return;
+    const int ntiles = (P + PAIR_TILE - 1) / PAIR_TILE;
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    unsigned long long tile_sum = 0ull;  // (arbiters << 32 | contacts) of this thread's candidates
+    for (int p = tile * PAIR_TILE + threadIdx.x; p < min(P, (tile + 1) * PAIR_TILE); p += blockDim.x) {
         int2 pr = pairs[p];
         int a = min(pr.x, pr.y), b = max(pr.x, pr.y);  // Arbiter::new: body1 = lower id (arbiter.rs:120-122)
         float4 pa = pose[a], pb = pose[b];
@@ -470,10 +516,15 @@ __global__ void __launch_bounds__(128) k_narrow(const Counters* cn, int cap_pair
             if (ovf) atomicExch(&cnw->err, SYLT_ERR_CAPACITY);
         }
         info[p] = n > 0 ? ((1ull << 32) | (unsigned)n) : 0ull;
+        tile_sum += n > 0 ? ((1ull << 32) | (unsigned)n) : 0ull;
         for (int k = 0; k < n; k++) {
             tmp_a[(size_t)p * MAXC + k] = make_float4(out[k].px, out[k].py, out[k].nx, out[k].ny);
             tmp_b[(size_t)p * MAXC + k] = make_float2(out[k].sep, __uint_as_float(out[k].feat));
         }
+    }
+    unsigned long long tot;
+    block_excl_scan<unsigned long long>(tile_sum, &tot, sh);
+    if (threadIdx.x == 0) pair_btot[tile] = tot;
     }
 }
 
@@ -497,26 +548,43 @@ __device__ __forceinline__ void pair_owner(int a, int b, int fa, int fb, int* ow
 
 template <int MAXC>
 __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int cap_arb, int cap_con, int B, int B_old, int have_old,
-                                               const int2* pairs, const unsigned long long* info, const unsigned long long* scan,
+                                               const int2* pairs, const unsigned long long* info, unsigned long long* scan, const unsigned long long* pair_btot,
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
                                                unsigned long long* used, int* uncolored, int fix_features, int keep_colors, unsigned* used_int, int regions) {
     pdl_wait();
-    if (step_failed(cn)) return;
-    int P = min(cn->n_pairs, cap_pairs);
+    const int failed = __ldcg(&cn->err);
+    int P = min(__ldcg(&cn->n_pairs), cap_pairs);
+    if (failed) return;  // (the set "being built" by a step behind a failed one is the last good set: it must not be touched)
     int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     __shared__ int s_hist[NCX];
+    __shared__ unsigned long long s_sc[34];
     if (threadIdx.x < NCX) s_hist[threadIdx.x] = 0;
     __syncthreads();
-    for (int i = tid; i <= B; i += nth) {
-        int rs = i < B ? min(row_start[i], P) : P;
-        cur.row_start[i] = (int)(scan[rs] >> 32);
-    }
-    for (int p = tid; p < P; p += nth) {
-        unsigned long long in = info[p];
+    (void)tid; (void)nth;
+    // Candidates in tiles of PAIR_TILE: (arbiter, contact) offset of a candidate = the tiles in front (k_narrow's totals) + the
+    // exclusive scan inside the tile.  The offsets are also stored (scan[p]): the solver kernel turns them into the per-body arbiter rows.
+    const int ntiles = (P + PAIR_TILE - 1) / PAIR_TILE;
+    for (int tile = blockIdx.x; tile < max(ntiles, 1); tile += gridDim.x) {
+    unsigned long long before = 0ull;
+    for (int k = threadIdx.x; k < tile; k += blockDim.x) before += pair_btot[k];
+    unsigned long long run;
+    block_excl_scan<unsigned long long>(before, &run, s_sc);
+    for (int p0 = tile * PAIR_TILE; p0 < (tile + 1) * PAIR_TILE; p0 += blockDim.x) {  // block-uniform trip count
+        const int p = p0 + threadIdx.x;
+        const unsigned long long in = p < P ? info[p] : 0ull;
+        unsigned long long part;
+        const unsigned long long s = run + block_excl_scan<unsigned long long>(in, &part, s_sc);
+        run += part;
+        if (p < P) scan[p] = s;
+        if (p == P - 1 || (P == 0 && p == 0)) {  // the grand totals
+            const unsigned long long total = P > 0 ? s + in : 0ull;
+            scan[P] = total;
+            cn->n_arb = (int)(total >> 32);
+            cn->n_con = (int)(unsigned)total;
+        }
         if (!in) continue;
         int n = (int)(unsigned)in;
-        unsigned long long s = scan[p];
         int a = (int)(s >> 32), coff = (int)(unsigned)s;
         if (a >= cap_arb || coff + n > cap_con) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); continue; }
         int2 pr = pairs[p];
@@ -583,8 +651,18 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
             uncolored[atomicAdd(&cn->n_uncolored, 1)] = a;
         }
     }
+    }
     __syncthreads();
     if (threadIdx.x < NCX && s_hist[threadIdx.x]) atomicAdd(&cn->color_count[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+// The arbiter rows of the bodies (ArbSet::row_start: first arbiter owned by body i) from the candidate rows and the candidate ->
+// arbiter offsets k_build stored; run by the solver kernels before their first grid barrier.
+__device__ __forceinline__ void fill_arbiter_rows(int B, int P, const int* row_start, const unsigned long long* scan, int* arow, int tid, int nth) {
+    for (int i = tid; i <= B; i += nth) {
+        const int rs = i < B ? min(row_start[i], P) : P;
+        arow[i] = (int)(__ldcg(&scan[rs]) >> 32);
+    }
 }
 
 template <typename T>
@@ -602,8 +680,6 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, i
         s_tile = t;
     }
     __syncthreads();
-    if (step_failed(cn)) return;  // (after the ticket: the counter must be back at zero for the next launch; err cannot change while
-                                  //  tiles wait for one another — only the last tile of a scan ever sets it)
     const int tile = s_tile;
     const int ntiles = max(1, (n + SCAN_TILE - 1) / SCAN_TILE);
     if (tile >= ntiles) return;
@@ -714,6 +790,10 @@ struct SolveArgs {
     ulonglong2* xrec;                                      // export planes (one per pass) of versioned boundary-body velocities
     unsigned step_tag;
     int probe_cta;                                         // diagnostics: the CTA whose set-up phases are stamped
+    // candidate rows + candidate -> (arbiter, contact) offsets of this step (fill_arbiter_rows)
+    const int* cand_row_start;
+    const unsigned long long* pscan;
+    int cap_pairs;
 };
 
 // ---- light grid barrier: one monotonic counter, release-add on arrival, acquire-poll until everybody arrived.
@@ -893,6 +973,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     };
     stamp(0);
     if (step_failed(cn)) return;  // grid-uniform: err only changes inside this kernel from here on
+    fill_arbiter_rows(a.B, min(*(volatile int*)&cn->n_pairs, a.cap_pairs), a.cand_row_start, a.pscan, a.cur.row_start, tid, nth);  // (for the next step's k_build)
     // The first joint in Vec order whose K is singular is where World::step returns Err (world.rs:127-129, quirk Q-15); K depends
     // on the poses only, so it is known before anything is pre-stepped.  (Visible to everybody after the barrier below.)
     for (int j = tid; j < a.J; j += nth) {
@@ -956,7 +1037,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     }
     grid_barrier(bar, bar_target);
     if (!a.run_solver) {
-        if (tid == 0 && !step_failed(cn)) cn->steps_done++;
+        if (tid == 0 && !step_failed(cn)) step_completed(cn);
         return;
     }
     if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // e.g. an arbiter without a free colour: no solve, error reported
@@ -1263,7 +1344,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
         a.pose[i] = p;
         a.force[i] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    if (tid == 0 && !aborted && *(volatile int*)&cn->err == 0) cn->steps_done++;
+    if (tid == 0 && !aborted && *(volatile int*)&cn->err == 0) step_completed(cn);
     stamp(7);
 }
 
@@ -1328,6 +1409,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     auto tstamp = [&]() { if (a.dbg && bid == a.probe_cta && lt == 0 && tq_ < 48) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[tq_++] = t; } };
     // a step that already failed in the broad phase (capacity) has holes in its arbiter arrays: nothing to solve, error reported
     if (step_failed(cn)) return;
+    fill_arbiter_rows(a.B, min(*(volatile int*)&cn->n_pairs, a.cap_pairs), a.cand_row_start, a.pscan, a.cur.row_start, tid, nth);  // read after the barrier of 2a
     color_new_arbiters<true>(a, cn, bar, bar_target);
     stamp(1);
     tstamp();
@@ -1508,7 +1590,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     }
     __syncthreads();
     if (!a.run_solver) {
-        if (tid == 0 && !step_failed(cn)) cn->steps_done++;  // (a failed set-up is reported; nothing else depends on it here)
+        if (tid == 0 && !step_failed(cn)) step_completed(cn);  // (a failed set-up is reported; nothing else depends on it here)
         return;
     }
     const bool bad = s_bad != 0;  // this CTA cannot solve; the error is flagged, the grid barrier below is still joined
@@ -1755,7 +1837,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         a.pose[b] = p;
         a.force[b] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     }
-    if (tid == 0) cn->steps_done++;  // (past the barrier above every CTA has seen err == 0)
+    if (tid == 0) step_completed(cn);  // (past the barrier above every CTA has seen err == 0)
     stamp(7);
 }
 
@@ -1982,7 +2064,8 @@ struct SyltWorld {
     DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, large, row_count, row_start, row_tmp;
     DBuf<int4> cinfo, cent_info;  // cent_info: interleaved (info, AABB) entries of the cell-ordered copy
     DBuf<int2> pairs;
-    DBuf<unsigned long long> info, pscan, claim, spart64;
+    DBuf<unsigned long long> info, pscan, claim, spart64, pair_btot;
+    DBuf<int> row_btot;
     DBuf<int> spart32;
     DBuf<float4> tmp_a;
     DBuf<float2> tmp_b;
@@ -2154,6 +2237,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->cinfo.ensure(B));
         SYLT_CUDA(w->cent_info.ensure(2 * B));
         SYLT_CUDA(w->row_count.ensure(B + 1));
+        SYLT_CUDA(w->row_btot.ensure(B / ROW_BLK + 2));
         SYLT_CUDA(w->row_start.ensure(B + 2));
         SYLT_CUDA(w->row_tmp.ensure(B * ROWTMP));
         SYLT_CUDA(w->used.ensure(B));
@@ -2248,6 +2332,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->pairs.ensure((size_t)cp));
         SYLT_CUDA(w->info.ensure((size_t)cp + 1));
         SYLT_CUDA(w->pscan.ensure((size_t)cp + 2));
+        SYLT_CUDA(w->pair_btot.ensure((size_t)cp / PAIR_TILE + 2));
         SYLT_CUDA(w->spart64.ensure((size_t)cp / SCAN_TILE + 2));
         SYLT_CUDA(w->sincl64.ensure((size_t)cp / SCAN_TILE + 2));
         {
@@ -2356,7 +2441,9 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     auto mark = [&]() { if (ktime && kt_n < 16) { if (!w->kt_ev[kt_n]) cudaEventCreate(&w->kt_ev[kt_n]); cudaEventRecord(w->kt_ev[kt_n++], st); } };
     mark();
     Counters* cn = w->counters.p;
-    SYLT_CUDA(cudaMemsetAsync(&cn->n_pairs, 0, sizeof(Counters) - offsetof(Counters, n_pairs), st));
+    static_assert((sizeof(Counters) - offsetof(Counters, n_pairs)) % sizeof(int) == 0, "Counters: per-step part is a whole number of ints");
+    k_reset_counters<<<1, 256, 0, st>>>(cn);
+    SYLT_CUDA(cudaGetLastError());
     if (B == 0) return SYLT_OK;
     if (!w->cells_clean) {
         SYLT_CUDA(cudaMemsetAsync(w->cell_count.p, 0, w->cell_count.cap * sizeof(int), st));
@@ -2364,7 +2451,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     }
     const int nbB = (B + 255) / 256;
     k_prepare<<<nbB, 256, 0, st>>>(B, w->pose.p, w->vel.p, w->force.p, w->mp.p, w->geom.p, w->bflags.p, w->lverts.p, w->rotc.p, w->aabb.p,
-                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p, w->used.p, w->used_int.p);
+                                   w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p, w->used.p, w->used_int.p, w->row_btot.p);
     w->launches++;
     mark();
     int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
@@ -2372,29 +2459,23 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     mark();
     SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp, cn));
     mark();
-    const int nbR = (B + 127) / 128;
+    const int nbR = (B + ROW_BLK - 1) / ROW_BLK;
     SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B + 3) / 4)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
-                         (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p, cn));
+                         (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p, cn, w->row_btot.p));
     w->launches += 2;
     mark();
-    e = run_scan<int>(w, w->row_count.p, w->row_start.p, B, nullptr, w->spart32.p, w->sincl32.p, 0, 1);
-    if (e) return e;
-    mark();
-    SYLT_CUDA(launch_pdl(k_rows_emit, dim3((unsigned)nbR), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1),
-                         w->large.p, w->n_large, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn));
+    SYLT_CUDA(launch_pdl(k_rows_emit, dim3((unsigned)nbR), dim3(ROW_BLK), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1),
+                         w->large.p, w->n_large, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn, w->row_count.p, w->row_btot.p));
     w->launches += 1;
     mark();
     const int gridP = w->num_sms * 8;
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_narrow<MAX_MANIFOLD>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p,
-                             w->bflags.p, w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn));
+                             w->bflags.p, w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn, w->pair_btot.p));
     else
         SYLT_CUDA(launch_pdl(k_narrow<2>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p,
-                             w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn));
+                             w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn, w->pair_btot.p));
     w->launches++;
-    mark();
-    e = run_scan<unsigned long long>(w, w->info.p, w->pscan.p, (int)w->cap_pairs, &cn->n_pairs, w->spart64.p, w->sincl64.p, 0, 2);
-    if (e) return e;
     mark();
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
     if (w->regions_on && (w->resort_pending || (full_step && w->steps_since_part >= w->regions_period))) {
@@ -2413,11 +2494,11 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->recolor_all = false;
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
-                             w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
+                             w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
                              w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0));
     else
         SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
-                             w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
+                             w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
                              w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
@@ -2441,6 +2522,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
     void* args[] = {&a};
     a.smem_slots = w->smem_slots; a.smem_contacts = w->smem_contacts;
+    a.cand_row_start = w->row_start.p; a.pscan = w->pscan.p; a.cap_pairs = (int)w->cap_pairs;
     a.vrec = w->vrec.p; a.jdeg = w->jdeg.p; a.jrank = w->jrank.p; a.sleep_ns = w->sleep_ns; a.slack_pct = w->slack_pct; a.fix_inverse = w->fix_inverse; a.dbg = w->timing ? w->dbg.p : nullptr;
     if (w->regions_on) {
         a.region_of = w->region_of.p; a.lidx = w->lidx.p; a.reg_start = w->reg_start.p; a.reg_bodies = w->reg_bodies.p;
@@ -2547,12 +2629,12 @@ int finish(SyltWorld* w) {
         if (w->last_regions) w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
         if (w->timing) print_solver_timing(w);
         if (w->kt_n > 1) {  // SYLT_KERNEL_TIMING: the last step's launches
-            static const char* names[] = {"prepare", "scan cells", "fill cells", "rows count", "scan rows", "rows emit", "narrow", "scan pairs", "(re-cut +) build", "solve"};
+            static const char* names[] = {"prepare", "scan cells", "fill cells", "rows count", "rows emit", "narrow", "(re-cut +) build", "solve"};
             fprintf(stderr, "kernels [us]:");
             for (int k = 1; k < w->kt_n; k++) {
                 float ms = 0.0f;
                 cudaEventElapsedTime(&ms, w->kt_ev[k - 1], w->kt_ev[k]);
-                fprintf(stderr, " %s %.1f", k - 1 < 10 ? names[k - 1] : "?", ms * 1e3f);
+                fprintf(stderr, " %s %.1f", k - 1 < 8 ? names[k - 1] : "?", ms * 1e3f);
             }
             fprintf(stderr, "\n");
         }
@@ -2579,6 +2661,9 @@ int finish(SyltWorld* w) {
         if (err == SYLT_ERR_NO_INVERSE) {
             w->n_arb_valid = (int)std::min<int64_t>(w->last.n_arb, w->cap_arb);
             w->n_con_valid = (int)std::min<int64_t>(w->last.n_con, w->cap_con);
+        } else if (completed > 0) {  // the last good set is the one of the last completed step of this call
+            w->n_arb_valid = (int)std::min<int64_t>(w->last.good_n_arb, w->cap_arb);
+            w->n_con_valid = (int)std::min<int64_t>(w->last.good_n_con, w->cap_con);
         }
         std::vector<SyltWorld::Segment> rest;  // the steps that did not run
         {
@@ -2725,7 +2810,7 @@ static void free_all(SyltWorld* w) {
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
-    w->row_start.release(); w->row_tmp.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
+    w->row_start.release(); w->row_tmp.release(); w->row_btot.release(); w->pair_btot.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
     w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
     w->prop.release(); w->order.release(); w->sincl32.release(); w->sincl64.release(); w->scan_flag.release(); w->scan_ticket.release();
     for (int k = 0; k < 2; k++) {
