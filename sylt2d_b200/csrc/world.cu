@@ -2129,7 +2129,8 @@ struct SyltWorld {
     struct Segment { float dt; int n; bool full; };
     std::vector<Segment> segs;
     int call_cur0 = 0, call_B_old0 = 0;
-    bool call_have_old0 = false, call_flags_stale0 = false;
+    bool call_have_old0 = false, call_flags_stale0 = false, call_pending0 = false, call_recolor0 = false;
+    int64_t call_since0 = 0;
     int n_arb_valid = 0, n_con_valid = 0;  // size of the arbiter set sylt_world_get_arbiters reads (the last set that was completed)
     unsigned epoch = 1;
     Counters last{};         // counters of the last completed step
@@ -2431,6 +2432,22 @@ int repartition(SyltWorld* w) {
     return SYLT_OK;
 }
 
+// The re-cut schedule of the region solver is host-side bookkeeping that runs ahead of the device (steps are enqueued, not
+// awaited): recut_due + the updates in enqueue_step.  replay_schedule() re-derives it for the steps of a call that completed
+// when a later step failed, so that the repeated steps re-cut (and recolour) exactly where the original ones would have.
+bool recut_due(const SyltWorld* w, bool full_step) {
+    return w->regions_on && (w->resort_pending || (full_step && w->steps_since_part >= w->regions_period));
+}
+void replay_schedule(SyltWorld* w, int64_t since0, bool pending0, bool recolor0, const std::vector<SyltWorld::Segment>& segs, int completed) {
+    w->steps_since_part = since0; w->resort_pending = pending0; w->recolor_all = recolor0;
+    for (const auto& sg : segs)
+        for (int k = 0; k < sg.n && completed > 0; k++, completed--) {
+            if (recut_due(w, sg.full)) { w->steps_since_part = 0; w->resort_pending = false; w->recolor_all = true; }
+            w->recolor_all = false;
+            if (w->regions_on) w->steps_since_part++;
+        }
+}
+
 // Enqueue one step (or one broad phase only) on the stream.  No host synchronisation.
 int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     const int B = (int)w->hb.size();
@@ -2478,7 +2495,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->launches++;
     mark();
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
-    if (w->regions_on && (w->resort_pending || (full_step && w->steps_since_part >= w->regions_period))) {
+    if (recut_due(w, full_step)) {
         // (re)partition by the current positions and last step's load (device side, no synchronisation); the colours encode the old cut
         k_resort<<<1, REBAL_THREADS, (SORT_CELLS + 1) * sizeof(int), st>>>(B, w->pose.p, w->reg_bodies.p, w->sort_keys.p, cn);
         SYLT_CUDA(cudaGetLastError());
@@ -2657,7 +2674,7 @@ int finish(SyltWorld* w) {
             if (ran == 0) { w->have_old = w->call_have_old0; w->B_old = w->call_B_old0; w->flags_stale = w->call_flags_stale0; }
         }
         w->cells_clean = false;
-        if (w->regions_on) w->resort_pending = true;  // a re-cut enqueued behind the failure was skipped: cut (and recolour) again
+        replay_schedule(w, w->call_since0, w->call_pending0, w->call_recolor0, w->segs, ran);  // re-cuts enqueued behind the failure did not happen
         if (err == SYLT_ERR_NO_INVERSE) {
             w->n_arb_valid = (int)std::min<int64_t>(w->last.n_arb, w->cap_arb);
             w->n_con_valid = (int)std::min<int64_t>(w->last.n_con, w->cap_con);
@@ -2712,6 +2729,7 @@ int prepare_call(SyltWorld* w) {
         SYLT_CUDA(cudaMemsetAsync(w->counters.p, 0, offsetof(Counters, n_pairs), w->stream));  // sticky error fields, steps_done
         w->segs.clear();
         w->call_cur0 = w->cur; w->call_have_old0 = w->have_old; w->call_B_old0 = w->B_old; w->call_flags_stale0 = w->flags_stale;
+        w->call_since0 = w->steps_since_part; w->call_pending0 = w->resort_pending; w->call_recolor0 = w->recolor_all;
     }
     return SYLT_OK;
 }
