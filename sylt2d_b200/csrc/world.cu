@@ -1366,15 +1366,24 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
 // Only the owner writes an arbiter's contacts back.  Worlds with joints use k_solve.
 constexpr int GADJ = NC;              // per body: its generic arbiters, indexed by the rank of their colour in `used`
 constexpr int GHOST_FLAG = 0x40000000;
-constexpr int CONE_CAP = 2048;        // ghost arbiters a CTA may replay
-constexpr int HASH_CAP = 4096;        // open-addressing tables of the cone walk (set-up scratch at the top of shared memory)
-constexpr int GB_MAX = 2048;          // ghost bodies of a CTA
-constexpr int OWN_MAX = 4096;         // arbiters a region may own
-constexpr int MAX_PLANES = 16;        // export planes: one per pass (iterations + 1)
+}  // namespace
+// table sizes of a region CTA that has an SM to itself (k_solve_regions<PER_SM> divides them by PER_SM)
+constexpr int CONE_CAP_1 = 2048;      // ghost arbiters a CTA may replay
+constexpr int HASH_CAP_1 = 4096;      // open-addressing tables of the cone walk (set-up scratch at the top of shared memory)
+constexpr int GB_MAX_1 = 2048;        // ghost bodies of a CTA
+constexpr int OWN_MAX_1 = 4096;       // arbiters a region may own
+namespace {
+constexpr int MAX_PLANES = 16;        // export planes: pass t uses plane t % MAX_PLANES; a grid barrier every MAX_PLANES passes keeps
+                                      // every CTA within one lap of the others, so a plane is never overwritten before it has been read
+constexpr int MAX_PASSES = 4096;      // passes (1 + iterations) the 12-bit pass field of an export tag can tell apart
 
 __device__ __forceinline__ unsigned hash_u32(unsigned x) { return fmix32(x * 2654435761u); }
 
-__global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a) {
+// PER_SM region CTAs share an SM (each with 1 / PER_SM of the threads, the shared memory and the table sizes): the passes are a chain
+// of short latency-bound colour hops, so two half-size regions per SM overlap each other's latencies.
+template <int PER_SM>
+__global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_regions(SolveArgs a) {
+    constexpr int CONE_CAP = ::CONE_CAP_1 / PER_SM, HASH_CAP = ::HASH_CAP_1 / PER_SM, GB_MAX = ::GB_MAX_1 / PER_SM, OWN_MAX = ::OWN_MAX_1 / PER_SM;
     extern __shared__ __align__(16) unsigned char sm_raw[];
     Counters* cn = a.cn;
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
@@ -1769,8 +1778,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
         pstamp(pass);
         colours(pass, 0, nint);
         pstamp(pass);
-        BodyIO xio{a.xrec + (size_t)pass * 2 * (size_t)a.B, a.sleep_ns, &cn->err};
-        const unsigned tag = (a.step_tag << 8) | pass;
+        BodyIO xio{a.xrec + (size_t)(pass % MAX_PLANES) * 2 * (size_t)a.B, a.sleep_ns, &cn->err};
+        const unsigned tag = (a.step_tag << 12) | pass;
         for (int k = lt; k < nbnd; k += T) {
             const float4 q = s_body[2 * s_bnd[k]];
             Vel o; o.v = mk(q.x, q.y); o.w = q.z;
@@ -1801,7 +1810,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve_regions(SolveArgs a)
     sweep(0u);
     stamp(4);
     // ---- 5. passes 1..I: apply_impulse (world.rs:132-140)
-    for (int it = 1; it <= a.iterations; it++) sweep((unsigned)it);
+    for (int it = 1; it <= a.iterations; it++) {
+        if (it % MAX_PLANES == 0) grid_barrier(bar, bar_target);  // (the reference's samples run 100 iterations: examples/samples/src/main.rs:10)
+        sweep((unsigned)it);
+    }
 
     stamp(5);
     // ---- 6. the owner writes its shared-memory resident contacts back (warm start of the next step, read-back).
@@ -2120,7 +2132,8 @@ struct SyltWorld {
     bool resort_pending = false;     // the partition of the current bodies has not been computed yet
     cudaEvent_t kt_ev[16] = {};      // SYLT_KERNEL_TIMING
     int kt_n = 0;
-    size_t solve_budget = 0;
+    size_t solve_budget = 0;         // dynamic shared memory of one k_solve_regions CTA
+    int regions_per_sm = 1, regions_blocks = 0, regions_threads = SOLVE_THREADS;  // SYLT_REGION_CTAS_PER_SM
 
     int64_t cap_pairs = 0, cap_arb = 0, cap_con = 0;
     int64_t user_pairs = 0, user_arb = 0, user_con = 0;
@@ -2405,12 +2418,12 @@ int repartition(SyltWorld* w) {
     const size_t B = w->hb.size();
     w->part_dirty = false;
     const bool was_on = w->regions_on;
-    const int G = std::min(1024, w->regions_count > 0 ? std::min(w->regions_count, w->coop_blocks) : w->coop_blocks);
+    const int G = std::min(1024, w->regions_count > 0 ? std::min(w->regions_count, w->regions_blocks) : w->regions_blocks);
     bool on = w->regions_mode == 2 || (w->regions_mode == 1 && B >= (size_t)w->regions_min_bodies);
-    if (B == 0 || G < 1 || !w->hj.empty() || w->iterations + 1 > (uint32_t)MAX_PLANES) on = false;  // joints / long solves: k_solve
+    if (B == 0 || G < 1 || !w->hj.empty() || w->iterations + 1 > (uint32_t)MAX_PASSES) on = false;  // joints: k_solve
     // a region may hold twice the average number of bodies (k_rebalance); 40 bytes each must leave room for the set-up scratch and the slots
     const size_t maxper = 2 * ((B + (size_t)G - 1) / (size_t)std::max(G, 1)) + 16;
-    if (on && maxper * 40 + (size_t)3 * HASH_CAP * 4 + (size_t)GB_MAX * 4 + (size_t)OWN_MAX * 8 + 32768 > w->solve_budget) on = false;
+    if (on && maxper * 40 + ((size_t)3 * HASH_CAP_1 * 4 + (size_t)GB_MAX_1 * 4 + (size_t)OWN_MAX_1 * 8 + 32768) / (size_t)w->regions_per_sm > w->solve_budget) on = false;
     if (on != was_on) w->recolor_all = true;  // the colour ranges mean something else
     w->regions_on = on;
     if (!on) return SYLT_OK;
@@ -2421,7 +2434,7 @@ int repartition(SyltWorld* w) {
     SYLT_CUDA(w->sort_keys.ensure(B));
     SYLT_CUDA(w->reg_start.ensure((size_t)G + 1));
     SYLT_CUDA(w->gadj.ensure(B * (size_t)GADJ));
-    SYLT_CUDA(w->cone_buf.ensure((size_t)w->coop_blocks * CONE_CAP));
+    SYLT_CUDA(w->cone_buf.ensure((size_t)w->regions_blocks * (CONE_CAP_1 / w->regions_per_sm)));
     {   // export planes: a record is valid when its tag matches (step_tag, pass); fresh memory must not hold a look-alike
         const size_t oldcap = w->xrec.cap;
         SYLT_CUDA(w->xrec.ensure((size_t)MAX_PLANES * 2 * B));
@@ -2545,13 +2558,14 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         a.region_of = w->region_of.p; a.lidx = w->lidx.p; a.reg_start = w->reg_start.p; a.reg_bodies = w->reg_bodies.p;
         a.n_regions = w->n_regions; a.smem_bytes = (int)w->solve_budget;
         a.gadj = w->gadj.p; a.cone_buf = w->cone_buf.p; a.xrec = w->xrec.p;
-        if (++w->step_tag > 0xfffff0u) {  // 24-bit tags: start over with clean planes
+        if (++w->step_tag > 0xffff0u) {  // 20-bit step tags (+ 12 bits of pass): start over with clean planes
             SYLT_CUDA(cudaMemsetAsync(w->xrec.p, 0, w->xrec.cap * sizeof(ulonglong2), st));
             w->step_tag = 1;
         }
         a.step_tag = w->step_tag;
-        a.probe_cta = getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->coop_blocks / 2;
-        SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve_regions, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_budget, st));
+        a.probe_cta = getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->regions_blocks / 2;
+        SYLT_CUDA(cudaLaunchCooperativeKernel(w->regions_per_sm == 2 ? (void*)k_solve_regions<2> : (void*)k_solve_regions<1>, dim3((unsigned)w->regions_blocks),
+                                              dim3((unsigned)w->regions_threads), args, w->solve_budget, st));
         w->steps_since_part++;
         w->last_regions = true;
     } else {
@@ -2573,11 +2587,11 @@ void print_solver_timing(SyltWorld* w) {
         fprintf(stderr, "step error %d (why %d, max slots %d, ghosts %d, uncoloured %d; pairs %d / %lld, arbiters %d / %lld, contacts %d / %lld, colouring rounds %d)\n",
                 w->last.err, w->last.why, w->last.max_slots, w->last.n_ghost, w->last.n_uncolored, w->last.n_pairs, (long long)w->cap_pairs, w->last.n_arb,
                 (long long)w->cap_arb, w->last.n_con, (long long)w->cap_con, w->last.rounds);
-    const int G = w->coop_blocks;
+    const int G = w->last_regions ? w->regions_blocks : w->coop_blocks;
     std::vector<unsigned long long> t(64 + 8 * 1024);
     if (cudaMemcpy(t.data(), w->dbg.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
     if (w->last_regions && t[32]) {
-        fprintf(stderr, "  set-up of CTA %d [us]: generic table + barrier | bodies, rows, cone roots | cone walk | ghost bodies | layout, ghost data | slot records | scan | contacts:", getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->coop_blocks / 2);
+        fprintf(stderr, "  set-up of CTA %d [us]: generic table + barrier | bodies, rows, cone roots | cone walk | ghost bodies | layout, ghost data | slot records | scan | contacts:", getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->regions_blocks / 2);
         for (int k = 33; k < 48 && t[k]; k++) fprintf(stderr, " %.1f", (t[k] - t[k - 1]) * 1e-3);
         fprintf(stderr, "\n");
     }
@@ -2796,20 +2810,24 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     if (const char* ev = getenv("SYLT_SOLVER_SMEM_CONTACTS")) w->smem_contacts = std::min(w->smem_contacts, std::max(0, atoi(ev)));
     w->solve_smem = fixed + (size_t)w->smem_contacts * 48;
     SYLT_CUDA(cudaFuncSetAttribute(k_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_smem));
-    {   // k_solve_regions: same budget, carved per partition (bodies of the region, slot records, contacts)
+    {   // k_solve_regions: the SM's shared memory, carved per partition (bodies of the region, slot records, contacts)
+        if (const char* ev = getenv("SYLT_REGION_CTAS_PER_SM")) w->regions_per_sm = atoi(ev) == 2 ? 2 : 1;
+        const void* kern = w->regions_per_sm == 2 ? (const void*)k_solve_regions<2> : (const void*)k_solve_regions<1>;
         cudaFuncAttributes fr;
-        SYLT_CUDA(cudaFuncGetAttributes(&fr, k_solve_regions));
-        const size_t b2 = (size_t)max_smem + 1024 - 1024 - fr.sharedSizeBytes - 1024;
+        SYLT_CUDA(cudaFuncGetAttributes(&fr, kern));
+        const size_t b2 = ((size_t)max_smem + 1024) / (size_t)w->regions_per_sm - 1024 - fr.sharedSizeBytes - 1024;  // 1 KB per CTA is reserved by the system
         w->solve_budget = b2 & ~(size_t)15;
-        SYLT_CUDA(cudaFuncSetAttribute(k_solve_regions, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_budget));
+        w->regions_threads = SOLVE_THREADS / w->regions_per_sm;
+        w->regions_blocks = w->num_sms * w->regions_per_sm;
+        SYLT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_budget));
         SYLT_CUDA(cudaFuncSetAttribute(k_resort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SORT_CELLS + 1) * sizeof(int))));
         int per2 = 0;
-        SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, k_solve_regions, SOLVE_THREADS, w->solve_budget));
+        SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, kern, w->regions_threads, w->solve_budget));
         if (const char* ev = getenv("SYLT_REGIONS")) w->regions_mode = std::min(2, std::max(0, atoi(ev)));
         if (const char* ev = getenv("SYLT_REGIONS_MIN_BODIES")) w->regions_min_bodies = std::max(1, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_COUNT")) w->regions_count = std::max(0, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_PERIOD")) w->regions_period = std::max(1, atoi(ev));
-        if (per2 < 1 || w->ctas_per_sm != 1) w->regions_mode = 0;
+        if (per2 < w->regions_per_sm || w->ctas_per_sm != 1) w->regions_mode = 0;
     }
     int per_sm = 0;
     SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_solve, w->solve_threads, w->solve_smem));
@@ -2878,7 +2896,7 @@ int sylt_world_set_fixes(SyltWorld* w, int fix_features, int fix_inverse) {
 }
 int sylt_world_set_iterations(SyltWorld* w, uint32_t it) {
     if (!w) return SYLT_ERR_INVALID;
-    if (w->iterations != it) w->part_dirty = true;  // the region solver is limited to MAX_PLANES - 1 iterations
+    if (w->iterations != it) w->part_dirty = true;  // (the region solver handles up to MAX_PASSES - 1 iterations)
     w->iterations = it;
     return SYLT_OK;
 }

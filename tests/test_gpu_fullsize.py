@@ -251,3 +251,22 @@ def test_long_run_energy_and_penetration_series_gpu_order_vs_canonical_order():
     q, t = m["multi_pendulum"], ORDER_TOL["multi_pendulum"]
     assert q["etot_first100_max_abs_diff_rel"] <= t["first100_rel"], q
     assert abs(q["etot_drift_gpu"] - q["etot_drift_canonical"]) <= t["drift_rel"] * abs(q["etot_drift_canonical"]), q
+
+
+def test_region_solver_with_the_samples_100_iterations(monkeypatch):
+    """The reference's own setting is ITERATIONS = 100 (examples/samples/src/main.rs:10): k_solve_regions recycles its 16 export
+    planes (a grid barrier every 16 passes), so long solves stay on the region solver.  Boxes + polygons, re-cut every 3 steps."""
+    monkeypatch.setenv("SYLT_REGIONS", "2")
+    monkeypatch.setenv("SYLT_REGIONS_PERIOD", "3")
+    from sylt2d_b200 import World
+    sc = scenes.mixed_pile(3000, seed=11, iterations=100)
+    g = World(sc.gravity, sc.iterations, device=0)
+    g.load_scene(sc)
+    g.step_n(sc.dt, 100)
+    w, o = _fresh_pair(sc, g.get_bodies())
+    _lockstep_from(sc, w, o, 5, "mixed_pile3000 I=100")
+    ga, _ = w.get_arbiters()
+    assert ga.shape[0] > 1000 and (ga["color"] < 32).any() and (ga["color"] >= 32).any()   # k_solve_regions ran (both colour classes)
+    sc = scenes.pyramid(12, 100)                                                           # the reference's literal demo5
+    w, o = _fresh_pair(sc)
+    _lockstep_from(sc, w, o, 40, "pyramid12 I=100 regions")
