@@ -14,6 +14,8 @@
  *   Body::new_polygon + World::add_body  src/body.rs:246-284  sylt_world_add_polygon / _add_bodies
  *   Joint::new + World::add_joint        src/joint.rs:26-55, src/world.rs:63-65    sylt_world_add_joint
  *   pub Joint.softness / .bias_factor    src/joint.rs:17-18   sylt_world_set_joint_params
+ *   pub Joint.local_anchor_1 / _2        src/joint.rs:19-20   sylt_world_add_joint_local / sylt_world_set_joint_local_anchors
+ *   pub Body.friction / mass / inv_mass / moi / inv_moi / width   src/body.rs:190-196   sylt_world_set_body_props
  *   Body::add_force                      src/body.rs:286-288  sylt_world_add_force
  *   pub Body fields (mutated between steps, e.g. examples/samples/src/main.rs:56-64)   sylt_world_set_bodies
  *   World::broad_phase                   src/world.rs:73-105  sylt_world_broad_phase
@@ -43,7 +45,9 @@ extern "C" {
 #define SYLT_ERR_ARBITER 2        /* Sylt2DErrors::Arbiter(..) — unreachable in the reference, kept for the mapping */
 #define SYLT_ERR_BODY_ORDER 3     /* reference panics: bodies not added in increasing-id order (arbiter.rs:120-122) */
 #define SYLT_ERR_BODY_NOT_FOUND 4 /* reference panics: Joint::new body lookup (joint.rs:31,36) */
-#define SYLT_ERR_CAPACITY 5       /* a device buffer capacity was exceeded (see sylt_world_set_capacity) */
+#define SYLT_ERR_CAPACITY 5       /* a fixed limit was exceeded: > 64 arbiter colours at one body, a polygon manifold over 2*SYLT_MAX_POLY_VERTS
+                                     contacts, a batch world over its slot capacity.  (Pair / arbiter / contact buffers of a single world grow
+                                     by themselves.)  The failed step changed nothing. */
 #define SYLT_ERR_CUDA 6           /* CUDA runtime error / no device; sylt_last_error_string() has the text */
 #define SYLT_ERR_INVALID 7        /* bad argument */
 #define SYLT_ERR_UNSUPPORTED 8    /* e.g. polygons with > SYLT_MAX_POLY_VERTS vertices */
@@ -135,7 +139,9 @@ int sylt_world_set_iterations(SyltWorld* w, uint32_t iterations);
  * inherit old contact 0's impulses (arbiter.rs:145-176).  fix_inverse: Mat2x2 inverse scaled by 1/det instead of det
  * (math_utils.rs:185-199), i.e. rigid instead of very soft joints. */
 int sylt_world_set_fixes(SyltWorld* w, int fix_features, int fix_inverse);
-/* 0 = keep; defaults: pairs 16*B, arbiters 8*B, contacts 16*B (grown automatically when bodies are added) */
+/* 0 = keep; defaults: pairs 16*B, arbiters 8*B, contacts 16*B (grown automatically when bodies are added).  These are starting
+ * sizes, not limits: a step that overflows a buffer changes nothing, the buffers are grown and the step is repeated (the
+ * reference's arbiter container is a HashMap, world.rs:24). */
 int sylt_world_set_capacity(SyltWorld* w, int64_t max_pairs, int64_t max_arbiters, int64_t max_contacts);
 
 int sylt_world_add_box(SyltWorld* w, uint64_t id, float width_x, float width_y, float mass, float friction,
@@ -146,6 +152,11 @@ int sylt_world_add_bodies(SyltWorld* w, const SyltBodyDesc* bodies, int32_t n, c
 int sylt_world_add_joint(SyltWorld* w, uint64_t id1, uint64_t id2, float anchor_x, float anchor_y, int32_t* out_index);
 int sylt_world_add_joints(SyltWorld* w, const SyltJointDesc* joints, int32_t n);
 int sylt_world_set_joint_params(SyltWorld* w, int32_t joint, float softness, float bias_factor);
+/* Joint with the local anchors given as they are (pub Joint.local_anchor_1 / _2, joint.rs:19-20: Joint::new computes them once
+ * from the bodies' poses, joint.rs:37-40, and a caller may edit them afterwards) */
+int sylt_world_add_joint_local(SyltWorld* w, uint64_t id1, uint64_t id2, float la1x, float la1y, float la2x, float la2y,
+                               float softness, float bias_factor, int32_t* out_index);
+int sylt_world_set_joint_local_anchors(SyltWorld* w, int32_t joint, float la1x, float la1y, float la2x, float la2y);
 int sylt_world_add_force(SyltWorld* w, int32_t body, float fx, float fy);
 
 int sylt_world_num_bodies(SyltWorld* w);
@@ -157,6 +168,10 @@ int sylt_world_get_bodies(SyltWorld* w, SyltBodyState* out, int32_t cap);
 int sylt_world_set_bodies(SyltWorld* w, int32_t first, int32_t count, const SyltBodyState* in);
 /* mass, inv_mass, moi, inv_moi, width.x, width.y, friction, shape — 8 floats per body (Body's read-mostly pub fields) */
 int sylt_world_get_body_props(SyltWorld* w, float* out8, int32_t cap);
+/* The same record written back: the reference reads these pub Body fields on every step (inv_mass / inv_moi: world.rs:115-118,
+ * arbiter.rs:198-211, joint.rs:74-92; width: collide.rs:141-142; friction: arbiter.rs:128 when an arbiter is created), so a caller
+ * may overwrite them between steps.  Taken as given (nothing is recomputed from mass); the shape entry is ignored. */
+int sylt_world_set_body_props(SyltWorld* w, int32_t first, int32_t count, const float* props8);
 /* arbiters in ascending (id1,id2) order with their contacts; returns count or -(error) */
 int sylt_world_get_arbiters(SyltWorld* w, SyltArbiterInfo* arbiters, int32_t arbiter_cap, SyltContact* contacts, int32_t contact_cap);
 int sylt_world_get_joints(SyltWorld* w, SyltJointState* out, int32_t cap);

@@ -62,6 +62,8 @@ def lib():
     L.orc_world_get_bodies.argtypes = [vp, vp, i32]
     L.orc_world_set_bodies.argtypes = [vp, i32, i32, vp]
     L.orc_world_get_body_props.argtypes = [vp, vp, i32]
+    L.orc_world_set_body_props.argtypes = [vp, i32, i32, vp]
+    L.orc_world_set_joint_local_anchors.argtypes = [vp, i32, f32, f32, f32, f32]
     L.orc_world_get_arbiters.argtypes = [vp, vp, i32, vp, i32]
     L.orc_world_get_joints.argtypes = [vp, vp, i32]
     L.orc_world_step.argtypes = [vp, f32]
@@ -197,6 +199,15 @@ class OracleWorld:
         out = np.zeros((self.num_bodies, 8), dtype=np.float32)
         self.L.orc_world_get_body_props(self.h, _ptr(out), out.shape[0])
         return out
+
+    def set_body_props(self, props, first=0):
+        p = np.ascontiguousarray(props, dtype=np.float32).reshape(-1, 8)
+        e = self.L.orc_world_set_body_props(self.h, first, p.shape[0], _ptr(p))
+        if e:
+            raise OracleError(e)
+
+    def set_joint_local_anchors(self, joint_index, la1, la2):
+        self.L.orc_world_set_joint_local_anchors(self.h, int(joint_index), la1[0], la1[1], la2[0], la2[1])
 
     def get_arbiters(self):
         na, nc = self.num_arbiters, self.num_contacts

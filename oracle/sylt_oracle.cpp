@@ -821,6 +821,23 @@ int orc_world_get_body_props(OrcWorld* w, float* o, int cap) {
     }
     return n;
 }
+// the pub Body fields the step reads every time (inv_mass / inv_moi: world.rs:115-118, arbiter.rs, joint.rs; width: collide.rs:141-142;
+// friction: arbiter.rs:128 at arbiter creation): a caller of the reference may overwrite them between steps
+int orc_world_set_body_props(OrcWorld* w, int first, int count, const float* in) {
+    if (first < 0 || count < 0 || (size_t)first + (size_t)count > w->bodies.size()) return ERR_INVALID;
+    for (int i = 0; i < count; i++) {
+        Body& b = w->bodies[(size_t)(first + i)];
+        const float* p = in + 8 * i;
+        b.mass = p[0]; b.inv_mass = p[1]; b.moi = p[2]; b.inv_moi = p[3]; b.width = {p[4], p[5]}; b.friction = p[6];
+    }
+    return ERR_OK;
+}
+// pub Joint.local_anchor_1 / local_anchor_2 (joint.rs:19-20)
+int orc_world_set_joint_local_anchors(OrcWorld* w, int j, float la1x, float la1y, float la2x, float la2y) {
+    if (j < 0 || (size_t)j >= w->joints.size()) return ERR_INVALID;
+    w->joints[(size_t)j].la1 = {la1x, la1y}; w->joints[(size_t)j].la2 = {la2x, la2y};
+    return ERR_OK;
+}
 static void export_contact(const Contact& c, OrcContact* o) {
     o->px = c.position.x; o->py = c.position.y; o->nx = c.normal.x; o->ny = c.normal.y;
     o->r1x = c.r1.x; o->r1y = c.r1.y; o->r2x = c.r2.x; o->r2y = c.r2.y;

@@ -79,6 +79,8 @@ int orc_world_get_bodies(OrcWorld* w, OrcBodyState* out, int cap);
 int orc_world_set_bodies(OrcWorld* w, int first, int count, const OrcBodyState* in);
 /* mass, inv_mass, moi, inv_moi, width.x, width.y, friction, shape  (8 floats per body) */
 int orc_world_get_body_props(OrcWorld* w, float* out8, int cap);
+int orc_world_set_body_props(OrcWorld* w, int first, int count, const float* in8);
+int orc_world_set_joint_local_anchors(OrcWorld* w, int j, float la1x, float la1y, float la2x, float la2y);
 int orc_world_get_arbiters(OrcWorld* w, OrcArbiterInfo* arb, int arb_cap, OrcContact* contacts, int contact_cap);
 int orc_world_get_joints(OrcWorld* w, OrcJointState* out, int cap);
 

@@ -7,6 +7,30 @@ pub const SYLT_ERR_NO_INVERSE: c_int = 1;
 pub const SYLT_ERR_ARBITER: c_int = 2;
 pub const SYLT_ERR_BODY_ORDER: c_int = 3;
 pub const SYLT_ERR_BODY_NOT_FOUND: c_int = 4;
+pub const SYLT_ERR_CAPACITY: c_int = 5;
+pub const SYLT_ERR_CUDA: c_int = 6;
+pub const SYLT_SHAPE_BOX: i32 = 0;
+pub const SYLT_SHAPE_POLYGON: i32 = 1;
+pub const SYLT_MAX_POLY_VERTS: usize = 8;
+pub const SYLT_MAX_MANIFOLD: usize = 2 * SYLT_MAX_POLY_VERTS;
+
+/// Body construction record (64 bytes, include/sylt2d_b200.h `SyltBodyDesc`)
+#[repr(C)]
+#[derive(Clone, Copy, Default, Debug)]
+pub struct SyltBodyDesc {
+    pub id: u64, pub shape: i32, pub vert_offset: i32, pub vert_count: i32, pub _pad: i32,
+    pub width_x: f32, pub width_y: f32, pub mass: f32, pub friction: f32,
+    pub x: f32, pub y: f32, pub rotation: f32, pub vx: f32, pub vy: f32, pub angular_velocity: f32,
+}
+
+pub fn desc_of(b: &crate::body::Body, vert_offset: i32, vert_count: i32) -> SyltBodyDesc {
+    SyltBodyDesc {
+        id: b.id as u64,
+        shape: match b.shape { crate::body::Shape::Box => SYLT_SHAPE_BOX, crate::body::Shape::ConvexPolygon => SYLT_SHAPE_POLYGON },
+        vert_offset, vert_count, _pad: 0, width_x: b.width.x, width_y: b.width.y, mass: b.mass, friction: b.friction,
+        x: b.position.x, y: b.position.y, rotation: b.rotation, vx: b.velocity.x, vy: b.velocity.y, angular_velocity: b.angular_velocity,
+    }
+}
 
 #[repr(C)]
 #[derive(Clone, Copy, Default, Debug)]
@@ -45,6 +69,13 @@ extern "C" {
                                   rot: f32, vx: f32, vy: f32, omega: f32, out_index: *mut i32) -> c_int;
     pub fn sylt_world_add_joint(w: *mut SyltWorld, id1: u64, id2: u64, ax: f32, ay: f32, out_index: *mut i32) -> c_int;
     pub fn sylt_world_set_joint_params(w: *mut SyltWorld, joint: i32, softness: f32, bias_factor: f32) -> c_int;
+    pub fn sylt_world_add_joint_local(w: *mut SyltWorld, id1: u64, id2: u64, la1x: f32, la1y: f32, la2x: f32, la2y: f32,
+                                      softness: f32, bias_factor: f32, out_index: *mut i32) -> c_int;
+    pub fn sylt_world_set_joint_local_anchors(w: *mut SyltWorld, joint: i32, la1x: f32, la1y: f32, la2x: f32, la2y: f32) -> c_int;
+    pub fn sylt_world_get_body_props(w: *mut SyltWorld, out8: *mut f32, cap: i32) -> c_int;
+    pub fn sylt_world_set_body_props(w: *mut SyltWorld, first: i32, count: i32, props8: *const f32) -> c_int;
+    pub fn sylt_collide_pairs(device: c_int, a: *const SyltBodyDesc, b: *const SyltBodyDesc, n: i32, verts_xy: *const f32, n_verts: i32,
+                              out: *mut SyltContact, cap: i32, out_counts: *mut i32) -> c_int;
     pub fn sylt_world_num_arbiters(w: *mut SyltWorld) -> c_int;
     pub fn sylt_world_num_contacts(w: *mut SyltWorld) -> c_int;
     pub fn sylt_world_get_bodies(w: *mut SyltWorld, out: *mut SyltBodyState, cap: i32) -> c_int;

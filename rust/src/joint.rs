@@ -1,4 +1,5 @@
-//! Joint::new(body_1, body_2, anchor, &world) with pub softness / bias_factor (reference: src/joint.rs:10-55).
+//! Joint::new(body_1, body_2, anchor, &world) with pub softness / bias_factor / local anchors (reference: src/joint.rs:10-55).
+//! All four are LIVE: World::step sends them before every step (the library ignores unchanged values).
 use crate::body::Body;
 use crate::math_utils::{Mat2x2, Vec2};
 use crate::world::World;
@@ -12,7 +13,6 @@ pub struct Joint {
     pub local_anchor_2: Vec2,
     pub body_1: Rc<RefCell<Body>>,
     pub body_2: Rc<RefCell<Body>>,
-    pub(crate) anchor: Vec2,
     pub(crate) index: Option<i32>,
 }
 
@@ -26,7 +26,7 @@ impl Joint {
             body_1: b1.clone(), body_2: b2.clone(),
             local_anchor_1: rt1 * (anchor - b1.borrow().position),
             local_anchor_2: rt2 * (anchor - b2.borrow().position),
-            softness: 0.0, bias_factor: 0.2, anchor, index: None,
+            softness: 0.0, bias_factor: 0.2, index: None,
         }
     }
 }

@@ -38,7 +38,7 @@ SYMBOLS = [
     "sylt_last_error_string", "sylt_device_count",
     "sylt_world_create", "sylt_world_destroy", "sylt_world_clear", "sylt_world_set_context", "sylt_world_set_iterations",
     "sylt_world_set_capacity", "sylt_world_set_fixes", "sylt_world_add_box", "sylt_world_add_polygon", "sylt_world_add_bodies", "sylt_world_add_joint",
-    "sylt_world_add_joints", "sylt_world_set_joint_params", "sylt_world_add_force", "sylt_world_num_bodies", "sylt_world_num_joints",
+    "sylt_world_add_joints", "sylt_world_set_joint_params", "sylt_world_add_joint_local", "sylt_world_set_joint_local_anchors", "sylt_world_set_body_props", "sylt_world_add_force", "sylt_world_num_bodies", "sylt_world_num_joints",
     "sylt_world_num_arbiters", "sylt_world_num_contacts", "sylt_world_get_bodies", "sylt_world_set_bodies", "sylt_world_get_body_props",
     "sylt_world_get_arbiters", "sylt_world_get_joints", "sylt_world_get_joint_order", "sylt_world_get_stats",
     "sylt_world_last_error_matrix", "sylt_world_broad_phase", "sylt_world_step", "sylt_world_step_n", "sylt_world_step_n_async",
@@ -86,6 +86,9 @@ def lib():
     L.sylt_world_add_joint.argtypes = [vp, u64, u64, f32, f32, vp]
     L.sylt_world_add_joints.argtypes = [vp, vp, i32]
     L.sylt_world_set_joint_params.argtypes = [vp, i32, f32, f32]
+    L.sylt_world_add_joint_local.argtypes = [vp, u64, u64, f32, f32, f32, f32, f32, f32, vp]
+    L.sylt_world_set_joint_local_anchors.argtypes = [vp, i32, f32, f32, f32, f32]
+    L.sylt_world_set_body_props.argtypes = [vp, i32, i32, vp]
     L.sylt_world_add_force.argtypes = [vp, i32, f32, f32]
     L.sylt_world_get_bodies.argtypes = [vp, vp, i32]
     L.sylt_world_set_bodies.argtypes = [vp, i32, i32, vp]

@@ -2065,6 +2065,7 @@ struct SyltWorld {
     int uploaded = 0;        // bodies already on the device
     bool class_dirty = true; // grid classification / flags need recomputing
     bool joints_dirty = true;
+    bool jparams_dirty = false;  // only softness / bias_factor / local anchors changed: re-upload, no re-colouring
     bool any_poly = false;
     int n_large = 0;
     GridParams gp{1.0f, 1023};
@@ -2408,6 +2409,22 @@ int flush(SyltWorld* w) {
         color_joints(w);
         SYLT_CUDA(cudaStreamSynchronize(w->stream));
         w->joints_dirty = false;
+        w->jparams_dirty = false;
+    }
+    if (w->jparams_dirty) {  // pub Joint fields edited by the caller: same joint graph, new numbers
+        const size_t J = w->hj.size();
+        std::vector<float4> la(J);
+        std::vector<float2> pr(J);
+        for (size_t j = 0; j < J; j++) {
+            la[j] = make_float4(w->hj[j].la1x, w->hj[j].la1y, w->hj[j].la2x, w->hj[j].la2y);
+            pr[j] = make_float2(w->hj[j].softness, w->hj[j].bias_factor);
+        }
+        if (J) {
+            SYLT_CUDA(cudaMemcpyAsync(w->jla.p, la.data(), J * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+            SYLT_CUDA(cudaMemcpyAsync(w->jparam.p, pr.data(), J * sizeof(float2), cudaMemcpyHostToDevice, w->stream));
+            SYLT_CUDA(cudaStreamSynchronize(w->stream));
+        }
+        w->jparams_dirty = false;
     }
     return SYLT_OK;
 }
@@ -2997,11 +3014,76 @@ int sylt_world_add_joint(SyltWorld* w, uint64_t id1, uint64_t id2, float ax, flo
     if (!e && out_index) *out_index = (int32_t)w->hj.size() - 1;
     return e;
 }
+static bool same_bits(float a, float b) { return memcmp(&a, &b, sizeof a) == 0; }
 int sylt_world_set_joint_params(SyltWorld* w, int32_t j, float softness, float bias_factor) {
     if (!w || j < 0 || (size_t)j >= w->hj.size()) return SYLT_ERR_INVALID;
-    w->hj[(size_t)j].softness = softness;
-    w->hj[(size_t)j].bias_factor = bias_factor;
+    HostJoint& q = w->hj[(size_t)j];
+    if (same_bits(q.softness, softness) && same_bits(q.bias_factor, bias_factor)) return SYLT_OK;  // (wrappers push the pub fields before every step)
+    q.softness = softness;
+    q.bias_factor = bias_factor;
+    w->jparams_dirty = true;
+    return SYLT_OK;
+}
+int sylt_world_set_joint_local_anchors(SyltWorld* w, int32_t j, float la1x, float la1y, float la2x, float la2y) {
+    if (!w || j < 0 || (size_t)j >= w->hj.size()) return SYLT_ERR_INVALID;
+    HostJoint& q = w->hj[(size_t)j];
+    if (same_bits(q.la1x, la1x) && same_bits(q.la1y, la1y) && same_bits(q.la2x, la2x) && same_bits(q.la2y, la2y)) return SYLT_OK;
+    q.la1x = la1x; q.la1y = la1y; q.la2x = la2x; q.la2y = la2y;
+    w->jparams_dirty = true;
+    return SYLT_OK;
+}
+int sylt_world_add_joint_local(SyltWorld* w, uint64_t id1, uint64_t id2, float la1x, float la1y, float la2x, float la2y, float softness,
+                               float bias_factor, int32_t* out_index) {
+    if (!w) return SYLT_ERR_INVALID;
+    const int b1 = find_body(w, id1), b2 = find_body(w, id2);
+    if (b1 < 0 || b2 < 0) return SYLT_ERR_BODY_NOT_FOUND;
+    if (w->inflight) finish(w);
+    cudaSetDevice(w->device);
+    const size_t j0 = w->hj.size();
+    HostJoint j = {b1, b2, la1x, la1y, la2x, la2y, softness, bias_factor, 0};
+    w->hj.push_back(j);
+    SYLT_CUDA(w->jp.ensure(j0 + 2, j0, w->stream));  // accumulated impulses: the new joint starts at zero, existing ones are kept
+    SYLT_CUDA(cudaMemsetAsync(w->jp.p + j0, 0, sizeof(float2), w->stream));
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
     w->joints_dirty = true;
+    w->part_dirty = true;  // worlds with joints use k_solve
+    if (out_index) *out_index = (int32_t)j0;
+    return SYLT_OK;
+}
+
+// pub Body fields the reference reads on every step, written back as the caller has them (nothing is re-derived from mass)
+int sylt_world_set_body_props(SyltWorld* w, int32_t first, int32_t count, const float* props8) {
+    if (!w || first < 0 || count < 0 || (size_t)first + (size_t)count > w->hb.size() || (count > 0 && !props8)) return SYLT_ERR_INVALID;
+    if (count == 0) return SYLT_OK;
+    int e = flush(w);  // (drains the queue, uploads pending bodies)
+    if (e) return e;
+    std::vector<float4> hm((size_t)count), hg((size_t)count);
+    for (int k = 0; k < count; k++) {
+        HostBody& b = w->hb[(size_t)(first + k)];
+        const float* p = props8 + 8 * (size_t)k;
+        b.mass = p[0]; b.inv_mass = p[1]; b.moi = p[2]; b.inv_moi = p[3]; b.friction = p[6];
+        if (b.shape == SYLT_SHAPE_BOX) {  // collide() reads Body.width (collide.rs:141-142); box-polygon pairs keep using the vertices stored at Body::new
+            b.width_x = p[4]; b.width_y = p[5];
+            float r = 0.0f;
+            for (int v = 0; v < b.nverts; v++) {
+                const V2 l = w->hverts[(size_t)(b.vert_offset + v)];
+                r = std::max(r, sqrtf(l.x * l.x + l.y * l.y));
+            }
+            const float rb = 0.5f * sqrtf(b.width_x * b.width_x + b.width_y * b.width_y);
+            b.radius = (rb > r || !(r == r)) ? rb : r;
+            if (!(b.radius == b.radius)) b.radius = 0.0f;
+        }
+        hm[(size_t)k] = make_float4(b.inv_mass, b.inv_moi, b.friction, 0.0f);
+        float off;
+        const int o = b.vert_offset;
+        memcpy(&off, &o, 4);
+        hg[(size_t)k] = make_float4(b.width_x, b.width_y, off, b.radius);
+    }
+    SYLT_CUDA(cudaMemcpyAsync(w->mp.p + first, hm.data(), (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+    SYLT_CUDA(cudaMemcpyAsync(w->geom.p + first, hg.data(), (size_t)count * sizeof(float4), cudaMemcpyHostToDevice, w->stream));
+    SYLT_CUDA(cudaStreamSynchronize(w->stream));
+    w->class_dirty = true;   // static / large classification and the grid cell depend on inv_mass and the radius
+    w->joints_dirty = true;  // the joint colouring treats bodies without inverse mass as static
     return SYLT_OK;
 }
 

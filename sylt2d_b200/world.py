@@ -247,6 +247,15 @@ class World:
         self.L.sylt_world_get_body_props(self.h, ptr(out), out.shape[0])
         return out
 
+    def set_body_props(self, props, first=0):
+        """Write back the (n, 8) records of get_body_props (mass, inv_mass, moi, inv_moi, width.x, width.y, friction, shape):
+        the pub Body fields the reference reads on every step."""
+        p = np.ascontiguousarray(props, dtype=np.float32).reshape(-1, 8)
+        check(self.L.sylt_world_set_body_props(self.h, first, p.shape[0], ptr(p)))
+
+    def set_joint_local_anchors(self, joint_index, la1, la2):
+        check(self.L.sylt_world_set_joint_local_anchors(self.h, int(joint_index), la1[0], la1[1], la2[0], la2[1]))
+
     def get_arbiters(self):
         na, nc = self.num_arbiters, self.num_contacts
         arb = np.zeros(na, dtype=ARBITER)

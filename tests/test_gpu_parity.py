@@ -912,3 +912,64 @@ def test_capacity_overflow_is_transparent():
     bb.step_n(sc.dt, 90)
     _assert_states_equal(a.get_bodies(), bb.get_bodies(), "mixed pile, grown capacity")
     assert a.get_stats()["arbiters"] == bb.get_stats()["arbiters"] > 600
+
+
+def test_pub_body_and_joint_fields_written_between_steps():
+    """Body.friction / mass / inv_mass / moi / inv_moi / width and Joint.local_anchor_* are pub fields the reference reads on every
+    step (world.rs:115-118, arbiter.rs:128,198-211, collide.rs:141-142, joint.rs:67-68): a caller may overwrite them between steps."""
+    sc = scenes.demo8(10) if False else scenes.pyramid(6, 10)
+    w, o = _mk(sc)
+    for s in range(60):
+        if s == 20:
+            p = w.get_body_props()
+            assert np.array_equal(p, o.get_body_props())
+            p[3, 6] = 0.9                                   # friction: only arbiters created from now on see it (quirk Q-17)
+            p[5, 0], p[5, 1], p[5, 2], p[5, 3] = 40.0, 1.0 / 40.0, 40.0 * 2.0 / 12.0, 12.0 / (40.0 * 2.0)   # a heavier box
+            p[7, 4], p[7, 5] = 1.2, 0.8                     # width: collide() reads it every step
+            p[9, 1], p[9, 3] = 0.0, 0.0                     # inv_mass = inv_moi = 0: the body becomes static (kinematic: it keeps moving, quirk Q-16)
+            w.set_body_props(p)
+            o.set_body_props(p)
+        if s == 40:
+            p = w.get_body_props()
+            p[9, 1], p[9, 3] = 0.1, 6.0                     # ... and dynamic again
+            w.set_body_props(p[9:10], first=9)
+            o.set_body_props(p[9:10], first=9)
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"props step {s}")
+    _assert_arbiters_equal(w, o, what="props")
+    assert np.array_equal(w.get_body_props(), o.get_body_props())
+    # joints: local anchors edited after Joint::new
+    sc = scenes.multi_pendulum(10)
+    w, o = _mk(sc)
+    for s in range(50):
+        if s == 15:
+            gj = w.get_joints()
+            la1, la2 = (float(gj["la1x"][3]) + 0.1, float(gj["la1y"][3])), (float(gj["la2x"][3]), float(gj["la2y"][3]) - 0.05)
+            w.set_joint_local_anchors(3, la1, la2)
+            o.set_joint_local_anchors(3, la1, la2)
+            w.set_joint_params(5, 0.02, 0.1)
+            o.set_joint_params(5, 0.02, 0.1)
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"joint fields step {s}")
+    _assert_joints_equal(w.get_joints(), o.get_joints(), "joint fields")
+
+
+def test_rust_wrapper_call_sequence_replayed_in_cpp(tmp_path):
+    """rust/src/world.rs cannot be compiled here (no rustc): tests/cpp/wrapper_sequence.cpp replays its per-step protocol in C++ —
+    host-side bodies / joints with pub fields, diffed against a mirror (upload_dirty), sylt_world_step, mirror_back, lazy arbiter
+    fetch — incl. a bomb launch between steps, mutated state / properties / joint fields and a context toggle, and compares every
+    step with the oracle bit for bit."""
+    import subprocess
+    import __graft_entry__ as g
+    from tests.test_abi import ROOT
+    g.build()
+    exe = os.path.join(str(tmp_path), "wrapper_sequence")
+    lib, orcdir = os.path.join(ROOT, "sylt2d_b200"), os.path.join(ROOT, "oracle")
+    subprocess.run(["g++", "-std=c++17", "-Wall", "-O1", os.path.join(ROOT, "tests", "cpp", "wrapper_sequence.cpp"), "-L", lib, "-lsylt2d_b200",
+                    "-L", orcdir, "-lorc", f"-Wl,-rpath,{lib}", f"-Wl,-rpath,{orcdir}", "-o", exe], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 0 and "bit-identical" in r.stdout, r.stdout + r.stderr
