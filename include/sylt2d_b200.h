@@ -66,7 +66,8 @@ typedef struct {
     int32_t shape;            /* SYLT_SHAPE_* */
     int32_t vert_offset;      /* polygons: first vertex in the `verts` array passed alongside */
     int32_t vert_count;
-    int32_t _pad;
+    int32_t group;            /* collision group, 0 .. 65535 (default 0): bodies of different groups never collide, so ONE World can hold many
+                                 independent worlds — boxes and polygons — stepped by the same launches (ids must stay unique and increasing) */
     float width_x, width_y;   /* boxes: Body.width; polygons: ignored (bounding box is recomputed, body.rs:263) */
     float mass, friction;     /* mass == FLT_MAX  =>  static (body.rs:208-216) */
     float x, y, rotation, vx, vy, angular_velocity;

@@ -18,7 +18,7 @@ pub const SYLT_MAX_MANIFOLD: usize = 2 * SYLT_MAX_POLY_VERTS;
 #[repr(C)]
 #[derive(Clone, Copy, Default, Debug)]
 pub struct SyltBodyDesc {
-    pub id: u64, pub shape: i32, pub vert_offset: i32, pub vert_count: i32, pub _pad: i32,
+    pub id: u64, pub shape: i32, pub vert_offset: i32, pub vert_count: i32, pub group: i32,
     pub width_x: f32, pub width_y: f32, pub mass: f32, pub friction: f32,
     pub x: f32, pub y: f32, pub rotation: f32, pub vx: f32, pub vy: f32, pub angular_velocity: f32,
 }
@@ -27,7 +27,7 @@ pub fn desc_of(b: &crate::body::Body, vert_offset: i32, vert_count: i32) -> Sylt
     SyltBodyDesc {
         id: b.id as u64,
         shape: match b.shape { crate::body::Shape::Box => SYLT_SHAPE_BOX, crate::body::Shape::ConvexPolygon => SYLT_SHAPE_POLYGON },
-        vert_offset, vert_count, _pad: 0, width_x: b.width.x, width_y: b.width.y, mass: b.mass, friction: b.friction,
+        vert_offset, vert_count, group: 0, width_x: b.width.x, width_y: b.width.y, mass: b.mass, friction: b.friction,
         x: b.position.x, y: b.position.y, rotation: b.rotation, vx: b.velocity.x, vy: b.velocity.y, angular_velocity: b.angular_velocity,
     }
 }

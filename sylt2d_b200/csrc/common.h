@@ -58,6 +58,7 @@ struct DBuf {
 struct HostBody {
     uint64_t id;
     int shape, nverts, vert_offset;
+    int group;     // collision group (SyltBodyDesc.group): bodies of different groups never pair
     float width_x, width_y, mass, inv_mass, moi, inv_moi, friction;
     float radius;  // bounding radius about the body position (broad phase only; not in the reference)
 };
@@ -98,6 +99,8 @@ inline float host_poly_moi(const std::vector<V2>& v) {
 inline int make_host_body(const SyltBodyDesc& d, const float* verts_xy, int n_verts_total, HostBody* hb, std::vector<V2>* local_verts) {
     hb->id = d.id;
     hb->shape = d.shape;
+    if (d.group < 0 || d.group > 0xffff) return SYLT_ERR_INVALID;
+    hb->group = d.group;
     hb->mass = d.mass;
     hb->friction = d.friction;
     std::vector<V2> v;

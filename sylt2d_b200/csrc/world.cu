@@ -167,9 +167,14 @@ __device__ __forceinline__ int cell_coord(float x, float cell) {
     q = fminf(fmaxf(q, -1.0e9f), 1.0e9f);
     return (int)q;
 }
-__device__ __forceinline__ int cell_hash(int cx, int cy, int mask) {
-    return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u)) & mask;
+__device__ __forceinline__ int cell_hash(int cx, int cy, int mask, int group = 0) {
+    return (int)(((unsigned)cx * 73856093u) ^ ((unsigned)cy * 19349663u) ^ ((unsigned)group * 2654435761u)) & mask;
 }
+// Collision groups (SyltBodyDesc.group): bodies of different groups never pair, i.e. one SyltWorld can hold many independent worlds
+// (boxes AND polygons) that share gravity / iterations / context and are stepped by the same launches.  The group sits in the upper
+// half of the flag word that travels with every cell entry, so the candidate test costs one more compare.
+constexpr int GROUP_SHIFT = 16;
+__device__ __forceinline__ int group_of(int flags) { return (int)((unsigned)flags >> GROUP_SHIFT); }
 __device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
     return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w);
 }
@@ -237,7 +242,7 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const floa
     if (!(fl & FLAG_LARGE)) {
         cx = cell_coord(0.5f * (minx + maxx), gp.cell);
         cy = cell_coord(0.5f * (miny + maxy), gp.cell);
-        int h = cell_hash(cx, cy, gp.mask);
+        int h = cell_hash(cx, cy, gp.mask, group_of(fl));
         rank[i] = atomicAdd(&cell_count[h], 1);
         if (maxx - minx > gp.cell || maxy - miny > gp.cell) atomicAdd(&cn->warn_ext, 1);
     }
@@ -254,7 +259,7 @@ __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, co
     if (i >= B) return;
     int4 ci = cinfo[i];
     if (ci.z & FLAG_LARGE) return;
-    int pos = cell_start[cell_hash(ci.x, ci.y, gp.mask)] + rank[i];
+    int pos = cell_start[cell_hash(ci.x, ci.y, gp.mask, group_of(ci.z))] + rank[i];
     cent_info[2 * pos] = make_int4(i, ci.x, ci.y, ci.z);  // info and AABB of an entry share one 32-byte sector
     cent_aabb[2 * pos] = aabb[i];
 }
@@ -266,8 +271,11 @@ constexpr int ROWTMP = 16;
 
 template <typename F>
 __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, const float4* aabb, const int4* cinfo, const int* cell_start,
-                                           const int4* cent_info, const float4* cent_aabb, const int* large, int n_large, GridParams gp, F&& found) {
+                                           const int4* cent_info, const float4* cent_aabb, const int* large_all, const int* large_start, GridParams gp, F&& found) {
     const bool st_i = (ci.z & FLAG_STATIC) != 0;
+    const int grp = group_of(ci.z);
+    const int* large = large_all + large_start[grp];                       // the large bodies of this body's group
+    const int n_large = large_start[grp + 1] - large_start[grp];
     if (!(ci.z & FLAG_LARGE)) {
         int x0 = cell_coord(my.x - 0.5f * gp.cell, gp.cell), x1 = cell_coord(my.z + 0.5f * gp.cell, gp.cell);
         int y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell), y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
@@ -278,7 +286,7 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
             for (int q = 0; q < 9; q++) {
                 int cx = x0 + q % 3, cy = y0 + q / 3;
                 bool ok = cx <= x1 && cy <= y1;
-                int h = cell_hash(cx, cy, gp.mask);
+                int h = cell_hash(cx, cy, gp.mask, grp);
                 k0[q] = ok ? cell_start[h] : 0;
                 k1[q] = ok ? cell_start[h + 1] : 0;
             }
@@ -288,7 +296,7 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
                 for (int k = k0[q]; k < k1[q]; k++) {
                     int4 cj = cent_info[2 * k];
                     float4 ab = cent_aabb[2 * k];
-                    if (cj.x <= i || cj.y != cx || cj.z != cy) continue;  // lower index owns the pair; another cell may share the bucket
+                    if (cj.x <= i || cj.y != cx || cj.z != cy || group_of(cj.w) != grp) continue;  // lower index owns the pair; another cell (or group) may share the bucket
                     if (st_i && (cj.w & FLAG_STATIC)) continue;
                     if (aabb_overlap(my, ab)) found(cj.x);
                 }
@@ -296,11 +304,11 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
         } else {
             for (int cy = y0; cy <= y1; cy++)
                 for (int cx = x0; cx <= x1; cx++) {
-                    int h = cell_hash(cx, cy, gp.mask);
+                    int h = cell_hash(cx, cy, gp.mask, grp);
                     int ke = cell_start[h + 1];
                     for (int k = cell_start[h]; k < ke; k++) {
                         int4 cj = cent_info[2 * k];
-                        if (cj.x <= i || cj.y != cx || cj.z != cy) continue;
+                        if (cj.x <= i || cj.y != cx || cj.z != cy || group_of(cj.w) != grp) continue;
                         if (st_i && (cj.w & FLAG_STATIC)) continue;
                         if (aabb_overlap(my, cent_aabb[2 * k])) found(cj.x);
                     }
@@ -331,8 +339,8 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
 // same buckets.  (Measured at 100k bodies: one thread per body 36 us, 16 lanes with a cell each 49 us — issue-bound, 32 M warp
 // instructions —, 4 lanes 39 us with 40 % of the lanes active.)
 __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
-                                                    const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_count, int* row_tmp,
-                                                    const Counters* cn, int* row_btot) {
+                                                    const float4* cent_aabb, const int* large_all, int n_large_all, const int* large_start, GridParams gp,
+                                                    int* row_count, int* row_tmp, const Counters* cn, int* row_btot) {
     pdl_wait();
     pdl_trigger();
     const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -340,17 +348,18 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     int i;
     float4 my;
     int4 ci;
-    if (g < B - n_large) {  // the cell-ordered entry already carries the body's index, cell, flags and AABB: one load level less
+    if (g < B - n_large_all) {  // the cell-ordered entry already carries the body's index, cell, flags and AABB: one load level less
         const int4 ce = cent_info[2 * g];
         my = cent_aabb[2 * g];
         i = ce.x;
         ci = make_int4(ce.y, ce.z, ce.w, 0);
     } else {
-        i = large[g - (B - n_large)];
+        i = large_all[g - (B - n_large_all)];
         my = aabb[i];
         ci = cinfo[i];
     }
     const bool st_i = (ci.z & FLAG_STATIC) != 0;
+    const int grp = group_of(ci.z);
     int* tmp = row_tmp + (size_t)i * ROWTMP;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
     bool fast = false;
@@ -362,7 +371,7 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     if (!fast) {  // warp-uniform
         if (lane == 0) {
             int cnt = 0;
-            row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) {
+            row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large_all, large_start, gp, [&](int j) {
                 if (cnt < ROWTMP) tmp[cnt] = j;
                 cnt++;
             });
@@ -376,12 +385,13 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     const int cx = x0 + lane % 3, cy = y0 + lane / 3;
     if (lane < 9) {
         if (cx <= x1 && cy <= y1) {
-            const int h = cell_hash(cx, cy, gp.mask);
+            const int h = cell_hash(cx, cy, gp.mask, grp);
             seg_k0 = cell_start[h];
             seg_n = cell_start[h + 1] - seg_k0;
         }
-    } else if (lane == 9) {
-        seg_n = n_large;
+    } else if (lane == 9) {  // the large bodies of this body's group
+        seg_k0 = large_start[grp];
+        seg_n = large_start[grp + 1] - seg_k0;
     }
     int seg_end = seg_n;  // inclusive prefix
 #pragma unroll
@@ -407,10 +417,10 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
                 const float4 ab = cent_aabb[2 * k];
                 const int scx = x0 + seg % 3, scy = y0 + seg / 3;
                 // lower index owns the pair; another cell may share the bucket; static-static pairs are skipped (world.rs:79-81)
-                hit = cj.x > i && cj.y == scx && cj.z == scy && !(st_i && (cj.w & FLAG_STATIC)) && aabb_overlap(my, ab);
+                hit = cj.x > i && cj.y == scx && cj.z == scy && group_of(cj.w) == grp && !(st_i && (cj.w & FLAG_STATIC)) && aabb_overlap(my, ab);
                 partner = cj.x;
             } else {
-                const int j = large[off];
+                const int j = large_all[s_k0 + off];
                 hit = !(st_i && (cinfo[j].z & FLAG_STATIC)) && aabb_overlap(my, aabb[j]);
                 partner = j;
             }
@@ -427,7 +437,7 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
 }
 
 __global__ void __launch_bounds__(ROW_BLK) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
-                                                       const float4* cent_aabb, const int* large, int n_large, GridParams gp, int* row_start, const int* row_tmp,
+                                                       const float4* cent_aabb, const int* large, const int* large_start, GridParams gp, int* row_start, const int* row_tmp,
                                                        int2* pairs, int cap_pairs, Counters* cn, const int* row_count, const int* row_btot) {
     __shared__ int sh[34];
     pdl_wait();
@@ -470,7 +480,7 @@ __global__ void __launch_bounds__(ROW_BLK) k_rows_emit(int B, const float4* aabb
         return;
     }
     int m = 0;
-    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cent_info, cent_aabb, large, n_large, gp, [&](int j) { pairs[base + m++] = make_int2(i, j); });
+    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cent_info, cent_aabb, large, large_start, gp, [&](int j) { pairs[base + m++] = make_int2(i, j); });
     for (int a = 1; a < n; a++) {
         int2 x = pairs[base + a];
         int b = a - 1;
@@ -1864,7 +1874,8 @@ __device__ __forceinline__ unsigned morton_spread(unsigned v) {  // 0b abcdefg -
     v = (v | (v << 1)) & 0x5555u;
     return v;
 }
-__global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* pose, int* perm, int* key_tmp, const Counters* cn) {
+__global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* pose, int* perm, int* key_tmp, const Counters* cn, const int* bflags,
+                                                          int n_groups) {
     extern __shared__ int s_hist[];  // SORT_CELLS + 1
     if (step_failed(cn)) return;
     __shared__ float s_red[4][32];
@@ -1922,13 +1933,15 @@ __global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* p
     __syncthreads();
     const float span = fmaxf(fmaxf(x1 - x0, y1 - y0), 1.0e-3f);
     const float inv = (float)(1 << SORT_BITS) / (span * 1.0001f);
-    auto key_of = [&](float4 p) -> int {
+    auto key_of = [&](int i, float4 p) -> int {
+        // several collision groups (independent worlds in one World): a region is a run of whole groups, wherever their bodies are
+        if (n_groups > 1) return (int)((long long)group_of(bflags[i]) * SORT_CELLS / n_groups);
         if (!(fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f)) return 0;
         const int cx = min((1 << SORT_BITS) - 1, max(0, (int)((p.x - x0) * inv))), cy = min((1 << SORT_BITS) - 1, max(0, (int)((p.y - y0) * inv)));
         return (int)(morton_spread((unsigned)cx) | (morton_spread((unsigned)cy) << 1));
     };
     for_bodies([&](int i, float4 p) {
-        const int k = key_of(p);
+        const int k = key_of(i, p);
         key_tmp[i] = k;
         atomicAdd(&s_hist[k], 1);
     });
@@ -2074,7 +2087,8 @@ struct SyltWorld {
     // device state
     DBuf<float4> pose, vel, force, mp, geom, aabb;
     DBuf<float2> rotc, lverts;
-    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, large, row_count, row_start, row_tmp;
+    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, large, large_start, row_count, row_start, row_tmp;
+    int n_groups = 1;        // collision groups in use (SyltBodyDesc.group)
     DBuf<int4> cinfo, cent_info;  // cent_info: interleaved (info, AABB) entries of the cell-ordered copy
     DBuf<int2> pairs;
     DBuf<unsigned long long> info, pscan, claim, spart64, pair_btot;
@@ -2309,13 +2323,23 @@ int flush(SyltWorld* w) {
         }
         cell = 1.1f * cell + 0.1f;
         std::vector<int> fl(B), large;
+        int n_groups = 1;
         for (size_t i = 0; i < B; i++) {
             const HostBody& b = w->hb[i];
-            int f = (b.shape == SYLT_SHAPE_POLYGON ? FLAG_POLY : 0) | (b.inv_mass == 0.0f ? FLAG_STATIC : 0) | (b.nverts << 8);
+            int f = (b.shape == SYLT_SHAPE_POLYGON ? FLAG_POLY : 0) | (b.inv_mass == 0.0f ? FLAG_STATIC : 0) | (b.nverts << 8) | (b.group << GROUP_SHIFT);
             if (2.2f * b.radius + 0.1f > cell || !(b.radius == b.radius)) { f |= FLAG_LARGE; large.push_back((int)i); }
             fl[i] = f;
+            n_groups = std::max(n_groups, b.group + 1);
         }
         w->n_large = (int)large.size();
+        w->n_groups = n_groups;
+        // the large bodies (ground, walls) bypass the grid: every body tests the ones of its own group — a CSR by group, index order inside
+        std::stable_sort(large.begin(), large.end(), [&](int x, int y) { return w->hb[(size_t)x].group < w->hb[(size_t)y].group; });
+        std::vector<int> lstart((size_t)n_groups + 1, 0);
+        for (int j : large) lstart[(size_t)w->hb[(size_t)j].group + 1]++;
+        for (int g = 0; g < n_groups; g++) lstart[(size_t)g + 1] += lstart[(size_t)g];
+        SYLT_CUDA(w->large_start.ensure((size_t)n_groups + 2));
+        SYLT_CUDA(cudaMemcpyAsync(w->large_start.p, lstart.data(), lstart.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
         int buckets = 1024;
         while ((size_t)buckets < 2 * B) buckets <<= 1;
         w->buckets = buckets;
@@ -2508,11 +2532,11 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     mark();
     const int nbR = (B + ROW_BLK - 1) / ROW_BLK;
     SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B + 3) / 4)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
-                         (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->gp, w->row_count.p, w->row_tmp.p, cn, w->row_btot.p));
+                         (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->large_start.p, w->gp, w->row_count.p, w->row_tmp.p, cn, w->row_btot.p));
     w->launches += 2;
     mark();
     SYLT_CUDA(launch_pdl(k_rows_emit, dim3((unsigned)nbR), dim3(ROW_BLK), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1),
-                         w->large.p, w->n_large, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn, w->row_count.p, w->row_btot.p));
+                         w->large.p, w->large_start.p, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn, w->row_count.p, w->row_btot.p));
     w->launches += 1;
     mark();
     const int gridP = w->num_sms * 8;
@@ -2527,7 +2551,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
     if (recut_due(w, full_step)) {
         // (re)partition by the current positions and last step's load (device side, no synchronisation); the colours encode the old cut
-        k_resort<<<1, REBAL_THREADS, (SORT_CELLS + 1) * sizeof(int), st>>>(B, w->pose.p, w->reg_bodies.p, w->sort_keys.p, cn);
+        k_resort<<<1, REBAL_THREADS, (SORT_CELLS + 1) * sizeof(int), st>>>(B, w->pose.p, w->reg_bodies.p, w->sort_keys.p, cn, w->bflags.p, w->n_groups);
         SYLT_CUDA(cudaGetLastError());
         k_rebalance<<<1, REBAL_THREADS, 0, st>>>(B, w->n_regions, w->reg_bodies.p, w->have_old ? old.row_start : nullptr, w->B_old, w->region_of.p,
                                                  w->lidx.p, w->reg_start.p, cn);
@@ -2863,7 +2887,7 @@ static void free_all(SyltWorld* w) {
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
-    w->row_start.release(); w->row_tmp.release(); w->row_btot.release(); w->pair_btot.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
+    w->row_start.release(); w->row_tmp.release(); w->large_start.release(); w->row_btot.release(); w->pair_btot.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
     w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
     w->prop.release(); w->order.release(); w->sincl32.release(); w->sincl64.release(); w->scan_flag.release(); w->scan_ticket.release();
     for (int k = 0; k < 2; k++) {

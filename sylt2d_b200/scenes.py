@@ -11,7 +11,7 @@ import numpy as np
 
 F32_MAX = float(np.finfo(np.float32).max)
 
-BODY_DESC = np.dtype([("id", "<u8"), ("shape", "<i4"), ("vert_offset", "<i4"), ("vert_count", "<i4"), ("_pad", "<i4"),
+BODY_DESC = np.dtype([("id", "<u8"), ("shape", "<i4"), ("vert_offset", "<i4"), ("vert_count", "<i4"), ("group", "<i4"),
                       ("width_x", "<f4"), ("width_y", "<f4"), ("mass", "<f4"), ("friction", "<f4"),
                       ("x", "<f4"), ("y", "<f4"), ("rotation", "<f4"), ("vx", "<f4"), ("vy", "<f4"), ("angular_velocity", "<f4")])
 JOINT_DESC = np.dtype([("id1", "<u8"), ("id2", "<u8"), ("anchor_x", "<f4"), ("anchor_y", "<f4"),
@@ -327,3 +327,32 @@ def tile_worlds(scene, n_worlds, seed=0, x_jitter=0.0, omega_jitter=0.0):
     body_off = (np.arange(n_worlds + 1, dtype=np.int64) * nb).astype(np.int32)
     joint_off = (np.arange(n_worlds + 1, dtype=np.int64) * nj).astype(np.int32)
     return bodies, body_off, joints, joint_off
+
+
+def group_worlds(scene, n_worlds, seed=0, x_jitter=0.0, omega_jitter=0.0):
+    """`n_worlds` independent copies of one scene inside ONE World: copy k gets collision group k (SyltBodyDesc.group), so
+    its bodies never meet the other copies', and ids k * stride + id (unique and increasing, as World::add_body needs).
+    Unlike tile_worlds / Batch this also takes polygon scenes.  Returns (scene, stride)."""
+    nb, nj = scene.bodies.shape[0], scene.joints.shape[0]
+    if n_worlds > 65536:
+        raise ValueError("at most 65536 collision groups")
+    stride = int(scene.bodies["id"].max()) + 1
+    bodies = np.tile(scene.bodies, n_worlds)
+    joints = np.tile(scene.joints, n_worlds)
+    k = np.repeat(np.arange(n_worlds, dtype=np.uint64), nb)
+    bodies["id"] = bodies["id"] + k * np.uint64(stride)
+    bodies["group"] = k.astype(np.int32)
+    if nj:
+        kj = np.repeat(np.arange(n_worlds, dtype=np.uint64), nj)
+        joints["id1"] = joints["id1"] + kj * np.uint64(stride)
+        joints["id2"] = joints["id2"] + kj * np.uint64(stride)
+    dyn = scene.bodies["mass"] < F32_MAX
+    rng = np.random.default_rng(seed)
+    if x_jitter:
+        jit = rng.uniform(-x_jitter, x_jitter, (n_worlds, nb)).astype(np.float32) * dyn[None, :]
+        bodies["x"] = (bodies["x"].reshape(n_worlds, nb) + jit).reshape(-1)
+    if omega_jitter and nb > 1:
+        w = bodies["angular_velocity"].reshape(n_worlds, nb).copy()
+        w[:, 1] = rng.uniform(-omega_jitter, omega_jitter, n_worlds).astype(np.float32)
+        bodies["angular_velocity"] = w.reshape(-1)
+    return Scene(f"{scene.name}x{n_worlds}", bodies, joints, scene.verts, scene.gravity, scene.iterations, scene.dt, scene.ctx), stride

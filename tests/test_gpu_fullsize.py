@@ -270,3 +270,48 @@ def test_region_solver_with_the_samples_100_iterations(monkeypatch):
     sc = scenes.pyramid(12, 100)                                                           # the reference's literal demo5
     w, o = _fresh_pair(sc)
     _lockstep_from(sc, w, o, 40, "pyramid12 I=100 regions")
+
+
+def _grouped_lockstep(scene, n_worlds, steps, sample, x_jitter=0.0, check_every=1):
+    """n_worlds copies of `scene` as collision groups of ONE World; the sampled copies in lock-step with one oracle world each."""
+    from sylt2d_b200 import World
+    big, stride = scenes.group_worlds(scene, n_worlds, seed=3, x_jitter=x_jitter)
+    nb, nj = scene.num_bodies, int(scene.joints.shape[0])
+    w = World(big.gravity, big.iterations, device=0)
+    w.load_scene(big)
+    oracles = {}
+    for k in sample:
+        sc_k = scenes.Scene(scene.name, big.bodies[k * nb:(k + 1) * nb].copy(), scene.joints, scene.verts, scene.gravity, scene.iterations, scene.dt, scene.ctx)
+        sc_k.bodies["id"] -= np.uint64(k * stride)
+        sc_k.bodies["group"] = 0
+        o = orc.OracleWorld(scene.gravity, scene.iterations, sincos_mode=1)
+        o.load_scene(sc_k)
+        oracles[k] = o
+    for s in range(steps):
+        w.step(big.dt)
+        arb, _ = w.get_arbiters()
+        world_of = (arb["id1"] // np.uint64(stride)).astype(np.int64)
+        assert np.array_equal(world_of, (arb["id2"] // np.uint64(stride)).astype(np.int64)), "an arbiter between two groups"
+        jo_all = w.get_joint_order()
+        st = w.get_bodies()
+        for k, o in oracles.items():
+            a = arb[world_of == k]
+            order = np.lexsort((a["id2"], a["id1"], a["color"]))
+            keys = np.stack([a["id1"][order] % np.uint64(stride), a["id2"][order] % np.uint64(stride)], axis=1).astype(np.uint64)
+            jo = jo_all[(jo_all >= k * nj) & (jo_all < (k + 1) * nj)] - k * nj
+            o.step_ordered(big.dt, keys, jo)
+            if s % check_every == 0 or s == steps - 1:
+                _assert_states_equal(st[k * nb:(k + 1) * nb], o.get_bodies(), f"{big.name} group {k} step {s}")
+    return w
+
+
+def test_independent_polygon_worlds_as_collision_groups():
+    """Batched worlds WITH polygons (the one-CTA-per-world kernel is boxes + joints only): one World, one collision group per
+    world — Arbiter::new's dispatch to collide_polygons for any non-box pair (arbiter.rs:124-127) in every world, bit-exact."""
+    w = _grouped_lockstep(scenes.demo8(10), 12, 80, sample=[0, 5, 11], x_jitter=0.01, check_every=4)     # polygons + boxes (k_solve: < 1000 bodies)
+    assert w.get_stats()["arbiters"] > 50
+    w = _grouped_lockstep(scenes.demo10(10), 6, 60, sample=[0, 3, 5], check_every=4)                      # the samples' polygon demo
+    w = _grouped_lockstep(scenes.multi_pendulum(10), 8, 60, sample=[0, 7], check_every=4)                 # joints across groups share colours
+    w = _grouped_lockstep(scenes.mixed_pile(150, seed=5), 16, 90, sample=[0, 9, 15], x_jitter=0.005, check_every=6)  # 2.4k bodies: region solver, regions = runs of groups
+    ga, _ = w.get_arbiters()
+    assert ga.shape[0] > 500 and (ga["color"] < 32).any()
