@@ -179,8 +179,9 @@ __device__ __forceinline__ bool aabb_overlap(float4 a, float4 b) {
     return !(a.x > b.z || b.x > a.z || a.y > b.w || b.y > a.w);
 }
 
-// per-step counters back to zero — unless an earlier step of the call failed: its counts are what the host grows the buffers from
-__global__ void k_reset_counters(Counters* cn) {
+// per-step counters back to zero — unless an earlier step of the call failed: its counts are what the host grows the buffers from.
+// Done by block 0 of k_prepare (nothing reads or writes them before the kernels behind it).
+__device__ __forceinline__ void reset_step_counters(Counters* cn) {
     if (step_failed(cn)) return;
     int* p = &cn->n_pairs;
     const int n = (int)((sizeof(Counters) - offsetof(Counters, n_pairs)) / sizeof(int));
@@ -192,6 +193,7 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const floa
                                                  int* cell_count, int* rank, GridParams gp, float gx, float gy, float dt, int integrate,
                                                  Counters* cn, ulonglong2* vrec, unsigned long long* used, unsigned* used_int, int* row_btot) {
     pdl_trigger();
+    if (blockIdx.x == 0) reset_step_counters(cn);
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= B) return;
     if ((i & (ROW_BLK - 1)) == 0) row_btot[i / ROW_BLK] = 0;  // candidates per block of bodies: accumulated by k_rows_count
@@ -244,7 +246,6 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const floa
         cy = cell_coord(0.5f * (miny + maxy), gp.cell);
         int h = cell_hash(cx, cy, gp.mask, group_of(fl));
         rank[i] = atomicAdd(&cell_count[h], 1);
-        if (maxx - minx > gp.cell || maxy - miny > gp.cell) atomicAdd(&cn->warn_ext, 1);
     }
     cinfo[i] = make_int4(cx, cy, fl, 0);
 }
@@ -561,7 +562,8 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int2* pairs, const unsigned long long* info, unsigned long long* scan, const unsigned long long* pair_btot,
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
-                                               unsigned long long* used, int* uncolored, int fix_features, int keep_colors, unsigned* used_int, int regions) {
+                                               unsigned long long* used, int* uncolored, int fix_features, int keep_colors, unsigned* used_int, int regions,
+                                               const int* region_of) {
     pdl_wait();
     const int failed = __ldcg(&cn->err);
     int P = min(__ldcg(&cn->n_pairs), cap_pairs);
@@ -605,15 +607,28 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         if (have_old && b2 < B_old) {
             int oo, op;
             pair_owner(b1, b2, bflags_old[b1], bflags_old[b2], &oo, &op);
-            int lo = old.row_start[oo], hi = old.row_start[oo + 1];
-            for (int k = lo; k < hi; k++)
-                if (old.partner[k] == op) { found = k; break; }
+            const int lo = old.row_start[oo], hi = old.row_start[oo + 1];
+            int part[8];  // rows are short: fetch the partners side by side (independent loads), then compare
+#pragma unroll
+            for (int k = 0; k < 8; k++) part[k] = lo + k < hi ? old.partner[lo + k] : -1;
+#pragma unroll
+            for (int k = 7; k >= 0; k--)
+                if (part[k] == op) found = lo + k;
+            for (int k = lo + 8; k < hi && found < 0; k++)
+                if (old.partner[k] == op) found = k;
         }
         float fr, pn = 0.0f, pt = 0.0f, pnb = 0.0f;
         int color = -1;
         if (found >= 0) {
             fr = old.friction[found];  // quirk Q-17: friction fixed at first insertion
-            if (keep_colors) color = old.color[found];  // dropped once after every repartition (the colour carries the arbiter's class)
+            if (keep_colors) color = old.color[found];  // (all dropped when the region solver is switched on or off: the ranges mean something else)
+            if (keep_colors == 2 && color >= 0) {       // the regions were just re-cut: a colour survives if its class does — interior
+                // (all dynamic bodies in the owner's region, colour < GEN_BIT) or generic.  Only arbiters near the new borders change.
+                const int R = region_of[pr.x];          // pr.x owns the pair
+                const bool s1 = (bflags[b1] & FLAG_STATIC) != 0, s2 = (bflags[b2] & FLAG_STATIC) != 0;
+                const bool interior = (s1 || region_of[b1] == R) && (s2 || region_of[b2] == R);
+                if ((color < GEN_BIT) != interior) color = -1;
+            }
             if (warm) {                // quirk Q-2: every new contact inherits old contact 0
                 int oc = old.meta[found].y;
                 float4 c = old.cc[oc];
@@ -1863,148 +1878,262 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     stamp(7);
 }
 
+// ------------------------------------------------------------------ re-cut of the regions (every `regions_period` steps)
 // Spatial order of the bodies for the region solver: a counting sort by the Z-order (Morton) index of a 128 x 128 grid laid
 // over the bounding box of the bodies, then by body index inside a cell (so the order, and with it the solve order, is
-// reproducible).  Consecutive runs of that order are compact blobs; k_rebalance cuts it into regions.  One CTA, every
-// `regions_period` steps; any order is valid, compactness only decides how many arbiters cross regions.
-constexpr int REBAL_THREADS = 1024, SORT_BITS = 7, SORT_CELLS = 1 << (2 * SORT_BITS);
+// reproducible); consecutive runs of that order are compact blobs.  The order is then cut into G regions of equal load: weight
+// of a body = 1 + 2 x (arbiters it owned last step), floored at the average weight so that no region gets more than twice the
+// average number of bodies (k_solve_regions keeps a region's bodies in shared memory).  Regions are consecutive runs of `perm`,
+// so perm itself is the CSR body list.  Any order is valid; compactness only decides how many arbiters cross regions.
+// ONE cooperative launch over all SMs (grid barriers between the phases; every sum is an integer, so the cut does not depend on
+// the number of CTAs): ~50 us at 100k bodies, where the single-CTA kernels it replaces took ~800 us.
+constexpr int RECUT_THREADS = 512, SORT_BITS = 7, SORT_CELLS = 1 << (2 * SORT_BITS), TRIM_BINS = 1024, TRIM_ROUNDS = 4;
+struct RecutScratch {  // zeroed by a memset in front of every launch
+    unsigned bar;
+    unsigned box[4];                         // order-preserving unsigned images of (-x0, x1, -y0, y1): all reduced with atomicMax (0 = nothing yet)
+    int trim[TRIM_ROUNDS][2 * TRIM_BINS];    // coordinate histograms of the trimming rounds (x, then y)
+    int hist[SORT_CELLS + 1];                // bodies per Morton cell
+    int fill[SORT_CELLS];                    // scatter cursors
+    long long part[1024], epart[1024];       // per-CTA sums of the weights / the floored weights
+    int first[1025];                         // B - (first position of region g), reduced with atomicMax (0 = empty)
+    unsigned long long stamp[16];            // %globaltimer of CTA 0 at the phase boundaries (diagnostics, SYLT_SOLVER_TIMING)
+};
 __device__ __forceinline__ unsigned morton_spread(unsigned v) {  // 0b abcdefg -> 0b 0a0b0c0d0e0f0g
     v = (v | (v << 4)) & 0x0f0fu;
     v = (v | (v << 2)) & 0x3333u;
     v = (v | (v << 1)) & 0x5555u;
     return v;
 }
-__global__ void __launch_bounds__(REBAL_THREADS) k_resort(int B, const float4* pose, int* perm, int* key_tmp, const Counters* cn, const int* bflags,
-                                                          int n_groups) {
-    extern __shared__ int s_hist[];  // SORT_CELLS + 1
-    if (step_failed(cn)) return;
-    __shared__ float s_red[4][32];
-    __shared__ int s_scan2[34];
+__device__ __forceinline__ int float_order(float f) { const int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }   // monotonic float -> int
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(RECUT_THREADS, 1) k_recut(int B, int G, const float4* pose, const int* bflags, int n_groups, const int* old_row_start,
+                                                           int B_old, int* perm, int* key_tmp, int* region_of, int* lidx, int* reg_start,
+                                                           RecutScratch* sc, const Counters* cn) {
+    extern __shared__ int s_cells[];  // SORT_CELLS + 1: cell offsets (also staging for the trimming histograms)
+    __shared__ long long sh64[34];
+    __shared__ int sh32[34];
+    __shared__ int s_lohi[4];
+    if (step_failed(cn)) return;  // grid-uniform at entry
     const int lt = threadIdx.x, T = blockDim.x, lane = lt & 31, wid = lt >> 5;
-    float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
-    auto for_bodies = [&](auto&& f) {
-        for (int i = lt; i < B; i += T) f(i, pose[i]);
-    };
-    for_bodies([&](int, float4 p) {
-        if (fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f) { x0 = fminf(x0, p.x); x1 = fmaxf(x1, p.x); y0 = fminf(y0, p.y); y1 = fmaxf(y1, p.y); }
-    });
+    const int tid = blockIdx.x * T + lt, nth = gridDim.x * T;
+    unsigned bar_target = 0;
+    int n_stamp = 0;
+    auto stamp = [&]() { if (tid == 0 && n_stamp < 16) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); sc->stamp[n_stamp++] = t; } };
+    stamp();
+    auto finite = [](float4 p) { return fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f; };
+    // ---- 1. bounding box of the (finite) body positions
+    {
+        float x0 = 3.0e38f, x1 = -3.0e38f, y0 = 3.0e38f, y1 = -3.0e38f;
+        for (int i = tid; i < B; i += nth) {
+            const float4 p = pose[i];
+            if (finite(p)) { x0 = fminf(x0, p.x); x1 = fmaxf(x1, p.x); y0 = fminf(y0, p.y); y1 = fmaxf(y1, p.y); }
+        }
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
-        y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        for (int o = 16; o > 0; o >>= 1) {
+            x0 = fminf(x0, __shfl_xor_sync(0xffffffffu, x0, o)); x1 = fmaxf(x1, __shfl_xor_sync(0xffffffffu, x1, o));
+            y0 = fminf(y0, __shfl_xor_sync(0xffffffffu, y0, o)); y1 = fmaxf(y1, __shfl_xor_sync(0xffffffffu, y1, o));
+        }
+        if (lane == 0 && x0 <= x1) {
+            atomicMax(&sc->box[0], (unsigned)float_order(-x0) ^ 0x80000000u); atomicMax(&sc->box[1], (unsigned)float_order(x1) ^ 0x80000000u);
+            atomicMax(&sc->box[2], (unsigned)float_order(-y0) ^ 0x80000000u); atomicMax(&sc->box[3], (unsigned)float_order(y1) ^ 0x80000000u);
+        }
     }
-    if (lane == 0) { s_red[0][wid] = x0; s_red[1][wid] = x1; s_red[2][wid] = y0; s_red[3][wid] = y1; }
-    for (int k = lt; k <= SORT_CELLS; k += T) s_hist[k] = 0;
-    __syncthreads();
-    for (int k = 0; k < (T >> 5); k++) { x0 = fminf(x0, s_red[0][k]); x1 = fmaxf(x1, s_red[1][k]); y0 = fminf(y0, s_red[2][k]); y1 = fmaxf(y1, s_red[3][k]); }
-    // A body that has been shot far away must not blow the grid up to one cell for everybody else: trim the box to the
-    // 0.1 % .. 99.9 % range of the coordinates (1024-bin histograms), again while that shrinks it a lot.  Bodies outside
-    // land in the edge cells.
-    for (int trim = 0; trim < 4; trim++) {
+    grid_barrier(&sc->bar, bar_target);
+    float x0, x1, y0, y1;
+    {
+        auto get = [&](int k) { const unsigned v = *(volatile unsigned*)&sc->box[k]; return v == 0u ? 0.0f : order_float((int)(v ^ 0x80000000u)); };
+        x0 = -get(0); x1 = get(1); y0 = -get(2); y1 = get(3);
+    }
+    // ---- 2. a body that has been shot far away must not blow the grid up to one cell for everybody else: trim the box to the
+    //         0.1 % .. 99.9 % range of the coordinates (1024-bin histograms), again while that shrinks it a lot.  Bodies outside
+    //         land in the edge cells.  (Every CTA takes the same decision from the same histogram.)
+    for (int round = 0; round < TRIM_ROUNDS; round++) {
+        const float sx = (float)TRIM_BINS / fmaxf(x1 - x0, 1.0e-6f), sy = (float)TRIM_BINS / fmaxf(y1 - y0, 1.0e-6f);
+        for (int k = lt; k < 2 * TRIM_BINS; k += T) s_cells[k] = 0;
         __syncthreads();
-        for (int k = lt; k < 2048; k += T) s_hist[k] = 0;
-        __syncthreads();
-        const float sx = 1024.0f / fmaxf(x1 - x0, 1.0e-6f), sy = 1024.0f / fmaxf(y1 - y0, 1.0e-6f);
-        for_bodies([&](int, float4 p) {
-            if (!(fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f)) return;
-            atomicAdd(&s_hist[min(1023, max(0, (int)((p.x - x0) * sx)))], 1);
-            atomicAdd(&s_hist[1024 + min(1023, max(0, (int)((p.y - y0) * sy)))], 1);
-        });
-        __syncthreads();
-        if (lt < 2) {  // lane 0: x, lane 1: y
-            const int* h = s_hist + 1024 * lt;
-            const int q = max(1, B / 1000);
-            int lo = 0, hi = 1023, acc = 0;
-            for (acc = h[0]; acc <= q && lo < 1023; acc += h[++lo]) {}
-            for (acc = h[1023]; acc <= q && hi > 0; acc += h[--hi]) {}
-            if (hi < lo) hi = lo;
-            s_red[lt][0] = (float)lo;
-            s_red[lt][1] = (float)(hi + 1);
+        for (int i = tid; i < B; i += nth) {
+            const float4 p = pose[i];
+            if (!finite(p)) continue;
+            atomicAdd(&s_cells[min(TRIM_BINS - 1, max(0, (int)((p.x - x0) * sx)))], 1);
+            atomicAdd(&s_cells[TRIM_BINS + min(TRIM_BINS - 1, max(0, (int)((p.y - y0) * sy)))], 1);
         }
         __syncthreads();
-        const float wx = (x1 - x0) / 1024.0f, wy = (y1 - y0) / 1024.0f;
-        const float nx0 = x0 + s_red[0][0] * wx, nx1 = x0 + s_red[0][1] * wx, ny0 = y0 + s_red[1][0] * wy, ny1 = y0 + s_red[1][1] * wy;
+        for (int k = lt; k < 2 * TRIM_BINS; k += T)
+            if (s_cells[k]) atomicAdd(&sc->trim[round][k], s_cells[k]);
+        grid_barrier(&sc->bar, bar_target);
+        for (int k = lt; k < 2 * TRIM_BINS; k += T) s_cells[k] = __ldcg(&sc->trim[round][k]);
+        __syncthreads();
+        if (wid < 2) {  // warp 0: x, warp 1: y — lane l owns bins [32 l, 32 l + 32)
+            const int* h = s_cells + TRIM_BINS * wid;
+            const int q = max(1, B / 1000);
+            int own = 0;
+            for (int k = 0; k < 32; k++) own += h[32 * lane + k];
+            int incl = own;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            const int total = __shfl_sync(0xffffffffu, incl, 31);
+            // lo = the first bin at which the running count from the left exceeds q; hi = the same from the right
+            int lo = TRIM_BINS - 1, hi = 0;
+            {
+                const unsigned m = __ballot_sync(0xffffffffu, incl > q);
+                if (m) {
+                    const int l = __ffs(m) - 1;
+                    int acc = __shfl_sync(0xffffffffu, incl - own, l), b = 32 * l;
+                    if (lane == l) { for (;; b++) { acc += h[b]; if (acc > q || b == TRIM_BINS - 1) break; } }
+                    lo = __shfl_sync(0xffffffffu, b, l);
+                }
+                const int from_right = total - (incl - own);  // bins [32 lane, end)
+                const unsigned mr = __ballot_sync(0xffffffffu, from_right > q);
+                if (mr) {
+                    const int l = 31 - __clz(mr);
+                    int acc = __shfl_sync(0xffffffffu, total - incl, l), b = 32 * l + 31;
+                    if (lane == l) { for (;; b--) { acc += h[b]; if (acc > q || b == 0) break; } }
+                    hi = __shfl_sync(0xffffffffu, b, l);
+                }
+            }
+            if (hi < lo) hi = lo;
+            if (lane == 0) { s_lohi[2 * wid] = lo; s_lohi[2 * wid + 1] = hi + 1; }
+        }
+        __syncthreads();
+        const float wx = (x1 - x0) / (float)TRIM_BINS, wy = (y1 - y0) / (float)TRIM_BINS;
+        const float nx0 = x0 + (float)s_lohi[0] * wx, nx1 = x0 + (float)s_lohi[1] * wx, ny0 = y0 + (float)s_lohi[2] * wy, ny1 = y0 + (float)s_lohi[3] * wy;
         const bool shrunk = (nx1 - nx0) < 0.25f * (x1 - x0) || (ny1 - ny0) < 0.25f * (y1 - y0);
+        __syncthreads();
         if (!shrunk) break;
         x0 = nx0; x1 = nx1; y0 = ny0; y1 = ny1;
     }
-    __syncthreads();
-    for (int k = lt; k <= SORT_CELLS; k += T) s_hist[k] = 0;
-    __syncthreads();
+    stamp();
+    // ---- 3. Morton keys + bodies per cell
     const float span = fmaxf(fmaxf(x1 - x0, y1 - y0), 1.0e-3f);
     const float inv = (float)(1 << SORT_BITS) / (span * 1.0001f);
-    auto key_of = [&](int i, float4 p) -> int {
-        // several collision groups (independent worlds in one World): a region is a run of whole groups, wherever their bodies are
-        if (n_groups > 1) return (int)((long long)group_of(bflags[i]) * SORT_CELLS / n_groups);
-        if (!(fabsf(p.x) < 1.0e30f && fabsf(p.y) < 1.0e30f)) return 0;
-        const int cx = min((1 << SORT_BITS) - 1, max(0, (int)((p.x - x0) * inv))), cy = min((1 << SORT_BITS) - 1, max(0, (int)((p.y - y0) * inv)));
-        return (int)(morton_spread((unsigned)cx) | (morton_spread((unsigned)cy) << 1));
-    };
-    for_bodies([&](int i, float4 p) {
-        const int k = key_of(i, p);
-        key_tmp[i] = k;
-        atomicAdd(&s_hist[k], 1);
-    });
-    __syncthreads();
-    {   // exclusive scan of the histogram: s_hist[k] = first position of cell k
-        const int per = SORT_CELLS / REBAL_THREADS, q0 = lt * per;
-        int sum = 0;
-        for (int k = 0; k < per; k++) sum += s_hist[q0 + k];
-        int tot;
-        int ex = block_excl_scan<int>(sum, &tot, s_scan2);
-        for (int k = 0; k < per; k++) { const int t = s_hist[q0 + k]; s_hist[q0 + k] = ex; ex += t; }
-    }
-    __syncthreads();
-    for (int i = lt; i < B; i += T) perm[atomicAdd(&s_hist[key_tmp[i]], 1)] = i;  // now s_hist[k] = end of cell k
-    __syncthreads();
-    for (int k = lt; k < SORT_CELLS; k += T) {  // ascending body index inside a cell (cells hold a handful of bodies)
-        const int lo = k ? s_hist[k - 1] : 0, hi = s_hist[k];
-        if (hi - lo > 256) continue;  // a degenerate pile-up in one cell: leave it unordered rather than sort it on one thread
-        for (int a2 = lo + 1; a2 < hi; a2++) {
-            const int x = perm[a2];
-            int b2 = a2 - 1;
-            while (b2 >= lo && perm[b2] > x) { perm[b2 + 1] = perm[b2]; b2--; }
-            perm[b2 + 1] = x;
+    for (int i = tid; i < B; i += nth) {
+        const float4 p = pose[i];
+        int k = 0;
+        if (n_groups > 1) k = (int)((long long)group_of(bflags[i]) * SORT_CELLS / n_groups);  // collision groups: a region is a run of whole groups
+        else if (finite(p)) {
+            const int cx = min((1 << SORT_BITS) - 1, max(0, (int)((p.x - x0) * inv))), cy = min((1 << SORT_BITS) - 1, max(0, (int)((p.y - y0) * inv)));
+            k = (int)(morton_spread((unsigned)cx) | (morton_spread((unsigned)cy) << 1));
         }
+        key_tmp[i] = k;
+        atomicAdd(&sc->hist[k], 1);
     }
-}
-
-// Cut the spatial order `perm` into G regions of equal load: weight of a body = 1 + 2 x (arbiters it owned last step),
-// floored at the average weight so that no region gets more than twice the average number of bodies (k_solve_regions
-// keeps a region's bodies in shared memory).  Regions are consecutive runs of `perm`, so perm itself is the CSR body list.
-__global__ void __launch_bounds__(REBAL_THREADS) k_rebalance(int B, int G, const int* perm, const int* old_row_start, int B_old, int* region_of, int* lidx,
-                                                            int* reg_start, const Counters* cn) {
-    __shared__ long long sh[34];
-    __shared__ int s_first[1025];
-    if (step_failed(cn)) return;
-    const int lt = threadIdx.x, T = blockDim.x;
-    const int chunk = (B + T - 1) / T, q0 = min(lt * chunk, B), q1 = min(q0 + chunk, B);
+    grid_barrier(&sc->bar, bar_target);
+    stamp();
+    // ---- 4. cell offsets (every CTA scans the histogram for itself), scatter, then ascending body index inside a cell
+    {
+        for (int k = lt; k < SORT_CELLS; k += T) s_cells[k] = __ldcg(&sc->hist[k]);  // coalesced
+        __syncthreads();
+        // thread t scans cells [32 t, 32 t + 32) — read through a rotation so that the lanes of a warp hit different banks
+        const int per = SORT_CELLS / RECUT_THREADS, q0 = lt * per;
+        int c[SORT_CELLS / RECUT_THREADS];
+        int sum = 0;
+#pragma unroll
+        for (int k = 0; k < per; k++) { const int kk = (k + lane) & (per - 1); c[k] = s_cells[q0 + kk]; sum += c[k]; }
+        int tot;
+        const int ex0 = block_excl_scan<int>(sum, &tot, sh32);
+        // (the rotated order is only a read order: rebuild the running sum in cell order)
+        int run = ex0;
+#pragma unroll
+        for (int k = 0; k < per; k++) {
+            // cell q0 + k was read at rotated position (k - lane) mod per
+            const int pos = (k - lane) & (per - 1);
+            int v = 0;
+#pragma unroll
+            for (int j = 0; j < per; j++) v = j == pos ? c[j] : v;
+            s_cells[q0 + k] = run;  // (own cells only: no other thread reads them before the barrier below)
+            run += v;
+        }
+        if (lt == 0) s_cells[SORT_CELLS] = tot;
+    }
+    __syncthreads();
+    stamp();
+    for (int i = tid; i < B; i += nth) {
+        const int k = key_tmp[i];
+        perm[s_cells[k] + atomicAdd(&sc->fill[k], 1)] = i;
+    }
+    grid_barrier(&sc->bar, bar_target);
+    stamp();
+    // (one warp per cell, a rank sort in registers: the bodies of a cell sit in consecutive positions, ids are distinct; a pile of
+    //  30 bodies in a cell would cost an insertion sort ~450 dependent global round trips)
+    for (int k = tid >> 5; k < SORT_CELLS; k += nth >> 5) {
+        const int lo = s_cells[k], hi = s_cells[k + 1], n = hi - lo;
+        if (n <= 1 || n > 256) continue;  // a degenerate pile-up in one cell: leave it unordered rather than sort it here (warp-uniform)
+        const int nr = (n + 31) >> 5;
+        int v[8], rank[8];
+#pragma unroll
+        for (int r = 0; r < 8; r++) {
+            const int idx = lo + lane + 32 * r;
+            v[r] = (r < nr && idx < hi) ? __ldcg(&perm[idx]) : 0x7fffffff;
+            rank[r] = 0;
+        }
+        __syncwarp();
+#pragma unroll
+        for (int r2 = 0; r2 < 8; r2++) {
+            if (r2 >= nr) break;
+            for (int src = 0; src < 32; src++) {
+                const int y = __shfl_sync(0xffffffffu, v[r2], src);
+#pragma unroll
+                for (int r = 0; r < 8; r++) rank[r] += y < v[r] ? 1 : 0;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < 8; r++)
+            if (v[r] != 0x7fffffff) perm[lo + rank[r]] = v[r];
+    }
+    grid_barrier(&sc->bar, bar_target);
+    stamp();
+    // ---- 5. cut the order into G regions of equal (floored) weight: CTA c owns positions [c0, c1), thread t a slice of those
     auto weight = [&](int b) -> long long { return (old_row_start && b < B_old) ? 1 + 2 * max(0, __ldg(&old_row_start[b + 1]) - __ldg(&old_row_start[b])) : 1; };
-    for (int g = lt; g <= G; g += T) s_first[g] = B;
-    long long sum = 0;
-    for (int i = q0; i < q1; i++) sum += weight(perm[i]);
-    long long total;
-    block_excl_scan<long long>(sum, &total, sh);
+    const int cchunk = (B + (int)gridDim.x - 1) / (int)gridDim.x, c0 = min((int)blockIdx.x * cchunk, B), c1 = min(c0 + cchunk, B);
+    const int tchunk = (c1 - c0 + T - 1) / T, q0 = min(c0 + lt * tchunk, c1), q1 = min(q0 + tchunk, c1);
+    {
+        long long sum = 0;
+        for (int i = q0; i < q1; i++) sum += weight(__ldcg(&perm[i]));
+        long long tot;
+        block_excl_scan<long long>(sum, &tot, sh64);
+        if (lt == 0) sc->part[blockIdx.x] = tot;
+    }
+    grid_barrier(&sc->bar, bar_target);
+    long long total;  // (gridDim.x <= RECUT_THREADS: one partial per thread, summed by the block)
+    block_excl_scan<long long>(lt < (int)gridDim.x ? __ldcg(&sc->part[lt]) : 0ll, &total, sh64);
     const long long wmin = (total + B - 1) / max(B, 1);
-    long long esum = 0;
-    for (int i = q0; i < q1; i++) esum += max(weight(perm[i]), wmin);
+    long long ex;
+    {
+        long long esum = 0;
+        for (int i = q0; i < q1; i++) esum += max(weight(__ldcg(&perm[i])), wmin);
+        long long tot;
+        ex = block_excl_scan<long long>(esum, &tot, sh64);
+        if (lt == 0) sc->epart[blockIdx.x] = tot;
+    }
+    grid_barrier(&sc->bar, bar_target);
     long long etotal;
-    long long ex = block_excl_scan<long long>(esum, &etotal, sh);
+    {
+        __shared__ long long s_before;
+        const long long pre = block_excl_scan<long long>(lt < (int)gridDim.x ? __ldcg(&sc->epart[lt]) : 0ll, &etotal, sh64);
+        if (lt == (int)blockIdx.x) s_before = pre;  // the floored weights of the CTAs in front of this one
+        __syncthreads();
+        ex += s_before;
+    }
     for (int i = q0; i < q1; i++) {
-        const int b = perm[i];
+        const int b = __ldcg(&perm[i]);
         const int reg = (int)min((long long)(G - 1), ex * (long long)G / max(etotal, 1ll));
         ex += max(weight(b), wmin);
         region_of[b] = reg;
-        atomicMin(&s_first[reg], i);
+        atomicMax(&sc->first[reg], B - i);  // = min over the positions
     }
+    grid_barrier(&sc->bar, bar_target);
+    // ---- 6. region starts (an empty region starts where the next one starts), then every body's index inside its region
+    for (int g = lt; g < G; g += T) { const int v = __ldcg(&sc->first[g]); s_cells[g] = v > 0 ? B - v : B; }
+    if (lt == 0) s_cells[G] = B;
     __syncthreads();
-    if (lt == 0) {  // empty regions start where the next one starts
-        s_first[G] = B;
-        for (int g = G - 1; g >= 0; g--) if (s_first[g] > s_first[g + 1]) s_first[g] = s_first[g + 1];
-    }
+    if (lt == 0)
+        for (int g = G - 1; g >= 0; g--) if (s_cells[g] > s_cells[g + 1]) s_cells[g] = s_cells[g + 1];
     __syncthreads();
-    for (int g = lt; g <= G; g += T) reg_start[g] = s_first[g];
-    for (int i = q0; i < q1; i++) { const int b = perm[i]; lidx[b] = i - s_first[region_of[b]]; }
+    if (blockIdx.x == 0)
+        for (int g = lt; g <= G; g += T) reg_start[g] = s_cells[g];
+    for (int i = q0; i < q1; i++) { const int b = __ldcg(&perm[i]); lidx[b] = i - s_cells[region_of[b]]; }
+    stamp();
 }
 
 // the flags a step used become the "old" flags of the next one — unless the step failed (it will be repeated)
@@ -2133,6 +2262,7 @@ struct SyltWorld {
     // regions (k_solve_regions): spatial partition of the bodies, recomputed on the host when bodies were added or the
     // share of cross-region arbiters has grown
     DBuf<int> region_of, lidx, reg_start, reg_bodies, sort_keys;
+    DBuf<RecutScratch> recut;
     DBuf<int2> gadj, cone_buf;
     DBuf<ulonglong2> xrec;
     unsigned step_tag = 0;
@@ -2473,6 +2603,7 @@ int repartition(SyltWorld* w) {
     SYLT_CUDA(w->lidx.ensure(B));
     SYLT_CUDA(w->reg_bodies.ensure(B));
     SYLT_CUDA(w->sort_keys.ensure(B));
+    SYLT_CUDA(w->recut.ensure(1));
     SYLT_CUDA(w->reg_start.ensure((size_t)G + 1));
     SYLT_CUDA(w->gadj.ensure(B * (size_t)GADJ));
     SYLT_CUDA(w->cone_buf.ensure((size_t)w->regions_blocks * (CONE_CAP_1 / w->regions_per_sm)));
@@ -2496,7 +2627,7 @@ void replay_schedule(SyltWorld* w, int64_t since0, bool pending0, bool recolor0,
     w->steps_since_part = since0; w->resort_pending = pending0; w->recolor_all = recolor0;
     for (const auto& sg : segs)
         for (int k = 0; k < sg.n && completed > 0; k++, completed--) {
-            if (recut_due(w, sg.full)) { w->steps_since_part = 0; w->resort_pending = false; w->recolor_all = true; }
+            if (recut_due(w, sg.full)) { w->steps_since_part = 0; w->resort_pending = false; }
             w->recolor_all = false;
             if (w->regions_on) w->steps_since_part++;
         }
@@ -2513,9 +2644,10 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     mark();
     Counters* cn = w->counters.p;
     static_assert((sizeof(Counters) - offsetof(Counters, n_pairs)) % sizeof(int) == 0, "Counters: per-step part is a whole number of ints");
-    k_reset_counters<<<1, 256, 0, st>>>(cn);
-    SYLT_CUDA(cudaGetLastError());
-    if (B == 0) return SYLT_OK;
+    if (B == 0) {  // an empty world: nothing runs, nothing is counted
+        SYLT_CUDA(cudaMemsetAsync(&cn->n_pairs, 0, sizeof(Counters) - offsetof(Counters, n_pairs), st));
+        return SYLT_OK;
+    }
     if (!w->cells_clean) {
         SYLT_CUDA(cudaMemsetAsync(w->cell_count.p, 0, w->cell_count.cap * sizeof(int), st));
         w->cells_clean = true;
@@ -2549,28 +2681,35 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->launches++;
     mark();
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
+    bool recut_now = false;
     if (recut_due(w, full_step)) {
-        // (re)partition by the current positions and last step's load (device side, no synchronisation); the colours encode the old cut
-        k_resort<<<1, REBAL_THREADS, (SORT_CELLS + 1) * sizeof(int), st>>>(B, w->pose.p, w->reg_bodies.p, w->sort_keys.p, cn, w->bflags.p, w->n_groups);
-        SYLT_CUDA(cudaGetLastError());
-        k_rebalance<<<1, REBAL_THREADS, 0, st>>>(B, w->n_regions, w->reg_bodies.p, w->have_old ? old.row_start : nullptr, w->B_old, w->region_of.p,
-                                                 w->lidx.p, w->reg_start.p, cn);
-        SYLT_CUDA(cudaGetLastError());
-        w->launches += 2;
+        // (re)partition by the current positions and last step's load (device side, no synchronisation)
+        SYLT_CUDA(cudaMemsetAsync(w->recut.p, 0, sizeof(RecutScratch), st));
+        {
+            int rB = B, rG = w->n_regions, rng = w->n_groups, rBold = w->B_old;
+            const float4* rpose = w->pose.p;
+            const int *rfl = w->bflags.p, *rold = w->have_old ? old.row_start : nullptr;
+            int *rperm = w->reg_bodies.p, *rkey = w->sort_keys.p, *rreg = w->region_of.p, *rlidx = w->lidx.p, *rstart = w->reg_start.p;
+            RecutScratch* rsc = w->recut.p;
+            const Counters* rcn = cn;
+            void* rargs[] = {&rB, &rG, &rpose, &rfl, &rng, &rold, &rBold, &rperm, &rkey, &rreg, &rlidx, &rstart, &rsc, &rcn};
+            SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_recut, dim3((unsigned)w->num_sms), dim3(RECUT_THREADS), rargs, (SORT_CELLS + 1) * sizeof(int), st));
+        }
+        w->launches += 1;
         w->steps_since_part = 0;
         w->resort_pending = false;
-        w->recolor_all = true;
+        recut_now = true;
     }
-    const int keep_colors = w->recolor_all ? 0 : 1;
+    const int keep_colors = w->recolor_all ? 0 : (recut_now ? 2 : 1);
     w->recolor_all = false;
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0));
+                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
     else
         SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0));
+                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
     mark();
@@ -2700,6 +2839,15 @@ int finish(SyltWorld* w) {
         w->have_last = true;
         if (w->last_regions) w->last.n_colors = __builtin_popcountll(w->last.color_mask) + __builtin_popcount(w->last.color_mask_int);
         if (w->timing) print_solver_timing(w);
+    if (w->timing && w->recut.p && w->steps_since_part <= 1) {
+        RecutScratch* hs = new RecutScratch;
+        if (cudaMemcpy(hs, w->recut.p, sizeof(RecutScratch), cudaMemcpyDeviceToHost) == cudaSuccess && hs->stamp[0]) {
+            fprintf(stderr, "k_recut phases [us] (box + trim | keys + histogram | cell scan | scatter | sort in cells | cut):");
+            for (int k = 1; k < 16 && hs->stamp[k]; k++) fprintf(stderr, " %.1f", (double)(hs->stamp[k] - hs->stamp[k - 1]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
+        delete hs;
+    }
         if (w->kt_n > 1) {  // SYLT_KERNEL_TIMING: the last step's launches
             static const char* names[] = {"prepare", "scan cells", "fill cells", "rows count", "rows emit", "narrow", "(re-cut +) build", "solve"};
             fprintf(stderr, "kernels [us]:");
@@ -2861,7 +3009,7 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
         w->regions_threads = SOLVE_THREADS / w->regions_per_sm;
         w->regions_blocks = w->num_sms * w->regions_per_sm;
         SYLT_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)w->solve_budget));
-        SYLT_CUDA(cudaFuncSetAttribute(k_resort, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SORT_CELLS + 1) * sizeof(int))));
+        SYLT_CUDA(cudaFuncSetAttribute(k_recut, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((SORT_CELLS + 1) * sizeof(int))));
         int per2 = 0;
         SYLT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per2, kern, w->regions_threads, w->solve_budget));
         if (const char* ev = getenv("SYLT_REGIONS")) w->regions_mode = std::min(2, std::max(0, atoi(ev)));
@@ -2897,7 +3045,7 @@ static void free_all(SyltWorld* w) {
     }
     w->jbodies.release(); w->jla.release(); w->jr.release(); w->jm.release(); w->jparam.release(); w->jp.release(); w->jbias.release();
     w->jorder.release(); w->jcolor_start.release();
-    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release(); w->sort_keys.release(); w->gadj.release(); w->cone_buf.release(); w->xrec.release();
+    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release(); w->sort_keys.release(); w->recut.release(); w->gadj.release(); w->cone_buf.release(); w->xrec.release();
 }
 
 int sylt_world_destroy(SyltWorld* w) {
