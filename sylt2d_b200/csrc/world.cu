@@ -252,15 +252,68 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const floa
 
 // bodies grouped by cell: a cell-ordered COPY of (index, cell, flags) and of the AABB, so that the row search streams
 // contiguous 32-byte entries instead of chasing body indices
-__global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, const float4* aabb, const int* rank, const int* cell_start,
-                                                    int4* cent_info, float4* cent_aabb, GridParams gp, const Counters* cn) {
+// Counting-sort offsets of the grid without a device-wide scan: k_cells_local leaves, per tile of CELL_TILE buckets, the exclusive
+// offsets inside the tile and the tile's total; k_fill_cells adds up the (few hundred) totals in its prologue.
+constexpr int CELL_TILE = 2048, MAX_CELL_TILES = 2048;  // (worlds with more buckets keep the look-back scan)
+__global__ void __launch_bounds__(256) k_cells_local(int buckets, int* cell_count, int* cell_local, int* tile_tot) {
+    __shared__ int sh[34];
     pdl_wait();
     pdl_trigger();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int base = blockIdx.x * CELL_TILE + threadIdx.x * 8;
+    int v[8], sum = 0;
+    if (base + 8 <= buckets) {
+        const int4 a = *(const int4*)(cell_count + base), b = *(const int4*)(cell_count + base + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        *(int4*)(cell_count + base) = make_int4(0, 0, 0, 0);  // the counters are ready for the next step
+        *(int4*)(cell_count + base + 4) = make_int4(0, 0, 0, 0);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; k++) { v[k] = base + k < buckets ? cell_count[base + k] : 0; if (base + k < buckets) cell_count[base + k] = 0; }
+    }
+#pragma unroll
+    for (int k = 0; k < 8; k++) sum += v[k];
+    int tot;
+    int ex = block_excl_scan<int>(sum, &tot, sh);
+#pragma unroll
+    for (int k = 0; k < 8; k++) { if (base + k < buckets) cell_local[base + k] = ex; ex += v[k]; }
+    if (threadIdx.x == 0) tile_tot[blockIdx.x] = tot;
+}
+
+// Bodies into their cells: a cell-ordered COPY of (index, cell, flags) and of the AABB, so that the row search streams contiguous
+// 32-byte entries instead of chasing body indices.  The large bodies (which bypass the grid) get entries of the same kind behind
+// the small ones, in the order of the `large` list.  Also turns the tile-local bucket offsets into absolute ones for the row kernels.
+__global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, const float4* aabb, const int* rank, const int* cell_local, const int* tile_tot,
+                                                    int ntiles, int buckets, int* cell_start, int4* cent_info, float4* cent_aabb, GridParams gp,
+                                                    const int* large, int n_large) {
+    __shared__ int s_tp[MAX_CELL_TILES + 1];  // buckets in front of tile t
+    __shared__ int sh[34];
+    pdl_wait();
+    pdl_trigger();
+    {
+        const int per = (ntiles + (int)blockDim.x - 1) / (int)blockDim.x, t0 = min((int)threadIdx.x * per, ntiles), t1 = min(t0 + per, ntiles);
+        int sum = 0;
+        for (int t = t0; t < t1; t++) sum += tile_tot[t];
+        int tot;
+        int ex = block_excl_scan<int>(sum, &tot, sh);
+        for (int t = t0; t < t1; t++) { s_tp[t] = ex; ex += tile_tot[t]; }
+        if (threadIdx.x == 0) s_tp[ntiles] = tot;
+    }
+    __syncthreads();
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    for (int h = tid; h <= buckets; h += nth) cell_start[h] = h < buckets ? s_tp[h / CELL_TILE] + cell_local[h] : s_tp[ntiles];
+    const int i = tid;
+    if (i < n_large) {  // the i-th large body
+        const int j = large[i];
+        const int4 cj = cinfo[j];
+        const int pos = B - n_large + i;
+        cent_info[2 * pos] = make_int4(j, cj.x, cj.y, cj.z);
+        cent_aabb[2 * pos] = aabb[j];
+    }
     if (i >= B) return;
-    int4 ci = cinfo[i];
+    const int4 ci = cinfo[i];
     if (ci.z & FLAG_LARGE) return;
-    int pos = cell_start[cell_hash(ci.x, ci.y, gp.mask, group_of(ci.z))] + rank[i];
+    const int h = cell_hash(ci.x, ci.y, gp.mask, group_of(ci.z));
+    const int pos = s_tp[h / CELL_TILE] + cell_local[h] + rank[i];
     cent_info[2 * pos] = make_int4(i, ci.x, ci.y, ci.z);  // info and AABB of an entry share one 32-byte sector
     cent_aabb[2 * pos] = aabb[i];
 }
@@ -361,6 +414,7 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     }
     const bool st_i = (ci.z & FLAG_STATIC) != 0;
     const int grp = group_of(ci.z);
+    const int large_base = B - n_large_all;  // the entries of the large bodies follow those of the small ones (k_fill_cells)
     int* tmp = row_tmp + (size_t)i * ROWTMP;
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
     bool fast = false;
@@ -391,8 +445,9 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
             seg_n = cell_start[h + 1] - seg_k0;
         }
     } else if (lane == 9) {  // the large bodies of this body's group
-        seg_k0 = large_start[grp];
-        seg_n = large_start[grp + 1] - seg_k0;
+        const int l0 = large_start[grp];
+        seg_k0 = large_base + l0;
+        seg_n = large_start[grp + 1] - l0;
     }
     int seg_end = seg_n;  // inclusive prefix
 #pragma unroll
@@ -412,18 +467,16 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
         int partner = 0;
         if (e < total) {
             const int off = e - (s_end - s_n);
-            if (seg < 9) {
+            {
                 const int k = s_k0 + off;
                 const int4 cj = cent_info[2 * k];
                 const float4 ab = cent_aabb[2 * k];
                 const int scx = x0 + seg % 3, scy = y0 + seg / 3;
-                // lower index owns the pair; another cell may share the bucket; static-static pairs are skipped (world.rs:79-81)
-                hit = cj.x > i && cj.y == scx && cj.z == scy && group_of(cj.w) == grp && !(st_i && (cj.w & FLAG_STATIC)) && aabb_overlap(my, ab);
+                // a cell entry: the lower index owns the pair, another cell (or group) may share the bucket; an entry of the large list: the
+                // small body owns the pair.  Static-static pairs are skipped (world.rs:79-81).
+                const bool mine = seg < 9 ? (cj.x > i && cj.y == scx && cj.z == scy && group_of(cj.w) == grp) : true;
+                hit = mine && !(st_i && (cj.w & FLAG_STATIC)) && aabb_overlap(my, ab);
                 partner = cj.x;
-            } else {
-                const int j = large_all[s_k0 + off];
-                hit = !(st_i && (cinfo[j].z & FLAG_STATIC)) && aabb_overlap(my, aabb[j]);
-                partner = j;
             }
         }
         const unsigned m = __ballot_sync(0xffffffffu, hit);
@@ -557,12 +610,13 @@ __device__ __forceinline__ void pair_owner(int a, int b, int fa, int fb, int* ow
     else { *owner = a; *partner = b; }
 }
 
+constexpr int UNC_STATIC = 0x40000000;  // body reference of an uncoloured-arbiter record: the body is static (takes no colour)
 template <int MAXC>
 __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int cap_arb, int cap_con, int B, int B_old, int have_old,
                                                const int2* pairs, const unsigned long long* info, unsigned long long* scan, const unsigned long long* pair_btot,
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
-                                               unsigned long long* used, int* uncolored, int fix_features, int keep_colors, unsigned* used_int, int regions,
+                                               unsigned long long* used, int4* unc_rec, int fix_features, int keep_colors, unsigned* used_int, int regions,
                                                const int* region_of) {
     pdl_wait();
     const int failed = __ldcg(&cn->err);
@@ -673,7 +727,15 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
             }
             atomicAdd(&s_hist[color], 1);
         } else {
-            uncolored[atomicAdd(&cn->n_uncolored, 1)] = a;
+            // everything the colouring rounds need to know about a new arbiter, in one 16-byte record: the rounds are chains of
+            // dependent L2 round trips, and this takes two links (bodies -> flags -> regions) out of every one of them
+            const bool s1 = (bflags[b1] & FLAG_STATIC) != 0, s2 = (bflags[b2] & FLAG_STATIC) != 0;
+            int interior = 0;
+            if (regions) {
+                const int R = region_of[pr.x];  // pr.x owns the pair
+                interior = ((s1 || region_of[b1] == R) && (s2 || region_of[b2] == R)) ? 1 : 0;
+            }
+            unc_rec[atomicAdd(&cn->n_uncolored, 1)] = make_int4(a, b1 | (s1 ? UNC_STATIC : 0), b2 | (s2 ? UNC_STATIC : 0), interior);
         }
     }
     }
@@ -792,7 +854,8 @@ struct SolveArgs {
     unsigned long long* used;
     unsigned* used_int;         // region solver: interior colours taken at a body
     unsigned long long* claim;  // B * NCX
-    int *uncolored, *uncolored2, *prop, *order;
+    int *uncolored, *uncolored2, *prop, *order;   // uncolored / uncolored2: the losers of a round (record indices), ping-pong; prop: by record
+    const int4* unc_rec;                         // new arbiters of this step (k_build): (arbiter, body1 | UNC_STATIC, body2 | UNC_STATIC, interior)
     ulonglong2* vrec;           // 2 per body: versioned velocities (see k_prepare)
     int sleep_ns;               // back-off between polls of the dataflow wait (0 = spin)
     int fix_inverse;            // opt-in corrected Mat2x2 inverse (NOT the reference)
@@ -928,35 +991,37 @@ __device__ __forceinline__ void color_new_arbiters(const SolveArgs& a, Counters*
             int* next_list = lists[(round + 1) & 1];
             const unsigned long long ep = (unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32;
             for (int k = ct; k < n; k += cs) {
-                int e = __ldcg(&cur_list[k]);
-                int2 b = a.cur.bodies[e];
-                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
+                const int r = round == 0 ? k : __ldcg(&cur_list[k]);  // (round 0: every record)
+                const int4 rec = __ldcg(&a.unc_rec[r]);
+                const int e = rec.x;
+                const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
+                const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
                 unsigned long long m = (d1 ? __ldcg(&a.used[b.x]) : 0ull) | (d2 ? __ldcg(&a.used[b.y]) : 0ull);
                 unsigned long long fr = ~m;
                 int c = -1;
                 if (REGIONS) {
-                    const int owner = a.cur.partner[e] == b.x ? b.y : b.x;
-                    const int R = a.region_of[owner];
-                    const bool interior = (!d1 || a.region_of[b.x] == R) && (!d2 || a.region_of[b.y] == R);
+                    const bool interior = rec.w != 0;
                     const unsigned fi = interior ? ~((d1 ? __ldcg(&a.used_int[b.x]) : 0u) | (d2 ? __ldcg(&a.used_int[b.y]) : 0u)) : 0u;
                     if (fi) c = __ffs((int)fi) - 1;                             // lowest free interior colour
                     else if (fr) c = GEN_BIT + __ffsll((long long)fr) - 1;      // lowest free generic colour
                 } else if (fr) {
                     c = __ffsll((long long)fr) - 1;  // lowest free colour
                 }
-                if (c < 0) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[e] = -1; continue; }
-                a.prop[e] = c;
+                if (c < 0) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[r] = -1; continue; }
+                a.prop[r] = c;
                 unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
                 if (d1) atomicMin(&a.claim[(size_t)b.x * NCX + c], val);
                 if (d2) atomicMin(&a.claim[(size_t)b.y * NCX + c], val);
             }
             if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
             for (int k = ct; k < n; k += cs) {
-                int e = __ldcg(&cur_list[k]);
-                int c = __ldcg(&a.prop[e]);
+                const int r = round == 0 ? k : __ldcg(&cur_list[k]);
+                const int c = __ldcg(&a.prop[r]);
                 if (c < 0) continue;
-                int2 b = a.cur.bodies[e];
-                bool d1 = !(a.bflags[b.x] & FLAG_STATIC), d2 = !(a.bflags[b.y] & FLAG_STATIC);
+                const int4 rec = __ldcg(&a.unc_rec[r]);
+                const int e = rec.x;
+                const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
+                const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
                 unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
                 bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NCX + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NCX + c]) == val);
                 if (win) {
@@ -971,7 +1036,7 @@ __device__ __forceinline__ void color_new_arbiters(const SolveArgs& a, Counters*
                     }
                     atomicAdd(&cn->color_count[c], 1);
                 } else {
-                    next_list[atomicAdd(&cn->remaining[round], 1)] = e;
+                    next_list[atomicAdd(&cn->remaining[round], 1)] = r;
                 }
             }
             if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
@@ -2216,7 +2281,7 @@ struct SyltWorld {
     // device state
     DBuf<float4> pose, vel, force, mp, geom, aabb;
     DBuf<float2> rotc, lverts;
-    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, large, large_start, row_count, row_start, row_tmp;
+    DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, cell_local, tile_tot, large, large_start, row_count, row_start, row_tmp;
     int n_groups = 1;        // collision groups in use (SyltBodyDesc.group)
     DBuf<int4> cinfo, cent_info;  // cent_info: interleaved (info, AABB) entries of the cell-ordered copy
     DBuf<int2> pairs;
@@ -2234,6 +2299,7 @@ struct SyltWorld {
     DBuf<int> jdeg;
     DBuf<int2> jrank;
     DBuf<int> uncolored, uncolored2, prop, order;
+    DBuf<int4> unc_rec;
     DBuf<Counters> counters;
     DBuf<int> sincl32, scan_ticket;
     DBuf<unsigned long long> sincl64;
@@ -2470,14 +2536,16 @@ int flush(SyltWorld* w) {
         for (int g = 0; g < n_groups; g++) lstart[(size_t)g + 1] += lstart[(size_t)g];
         SYLT_CUDA(w->large_start.ensure((size_t)n_groups + 2));
         SYLT_CUDA(cudaMemcpyAsync(w->large_start.p, lstart.data(), lstart.size() * sizeof(int), cudaMemcpyHostToDevice, w->stream));
-        int buckets = 1024;
-        while ((size_t)buckets < 2 * B) buckets <<= 1;
+        int buckets = 2048;
+        while ((size_t)buckets < 2 * B && buckets < CELL_TILE * MAX_CELL_TILES) buckets <<= 1;  // (beyond 2 M bodies the buckets fill up: still correct, slower)
         w->buckets = buckets;
         w->gp.cell = cell;
         w->gp.mask = buckets - 1;
         if ((size_t)buckets + 1 > w->cell_count.cap) w->cells_clean = false;
         SYLT_CUDA(w->cell_count.ensure((size_t)buckets + 1));
         SYLT_CUDA(w->cell_start.ensure((size_t)buckets + 2));
+        SYLT_CUDA(w->cell_local.ensure((size_t)buckets + 8));
+        SYLT_CUDA(w->tile_tot.ensure((size_t)buckets / CELL_TILE + 2));
         size_t sp = ((size_t)std::max<size_t>(buckets, B + 1) + SCAN_TILE - 1) / SCAN_TILE + 1;
         SYLT_CUDA(w->spart32.ensure(sp));
         SYLT_CUDA(w->sincl32.ensure(sp));
@@ -2515,6 +2583,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->tmp_a.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->tmp_b.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->uncolored.ensure((size_t)ca));
+        SYLT_CUDA(w->unc_rec.ensure((size_t)ca));
         SYLT_CUDA(w->uncolored2.ensure((size_t)ca));
         SYLT_CUDA(w->prop.ensure((size_t)ca));
         SYLT_CUDA(w->order.ensure((size_t)ca));
@@ -2657,10 +2726,12 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
                                    w->cinfo.p, w->cell_count.p, w->rank.p, w->gp, w->gx, w->gy, dt, full_step ? 1 : 0, cn, w->vrec.p, w->used.p, w->used_int.p, w->row_btot.p);
     w->launches++;
     mark();
-    int e = run_scan<int>(w, w->cell_count.p, w->cell_start.p, w->buckets, nullptr, w->spart32.p, w->sincl32.p, 1, 0);
-    if (e) return e;
+    const int ntiles = (w->buckets + CELL_TILE - 1) / CELL_TILE;
+    SYLT_CUDA(launch_pdl(k_cells_local, dim3((unsigned)ntiles), dim3(256), 0, st, w->buckets, w->cell_count.p, w->cell_local.p, w->tile_tot.p));
+    w->launches++;
     mark();
-    SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp, cn));
+    SYLT_CUDA(launch_pdl(k_fill_cells, dim3((unsigned)nbB), dim3(256), 0, st, B, w->cinfo.p, w->aabb.p, w->rank.p, w->cell_local.p, w->tile_tot.p, ntiles, w->buckets,
+                         w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp, w->large.p, w->n_large));
     mark();
     const int nbR = (B + ROW_BLK - 1) / ROW_BLK;
     SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B + 3) / 4)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
@@ -2705,11 +2776,11 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
     else
         SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->uncolored.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
     mark();
@@ -2727,7 +2798,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         w->epoch = 1;
     }
     a.pose = w->pose.p; a.vel = w->vel.p; a.force = w->force.p; a.mp = w->mp.p; a.rotc = w->rotc.p; a.bflags = w->bflags.p;
-    a.cur = cur; a.used = w->used.p; a.used_int = w->used_int.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.uncolored2 = w->uncolored2.p; a.prop = w->prop.p; a.order = w->order.p;
+    a.cur = cur; a.used = w->used.p; a.used_int = w->used_int.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.uncolored2 = w->uncolored2.p; a.unc_rec = w->unc_rec.p; a.prop = w->prop.p; a.order = w->order.p;
     a.jbodies = w->jbodies.p; a.jla = w->jla.p; a.jparam = w->jparam.p; a.jp = w->jp.p; a.jr = w->jr.p; a.jm = w->jm.p; a.jbias = w->jbias.p;
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
     void* args[] = {&a};
@@ -3034,9 +3105,9 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
 static void free_all(SyltWorld* w) {
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
-    w->cell_count.release(); w->cell_start.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
+    w->cell_count.release(); w->cell_start.release(); w->cell_local.release(); w->tile_tot.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->large_start.release(); w->row_btot.release(); w->pair_btot.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
-    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release();
+    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release(); w->unc_rec.release();
     w->prop.release(); w->order.release(); w->sincl32.release(); w->sincl64.release(); w->scan_flag.release(); w->scan_ticket.release();
     for (int k = 0; k < 2; k++) {
         auto& a = w->arb[k];
