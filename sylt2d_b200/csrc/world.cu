@@ -4,23 +4,24 @@
 // algorithmic structure (nothing here is a translation of the Rust loops):
 //
 //   k_prepare      body        (cos,sin) cache, conservative AABB, hashed uniform-grid cell, force integration
-//                              (world.rs:113-120)
-//   scan           bucket      counting-sort offsets of the grid (hand-written single-pass look-back scan)
-//   k_fill_cells   body        bodies grouped by cell
-//   k_rows<count|emit>  body   candidate rows: for body i every AABB-overlapping partner it "owns", partner-sorted;
-//                              static-static pairs skipped (world.rs:79-81).  Large bodies (ground, walls) bypass
-//                              the grid through a short list.
-//   k_narrow       pair        one thread per candidate pair: box_box / poly_poly (narrow.cuh)
-//   scan           pair        (arbiter, contact) offsets in one packed 64-bit scan
-//   k_build        pair        compaction into the arbiter / contact SoA; match against last step's arbiters
-//                              (Arbiter::update, arbiter.rs:137-181 incl. quirk Q-2; friction persistence Q-17);
-//                              persisting arbiters keep their colour
+//                              (world.rs:113-120); zeroes the per-step counters
+//   k_cells_local  bucket      counting-sort offsets of the grid: exclusive offsets inside tiles of 2048 buckets + one total
+//                              per tile (no device-wide scan: the consumer adds up the tile totals)
+//   k_fill_cells   body        bodies grouped by cell (a cell-ordered copy of index / cell / flags / AABB)
+//   k_rows_count   body        candidate rows, one warp per body: for body i every AABB-overlapping partner it "owns";
+//                              static-static pairs skipped (world.rs:79-81), other collision groups skipped.  Large bodies
+//                              (ground, walls) bypass the grid through a short list.  Leaves one total per 128 bodies.
+//   k_rows_emit    body        rows laid out in body order (prefix = block totals in front + in-block scan), partner-sorted
+//   k_narrow       pair        one thread per candidate pair: box_box / poly_poly (narrow.cuh); one total per 256 pairs
+//   k_build        pair        compaction into the arbiter / contact SoA (offsets = tile totals in front + in-tile scan);
+//                              match against last step's arbiters (Arbiter::update, arbiter.rs:137-181 incl. quirk Q-2;
+//                              friction persistence Q-17); persisting arbiters keep their colour
 //   k_solve        cooperative persistent kernel: incremental graph colouring of new arbiters, then
 //                              Arbiter::pre_step / Joint::pre_step / iterations x apply_impulse in colour order as a
 //                              version-gated dataflow sweep through L2 (arbiter.rs:182-298, joint.rs:57-130), then
 //                              position integration (world.rs:143-150).  Worlds with joints, small worlds.
 //   k_solve_regions            the same sweep for joint-free worlds of >= 1000 bodies: bodies partitioned into regions
-//                              (k_resort, k_rebalance) that live in shared memory, cross-region arbiters replayed
+//                              (k_recut, every 128 steps) that live in shared memory, cross-region arbiters replayed
 //                              redundantly from ghost bodies (see the comment at the kernel)
 //
 // Gauss-Seidel order: arbiter colours ascending, then joint colours ascending (within a colour constraints touch
@@ -109,9 +110,7 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
-// ------------------------------------------------------------------ device-wide exclusive scan (single pass, k_scan_lookback)
-constexpr int SCAN_THREADS = 256, SCAN_ITEMS = 8, SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
-
+// ------------------------------------------------------------------ block-level scans
 template <typename T>
 __device__ __forceinline__ T warp_incl_scan(T v) {
 #pragma unroll
@@ -140,16 +139,6 @@ __device__ __forceinline__ T block_excl_scan(T v, T* total, T* sh /* >= 33 */) {
     __syncthreads();
     return r;
 }
-
-// Single-pass exclusive scan (decoupled look-back): one launch instead of reduce / partials / apply.  A tile publishes its
-// aggregate, then sums the published aggregates of its predecessors until it meets one whose inclusive prefix is known.
-// Tiles are handed out by an atomic ticket, so a tile only ever waits for tiles that are already running.  The flags carry
-// the launch's epoch: no reset between launches.  The last tile also turns the grand total into the step counters.
-//   flag[t] = epoch << 2 | state, state 1 = agg[t] valid, 2 = incl[t] valid
-struct Counters;
-template <typename T>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, int n_host, const int* n_dev, unsigned* flag, T* agg, T* incl,
-                                                                int* ticket, unsigned epoch, int zero_in, Counters* cn, int totals_mode, int cap_pairs);
 
 // The two prefix sums of the candidate chain (rows -> pairs, pairs -> arbiters / contacts) have no kernel of their own: the
 // producer leaves one total per block of ROW_BLK bodies / PAIR_TILE candidates, and every consumer block adds up the totals in
@@ -749,87 +738,6 @@ __device__ __forceinline__ void fill_arbiter_rows(int B, int P, const int* row_s
     for (int i = tid; i <= B; i += nth) {
         const int rs = i < B ? min(row_start[i], P) : P;
         arow[i] = (int)(__ldcg(&scan[rs]) >> 32);
-    }
-}
-
-template <typename T>
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_lookback(T* in, T* out, int n_host, const int* n_dev, unsigned* flag, T* agg, T* incl,
-                                                                int* ticket, unsigned epoch, int zero_in, Counters* cn, int totals_mode, int cap_pairs) {
-    __shared__ T sh[33];
-    __shared__ int s_tile;
-    __shared__ T s_prefix;
-    pdl_wait();
-    pdl_trigger();
-    const int n = n_dev ? min(*n_dev, n_host) : n_host;
-    if (threadIdx.x == 0) {
-        const int t = atomicAdd(ticket, 1);
-        if (t == (int)gridDim.x - 1) atomicExch(ticket, 0);  // every tile of this launch has its ticket: ready for the next launch
-        s_tile = t;
-    }
-    __syncthreads();
-    const int tile = s_tile;
-    const int ntiles = max(1, (n + SCAN_TILE - 1) / SCAN_TILE);
-    if (tile >= ntiles) return;
-    const int base = tile * SCAN_TILE;
-    T v[SCAN_ITEMS];
-    T s = 0;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const int i = base + threadIdx.x * SCAN_ITEMS + k;
-        v[k] = i < n ? in[i] : T(0);
-        s += v[k];
-        if (zero_in && i < n) in[i] = T(0);
-    }
-    T tot;
-    T ex = block_excl_scan(s, &tot, sh);
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        T prefix = 0;
-        volatile unsigned* vflag = flag;
-        if (tile == 0) {
-            if (lane == 0) { incl[0] = tot; __threadfence(); vflag[0] = (epoch << 2) | 2u; }
-        } else {
-            if (lane == 0) { agg[tile] = tot; __threadfence(); vflag[tile] = (epoch << 2) | 1u; }
-            for (int look = tile - 1;; look -= 32) {
-                const int t = look - lane;
-                unsigned f = 2u;  // tiles before the first one: an inclusive prefix of 0
-                if (t >= 0) {
-                    do { f = vflag[t]; } while ((f >> 2) != epoch || (f & 3u) == 0u);
-                }
-                __threadfence();
-                const bool full = (f & 3u) == 2u;
-                T val = 0;
-                if (t >= 0) val = full ? __ldcg(&incl[t]) : __ldcg(&agg[t]);
-                const unsigned fm = __ballot_sync(0xffffffffu, full);
-                const int first = __ffs(fm) - 1;  // nearest predecessor with a complete prefix
-                T c = (fm == 0u || lane <= first) ? val : T(0);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-                prefix += c;
-                if (fm) break;
-            }
-            if (lane == 0) { incl[tile] = prefix + tot; __threadfence(); vflag[tile] = (epoch << 2) | 2u; }
-        }
-        if (lane == 0) s_prefix = prefix;
-    }
-    __syncthreads();
-    ex += s_prefix;
-#pragma unroll
-    for (int k = 0; k < SCAN_ITEMS; k++) {
-        const int i = base + threadIdx.x * SCAN_ITEMS + k;
-        if (i < n) out[i] = ex;
-        ex += v[k];
-    }
-    if (tile == ntiles - 1 && threadIdx.x == 0) {
-        const T total = s_prefix + tot;
-        out[n] = total;
-        if (totals_mode == 1) {  // candidate rows -> pairs
-            cn->n_pairs = (int)total;
-            if ((long long)total > (long long)cap_pairs) cn->err = SYLT_ERR_CAPACITY;
-        } else if (totals_mode == 2) {  // packed (arbiters << 32 | contacts)
-            cn->n_arb = (int)((unsigned long long)total >> 32);
-            cn->n_con = (int)(unsigned)total;
-        }
     }
 }
 
@@ -2285,9 +2193,8 @@ struct SyltWorld {
     int n_groups = 1;        // collision groups in use (SyltBodyDesc.group)
     DBuf<int4> cinfo, cent_info;  // cent_info: interleaved (info, AABB) entries of the cell-ordered copy
     DBuf<int2> pairs;
-    DBuf<unsigned long long> info, pscan, claim, spart64, pair_btot;
+    DBuf<unsigned long long> info, pscan, claim, pair_btot;
     DBuf<int> row_btot;
-    DBuf<int> spart32;
     DBuf<float4> tmp_a;
     DBuf<float2> tmp_b;
     DBuf<unsigned long long> used;
@@ -2301,10 +2208,6 @@ struct SyltWorld {
     DBuf<int> uncolored, uncolored2, prop, order;
     DBuf<int4> unc_rec;
     DBuf<Counters> counters;
-    DBuf<int> sincl32, scan_ticket;
-    DBuf<unsigned long long> sincl64;
-    DBuf<unsigned> scan_flag;
-    unsigned scan_epoch = 0;
     bool cells_clean = false;  // cell_count is all zero (the cell scan re-zeroes what it reads)
     // arbiters, double buffered
     struct ArbBufs {
@@ -2376,21 +2279,6 @@ namespace {
 
 int use_device(SyltWorld* w) {
     SYLT_CUDA(cudaSetDevice(w->device));
-    return SYLT_OK;
-}
-
-template <typename T>
-int run_scan(SyltWorld* w, T* in, T* out, int n_bound, const int* n_dev, T* agg, T* incl, int zero_in, int totals_mode) {
-    int nb = (n_bound + SCAN_TILE - 1) / SCAN_TILE;
-    if (nb < 1) nb = 1;
-    if (w->scan_epoch >= 0x3ffffff0u) {  // 30-bit epochs: start over with clean flags
-        SYLT_CUDA(cudaMemsetAsync(w->scan_flag.p, 0, w->scan_flag.cap * sizeof(unsigned), w->stream));
-        w->scan_epoch = 0;
-    }
-    SYLT_CUDA(launch_pdl(k_scan_lookback<T>, dim3((unsigned)nb), dim3(SCAN_THREADS), 0, w->stream, in, out, n_bound, n_dev, w->scan_flag.p, agg, incl, w->scan_ticket.p,
-                         ++w->scan_epoch, zero_in, w->counters.p, totals_mode, (int)w->cap_pairs));
-    w->launches++;
-    SYLT_CUDA(cudaGetLastError());
     return SYLT_OK;
 }
 
@@ -2546,13 +2434,6 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->cell_start.ensure((size_t)buckets + 2));
         SYLT_CUDA(w->cell_local.ensure((size_t)buckets + 8));
         SYLT_CUDA(w->tile_tot.ensure((size_t)buckets / CELL_TILE + 2));
-        size_t sp = ((size_t)std::max<size_t>(buckets, B + 1) + SCAN_TILE - 1) / SCAN_TILE + 1;
-        SYLT_CUDA(w->spart32.ensure(sp));
-        SYLT_CUDA(w->sincl32.ensure(sp));
-        if (!w->scan_ticket.p) {
-            SYLT_CUDA(w->scan_ticket.ensure(1));
-            SYLT_CUDA(cudaMemsetAsync(w->scan_ticket.p, 0, sizeof(int), w->stream));
-        }
         SYLT_CUDA(w->counters.ensure(1));
         if (w->have_old && w->B_old > 0 && !w->flags_stale)  // keep the flags the last step used for the next arbiter match
             SYLT_CUDA(cudaMemcpyAsync(w->bflags_old.p, w->bflags.p, (size_t)w->B_old * sizeof(int), cudaMemcpyDeviceToDevice, w->stream));  // (flags_stale: bflags_old already holds them)
@@ -2570,16 +2451,6 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->info.ensure((size_t)cp + 1));
         SYLT_CUDA(w->pscan.ensure((size_t)cp + 2));
         SYLT_CUDA(w->pair_btot.ensure((size_t)cp / PAIR_TILE + 2));
-        SYLT_CUDA(w->spart64.ensure((size_t)cp / SCAN_TILE + 2));
-        SYLT_CUDA(w->sincl64.ensure((size_t)cp / SCAN_TILE + 2));
-        {
-            const size_t nf = std::max(sp, (size_t)cp / SCAN_TILE + 2);
-            if (nf > w->scan_flag.cap) {
-                SYLT_CUDA(w->scan_flag.ensure(nf));
-                SYLT_CUDA(cudaMemsetAsync(w->scan_flag.p, 0, w->scan_flag.cap * sizeof(unsigned), w->stream));
-                w->scan_epoch = 0;
-            }
-        }
         SYLT_CUDA(w->tmp_a.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->tmp_b.ensure((size_t)cp * maxc));
         SYLT_CUDA(w->uncolored.ensure((size_t)ca));
@@ -3107,8 +2978,8 @@ static void free_all(SyltWorld* w) {
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cell_local.release(); w->tile_tot.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->large_start.release(); w->row_btot.release(); w->pair_btot.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
-    w->spart64.release(); w->spart32.release(); w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release(); w->unc_rec.release();
-    w->prop.release(); w->order.release(); w->sincl32.release(); w->sincl64.release(); w->scan_flag.release(); w->scan_ticket.release();
+    w->tmp_a.release(); w->tmp_b.release(); w->used.release(); w->used_int.release(); w->vrec.release(); w->jdeg.release(); w->jrank.release(); w->uncolored.release(); w->uncolored2.release(); w->unc_rec.release();
+    w->prop.release(); w->order.release();
     for (int k = 0; k < 2; k++) {
         auto& a = w->arb[k];
         a.bodies.release(); a.meta.release(); a.partner.release(); a.color.release(); a.row_start.release(); a.friction.release();
