@@ -381,12 +381,16 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
 // (a large body, a wider window) is searched by lane 0 alone.  Bodies are taken in cell order, so neighbouring warps search the
 // same buckets.  (Measured at 100k bodies: one thread per body 36 us, 16 lanes with a cell each 49 us — issue-bound, 32 M warp
 // instructions —, 4 lanes 39 us with 40 % of the lanes active.)
+template <int LPB>  // lanes per body: 16 (two bodies per warp — the kernel is bound by the number of warp lifetimes, see above) or 32
 __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
                                                     const float4* cent_aabb, const int* large_all, int n_large_all, const int* large_start, GridParams gp,
                                                     int* row_count, int* row_tmp, const Counters* cn, int* row_btot) {
     pdl_wait();
     pdl_trigger();
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    static_assert(LPB == 16 || LPB == 32, "one lane per segment (9 cells + the large list) is needed");
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) / LPB, lane = threadIdx.x & (LPB - 1);   // lane: inside the body's group of lanes
+    const int gshift = (threadIdx.x & 31) & ~(LPB - 1);                                              // first lane of the group inside its warp
+    const unsigned gmask = LPB == 32 ? 0xffffffffu : (0xffffu << gshift);
     if (g >= B) return;
     int i;
     float4 my;
@@ -412,7 +416,7 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
         y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell); y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
         fast = x1 - x0 <= 2 && y1 - y0 <= 2;
     }
-    if (!fast) {  // warp-uniform
+    if (!fast) {  // uniform over the body's lanes
         if (lane == 0) {
             int cnt = 0;
             row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large_all, large_start, gp, [&](int j) {
@@ -441,17 +445,17 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     int seg_end = seg_n;  // inclusive prefix
 #pragma unroll
     for (int o = 1; o < 16; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, seg_end, o);
+        const int u = __shfl_up_sync(gmask, seg_end, o, LPB);
         if (lane >= o) seg_end += u;
     }
-    const int total = __shfl_sync(0xffffffffu, seg_end, 9);
+    const int total = __shfl_sync(gmask, seg_end, 9, LPB);
     int found = 0;
-    for (int base = 0; base < total; base += 32) {
+    for (int base = 0; base < total; base += LPB) {
         const int e = base + lane;
         int seg = 0;  // the segment entry e belongs to: the number of segments that end at or before e
 #pragma unroll
-        for (int q = 0; q < 9; q++) seg += e >= __shfl_sync(0xffffffffu, seg_end, q);
-        const int s_end = __shfl_sync(0xffffffffu, seg_end, seg), s_n = __shfl_sync(0xffffffffu, seg_n, seg), s_k0 = __shfl_sync(0xffffffffu, seg_k0, seg);
+        for (int q = 0; q < 9; q++) seg += e >= __shfl_sync(gmask, seg_end, q, LPB);
+        const int s_end = __shfl_sync(gmask, seg_end, seg, LPB), s_n = __shfl_sync(gmask, seg_n, seg, LPB), s_k0 = __shfl_sync(gmask, seg_k0, seg, LPB);
         bool hit = false;
         int partner = 0;
         if (e < total) {
@@ -468,7 +472,7 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
                 partner = cj.x;
             }
         }
-        const unsigned m = __ballot_sync(0xffffffffu, hit);
+        const unsigned m = (__ballot_sync(gmask, hit) >> gshift) & (LPB == 32 ? 0xffffffffu : 0xffffu);
         const int pos = found + __popc(m & ((1u << lane) - 1u));
         if (hit && pos < ROWTMP) tmp[pos] = partner;
         found += __popc(m);
@@ -2605,7 +2609,8 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
                          w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1), w->gp, w->large.p, w->n_large));
     mark();
     const int nbR = (B + ROW_BLK - 1) / ROW_BLK;
-    SYLT_CUDA(launch_pdl(k_rows_count, dim3((unsigned)((B + 3) / 4)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
+    static const int rows_lpb = getenv("SYLT_ROWS_LPB") ? atoi(getenv("SYLT_ROWS_LPB")) : 16;
+    SYLT_CUDA(launch_pdl(rows_lpb == 32 ? k_rows_count<32> : k_rows_count<16>, dim3((unsigned)(rows_lpb == 32 ? (B + 3) / 4 : (B + 7) / 8)), dim3(128), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p,
                          (float4*)(w->cent_info.p + 1), w->large.p, w->n_large, w->large_start.p, w->gp, w->row_count.p, w->row_tmp.p, cn, w->row_btot.p));
     w->launches += 2;
     mark();
@@ -2644,12 +2649,13 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     }
     const int keep_colors = w->recolor_all ? 0 : (recut_now ? 2 : 1);
     w->recolor_all = false;
+    static const int build_mult = getenv("SYLT_BUILD_MULT") ? atoi(getenv("SYLT_BUILD_MULT")) : 4;  // CTAs per SM of k_build (8 measured slower: 32.8 vs 26.7 us at 100k bodies)
     if (w->any_poly)
-        SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
+        SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
                              w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
     else
-        SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * 4)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
+        SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
                              w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
     w->launches += 1;
