@@ -311,10 +311,12 @@ __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, co
 // body, large-large pairs to the lower index.  Partners are emitted sorted ascending.
 // The count pass remembers the first ROWTMP partners it finds so that the emit pass does not repeat the grid walk.
 constexpr int ROWTMP = 16;
+constexpr int WIDE_WINDOW = 64;  // a search window of more cells than this is searched by walking the (cell-ordered) entries instead
 
 template <typename F>
 __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, const float4* aabb, const int4* cinfo, const int* cell_start,
-                                           const int4* cent_info, const float4* cent_aabb, const int* large_all, const int* large_start, GridParams gp, F&& found) {
+                                           const int4* cent_info, const float4* cent_aabb, const int* large_all, const int* large_start, int n_small,
+                                           GridParams gp, F&& found) {
     const bool st_i = (ci.z & FLAG_STATIC) != 0;
     const int grp = group_of(ci.z);
     const int* large = large_all + large_start[grp];                       // the large bodies of this body's group
@@ -343,6 +345,14 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
                     if (st_i && (cj.w & FLAG_STATIC)) continue;
                     if (aabb_overlap(my, ab)) found(cj.x);
                 }
+            }
+        } else if ((long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1) > WIDE_WINDOW) {
+            // a window of many cells (a body at huge coordinates: the AABB margin grows with |x|): walk the entries, not the cells
+            for (int k = 0; k < n_small; k++) {
+                const int4 cj = cent_info[2 * k];
+                if (cj.x <= i || group_of(cj.w) != grp) continue;
+                if (st_i && (cj.w & FLAG_STATIC)) continue;
+                if (aabb_overlap(my, cent_aabb[2 * k])) found(cj.x);
             }
         } else {
             for (int cy = y0; cy <= y1; cy++)
@@ -416,10 +426,39 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
         y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell); y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
         fast = x1 - x0 <= 2 && y1 - y0 <= 2;
     }
+    if (!fast && !(ci.z & FLAG_LARGE) && (long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1) > WIDE_WINDOW) {
+        // a body at huge coordinates (the AABB margin grows with |x|, and so does the window): all lanes walk the entries of the small
+        // bodies, then the large list of the group — O(B) for this body, but no million-cell window (an exploding world stays steppable)
+        int found = 0;
+        const int l0 = large_start[grp], l1 = large_start[grp + 1];
+        const int n_all = large_base + (l1 - l0);
+        for (int base = 0; base < n_all; base += LPB) {
+            const int e = base + lane;
+            bool hit = false;
+            int partner = 0;
+            if (e < n_all) {
+                const int k = e < large_base ? e : large_base + l0 + (e - large_base);
+                const int4 cj = cent_info[2 * k];
+                const float4 ab = cent_aabb[2 * k];
+                const bool mine = e < large_base ? (cj.x > i && group_of(cj.w) == grp) : true;
+                hit = mine && !(st_i && (cj.w & FLAG_STATIC)) && aabb_overlap(my, ab);
+                partner = cj.x;
+            }
+            const unsigned m = (__ballot_sync(gmask, hit) >> gshift) & (LPB == 32 ? 0xffffffffu : 0xffffu);
+            const int pos = found + __popc(m & ((1u << lane) - 1u));
+            if (hit && pos < ROWTMP) tmp[pos] = partner;
+            found += __popc(m);
+        }
+        if (lane == 0) {
+            row_count[i] = found;
+            if (found) atomicAdd(&row_btot[i / ROW_BLK], found);
+        }
+        return;
+    }
     if (!fast) {  // uniform over the body's lanes
         if (lane == 0) {
             int cnt = 0;
-            row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large_all, large_start, gp, [&](int j) {
+            row_search(i, B, my, ci, aabb, cinfo, cell_start, cent_info, cent_aabb, large_all, large_start, large_base, gp, [&](int j) {
                 if (cnt < ROWTMP) tmp[cnt] = j;
                 cnt++;
             });
@@ -485,7 +524,7 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
 
 __global__ void __launch_bounds__(ROW_BLK) k_rows_emit(int B, const float4* aabb, const int4* cinfo, const int* cell_start, const int4* cent_info,
                                                        const float4* cent_aabb, const int* large, const int* large_start, GridParams gp, int* row_start, const int* row_tmp,
-                                                       int2* pairs, int cap_pairs, Counters* cn, const int* row_count, const int* row_btot) {
+                                                       int2* pairs, int cap_pairs, Counters* cn, const int* row_count, const int* row_btot, int n_small) {
     __shared__ int sh[34];
     pdl_wait();
     pdl_trigger();
@@ -527,7 +566,7 @@ __global__ void __launch_bounds__(ROW_BLK) k_rows_emit(int B, const float4* aabb
         return;
     }
     int m = 0;
-    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cent_info, cent_aabb, large, large_start, gp, [&](int j) { pairs[base + m++] = make_int2(i, j); });
+    row_search(i, B, aabb[i], cinfo[i], aabb, cinfo, cell_start, cent_info, cent_aabb, large, large_start, n_small, gp, [&](int j) { pairs[base + m++] = make_int2(i, j); });
     for (int a = 1; a < n; a++) {
         int2 x = pairs[base + a];
         int b = a - 1;
@@ -2615,7 +2654,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->launches += 2;
     mark();
     SYLT_CUDA(launch_pdl(k_rows_emit, dim3((unsigned)nbR), dim3(ROW_BLK), 0, st, B, w->aabb.p, w->cinfo.p, w->cell_start.p, w->cent_info.p, (float4*)(w->cent_info.p + 1),
-                         w->large.p, w->large_start.p, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn, w->row_count.p, w->row_btot.p));
+                         w->large.p, w->large_start.p, w->gp, w->row_start.p, w->row_tmp.p, w->pairs.p, (int)w->cap_pairs, cn, w->row_count.p, w->row_btot.p, B - w->n_large));
     w->launches += 1;
     mark();
     const int gridP = w->num_sms * 8;

@@ -973,3 +973,30 @@ def test_rust_wrapper_call_sequence_replayed_in_cpp(tmp_path):
                     "-L", orcdir, "-lorc", f"-Wl,-rpath,{lib}", f"-Wl,-rpath,{orcdir}", "-o", exe], check=True)
     r = subprocess.run([exe], capture_output=True, text=True)
     assert r.returncode == 0 and "bit-identical" in r.stdout, r.stdout + r.stderr
+
+
+def test_bodies_at_huge_coordinates_stay_exact_and_cheap():
+    """The conservative AABB margin grows with |x|; at |x| ~ 1e7 a body's search window is hundreds of cells wide.  Such bodies are
+    searched by walking the cell-ordered entries instead of the cells (k_rows_count's wide path): the pair set stays a superset of
+    the all-pairs oracle's hits (bit-exact arbiters and states) and a step stays cheap (an exploding polygon pile used to take
+    150 ms per step)."""
+    import time
+    b = scenes._Builder()
+    scenes._ground(b)
+    for r in range(6):
+        for c in range(6 - r):
+            b.box(1.0, 1.0, 10.0, 0.2, (-3.0 + 0.5625 * r + 1.125 * c, 0.75 + 1.05 * r))
+    for k in range(60):                                     # far away: ulp(1e7) = 1, so neighbours one unit apart overlap by construction
+        b.box(1.5, 1.5, 5.0, 0.3, (1.0e7 + (k // 2) * 6.0 + (k % 2) * 1.0, 3.0e6 + (k % 3)), rot=0.1 * k, vel=(0.5 * (k % 5), -1.0))
+    b.box(2.0, 2.0, 5.0, 0.3, (-4.0e8, 2.0e8), vel=(1.0e4, 0.0))
+    sc = b.scene("far_bodies", iterations=10)
+    w, o = _mk(sc)                                          # oracle: the reference's all-pairs loop
+    t0 = time.perf_counter()
+    for s in range(6):
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"far bodies step {s}")
+    ga = _assert_arbiters_equal(w, o, what="far bodies")
+    assert (ga["body1"] > 21).sum() >= 20                   # the far bodies do touch one another
+    assert time.perf_counter() - t0 < 5.0
