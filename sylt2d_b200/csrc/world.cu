@@ -79,6 +79,8 @@ struct Counters {
     int n_ghost;                    // replicas of generic arbiters replayed by neighbouring regions
     int max_slots, n_nonres;        // load of the busiest CTA; slots whose records / contacts did not fit into shared memory
     int why;                        // diagnostics: bit mask of what overflowed in k_solve_regions
+    int n_unc_generic;              // new arbiters of this step that cross regions (k_build)
+    int n_promoted;                 // new interior arbiters that found no free interior colour (they take a generic one, grid-wide)
     unsigned long long color_mask;  // generic colours in use
     unsigned color_mask_int;        // interior colours in use
 };
@@ -649,7 +651,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
                                                unsigned long long* used, int4* unc_rec, int fix_features, int keep_colors, unsigned* used_int, int regions,
-                                               const int* region_of) {
+                                               const int* region_of, int2* gadj) {
     pdl_wait();
     const int failed = __ldcg(&cn->err);
     int P = min(__ldcg(&cn->n_pairs), cap_pairs);
@@ -756,16 +758,22 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                 const int bit = regions ? color - GEN_BIT : color;
                 if (d1) atomicOr(&used[b1], 1ull << bit);
                 if (d2) atomicOr(&used[b2], 1ull << bit);
+                if (regions) {  // the per-body table of generic arbiters the region solver's cone walk reads (slot = colour bit)
+                    const int2 entry = make_int2(a, region_of[pr.x] | (color << 16));
+                    if (d1) gadj[(size_t)b1 * NC + bit] = entry;
+                    if (d2) gadj[(size_t)b2 * NC + bit] = entry;
+                }
             }
             atomicAdd(&s_hist[color], 1);
         } else {
             // everything the colouring rounds need to know about a new arbiter, in one 16-byte record: the rounds are chains of
             // dependent L2 round trips, and this takes two links (bodies -> flags -> regions) out of every one of them
             const bool s1 = (bflags[b1] & FLAG_STATIC) != 0, s2 = (bflags[b2] & FLAG_STATIC) != 0;
-            int interior = 0;
+            int interior = 0;  // region solver: owner region + 1 (interior) or -(owner region + 1) (cross-region)
             if (regions) {
                 const int R = region_of[pr.x];  // pr.x owns the pair
-                interior = ((s1 || region_of[b1] == R) && (s2 || region_of[b2] == R)) ? 1 : 0;
+                interior = ((s1 || region_of[b1] == R) && (s2 || region_of[b2] == R)) ? R + 1 : -(R + 1);
+                if (interior < 0) atomicAdd(&cn->n_unc_generic, 1);
             }
             unc_rec[atomicAdd(&cn->n_uncolored, 1)] = make_int4(a, b1 | (s1 ? UNC_STATIC : 0), b2 | (s2 ? UNC_STATIC : 0), interior);
         }
@@ -922,83 +930,153 @@ struct BodyIO {
 // region of the pair's owner body (k_solve_regions solves those in shared memory); every other arbiter, and an interior
 // candidate that finds no free interior colour, takes a colour >= GEN_BIT ("generic": solved through the versioned
 // records in L2).  The class of an arbiter IS its colour range, so it persists with the colour.
+constexpr int LOCAL_UNC_MAX = 8192;     // region solver: up to this many new arbiters per step (and SOLO_GEN_MAX cross-region ones among them)
+constexpr int SOLO_GEN_MAX = 2048;      // every region CTA colours its own new interior arbiters with block barriers only
+constexpr int PROMOTE_ROUND0 = 128;     // grid-wide rounds of the interior arbiters that overflowed into the generic colours
 template <bool REGIONS>
-__device__ __forceinline__ void color_new_arbiters(const SolveArgs& a, Counters* cn, unsigned* bar, unsigned& bar_target) {
+__device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters* cn, unsigned* bar, unsigned& bar_target, unsigned char* scratch, int scratch_bytes) {  // true: the grid has met at a barrier
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int T = blockDim.x, bid = blockIdx.x, lt = threadIdx.x;
     const int nunc = *(volatile int*)&cn->n_uncolored;
-    if (nunc > 0) {
-        // round r reads the list L[r & 1] (n entries); arbiters that lose a claim append themselves to the other list,
-        // whose length is counted in cn->remaining[r].  The grid runs the rounds while many arbiters are left, then
-        // CTA 0 finishes the stragglers alone with block barriers while the others wait at one grid barrier.
-        int* lists[2] = {a.uncolored, a.uncolored2};
-        int n = nunc;
+    if (nunc <= 0) return false;
+    int* lists[2] = {a.uncolored, a.uncolored2};
+    // one record of one round: the colour it proposes (-1: none free at all, -2: no free INTERIOR colour and `promote`)
+    auto propose = [&](const int4 rec, int round, bool promote) -> int {
+        const int e = rec.x;
+        const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
+        const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
+        int c = -1;
+        if (REGIONS && rec.w > 0) {  // interior: lowest free interior colour
+            const unsigned fi = ~((d1 ? __ldcg(&a.used_int[b.x]) : 0u) | (d2 ? __ldcg(&a.used_int[b.y]) : 0u));
+            if (fi) c = __ffs((int)fi) - 1;
+            else if (promote) return -2;
+        }
+        if (c < 0) {
+            const unsigned long long fr = ~((d1 ? __ldcg(&a.used[b.x]) : 0ull) | (d2 ? __ldcg(&a.used[b.y]) : 0ull));
+            if (fr) c = (REGIONS ? GEN_BIT : 0) + __ffsll((long long)fr) - 1;  // lowest free (generic) colour
+        }
+        if (c < 0) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); return -1; }
+        const unsigned long long val = ((unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32) | fmix32((unsigned)e * 2654435761u + (unsigned)round);
+        if (d1) atomicMin(&a.claim[(size_t)b.x * NCX + c], val);
+        if (d2) atomicMin(&a.claim[(size_t)b.y * NCX + c], val);
+        return c;
+    };
+    // ... and whether its claim survived: then the colour is final
+    auto settle = [&](const int4 rec, int round, int c) -> bool {
+        const int e = rec.x;
+        const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
+        const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
+        const unsigned long long val = ((unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32) | fmix32((unsigned)e * 2654435761u + (unsigned)round);
+        const bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NCX + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NCX + c]) == val);
+        if (!win) return false;
+        a.cur.color[e] = c;
+        if (REGIONS && c < GEN_BIT) {
+            if (d1) atomicOr(&a.used_int[b.x], 1u << c);
+            if (d2) atomicOr(&a.used_int[b.y], 1u << c);
+        } else {
+            const int bit = REGIONS ? c - GEN_BIT : c;
+            if (d1) atomicOr(&a.used[b.x], 1ull << bit);
+            if (d2) atomicOr(&a.used[b.y], 1ull << bit);
+            if (REGIONS) {  // (as k_build does for the persisting ones; rec.w = +-(owner region + 1))
+                const int2 entry = make_int2(e, ((rec.w < 0 ? -rec.w : rec.w) - 1) | (c << 16));
+                if (d1) a.gadj[(size_t)b.x * NC + bit] = entry;
+                if (d2) a.gadj[(size_t)b.y * NC + bit] = entry;
+            }
+        }
+        atomicAdd(&cn->color_count[c], 1);
+        return true;
+    };
+    // Grid-wide rounds.  Round r reads the list L[r & 1] (n entries; `identity`: the first round takes every record); arbiters that
+    // lose a claim append themselves to the other list, whose length is counted in cn->remaining[r].  The grid runs the rounds
+    // while many arbiters are left, then CTA 0 finishes the stragglers alone with block barriers while the others wait at one
+    // grid barrier.
+    auto grid_rounds = [&](int n, int round0, bool identity) {
         bool solo = n <= T;  // block-uniform and identical in every CTA (one entry per thread of CTA 0)
-        int round = 0;
-        for (; round < MAX_ROUNDS; round++) {
+        int round = round0;
+        for (; round < round0 + PROMOTE_ROUND0; round++) {
             if (solo && bid != 0) break;
             const int ct = solo ? lt : tid, cs = solo ? T : nth;
             const int* cur_list = lists[round & 1];
             int* next_list = lists[(round + 1) & 1];
-            const unsigned long long ep = (unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32;
+            const bool ident = identity && round == round0;
             for (int k = ct; k < n; k += cs) {
-                const int r = round == 0 ? k : __ldcg(&cur_list[k]);  // (round 0: every record)
-                const int4 rec = __ldcg(&a.unc_rec[r]);
-                const int e = rec.x;
-                const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
-                const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
-                unsigned long long m = (d1 ? __ldcg(&a.used[b.x]) : 0ull) | (d2 ? __ldcg(&a.used[b.y]) : 0ull);
-                unsigned long long fr = ~m;
-                int c = -1;
-                if (REGIONS) {
-                    const bool interior = rec.w != 0;
-                    const unsigned fi = interior ? ~((d1 ? __ldcg(&a.used_int[b.x]) : 0u) | (d2 ? __ldcg(&a.used_int[b.y]) : 0u)) : 0u;
-                    if (fi) c = __ffs((int)fi) - 1;                             // lowest free interior colour
-                    else if (fr) c = GEN_BIT + __ffsll((long long)fr) - 1;      // lowest free generic colour
-                } else if (fr) {
-                    c = __ffsll((long long)fr) - 1;  // lowest free colour
-                }
-                if (c < 0) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); a.prop[r] = -1; continue; }
-                a.prop[r] = c;
-                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
-                if (d1) atomicMin(&a.claim[(size_t)b.x * NCX + c], val);
-                if (d2) atomicMin(&a.claim[(size_t)b.y * NCX + c], val);
+                const int r = ident ? k : __ldcg(&cur_list[k]);
+                a.prop[r] = propose(__ldcg(&a.unc_rec[r]), round, false);
             }
             if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
             for (int k = ct; k < n; k += cs) {
-                const int r = round == 0 ? k : __ldcg(&cur_list[k]);
+                const int r = ident ? k : __ldcg(&cur_list[k]);
                 const int c = __ldcg(&a.prop[r]);
                 if (c < 0) continue;
-                const int4 rec = __ldcg(&a.unc_rec[r]);
-                const int e = rec.x;
-                const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
-                const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
-                unsigned long long val = ep | fmix32((unsigned)e * 2654435761u + (unsigned)round);
-                bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NCX + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NCX + c]) == val);
-                if (win) {
-                    a.cur.color[e] = c;
-                    if (REGIONS && c < GEN_BIT) {
-                        if (d1) atomicOr(&a.used_int[b.x], 1u << c);
-                        if (d2) atomicOr(&a.used_int[b.y], 1u << c);
-                    } else {
-                        const int bit = REGIONS ? c - GEN_BIT : c;
-                        if (d1) atomicOr(&a.used[b.x], 1ull << bit);
-                        if (d2) atomicOr(&a.used[b.y], 1ull << bit);
-                    }
-                    atomicAdd(&cn->color_count[c], 1);
-                } else {
-                    next_list[atomicAdd(&cn->remaining[round], 1)] = r;
-                }
+                if (!settle(__ldcg(&a.unc_rec[r]), round, c)) next_list[atomicAdd(&cn->remaining[round], 1)] = r;
             }
             if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
             n = *(volatile int*)&cn->remaining[round];
             if (n == 0) break;
             if (n <= T) solo = true;  // the stragglers are CTA 0's job; the others go and wait
         }
-        if (bid == 0 && lt == 0) cn->rounds = round + 1;
+        if (bid == 0 && lt == 0) atomicMax(&cn->rounds, round - round0 + 1);
         if (solo) grid_barrier(bar, bar_target);  // everybody waits for CTA 0's colours
+    };
+    // Region solver, the usual step (a few thousand new arbiters): an interior arbiter only ever meets interior arbiters of its
+    // own region at its dynamic bodies, so every CTA colours the new interior arbiters of its region by itself — the same
+    // propose / claim rounds, but with block barriers instead of grid barriers — while CTA 0 also takes the (few) cross-region ones
+    // along.  One grid barrier at the end.  An interior arbiter without a free interior colour is "promoted": it takes a generic
+    // colour in grid-wide rounds behind that barrier (a body touching more than 32 others inside its region; rare).
+    const int ngen = REGIONS ? *(volatile int*)&cn->n_unc_generic : 0;
+    if (REGIONS && nunc <= LOCAL_UNC_MAX && ngen <= SOLO_GEN_MAX && (size_t)nunc * 32 <= (size_t)scratch_bytes) {
+        __shared__ int s_n, s_nn;
+        int4* l_rec = (int4*)scratch;          // my records
+        int* l_idx = (int*)(l_rec + nunc);     // their indices in unc_rec
+        int* l_cur = l_idx + nunc;             // the records still uncoloured (indices into l_rec), ping-pong
+        int* l_next = l_cur + nunc;
+        int* l_prop = l_next + nunc;
+        if (lt == 0) s_n = 0;
+        __syncthreads();
+        for (int k0 = lt; k0 < nunc; k0 += 8 * T) {  // (every CTA reads every record: eight independent loads in flight per thread)
+            int4 rec[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) rec[u] = k0 + u * T < nunc ? __ldcg(&a.unc_rec[k0 + u * T]) : make_int4(0, 0, 0, 0x7fffffff);
+#pragma unroll
+            for (int u = 0; u < 8; u++)
+                if (rec[u].w == bid + 1 || (bid == 0 && rec[u].w <= 0)) {
+                    const int q = atomicAdd(&s_n, 1);
+                    l_rec[q] = rec[u]; l_idx[q] = k0 + u * T; l_cur[q] = q;
+                }
+        }
+        __syncthreads();
+        int n = s_n, round = 0;
+        for (; n > 0 && round < PROMOTE_ROUND0; round++) {
+            if (lt == 0) s_nn = 0;
+            for (int k = lt; k < n; k += T) {
+                const int q = l_cur[k];
+                const int c = propose(l_rec[q], round, true);
+                l_prop[q] = c;
+                if (c == -2) lists[PROMOTE_ROUND0 & 1][atomicAdd(&cn->n_promoted, 1)] = l_idx[q];
+            }
+            __threadfence();
+            __syncthreads();
+            for (int k = lt; k < n; k += T) {
+                const int q = l_cur[k];
+                const int c = l_prop[q];
+                if (c < 0) continue;
+                if (!settle(l_rec[q], round, c)) l_next[atomicAdd(&s_nn, 1)] = q;
+            }
+            __threadfence();
+            __syncthreads();
+            n = s_nn;
+            int* t = l_cur; l_cur = l_next; l_next = t;
+            __syncthreads();
+        }
+        if (n > 0) atomicExch(&cn->err, SYLT_ERR_INTERNAL);  // (never: a round always colours the arbiter with the smallest priority)
+        if (lt == 0 && round > 0) atomicMax(&cn->rounds, round);
+        grid_barrier(bar, bar_target);
+        const int np = *(volatile int*)&cn->n_promoted;
+        if (np > 0) grid_rounds(np, PROMOTE_ROUND0, false);
+        return true;
     }
-
+    grid_rounds(nunc, 0, true);
+    return true;
 }
 
 __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
@@ -1036,7 +1114,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     float4* s_cb = s_ca + CONCAP;
     float4* s_cc = s_cb + CONCAP;
 
-    color_new_arbiters<false>(a, cn, bar, bar_target);
+    color_new_arbiters<false>(a, cn, bar, bar_target, nullptr, 0);
 
     stamp(1);
     // ---- 2. colour-major order (within a colour the order is irrelevant: disjoint dynamic bodies) and this CTA's share
@@ -1460,24 +1538,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     // a step that already failed in the broad phase (capacity) has holes in its arbiter arrays: nothing to solve, error reported
     if (step_failed(cn)) return;
     fill_arbiter_rows(a.B, min(*(volatile int*)&cn->n_pairs, a.cap_pairs), a.cand_row_start, a.pscan, a.cur.row_start, tid, nth);  // read after the barrier of 2a
-    color_new_arbiters<true>(a, cn, bar, bar_target);
+    // (the per-body table of generic arbiters `gadj` — slot = colour bit, entry = (arbiter, owner region | colour << 16) — was written by
+    // k_build and by the colouring; the rows and the colours of other CTAs' arbiters are visible behind the grid barrier)
+    if (!color_new_arbiters<true>(a, cn, bar, bar_target, sm_raw, a.smem_bytes)) grid_barrier(bar, bar_target);
     stamp(1);
     tstamp();
     if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // an arbiter without a free colour (every CTA sees it: the colouring ends with a barrier)
     auto dynamic = [&](int b) { return !(a.bflags[b] & FLAG_STATIC); };
-    auto owner_region = [&](int e, int2 b) { return a.region_of[a.cur.partner[e] == b.x ? b.y : b.x]; };
-
-    // ---- 2a. per-body table of the generic arbiters (colours are distinct around a body: the slot is the colour's rank)
-    for (int e = tid; e < A; e += nth) {
-        const int c = __ldcg(&a.cur.color[e]);
-        if (c < GEN_BIT) continue;
-        const int2 b = a.cur.bodies[e];
-        const unsigned long long lower = (1ull << (c - GEN_BIT)) - 1ull;
-        const int2 entry = make_int2(e, owner_region(e, b) | (c << 16));  // what the cone walk needs to know about e without touching it
-        if (dynamic(b.x)) a.gadj[(size_t)b.x * GADJ + __popcll(__ldcg(&a.used[b.x]) & lower)] = entry;
-        if (dynamic(b.y)) a.gadj[(size_t)b.y * GADJ + __popcll(__ldcg(&a.used[b.y]) & lower)] = entry;
-    }
-    grid_barrier(bar, bar_target);
     tstamp();
     unsigned long long t_setup0 = 0;
     if (a.dbg && lt == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_setup0));
@@ -1519,7 +1586,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
             while (m) {
                 const int k = __ffsll((long long)m) - 1;
                 m &= m - 1ull;
-                const int2 f = __ldcg(&a.gadj[(size_t)z * GADJ + __popcll(uz & ((1ull << k) - 1ull))]);
+                const int2 f = __ldcg(&a.gadj[(size_t)z * GADJ + k]);
                 if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + k);  // (an own arbiter is a root of the walk anyway)
             }
         }
@@ -1557,10 +1624,10 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     }
     for (int k = lt; k < s_nbnd; k += T) {  // every generic arbiter at a boundary body is replayed here, whoever owns it
         const int b = s_bndg[k];
-        const int ng = __popcll(__ldcg(&a.used[b]));
-        for (int r = 0; r < ng; r++) {
-            const int2 f = __ldcg(&a.gadj[(size_t)b * GADJ + r]);
-            if ((f.y & 0xffff) != R) add_ghost(f.x, f.y >> 16);
+        for (unsigned long long m = __ldcg(&a.used[b]); m; m &= m - 1ull) {
+            const int kb = __ffsll((long long)m) - 1;
+            const int2 f = __ldcg(&a.gadj[(size_t)b * GADJ + kb]);
+            if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + kb);
         }
     }
     __syncthreads();
@@ -2692,11 +2759,11 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p));
     else
         SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
     mark();
@@ -2783,6 +2850,7 @@ void print_solver_timing(SyltWorld* w) {
         fprintf(stderr, "  pass 5, all CTAs [us] min/avg/max: interior %.2f/%.2f/%.2f  export+import %.2f/%.2f/%.2f  generic %.2f/%.2f/%.2f\n", mn[0], sm[0] / G, mx[0],
                 mn[1], sm[1] / G, mx[1], mn[2], sm[2] / G, mx[2]);
     }
+    fprintf(stderr, "new arbiters %d of %d, colouring rounds %d\n", w->last.n_uncolored, w->last.n_arb, w->last.rounds);
     fprintf(stderr, "k_solve sections [us]: colour %.1f order %.1f residency %.1f pass0 %.1f iterations %.1f writeback %.1f integrate %.1f total %.1f\n",
             (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3,
             (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
