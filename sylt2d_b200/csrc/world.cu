@@ -55,6 +55,7 @@ namespace {
 constexpr int NC = 64;          // max arbiter colours (one bit each in the per-body 64-bit `used` mask)
 constexpr int GEN_BIT = 32;     // region solver: colours [0, GEN_BIT) are interior colours (bits of `used_int`), colour GEN_BIT + k is bit k of `used`
 constexpr int NCX = NC + GEN_BIT;
+constexpr int MAX_REGIONS = 1024;  // region solver: CTAs of the cooperative launch
 constexpr int MAX_ROUNDS = 256; // colouring rounds per step (only new arbiters take part)
 constexpr int FLAG_POLY = 1, FLAG_LARGE = 2, FLAG_STATIC = 4;
 
@@ -79,8 +80,9 @@ struct Counters {
     int n_ghost;                    // replicas of generic arbiters replayed by neighbouring regions
     int max_slots, n_nonres;        // load of the busiest CTA; slots whose records / contacts did not fit into shared memory
     int why;                        // diagnostics: bit mask of what overflowed in k_solve_regions
-    int n_unc_generic;              // new arbiters of this step that cross regions (k_build)
     int n_promoted;                 // new interior arbiters that found no free interior colour (they take a generic one, grid-wide)
+    int bin_overflow;               // a region has more new arbiters than its bin holds: this step is coloured by the grid-wide rounds
+    int region_new[MAX_REGIONS + 1];  // new arbiters per owner region (interior ones; the cross-region ones are counted at [n_regions])
     unsigned long long color_mask;  // generic colours in use
     unsigned color_mask_int;        // interior colours in use
 };
@@ -651,7 +653,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
                                                unsigned long long* used, int4* unc_rec, int fix_features, int keep_colors, unsigned* used_int, int regions,
-                                               const int* region_of, int2* gadj) {
+                                               const int* region_of, int2* gadj, int n_regions, int4* unc_bin, int* unc_bin_idx, int bin_cap) {
     pdl_wait();
     const int failed = __ldcg(&cn->err);
     int P = min(__ldcg(&cn->n_pairs), cap_pairs);
@@ -773,9 +775,16 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
             if (regions) {
                 const int R = region_of[pr.x];  // pr.x owns the pair
                 interior = ((s1 || region_of[b1] == R) && (s2 || region_of[b2] == R)) ? R + 1 : -(R + 1);
-                if (interior < 0) atomicAdd(&cn->n_unc_generic, 1);
             }
-            unc_rec[atomicAdd(&cn->n_uncolored, 1)] = make_int4(a, b1 | (s1 ? UNC_STATIC : 0), b2 | (s2 ? UNC_STATIC : 0), interior);
+            const int4 rec = make_int4(a, b1 | (s1 ? UNC_STATIC : 0), b2 | (s2 ? UNC_STATIC : 0), interior);
+            const int ui = atomicAdd(&cn->n_uncolored, 1);
+            unc_rec[ui] = rec;
+            if (regions) {  // ... and once more in the bin of the region CTA that will colour it (the cross-region ones: one bin behind the regions')
+                const int bin = interior > 0 ? interior - 1 : n_regions;
+                const int q = atomicAdd(&cn->region_new[bin], 1);
+                if (q < bin_cap) { unc_bin[(size_t)bin * bin_cap + q] = rec; unc_bin_idx[(size_t)bin * bin_cap + q] = ui; }
+                else cn->bin_overflow = 1;
+            }
         }
     }
     }
@@ -797,6 +806,8 @@ __device__ __forceinline__ unsigned fmix32(unsigned h) {  // bijective mix: uniq
     h ^= h >> 16; h *= 0x85ebca6bu; h ^= h >> 13; h *= 0xc2b2ae35u; h ^= h >> 16;
     return h;
 }
+
+__device__ __forceinline__ unsigned hash_u32(unsigned x) { return fmix32(x * 2654435761u); }
 
 struct SolveArgs {
     Counters* cn;
@@ -837,6 +848,10 @@ struct SolveArgs {
     ulonglong2* xrec;                                      // export planes (one per pass) of versioned boundary-body velocities
     unsigned step_tag;
     int probe_cta;                                         // diagnostics: the CTA whose set-up phases are stamped
+    const int4* unc_bin;                                   // new arbiters binned by owner region (k_build); bin n_regions: the cross-region ones
+    const int* unc_bin_idx;                                //   their indices in unc_rec
+    int bin_cap;
+    int color_local;                                       // CTA-local colouring of new interior arbiters (SYLT_COLOR_LOCAL=0: grid-wide rounds only)
     // candidate rows + candidate -> (arbiter, contact) offsets of this step (fill_arbiter_rows)
     const int* cand_row_start;
     const unsigned long long* pscan;
@@ -930,60 +945,82 @@ struct BodyIO {
 // region of the pair's owner body (k_solve_regions solves those in shared memory); every other arbiter, and an interior
 // candidate that finds no free interior colour, takes a colour >= GEN_BIT ("generic": solved through the versioned
 // records in L2).  The class of an arbiter IS its colour range, so it persists with the colour.
-constexpr int LOCAL_UNC_MAX = 8192;     // region solver: up to this many new arbiters per step (and SOLO_GEN_MAX cross-region ones among them)
-constexpr int SOLO_GEN_MAX = 2048;      // every region CTA colours its own new interior arbiters with block barriers only
 constexpr int PROMOTE_ROUND0 = 128;     // grid-wide rounds of the interior arbiters that overflowed into the generic colours
+constexpr int CB = 4;                   // records a thread has in flight at once: a round is a chain of dependent L2 round trips
 template <bool REGIONS>
 __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters* cn, unsigned* bar, unsigned& bar_target, unsigned char* scratch, int scratch_bytes) {  // true: the grid has met at a barrier
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int T = blockDim.x, bid = blockIdx.x, lt = threadIdx.x;
     const int nunc = *(volatile int*)&cn->n_uncolored;
     if (nunc <= 0) return false;
+    int cq_ = 0;
+    auto cstamp = [&]() { if (a.dbg && (bid == 0 || bid == a.probe_cta) && lt == 0 && cq_ < 8) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[(bid == 0 ? 48 : 56) + cq_++] = t; } };
+    cstamp();
     int* lists[2] = {a.uncolored, a.uncolored2};
-    // one record of one round: the colour it proposes (-1: none free at all, -2: no free INTERIOR colour and `promote`)
-    auto propose = [&](const int4 rec, int round, bool promote) -> int {
-        const int e = rec.x;
-        const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
+    const int4 no_rec = make_int4(-1, UNC_STATIC, UNC_STATIC, 0);  // (a lane without a record: loads body 0, does nothing)
+    struct Masks { unsigned fi; unsigned long long fr; };
+    // The loads of a round are unconditional (static bodies included, masked afterwards) and issued for CB records before any of
+    // them is used: one L2 round trip per phase instead of one per record and branch.
+    auto load_masks = [&](const int4 rec, bool local) -> Masks {  // free interior / generic colours at the dynamic bodies of the pair
+        const int bx = rec.y & ~UNC_STATIC, by = rec.z & ~UNC_STATIC;
         const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
+        // (the CTA-local rounds promote an interior arbiter without a free interior colour instead of looking at the generic ones)
+        const bool want_gen = !REGIONS || !local || rec.w <= 0, want_int = REGIONS && rec.w > 0;
+        unsigned long long y1 = 0ull, y2 = 0ull;
+        unsigned x1 = 0u, x2 = 0u;
+        if (want_gen) { y1 = __ldcg(&a.used[bx]); y2 = __ldcg(&a.used[by]); }
+        if (want_int) { x1 = __ldcg(&a.used_int[bx]); x2 = __ldcg(&a.used_int[by]); }
+        Masks m;
+        m.fi = ~((d1 ? x1 : 0u) | (d2 ? x2 : 0u));
+        m.fr = ~((d1 ? y1 : 0ull) | (d2 ? y2 : 0ull));
+        return m;
+    };
+    auto claim_val = [&](int e, int round) -> unsigned long long {
+        return ((unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32) | fmix32((unsigned)e * 2654435761u + (unsigned)round);
+    };
+    // one record of one round: the colour it goes for (-1: none free at all, -2: no free INTERIOR colour and `promote`)
+    auto pick = [&](const int4 rec, const Masks m, bool promote) -> int {
         int c = -1;
         if (REGIONS && rec.w > 0) {  // interior: lowest free interior colour
-            const unsigned fi = ~((d1 ? __ldcg(&a.used_int[b.x]) : 0u) | (d2 ? __ldcg(&a.used_int[b.y]) : 0u));
-            if (fi) c = __ffs((int)fi) - 1;
+            if (m.fi) c = __ffs((int)m.fi) - 1;
             else if (promote) return -2;
         }
-        if (c < 0) {
-            const unsigned long long fr = ~((d1 ? __ldcg(&a.used[b.x]) : 0ull) | (d2 ? __ldcg(&a.used[b.y]) : 0ull));
-            if (fr) c = (REGIONS ? GEN_BIT : 0) + __ffsll((long long)fr) - 1;  // lowest free (generic) colour
-        }
-        if (c < 0) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); return -1; }
-        const unsigned long long val = ((unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32) | fmix32((unsigned)e * 2654435761u + (unsigned)round);
-        if (d1) atomicMin(&a.claim[(size_t)b.x * NCX + c], val);
-        if (d2) atomicMin(&a.claim[(size_t)b.y * NCX + c], val);
+        if (c < 0 && m.fr) c = (REGIONS ? GEN_BIT : 0) + __ffsll((long long)m.fr) - 1;  // lowest free (generic) colour
+        if (c < 0) atomicExch(&cn->err, SYLT_ERR_CAPACITY);
         return c;
     };
-    // ... and whether its claim survived: then the colour is final
-    auto settle = [&](const int4 rec, int round, int c) -> bool {
-        const int e = rec.x;
-        const int2 b = make_int2(rec.y & ~UNC_STATIC, rec.z & ~UNC_STATIC);
+    auto propose = [&](const int4 rec, const Masks m, int round) -> int {  // ... and its claims in the global cells
+        const int c = pick(rec, m, false);
+        if (c < 0) return -1;
+        const unsigned long long val = claim_val(rec.x, round);
+        if (!(rec.y & UNC_STATIC)) atomicMin(&a.claim[(size_t)(rec.y & ~UNC_STATIC) * NCX + c], val);
+        if (!(rec.z & UNC_STATIC)) atomicMin(&a.claim[(size_t)(rec.z & ~UNC_STATIC) * NCX + c], val);
+        return c;
+    };
+    // the colour of a record whose claims survived is final
+    auto finalize = [&](const int4 rec, int c) {
+        const int e = rec.x, bx = rec.y & ~UNC_STATIC, by = rec.z & ~UNC_STATIC;
         const bool d1 = !(rec.y & UNC_STATIC), d2 = !(rec.z & UNC_STATIC);
-        const unsigned long long val = ((unsigned long long)(~(a.epoch_base + (unsigned)round)) << 32) | fmix32((unsigned)e * 2654435761u + (unsigned)round);
-        const bool win = (!d1 || __ldcg(&a.claim[(size_t)b.x * NCX + c]) == val) && (!d2 || __ldcg(&a.claim[(size_t)b.y * NCX + c]) == val);
-        if (!win) return false;
         a.cur.color[e] = c;
         if (REGIONS && c < GEN_BIT) {
-            if (d1) atomicOr(&a.used_int[b.x], 1u << c);
-            if (d2) atomicOr(&a.used_int[b.y], 1u << c);
+            if (d1) atomicOr(&a.used_int[bx], 1u << c);
+            if (d2) atomicOr(&a.used_int[by], 1u << c);
         } else {
             const int bit = REGIONS ? c - GEN_BIT : c;
-            if (d1) atomicOr(&a.used[b.x], 1ull << bit);
-            if (d2) atomicOr(&a.used[b.y], 1ull << bit);
+            if (d1) atomicOr(&a.used[bx], 1ull << bit);
+            if (d2) atomicOr(&a.used[by], 1ull << bit);
             if (REGIONS) {  // (as k_build does for the persisting ones; rec.w = +-(owner region + 1))
                 const int2 entry = make_int2(e, ((rec.w < 0 ? -rec.w : rec.w) - 1) | (c << 16));
-                if (d1) a.gadj[(size_t)b.x * NC + bit] = entry;
-                if (d2) a.gadj[(size_t)b.y * NC + bit] = entry;
+                if (d1) a.gadj[(size_t)bx * NC + bit] = entry;
+                if (d2) a.gadj[(size_t)by * NC + bit] = entry;
             }
         }
-        atomicAdd(&cn->color_count[c], 1);
+        if (!REGIONS) atomicAdd(&cn->color_count[c], 1);  // (k_solve's colour-major order)
+    };
+    auto settle = [&](const int4 rec, int round, int c, unsigned long long cl1, unsigned long long cl2) -> bool {  // (cl1, cl2: its claim cells)
+        const unsigned long long val = claim_val(rec.x, round);
+        if ((!(rec.y & UNC_STATIC) && cl1 != val) || (!(rec.z & UNC_STATIC) && cl2 != val)) return false;
+        finalize(rec, c);
         return true;
     };
     // Grid-wide rounds.  Round r reads the list L[r & 1] (n entries; `identity`: the first round takes every record); arbiters that
@@ -999,16 +1036,38 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
             const int* cur_list = lists[round & 1];
             int* next_list = lists[(round + 1) & 1];
             const bool ident = identity && round == round0;
-            for (int k = ct; k < n; k += cs) {
-                const int r = ident ? k : __ldcg(&cur_list[k]);
-                a.prop[r] = propose(__ldcg(&a.unc_rec[r]), round, false);
+            for (int k0 = ct; k0 < n; k0 += CB * cs) {
+                int r[CB];
+                int4 rec[CB];
+                Masks m[CB];
+#pragma unroll
+                for (int u = 0; u < CB; u++) r[u] = k0 + u * cs < n ? (ident ? k0 + u * cs : __ldcg(&cur_list[k0 + u * cs])) : -1;
+#pragma unroll
+                for (int u = 0; u < CB; u++) rec[u] = r[u] >= 0 ? __ldcg(&a.unc_rec[r[u]]) : no_rec;
+#pragma unroll
+                for (int u = 0; u < CB; u++) m[u] = load_masks(rec[u], false);
+#pragma unroll
+                for (int u = 0; u < CB; u++)
+                    if (r[u] >= 0) a.prop[r[u]] = propose(rec[u], m[u], round);
             }
             if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
-            for (int k = ct; k < n; k += cs) {
-                const int r = ident ? k : __ldcg(&cur_list[k]);
-                const int c = __ldcg(&a.prop[r]);
-                if (c < 0) continue;
-                if (!settle(__ldcg(&a.unc_rec[r]), round, c)) next_list[atomicAdd(&cn->remaining[round], 1)] = r;
+            for (int k0 = ct; k0 < n; k0 += CB * cs) {
+                int r[CB], c[CB];
+                int4 rec[CB];
+                unsigned long long cl1[CB], cl2[CB];
+#pragma unroll
+                for (int u = 0; u < CB; u++) r[u] = k0 + u * cs < n ? (ident ? k0 + u * cs : __ldcg(&cur_list[k0 + u * cs])) : -1;
+#pragma unroll
+                for (int u = 0; u < CB; u++) { rec[u] = r[u] >= 0 ? __ldcg(&a.unc_rec[r[u]]) : no_rec; c[u] = r[u] >= 0 ? __ldcg(&a.prop[r[u]]) : -1; }
+#pragma unroll
+                for (int u = 0; u < CB; u++) {
+                    const int cc = max(c[u], 0);
+                    cl1[u] = __ldcg(&a.claim[(size_t)(rec[u].y & ~UNC_STATIC) * NCX + cc]);
+                    cl2[u] = __ldcg(&a.claim[(size_t)(rec[u].z & ~UNC_STATIC) * NCX + cc]);
+                }
+#pragma unroll
+                for (int u = 0; u < CB; u++)
+                    if (c[u] >= 0 && !settle(rec[u], round, c[u], cl1[u], cl2[u])) next_list[atomicAdd(&cn->remaining[round], 1)] = r[u];
             }
             if (solo) { __threadfence(); __syncthreads(); } else grid_barrier(bar, bar_target);
             n = *(volatile int*)&cn->remaining[round];
@@ -1020,57 +1079,85 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
     };
     // Region solver, the usual step (a few thousand new arbiters): an interior arbiter only ever meets interior arbiters of its
     // own region at its dynamic bodies, so every CTA colours the new interior arbiters of its region by itself — the same
-    // propose / claim rounds, but with block barriers instead of grid barriers — while CTA 0 also takes the (few) cross-region ones
-    // along.  One grid barrier at the end.  An interior arbiter without a free interior colour is "promoted": it takes a generic
+    // propose / claim rounds, but with block barriers instead of grid barriers, on the records k_build dropped into the region's bin
+    // — while CTA 0 also takes the (few) cross-region ones along.  One grid barrier at the end.  An interior arbiter without a free interior colour is "promoted": it takes a generic
     // colour in grid-wide rounds behind that barrier (a body touching more than 32 others inside its region; rare).
-    const int ngen = REGIONS ? *(volatile int*)&cn->n_unc_generic : 0;
-    if (REGIONS && nunc <= LOCAL_UNC_MAX && ngen <= SOLO_GEN_MAX && (size_t)nunc * 32 <= (size_t)scratch_bytes) {
-        __shared__ int s_n, s_nn;
-        int4* l_rec = (int4*)scratch;          // my records
-        int* l_idx = (int*)(l_rec + nunc);     // their indices in unc_rec
-        int* l_cur = l_idx + nunc;             // the records still uncoloured (indices into l_rec), ping-pong
-        int* l_next = l_cur + nunc;
-        int* l_prop = l_next + nunc;
-        if (lt == 0) s_n = 0;
-        __syncthreads();
-        for (int k0 = lt; k0 < nunc; k0 += 8 * T) {  // (every CTA reads every record: eight independent loads in flight per thread)
-            int4 rec[8];
-#pragma unroll
-            for (int u = 0; u < 8; u++) rec[u] = k0 + u * T < nunc ? __ldcg(&a.unc_rec[k0 + u * T]) : make_int4(0, 0, 0, 0x7fffffff);
-#pragma unroll
-            for (int u = 0; u < 8; u++)
-                if (rec[u].w == bid + 1 || (bid == 0 && rec[u].w <= 0)) {
-                    const int q = atomicAdd(&s_n, 1);
-                    l_rec[q] = rec[u]; l_idx[q] = k0 + u * T; l_cur[q] = q;
-                }
-        }
-        __syncthreads();
-        int n = s_n, round = 0;
-        for (; n > 0 && round < PROMOTE_ROUND0; round++) {
-            if (lt == 0) s_nn = 0;
-            for (int k = lt; k < n; k += T) {
-                const int q = l_cur[k];
-                const int c = propose(l_rec[q], round, true);
-                l_prop[q] = c;
-                if (c == -2) lists[PROMOTE_ROUND0 & 1][atomicAdd(&cn->n_promoted, 1)] = l_idx[q];
+    // The claims of these rounds are cells of a hash table in shared memory, keyed by (body, colour): two keys that share a cell
+    // only cost the loser another round.  A claim value is unique inside the CTA (round | priority | list position).
+    if (REGIONS && a.color_local && *(volatile int*)&cn->bin_overflow == 0) {
+        __shared__ int s_nn;
+        const int n_int = bid < a.n_regions ? min(__ldcg(&cn->region_new[bid]), a.bin_cap) : 0;
+        const int n_gen = bid == 0 ? min(__ldcg(&cn->region_new[a.n_regions]), a.bin_cap) : 0;
+        const int n0 = n_int + n_gen;
+        const int HT = scratch_bytes >= 160 * 1024 ? 16384 : 8192;
+        unsigned* ht = (unsigned*)scratch;     // claim cells
+        int4* l_rec = (int4*)(ht + HT);        // my records
+        int* l_cur = (int*)(l_rec + n0);       // the records still uncoloured (indices into l_rec), ping-pong
+        int* l_next = l_cur + n0;
+        int* l_prop = l_next + n0;
+        int n = n0, round = 0;
+        if (n0 > 0) {
+            for (int k = lt; k < HT; k += T) ht[k] = 0xffffffffu;
+            for (int k = lt; k < n0; k += T) {
+                l_rec[k] = __ldcg(&a.unc_bin[(size_t)(k < n_int ? bid : a.n_regions) * a.bin_cap + (k < n_int ? k : k - n_int)]);
+                l_cur[k] = k;
             }
-            __threadfence();
+            __syncthreads();
+        }
+        cstamp();
+        auto cell = [&](int body, int c) -> unsigned* { return &ht[hash_u32((unsigned)body * 128u + (unsigned)c) & (unsigned)(HT - 1)]; };
+        auto local_val = [&](int e, int q, int rnd) -> unsigned {
+            return ((unsigned)(~rnd & 0x3f) << 26) | ((fmix32((unsigned)e * 2654435761u + (unsigned)rnd) & 0x1fffu) << 13) | (unsigned)q;
+        };
+        for (; n > 0 && round < 60; round++) {
+            if (lt == 0) s_nn = 0;
+            for (int k0 = lt; k0 < n; k0 += CB * T) {
+                int q[CB];
+                int4 rec[CB];
+                Masks m[CB];
+#pragma unroll
+                for (int u = 0; u < CB; u++) { q[u] = k0 + u * T < n ? l_cur[k0 + u * T] : -1; rec[u] = q[u] >= 0 ? l_rec[q[u]] : no_rec; }
+#pragma unroll
+                for (int u = 0; u < CB; u++) m[u] = load_masks(rec[u], true);
+#pragma unroll
+                for (int u = 0; u < CB; u++)
+                    if (q[u] >= 0) {
+                        const int c = pick(rec[u], m[u], true);
+                        l_prop[q[u]] = c;
+                        if (c >= 0) {
+                            const unsigned val = local_val(rec[u].x, q[u], round);
+                            if (!(rec[u].y & UNC_STATIC)) atomicMin(cell(rec[u].y, c), val);
+                            if (!(rec[u].z & UNC_STATIC)) atomicMin(cell(rec[u].z, c), val);
+                        } else if (c == -2) {
+                            lists[PROMOTE_ROUND0 & 1][atomicAdd(&cn->n_promoted, 1)] =
+                                __ldcg(&a.unc_bin_idx[(size_t)(q[u] < n_int ? bid : a.n_regions) * a.bin_cap + (q[u] < n_int ? q[u] : q[u] - n_int)]);
+                        }
+                    }
+            }
             __syncthreads();
             for (int k = lt; k < n; k += T) {
-                const int q = l_cur[k];
-                const int c = l_prop[q];
+                const int q = l_cur[k], c = l_prop[q];
                 if (c < 0) continue;
-                if (!settle(l_rec[q], round, c)) l_next[atomicAdd(&s_nn, 1)] = q;
+                const int4 rec = l_rec[q];
+                const unsigned val = local_val(rec.x, q, round);
+                const bool win = ((rec.y & UNC_STATIC) || *cell(rec.y, c) == val) && ((rec.z & UNC_STATIC) || *cell(rec.z, c) == val);
+                if (win) finalize(rec, c);
+                else l_next[atomicAdd(&s_nn, 1)] = q;
             }
-            __threadfence();
+            __threadfence();  // (the winners' bits in used / used_int: read by the losers in the next round)
             __syncthreads();
             n = s_nn;
             int* t = l_cur; l_cur = l_next; l_next = t;
             __syncthreads();
         }
-        if (n > 0) atomicExch(&cn->err, SYLT_ERR_INTERNAL);  // (never: a round always colours the arbiter with the smallest priority)
+        for (int k = lt; k < n; k += T) {  // (never in practice: 60 rounds were not enough — the rest joins the grid-wide rounds)
+            const int q = l_cur[k];
+            lists[PROMOTE_ROUND0 & 1][atomicAdd(&cn->n_promoted, 1)] = __ldcg(&a.unc_bin_idx[(size_t)(q < n_int ? bid : a.n_regions) * a.bin_cap + (q < n_int ? q : q - n_int)]);
+        }
+        cstamp();
         if (lt == 0 && round > 0) atomicMax(&cn->rounds, round);
         grid_barrier(bar, bar_target);
+        cstamp();
         const int np = *(volatile int*)&cn->n_promoted;
         if (np > 0) grid_rounds(np, PROMOTE_ROUND0, false);
         return true;
@@ -1491,12 +1578,12 @@ constexpr int CONE_CAP_1 = 2048;      // ghost arbiters a CTA may replay
 constexpr int HASH_CAP_1 = 4096;      // open-addressing tables of the cone walk (set-up scratch at the top of shared memory)
 constexpr int GB_MAX_1 = 2048;        // ghost bodies of a CTA
 constexpr int OWN_MAX_1 = 4096;       // arbiters a region may own
+constexpr int UNC_BIN_CAP_1 = 2048;   // new arbiters of one step a region CTA colours by itself (more: grid-wide rounds for that step)
 namespace {
 constexpr int MAX_PLANES = 16;        // export planes: pass t uses plane t % MAX_PLANES; a grid barrier every MAX_PLANES passes keeps
                                       // every CTA within one lap of the others, so a plane is never overwritten before it has been read
 constexpr int MAX_PASSES = 4096;      // passes (1 + iterations) the 12-bit pass field of an export tag can tell apart
 
-__device__ __forceinline__ unsigned hash_u32(unsigned x) { return fmix32(x * 2654435761u); }
 
 // PER_SM region CTAs share an SM (each with 1 / PER_SM of the threads, the shared memory and the table sizes): the passes are a chain
 // of short latency-bound colour hops, so two half-size regions per SM overlap each other's latencies.
@@ -2316,7 +2403,8 @@ struct SyltWorld {
     DBuf<int> jdeg;
     DBuf<int2> jrank;
     DBuf<int> uncolored, uncolored2, prop, order;
-    DBuf<int4> unc_rec;
+    DBuf<int4> unc_rec, unc_bin;
+    DBuf<int> unc_bin_idx;
     DBuf<Counters> counters;
     bool cells_clean = false;  // cell_count is all zero (the cell scan re-zeroes what it reads)
     // arbiters, double buffered
@@ -2633,6 +2721,8 @@ int flush(SyltWorld* w) {
     return SYLT_OK;
 }
 
+int unc_bin_cap(const SyltWorld* w) { return UNC_BIN_CAP_1 / std::max(w->regions_per_sm, 1); }
+
 // Region solver on / off for the current bodies, and its buffers.  The partition itself (k_resort + k_rebalance) is enqueued
 // with the next step; nothing here synchronises with the device beyond (re)allocation.
 int repartition(SyltWorld* w) {
@@ -2657,6 +2747,8 @@ int repartition(SyltWorld* w) {
     SYLT_CUDA(w->reg_start.ensure((size_t)G + 1));
     SYLT_CUDA(w->gadj.ensure(B * (size_t)GADJ));
     SYLT_CUDA(w->cone_buf.ensure((size_t)w->regions_blocks * (CONE_CAP_1 / w->regions_per_sm)));
+    SYLT_CUDA(w->unc_bin.ensure((size_t)(G + 1) * (size_t)unc_bin_cap(w)));
+    SYLT_CUDA(w->unc_bin_idx.ensure((size_t)(G + 1) * (size_t)unc_bin_cap(w)));
     {   // export planes: a record is valid when its tag matches (step_tag, pass); fresh memory must not hold a look-alike
         const size_t oldcap = w->xrec.cap;
         SYLT_CUDA(w->xrec.ensure((size_t)MAX_PLANES * 2 * B));
@@ -2759,11 +2851,13 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p, w->n_regions,
+                             w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w)));
     else
         SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p, w->n_regions,
+                             w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w)));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
     mark();
@@ -2797,6 +2891,9 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
             w->step_tag = 1;
         }
         a.step_tag = w->step_tag;
+        static const int color_local = getenv("SYLT_COLOR_LOCAL") ? atoi(getenv("SYLT_COLOR_LOCAL")) : 1;
+        a.color_local = color_local;
+        a.unc_bin = w->unc_bin.p; a.unc_bin_idx = w->unc_bin_idx.p; a.bin_cap = unc_bin_cap(w);
         a.probe_cta = getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->regions_blocks / 2;
         SYLT_CUDA(cudaLaunchCooperativeKernel(w->regions_per_sm == 2 ? (void*)k_solve_regions<2> : (void*)k_solve_regions<1>, dim3((unsigned)w->regions_blocks),
                                               dim3((unsigned)w->regions_threads), args, w->solve_budget, st));
@@ -2850,7 +2947,13 @@ void print_solver_timing(SyltWorld* w) {
         fprintf(stderr, "  pass 5, all CTAs [us] min/avg/max: interior %.2f/%.2f/%.2f  export+import %.2f/%.2f/%.2f  generic %.2f/%.2f/%.2f\n", mn[0], sm[0] / G, mx[0],
                 mn[1], sm[1] / G, mx[1], mn[2], sm[2] / G, mx[2]);
     }
-    fprintf(stderr, "new arbiters %d of %d, colouring rounds %d\n", w->last.n_uncolored, w->last.n_arb, w->last.rounds);
+    fprintf(stderr, "new arbiters %d (%d cross-region, %d promoted) of %d, colouring rounds %d\n", w->last.n_uncolored, w->last_regions ? w->last.region_new[w->n_regions] : 0, w->last.n_promoted, w->last.n_arb, w->last.rounds);
+    for (int base : {48, 56})
+        if (w->last_regions && t[(size_t)base]) {
+            fprintf(stderr, "  colouring of CTA %s [us since kernel start]:", base == 48 ? "0" : "probe");
+            for (int k = base; k < base + 8 && t[(size_t)k]; k++) fprintf(stderr, " %.1f", (double)(t[(size_t)k] - t[0]) * 1e-3);
+            fprintf(stderr, "\n");
+        }
     fprintf(stderr, "k_solve sections [us]: colour %.1f order %.1f residency %.1f pass0 %.1f iterations %.1f writeback %.1f integrate %.1f total %.1f\n",
             (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3,
             (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
