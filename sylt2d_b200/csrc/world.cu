@@ -114,6 +114,21 @@ cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t sme
     return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
 }
 
+// 32-byte records move as ONE request (sm_100: 256-bit global loads / stores; p must be 32-byte aligned)
+struct Rec32 { int4 a, b; };
+__device__ __forceinline__ Rec32 ld256(const void* p) {
+    Rec32 r;
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.a.x), "=r"(r.a.y), "=r"(r.a.z), "=r"(r.a.w), "=r"(r.b.x), "=r"(r.b.y), "=r"(r.b.z), "=r"(r.b.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void st256(void* p, const int4 a, const int4 b) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+__device__ __forceinline__ float4 as_f4(const int4 v) { return make_float4(__int_as_float(v.x), __int_as_float(v.y), __int_as_float(v.z), __int_as_float(v.w)); }
+__device__ __forceinline__ int4 as_i4(const float4 v) { return make_int4(__float_as_int(v.x), __float_as_int(v.y), __float_as_int(v.z), __float_as_int(v.w)); }
+
 // ------------------------------------------------------------------ block-level scans
 template <typename T>
 __device__ __forceinline__ T warp_incl_scan(T v) {
@@ -637,6 +652,7 @@ struct ArbSet {
     int* color;
     int* row_start;    // per body: first arbiter of its row (B+1 entries)
     float4 *ca, *cb, *cc, *cd;  // contacts: (nx,ny,r1x,r1y) (r2x,r2y,mass_n,mass_t) (bias,pn,pt,sep) (px,py,pnb,feat)
+    float4* cin;       // region solver: 2 per contact, what its set-up reads: (position, normal) (separation, pn, pt, -); k_build
 };
 
 __device__ __forceinline__ void pair_owner(int a, int b, int fa, int fb, int* owner, int* partner) {
@@ -647,13 +663,14 @@ __device__ __forceinline__ void pair_owner(int a, int b, int fa, int fb, int* ow
 }
 
 constexpr int UNC_STATIC = 0x40000000;  // body reference of an uncoloured-arbiter record: the body is static (takes no colour)
+constexpr int SR_STATIC = 0x40000000, SR_OWNER2 = 0x20000000, SR_BODY = 0x1fffffff;  // body references of a solver record (srec)
 template <int MAXC>
 __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int cap_arb, int cap_con, int B, int B_old, int have_old,
                                                const int2* pairs, const unsigned long long* info, unsigned long long* scan, const unsigned long long* pair_btot,
                                                const int* row_start, const float4* tmp_a, const float2* tmp_b, const float4* mp,
                                                const int* bflags, const int* bflags_old, ArbSet cur, ArbSet old, int warm,
                                                unsigned long long* used, int4* unc_rec, int fix_features, int keep_colors, unsigned* used_int, int regions,
-                                               const int* region_of, int2* gadj, int n_regions, int4* unc_bin, int* unc_bin_idx, int bin_cap) {
+                                               const int* rloc, int2* gadj, int n_regions, int4* unc_bin, int* unc_bin_idx, int bin_cap, int4* srec) {
     pdl_wait();
     const int failed = __ldcg(&cn->err);
     int P = min(__ldcg(&cn->n_pairs), cap_pairs);
@@ -709,15 +726,17 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         }
         float fr, pn = 0.0f, pt = 0.0f, pnb = 0.0f;
         int color = -1;
+        const bool s1 = (bflags[b1] & FLAG_STATIC) != 0, s2 = (bflags[b2] & FLAG_STATIC) != 0;
+        // region solver: (region << 16 | index inside the region) of the two bodies; pr.x owns the pair
+        const int rl1 = regions ? rloc[b1] : 0, rl2 = regions ? rloc[b2] : 0;
+        const int Rown = (pr.x == b1 ? rl1 : rl2) >> 16;
+        const bool interior_pair = (s1 || (rl1 >> 16) == Rown) && (s2 || (rl2 >> 16) == Rown);
         if (found >= 0) {
             fr = old.friction[found];  // quirk Q-17: friction fixed at first insertion
             if (keep_colors) color = old.color[found];  // (all dropped when the region solver is switched on or off: the ranges mean something else)
             if (keep_colors == 2 && color >= 0) {       // the regions were just re-cut: a colour survives if its class does — interior
                 // (all dynamic bodies in the owner's region, colour < GEN_BIT) or generic.  Only arbiters near the new borders change.
-                const int R = region_of[pr.x];          // pr.x owns the pair
-                const bool s1 = (bflags[b1] & FLAG_STATIC) != 0, s2 = (bflags[b2] & FLAG_STATIC) != 0;
-                const bool interior = (s1 || region_of[b1] == R) && (s2 || region_of[b2] == R);
-                if ((color < GEN_BIT) != interior) color = -1;
+                if ((color < GEN_BIT) != interior_pair) color = -1;
             }
             if (warm) {                // quirk Q-2: every new contact inherits old contact 0
                 int oc = old.meta[found].y;
@@ -732,6 +751,10 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         cur.partner[a] = pr.y;
         cur.friction[a] = fr;
         cur.color[a] = color;
+        if (regions) {  // everything the region solver's set-up needs to know about the arbiter, in one 32-byte record
+            st256(&srec[2 * (size_t)a], make_int4(b1 | (s1 ? SR_STATIC : 0) | (pr.x == b2 ? SR_OWNER2 : 0), b2 | (s2 ? SR_STATIC : 0), rl1, rl2),
+                  make_int4(n, coff, __float_as_int(fr), 0));
+        }
         for (int k = 0; k < n; k++) {
             float4 ta = tmp_a[(size_t)p * MAXC + k];
             float2 tb = tmp_b[(size_t)p * MAXC + k];
@@ -746,13 +769,18 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                     }
                 }
             }
-            cur.ca[coff + k] = make_float4(ta.z, ta.w, 0.0f, 0.0f);
-            cur.cb[coff + k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            cur.cc[coff + k] = make_float4(0.0f, pn, pt, tb.x);
+            if (regions != 2) {  // (regions == 2: a full step of the region solver reads `cin` and writes these three itself)
+                cur.ca[coff + k] = make_float4(ta.z, ta.w, 0.0f, 0.0f);
+                cur.cb[coff + k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                cur.cc[coff + k] = make_float4(0.0f, pn, pt, tb.x);
+            }
             cur.cd[coff + k] = make_float4(ta.x, ta.y, pnb, tb.y);
+            if (regions) {  // ... and about the contact: (position, normal | separation, pn, pt)
+                st256(&cur.cin[2 * (size_t)(coff + k)], as_i4(ta), as_i4(make_float4(tb.x, pn, pt, 0.0f)));
+            }
         }
         if (color >= 0) {
-            const bool d1 = !(bflags[b1] & FLAG_STATIC), d2 = !(bflags[b2] & FLAG_STATIC);
+            const bool d1 = !s1, d2 = !s2;
             if (regions && color < GEN_BIT) {
                 if (d1) atomicOr(&used_int[b1], 1u << color);
                 if (d2) atomicOr(&used_int[b2], 1u << color);
@@ -761,7 +789,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
                 if (d1) atomicOr(&used[b1], 1ull << bit);
                 if (d2) atomicOr(&used[b2], 1ull << bit);
                 if (regions) {  // the per-body table of generic arbiters the region solver's cone walk reads (slot = colour bit)
-                    const int2 entry = make_int2(a, region_of[pr.x] | (color << 16));
+                    const int2 entry = make_int2(a, Rown | (color << 16));
                     if (d1) gadj[(size_t)b1 * NC + bit] = entry;
                     if (d2) gadj[(size_t)b2 * NC + bit] = entry;
                 }
@@ -770,12 +798,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         } else {
             // everything the colouring rounds need to know about a new arbiter, in one 16-byte record: the rounds are chains of
             // dependent L2 round trips, and this takes two links (bodies -> flags -> regions) out of every one of them
-            const bool s1 = (bflags[b1] & FLAG_STATIC) != 0, s2 = (bflags[b2] & FLAG_STATIC) != 0;
-            int interior = 0;  // region solver: owner region + 1 (interior) or -(owner region + 1) (cross-region)
-            if (regions) {
-                const int R = region_of[pr.x];  // pr.x owns the pair
-                interior = ((s1 || region_of[b1] == R) && (s2 || region_of[b2] == R)) ? R + 1 : -(R + 1);
-            }
+            const int interior = !regions ? 0 : interior_pair ? Rown + 1 : -(Rown + 1);  // region solver: +-(owner region + 1), + = interior
             const int4 rec = make_int4(a, b1 | (s1 ? UNC_STATIC : 0), b2 | (s2 ? UNC_STATIC : 0), interior);
             const int ui = atomicAdd(&cn->n_uncolored, 1);
             unc_rec[ui] = rec;
@@ -844,6 +867,7 @@ struct SolveArgs {
     // regions (k_solve_regions): every body belongs to one region, region r is solved by CTA r
     const int *region_of, *lidx, *reg_start, *reg_bodies;  // body -> region, body -> index inside its region, CSR of the regions
     int n_regions, smem_bytes;                             // dynamic shared memory of k_solve_regions
+    const int4* srec;                                      // 2 per arbiter: (b1 | flags, b2 | flags, region << 16 | local index of b1, of b2) (contacts, first contact, friction, -)
     int2 *gadj, *cone_buf;                                 // per body: its generic arbiters (arbiter, owner region | colour << 16); per CTA: ghost arbiters (arbiter, colour)
     ulonglong2* xrec;                                      // export planes (one per pass) of versioned boundary-body velocities
     unsigned step_tag;
@@ -1601,9 +1625,12 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         if (a.dbg && tid == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[k] = t; }
     };
     stamp(0);
-    __shared__ int s_cnt[NCX], s_fill[NCX], s_cstart[NCX + 1], s_clist[NCX];
+    __shared__ int s_cnt[NCX], s_fill[NCX], s_cstart[NCX + 1], s_clist[NCX], s_ccnt[NCX], s_cfill[NCX];  // slots / contacts by colour
     __shared__ int s_ncl, s_nint, s_nbnd, s_L, s_ngh, s_ngb, s_nown, s_bad;
     __shared__ int s_scan[34];
+    __shared__ int2 s_hop[NCX];
+    __shared__ int s_wtot[3], s_wctot[3];
+    __shared__ unsigned s_wbal[3];
     // Shared memory, carved as the sizes become known: boundary lists [nb], bodies (32 bytes each: own, then ghosts), ghost
     // list, slot records (12 bytes), contacts (36 bytes, all that is left).  During set-up the top of the area holds the
     // scratch of the cone walk: hash tables, the ghost ids, the (arbiter, colour) list of the own arbiters.
@@ -1631,14 +1658,17 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     stamp(1);
     tstamp();
     if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // an arbiter without a free colour (every CTA sees it: the colouring ends with a barrier)
-    auto dynamic = [&](int b) { return !(a.bflags[b] & FLAG_STATIC); };
     tstamp();
     unsigned long long t_setup0 = 0;
     if (a.dbg && lt == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_setup0));
 
+    // The set-up below is bound by the number of scattered 32-byte sectors a CTA has to fetch (~2 ns each per SM), so everything
+    // it needs to know about an arbiter comes in one 32-byte record k_build wrote (`srec`: bodies with their static flags,
+    // (region, local index) of both bodies | contact count, first contact, friction) and about a contact in another
+    // (`cin`: position, normal | separation, pn, pt).
     // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) listed and counted by colour
     BodyIO io{a.vrec, a.sleep_ns, &cn->err};
-    if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; }
+    if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; s_ccnt[lt] = 0; }
     if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_nown = 0; s_bad = (const unsigned char*)(s_body + 2 * (size_t)nb) > scratch_lo ? 1 : 0; }
     for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
     __syncthreads();
@@ -1661,85 +1691,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         if (g < CONE_CAP) { ghosts[g] = make_int2(f, c); atomicAdd(&s_cnt[c], 1); }
         else s_bad = 1;
     };
-    // everything arbiter e (generic, colour c) depends on inside one generic phase: lower-coloured generic arbiters at its bodies
-    auto expand = [&](int e, int c) {
-        const int2 b = a.cur.bodies[e];
-#pragma unroll
-        for (int side = 0; side < 2; side++) {
-            const int z = side ? b.y : b.x;
-            if (!dynamic(z)) continue;
-            const unsigned long long uz = __ldcg(&a.used[z]);
-            unsigned long long m = uz & ((1ull << (c - GEN_BIT)) - 1ull);
-            while (m) {
-                const int k = __ffsll((long long)m) - 1;
-                m &= m - 1ull;
-                const int2 f = __ldcg(&a.gadj[(size_t)z * GADJ + k]);
-                if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + k);  // (an own arbiter is a root of the walk anyway)
-            }
-        }
-    };
-    for (int lb = lt; lb < nb && fits; lb += T) {  // bodies: state, boundary list, the arbiters of the body's row
-        const int b = a.reg_bodies[rb0 + lb];
-        Vel v;
-        float im, ii;
-        io.get(b, v, im, ii);
-        const float4 p = a.pose[b];
-        const unsigned long long ub = dynamic(b) ? __ldcg(&a.used[b]) : 0ull;
-        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
-        s_body[2 * lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
-        s_body[2 * lb + 1] = make_float4(p.x, p.y, im, ii);
-        if (ub != 0ull) {  // a boundary body: exported every pass
-            const int k = atomicAdd(&s_nbnd, 1);
-            s_bnd[k] = lb;
-            s_bndg[k] = b;
-        }
-        if (e1 > e0) {
-            const int k = atomicAdd(&s_nown, e1 - e0);
-            for (int e = e0; e < e1; e++)
-                if (k + e - e0 < OWN_MAX) t_own[k + e - e0] = make_int2(e, -1); else s_bad = 1;
-        }
-    }
-    __syncthreads();
-    const int nown = min(s_nown, OWN_MAX);
-    for (int k = lt; k < nown; k += T) {  // own arbiters: colour; the generic ones are the roots of the cone walk (level 0)
-        const int e = t_own[k].x;
-        const int c = __ldcg(&a.cur.color[e]);
-        t_own[k].y = c;
-        if (c < 0) continue;
-        atomicAdd(&s_cnt[c], 1);
-        if (c >= GEN_BIT) expand(e, c);
-    }
-    for (int k = lt; k < s_nbnd; k += T) {  // every generic arbiter at a boundary body is replayed here, whoever owns it
-        const int b = s_bndg[k];
-        for (unsigned long long m = __ldcg(&a.used[b]); m; m &= m - 1ull) {
-            const int kb = __ffsll((long long)m) - 1;
-            const int2 f = __ldcg(&a.gadj[(size_t)b * GADJ + kb]);
-            if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + kb);
-        }
-    }
-    __syncthreads();
-    tstamp();
-    // ---- 2c. cone walk: ghost arbiters found in one level are expanded in the next, until nothing new turns up
-    int levels = 0;
-    for (int f0 = 0;; levels++) {
-        const int f1 = min(s_ngh, CONE_CAP);
-        __syncthreads();
-        if (f1 == f0) break;
-        for (int g = f0 + lt; g < f1; g += T) { const int2 f = __ldcg(&ghosts[g]); expand(f.x, f.y); }
-        __syncthreads();
-        f0 = f1;
-    }
-    const int ngh = min(s_ngh, CONE_CAP);
-    tstamp();
-    // ---- 2d. ghost bodies: bodies of other regions that this CTA's slots touch (dynamic: re-imported every pass; static: once)
-    auto body_insert = [&](int z) {
+    // ghost bodies: bodies of other regions that this CTA's slots touch (dynamic: re-imported every pass; static: once)
+    auto body_insert = [&](int z, bool is_static) {
         unsigned h = hash_u32((unsigned)z ^ 0x9e3779b9u) & (HASH_CAP - 1);
         for (int probe = 0; probe < HASH_CAP; probe++) {
             const int old = atomicCAS(&h_body[h], 0, z + 1);
             if (old == 0) {
                 const int g = atomicAdd(&s_ngb, 1);
                 h_bval[h] = g;
-                if (g < GB_MAX) t_gb[g] = z | (dynamic(z) ? 0 : GHOST_FLAG); else s_bad = 1;
+                if (g < GB_MAX) t_gb[g] = z | (is_static ? GHOST_FLAG : 0); else s_bad = 1;
                 return;
             }
             if (old == z + 1) return;
@@ -1758,38 +1718,141 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         s_bad = 1;
         return 0;
     };
-    auto ghost_bodies_of = [&](int e) {
-        const int2 b = a.cur.bodies[e];
-        if (a.region_of[b.x] != R) body_insert(b.x);
-        if (a.region_of[b.y] != R) body_insert(b.y);
+    // One arbiter joins this CTA's slots (own: e is a row of one of its bodies; ghost: a replica): its contacts are counted for the
+    // layout, its bodies of other regions become ghost bodies, and — a generic arbiter of colour c — everything it depends on
+    // inside one generic phase, the lower-coloured generic arbiters at its dynamic bodies, joins too.
+    auto adopt = [&](int c, const int4 ra, int n) {
+        atomicAdd(&s_ccnt[c], n);
+        const int z1 = ra.x & SR_BODY, z2 = ra.y & SR_BODY;
+        const bool st1 = (ra.x & SR_STATIC) != 0, st2 = (ra.y & SR_STATIC) != 0;
+        if ((ra.z >> 16) != R) body_insert(z1, st1);
+        if ((ra.w >> 16) != R) body_insert(z2, st2);
+        if (c < GEN_BIT) return;
+        unsigned long long u1 = 0ull, u2 = 0ull;
+        if (!st1) u1 = __ldcg(&a.used[z1]);
+        if (!st2) u2 = __ldcg(&a.used[z2]);
+        const unsigned long long lower = (1ull << (c - GEN_BIT)) - 1ull;
+#pragma unroll
+        for (int side = 0; side < 2; side++) {
+            const int z = side ? z2 : z1;
+            for (unsigned long long m = (side ? u2 : u1) & lower; m; m &= m - 1ull) {
+                const int k = __ffsll((long long)m) - 1;
+                const int2 f = __ldcg(&a.gadj[(size_t)z * GADJ + k]);
+                if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + k);  // (an own arbiter is a root of the walk anyway)
+            }
+        }
     };
-    for (int k = lt; k < nown; k += T) if (t_own[k].y >= 0) ghost_bodies_of(t_own[k].x);
-    for (int g = lt; g < ngh; g += T) ghost_bodies_of(__ldcg(&ghosts[g]).x);
+    for (int lb = lt; lb < nb && fits; lb += T) {  // bodies: state, boundary list, the arbiters of the body's row
+        const int b = a.reg_bodies[rb0 + lb];
+        const Rec32 vr = ld256(a.vrec + 2 * (size_t)b);  // { vx | ver, vy | ver } { w | ver, inv_mass | inv_moi } (k_prepare)
+        Vel v;
+        v.v = mk(__int_as_float(vr.a.x), __int_as_float(vr.a.z)); v.w = __int_as_float(vr.b.x);
+        const float im = __int_as_float(vr.b.z), ii = __int_as_float(vr.b.w);
+        const float4 p = a.pose[b];
+        const unsigned long long ub = __ldcg(&a.used[b]);  // (never set at a static body)
+        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
+        s_body[2 * lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
+        s_body[2 * lb + 1] = make_float4(p.x, p.y, im, ii);
+        if (ub != 0ull) {  // a boundary body: exported every pass
+            const int k = atomicAdd(&s_nbnd, 1);
+            s_bnd[k] = lb;
+            s_bndg[k] = b;
+            for (unsigned long long m = ub; m; m &= m - 1ull) {  // every generic arbiter at a boundary body is replayed here, whoever owns it
+                const int kb = __ffsll((long long)m) - 1;
+                const int2 f = __ldcg(&a.gadj[(size_t)b * GADJ + kb]);
+                if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + kb);
+            }
+        }
+        if (e1 > e0) {
+            const int k = atomicAdd(&s_nown, e1 - e0);
+            for (int e = e0; e < e1; e++)
+                if (k + e - e0 < OWN_MAX) t_own[k + e - e0] = make_int2(e, -1); else s_bad = 1;
+        }
+    }
     __syncthreads();
+    const int nown = min(s_nown, OWN_MAX);
+    constexpr int SB = 4;  // arbiters a thread has in flight at once
+    for (int k0 = lt; k0 < nown; k0 += SB * T) {  // own arbiters: colour; the generic ones are the roots of the cone walk (level 0)
+        int e[SB], c[SB], n[SB];
+        int4 ra[SB];
+#pragma unroll
+        for (int u = 0; u < SB; u++) e[u] = k0 + u * T < nown ? t_own[k0 + u * T].x : -1;
+#pragma unroll
+        for (int u = 0; u < SB; u++)
+            if (e[u] >= 0) { c[u] = __ldcg(&a.cur.color[e[u]]); const Rec32 r = ld256(&a.srec[2 * (size_t)e[u]]); ra[u] = r.a; n[u] = r.b.x; }
+#pragma unroll
+        for (int u = 0; u < SB; u++) {
+            if (e[u] < 0) continue;
+            t_own[k0 + u * T].y = c[u];
+            if (c[u] < 0) continue;
+            atomicAdd(&s_cnt[c[u]], 1);
+            adopt(c[u], ra[u], n[u]);
+        }
+    }
+    __syncthreads();
+    tstamp();
+    // ---- 2c. cone walk: ghost arbiters found in one level are adopted in the next, until nothing new turns up
+    int levels = 0;
+    for (int f0 = 0;; levels++) {
+        const int f1 = min(s_ngh, CONE_CAP);
+        __syncthreads();
+        if (f1 == f0) break;
+        for (int g = f0 + lt; g < f1; g += T) {
+            const int2 f = __ldcg(&ghosts[g]);
+            const Rec32 r = ld256(&a.srec[2 * (size_t)f.x]);
+            adopt(f.y, r.a, r.b.x);
+        }
+        __syncthreads();
+        f0 = f1;
+    }
+    const int ngh = min(s_ngh, CONE_CAP);
+    tstamp();
     const int ngb_found = min(s_ngb, GB_MAX);
     tstamp();
-    // ---- 2e. slot layout: generic colours first (their contacts must be shared-memory resident), then the interior colours
+    // ---- 2e. slot layout: generic colours first (their contacts must be shared-memory resident), then the interior colours; the
+    //          contacts of a colour's slots are laid out colour by colour in the same order
     int* s_gb = (int*)(s_body + 2 * ((size_t)nb + ngb_found));  // ghost bodies: global index | GHOST_FLAG if static (never imported again)
-    if (lt == 0) {
-        int run = 0, ncl = 0, nint = 0, ngen = 0;
-        unsigned long long mask = 0ull;
-        unsigned mask_int = 0u;
-        for (int c = GEN_BIT; c < NCX; c++) { s_cstart[c] = run; run += s_cnt[c]; if (s_cnt[c]) { mask |= 1ull << (c - GEN_BIT); ngen += s_cnt[c]; } }
-        for (int c = 0; c < GEN_BIT; c++) { s_cstart[c] = run; run += s_cnt[c]; if (s_cnt[c]) { mask_int |= 1u << c; s_clist[ncl++] = c; nint++; } }
-        for (int c = GEN_BIT; c < NCX; c++) if (s_cnt[c]) s_clist[ncl++] = c;
-        s_cstart[NCX] = run;
-        s_ncl = ncl; s_nint = nint; s_L = run;
-        if (mask) atomicOr(&cn->color_mask, mask);
-        if (mask_int) atomicOr(&cn->color_mask_int, mask_int);
-        if (ngen) atomicAdd(&cn->n_generic, ngen - ngh);
-        if (ngh) atomicAdd(&cn->n_ghost, ngh);
-        atomicMax(&cn->max_slots, run);
-        // everything but the contacts must fit below the scratch; bodies are referenced through 15-bit indices
-        const bool room = (const unsigned char*)(s_gb + ngb_found + 4 * (size_t)run) <= scratch_lo && nb + ngb_found < 0x8000;
-        if (s_bad || !room) {
-            s_bad = 1;
-            atomicExch(&cn->err, SYLT_ERR_CAPACITY);
-            atomicOr(&cn->why, 1 | (!room ? 2 : 0) | (s_ngh > CONE_CAP ? 4 : 0) | (s_ngb > GB_MAX ? 8 : 0) | (!fits ? 16 : 0) | (s_nown > OWN_MAX ? 64 : 0));
+    {   // (96 colours: one thread each, three warps; layout order of the warps: generic 32-63, generic 64-95, interior 0-31)
+        static_assert(NCX == 96 && GEN_BIT == 32, "slot layout: three warps of colours");
+        const int wq = lt >> 5, lq = lt & 31;
+        int cntc = 0, ccn = 0, incl = 0, cincl = 0;
+        unsigned bal = 0u;
+        if (lt < NCX) {
+            cntc = s_cnt[lt]; ccn = s_ccnt[lt];
+            bal = __ballot_sync(0xffffffffu, cntc > 0);
+            incl = warp_incl_scan(cntc); cincl = warp_incl_scan(ccn);
+            if (lq == 31) { s_wtot[wq] = incl; s_wctot[wq] = cincl; }
+            if (lq == 0) s_wbal[wq] = bal;
+        }
+        __syncthreads();
+        if (lt < NCX) {
+            const int before = wq == 1 ? 0 : wq == 2 ? s_wtot[1] : s_wtot[1] + s_wtot[2];
+            const int cbefore = wq == 1 ? 0 : wq == 2 ? s_wctot[1] : s_wctot[1] + s_wctot[2];
+            s_cstart[lt] = before + incl - cntc;
+            s_cfill[lt] = cbefore + cincl - ccn;
+            if (cntc > 0) {  // the colour list: interior colours ascending, then the generic ones
+                const int below = __popc(bal & ((1u << lq) - 1u));
+                s_clist[wq == 0 ? below : __popc(s_wbal[0]) + (wq == 2 ? __popc(s_wbal[1]) : 0) + below] = lt;
+            }
+        }
+        if (lt == 0) {
+            const int run = s_wtot[0] + s_wtot[1] + s_wtot[2], ngen = s_wtot[1] + s_wtot[2];
+            const unsigned mask_int = s_wbal[0];
+            const unsigned long long mask = (unsigned long long)s_wbal[1] | ((unsigned long long)s_wbal[2] << 32);
+            s_cstart[NCX] = run;
+            s_nint = __popc(mask_int); s_ncl = __popc(mask_int) + __popcll(mask); s_L = run;
+            if (mask) atomicOr(&cn->color_mask, mask);
+            if (mask_int) atomicOr(&cn->color_mask_int, mask_int);
+            if (ngen) atomicAdd(&cn->n_generic, ngen - ngh);
+            if (ngh) atomicAdd(&cn->n_ghost, ngh);
+            atomicMax(&cn->max_slots, run);
+            // everything but the contacts must fit below the scratch; bodies are referenced through 15-bit indices
+            const bool room = (const unsigned char*)(s_gb + ngb_found + 4 * (size_t)run) <= scratch_lo && nb + ngb_found < 0x8000;
+            if (s_bad || !room) {
+                s_bad = 1;
+                atomicExch(&cn->err, SYLT_ERR_CAPACITY);
+                atomicOr(&cn->why, 1 | (!room ? 2 : 0) | (s_ngh > CONE_CAP ? 4 : 0) | (s_ngb > GB_MAX ? 8 : 0) | (!fits ? 16 : 0) | (s_nown > OWN_MAX ? 64 : 0));
+            }
         }
     }
     __syncthreads();
@@ -1811,81 +1874,97 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     for (int g = lt; g < ngb && !bad; g += T) {  // ghosts: positions, inverse masses (and, for static ones, the velocity) once; dynamic velocities arrive every pass
         const int zf = t_gb[g], z = zf & ~GHOST_FLAG;
         s_gb[g] = zf;
-        Vel v;
-        float im, ii;
-        io.get(z, v, im, ii);
+        const Rec32 vr = ld256(a.vrec + 2 * (size_t)z);
         const float4 p = a.pose[z];
-        s_body[2 * (nb + g)] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
-        s_body[2 * (nb + g) + 1] = make_float4(p.x, p.y, im, ii);
+        s_body[2 * (nb + g)] = make_float4(__int_as_float(vr.a.x), __int_as_float(vr.a.z), __int_as_float(vr.b.x), 0.0f);
+        s_body[2 * (nb + g) + 1] = make_float4(p.x, p.y, __int_as_float(vr.b.z), __int_as_float(vr.b.w));
     }
     const bool acc = a.accumulate != 0;
     const float kbias = a.poscorr ? 0.2f : 0.0f;
 
     stamp(2);
     tstamp();
-    // ---- 3. slots: position by colour, record (the bodies' shared-memory indices come from the hash table), then the contacts
-    //         (which overwrite the scratch)
+    // ---- 3. slots: position by colour, record (a ghost body's shared-memory index comes from the hash table) and contacts.  Every
+    //         record and contact is read into registers (PB slots per thread) before the first contact is stored: the contacts
+    //         overwrite the set-up scratch (hash tables, lists).
     constexpr int SREF_STATIC = 0x8000;
-    auto body_ref = [&](int z) -> int {
-        return (a.region_of[z] == R ? a.lidx[z] : nb + body_lookup(z)) | (dynamic(z) ? 0 : SREF_STATIC);
-    };
-    auto place = [&](int e, int c, int flag) {
+    const int n_generic_slots = s_cstart[0];  // generic colours come first in the layout
+    auto place = [&](int c, int flag, const int4 ra, const int4 rb) {
         const int ls = s_cstart[c] + atomicAdd(&s_fill[c], 1);
         if (ls >= s_cstart[c] + s_cnt[c]) { atomicExch(&cn->err, SYLT_ERR_INTERNAL); atomicOr(&cn->why, 128); return; }  // (never: counted and placed from the same lists)
-        const int2 b = a.cur.bodies[e];
-        const int2 mt = a.cur.meta[e];
-        s_sb[ls] = body_ref(b.x) | (body_ref(b.y) << 16);
-        s_sc[ls] = mt.x;
-        s_so[ls] = mt.y | flag;  // contact offsets stay below 2^30
-        s_sf[ls] = a.cur.friction[e];
+        const int lc = atomicAdd(&s_cfill[c], rb.x);
+        const bool res = lc + rb.x <= CONCAP;
+        const int ref1 = ((ra.z >> 16) == R ? (ra.z & 0xffff) : nb + body_lookup(ra.x & SR_BODY)) | ((ra.x & SR_STATIC) ? SREF_STATIC : 0);
+        const int ref2 = ((ra.w >> 16) == R ? (ra.w & 0xffff) : nb + body_lookup(ra.y & SR_BODY)) | ((ra.y & SR_STATIC) ? SREF_STATIC : 0);
+        s_sb[ls] = ref1 | (ref2 << 16);
+        s_sc[ls] = res ? (lc << 8) | rb.x : -1 - rb.x;
+        s_so[ls] = rb.y | flag;  // contact offsets stay below 2^30
+        s_sf[ls] = __int_as_float(rb.z);
+        if (!res) {  // contacts stay in the global arrays
+            atomicAdd(&cn->n_nonres, 1);
+            if (ls < n_generic_slots) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); atomicOr(&cn->why, 32); }  // a replica has no global working storage
+        }
     };
-    if (!bad) {
-        for (int k = lt; k < nown; k += T) { const int2 ec = t_own[k]; if (ec.y >= 0) place(ec.x, ec.y, 0); }
-        for (int g = lt; g < ngh; g += T) { const int2 f = __ldcg(&ghosts[g]); place(f.x, f.y, GHOST_FLAG); }
+    const int nall = bad ? 0 : nown + ngh;
+    for (int k0 = lt; k0 < nall; k0 += SB * T) {
+        int e[SB], c[SB];
+        int4 ra[SB], rb[SB];
+#pragma unroll
+        for (int u = 0; u < SB; u++) {
+            const int k = k0 + u * T;
+            e[u] = -1; c[u] = 0;
+            if (k < nown) { const int2 ec = t_own[k]; if (ec.y >= 0) { e[u] = ec.x; c[u] = ec.y; } }
+            else if (k < nall) { const int2 f = __ldcg(&ghosts[k - nown]); e[u] = f.x; c[u] = f.y; }
+        }
+#pragma unroll
+        for (int u = 0; u < SB; u++)
+            if (e[u] >= 0) { const Rec32 r = ld256(&a.srec[2 * (size_t)e[u]]); ra[u] = r.a; rb[u] = r.b; }
+#pragma unroll
+        for (int u = 0; u < SB; u++)
+            if (e[u] >= 0) place(c[u], k0 + u * T < nown ? 0 : GHOST_FLAG, ra[u], rb[u]);
     }
     __syncthreads();  // the scratch is dead from here on
     tstamp();
-    {   // in-place exclusive scan of the contact counts: count -> offset << 8 | count
-        const int chunk = (L + T - 1) / T, q0 = min(lt * chunk, L), q1 = min(q0 + chunk, L);
-        int sum = 0;
-        for (int k = q0; k < q1; k++) sum += s_sc[k];
-        int tot;
-        int ex = block_excl_scan<int>(sum, &tot, s_scan);
-        for (int k = q0; k < q1; k++) { const int t = s_sc[k]; s_sc[k] = (ex << 8) | t; ex += t; }
-    }
-    __syncthreads();
     tstamp();
-    const int n_generic_slots = s_cstart[0];  // generic colours come first in the layout
-    for (int ls = lt; ls < L; ls += T) {
-        const int sc = s_sc[ls], lc = sc >> 8, n = sc & 0xff, coff = s_so[ls] & ~GHOST_FLAG;
-        const bool res = lc + n <= CONCAP;
-        float4 ca[2], cc[2], cd[2];
-        if (res && n <= 2) {  // the usual case (box contacts): all loads in flight at once
+    for (int ls0 = lt; ls0 < L; ls0 += 2 * T) {  // contacts: two slots (up to four contacts) in flight per thread
+        int sc[2], co[2];
+        float4 ci[2][2][2];
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            const int ls = ls0 + v * T;
+            sc[v] = ls < L ? s_sc[ls] : -1;
+            co[v] = ls < L ? (s_so[ls] & ~GHOST_FLAG) : 0;
+        }
+#pragma unroll
+        for (int v = 0; v < 2; v++)
 #pragma unroll
             for (int q = 0; q < 2; q++)
-                if (q < n) { ca[q] = a.cur.ca[coff + q]; cc[q] = a.cur.cc[coff + q]; cd[q] = a.cur.cd[coff + q]; }
-        }
-        if (!res) {
-            s_sc[ls] = -1 - n;  // contacts stay in the global arrays
-            atomicAdd(&cn->n_nonres, 1);
-            if (ls < n_generic_slots) { atomicExch(&cn->err, SYLT_ERR_CAPACITY); atomicOr(&cn->why, 32); }  // a replica has no global working storage
-        } else if (n <= 2) {
+                if (sc[v] >= 0 && q < (sc[v] & 0xff)) {
+                    const Rec32 r = ld256(&a.cur.cin[2 * (size_t)(co[v] + q)]);
+                    ci[v][q][0] = as_f4(r.a);
+                    ci[v][q][1] = as_f4(r.b);
+                }
+#pragma unroll
+        for (int v = 0; v < 2; v++) {
+            if (sc[v] < 0) continue;
+            const int lc = sc[v] >> 8, n = sc[v] & 0xff;
 #pragma unroll
             for (int q = 0; q < 2; q++)
                 if (q < n) {
-                    s_c0[lc + q] = make_float4(cd[q].x, cd[q].y, ca[q].x, ca[q].y);
-                    s_c1[lc + q] = make_float4(0.0f, 0.0f, cc[q].w, cc[q].y);
-                    s_c2[lc + q] = cc[q].z;
+                    s_c0[lc + q] = ci[v][q][0];
+                    s_c1[lc + q] = make_float4(0.0f, 0.0f, ci[v][q][1].x, ci[v][q][1].y);
+                    s_c2[lc + q] = ci[v][q][1].z;
                 }
-        } else {
-            for (int q = 0; q < n; q++) {
-                const float4 xa = a.cur.ca[coff + q], xc = a.cur.cc[coff + q], xd = a.cur.cd[coff + q];
-                s_c0[lc + q] = make_float4(xd.x, xd.y, xa.x, xa.y);
-                s_c1[lc + q] = make_float4(0.0f, 0.0f, xc.w, xc.y);
-                s_c2[lc + q] = xc.z;
+            for (int q = 2; q < n; q++) {  // (polygon manifolds)
+                const float4 x0 = a.cur.cin[2 * (size_t)(co[v] + q)], x1 = a.cur.cin[2 * (size_t)(co[v] + q) + 1];
+                s_c0[lc + q] = x0;
+                s_c1[lc + q] = make_float4(0.0f, 0.0f, x1.x, x1.y);
+                s_c2[lc + q] = x1.z;
             }
         }
     }
+    tstamp();
+    if (lt < ncl) { const int c = s_clist[lt]; s_hop[lt] = make_int2(s_cstart[c], s_cnt[c]); }  // (visible behind the barrier in front of the passes)
     if (a.dbg && lt == 0) {  // diagnostics: the CTA's load
         int mxc = 0;
         for (int k = 0; k < ncl; k++) mxc = max(mxc, s_cnt[s_clist[k]]);
@@ -1905,6 +1984,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
 
     // One slot of one colour hop.  Bodies and (normally) contacts are in shared memory; r1, r2 are recomputed from the
     // contact position exactly as Arbiter::pre_step / apply_impulse do (arbiter.rs:192-193, 236-237).
+    bool hop_probe = false;
+    int hop_k = 0;
+#define HOPCLK(k, dep) do { if (hop_probe) { unsigned long long t_; float d_ = (dep); asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "f"(d_) : "memory"); a.dbg[64 + 8 * 1024 + hop_k * 8 + (k)] = t_; } } while (0)
     auto solve_slot = [&](int ls, unsigned pass) {
         const int sb = s_sb[ls], sc = s_sc[ls];
         const float fr = s_sf[ls];
@@ -1915,7 +1997,31 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         v1.v = mk(q1.x, q1.y); v1.w = q1.z; v2.v = mk(q2.x, q2.y); v2.w = q2.z;
         const V2 p1 = mk(m1.x, m1.y), p2 = mk(m2.x, m2.y);
         const float im1 = m1.z, ii1 = m1.w, im2 = m2.z, ii2 = m2.w;
-        if (sc >= 0) {
+        if (sc >= 0 && pass != 0u && (sc & 0xff) <= 2) {
+            // the usual slot of an iteration (box contacts: one or two, resident): everything is loaded before the dependent chain starts
+            const int lc = sc >> 8, n = sc & 0xff, l2 = lc + max(n, 1) - 1;
+            const float4 c0a = s_c0[lc], c1a = s_c1[lc], c0b = s_c0[l2], c1b = s_c1[l2];
+            const float pta = s_c2[lc], ptb = s_c2[l2];
+            HOPCLK(1, c0b.x + c1b.x + ptb + q1.x + q2.x + m1.x + m2.x);
+            if (n >= 1) {
+                ContactConst k0;
+                k0.n = mk(c0a.z, c0a.w); k0.r1 = mk(c0a.x, c0a.y) - p1; k0.r2 = mk(c0a.x, c0a.y) - p2;
+                k0.mass_n = c1a.x; k0.mass_t = c1a.y; k0.bias = c1a.z;
+                float pn = c1a.w, pt = pta;
+                contact_apply(k0, fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
+                if (acc) { s_c1[lc].w = pn; s_c2[lc] = pt; }
+            }
+            HOPCLK(2, v1.v.x + v2.v.x + v1.w + v2.w);
+            if (n == 2) {
+                ContactConst k0;
+                k0.n = mk(c0b.z, c0b.w); k0.r1 = mk(c0b.x, c0b.y) - p1; k0.r2 = mk(c0b.x, c0b.y) - p2;
+                k0.mass_n = c1b.x; k0.mass_t = c1b.y; k0.bias = c1b.z;
+                float pn = c1b.w, pt = ptb;
+                contact_apply(k0, fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
+                if (acc) { s_c1[l2].w = pn; s_c2[l2] = pt; }
+            }
+            HOPCLK(3, v1.v.x + v2.v.x + v1.w + v2.w);
+        } else if (sc >= 0) {
             const int lc = sc >> 8, n = sc & 0xff;
             for (int q = 0; q < n; q++) {
                 const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
@@ -1936,15 +2042,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
             // storage (a replica in that situation has failed the step, SYLT_ERR_CAPACITY, and is skipped: it must not touch them)
             const int2 mt = make_int2(-1 - sc, s_so[ls]);
             for (int q = 0; q < mt.x; q++) {
-                const float4 ca = a.cur.ca[mt.y + q], cc = a.cur.cc[mt.y + q];
                 ContactConst k0;
                 if (pass == 0u) {
-                    const float4 cd = a.cur.cd[mt.y + q];
-                    contact_prestep(mk(cd.x, cd.y), mk(ca.x, ca.y), cc.w, p1, p2, im1, ii1, im2, ii2, a.inv_dt, kbias, acc, cc.y, cc.z, v1, v2, k0);
-                    a.cur.ca[mt.y + q] = make_float4(ca.x, ca.y, k0.r1.x, k0.r1.y);
+                    const float4 x0 = a.cur.cin[2 * (size_t)(mt.y + q)], x1 = a.cur.cin[2 * (size_t)(mt.y + q) + 1];  // (position, normal) (separation, pn, pt, -)
+                    contact_prestep(mk(x0.x, x0.y), mk(x0.z, x0.w), x1.x, p1, p2, im1, ii1, im2, ii2, a.inv_dt, kbias, acc, x1.y, x1.z, v1, v2, k0);
+                    a.cur.ca[mt.y + q] = make_float4(x0.z, x0.w, k0.r1.x, k0.r1.y);
                     a.cur.cb[mt.y + q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
-                    a.cur.cc[mt.y + q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
+                    a.cur.cc[mt.y + q] = make_float4(k0.bias, x1.y, x1.z, x1.x);
                 } else {
+                    const float4 ca = a.cur.ca[mt.y + q], cc = a.cur.cc[mt.y + q];
                     const float4 cb = a.cur.cb[mt.y + q];
                     k0.n = mk(ca.x, ca.y); k0.r1 = mk(ca.z, ca.w); k0.r2 = mk(cb.x, cb.y);
                     k0.mass_n = cb.z; k0.mass_t = cb.w; k0.bias = cc.x;
@@ -1963,9 +2069,16 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     };
     auto colours = [&](unsigned pass, int k0, int k1) {  // colour hops k0..k1 of the list
         for (int k = k0; k < k1; k++) {
-            const int c = s_clist[k], cnt = s_cnt[c], base = s_cstart[c];
-            for (int i = lt; i < cnt; i += T) solve_slot(base + i, pass);
+            const int2 h = s_hop[k];  // (first slot, slots) of the hop's colour
+            hop_probe = a.dbg && bid == a.probe_cta && lt == 0 && pass == 5u && k < 8;
+            hop_k = k;
+            HOPCLK(0, 0.0f);
+            for (int i = lt; i < h.y; i += T) solve_slot(h.x + i, pass);
+            HOPCLK(4, 0.0f);
             __syncthreads();
+            HOPCLK(5, 0.0f);
+            if (hop_probe) a.dbg[64 + 8 * 1024 + k * 8 + 6] = (unsigned long long)h.y;
+            hop_probe = false;
         }
     };
     // One pass: interior colours; boundary bodies out (plane `pass` of the export records); ghosts in; generic colours.
@@ -2027,7 +2140,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
             const V2 r1 = mk(c0.x, c0.y) - mk(m1.x, m1.y), r2 = mk(c0.x, c0.y) - mk(m2.x, m2.y);
             a.cur.ca[coff + q] = make_float4(c0.z, c0.w, r1.x, r1.y);
             a.cur.cb[coff + q] = make_float4(r2.x, r2.y, c1.x, c1.y);
-            a.cur.cc[coff + q] = make_float4(c1.z, c1.w, s_c2[lc + q], a.cur.cc[coff + q].w);
+            a.cur.cc[coff + q] = make_float4(c1.z, c1.w, s_c2[lc + q], 0.0f);  // (the separation stays in cin: k_fill_sep, on demand)
         }
     }
 
@@ -2302,11 +2415,17 @@ __global__ void __launch_bounds__(RECUT_THREADS, 1) k_recut(int B, int G, const 
     __syncthreads();
     if (blockIdx.x == 0)
         for (int g = lt; g <= G; g += T) reg_start[g] = s_cells[g];
-    for (int i = q0; i < q1; i++) { const int b = __ldcg(&perm[i]); lidx[b] = i - s_cells[region_of[b]]; }
+    for (int i = q0; i < q1; i++) { const int b = __ldcg(&perm[i]); const int reg = region_of[b]; lidx[b] = (reg << 16) | (i - s_cells[reg]); }  // (region, index inside it: < 2^15)
     stamp();
 }
 
 // the flags a step used become the "old" flags of the next one — unless the step failed (it will be repeated)
+// separations of a set the region solver wrote back (it does not carry them through the solve): cin -> cc.w, when somebody asks
+__global__ void k_fill_sep(int n, const float4* cin, float4* cc) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) cc[i].w = cin[2 * (size_t)i + 1].x;
+}
+
 __global__ void k_copy_flags(int B, const int* src, int* dst, const Counters* cn) {
     if (step_failed(cn)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2403,7 +2522,7 @@ struct SyltWorld {
     DBuf<int> jdeg;
     DBuf<int2> jrank;
     DBuf<int> uncolored, uncolored2, prop, order;
-    DBuf<int4> unc_rec, unc_bin;
+    DBuf<int4> unc_rec, unc_bin, srec;   // srec: 2 per arbiter, cin: 2 per contact (region solver set-up records, k_build)
     DBuf<int> unc_bin_idx;
     DBuf<Counters> counters;
     bool cells_clean = false;  // cell_count is all zero (the cell scan re-zeroes what it reads)
@@ -2412,7 +2531,8 @@ struct SyltWorld {
         DBuf<int2> bodies, meta;
         DBuf<int> partner, color, row_start;
         DBuf<float> friction;
-        DBuf<float4> ca, cb, cc, cd;
+        DBuf<float4> ca, cb, cc, cd, cin;
+        bool sep_in_cin = false;  // the set was solved by the region solver: cc.w (separation) is filled in from cin on demand
     } arb[2];
     int cur = 0;             // index being built next
     bool have_old = false;   // an arbiter set from a previous step/broad phase exists
@@ -2468,7 +2588,7 @@ struct SyltWorld {
         ArbSet s;
         ArbBufs& b = arb[k];
         s.bodies = b.bodies.p; s.meta = b.meta.p; s.partner = b.partner.p; s.friction = b.friction.p; s.color = b.color.p;
-        s.row_start = b.row_start.p; s.ca = b.ca.p; s.cb = b.cb.p; s.cc = b.cc.p; s.cd = b.cd.p;
+        s.row_start = b.row_start.p; s.ca = b.ca.p; s.cb = b.cb.p; s.cc = b.cc.p; s.cd = b.cd.p; s.cin = b.cin.p;
         return s;
     }
 };
@@ -2656,6 +2776,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->uncolored2.ensure((size_t)ca));
         SYLT_CUDA(w->prop.ensure((size_t)ca));
         SYLT_CUDA(w->order.ensure((size_t)ca));
+        SYLT_CUDA(w->srec.ensure(2 * (size_t)ca));
         for (int k = 0; k < 2; k++) {
             SyltWorld::ArbBufs& a = w->arb[k];
             const bool keep_set = (k != w->cur) && w->have_old && w->have_last;  // last step's arbiters survive a regrow
@@ -2670,6 +2791,7 @@ int flush(SyltWorld* w) {
             SYLT_CUDA(a.cb.ensure((size_t)cc, kc, w->stream));
             SYLT_CUDA(a.cc.ensure((size_t)cc, kc, w->stream));
             SYLT_CUDA(a.cd.ensure((size_t)cc, kc, w->stream));
+            SYLT_CUDA(a.cin.ensure(2 * (size_t)cc, 2 * kc, w->stream));
         }
         w->cap_pairs = (int64_t)std::min<size_t>(w->pairs.cap, (size_t)cp);
         w->cap_arb = ca;
@@ -2851,13 +2973,13 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (w->any_poly)
         SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p, w->n_regions,
-                             w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w)));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? (full_step ? 2 : 1) : 0, w->lidx.p, w->gadj.p, w->n_regions,
+                             w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w), w->srec.p));
     else
         SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? 1 : 0, w->region_of.p, w->gadj.p, w->n_regions,
-                             w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w)));
+                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? (full_step ? 2 : 1) : 0, w->lidx.p, w->gadj.p, w->n_regions,
+                             w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w), w->srec.p));
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
     mark();
@@ -2885,7 +3007,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (w->regions_on) {
         a.region_of = w->region_of.p; a.lidx = w->lidx.p; a.reg_start = w->reg_start.p; a.reg_bodies = w->reg_bodies.p;
         a.n_regions = w->n_regions; a.smem_bytes = (int)w->solve_budget;
-        a.gadj = w->gadj.p; a.cone_buf = w->cone_buf.p; a.xrec = w->xrec.p;
+        a.gadj = w->gadj.p; a.cone_buf = w->cone_buf.p; a.xrec = w->xrec.p; a.srec = w->srec.p;
         if (++w->step_tag > 0xffff0u) {  // 20-bit step tags (+ 12 bits of pass): start over with clean planes
             SYLT_CUDA(cudaMemsetAsync(w->xrec.p, 0, w->xrec.cap * sizeof(ulonglong2), st));
             w->step_tag = 1;
@@ -2897,10 +3019,12 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         a.probe_cta = getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->regions_blocks / 2;
         SYLT_CUDA(cudaLaunchCooperativeKernel(w->regions_per_sm == 2 ? (void*)k_solve_regions<2> : (void*)k_solve_regions<1>, dim3((unsigned)w->regions_blocks),
                                               dim3((unsigned)w->regions_threads), args, w->solve_budget, st));
+        w->arb[w->cur].sep_in_cin = full_step;
         w->steps_since_part++;
         w->last_regions = true;
     } else {
         w->last_regions = false;
+        w->arb[w->cur].sep_in_cin = false;
         SYLT_CUDA(cudaLaunchCooperativeKernel((void*)k_solve, dim3((unsigned)w->coop_blocks), dim3((unsigned)w->solve_threads), args, w->solve_smem, st));
     }
     w->launches++;
@@ -2919,7 +3043,7 @@ void print_solver_timing(SyltWorld* w) {
                 w->last.err, w->last.why, w->last.max_slots, w->last.n_ghost, w->last.n_uncolored, w->last.n_pairs, (long long)w->cap_pairs, w->last.n_arb,
                 (long long)w->cap_arb, w->last.n_con, (long long)w->cap_con, w->last.rounds);
     const int G = w->last_regions ? w->regions_blocks : w->coop_blocks;
-    std::vector<unsigned long long> t(64 + 8 * 1024);
+    std::vector<unsigned long long> t(64 + 8 * 1024 + 64);
     if (cudaMemcpy(t.data(), w->dbg.p, t.size() * sizeof(unsigned long long), cudaMemcpyDeviceToHost) != cudaSuccess) return;
     if (w->last_regions && t[32]) {
         fprintf(stderr, "  set-up of CTA %d [us]: generic table + barrier | bodies, rows, cone roots | cone walk | ghost bodies | layout, ghost data | slot records | scan | contacts:", getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->regions_blocks / 2);
@@ -2954,6 +3078,12 @@ void print_solver_timing(SyltWorld* w) {
             for (int k = base; k < base + 8 && t[(size_t)k]; k++) fprintf(stderr, " %.1f", (double)(t[(size_t)k] - t[0]) * 1e-3);
             fprintf(stderr, "\n");
         }
+    for (int k = 0; k < 8; k++) {
+        const unsigned long long* h = &t[(size_t)(64 + 8 * 1024 + k * 8)];
+        if (w->last_regions && h[5])
+            fprintf(stderr, "  hop %d of pass 5, probe CTA, thread 0 [cycles]: loads %lld, contact a %lld, contact b %lld, stores %lld, barrier %lld (%llu slots in the colour)\n", k,
+                    (long long)(h[1] - h[0]), (long long)(h[2] - h[1]), (long long)(h[3] - h[2]), (long long)(h[4] - h[3]), (long long)(h[5] - h[4]), h[6]);
+    }
     fprintf(stderr, "k_solve sections [us]: colour %.1f order %.1f residency %.1f pass0 %.1f iterations %.1f writeback %.1f integrate %.1f total %.1f\n",
             (t[1] - t[0]) * 1e-3, (t[2] - t[1]) * 1e-3, (t[3] - t[2]) * 1e-3, (t[4] - t[3]) * 1e-3, (t[5] - t[4]) * 1e-3, (t[6] - t[5]) * 1e-3,
             (t[7] - t[6]) * 1e-3, (t[7] - t[0]) * 1e-3);
@@ -3148,8 +3278,8 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
     if (const char* ev = getenv("SYLT_SOLVER_SLEEP_NS")) w->sleep_ns = std::max(0, atoi(ev));
     if (const char* ev = getenv("SYLT_SOLVER_SLACK")) w->slack_pct = std::max(0, atoi(ev));
     if (const char* ev = getenv("SYLT_SOLVER_TIMING")) w->timing = atoi(ev) != 0;
-    SYLT_CUDA(w->dbg.ensure(64 + 8 * 1024));
-    SYLT_CUDA(cudaMemset(w->dbg.p, 0, (64 + 8 * 1024) * sizeof(unsigned long long)));
+    SYLT_CUDA(w->dbg.ensure(64 + 8 * 1024 + 64));
+    SYLT_CUDA(cudaMemset(w->dbg.p, 0, (64 + 8 * 1024 + 64) * sizeof(unsigned long long)));
     if (const char* ev = getenv("SYLT_SOLVER_SMEM_SLOTS")) w->smem_slots = std::max(0, atoi(ev));  // tests: force the global-memory path
     size_t fixed = (size_t)w->smem_slots * 32 + (((size_t)w->smem_slots + 3) & ~(size_t)3) * 4;
     if (fixed + 48 > budget) { w->smem_slots = 0; fixed = 0; }
@@ -3199,7 +3329,7 @@ static void free_all(SyltWorld* w) {
     for (int k = 0; k < 2; k++) {
         auto& a = w->arb[k];
         a.bodies.release(); a.meta.release(); a.partner.release(); a.color.release(); a.row_start.release(); a.friction.release();
-        a.ca.release(); a.cb.release(); a.cc.release(); a.cd.release();
+        a.ca.release(); a.cb.release(); a.cc.release(); a.cd.release(); a.cin.release();
     }
     w->jbodies.release(); w->jla.release(); w->jr.release(); w->jm.release(); w->jparam.release(); w->jp.release(); w->jbias.release();
     w->jorder.release(); w->jcolor_start.release();
@@ -3498,6 +3628,10 @@ int sylt_world_get_arbiters(SyltWorld* w, SyltArbiterInfo* arbiters, int32_t arb
     if (A == 0) return 0;
     if (cudaSetDevice(w->device) != cudaSuccess) return -SYLT_ERR_CUDA;
     SyltWorld::ArbBufs& ab = w->arb[w->cur ^ 1];  // last completed step
+    if (ab.sep_in_cin && Cn > 0) {
+        k_fill_sep<<<(Cn + 255) / 256, 256, 0, w->stream>>>(Cn, ab.cin.p, ab.cc.p);
+        ab.sep_in_cin = false;
+    }
     std::vector<int2> bodies((size_t)A), meta((size_t)A);
     std::vector<float> fr((size_t)A);
     std::vector<int> col((size_t)A);
