@@ -971,14 +971,16 @@ struct BodyIO {
 // records in L2).  The class of an arbiter IS its colour range, so it persists with the colour.
 constexpr int PROMOTE_ROUND0 = 128;     // grid-wide rounds of the interior arbiters that overflowed into the generic colours
 constexpr int CB = 4;                   // records a thread has in flight at once: a round is a chain of dependent L2 round trips
-template <bool REGIONS>
-__device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters* cn, unsigned* bar, unsigned& bar_target, unsigned char* scratch, int scratch_bytes) {  // true: the grid has met at a barrier
+// `work`: something every CTA has to do that does not depend on the colours; it is called exactly once, where the CTA would wait.
+template <bool REGIONS, typename Work>
+__device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters* cn, unsigned* bar, unsigned& bar_target, unsigned char* scratch, int scratch_bytes, Work work) {  // true: the grid has met at a barrier
     const int tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
     const int T = blockDim.x, bid = blockIdx.x, lt = threadIdx.x;
     const int nunc = *(volatile int*)&cn->n_uncolored;
-    if (nunc <= 0) return false;
+    if (nunc <= 0) { work(); return false; }
+    const int gen_cta = REGIONS ? max(a.n_regions - 1, 0) : 0;  // the CTA that colours the cross-region arbiters (box piles: the last region is the lightest)
     int cq_ = 0;
-    auto cstamp = [&]() { if (a.dbg && (bid == 0 || bid == a.probe_cta) && lt == 0 && cq_ < 8) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[(bid == 0 ? 48 : 56) + cq_++] = t; } };
+    auto cstamp = [&]() { if (a.dbg && (bid == gen_cta || bid == a.probe_cta) && lt == 0 && cq_ < 8) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[(bid == gen_cta ? 48 : 56) + cq_++] = t; } };
     cstamp();
     int* lists[2] = {a.uncolored, a.uncolored2};
     const int4 no_rec = make_int4(-1, UNC_STATIC, UNC_STATIC, 0);  // (a lane without a record: loads body 0, does nothing)
@@ -1111,7 +1113,7 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
     if (REGIONS && a.color_local && *(volatile int*)&cn->bin_overflow == 0) {
         __shared__ int s_nn;
         const int n_int = bid < a.n_regions ? min(__ldcg(&cn->region_new[bid]), a.bin_cap) : 0;
-        const int n_gen = bid == 0 ? min(__ldcg(&cn->region_new[a.n_regions]), a.bin_cap) : 0;
+        const int n_gen = bid == gen_cta ? min(__ldcg(&cn->region_new[a.n_regions]), a.bin_cap) : 0;
         const int n0 = n_int + n_gen;
         const int HT = scratch_bytes >= 160 * 1024 ? 16384 : 8192;
         unsigned* ht = (unsigned*)scratch;     // claim cells
@@ -1180,13 +1182,17 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
         }
         cstamp();
         if (lt == 0 && round > 0) atomicMax(&cn->rounds, round);
+        __syncthreads();  // (the scratch is dead: `work` may use the shared memory)
+        if (bid != gen_cta) work();  // everybody else would only wait for the cross-region colours
         grid_barrier(bar, bar_target);
+        if (bid == gen_cta) work();
         cstamp();
         const int np = *(volatile int*)&cn->n_promoted;
         if (np > 0) grid_rounds(np, PROMOTE_ROUND0, false);
         return true;
     }
     grid_rounds(nunc, 0, true);
+    work();
     return true;
 }
 
@@ -1225,7 +1231,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
     float4* s_cb = s_ca + CONCAP;
     float4* s_cc = s_cb + CONCAP;
 
-    color_new_arbiters<false>(a, cn, bar, bar_target, nullptr, 0);
+    color_new_arbiters<false>(a, cn, bar, bar_target, nullptr, 0, [] {});
 
     stamp(1);
     // ---- 2. colour-major order (within a colour the order is irrelevant: disjoint dynamic bodies) and this CTA's share
@@ -1654,7 +1660,32 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     fill_arbiter_rows(a.B, min(*(volatile int*)&cn->n_pairs, a.cap_pairs), a.cand_row_start, a.pscan, a.cur.row_start, tid, nth);  // read after the barrier of 2a
     // (the per-body table of generic arbiters `gadj` — slot = colour bit, entry = (arbiter, owner region | colour << 16) — was written by
     // k_build and by the colouring; the rows and the colours of other CTAs' arbiters are visible behind the grid barrier)
-    if (!color_new_arbiters<true>(a, cn, bar, bar_target, sm_raw, a.smem_bytes)) grid_barrier(bar, bar_target);
+    // The part of the set-up that needs no colours — the tables, the region's bodies, the list of its own arbiters — runs where the CTA
+    // would otherwise wait for the cross-region colours.  (The rows of its own bodies come straight from the candidate rows.)
+    int2* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA (arbiter, colour), in discovery order
+    auto bodies_in = [&]() {
+        if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; s_ccnt[lt] = 0; }
+        if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_nown = 0; s_bad = (const unsigned char*)(s_body + 2 * (size_t)nb) > scratch_lo ? 1 : 0; }
+        for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
+        __syncthreads();
+        const int P = min(*(volatile int*)&cn->n_pairs, a.cap_pairs);
+        for (int lb = lt; lb < nb && !s_bad; lb += T) {  // bodies: state, the arbiters of the body's row
+            const int b = a.reg_bodies[rb0 + lb];
+            const Rec32 vr = ld256(a.vrec + 2 * (size_t)b);  // { vx | ver, vy | ver } { w | ver, inv_mass | inv_moi } (k_prepare)
+            const float4 p = a.pose[b];
+            const int r0 = min(a.cand_row_start[b], P), r1 = b + 1 < a.B ? min(a.cand_row_start[b + 1], P) : P;
+            const int e0 = (int)(__ldcg(&a.pscan[r0]) >> 32), e1 = min((int)(__ldcg(&a.pscan[r1]) >> 32), A);
+            s_body[2 * lb] = make_float4(__int_as_float(vr.a.x), __int_as_float(vr.a.z), __int_as_float(vr.b.x), 0.0f);
+            s_body[2 * lb + 1] = make_float4(p.x, p.y, __int_as_float(vr.b.z), __int_as_float(vr.b.w));
+            if (e1 > e0) {
+                const int k = atomicAdd(&s_nown, e1 - e0);
+                for (int e = e0; e < e1; e++)
+                    if (k + e - e0 < OWN_MAX) t_own[k + e - e0] = make_int2(e, -1); else s_bad = 1;
+            }
+        }
+        __syncthreads();
+    };
+    if (!color_new_arbiters<true>(a, cn, bar, bar_target, sm_raw, a.smem_bytes, bodies_in)) grid_barrier(bar, bar_target);
     stamp(1);
     tstamp();
     if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // an arbiter without a free colour (every CTA sees it: the colouring ends with a barrier)
@@ -1667,13 +1698,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     // (region, local index) of both bodies | contact count, first contact, friction) and about a contact in another
     // (`cin`: position, normal | separation, pn, pt).
     // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) listed and counted by colour
-    BodyIO io{a.vrec, a.sleep_ns, &cn->err};
-    if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; s_ccnt[lt] = 0; }
-    if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_nown = 0; s_bad = (const unsigned char*)(s_body + 2 * (size_t)nb) > scratch_lo ? 1 : 0; }
-    for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
-    __syncthreads();
-    const bool fits = !s_bad;  // the region's bodies alone must leave room for the scratch (the host sizes the regions accordingly)
-    int2* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA (arbiter, colour), in discovery order
+    const bool fits = (const unsigned char*)(s_body + 2 * (size_t)nb) <= scratch_lo;  // the region's bodies alone must leave room for the scratch (the host sizes the regions accordingly)
     auto arb_insert = [&](int f) -> bool {  // true: f is new
         unsigned h = hash_u32((unsigned)f) & (HASH_CAP - 1);
         for (int probe = 0; probe < HASH_CAP; probe++) {
@@ -1742,17 +1767,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
             }
         }
     };
-    for (int lb = lt; lb < nb && fits; lb += T) {  // bodies: state, boundary list, the arbiters of the body's row
+    for (int lb = lt; lb < nb && fits; lb += T) {  // boundary bodies (the colours at every body are final now)
         const int b = a.reg_bodies[rb0 + lb];
-        const Rec32 vr = ld256(a.vrec + 2 * (size_t)b);  // { vx | ver, vy | ver } { w | ver, inv_mass | inv_moi } (k_prepare)
-        Vel v;
-        v.v = mk(__int_as_float(vr.a.x), __int_as_float(vr.a.z)); v.w = __int_as_float(vr.b.x);
-        const float im = __int_as_float(vr.b.z), ii = __int_as_float(vr.b.w);
-        const float4 p = a.pose[b];
         const unsigned long long ub = __ldcg(&a.used[b]);  // (never set at a static body)
-        const int e0 = a.cur.row_start[b], e1 = min(a.cur.row_start[b + 1], A);
-        s_body[2 * lb] = make_float4(v.v.x, v.v.y, v.w, 0.0f);
-        s_body[2 * lb + 1] = make_float4(p.x, p.y, im, ii);
         if (ub != 0ull) {  // a boundary body: exported every pass
             const int k = atomicAdd(&s_nbnd, 1);
             s_bnd[k] = lb;
@@ -1762,11 +1779,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
                 const int2 f = __ldcg(&a.gadj[(size_t)b * GADJ + kb]);
                 if ((f.y & 0xffff) != R) add_ghost(f.x, GEN_BIT + kb);
             }
-        }
-        if (e1 > e0) {
-            const int k = atomicAdd(&s_nown, e1 - e0);
-            for (int e = e0; e < e1; e++)
-                if (k + e - e0 < OWN_MAX) t_own[k + e - e0] = make_int2(e, -1); else s_bad = 1;
         }
     }
     __syncthreads();
