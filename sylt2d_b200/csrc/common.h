@@ -20,7 +20,7 @@ void set_last_error(const std::string& s);
         cudaError_t e__ = (call);                                                              \
         if (e__ != cudaSuccess) {                                                              \
             char buf__[512];                                                                   \
-            snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            snprintf(buf__, sizeof buf__, "%s:%d: %.300s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
             sylt::set_last_error(buf__);                                                       \
             return SYLT_ERR_CUDA;                                                              \
         }                                                                                      \

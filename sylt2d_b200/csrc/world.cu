@@ -1633,7 +1633,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     stamp(0);
     __shared__ int s_cnt[NCX], s_fill[NCX], s_cstart[NCX + 1], s_clist[NCX], s_ccnt[NCX], s_cfill[NCX];  // slots / contacts by colour
     __shared__ int s_ncl, s_nint, s_nbnd, s_L, s_ngh, s_ngb, s_nown, s_bad;
-    __shared__ int s_scan[34];
     __shared__ int2 s_hop[NCX];
     __shared__ int s_wtot[3], s_wctot[3];
     __shared__ unsigned s_wbal[3];
@@ -2567,6 +2566,7 @@ struct SyltWorld {
     unsigned step_tag = 0;
     int regions_mode = 1;            // SYLT_REGIONS: 0 = never (k_solve only), 1 = joint-free worlds of at least regions_min_bodies (default), 2 = always
     int regions_min_bodies = 1000, regions_count = 0, regions_period = 128;
+    bool color_local = true;         // SYLT_COLOR_LOCAL=0: new arbiters are coloured by the grid-wide rounds only (diagnostics)
     bool regions_on = false;         // the partition on the device is valid for the current bodies
     bool part_dirty = true;          // bodies were added / the mode may have changed
     bool last_regions = false;       // the last enqueued step ran k_solve_regions
@@ -3025,8 +3025,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
             w->step_tag = 1;
         }
         a.step_tag = w->step_tag;
-        static const int color_local = getenv("SYLT_COLOR_LOCAL") ? atoi(getenv("SYLT_COLOR_LOCAL")) : 1;
-        a.color_local = color_local;
+        a.color_local = w->color_local ? 1 : 0;
         a.unc_bin = w->unc_bin.p; a.unc_bin_idx = w->unc_bin_idx.p; a.bin_cap = unc_bin_cap(w);
         a.probe_cta = getenv("SYLT_PROBE_CTA") ? atoi(getenv("SYLT_PROBE_CTA")) : w->regions_blocks / 2;
         SYLT_CUDA(cudaLaunchCooperativeKernel(w->regions_per_sm == 2 ? (void*)k_solve_regions<2> : (void*)k_solve_regions<1>, dim3((unsigned)w->regions_blocks),
@@ -3316,6 +3315,7 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
         if (const char* ev = getenv("SYLT_REGIONS_MIN_BODIES")) w->regions_min_bodies = std::max(1, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_COUNT")) w->regions_count = std::max(0, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_PERIOD")) w->regions_period = std::max(1, atoi(ev));
+        if (const char* ev = getenv("SYLT_COLOR_LOCAL")) w->color_local = atoi(ev) != 0;
         if (per2 < w->regions_per_sm || w->ctas_per_sm != 1) w->regions_mode = 0;
     }
     int per_sm = 0;

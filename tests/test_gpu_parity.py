@@ -753,6 +753,26 @@ def test_region_solver_bit_exact(monkeypatch, count, period):
     _run_lockstep(scenes.bridge(10), 20)                                             # joints: falls back to k_solve
 
 
+@pytest.mark.parametrize("count,local", [(1, 1), (3, 1), (3, 0)])
+def test_region_solver_interior_colours_overflow_into_generic_ones(monkeypatch, count, local):
+    """A dynamic plank carrying 45 boxes inside ONE region has more arbiters than there are interior colours (32): the region's CTA
+    colours what it can by itself (block barriers, shared-memory claims) and promotes the rest to generic colours in grid-wide rounds
+    (local = 0: the grid-wide rounds colour everything).  Bit-exact vs the oracle; colours stay proper."""
+    monkeypatch.setenv("SYLT_REGIONS", "2")
+    monkeypatch.setenv("SYLT_REGIONS_COUNT", str(count))
+    monkeypatch.setenv("SYLT_COLOR_LOCAL", str(local))
+    b = scenes._Builder()
+    scenes._ground(b)
+    b.box(60.0, 1.0, 500.0, 0.3, (0.0, 0.55))
+    for i in range(45):
+        b.box(1.0, 1.0, 5.0, 0.3, (-27.5 + 1.25 * i, 1.6))
+    w, _ = _run_lockstep(b.scene("plank45", iterations=10), 40, check_every=5)
+    ga, _ = w.get_arbiters()
+    assert ga.shape[0] >= 46 and ga["color"].max() >= 32
+    if count == 1:  # everything is interior to the one region: all 32 interior colours are taken at the plank, the rest was promoted
+        assert (ga["color"] < 32).sum() >= 32
+
+
 def test_region_solver_survives_a_body_shot_far_away(monkeypatch):
     """One body far outside the pile must not collapse the spatial partition (k_resort trims its grid to the bulk of the
     bodies): the regions stay compact (most arbiters interior), the step succeeds and stays bit-identical to the oracle."""
