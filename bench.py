@@ -246,6 +246,24 @@ def bench_world100k(device, steps, cpu=True):
     out["roofline_frac_whole_step"] = by / (ms_step * 1e-3) / 1e9 / peak
     out["solver_bytes_per_step"] = ITER * 120 * C
     out["body_steps_per_sec"] = B / (ms_step * 1e-3)
+    # per-kernel durations of a step (CUDA events between the launches: this serialises the chain, so their sum exceeds ms_step);
+    # the solver fraction is quoted for the WHOLE solver launch — colouring of new arbiters, set-up, pre-step, iterations, write-back
+    w.set_kernel_timing(True)
+    kt = []
+    for _ in range(15):
+        w.step(sc.dt)
+        kt.append(w.kernel_times())
+    w.set_kernel_timing(False)
+    med = {k: float(np.median([t[k] for t in kt if k in t])) for k in kt[-1]}
+    out["kernel_us_median_of_15_steps"] = med
+    if "solve" in med and med["solve"] > 0:
+        Cn = w.get_stats()["contacts"]
+        out["solver_kernel"] = {"name": "k_solve_regions", "us": med["solve"], "algorithmic_bytes": ITER * 120 * Cn,
+                                "achieved_gbs": ITER * 120 * Cn / (med["solve"] * 1e-6) / 1e9, "peak_gbs": peak,
+                                "frac": ITER * 120 * Cn / (med["solve"] * 1e-6) / 1e9 / peak,
+                                "note": "I x 120 B x contacts over the duration of the whole solver launch; the work is done in shared memory "
+                                        "(issue / latency bound colour hops), DRAM traffic of the launch is ~40 MB"}
+        out["non_solver_kernels_us"] = float(sum(v for k, v in med.items() if k != "solve"))
     # end to end: what a caller of World::step pays when it mirrors the world on the host after every step
     t0 = time.perf_counter()
     for _ in range(20):

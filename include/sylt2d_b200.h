@@ -193,6 +193,11 @@ int sylt_world_timer_start(SyltWorld* w);
 int sylt_world_timer_stop(SyltWorld* w, float* out_ms);
 /* number of kernel launches issued by this handle so far */
 int64_t sylt_world_launch_count(SyltWorld* w);
+/* Diagnostics: with kernel timing on, CUDA events are recorded between the launches of every step (this serialises the chain of
+ * short kernels, so the step itself gets slower).  get_kernel_times returns the durations [us] of the LAST step's launches in
+ * order — prepare, cells, fill cells, rows count, rows emit, narrow, (re-cut +) build, solve — and their number (or -error). */
+int sylt_world_set_kernel_timing(SyltWorld* w, int on);
+int sylt_world_get_kernel_times(SyltWorld* w, float* out_us, int32_t cap);
 
 /* Narrow phase on n explicit pairs (collide / collide_polygons called directly, as examples/collision-debug does).
  * a[i], b[i] describe the two bodies of pair i; verts holds polygon vertices.  Writes up to `cap` contacts per pair

@@ -42,7 +42,7 @@ SYMBOLS = [
     "sylt_world_num_arbiters", "sylt_world_num_contacts", "sylt_world_get_bodies", "sylt_world_set_bodies", "sylt_world_get_body_props",
     "sylt_world_get_arbiters", "sylt_world_get_joints", "sylt_world_get_joint_order", "sylt_world_get_stats",
     "sylt_world_last_error_matrix", "sylt_world_broad_phase", "sylt_world_step", "sylt_world_step_n", "sylt_world_step_n_async",
-    "sylt_world_sync", "sylt_world_timer_start", "sylt_world_timer_stop", "sylt_world_launch_count", "sylt_collide_pairs", "sylt_sincos",
+    "sylt_world_sync", "sylt_world_timer_start", "sylt_world_timer_stop", "sylt_world_launch_count", "sylt_world_set_kernel_timing", "sylt_world_get_kernel_times", "sylt_collide_pairs", "sylt_sincos",
     "sylt_batch_create", "sylt_batch_destroy", "sylt_batch_set_context", "sylt_batch_set_capacity", "sylt_batch_set_export_worlds", "sylt_batch_set_fixes", "sylt_batch_step_n", "sylt_batch_step_n_async",
     "sylt_batch_sync", "sylt_batch_step_host", "sylt_batch_step_host6", "sylt_batch_timer_start", "sylt_batch_timer_stop", "sylt_batch_launch_count", "sylt_batch_num_worlds",
     "sylt_batch_num_bodies", "sylt_batch_get_bodies", "sylt_batch_set_bodies", "sylt_batch_get_arbiters", "sylt_batch_get_joints",
@@ -102,6 +102,8 @@ def lib():
     L.sylt_world_step_n.argtypes = [vp, f32, i32]
     L.sylt_world_step_n_async.argtypes = [vp, f32, i32]
     L.sylt_world_timer_stop.argtypes = [vp, vp]
+    L.sylt_world_set_kernel_timing.argtypes = [vp, C.c_int]
+    L.sylt_world_get_kernel_times.argtypes = [vp, vp, C.c_int32]
     L.sylt_world_launch_count.argtypes = [vp]
     L.sylt_world_launch_count.restype = i64
     L.sylt_collide_pairs.argtypes = [i32, vp, vp, i32, vp, i32, vp, i32, vp]

@@ -1995,9 +1995,15 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
 
     // One slot of one colour hop.  Bodies and (normally) contacts are in shared memory; r1, r2 are recomputed from the
     // contact position exactly as Arbiter::pre_step / apply_impulse do (arbiter.rs:192-193, 236-237).
+    // -DSYLT_HOP_PROBE: cycle stamps inside the colour hops of pass 5 in the probe CTA (diagnostics build only: the probes cost ~10 % of
+    // the loop's instructions)
+#ifdef SYLT_HOP_PROBE
     bool hop_probe = false;
     int hop_k = 0;
 #define HOPCLK(k, dep) do { if (hop_probe) { unsigned long long t_; float d_ = (dep); asm volatile("mov.u64 %0, %%clock64;" : "=l"(t_) : "f"(d_) : "memory"); a.dbg[64 + 8 * 1024 + hop_k * 8 + (k)] = t_; } } while (0)
+#else
+#define HOPCLK(k, dep) do { } while (0)
+#endif
     auto solve_slot = [&](int ls, unsigned pass) {
         const int sb = s_sb[ls], sc = s_sc[ls];
         const float fr = s_sf[ls];
@@ -2081,15 +2087,19 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     auto colours = [&](unsigned pass, int k0, int k1) {  // colour hops k0..k1 of the list
         for (int k = k0; k < k1; k++) {
             const int2 h = s_hop[k];  // (first slot, slots) of the hop's colour
+#ifdef SYLT_HOP_PROBE
             hop_probe = a.dbg && bid == a.probe_cta && lt == 0 && pass == 5u && k < 8;
             hop_k = k;
+#endif
             HOPCLK(0, 0.0f);
             for (int i = lt; i < h.y; i += T) solve_slot(h.x + i, pass);
             HOPCLK(4, 0.0f);
             __syncthreads();
             HOPCLK(5, 0.0f);
+#ifdef SYLT_HOP_PROBE
             if (hop_probe) a.dbg[64 + 8 * 1024 + k * 8 + 6] = (unsigned long long)h.y;
             hop_probe = false;
+#endif
         }
     };
     // One pass: interior colours; boundary bodies out (plane `pass` of the export records); ghosts in; generic colours.
@@ -2574,8 +2584,9 @@ struct SyltWorld {
     int n_regions = 0;
     int64_t steps_since_part = 0;
     bool resort_pending = false;     // the partition of the current bodies has not been computed yet
-    cudaEvent_t kt_ev[16] = {};      // SYLT_KERNEL_TIMING
+    cudaEvent_t kt_ev[16] = {};      // SYLT_KERNEL_TIMING / sylt_world_set_kernel_timing
     int kt_n = 0;
+    bool kernel_timing = false, kernel_timing_print = false;
     size_t solve_budget = 0;         // dynamic shared memory of one k_solve_regions CTA
     int regions_per_sm = 1, regions_blocks = 0, regions_threads = SOLVE_THREADS;  // SYLT_REGION_CTAS_PER_SM
 
@@ -2914,7 +2925,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     const int B = (int)w->hb.size();
     cudaStream_t st = w->stream;
     // SYLT_KERNEL_TIMING=1: events between the launches of every step (diagnostics; it serialises the launch chain)
-    static const bool ktime = getenv("SYLT_KERNEL_TIMING") && atoi(getenv("SYLT_KERNEL_TIMING"));
+    const bool ktime = w->kernel_timing;
     int kt_n = 0;
     auto mark = [&]() { if (ktime && kt_n < 16) { if (!w->kt_ev[kt_n]) cudaEventCreate(&w->kt_ev[kt_n]); cudaEventRecord(w->kt_ev[kt_n++], st); } };
     mark();
@@ -3147,7 +3158,7 @@ int finish(SyltWorld* w) {
         }
         delete hs;
     }
-        if (w->kt_n > 1) {  // SYLT_KERNEL_TIMING: the last step's launches
+        if (w->kt_n > 1 && w->kernel_timing_print) {  // SYLT_KERNEL_TIMING: the last step's launches
             static const char* names[] = {"prepare", "scan cells", "fill cells", "rows count", "rows emit", "narrow", "(re-cut +) build", "solve"};
             fprintf(stderr, "kernels [us]:");
             for (int k = 1; k < w->kt_n; k++) {
@@ -3316,6 +3327,7 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
         if (const char* ev = getenv("SYLT_REGIONS_COUNT")) w->regions_count = std::max(0, atoi(ev));
         if (const char* ev = getenv("SYLT_REGIONS_PERIOD")) w->regions_period = std::max(1, atoi(ev));
         if (const char* ev = getenv("SYLT_COLOR_LOCAL")) w->color_local = atoi(ev) != 0;
+        if (const char* ev = getenv("SYLT_KERNEL_TIMING")) w->kernel_timing = w->kernel_timing_print = atoi(ev) != 0;
         if (per2 < w->regions_per_sm || w->ctas_per_sm != 1) w->regions_mode = 0;
     }
     int per_sm = 0;
@@ -3771,6 +3783,25 @@ int sylt_world_timer_stop(SyltWorld* w, float* ms) {
     return SYLT_OK;
 }
 int64_t sylt_world_launch_count(SyltWorld* w) { return w ? w->launches : 0; }
+
+int sylt_world_set_kernel_timing(SyltWorld* w, int on) {
+    if (!w) return SYLT_ERR_INVALID;
+    w->kernel_timing = on != 0;
+    if (!on) w->kt_n = 0;
+    return SYLT_OK;
+}
+int sylt_world_get_kernel_times(SyltWorld* w, float* out_us, int32_t cap) {
+    if (!w || (cap > 0 && !out_us)) return -SYLT_ERR_INVALID;
+    if (cudaSetDevice(w->device) != cudaSuccess) return -SYLT_ERR_CUDA;
+    if (w->inflight) { const int e = finish(w); if (e) return -e; }
+    int n = 0;
+    for (int k = 1; k < w->kt_n && n < cap; k++, n++) {
+        float ms = 0.0f;
+        if (cudaEventElapsedTime(&ms, w->kt_ev[k - 1], w->kt_ev[k]) != cudaSuccess) return -SYLT_ERR_CUDA;
+        out_us[n] = ms * 1e3f;
+    }
+    return n;
+}
 
 int sylt_collide_pairs(int device, const SyltBodyDesc* a, const SyltBodyDesc* b, int32_t n, const float* verts_xy, int32_t n_verts,
                        SyltContact* out, int32_t cap, int32_t* out_counts) {

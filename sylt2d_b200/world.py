@@ -214,6 +214,20 @@ class World:
         check(self.L.sylt_world_timer_stop(self.h, C.byref(ms)))
         return ms.value
 
+    KERNEL_NAMES = ("prepare", "cells", "fill_cells", "rows_count", "rows_emit", "narrow", "build", "solve")
+
+    def set_kernel_timing(self, on=True):
+        """Diagnostics: CUDA events between the launches of every step (serialises the chain of short kernels)."""
+        check(self.L.sylt_world_set_kernel_timing(self.h, 1 if on else 0))
+
+    def kernel_times(self):
+        """{kernel: microseconds} of the last step's launches (needs set_kernel_timing)."""
+        buf = (C.c_float * 16)()
+        n = self.L.sylt_world_get_kernel_times(self.h, buf, 16)
+        if n < 0:
+            check(-n)
+        return {self.KERNEL_NAMES[k] if k < len(self.KERNEL_NAMES) else f"k{k}": float(buf[k]) for k in range(n)}
+
     @property
     def launch_count(self):
         return self.L.sylt_world_launch_count(self.h)
