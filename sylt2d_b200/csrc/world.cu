@@ -1662,42 +1662,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     // The part of the set-up that needs no colours — the tables, the region's bodies, the list of its own arbiters — runs where the CTA
     // would otherwise wait for the cross-region colours.  (The rows of its own bodies come straight from the candidate rows.)
     int2* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA (arbiter, colour), in discovery order
-    auto bodies_in = [&]() {
-        if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; s_ccnt[lt] = 0; }
-        if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_nown = 0; s_bad = (const unsigned char*)(s_body + 2 * (size_t)nb) > scratch_lo ? 1 : 0; }
-        for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
-        __syncthreads();
-        const int P = min(*(volatile int*)&cn->n_pairs, a.cap_pairs);
-        for (int lb = lt; lb < nb && !s_bad; lb += T) {  // bodies: state, the arbiters of the body's row
-            const int b = a.reg_bodies[rb0 + lb];
-            const Rec32 vr = ld256(a.vrec + 2 * (size_t)b);  // { vx | ver, vy | ver } { w | ver, inv_mass | inv_moi } (k_prepare)
-            const float4 p = a.pose[b];
-            const int r0 = min(a.cand_row_start[b], P), r1 = b + 1 < a.B ? min(a.cand_row_start[b + 1], P) : P;
-            const int e0 = (int)(__ldcg(&a.pscan[r0]) >> 32), e1 = min((int)(__ldcg(&a.pscan[r1]) >> 32), A);
-            s_body[2 * lb] = make_float4(__int_as_float(vr.a.x), __int_as_float(vr.a.z), __int_as_float(vr.b.x), 0.0f);
-            s_body[2 * lb + 1] = make_float4(p.x, p.y, __int_as_float(vr.b.z), __int_as_float(vr.b.w));
-            if (e1 > e0) {
-                const int k = atomicAdd(&s_nown, e1 - e0);
-                for (int e = e0; e < e1; e++)
-                    if (k + e - e0 < OWN_MAX) t_own[k + e - e0] = make_int2(e, -1); else s_bad = 1;
-            }
-        }
-        __syncthreads();
-    };
-    if (!color_new_arbiters<true>(a, cn, bar, bar_target, sm_raw, a.smem_bytes, bodies_in)) grid_barrier(bar, bar_target);
-    stamp(1);
-    tstamp();
-    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // an arbiter without a free colour (every CTA sees it: the colouring ends with a barrier)
-    tstamp();
-    unsigned long long t_setup0 = 0;
-    if (a.dbg && lt == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_setup0));
-
-    // The set-up below is bound by the number of scattered 32-byte sectors a CTA has to fetch (~2 ns each per SM), so everything
-    // it needs to know about an arbiter comes in one 32-byte record k_build wrote (`srec`: bodies with their static flags,
-    // (region, local index) of both bodies | contact count, first contact, friction) and about a contact in another
-    // (`cin`: position, normal | separation, pn, pt).
-    // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) listed and counted by colour
-    const bool fits = (const unsigned char*)(s_body + 2 * (size_t)nb) <= scratch_lo;  // the region's bodies alone must leave room for the scratch (the host sizes the regions accordingly)
     auto arb_insert = [&](int f) -> bool {  // true: f is new
         unsigned h = hash_u32((unsigned)f) & (HASH_CAP - 1);
         for (int probe = 0; probe < HASH_CAP; probe++) {
@@ -1766,6 +1730,64 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
             }
         }
     };
+    constexpr int SB = 4;  // arbiters a thread has in flight at once
+    auto bodies_in = [&]() {
+        if (lt < NCX) { s_cnt[lt] = 0; s_fill[lt] = 0; s_ccnt[lt] = 0; }
+        if (lt == 0) { s_nbnd = 0; s_ngh = 0; s_ngb = 0; s_nown = 0; s_bad = (const unsigned char*)(s_body + 2 * (size_t)nb) > scratch_lo ? 1 : 0; }
+        for (int k = lt; k < 3 * HASH_CAP; k += T) h_arb[k] = 0;
+        __syncthreads();
+        const int P = min(*(volatile int*)&cn->n_pairs, a.cap_pairs);
+        for (int lb = lt; lb < nb && !s_bad; lb += T) {  // bodies: state, the arbiters of the body's row
+            const int b = a.reg_bodies[rb0 + lb];
+            const Rec32 vr = ld256(a.vrec + 2 * (size_t)b);  // { vx | ver, vy | ver } { w | ver, inv_mass | inv_moi } (k_prepare)
+            const float4 p = a.pose[b];
+            const int r0 = min(a.cand_row_start[b], P), r1 = b + 1 < a.B ? min(a.cand_row_start[b + 1], P) : P;
+            const int e0 = (int)(__ldcg(&a.pscan[r0]) >> 32), e1 = min((int)(__ldcg(&a.pscan[r1]) >> 32), A);
+            s_body[2 * lb] = make_float4(__int_as_float(vr.a.x), __int_as_float(vr.a.z), __int_as_float(vr.b.x), 0.0f);
+            s_body[2 * lb + 1] = make_float4(p.x, p.y, __int_as_float(vr.b.z), __int_as_float(vr.b.w));
+            if (e1 > e0) {
+                const int k = atomicAdd(&s_nown, e1 - e0);
+                for (int e = e0; e < e1; e++)
+                    if (k + e - e0 < OWN_MAX) t_own[k + e - e0] = make_int2(e, -1); else s_bad = 1;
+            }
+        }
+        __syncthreads();
+        // own arbiters with an interior colour (persisting, or coloured by this CTA a moment ago): counted and adopted here; the generic
+        // ones and the ones still without a colour (cross-region, promoted) are marked and wait for the grid barrier (t_own.y = -2)
+        const int nown_ = min(s_nown, OWN_MAX);
+        for (int k0 = lt; k0 < nown_; k0 += SB * T) {
+            int e[SB], c[SB], n[SB];
+            int4 ra[SB];
+#pragma unroll
+            for (int u = 0; u < SB; u++) e[u] = k0 + u * T < nown_ ? t_own[k0 + u * T].x : -1;
+#pragma unroll
+            for (int u = 0; u < SB; u++)
+                if (e[u] >= 0) { c[u] = __ldcg(&a.cur.color[e[u]]); const Rec32 r = ld256(&a.srec[2 * (size_t)e[u]]); ra[u] = r.a; n[u] = r.b.x; }
+#pragma unroll
+            for (int u = 0; u < SB; u++) {
+                if (e[u] < 0) continue;
+                if (c[u] < 0 || c[u] >= GEN_BIT) { t_own[k0 + u * T].y = -2; continue; }
+                t_own[k0 + u * T].y = c[u];
+                atomicAdd(&s_cnt[c[u]], 1);
+                adopt(c[u], ra[u], n[u]);
+            }
+        }
+        __syncthreads();
+    };
+    if (!color_new_arbiters<true>(a, cn, bar, bar_target, sm_raw, a.smem_bytes, bodies_in)) grid_barrier(bar, bar_target);
+    stamp(1);
+    tstamp();
+    if (*(volatile int*)&cn->err == SYLT_ERR_CAPACITY) return;  // an arbiter without a free colour (every CTA sees it: the colouring ends with a barrier)
+    tstamp();
+    unsigned long long t_setup0 = 0;
+    if (a.dbg && lt == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t_setup0));
+
+    // The set-up below is bound by the number of scattered 32-byte sectors a CTA has to fetch (~2 ns each per SM), so everything
+    // it needs to know about an arbiter comes in one 32-byte record k_build wrote (`srec`: bodies with their static flags,
+    // (region, local index) of both bodies | contact count, first contact, friction) and about a contact in another
+    // (`cin`: position, normal | separation, pn, pt).
+    // ---- 2b. the region's bodies into shared memory; its own arbiters (the rows its bodies own) listed and counted by colour
+    const bool fits = (const unsigned char*)(s_body + 2 * (size_t)nb) <= scratch_lo;  // the region's bodies alone must leave room for the scratch (the host sizes the regions accordingly)
     for (int lb = lt; lb < nb && fits; lb += T) {  // boundary bodies (the colours at every body are final now)
         const int b = a.reg_bodies[rb0 + lb];
         const unsigned long long ub = __ldcg(&a.used[b]);  // (never set at a static body)
@@ -1782,12 +1804,11 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     }
     __syncthreads();
     const int nown = min(s_nown, OWN_MAX);
-    constexpr int SB = 4;  // arbiters a thread has in flight at once
-    for (int k0 = lt; k0 < nown; k0 += SB * T) {  // own arbiters: colour; the generic ones are the roots of the cone walk (level 0)
+    for (int k0 = lt; k0 < nown; k0 += SB * T) {  // the own arbiters left over: the generic ones are the roots of the cone walk (level 0)
         int e[SB], c[SB], n[SB];
         int4 ra[SB];
 #pragma unroll
-        for (int u = 0; u < SB; u++) e[u] = k0 + u * T < nown ? t_own[k0 + u * T].x : -1;
+        for (int u = 0; u < SB; u++) { e[u] = -1; if (k0 + u * T < nown) { const int2 t = t_own[k0 + u * T]; if (t.y == -2) e[u] = t.x; } }
 #pragma unroll
         for (int u = 0; u < SB; u++)
             if (e[u] >= 0) { c[u] = __ldcg(&a.cur.color[e[u]]); const Rec32 r = ld256(&a.srec[2 * (size_t)e[u]]); ra[u] = r.a; n[u] = r.b.x; }
