@@ -53,7 +53,7 @@ extern "C" {
 #define SYLT_ERR_UNSUPPORTED 8    /* e.g. polygons with > SYLT_MAX_POLY_VERTS vertices */
 #define SYLT_ERR_INTERNAL 9       /* solver watchdog: an ordered wait never completed (a bug; the step result is invalid) */
 
-#define SYLT_MAX_POLY_VERTS 8     /* per polygon; manifolds hold up to 2*SYLT_MAX_POLY_VERTS contacts (reference: unbounded) */
+#define SYLT_MAX_POLY_VERTS 32    /* per polygon; a manifold of two polygons holds up to n1 + n2 contacts (reference: unbounded) */
 #define SYLT_SHAPE_BOX 0
 #define SYLT_SHAPE_POLYGON 1
 

@@ -11,7 +11,7 @@ pub const SYLT_ERR_CAPACITY: c_int = 5;
 pub const SYLT_ERR_CUDA: c_int = 6;
 pub const SYLT_SHAPE_BOX: i32 = 0;
 pub const SYLT_SHAPE_POLYGON: i32 = 1;
-pub const SYLT_MAX_POLY_VERTS: usize = 8;
+pub const SYLT_MAX_POLY_VERTS: usize = 32;
 pub const SYLT_MAX_MANIFOLD: usize = 2 * SYLT_MAX_POLY_VERTS;
 
 /// Body construction record (64 bytes, include/sylt2d_b200.h `SyltBodyDesc`)

@@ -19,8 +19,8 @@ struct ContactOut {
     uint32_t feat;
 };
 
-constexpr int MAX_POLY_VERTS = 8;
-constexpr int MAX_MANIFOLD = 2 * MAX_POLY_VERTS;
+constexpr int MAX_POLY_VERTS = 32;               // per polygon (SYLT_MAX_POLY_VERTS); the kernels come in tiers of 8 / 16 / 32 vertices,
+constexpr int MAX_MANIFOLD = 2 * MAX_POLY_VERTS; // chosen by the largest polygon of the world; a manifold has at most n0 + n1 contacts
 
 struct ClipV {
     V2 v;
@@ -155,8 +155,10 @@ SYLT_HD bool polys_intersect(const V2* c0, int n0, const V2* c1, int n1) {
 }
 
 // collide_polygons (collide_polygon.rs:83-203) on world-space vertex lists c0 (body1) and c1 (body2).
-// Returns the contact count; *overflow is set when the clipped polygon would exceed MAX_MANIFOLD vertices.
+// Returns the contact count; *overflow is set when the clipped polygon would exceed 2 * MAXV vertices (never for convex input).
+template <int MAXV>  // vertices per polygon the caller's tier allows: the clipped polygon has at most 2 * MAXV
 SYLT_HD int poly_poly(const V2* c0, int n0, const V2* c1, int n1, ContactOut* out, bool* overflow) {
+    constexpr int MAX_MANIFOLD = 2 * MAXV;
     if (n0 <= 0 || n1 <= 0) return 0;
     if (!polys_intersect(c0, n0, c1, n1)) return 0;
     V2 bufa[MAX_MANIFOLD], bufb[MAX_MANIFOLD];
@@ -189,7 +191,7 @@ SYLT_HD int poly_poly(const V2* c0, int n0, const V2* c1, int n1, ContactOut* ou
         np = nc;
     }
     // nearest-edge unit normal of c1 for every surviving vertex (collide_polygon.rs:127-149), contacts (:175-192)
-    V2 unit[MAX_POLY_VERTS];  // the unit normal of an edge does not depend on the vertex: once per edge (the reference recomputes it per vertex, same bits)
+    V2 unit[MAXV];  // the unit normal of an edge does not depend on the vertex: once per edge (the reference recomputes it per vertex, same bits)
     for (int j = 0; j < n1; j++) {
         V2 e = pv(c1, n1, j + 1) - pv(c1, n1, j);
         V2 nrm = mk(-e.y, e.x);

@@ -620,14 +620,15 @@ __global__ void __launch_bounds__(128) k_narrow(const Counters* cn, int cap_pair
         if (MAXC == 2 || !((fa | fb) & FLAG_POLY)) {
             n = box_box(mk(pa.x, pa.y), ra.x, ra.y, mk(ga.x, ga.y), mk(pb.x, pb.y), rb.x, rb.y, mk(gb.x, gb.y), out);
         } else {
-            V2 w0[MAX_POLY_VERTS], w1[MAX_POLY_VERTS];
+            constexpr int MAXV = MAXC / 2 > 0 ? MAXC / 2 : 1;
+            V2 w0[MAXV], w1[MAXV];
             int n0 = (fa >> 8) & 0xff, n1 = (fb >> 8) & 0xff;
             int o0 = __float_as_int(ga.z), o1 = __float_as_int(gb.z);
             M2 r0 = rot_cs(ra.x, ra.y), r1 = rot_cs(rb.x, rb.y);
             for (int k = 0; k < n0; k++) { float2 l = lverts[o0 + k]; w0[k] = r0 * mk(l.x, l.y) + mk(pa.x, pa.y); }  // rotate + translate (body.rs:148-168)
             for (int k = 0; k < n1; k++) { float2 l = lverts[o1 + k]; w1[k] = r1 * mk(l.x, l.y) + mk(pb.x, pb.y); }
             bool ovf = false;
-            n = poly_poly(w0, n0, w1, n1, out, &ovf);
+            n = poly_poly<MAXV>(w0, n0, w1, n1, out, &ovf);
             if (ovf) atomicExch(&cnw->err, SYLT_ERR_CAPACITY);
         }
         info[p] = n > 0 ? ((1ull << 32) | (unsigned)n) : 0ull;
@@ -2491,7 +2492,7 @@ __global__ void k_collide_pairs(int n, const SyltBodyDesc* A, const SyltBodyDesc
         for (int k = 0; k < n0; k++) { float2 l = lverts[loff[4 * p] + k]; w0[k] = r0 * mk(l.x, l.y) + mk(a.x, a.y); }
         for (int k = 0; k < n1; k++) { float2 l = lverts[loff[4 * p + 2] + k]; w1[k] = r1 * mk(l.x, l.y) + mk(b.x, b.y); }
         bool ovf = false;
-        m = poly_poly(w0, n0, w1, n1, o, &ovf);
+        m = poly_poly<MAX_POLY_VERTS>(w0, n0, w1, n1, o, &ovf);
     }
     counts[p] = m;
     for (int k = 0; k < m && k < cap; k++) {
@@ -2540,6 +2541,7 @@ struct SyltWorld {
     bool joints_dirty = true;
     bool jparams_dirty = false;  // only softness / bias_factor / local anchors changed: re-upload, no re-colouring
     bool any_poly = false;
+    int max_poly_verts = 0;  // largest polygon of the world: picks the tier (8 / 16 / 32 vertices) of the narrow phase
     int n_large = 0;
     GridParams gp{1.0f, 1023};
     int buckets = 1024;
@@ -2639,6 +2641,8 @@ struct SyltWorld {
 
 namespace {
 
+// contacts a candidate pair may have: 2 (boxes only) or twice the tier (8 / 16 / 32 vertices) of the world's largest polygon
+int manifold_tier(const SyltWorld* w) { return !w->any_poly ? 2 : w->max_poly_verts <= 8 ? 16 : w->max_poly_verts <= 16 ? 32 : 64; }
 int use_device(SyltWorld* w) {
     SYLT_CUDA(cudaSetDevice(w->device));
     return SYLT_OK;
@@ -2808,7 +2812,7 @@ int flush(SyltWorld* w) {
         int64_t cc = w->user_con ? w->user_con : std::max<int64_t>(16 * (int64_t)B, 4096);
         if (w->any_poly && !w->user_con) cc *= 2;
         cp = std::max(cp, w->grow_pairs); ca = std::max(ca, w->grow_arb); cc = std::max(cc, w->grow_con);  // a step overflowed before
-        const int maxc = w->any_poly ? MAX_MANIFOLD : 2;
+        const int maxc = manifold_tier(w);
         SYLT_CUDA(w->pairs.ensure((size_t)cp));
         SYLT_CUDA(w->info.ensure((size_t)cp + 1));
         SYLT_CUDA(w->pscan.ensure((size_t)cp + 2));
@@ -2983,12 +2987,12 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     w->launches += 1;
     mark();
     const int gridP = w->num_sms * 8;
-    if (w->any_poly)
-        SYLT_CUDA(launch_pdl(k_narrow<MAX_MANIFOLD>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p,
-                             w->bflags.p, w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn, w->pair_btot.p));
-    else
-        SYLT_CUDA(launch_pdl(k_narrow<2>, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p,
+    const int maxc = manifold_tier(w);  // contacts a pair may have: 2 (boxes only) or twice the largest polygon's tier (8 / 16 / 32 vertices)
+    {
+        auto kn = maxc == 2 ? k_narrow<2> : maxc == 16 ? k_narrow<16> : maxc == 32 ? k_narrow<32> : k_narrow<64>;
+        SYLT_CUDA(launch_pdl(kn, dim3((unsigned)gridP), dim3(128), 0, st, cn, (int)w->cap_pairs, w->pairs.p, w->pose.p, w->rotc.p, w->geom.p, w->bflags.p,
                              w->lverts.p, w->info.p, w->tmp_a.p, w->tmp_b.p, cn, w->pair_btot.p));
+    }
     w->launches++;
     mark();
     ArbSet cur = w->set(w->cur), old = w->set(w->cur ^ 1);
@@ -3014,16 +3018,13 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     const int keep_colors = w->recolor_all ? 0 : (recut_now ? 2 : 1);
     w->recolor_all = false;
     static const int build_mult = getenv("SYLT_BUILD_MULT") ? atoi(getenv("SYLT_BUILD_MULT")) : 4;  // CTAs per SM of k_build (8 measured slower: 32.8 vs 26.7 us at 100k bodies)
-    if (w->any_poly)
-        SYLT_CUDA(launch_pdl(k_build<MAX_MANIFOLD>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
+    {
+        auto kb = maxc == 2 ? k_build<2> : maxc == 16 ? k_build<16> : maxc == 32 ? k_build<32> : k_build<64>;
+        SYLT_CUDA(launch_pdl(kb, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
                              w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
                              w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? (full_step ? 2 : 1) : 0, w->lidx.p, w->gadj.p, w->n_regions,
                              w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w), w->srec.p));
-    else
-        SYLT_CUDA(launch_pdl(k_build<2>, dim3((unsigned)(w->num_sms * build_mult)), dim3(256), 0, st, cn, (int)w->cap_pairs, (int)w->cap_arb, (int)w->cap_con, B, w->B_old,
-                             w->have_old ? 1 : 0, w->pairs.p, w->info.p, w->pscan.p, w->pair_btot.p, w->row_start.p, w->tmp_a.p, w->tmp_b.p, w->mp.p, w->bflags.p, w->bflags_old.p, cur, old,
-                             w->warm, w->used.p, w->unc_rec.p, w->fix_features, keep_colors, w->used_int.p, w->regions_on ? (full_step ? 2 : 1) : 0, w->lidx.p, w->gadj.p, w->n_regions,
-                             w->unc_bin.p, w->unc_bin_idx.p, unc_bin_cap(w), w->srec.p));
+    }
     w->launches += 1;
     SYLT_CUDA(cudaGetLastError());
     mark();
@@ -3398,7 +3399,7 @@ int sylt_world_clear(SyltWorld* w) {  // world.rs:67-71
     cudaSetDevice(w->device);
     cudaStreamSynchronize(w->stream);
     w->hb.clear(); w->hverts.clear(); w->pending.clear(); w->hj.clear(); w->h_jorder.clear();
-    w->uploaded = 0; w->class_dirty = true; w->joints_dirty = true; w->any_poly = false; w->n_large = 0;
+    w->uploaded = 0; w->class_dirty = true; w->joints_dirty = true; w->any_poly = false; w->max_poly_verts = 0; w->n_large = 0;
     w->have_old = false; w->B_old = 0; w->have_last = false; w->n_joint_colors = 0; w->inflight = false; w->flags_stale = false;
     w->regions_on = false; w->part_dirty = true; w->recolor_all = false; w->last_regions = false;
     w->segs.clear(); w->n_arb_valid = 0; w->n_con_valid = 0;
@@ -3438,7 +3439,7 @@ int sylt_world_add_bodies(SyltWorld* w, const SyltBodyDesc* bodies, int32_t n, c
         HostBody hb;
         int e = make_host_body(bodies[i], verts_xy, n_verts, &hb, &w->hverts);
         if (e) { w->hb.resize(b0); w->hverts.resize(v0); w->pending.resize(b0 - (size_t)w->uploaded); return e; }
-        if (hb.shape == SYLT_SHAPE_POLYGON) w->any_poly = true;
+        if (hb.shape == SYLT_SHAPE_POLYGON) { w->any_poly = true; w->max_poly_verts = std::max(w->max_poly_verts, hb.nverts); }
         w->hb.push_back(hb);
         SyltBodyState s = {bodies[i].x, bodies[i].y, bodies[i].rotation, bodies[i].vx, bodies[i].vy, bodies[i].angular_velocity, 0.0f, 0.0f, 0.0f};
         w->pending.push_back(s);

@@ -165,6 +165,53 @@ def test_narrow_phase_polygons_bit_exact():
     assert hits > 300
 
 
+def test_polygons_up_to_32_vertices_bit_exact(monkeypatch):
+    """The narrow phase comes in tiers of 8 / 16 / 32 vertices per polygon (the reference is unbounded, src/body.rs:246): pairs of
+    9..32-gons through sylt_collide_pairs, worlds whose largest polygon has 12, 20 and 32 vertices in lock-step with the oracle (both
+    single-world solvers), and a 33-gon is refused."""
+    from sylt2d_b200 import collide_pairs, World, Body, SyltError
+    rng = np.random.default_rng(9)
+    n = 300
+    verts, A, B = [], np.zeros(n, dtype=scenes.BODY_DESC), np.zeros(n, dtype=scenes.BODY_DESC)
+    nv, descs = 0, []
+    for i in range(n):
+        pa = rng.uniform(-20, 20, 2)
+        pb = pa + rng.uniform(-1.2, 1.2, 2)
+        pair = []
+        for D, p in ((A, pa), (B, pb)):
+            k = int(rng.integers(9, 33))
+            ang = np.sort(rng.uniform(0, 2 * np.pi, k))
+            r = rng.uniform(0.5, 1.2)
+            v = np.stack([r * np.cos(ang), r * np.sin(ang)], 1).astype(np.float32)
+            D["mass"][i], D["x"][i], D["y"][i], D["rotation"][i] = 1.0, p[0], p[1], rng.uniform(-7, 7)
+            D["shape"][i], D["vert_offset"][i], D["vert_count"][i] = 1, nv, k
+            verts.append(v)
+            nv += k
+            pair.append(dict(shape=1, verts=v, pos=(D["x"][i], D["y"][i]), rot=D["rotation"][i]))
+        descs.append(pair)
+    out, cnt = collide_pairs(A, B, np.concatenate(verts), cap=64)
+    hits = 0
+    for i in range(n):
+        exp = orc.collide_pair(descs[i][0], descs[i][1], sincos_mode=1)
+        assert cnt[i] == len(exp), i
+        for f in CONTACT_GEOM:
+            assert np.array_equal(out[i, :cnt[i]][f], exp[f]), (i, f)
+        hits += cnt[i] > 2
+    assert hits > 50  # manifolds with more contacts than a box pair can have
+    for regions in ("0", "2"):
+        monkeypatch.setenv("SYLT_REGIONS", regions)
+        for k in (12, 20, 32):
+            b = scenes._Builder()
+            scenes._ground(b)
+            for i in range(6):
+                b.polygon(scenes.regular_ngon(k if i % 2 == 0 else 5, 0.6, 0.1 * i), 4.0, 0.4, (-4.0 + 1.5 * i, 1.0 + 0.9 * (i % 3)), 0.2 * i)
+                b.box(0.8, 0.8, 3.0, 0.4, (-4.0 + 1.5 * i, 4.0 + 0.5 * (i % 2)))
+            _run_lockstep(b.scene(f"ngon{k}", iterations=10), 50, check_every=5)
+    w = World((0.0, -10.0), 10, device=0)
+    with pytest.raises(SyltError):
+        w.add_body(Body.new_polygon(scenes.regular_ngon(33, 1.0), 1.0))
+
+
 @pytest.mark.parametrize("name,steps", [("pyramid6", 120), ("demo1", 150), ("demo2", 80), ("demo3", 150), ("demo4", 120), ("demo6", 150),
                                         ("demo8", 120), ("demo10", 100), ("bridge", 100), ("multi_pendulum", 100)])
 def test_world_step_bit_exact_in_gpu_order(name, steps):
