@@ -820,6 +820,33 @@ def test_region_solver_interior_colours_overflow_into_generic_ones(monkeypatch, 
         assert (ga["color"] < 32).sum() >= 32
 
 
+def test_region_solver_prestep_keeps_the_signs_of_zero_velocities(monkeypatch):
+    """With warm starting off every accumulated impulse is zero when Arbiter::pre_step applies it (arbiter.rs:216-223), so the region
+    solver computes the contact constants in one flat loop instead of an ordered sweep — unless some velocity is exactly -0.0: subtracting
+    a zero impulse can turn it into +0.0, and then the ordered sweep runs.  Velocities must match the oracle including the sign of zeros."""
+    monkeypatch.setenv("SYLT_REGIONS", "2")
+    monkeypatch.setenv("SYLT_REGIONS_COUNT", "4")
+    sc = scenes.pyramid(6, 10)
+    dyn = np.nonzero(sc.bodies["mass"] < scenes.F32_MAX)[0]
+    sc.bodies["vx"][dyn[::2]] = -0.0
+    sc.bodies["angular_velocity"][dyn[::3]] = -0.0
+    sc.bodies["y"][dyn] -= 0.02  # in contact from the first step on
+    w, o = _mk(sc)
+    for s in range(12):
+        if s == 6:  # ... and once more in the middle of the run
+            st = w.get_bodies()
+            st["vx"][dyn[1::2]] = -0.0
+            w.set_bodies(st)
+            o.set_bodies(st)
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        g, r = w.get_bodies(), o.get_bodies()
+        _assert_states_equal(g, r, f"step {s}")
+        for f in ("vx", "vy", "angular_velocity"):
+            assert np.array_equal(np.signbit(g[f]), np.signbit(r[f])), (s, f, np.nonzero(np.signbit(g[f]) != np.signbit(r[f]))[0][:8])
+
+
 def test_region_solver_survives_a_body_shot_far_away(monkeypatch):
     """One body far outside the pile must not collapse the spatial partition (k_resort trims its grid to the bulk of the
     bodies): the regions stay compact (most arbiters interior), the step succeeds and stays bit-identical to the oracle."""
