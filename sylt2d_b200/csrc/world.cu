@@ -1115,21 +1115,22 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
     // — while CTA 0 also takes the (few) cross-region ones along.  One grid barrier at the end.  An interior arbiter without a free interior colour is "promoted": it takes a generic
     // colour in grid-wide rounds behind that barrier (a body touching more than 32 others inside its region; rare).
     // The claims of these rounds are cells of a hash table in shared memory, keyed by (body, colour): two keys that share a cell
-    // only cost the loser another round.  A claim value is unique inside the CTA (round | priority | list position).
+    // only cost the loser another round.  A claim value (round | priority of the arbiter) is unique.
     if (REGIONS && a.color_local && *(volatile int*)&cn->bin_overflow == 0) {
         __shared__ int s_nn;
         const int n_int = bid < a.n_regions ? min(__ldcg(&cn->region_new[bid]), a.bin_cap) : 0;
         const int n_gen = bid == gen_cta ? min(__ldcg(&cn->region_new[a.n_regions]), a.bin_cap) : 0;
         const int n0 = n_int + n_gen;
-        const int HT = scratch_bytes >= 160 * 1024 ? 16384 : 8192;
-        unsigned* ht = (unsigned*)scratch;     // claim cells
+        int HT = 16384;                        // claim cells: as many as fit next to the lists
+        while (HT > 1024 && (size_t)HT * 8 + (size_t)n0 * 28 + 64 > (size_t)scratch_bytes) HT >>= 1;
+        unsigned long long* ht = (unsigned long long*)scratch;
         int4* l_rec = (int4*)(ht + HT);        // my records
         int* l_cur = (int*)(l_rec + n0);       // the records still uncoloured (indices into l_rec), ping-pong
         int* l_next = l_cur + n0;
         int* l_prop = l_next + n0;
         int n = n0, round = 0;
         if (n0 > 0) {
-            for (int k = lt; k < HT; k += T) ht[k] = 0xffffffffu;
+            for (int k = lt; k < HT; k += T) ht[k] = ~0ull;
             for (int k = lt; k < n0; k += T) {
                 l_rec[k] = __ldcg(&a.unc_bin[(size_t)(k < n_int ? bid : a.n_regions) * a.bin_cap + (k < n_int ? k : k - n_int)]);
                 l_cur[k] = k;
@@ -1137,9 +1138,11 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
             __syncthreads();
         }
         cstamp();
-        auto cell = [&](int body, int c) -> unsigned* { return &ht[hash_u32((unsigned)body * 128u + (unsigned)c) & (unsigned)(HT - 1)]; };
-        auto local_val = [&](int e, int q, int rnd) -> unsigned {
-            return ((unsigned)(~rnd & 0x3f) << 26) | ((fmix32((unsigned)e * 2654435761u + (unsigned)rnd) & 0x1fffu) << 13) | (unsigned)q;
+        auto cell = [&](int body, int c) -> unsigned long long* { return &ht[hash_u32((unsigned)body * 128u + (unsigned)c) & (unsigned)(HT - 1)]; };
+        // (later rounds claim with smaller values, so the table is never cleared; fmix32 is a bijection: the value is unique per
+        // arbiter and does not depend on the order in which k_build filled the bin — the colours are reproducible run to run)
+        auto local_val = [&](int e, int rnd) -> unsigned long long {
+            return ((unsigned long long)(unsigned)(~rnd) << 32) | fmix32((unsigned)e * 2654435761u + (unsigned)rnd);
         };
         for (; n > 0 && round < 60; round++) {
             if (lt == 0) s_nn = 0;
@@ -1157,7 +1160,7 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
                         const int c = pick(rec[u], m[u], true);
                         l_prop[q[u]] = c;
                         if (c >= 0) {
-                            const unsigned val = local_val(rec[u].x, q[u], round);
+                            const unsigned long long val = local_val(rec[u].x, round);
                             if (!(rec[u].y & UNC_STATIC)) atomicMin(cell(rec[u].y, c), val);
                             if (!(rec[u].z & UNC_STATIC)) atomicMin(cell(rec[u].z, c), val);
                         } else if (c == -2) {
@@ -1171,7 +1174,7 @@ __device__ __forceinline__ bool color_new_arbiters(const SolveArgs& a, Counters*
                 const int q = l_cur[k], c = l_prop[q];
                 if (c < 0) continue;
                 const int4 rec = l_rec[q];
-                const unsigned val = local_val(rec.x, q, round);
+                const unsigned long long val = local_val(rec.x, round);
                 const bool win = ((rec.y & UNC_STATIC) || *cell(rec.y, c) == val) && ((rec.z & UNC_STATIC) || *cell(rec.z, c) == val);
                 if (win) finalize(rec, c);
                 else l_next[atomicAdd(&s_nn, 1)] = q;

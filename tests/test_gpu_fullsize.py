@@ -141,6 +141,27 @@ def test_config3_100k_across_region_recuts_bit_exact(monkeypatch):
     assert ga.shape[0] > 50000 and (ga["color"] < 32).any() and (ga["color"] >= 32).any()  # the region solver ran: both colour classes
 
 
+def test_large_world_is_reproducible_run_to_run():
+    """Two fresh worlds stepped through the same 100k-body scene (falling phase, thousands of new arbiters per step coloured per
+    region, a region re-cut) end in bit-identical states with identical colours: nothing in the step depends on the order in which
+    threads happen to run (atomics hand out list positions, never priorities)."""
+    from sylt2d_b200 import World
+    sc = scenes.box_drop(100000, seed=42, iterations=10)
+    res = []
+    for _ in range(2):
+        w = World(sc.gravity, sc.iterations, device=0)
+        w.load_scene(sc)
+        w.step_n(sc.dt, 140)
+        ga, gc = w.get_arbiters()
+        res.append((w.get_bodies(), ga, gc))
+    (b0, a0, c0), (b1, a1, c1) = res
+    for f in b0.dtype.names:
+        assert np.array_equal(b0[f].view(np.uint32) if b0[f].dtype == np.float32 else b0[f], b1[f].view(np.uint32) if b1[f].dtype == np.float32 else b1[f]), f
+    assert a0.shape == a1.shape and a0.tobytes() == a1.tobytes()
+    assert c0.tobytes() == c1.tobytes()
+    assert a0.shape[0] > 50000
+
+
 @pytest.mark.parametrize("regions", ["0", "1", "2"])
 def test_large_world_both_solvers_bit_exact(monkeypatch, regions):
     """The same 20k-body world under k_solve only (0), the default choice (1) and k_solve_regions forced (2)."""
