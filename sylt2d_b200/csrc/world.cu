@@ -170,9 +170,11 @@ constexpr int PAIR_TILE = 256;   // candidates per tile of k_narrow / k_build
 struct GridParams {
     float cell;
     int mask;  // buckets - 1
+    float inv_cell;
 };
-__device__ __forceinline__ int cell_coord(float x, float cell) {
-    float q = floorf(x / cell);
+// (any monotone function of x works, as long as the bodies are binned and searched with the same one: a multiplication, not a division)
+__device__ __forceinline__ int cell_coord(float x, float inv_cell) {
+    float q = floorf(x * inv_cell);
     q = fminf(fmaxf(q, -1.0e9f), 1.0e9f);
     return (int)q;
 }
@@ -255,8 +257,8 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const floa
     aabb[i] = make_float4(minx, miny, maxx, maxy);
     int cx = 0, cy = 0;
     if (!(fl & FLAG_LARGE)) {
-        cx = cell_coord(0.5f * (minx + maxx), gp.cell);
-        cy = cell_coord(0.5f * (miny + maxy), gp.cell);
+        cx = cell_coord(0.5f * (minx + maxx), gp.inv_cell);
+        cy = cell_coord(0.5f * (miny + maxy), gp.inv_cell);
         int h = cell_hash(cx, cy, gp.mask, group_of(fl));
         rank[i] = atomicAdd(&cell_count[h], 1);
     }
@@ -346,8 +348,8 @@ __device__ __forceinline__ void row_search(int i, int B, float4 my, int4 ci, con
     const int* large = large_all + large_start[grp];                       // the large bodies of this body's group
     const int n_large = large_start[grp + 1] - large_start[grp];
     if (!(ci.z & FLAG_LARGE)) {
-        int x0 = cell_coord(my.x - 0.5f * gp.cell, gp.cell), x1 = cell_coord(my.z + 0.5f * gp.cell, gp.cell);
-        int y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell), y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
+        int x0 = cell_coord(my.x - 0.5f * gp.cell, gp.inv_cell), x1 = cell_coord(my.z + 0.5f * gp.cell, gp.inv_cell);
+        int y0 = cell_coord(my.y - 0.5f * gp.cell, gp.inv_cell), y1 = cell_coord(my.w + 0.5f * gp.cell, gp.inv_cell);
         if (x1 - x0 <= 2 && y1 - y0 <= 2) {
             // the usual 3x3 block: fetch all bucket ranges first (independent loads), then stream the entries
             int k0[9], k1[9];
@@ -446,8 +448,8 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     int x0 = 0, x1 = 0, y0 = 0, y1 = 0;
     bool fast = false;
     if (!(ci.z & FLAG_LARGE)) {
-        x0 = cell_coord(my.x - 0.5f * gp.cell, gp.cell); x1 = cell_coord(my.z + 0.5f * gp.cell, gp.cell);
-        y0 = cell_coord(my.y - 0.5f * gp.cell, gp.cell); y1 = cell_coord(my.w + 0.5f * gp.cell, gp.cell);
+        x0 = cell_coord(my.x - 0.5f * gp.cell, gp.inv_cell); x1 = cell_coord(my.z + 0.5f * gp.cell, gp.inv_cell);
+        y0 = cell_coord(my.y - 0.5f * gp.cell, gp.inv_cell); y1 = cell_coord(my.w + 0.5f * gp.cell, gp.inv_cell);
         fast = x1 - x0 <= 2 && y1 - y0 <= 2;
     }
     if (!fast && !(ci.z & FLAG_LARGE) && (long long)(x1 - x0 + 1) * (long long)(y1 - y0 + 1) > WIDE_WINDOW) {
@@ -515,9 +517,12 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     int found = 0;
     for (int base = 0; base < total; base += LPB) {
         const int e = base + lane;
-        int seg = 0;  // the segment entry e belongs to: the number of segments that end at or before e
+        int seg = 0;  // the segment entry e belongs to: the number of segments (of the first nine) that end at or before e — the ends ascend
 #pragma unroll
-        for (int q = 0; q < 9; q++) seg += e >= __shfl_sync(gmask, seg_end, q, LPB);
+        for (int st = 8; st >= 1; st >>= 1) {
+            const int v = __shfl_sync(gmask, seg_end, min(seg + st - 1, 8), LPB);
+            if (seg + st <= 9 && e >= v) seg += st;
+        }
         const int s_end = __shfl_sync(gmask, seg_end, seg, LPB), s_n = __shfl_sync(gmask, seg_n, seg, LPB), s_k0 = __shfl_sync(gmask, seg_k0, seg, LPB);
         bool hit = false;
         int partner = 0;
@@ -2584,7 +2589,7 @@ struct SyltWorld {
     bool any_poly = false;
     int max_poly_verts = 0;  // largest polygon of the world: picks the tier (8 / 16 / 32 vertices) of the narrow phase
     int n_large = 0;
-    GridParams gp{1.0f, 1023};
+    GridParams gp{1.0f, 1023, 1.0f};
     int buckets = 1024;
 
     // device state
@@ -2835,6 +2840,7 @@ int flush(SyltWorld* w) {
         while ((size_t)buckets < 2 * B && buckets < CELL_TILE * MAX_CELL_TILES) buckets <<= 1;  // (beyond 2 M bodies the buckets fill up: still correct, slower)
         w->buckets = buckets;
         w->gp.cell = cell;
+        w->gp.inv_cell = 1.0f / cell;
         w->gp.mask = buckets - 1;
         if ((size_t)buckets + 1 > w->cell_count.cap) w->cells_clean = false;
         SYLT_CUDA(w->cell_count.ensure((size_t)buckets + 1));
