@@ -879,7 +879,7 @@ struct SolveArgs {
     const int *region_of, *lidx, *reg_start, *reg_bodies;  // body -> region, body -> index inside its region, CSR of the regions
     int n_regions, smem_bytes;                             // dynamic shared memory of k_solve_regions
     const int4* srec;                                      // 2 per arbiter: (b1 | flags, b2 | flags, region << 16 | local index of b1, of b2) (contacts, first contact, friction, -)
-    int2 *gadj, *cone_buf;                                 // per body: its generic arbiters (arbiter, owner region | colour << 16); per CTA: ghost arbiters (arbiter, colour)
+    int2* gadj;                                            // per body: its generic arbiters (arbiter, owner region | colour << 16), indexed by the colour bit
     ulonglong2* xrec;                                      // export planes (one per pass) of versioned boundary-body velocities
     unsigned step_tag, step_serial;
     int probe_cta;                                         // diagnostics: the CTA whose set-up phases are stamped
@@ -1664,7 +1664,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     int* h_bval = h_body + HASH_CAP;
     int* t_gb = h_arb - GB_MAX;                           // ghost bodies in discovery order
     int2* t_own = (int2*)t_gb - OWN_MAX;                  // (arbiter, colour) of the arbiters this region owns
-    const unsigned char* scratch_lo = (const unsigned char*)t_own;
+    int2* ghosts = t_own - CONE_CAP;                      // ghost arbiters of this CTA (arbiter, colour), in discovery order
+    const unsigned char* scratch_lo = (const unsigned char*)ghosts;
 
     int tq_ = 32;
     auto tstamp = [&]() { if (a.dbg && bid == a.probe_cta && lt == 0 && tq_ < 48) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[tq_++] = t; } };
@@ -1675,7 +1676,6 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     // k_build and by the colouring; the rows and the colours of other CTAs' arbiters are visible behind the grid barrier)
     // The part of the set-up that needs no colours — the tables, the region's bodies, the list of its own arbiters — runs where the CTA
     // would otherwise wait for the cross-region colours.  (The rows of its own bodies come straight from the candidate rows.)
-    int2* ghosts = a.cone_buf + (size_t)bid * CONE_CAP;  // ghost arbiters of this CTA (arbiter, colour), in discovery order
     auto arb_insert = [&](int f) -> bool {  // true: f is new
         unsigned h = hash_u32((unsigned)f) & (HASH_CAP - 1);
         for (int probe = 0; probe < HASH_CAP; probe++) {
@@ -1844,7 +1844,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         __syncthreads();
         if (f1 == f0) break;
         for (int g = f0 + lt; g < f1; g += T) {
-            const int2 f = __ldcg(&ghosts[g]);
+            const int2 f = ghosts[g];
             const Rec32 r = ld256(&a.srec[2 * (size_t)f.x]);
             adopt(f.y, r.a, r.b.x);
         }
@@ -1960,7 +1960,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
             const int k = k0 + u * T;
             e[u] = -1; c[u] = 0;
             if (k < nown) { const int2 ec = t_own[k]; if (ec.y >= 0) { e[u] = ec.x; c[u] = ec.y; } }
-            else if (k < nall) { const int2 f = __ldcg(&ghosts[k - nown]); e[u] = f.x; c[u] = f.y; }
+            else if (k < nall) { const int2 f = ghosts[k - nown]; e[u] = f.x; c[u] = f.y; }
         }
 #pragma unroll
         for (int u = 0; u < SB; u++)
@@ -2640,7 +2640,7 @@ struct SyltWorld {
     // share of cross-region arbiters has grown
     DBuf<int> region_of, lidx, reg_start, reg_bodies, sort_keys;
     DBuf<RecutScratch> recut;
-    DBuf<int2> gadj, cone_buf;
+    DBuf<int2> gadj;
     DBuf<ulonglong2> xrec;
     unsigned step_tag = 0, step_serial = 0;
     int regions_mode = 1;            // SYLT_REGIONS: 0 = never (k_solve only), 1 = joint-free worlds of at least regions_min_bodies (default), 2 = always
@@ -2951,7 +2951,7 @@ int repartition(SyltWorld* w) {
     if (B == 0 || G < 1 || !w->hj.empty() || w->iterations + 1 > (uint32_t)MAX_PASSES) on = false;  // joints: k_solve
     // a region may hold twice the average number of bodies (k_rebalance); 40 bytes each must leave room for the set-up scratch and the slots
     const size_t maxper = 2 * ((B + (size_t)G - 1) / (size_t)std::max(G, 1)) + 16;
-    if (on && maxper * 40 + ((size_t)3 * HASH_CAP_1 * 4 + (size_t)GB_MAX_1 * 4 + (size_t)OWN_MAX_1 * 8 + 32768) / (size_t)w->regions_per_sm > w->solve_budget) on = false;
+    if (on && maxper * 40 + ((size_t)3 * HASH_CAP_1 * 4 + (size_t)GB_MAX_1 * 4 + (size_t)OWN_MAX_1 * 8 + (size_t)CONE_CAP_1 * 8 + 32768) / (size_t)w->regions_per_sm > w->solve_budget) on = false;
     if (on != was_on) w->recolor_all = true;  // the colour ranges mean something else
     w->regions_on = on;
     if (!on) return SYLT_OK;
@@ -2963,7 +2963,6 @@ int repartition(SyltWorld* w) {
     SYLT_CUDA(w->recut.ensure(1));
     SYLT_CUDA(w->reg_start.ensure((size_t)G + 1));
     SYLT_CUDA(w->gadj.ensure(B * (size_t)GADJ));
-    SYLT_CUDA(w->cone_buf.ensure((size_t)w->regions_blocks * (CONE_CAP_1 / w->regions_per_sm)));
     SYLT_CUDA(w->unc_bin.ensure((size_t)(G + 1) * (size_t)unc_bin_cap(w)));
     SYLT_CUDA(w->unc_bin_idx.ensure((size_t)(G + 1) * (size_t)unc_bin_cap(w)));
     {   // export planes: a record is valid when its tag matches (step_tag, pass); fresh memory must not hold a look-alike
@@ -3100,7 +3099,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
     if (w->regions_on) {
         a.region_of = w->region_of.p; a.lidx = w->lidx.p; a.reg_start = w->reg_start.p; a.reg_bodies = w->reg_bodies.p;
         a.n_regions = w->n_regions; a.smem_bytes = (int)w->solve_budget;
-        a.gadj = w->gadj.p; a.cone_buf = w->cone_buf.p; a.xrec = w->xrec.p; a.srec = w->srec.p;
+        a.gadj = w->gadj.p; a.xrec = w->xrec.p; a.srec = w->srec.p;
         if (++w->step_tag > 0xffff0u) {  // 20-bit step tags (+ 12 bits of pass): start over with clean planes
             SYLT_CUDA(cudaMemsetAsync(w->xrec.p, 0, w->xrec.cap * sizeof(ulonglong2), st));
             w->step_tag = 1;
@@ -3428,7 +3427,7 @@ static void free_all(SyltWorld* w) {
     }
     w->jbodies.release(); w->jla.release(); w->jr.release(); w->jm.release(); w->jparam.release(); w->jp.release(); w->jbias.release();
     w->jorder.release(); w->jcolor_start.release();
-    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release(); w->sort_keys.release(); w->recut.release(); w->gadj.release(); w->cone_buf.release(); w->xrec.release();
+    w->region_of.release(); w->lidx.release(); w->reg_start.release(); w->reg_bodies.release(); w->sort_keys.release(); w->recut.release(); w->gadj.release(); w->xrec.release();
 }
 
 int sylt_world_destroy(SyltWorld* w) {
