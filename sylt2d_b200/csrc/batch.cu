@@ -930,7 +930,8 @@ struct SyltBatch {
     DBuf<SlotExport> exp_slots;
     DBuf<StatsOut> stats;
     DBuf<SyltBodyState> stage;
-    static constexpr int NS = 4;
+    static constexpr int NS = 4, MAX_CHUNKS = 64;
+    cudaEvent_t pipe_ev[2 * MAX_CHUNKS] = {};
     cudaStream_t xs[NS] = {nullptr, nullptr, nullptr, nullptr};  // copy/compute pipeline of sylt_batch_step_host
 };
 
@@ -1181,6 +1182,8 @@ int sylt_batch_destroy(SyltBatch* b) {
     if (b->stream) cudaStreamDestroy(b->stream);
     for (int k = 0; k < SyltBatch::NS; k++)
         if (b->xs[k]) cudaStreamDestroy(b->xs[k]);
+    for (cudaEvent_t ev : b->pipe_ev)
+        if (ev) cudaEventDestroy(ev);
     delete b;
     return SYLT_OK;
 }
@@ -1257,14 +1260,33 @@ static int step_host_impl(SyltBatch* b, float dt, int32_t n, const float* in, fl
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, b->device);
         b->wave = std::max(1, per_sm) * std::max(1, sms);
     }
-    const int chunks = std::max(1, std::min(16, W / (2 * b->wave)));
+    static const int env_chunks = getenv("SYLT_BATCH_CHUNKS") ? atoi(getenv("SYLT_BATCH_CHUNKS")) : 0;
+    static const int env_mode = getenv("SYLT_BATCH_PIPE") ? atoi(getenv("SYLT_BATCH_PIPE")) : 1;  // 0: every chunk on one of four streams (upload, step, download in stream order)
+    const int chunks = std::max(1, std::min(env_chunks > 0 ? std::min(env_chunks, SyltBatch::MAX_CHUNKS) : 16, W / (2 * b->wave)));
     const int per = (W + chunks - 1) / chunks;
     for (int c = 0; c < chunks; c++) {
         const int w0 = std::min(W, c * per), w1 = std::min(W, w0 + per);
         if (w1 <= w0) continue;
-        cudaStream_t st = b->xs[c % SyltBatch::NS];
         const int o0 = b->h_body_off[(size_t)w0], cnt = b->h_body_off[(size_t)w1] - o0;
         float* sg = stage + (size_t)o0 * fpb;
+        if (env_mode == 1) {  // three-stage pipeline: one upload stream, two compute streams, one download stream, events between them
+            cudaStream_t up = b->xs[0], down = b->xs[1], cs = b->xs[2 + (c & 1)];
+            if (!b->pipe_ev[2 * c]) { SYLT_CUDA(cudaEventCreateWithFlags(&b->pipe_ev[2 * c], cudaEventDisableTiming)); SYLT_CUDA(cudaEventCreateWithFlags(&b->pipe_ev[2 * c + 1], cudaEventDisableTiming)); }
+            if (in && cnt) {
+                SYLT_CUDA(cudaMemcpyAsync(sg, in + (size_t)o0 * fpb, (size_t)cnt * fpb * sizeof(float), cudaMemcpyHostToDevice, up));
+                SYLT_CUDA(cudaEventRecord(b->pipe_ev[2 * c], up));
+                SYLT_CUDA(cudaStreamWaitEvent(cs, b->pipe_ev[2 * c], 0));
+            }
+            int e = batch_enqueue(b, dt, n, w0, w1, cs, (in && cnt) ? stage : nullptr, (out && cnt) ? stage : nullptr, fpb);
+            if (e) return e;
+            if (out && cnt) {
+                SYLT_CUDA(cudaEventRecord(b->pipe_ev[2 * c + 1], cs));
+                SYLT_CUDA(cudaStreamWaitEvent(down, b->pipe_ev[2 * c + 1], 0));
+                SYLT_CUDA(cudaMemcpyAsync(out + (size_t)o0 * fpb, sg, (size_t)cnt * fpb * sizeof(float), cudaMemcpyDeviceToHost, down));
+            }
+            continue;
+        }
+        cudaStream_t st = b->xs[c % SyltBatch::NS];
         if (in && cnt) SYLT_CUDA(cudaMemcpyAsync(sg, in + (size_t)o0 * fpb, (size_t)cnt * fpb * sizeof(float), cudaMemcpyHostToDevice, st));
         // the step kernel itself reads the host-format records and writes them back (n == 0: zero steps, i.e. a pure conversion)
         int e = batch_enqueue(b, dt, n, w0, w1, st, (in && cnt) ? stage : nullptr, (out && cnt) ? stage : nullptr, fpb);
