@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(256) k_prepare(int B, float4* pose, const floa
 // contiguous 32-byte entries instead of chasing body indices
 // Counting-sort offsets of the grid without a device-wide scan: k_cells_local leaves, per tile of CELL_TILE buckets, the exclusive
 // offsets inside the tile and the tile's total; k_fill_cells adds up the (few hundred) totals in its prologue.
-constexpr int CELL_TILE = 2048, MAX_CELL_TILES = 2048;  // (worlds with more buckets keep the look-back scan)
+constexpr int CELL_TILE = 2048, MAX_CELL_TILES = 2048;  // (the bucket count stops growing at CELL_TILE * MAX_CELL_TILES)
 __global__ void __launch_bounds__(256) k_cells_local(int buckets, int* cell_count, int* cell_local, int* tile_tot) {
     __shared__ int sh[34];
     pdl_wait();
@@ -1600,7 +1600,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
 
 // ------------------------------------------------------------------ region solver
 // The same sequential sweep as k_solve — passes x colours ascending — with a different execution plan.
-// Bodies are partitioned into compact spatial regions (k_resort + k_rebalance, every `regions_period` steps); region r belongs to CTA r for the
+// Bodies are partitioned into compact spatial regions (k_recut, every `regions_period` steps); region r belongs to CTA r for the
 // whole solve and its body velocities live in that CTA's shared memory.  Arbiters come in two classes (the colour
 // range IS the class, see color_new_arbiters): interior (colour < GEN_BIT: all dynamic bodies in the owner's region)
 // and generic (cross-region pairs).  Interior arbiters of different regions touch disjoint dynamic bodies, so the
@@ -1614,7 +1614,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
 // L2 — and replays the cone in colour order in its own shared memory.  f32 arithmetic is deterministic, so every
 // replica of a generic arbiter computes the same bits; a pass costs ONE L2 hand-off instead of one per generic colour.
 // Only the owner writes an arbiter's contacts back.  Worlds with joints use k_solve.
-constexpr int GADJ = NC;              // per body: its generic arbiters, indexed by the rank of their colour in `used`
+constexpr int GADJ = NC;              // per body: its generic arbiters, indexed by the colour bit (GEN_BIT + k -> entry k)
 constexpr int GHOST_FLAG = 0x40000000;
 }  // namespace
 // table sizes of a region CTA that has an SM to itself (k_solve_regions<PER_SM> divides them by PER_SM)
@@ -1671,7 +1671,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     auto tstamp = [&]() { if (a.dbg && bid == a.probe_cta && lt == 0 && tq_ < 48) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); a.dbg[tq_++] = t; } };
     // a step that already failed in the broad phase (capacity) has holes in its arbiter arrays: nothing to solve, error reported
     if (step_failed(cn)) return;
-    fill_arbiter_rows(a.B, min(*(volatile int*)&cn->n_pairs, a.cap_pairs), a.cand_row_start, a.pscan, a.cur.row_start, tid, nth);  // read after the barrier of 2a
+    fill_arbiter_rows(a.B, min(*(volatile int*)&cn->n_pairs, a.cap_pairs), a.cand_row_start, a.pscan, a.cur.row_start, tid, nth);  // (for the next step's k_build and k_recut; this kernel takes its rows from the candidate rows)
     // (the per-body table of generic arbiters `gadj` — slot = colour bit, entry = (arbiter, owner region | colour << 16) — was written by
     // k_build and by the colouring; the rows and the colours of other CTAs' arbiters are visible behind the grid barrier)
     // The part of the set-up that needs no colours — the tables, the region's bodies, the list of its own arbiters — runs where the CTA
@@ -2940,7 +2940,7 @@ int flush(SyltWorld* w) {
 
 int unc_bin_cap(const SyltWorld* w) { return UNC_BIN_CAP_1 / std::max(w->regions_per_sm, 1); }
 
-// Region solver on / off for the current bodies, and its buffers.  The partition itself (k_resort + k_rebalance) is enqueued
+// Region solver on / off for the current bodies, and its buffers.  The partition itself (k_recut) is enqueued
 // with the next step; nothing here synchronises with the device beyond (re)allocation.
 int repartition(SyltWorld* w) {
     const size_t B = w->hb.size();
@@ -2949,7 +2949,7 @@ int repartition(SyltWorld* w) {
     const int G = std::min(1024, w->regions_count > 0 ? std::min(w->regions_count, w->regions_blocks) : w->regions_blocks);
     bool on = w->regions_mode == 2 || (w->regions_mode == 1 && B >= (size_t)w->regions_min_bodies);
     if (B == 0 || G < 1 || !w->hj.empty() || w->iterations + 1 > (uint32_t)MAX_PASSES) on = false;  // joints: k_solve
-    // a region may hold twice the average number of bodies (k_rebalance); 40 bytes each must leave room for the set-up scratch and the slots
+    // a region may hold twice the average number of bodies (k_recut floors the weights at the average); 40 bytes each must leave room for the set-up scratch and the slots
     const size_t maxper = 2 * ((B + (size_t)G - 1) / (size_t)std::max(G, 1)) + 16;
     if (on && maxper * 40 + ((size_t)3 * HASH_CAP_1 * 4 + (size_t)GB_MAX_1 * 4 + (size_t)OWN_MAX_1 * 8 + (size_t)CONE_CAP_1 * 8 + 32768) / (size_t)w->regions_per_sm > w->solve_budget) on = false;
     if (on != was_on) w->recolor_all = true;  // the colour ranges mean something else
