@@ -820,6 +820,17 @@ def test_region_solver_interior_colours_overflow_into_generic_ones(monkeypatch, 
         assert (ga["color"] < 32).sum() >= 32
 
 
+def test_region_solver_two_ctas_per_sm(monkeypatch):
+    """SYLT_REGION_CTAS_PER_SM=2 (opt-in): two half-size region CTAs per SM — half the threads, half the shared memory, half-size tables
+    and bins; same results."""
+    monkeypatch.setenv("SYLT_REGIONS", "2")
+    monkeypatch.setenv("SYLT_REGION_CTAS_PER_SM", "2")
+    monkeypatch.setenv("SYLT_REGIONS_PERIOD", "3")
+    _run_lockstep(scenes.pyramid(7, 10), 40, check_every=4)
+    w = _lockstep_big(scenes.box_drop(20000, seed=5, iterations=10), 150, 4)
+    assert w.get_stats()["arbiters"] > 10000
+
+
 def test_region_solver_prestep_keeps_the_signs_of_zero_velocities(monkeypatch):
     """With warm starting off every accumulated impulse is zero when Arbiter::pre_step applies it (arbiter.rs:216-223), so the region
     solver computes the contact constants in one flat loop instead of an ordered sweep — unless some velocity is exactly -0.0: subtracting
