@@ -745,10 +745,10 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         if (found >= 0) {
             fr = old.friction[found];  // quirk Q-17: friction fixed at first insertion
             if (keep_colors) color = old.color[found];  // (all dropped when the region solver is switched on or off: the ranges mean something else)
-            if (keep_colors == 2 && color >= 0) {       // the regions were just re-cut: a colour survives if its class does — interior
-                // (all dynamic bodies in the owner's region, colour < GEN_BIT) or generic.  Only arbiters near the new borders change.
-                if ((color < GEN_BIT) != interior_pair) color = -1;
-            }
+            // Region solver: a colour survives if its class does — interior (all dynamic bodies in the owner's region, colour < GEN_BIT)
+            // or generic.  The class of a pair changes when the regions are re-cut (only arbiters near the new borders) and when one
+            // of its bodies is made static or dynamic between steps (set_body_props).
+            if (regions && color >= 0 && (color < GEN_BIT) != interior_pair) color = -1;
             if (warm) {                // quirk Q-2: every new contact inherits old contact 0
                 int oc = old.meta[found].y;
                 float4 c = old.cc[oc];

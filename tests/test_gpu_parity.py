@@ -820,6 +820,32 @@ def test_region_solver_interior_colours_overflow_into_generic_ones(monkeypatch, 
         assert (ga["color"] < 32).sum() >= 32
 
 
+def test_region_solver_body_made_static_and_dynamic_again(monkeypatch):
+    """A body whose inv_mass / inv_moi are zeroed between steps (and restored later) changes the class of its arbiters — an arbiter whose
+    other body lives in another region is interior while the body is static and cross-region once it moves: the colours of such
+    arbiters are dropped instead of kept (an interior colour at a dynamic body of another region would never be exported)."""
+    monkeypatch.setenv("SYLT_REGIONS", "2")
+    monkeypatch.setenv("SYLT_REGIONS_COUNT", "6")
+    sc = scenes.pyramid(8, 10)
+    w, o = _mk(sc)
+    flip = [10, 18, 25, 27]  # boxes of rows 1-4 that touch neither the ground nor each other (a pair of two static bodies is skipped
+    for s in range(50):      # by the broad phase, world.rs:79-81, and the reference then keeps its stale arbiter: DESIGN.md §8)
+        if s in (15, 30):
+            p = w.get_body_props()
+            for i in flip:
+                if s == 15:
+                    p[i, 1], p[i, 3] = 0.0, 0.0          # static (kinematic: keeps its velocity, quirk Q-16)
+                else:
+                    p[i, 1], p[i, 3] = 0.1, 6.0          # dynamic again
+            w.set_body_props(p)
+            o.set_body_props(p)
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+        _assert_states_equal(w.get_bodies(), o.get_bodies(), f"step {s}")
+    _assert_arbiters_equal(w, o)
+
+
 def test_region_solver_two_ctas_per_sm(monkeypatch):
     """SYLT_REGION_CTAS_PER_SM=2 (opt-in): two half-size region CTAs per SM — half the threads, half the shared memory, half-size tables
     and bins; same results."""
