@@ -32,6 +32,7 @@
 #include <algorithm>
 #include <cstdlib>
 #include <mutex>
+#include <thread>
 #include "common.h"
 #include "narrow.cuh"
 #include "solver.cuh"
@@ -2656,6 +2657,8 @@ struct SyltWorld {
     cudaEvent_t kt_ev[16] = {};      // SYLT_KERNEL_TIMING / sylt_world_set_kernel_timing
     int kt_n = 0;
     bool kernel_timing = false, kernel_timing_print = false;
+    void* rb_host = nullptr;         // pinned staging of sylt_world_get_arbiters
+    size_t rb_cap = 0;
     size_t solve_budget = 0;         // dynamic shared memory of one k_solve_regions CTA
     int regions_per_sm = 1, regions_blocks = 0, regions_threads = SOLVE_THREADS;  // SYLT_REGION_CTAS_PER_SM
 
@@ -3414,6 +3417,7 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
 }
 
 static void free_all(SyltWorld* w) {
+    if (w->rb_host) { cudaFreeHost(w->rb_host); w->rb_host = nullptr; w->rb_cap = 0; }
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cell_local.release(); w->tile_tot.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
@@ -3726,46 +3730,80 @@ int sylt_world_get_arbiters(SyltWorld* w, SyltArbiterInfo* arbiters, int32_t arb
         k_fill_sep<<<(Cn + 255) / 256, 256, 0, w->stream>>>(Cn, ab.cin.p, ab.cc.p);
         ab.sep_in_cin = false;
     }
-    std::vector<int2> bodies((size_t)A), meta((size_t)A);
-    std::vector<float> fr((size_t)A);
-    std::vector<int> col((size_t)A);
-    std::vector<float4> ca((size_t)Cn), cb((size_t)Cn), cc((size_t)Cn), cd((size_t)Cn);
-    cudaMemcpyAsync(bodies.data(), ab.bodies.p, (size_t)A * sizeof(int2), cudaMemcpyDeviceToHost, w->stream);
-    cudaMemcpyAsync(meta.data(), ab.meta.p, (size_t)A * sizeof(int2), cudaMemcpyDeviceToHost, w->stream);
-    cudaMemcpyAsync(fr.data(), ab.friction.p, (size_t)A * sizeof(float), cudaMemcpyDeviceToHost, w->stream);
-    cudaMemcpyAsync(col.data(), ab.color.p, (size_t)A * sizeof(int), cudaMemcpyDeviceToHost, w->stream);
-    cudaMemcpyAsync(ca.data(), ab.ca.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
-    cudaMemcpyAsync(cb.data(), ab.cb.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
-    cudaMemcpyAsync(cc.data(), ab.cc.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
-    cudaMemcpyAsync(cd.data(), ab.cd.p, (size_t)Cn * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+    // one pinned staging area (kept and grown by the handle: no page faults, DMA at link speed), the eight arrays behind one another
+    const size_t bytes = (size_t)A * (2 * sizeof(int2) + sizeof(float) + sizeof(int)) + (size_t)Cn * 4 * sizeof(float4) + 8 * 16;
+    if (bytes > w->rb_cap) {
+        if (w->rb_host) cudaFreeHost(w->rb_host);
+        w->rb_host = nullptr; w->rb_cap = 0;
+        if (cudaMallocHost(&w->rb_host, bytes + bytes / 4) != cudaSuccess) { set_last_error("cudaMallocHost (arbiter read-back)"); return -SYLT_ERR_CUDA; }
+        w->rb_cap = bytes + bytes / 4;
+    }
+    unsigned char* hp = (unsigned char*)w->rb_host;
+    auto take = [&](const void* dev, size_t n) {
+        void* h = hp;
+        cudaMemcpyAsync(h, dev, n, cudaMemcpyDeviceToHost, w->stream);
+        hp += (n + 15) & ~(size_t)15;
+        return h;
+    };
+    const int2* bodies = (const int2*)take(ab.bodies.p, (size_t)A * sizeof(int2));
+    const int2* meta = (const int2*)take(ab.meta.p, (size_t)A * sizeof(int2));
+    const float* fr = (const float*)take(ab.friction.p, (size_t)A * sizeof(float));
+    const int* col = (const int*)take(ab.color.p, (size_t)A * sizeof(int));
+    const float4* ca = (const float4*)take(ab.ca.p, (size_t)Cn * sizeof(float4));
+    const float4* cb = (const float4*)take(ab.cb.p, (size_t)Cn * sizeof(float4));
+    const float4* cc = (const float4*)take(ab.cc.p, (size_t)Cn * sizeof(float4));
+    const float4* cd = (const float4*)take(ab.cd.p, (size_t)Cn * sizeof(float4));
     cudaError_t e = cudaStreamSynchronize(w->stream);
     if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -SYLT_ERR_CUDA; }
-    std::vector<int> idx((size_t)A);
-    for (int i = 0; i < A; i++) idx[(size_t)i] = i;
-    std::sort(idx.begin(), idx.end(), [&](int x, int y) {
-        const int2 &a = bodies[(size_t)x], &b = bodies[(size_t)y];
+    // key order (ArbiterKey: id pair = body pair); the device order (owner body, partner) already is that order unless small-large
+    // pairs are around: sort only then
+    // key order (ArbiterKey: id pair = body pair).  The device order is (owner body, partner): already key order except for the pairs
+    // of a small body with a large one of lower index (the small body owns those).  So: the ascending run that the device order
+    // contains, the few stragglers sorted, and a merge — not a sort of everything.
+    std::vector<int> idx((size_t)A), run, rest;
+    std::vector<int> coff((size_t)A + 1);
+    run.reserve((size_t)A);
+    auto less = [&](int x, int y) {
+        const int2 &a = bodies[x], &b = bodies[y];
         return a.x != b.x ? a.x < b.x : a.y < b.y;
-    });
+    };
+    for (int i = 0; i < A; i++) {
+        if (run.empty() || !less(i, run.back())) run.push_back(i);
+        else rest.push_back(i);
+    }
+    std::sort(rest.begin(), rest.end(), less);
+    std::merge(run.begin(), run.end(), rest.begin(), rest.end(), idx.begin(), less);
+    coff[0] = 0;
+    for (int k = 0; k < A; k++) coff[(size_t)k + 1] = coff[(size_t)k] + meta[idx[(size_t)k]].x;
     const bool zero_r = !w->last_was_step || w->last_iterations == 0;  // r1/r2 are only stored by apply_impulse (arbiter.rs:236-237)
-    int co = 0;
-    for (int k = 0; k < A; k++) {
-        int a = idx[(size_t)k];
-        SyltArbiterInfo& o = arbiters[k];
-        o.body1 = bodies[(size_t)a].x; o.body2 = bodies[(size_t)a].y;
-        o.id1 = w->hb[(size_t)o.body1].id; o.id2 = w->hb[(size_t)o.body2].id;
-        o.friction = fr[(size_t)a]; o.num_contacts = meta[(size_t)a].x; o.contact_offset = co; o.color = col[(size_t)a];
-        for (int q = 0; q < meta[(size_t)a].x; q++) {
-            size_t ci = (size_t)(meta[(size_t)a].y + q);
-            SyltContact& c = contacts[co++];
-            c.px = cd[ci].x; c.py = cd[ci].y; c.nx = ca[ci].x; c.ny = ca[ci].y;
-            c.r1x = zero_r ? 0.0f : ca[ci].z; c.r1y = zero_r ? 0.0f : ca[ci].w; c.r2x = zero_r ? 0.0f : cb[ci].x; c.r2y = zero_r ? 0.0f : cb[ci].y;
-            c.separation = cc[ci].w; c.pn = cc[ci].y; c.pt = cc[ci].z; c.pnb = cd[ci].z;
-            c.mass_normal = cb[ci].z; c.mass_tangent = cb[ci].w; c.bias = cc[ci].x;
-            uint32_t ft;
-            memcpy(&ft, &cd[ci].w, 4);
-            c.in_edge_1 = ft & 0xff; c.out_edge_1 = (ft >> 8) & 0xff; c.in_edge_2 = (ft >> 16) & 0xff; c.out_edge_2 = (ft >> 24) & 0xff;
-            c.feature_value = 0;
+    auto fill = [&](int k0, int k1) {
+        for (int k = k0; k < k1; k++) {
+            const int a = idx[(size_t)k];
+            SyltArbiterInfo& o = arbiters[k];
+            o.body1 = bodies[a].x; o.body2 = bodies[a].y;
+            o.id1 = w->hb[(size_t)o.body1].id; o.id2 = w->hb[(size_t)o.body2].id;
+            o.friction = fr[a]; o.num_contacts = meta[a].x; o.contact_offset = coff[(size_t)k]; o.color = col[a];
+            for (int q = 0; q < meta[a].x; q++) {
+                const size_t ci = (size_t)(meta[a].y + q);
+                SyltContact& c = contacts[coff[(size_t)k] + q];
+                c.px = cd[ci].x; c.py = cd[ci].y; c.nx = ca[ci].x; c.ny = ca[ci].y;
+                c.r1x = zero_r ? 0.0f : ca[ci].z; c.r1y = zero_r ? 0.0f : ca[ci].w; c.r2x = zero_r ? 0.0f : cb[ci].x; c.r2y = zero_r ? 0.0f : cb[ci].y;
+                c.separation = cc[ci].w; c.pn = cc[ci].y; c.pt = cc[ci].z; c.pnb = cd[ci].z;
+                c.mass_normal = cb[ci].z; c.mass_tangent = cb[ci].w; c.bias = cc[ci].x;
+                uint32_t ft;
+                memcpy(&ft, &cd[ci].w, 4);
+                c.in_edge_1 = ft & 0xff; c.out_edge_1 = (ft >> 8) & 0xff; c.in_edge_2 = (ft >> 16) & 0xff; c.out_edge_2 = (ft >> 24) & 0xff;
+                c.feature_value = 0;
+            }
         }
+    };
+    const int nthreads = A >= 32768 ? 8 : 1;  // (a 100k-body world has ~230k arbiters: the assembly is worth a few host threads)
+    if (nthreads == 1) {
+        fill(0, A);
+    } else {
+        std::vector<std::thread> th;
+        for (int t = 0; t < nthreads; t++) th.emplace_back(fill, (int)((long long)A * t / nthreads), (int)((long long)A * (t + 1) / nthreads));
+        for (auto& t : th) t.join();
     }
     return A;
 }
