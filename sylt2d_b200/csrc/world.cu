@@ -2516,6 +2516,15 @@ __global__ void k_fill_sep(int n, const float4* cin, float4* cc) {
     if (i < n) cc[i].w = cin[2 * (size_t)i + 1].x;
 }
 
+// SyltBodyState records (x, y, rotation, vx, vy, angular_velocity, fx, fy, torque) for sylt_world_get_bodies
+__global__ void k_pack_states(int n, const float4* pose, const float4* vel, const float4* force, float* out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 p = pose[i], v = vel[i], f = force[i];
+    float* o = out + 9 * (size_t)i;
+    o[0] = p.x; o[1] = p.y; o[2] = p.z; o[3] = v.x; o[4] = v.y; o[5] = v.z; o[6] = f.x; o[7] = f.y; o[8] = f.z;
+}
+
 __global__ void k_copy_flags(int B, const int* src, int* dst, const Counters* cn) {
     if (step_failed(cn)) return;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -2659,6 +2668,9 @@ struct SyltWorld {
     bool kernel_timing = false, kernel_timing_print = false;
     void* rb_host = nullptr;         // pinned staging of sylt_world_get_arbiters
     size_t rb_cap = 0;
+    void* sb_host = nullptr;         // ... and of sylt_world_get_bodies (packed on the device first)
+    size_t sb_cap = 0;
+    DBuf<float> pack_dev;
     size_t solve_budget = 0;         // dynamic shared memory of one k_solve_regions CTA
     int regions_per_sm = 1, regions_blocks = 0, regions_threads = SOLVE_THREADS;  // SYLT_REGION_CTAS_PER_SM
 
@@ -3418,6 +3430,8 @@ int sylt_world_create(float gx, float gy, uint32_t iterations, int device, SyltW
 
 static void free_all(SyltWorld* w) {
     if (w->rb_host) { cudaFreeHost(w->rb_host); w->rb_host = nullptr; w->rb_cap = 0; }
+    if (w->sb_host) { cudaFreeHost(w->sb_host); w->sb_host = nullptr; w->sb_cap = 0; }
+    w->pack_dev.release();
     w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cell_local.release(); w->tile_tot.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
@@ -3673,17 +3687,20 @@ int sylt_world_get_bodies(SyltWorld* w, SyltBodyState* out, int32_t cap) {
     int nd = std::min(n, w->uploaded);
     if (nd > 0) {
         if (cudaSetDevice(w->device) != cudaSuccess) return -SYLT_ERR_CUDA;
-        std::vector<float4> p((size_t)nd), v((size_t)nd), f((size_t)nd);
-        cudaError_t e = cudaMemcpyAsync(p.data(), w->pose.p, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(v.data(), w->vel.p, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(f.data(), w->force.p, (size_t)nd * sizeof(float4), cudaMemcpyDeviceToHost, w->stream);
+        // packed on the device (9 floats per body), one copy through the handle's pinned staging area
+        const size_t bytes = (size_t)nd * sizeof(SyltBodyState);
+        if (w->pack_dev.ensure((size_t)nd * 9) != cudaSuccess) return -SYLT_ERR_CUDA;
+        if (bytes > w->sb_cap) {
+            if (w->sb_host) cudaFreeHost(w->sb_host);
+            w->sb_host = nullptr; w->sb_cap = 0;
+            if (cudaMallocHost(&w->sb_host, bytes + bytes / 4 + 64) != cudaSuccess) { set_last_error("cudaMallocHost (body read-back)"); return -SYLT_ERR_CUDA; }
+            w->sb_cap = bytes + bytes / 4 + 64;
+        }
+        k_pack_states<<<(nd + 255) / 256, 256, 0, w->stream>>>(nd, w->pose.p, w->vel.p, w->force.p, w->pack_dev.p);
+        cudaError_t e = cudaMemcpyAsync(w->sb_host, w->pack_dev.p, bytes, cudaMemcpyDeviceToHost, w->stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(w->stream);
         if (e != cudaSuccess) { set_last_error(cudaGetErrorString(e)); return -SYLT_ERR_CUDA; }
-        for (int i = 0; i < nd; i++) {
-            SyltBodyState s = {p[(size_t)i].x, p[(size_t)i].y, p[(size_t)i].z, v[(size_t)i].x, v[(size_t)i].y, v[(size_t)i].z,
-                               f[(size_t)i].x, f[(size_t)i].y, f[(size_t)i].z};
-            out[i] = s;
-        }
+        memcpy(out, w->sb_host, bytes);
     }
     for (int i = nd; i < n; i++) out[i] = w->pending[(size_t)(i - w->uploaded)];
     return n;
