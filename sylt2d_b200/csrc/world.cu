@@ -2655,6 +2655,7 @@ struct SyltWorld {
     unsigned step_tag = 0, step_serial = 0;
     int regions_mode = 1;            // SYLT_REGIONS: 0 = never (k_solve only), 1 = joint-free worlds of at least regions_min_bodies (default), 2 = always
     int regions_min_bodies = 1000, regions_count = 0, regions_period = 128;
+    int regions_mode_saved = 1, regions_suspended_at = 0;  // region solver suspended (a region did not fit) at this many contacts
     bool color_local = true;         // SYLT_COLOR_LOCAL=0: new arbiters are coloured by the grid-wide rounds only (diagnostics)
     bool regions_on = false;         // the partition on the device is valid for the current bodies
     bool part_dirty = true;          // bodies were added / the mode may have changed
@@ -3259,6 +3260,13 @@ int finish(SyltWorld* w) {
         int total = 0;
         for (const auto& sg : w->segs) total += sg.n;
         if (err == SYLT_OK) {
+            if (w->regions_suspended_at > 0 && w->last.n_con > 0 && (int64_t)w->last.n_con * 4 < (int64_t)w->regions_suspended_at * 3) {
+                // a world that fell back to k_solve because a region did not fit: three quarters of the contacts it had then — try again
+                // (the next failure suspends it at the lower count, so the retries die out)
+                w->regions_mode = w->regions_mode_saved;
+                w->regions_suspended_at = 0;
+                w->part_dirty = true;
+            }
             w->n_arb_valid = (int)std::min<int64_t>(w->last.n_arb, w->cap_arb);
             w->n_con_valid = (int)std::min<int64_t>(w->last.n_con, w->cap_con);
             w->segs.clear();
@@ -3295,7 +3303,10 @@ int finish(SyltWorld* w) {
         if (w->last.n_pairs > w->cap_pairs) { w->grow_pairs = std::max<int64_t>(2 * w->cap_pairs, (int64_t)w->last.n_pairs * 3 / 2); grown = true; }
         if (w->last.n_arb > w->cap_arb) { w->grow_arb = std::max<int64_t>(2 * w->cap_arb, (int64_t)w->last.n_arb * 3 / 2); grown = true; }
         if (w->last.n_con > w->cap_con) { w->grow_con = std::max<int64_t>(2 * w->cap_con, (int64_t)w->last.n_con * 3 / 2); grown = true; }
-        if (w->last_regions && w->last.why != 0) {  // a region outgrew k_solve_regions' tables: this world goes on with k_solve
+        if (w->last_regions && w->last.why != 0) {  // a region outgrew k_solve_regions' tables: this world goes on with k_solve —
+            // until its contact count has come down again (a pile is densest while it lands): see the success path above
+            w->regions_mode_saved = w->regions_mode;
+            w->regions_suspended_at = std::max(1, w->last.n_con);
             w->regions_mode = 0;
             w->part_dirty = true;
             grown = true;
