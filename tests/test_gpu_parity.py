@@ -846,6 +846,27 @@ def test_region_solver_body_made_static_and_dynamic_again(monkeypatch):
     _assert_arbiters_equal(w, o)
 
 
+def test_kernel_timing_api_reports_the_launch_chain():
+    """sylt_world_set_kernel_timing / get_kernel_times (diagnostics used by bench.py): eight launches per step, positive durations;
+    switching it off again leaves the results untouched."""
+    sc = scenes.pyramid(10, 10)
+    w, o = _mk(sc)
+    w.set_kernel_timing(True)
+    for _ in range(5):
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+    kt = w.kernel_times()
+    assert list(kt) == list(w.KERNEL_NAMES) and all(v > 0.0 for v in kt.values()), kt
+    w.set_kernel_timing(False)
+    for _ in range(5):
+        w.step(sc.dt)
+        keys, jo = w.solve_order()
+        o.step_ordered(sc.dt, keys, jo)
+    assert w.kernel_times() == {}
+    _assert_states_equal(w.get_bodies(), o.get_bodies(), "kernel timing on / off")
+
+
 def test_region_solver_two_ctas_per_sm(monkeypatch):
     """SYLT_REGION_CTAS_PER_SM=2 (opt-in): two half-size region CTAs per SM — half the threads, half the shared memory, half-size tables
     and bins; same results."""
