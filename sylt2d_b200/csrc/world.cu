@@ -964,6 +964,20 @@ struct BodyIO {
             }
         }
     }
+    // The same records moved as ONE 256-bit access (sm_100; the export planes of k_solve_regions: the fourth word is not used there).  A
+    // 32-byte access need not be single-copy atomic as a whole: every 64-bit word still carries its own copy of the version.
+    __device__ __forceinline__ bool try_get256(int b, unsigned expect, Vel& v) const {
+        unsigned w0, w1, w2, w3, w4, w5, w6, w7;
+        asm volatile("ld.relaxed.gpu.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "l"(vrec + 2 * (size_t)b) : "memory");
+        v.v = mk(__uint_as_float(w0), __uint_as_float(w2));
+        v.w = __uint_as_float(w4);
+        return w1 == expect && w3 == expect && w5 == expect;
+    }
+    __device__ __forceinline__ void put256(int b, const Vel& v, unsigned ver) const {
+        asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"l"(vrec + 2 * (size_t)b), "r"(__float_as_uint(v.v.x)), "r"(ver), "r"(__float_as_uint(v.v.y)), "r"(ver), "r"(__float_as_uint(v.w)), "r"(ver), "r"(0u), "r"(0u) : "memory");
+    }
     __device__ __forceinline__ void put(int b, const Vel& v, unsigned ver) const {
         unsigned long long t = (unsigned long long)ver << 32;
         unsigned long long x = t | __float_as_uint(v.v.x), y = t | __float_as_uint(v.v.y), w = t | __float_as_uint(v.w);
@@ -2148,15 +2162,14 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         for (int k = lt; k < nbnd; k += T) {
             const float4 q = s_body[2 * s_bnd[k]];
             Vel o; o.v = mk(q.x, q.y); o.w = q.z;
-            xio.put(s_bndg[k], o, tag);
+            xio.put256(s_bndg[k], o, tag);
         }
         for (int g = lt; g < ngb; g += T) {
             const int z = s_gb[g];
             if (z & GHOST_FLAG) continue;  // static
             Vel o;
-            float im, ii;
             unsigned spins = 0;
-            while (!xio.try_get(z, tag, true, o, im, ii)) {
+            while (!xio.try_get256(z, tag, o)) {
                 if ((++spins & 0x3ffu) == 0u) {
                     if (*(volatile int*)&cn->err != 0) break;  // a failed step: the owner may never export
                     if (spins > (1u << 23)) { atomicExch(&cn->err, SYLT_ERR_INTERNAL); break; }
