@@ -939,12 +939,14 @@ struct BodyIO {
         return r;
     }
     __device__ __forceinline__ bool try_get(int b, unsigned expect, bool check, Vel& v, float& im, float& ii) const {
-        ulonglong2 lo = ld(vrec + 2 * (size_t)b), hi = ld(vrec + 2 * (size_t)b + 1);
-        v.v = mk(__uint_as_float((unsigned)lo.x), __uint_as_float((unsigned)lo.y));
-        v.w = __uint_as_float((unsigned)hi.x);
-        im = __uint_as_float((unsigned)hi.y);
-        ii = __uint_as_float((unsigned)(hi.y >> 32));
-        return !check || ((unsigned)(lo.x >> 32) == expect && (unsigned)(lo.y >> 32) == expect && (unsigned)(hi.x >> 32) == expect);
+        unsigned w0, w1, w2, w3, w4, w5, w6, w7;  // one 256-bit access (sm_100): a record is 32 bytes; every 64-bit word carries the version
+        asm volatile("ld.relaxed.gpu.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                     : "=r"(w0), "=r"(w1), "=r"(w2), "=r"(w3), "=r"(w4), "=r"(w5), "=r"(w6), "=r"(w7) : "l"(vrec + 2 * (size_t)b) : "memory");
+        v.v = mk(__uint_as_float(w0), __uint_as_float(w2));
+        v.w = __uint_as_float(w4);
+        im = __uint_as_float(w6);
+        ii = __uint_as_float(w7);
+        return !check || (w1 == expect && w3 == expect && w5 == expect);
     }
     __device__ __forceinline__ void get(int b, Vel& v, float& im, float& ii) const { try_get(b, 0u, false, v, im, ii); }
     // wait for both bodies of a constraint (static bodies are read once and never waited for)
@@ -978,11 +980,10 @@ struct BodyIO {
         asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
                      ::"l"(vrec + 2 * (size_t)b), "r"(__float_as_uint(v.v.x)), "r"(ver), "r"(__float_as_uint(v.v.y)), "r"(ver), "r"(__float_as_uint(v.w)), "r"(ver), "r"(0u), "r"(0u) : "memory");
     }
-    __device__ __forceinline__ void put(int b, const Vel& v, unsigned ver) const {
-        unsigned long long t = (unsigned long long)ver << 32;
-        unsigned long long x = t | __float_as_uint(v.v.x), y = t | __float_as_uint(v.v.y), w = t | __float_as_uint(v.w);
-        asm volatile("st.relaxed.gpu.global.v2.b64 [%0], {%1, %2};" ::"l"(vrec + 2 * (size_t)b), "l"(x), "l"(y) : "memory");
-        asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"((unsigned long long*)(vrec + 2 * (size_t)b + 1)), "l"(w) : "memory");
+    __device__ __forceinline__ void put(int b, const Vel& v, unsigned ver, float im, float ii) const {  // (im, ii: the record's fourth word, unchanged)
+        asm volatile("st.relaxed.gpu.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                     ::"l"(vrec + 2 * (size_t)b), "r"(__float_as_uint(v.v.x)), "r"(ver), "r"(__float_as_uint(v.v.y)), "r"(ver), "r"(__float_as_uint(v.w)), "r"(ver),
+                       "r"(__float_as_uint(im)), "r"(__float_as_uint(ii)) : "memory");
     }
 };
 
@@ -1443,8 +1444,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
             v.cb[q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
             v.cc[q] = make_float4(k0.bias, cc.y, cc.z, cc.w);
         }
-        if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1);
-        if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1);
+        if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1, im1, ii1);
+        if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1, im2, ii2);
     };
     auto apply_slot = [&](int c, int i, unsigned pass) {
         SlotView v;
@@ -1463,8 +1464,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
             contact_apply(k0, v.fr, im1, ii1, im2, ii2, acc, pn, pt, v1, v2);
             if (acc) v.cc[q] = make_float4(cc.x, pn, pt, cc.w);
         }
-        if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1);
-        if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1);
+        if (!(v.r1 & VSTATIC)) io.put(b1, v1, e1 + 1, im1, ii1);
+        if (!(v.r2 & VSTATIC)) io.put(b2, v2, e2 + 1, im2, ii2);
     };
     auto joint_expect = [&](int j, int2 b, unsigned pass, unsigned& e1, unsigned& e2) {
         int2 jr = a.jrank[j];
@@ -1523,8 +1524,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                     a.jp[j] = make_float2(pacc.x, pacc.y);
                 }
             }
-            if (!(r1 & VSTATIC)) io.put(b.x, w1, e1 + 1);
-            if (!(r2 & VSTATIC)) io.put(b.y, w2, e2 + 1);
+            if (!(r1 & VSTATIC)) io.put(b.x, w1, e1 + 1, im1, ii1);
+            if (!(r2 & VSTATIC)) io.put(b.y, w2, e2 + 1, im2, ii2);
             }
         }
     }
@@ -1566,8 +1567,8 @@ __global__ void __launch_bounds__(SOLVE_THREADS, 1) k_solve(SolveArgs a) {
                 V2 pacc = mk(pa.x, pa.y);
                 joint_apply(jc, im1, ii1, im2, ii2, pacc, v1, v2);
                 a.jp[j] = make_float2(pacc.x, pacc.y);
-                if (!(r1 & VSTATIC)) io.put(b.x, v1, e1 + 1);
-                if (!(r2 & VSTATIC)) io.put(b.y, v2, e2 + 1);
+                if (!(r1 & VSTATIC)) io.put(b.x, v1, e1 + 1, im1, ii1);
+                if (!(r2 & VSTATIC)) io.put(b.y, v2, e2 + 1, im2, ii2);
                 }
             }
         }
