@@ -322,16 +322,14 @@ __global__ void __launch_bounds__(256) k_fill_cells(int B, const int4* cinfo, co
         const int j = large[i];
         const int4 cj = cinfo[j];
         const int pos = B - n_large + i;
-        cent_info[2 * pos] = make_int4(j, cj.x, cj.y, cj.z);
-        cent_aabb[2 * pos] = aabb[j];
+        st256(&cent_info[2 * pos], make_int4(j, cj.x, cj.y, cj.z), as_i4(aabb[j]));
     }
     if (i >= B) return;
     const int4 ci = cinfo[i];
     if (ci.z & FLAG_LARGE) return;
     const int h = cell_hash(ci.x, ci.y, gp.mask, group_of(ci.z));
     const int pos = s_tp[h / CELL_TILE] + cell_local[h] + rank[i];
-    cent_info[2 * pos] = make_int4(i, ci.x, ci.y, ci.z);  // info and AABB of an entry share one 32-byte sector
-    cent_aabb[2 * pos] = aabb[i];
+    st256(&cent_info[2 * pos], make_int4(i, ci.x, ci.y, ci.z), as_i4(aabb[i]));  // info and AABB of an entry: one 32-byte sector, one request
 }
 
 // Row i = partners body i owns: small-small pairs belong to the lower index, small-large pairs to the small
@@ -433,8 +431,9 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
     float4 my;
     int4 ci;
     if (g < B - n_large_all) {  // the cell-ordered entry already carries the body's index, cell, flags and AABB: one load level less
-        const int4 ce = cent_info[2 * g];
-        my = cent_aabb[2 * g];
+        const Rec32 own = ld256(&cent_info[2 * g]);
+        const int4 ce = own.a;
+        my = as_f4(own.b);
         i = ce.x;
         ci = make_int4(ce.y, ce.z, ce.w, 0);
     } else {
@@ -465,8 +464,9 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
             int partner = 0;
             if (e < n_all) {
                 const int k = e < large_base ? e : large_base + l0 + (e - large_base);
-                const int4 cj = cent_info[2 * k];
-                const float4 ab = cent_aabb[2 * k];
+                const Rec32 ent = ld256(&cent_info[2 * k]);
+                const int4 cj = ent.a;
+                const float4 ab = as_f4(ent.b);
                 const bool mine = e < large_base ? (cj.x > i && group_of(cj.w) == grp) : true;
                 hit = mine && !(st_i && (cj.w & FLAG_STATIC)) && aabb_overlap(my, ab);
                 partner = cj.x;
@@ -531,8 +531,9 @@ __global__ void __launch_bounds__(128) k_rows_count(int B, const float4* aabb, c
             const int off = e - (s_end - s_n);
             {
                 const int k = s_k0 + off;
-                const int4 cj = cent_info[2 * k];
-                const float4 ab = cent_aabb[2 * k];
+                const Rec32 ent = ld256(&cent_info[2 * k]);
+                const int4 cj = ent.a;
+                const float4 ab = as_f4(ent.b);
                 const int scx = x0 + seg % 3, scy = y0 + seg / 3;
                 // a cell entry: the lower index owns the pair, another cell (or group) may share the bucket; an entry of the large list: the
                 // small body owns the pair.  Static-static pairs are skipped (world.rs:79-81).
