@@ -852,7 +852,7 @@ struct SolveArgs {
     float dt, inv_dt;
     unsigned epoch_base;
     int smem_slots, smem_contacts;  // shared-memory residency budget per CTA
-    float4 *pose, *vel, *force;
+    float4 *pose, *vel, *force, *pose_prev;
     const float4* mp;
     const float2* rotc;
     const int* bflags;
@@ -2237,15 +2237,13 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     for (int ls = lt; ls < L; ls += T) {
         const int sc = s_sc[ls], so = s_so[ls];
         if (sc < 0 || (so & GHOST_FLAG)) continue;
-        const int sb = s_sb[ls];
-        const float4 m1 = s_body[2 * (sb & 0x7fff) + 1], m2 = s_body[2 * ((sb >> 16) & 0x7fff) + 1];
+        // Only what the next step reads (the accumulated impulses) and the bias go back: r1, r2, mass_normal, mass_tangent and the
+        // separation are only ever read by sylt_world_get_arbiters, which has k_fill_contacts recompute them — the same
+        // contact_constants() on the same inputs (cin, the poses from before the integration, the masses) gives the same bits.
         const int coff = so, lc = sc >> 8, n = sc & 0xff;
         for (int q = 0; q < n; q++) {
-            const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
-            const V2 r1 = mk(c0.x, c0.y) - mk(m1.x, m1.y), r2 = mk(c0.x, c0.y) - mk(m2.x, m2.y);
-            a.cur.ca[coff + q] = make_float4(c0.z, c0.w, r1.x, r1.y);
-            a.cur.cb[coff + q] = make_float4(r2.x, r2.y, c1.x, c1.y);
-            a.cur.cc[coff + q] = make_float4(c1.z, c1.w, s_c2[lc + q], 0.0f);  // (the separation stays in cin: k_fill_sep, on demand)
+            const float4 c1 = s_c1[lc + q];
+            a.cur.cc[coff + q] = make_float4(c1.z, c1.w, s_c2[lc + q], 0.0f);
         }
     }
 
@@ -2256,6 +2254,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         const float4 q = s_body[2 * lb];
         a.vel[b] = make_float4(q.x, q.y, q.z, 0.0f);
         float4 p = a.pose[b];
+        a.pose_prev[b] = p;  // (for k_fill_contacts)
         V2 np = mk(p.x, p.y) + mk(q.x, q.y) * a.dt;
         p.x = np.x; p.y = np.y;
         p.z += q.z * a.dt;
@@ -2525,10 +2524,22 @@ __global__ void __launch_bounds__(RECUT_THREADS, 1) k_recut(int B, int G, const 
 }
 
 // the flags a step used become the "old" flags of the next one — unless the step failed (it will be repeated)
-// separations of a set the region solver wrote back (it does not carry them through the solve): cin -> cc.w, when somebody asks
-__global__ void k_fill_sep(int n, const float4* cin, float4* cc) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) cc[i].w = cin[2 * (size_t)i + 1].x;
+// The solve fields of a set the region solver wrote back that nothing on the device reads again — r1, r2, mass_normal, mass_tangent
+// (arbiter.rs:192-215) and the separation — when somebody asks for the arbiters: contact_constants() on what the step itself used.
+__global__ void k_fill_contacts(int A, const int2* bodies, const int2* meta, const float4* cin, const float4* pose_prev, const float4* mp,
+                                float inv_dt, float kbias, float4* ca, float4* cb, float4* cc) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= A) return;
+    const int2 b = bodies[e], mt = meta[e];
+    const float4 p1 = pose_prev[b.x], p2 = pose_prev[b.y], m1 = mp[b.x], m2 = mp[b.y];
+    for (int q = 0; q < mt.x; q++) {
+        const float4 x0 = cin[2 * (size_t)(mt.y + q)], x1 = cin[2 * (size_t)(mt.y + q) + 1];
+        ContactConst k0;
+        contact_constants(mk(x0.x, x0.y), mk(x0.z, x0.w), x1.x, mk(p1.x, p1.y), mk(p2.x, p2.y), m1.x, m1.y, m2.x, m2.y, inv_dt, kbias, k0);
+        ca[mt.y + q] = make_float4(x0.z, x0.w, k0.r1.x, k0.r1.y);
+        cb[mt.y + q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
+        cc[mt.y + q].w = x1.x;
+    }
 }
 
 // SyltBodyState records (x, y, rotation, vx, vy, angular_velocity, fx, fy, torque) for sylt_world_get_bodies
@@ -2618,7 +2629,7 @@ struct SyltWorld {
     int buckets = 1024;
 
     // device state
-    DBuf<float4> pose, vel, force, mp, geom, aabb;
+    DBuf<float4> pose, vel, force, mp, geom, aabb, pose_prev;  // pose_prev: the poses the last region-solver step solved with
     DBuf<float2> rotc, lverts;
     DBuf<int> bflags, bflags_old, rank, cell_count, cell_start, cell_local, tile_tot, large, large_start, row_count, row_start, row_tmp;
     int n_groups = 1;        // collision groups in use (SyltBodyDesc.group)
@@ -2647,7 +2658,8 @@ struct SyltWorld {
         DBuf<int> partner, color, row_start;
         DBuf<float> friction;
         DBuf<float4> ca, cb, cc, cd, cin;
-        bool sep_in_cin = false;  // the set was solved by the region solver: cc.w (separation) is filled in from cin on demand
+        bool sep_in_cin = false;  // the set was solved by the region solver: r1, r2, masses and the separation are filled in on demand
+        float lazy_inv_dt = 0.0f, lazy_kbias = 0.0f;
     } arb[2];
     int cur = 0;             // index being built next
     bool have_old = false;   // an arbiter set from a previous step/broad phase exists
@@ -2783,6 +2795,7 @@ int flush(SyltWorld* w) {
         SYLT_CUDA(w->pose.ensure(B, keep, w->stream));
         SYLT_CUDA(w->vel.ensure(B, keep, w->stream));
         SYLT_CUDA(w->force.ensure(B, keep, w->stream));
+        SYLT_CUDA(w->pose_prev.ensure(B, keep, w->stream));
         SYLT_CUDA(w->mp.ensure(B, keep, w->stream));
         SYLT_CUDA(w->geom.ensure(B, keep, w->stream));
         SYLT_CUDA(w->bflags_old.ensure(B, keep, w->stream));
@@ -3119,7 +3132,7 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         SYLT_CUDA(cudaMemsetAsync(w->claim.p, 0xff, w->claim.cap * sizeof(unsigned long long), st));
         w->epoch = 1;
     }
-    a.pose = w->pose.p; a.vel = w->vel.p; a.force = w->force.p; a.mp = w->mp.p; a.rotc = w->rotc.p; a.bflags = w->bflags.p;
+    a.pose = w->pose.p; a.vel = w->vel.p; a.force = w->force.p; a.pose_prev = w->pose_prev.p; a.mp = w->mp.p; a.rotc = w->rotc.p; a.bflags = w->bflags.p;
     a.cur = cur; a.used = w->used.p; a.used_int = w->used_int.p; a.claim = w->claim.p; a.uncolored = w->uncolored.p; a.uncolored2 = w->uncolored2.p; a.unc_rec = w->unc_rec.p; a.prop = w->prop.p; a.order = w->order.p;
     a.jbodies = w->jbodies.p; a.jla = w->jla.p; a.jparam = w->jparam.p; a.jp = w->jp.p; a.jr = w->jr.p; a.jm = w->jm.p; a.jbias = w->jbias.p;
     a.jorder = w->jorder.p; a.jcolor_start = w->jcolor_start.p;
@@ -3143,6 +3156,8 @@ int enqueue_step(SyltWorld* w, float dt, bool full_step) {
         SYLT_CUDA(cudaLaunchCooperativeKernel(w->regions_per_sm == 2 ? (void*)k_solve_regions<2> : (void*)k_solve_regions<1>, dim3((unsigned)w->regions_blocks),
                                               dim3((unsigned)w->regions_threads), args, w->solve_budget, st));
         w->arb[w->cur].sep_in_cin = full_step;
+        w->arb[w->cur].lazy_inv_dt = a.inv_dt;
+        w->arb[w->cur].lazy_kbias = a.poscorr ? 0.2f : 0.0f;
         w->steps_since_part++;
         w->last_regions = true;
     } else {
@@ -3358,6 +3373,21 @@ int prepare_call(SyltWorld* w) {
     return SYLT_OK;
 }
 
+// r1 / r2 / masses / separation of the last completed arbiter set, if the region solver left them to be computed on demand.  Must run
+// before anything they are computed from changes (the masses: sylt_world_set_body_props).
+int materialise_arbiters(SyltWorld* w) {
+    SyltWorld::ArbBufs& ab = w->arb[w->cur ^ 1];
+    if (!ab.sep_in_cin) return SYLT_OK;
+    ab.sep_in_cin = false;
+    const int A = w->have_last ? (int)std::min<int64_t>(w->n_arb_valid, w->cap_arb) : 0;
+    if (A <= 0) return SYLT_OK;
+    SYLT_CUDA(cudaSetDevice(w->device));
+    k_fill_contacts<<<(A + 127) / 128, 128, 0, w->stream>>>(A, ab.bodies.p, ab.meta.p, ab.cin.p, w->pose_prev.p, w->mp.p, ab.lazy_inv_dt, ab.lazy_kbias,
+                                                             ab.ca.p, ab.cb.p, ab.cc.p);
+    SYLT_CUDA(cudaGetLastError());
+    return SYLT_OK;
+}
+
 int do_steps(SyltWorld* w, float dt, int n, bool full, bool wait) {
     if (!w) return SYLT_ERR_INVALID;
     int e = prepare_call(w);
@@ -3458,7 +3488,7 @@ static void free_all(SyltWorld* w) {
     if (w->rb_host) { cudaFreeHost(w->rb_host); w->rb_host = nullptr; w->rb_cap = 0; }
     if (w->sb_host) { cudaFreeHost(w->sb_host); w->sb_host = nullptr; w->sb_cap = 0; }
     w->pack_dev.release();
-    w->pose.release(); w->vel.release(); w->force.release(); w->mp.release(); w->geom.release(); w->aabb.release();
+    w->pose.release(); w->vel.release(); w->force.release(); w->pose_prev.release(); w->mp.release(); w->geom.release(); w->aabb.release();
     w->rotc.release(); w->lverts.release(); w->bflags.release(); w->bflags_old.release(); w->rank.release();
     w->cell_count.release(); w->cell_start.release(); w->cell_local.release(); w->tile_tot.release(); w->cent_info.release(); w->large.release(); w->row_count.release();
     w->row_start.release(); w->row_tmp.release(); w->large_start.release(); w->row_btot.release(); w->pair_btot.release(); w->cinfo.release(); w->pairs.release(); w->info.release(); w->pscan.release(); w->claim.release();
@@ -3655,6 +3685,7 @@ int sylt_world_set_body_props(SyltWorld* w, int32_t first, int32_t count, const 
     if (count == 0) return SYLT_OK;
     int e = flush(w);  // (drains the queue, uploads pending bodies)
     if (e) return e;
+    if ((e = materialise_arbiters(w))) return e;  // (computed from the masses the last step used)
     std::vector<float4> hm((size_t)count), hg((size_t)count);
     for (int k = 0; k < count; k++) {
         HostBody& b = w->hb[(size_t)(first + k)];
@@ -3769,10 +3800,7 @@ int sylt_world_get_arbiters(SyltWorld* w, SyltArbiterInfo* arbiters, int32_t arb
     if (A == 0) return 0;
     if (cudaSetDevice(w->device) != cudaSuccess) return -SYLT_ERR_CUDA;
     SyltWorld::ArbBufs& ab = w->arb[w->cur ^ 1];  // last completed step
-    if (ab.sep_in_cin && Cn > 0) {
-        k_fill_sep<<<(Cn + 255) / 256, 256, 0, w->stream>>>(Cn, ab.cin.p, ab.cc.p);
-        ab.sep_in_cin = false;
-    }
+    if (materialise_arbiters(w)) return -SYLT_ERR_CUDA;
     // one pinned staging area (kept and grown by the handle: no page faults, DMA at link speed), the eight arrays behind one another
     const size_t bytes = (size_t)A * (2 * sizeof(int2) + sizeof(float) + sizeof(int)) + (size_t)Cn * 4 * sizeof(float4) + 8 * 16;
     if (bytes > w->rb_cap) {
