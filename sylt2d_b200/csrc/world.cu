@@ -1932,7 +1932,7 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     int* s_so = (int*)(s_sf + L);                         //       first contact in the global arrays
     float4* s_c0 = (float4*)(((size_t)(s_so + L) + 15) & ~(size_t)15);  // contact: (position, normal)
     const int CONCAP = bad ? 0 : (int)(((sm_raw + a.smem_bytes - (unsigned char*)s_c0) / 36) & ~(size_t)3);
-    float4* s_c1 = s_c0 + CONCAP;                         //          (mass_normal, mass_tangent, bias, pn); before pre_step: (-, -, separation, pn)
+    float4* s_c1 = s_c0 + CONCAP;                         //          (mass_normal, mass_tangent, bias, pn)
     float* s_c2 = (float*)(s_c1 + CONCAP);                //          pt
     for (int g = lt; g < ngb && !bad; g += T) {  // ghosts: positions, inverse masses (and, for static ones, the velocity) once; dynamic velocities arrive every pass
         const int zf = t_gb[g], z = zf & ~GHOST_FLAG;
@@ -2011,19 +2011,21 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
         for (int v = 0; v < 2; v++) {
             if (sc[v] < 0) continue;
             const int lc = sc[v] >> 8, n = sc[v] & 0xff;
+            // the velocity-independent half of Arbiter::pre_step (arbiter.rs:192-215) right here: this loop waits for memory, not for arithmetic
+            const int sb = s_sb[ls0 + v * T];
+            const float4 m1 = s_body[2 * (sb & 0x7fff) + 1], m2 = s_body[2 * ((sb >> 16) & 0x7fff) + 1];
+            auto put_contact = [&](int l, const float4 x0, const float4 x1) {  // x0 = (position, normal), x1 = (separation, pn, pt, -)
+                ContactConst k0;
+                contact_constants(mk(x0.x, x0.y), mk(x0.z, x0.w), x1.x, mk(m1.x, m1.y), mk(m2.x, m2.y), m1.z, m1.w, m2.z, m2.w, a.inv_dt, kbias, k0);
+                s_c0[l] = x0;
+                s_c1[l] = make_float4(k0.mass_n, k0.mass_t, k0.bias, x1.y);
+                s_c2[l] = x1.z;
+            };
 #pragma unroll
             for (int q = 0; q < 2; q++)
-                if (q < n) {
-                    s_c0[lc + q] = ci[v][q][0];
-                    s_c1[lc + q] = make_float4(0.0f, 0.0f, ci[v][q][1].x, ci[v][q][1].y);
-                    s_c2[lc + q] = ci[v][q][1].z;
-                }
-            for (int q = 2; q < n; q++) {  // (polygon manifolds)
-                const float4 x0 = a.cur.cin[2 * (size_t)(co[v] + q)], x1 = a.cur.cin[2 * (size_t)(co[v] + q) + 1];
-                s_c0[lc + q] = x0;
-                s_c1[lc + q] = make_float4(0.0f, 0.0f, x1.x, x1.y);
-                s_c2[lc + q] = x1.z;
-            }
+                if (q < n) put_contact(lc + q, ci[v][q][0], ci[v][q][1]);
+            for (int q = 2; q < n; q++)  // (polygon manifolds)
+                put_contact(lc + q, a.cur.cin[2 * (size_t)(co[v] + q)], a.cur.cin[2 * (size_t)(co[v] + q) + 1]);
         }
     }
     tstamp();
@@ -2096,9 +2098,9 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
                 const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
                 const float pt0 = s_c2[lc + q];
                 ContactConst k0;
-                if (pass == 0u) {
-                    contact_prestep(mk(c0.x, c0.y), mk(c0.z, c0.w), c1.z, p1, p2, im1, ii1, im2, ii2, a.inv_dt, kbias, acc, c1.w, pt0, v1, v2, k0);
-                    s_c1[lc + q] = make_float4(k0.mass_n, k0.mass_t, k0.bias, c1.w);
+                if (pass == 0u) {  // the ordered half of Arbiter::pre_step (arbiter.rs:216-223); the constants were computed with the set-up
+                    k0.n = mk(c0.z, c0.w); k0.r1 = mk(c0.x, c0.y) - p1; k0.r2 = mk(c0.x, c0.y) - p2;
+                    if (acc) contact_warmstart(k0, im1, ii1, im2, ii2, c1.w, pt0, v1, v2);
                 } else {
                     k0.n = mk(c0.z, c0.w); k0.r1 = mk(c0.x, c0.y) - p1; k0.r2 = mk(c0.x, c0.y) - p2;
                     k0.mass_n = c1.x; k0.mass_t = c1.y; k0.bias = c1.z;
@@ -2189,32 +2191,22 @@ __global__ void __launch_bounds__(SOLVE_THREADS / PER_SM, PER_SM) k_solve_region
     // ---- 4. pass 0: Arbiter::pre_step (arbiter.rs:182-228).  Its ordered half is the warm start (:216-223); without accumulation there is
     //         none, and with every accumulated impulse zero (warm starting off: k_build zeroes them) it subtracts +-0 from every
     //         velocity — which changes nothing unless a velocity is exactly -0.0 (k_prepare looks).  Then the pre-step is just the
-    //         constants of every contact (:192-215): one flat loop over the slots, no colour hops, no hand-off.  (With warm starting on,
-    //         constants and warm start in ONE ordered sweep measured faster than the flat loop plus an ordered warm start.)
+    //         constants of every contact (:192-215), and those were computed while the contacts were loaded: no colour hops, no hand-off.
     const bool flat_prestep = !acc || (!a.warm && *(volatile unsigned*)&cn->neg_zero_tag != a.step_serial);  // grid-uniform
     if (flat_prestep) {
-        for (int ls = lt; ls < L; ls += T) {
-            const int sb = s_sb[ls], sc = s_sc[ls];
+        for (int ls = lt; ls < L; ls += T) {  // (only the own slots beyond the shared-memory budget are left: the global arrays are their storage)
+            const int sc = s_sc[ls];
+            if (sc >= 0 || (s_so[ls] & GHOST_FLAG)) continue;
+            const int sb = s_sb[ls];
             const float4 m1 = s_body[2 * (sb & 0x7fff) + 1], m2 = s_body[2 * ((sb >> 16) & 0x7fff) + 1];
-            const V2 p1 = mk(m1.x, m1.y), p2 = mk(m2.x, m2.y);
-            if (sc >= 0) {
-                const int lc = sc >> 8, n = sc & 0xff;
-                for (int q = 0; q < n; q++) {
-                    const float4 c0 = s_c0[lc + q], c1 = s_c1[lc + q];
-                    ContactConst k0;
-                    contact_constants(mk(c0.x, c0.y), mk(c0.z, c0.w), c1.z, p1, p2, m1.z, m1.w, m2.z, m2.w, a.inv_dt, kbias, k0);
-                    s_c1[lc + q] = make_float4(k0.mass_n, k0.mass_t, k0.bias, c1.w);
-                }
-            } else if (!(s_so[ls] & GHOST_FLAG)) {  // (an own slot beyond the shared-memory budget: the global arrays are its storage)
-                const int n = -1 - sc, coff = s_so[ls];
-                for (int q = 0; q < n; q++) {
-                    const float4 x0 = a.cur.cin[2 * (size_t)(coff + q)], x1 = a.cur.cin[2 * (size_t)(coff + q) + 1];
-                    ContactConst k0;
-                    contact_constants(mk(x0.x, x0.y), mk(x0.z, x0.w), x1.x, p1, p2, m1.z, m1.w, m2.z, m2.w, a.inv_dt, kbias, k0);
-                    a.cur.ca[coff + q] = make_float4(x0.z, x0.w, k0.r1.x, k0.r1.y);
-                    a.cur.cb[coff + q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
-                    a.cur.cc[coff + q] = make_float4(k0.bias, x1.y, x1.z, x1.x);
-                }
+            const int n = -1 - sc, coff = s_so[ls];
+            for (int q = 0; q < n; q++) {
+                const float4 x0 = a.cur.cin[2 * (size_t)(coff + q)], x1 = a.cur.cin[2 * (size_t)(coff + q) + 1];
+                ContactConst k0;
+                contact_constants(mk(x0.x, x0.y), mk(x0.z, x0.w), x1.x, mk(m1.x, m1.y), mk(m2.x, m2.y), m1.z, m1.w, m2.z, m2.w, a.inv_dt, kbias, k0);
+                a.cur.ca[coff + q] = make_float4(x0.z, x0.w, k0.r1.x, k0.r1.y);
+                a.cur.cb[coff + q] = make_float4(k0.r2.x, k0.r2.y, k0.mass_n, k0.mass_t);
+                a.cur.cc[coff + q] = make_float4(k0.bias, x1.y, x1.z, x1.x);
             }
         }
         __syncthreads();
