@@ -660,7 +660,7 @@ __global__ void __launch_bounds__(128) k_narrow(const Counters* cn, int cap_pair
 struct ArbSet {
     int2* bodies;      // (body1, body2), body1 < body2
     int2* meta;        // (num_contacts, contact_offset)
-    int* partner;      // partner index in the owner's row (lookup key for the next step)
+    int2* partner;     // (partner index in the owner's row: the lookup key of the next step, first contact)
     float* friction;
     int* color;
     int* row_start;    // per body: first arbiter of its row (B+1 entries)
@@ -723,19 +723,21 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         int b1 = min(pr.x, pr.y), b2 = max(pr.x, pr.y);
         float4 m1 = mp[b1], m2 = mp[b2];
         // ---- Arbiter::update / insert (world.rs:85-98): look the pair up in last step's arbiters
-        int found = -1;
+        int found = -1, found_con = 0;  // last step's arbiter of the pair and its first contact (carried in the row entry: one dependent level less)
         if (have_old && b2 < B_old) {
             int oo, op;
             pair_owner(b1, b2, bflags_old[b1], bflags_old[b2], &oo, &op);
             const int lo = old.row_start[oo], hi = old.row_start[oo + 1];
-            int part[8];  // rows are short: fetch the partners side by side (independent loads), then compare
+            int2 part[8];  // rows are short: fetch the entries side by side (independent loads), then compare
 #pragma unroll
-            for (int k = 0; k < 8; k++) part[k] = lo + k < hi ? old.partner[lo + k] : -1;
+            for (int k = 0; k < 8; k++) part[k] = lo + k < hi ? old.partner[lo + k] : make_int2(-1, 0);
 #pragma unroll
             for (int k = 7; k >= 0; k--)
-                if (part[k] == op) found = lo + k;
-            for (int k = lo + 8; k < hi && found < 0; k++)
-                if (old.partner[k] == op) found = k;
+                if (part[k].x == op) { found = lo + k; found_con = part[k].y; }
+            for (int k = lo + 8; k < hi && found < 0; k++) {
+                const int2 pe = old.partner[k];
+                if (pe.x == op) { found = k; found_con = pe.y; }
+            }
         }
         float fr, pn = 0.0f, pt = 0.0f, pnb = 0.0f;
         int color = -1;
@@ -752,7 +754,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
             // of its bodies is made static or dynamic between steps (set_body_props).
             if (regions && color >= 0 && (color < GEN_BIT) != interior_pair) color = -1;
             if (warm) {                // quirk Q-2: every new contact inherits old contact 0
-                int oc = old.meta[found].y;
+                const int oc = found_con;
                 float4 c = old.cc[oc];
                 pn = c.y; pt = c.z; pnb = old.cd[oc].z;
             }
@@ -761,7 +763,7 @@ __global__ void __launch_bounds__(256) k_build(Counters* cn, int cap_pairs, int 
         }
         cur.bodies[a] = make_int2(b1, b2);
         cur.meta[a] = make_int2(n, coff);
-        cur.partner[a] = pr.y;
+        cur.partner[a] = make_int2(pr.y, coff);
         cur.friction[a] = fr;
         cur.color[a] = color;
         if (regions) {  // everything the region solver's set-up needs to know about the arbiter, in one 32-byte record
@@ -2647,7 +2649,8 @@ struct SyltWorld {
     // arbiters, double buffered
     struct ArbBufs {
         DBuf<int2> bodies, meta;
-        DBuf<int> partner, color, row_start;
+        DBuf<int2> partner;
+        DBuf<int> color, row_start;
         DBuf<float> friction;
         DBuf<float4> ca, cb, cc, cd, cin;
         bool sep_in_cin = false;  // the set was solved by the region solver: r1, r2, masses and the separation are filled in on demand
